@@ -1,0 +1,10 @@
+"""cal_b200 -- B200-native (sm_100a) implementation of the CAL hot path.
+
+CausalGCN / CausalGAT forward + backward over batched mini-graphs as
+hand-written CUDA kernels behind a C-ABI library (``include/cal_b200.h``),
+wrapped in ``nn.Module``s that keep the reference constructor / forward
+signature (model.py:14-22,85 and model.py:316-320,380 upstream).
+"""
+__version__ = "0.1.0"
+
+from .data import Batch, Data, DataLoader, make_batches, make_dataset  # noqa: F401
