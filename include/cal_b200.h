@@ -1,0 +1,196 @@
+/*
+ * cal_b200.h -- C ABI of the B200-native CAL hot path (libcal_b200.so).
+ *
+ * Drop-in boundary for the CausalGCN / CausalGAT forward + backward of
+ * yongduosui/CAL.  Every entry point names the reference interface it
+ * replaces (file:line relative to the upstream repo).  Plain pointers and
+ * sizes only: no torch types, no C++ types, no exceptions.
+ *
+ * Conventions
+ *  - All data pointers are DEVICE pointers, 16-byte aligned, contiguous
+ *    row-major.  The library never allocates, frees or retains them.
+ *  - `stream` is a cudaStream_t passed as void*.  Calls are asynchronous
+ *    w.r.t. the host, never synchronise, and are CUDA-graph capturable.
+ *  - Return value: 0 = ok, < 0 = CAL_E* argument error (checked on the host
+ *    before any launch), > 0 = cudaError_t of a failed launch.
+ *  - Batch sizes live in DEVICE memory (`dims`: int32[4] = {N nodes,
+ *    E edge_index columns, B graphs, 0}) so that one captured CUDA graph
+ *    serves every batch that fits the capacities in `cal_caps`.
+ *  - Data-dependent violations (node id out of range, `batch` not sorted)
+ *    are reported through the int32 status word at workspace region
+ *    CAL_WS_STATUS (0 = ok), not through the return value.
+ */
+#ifndef CAL_B200_H
+#define CAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAL_ABI_VERSION 1
+#define CAL_MAX_LAYERS 8
+#define CAL_MAX_BN (1 + CAL_MAX_LAYERS + 2 + 6)
+
+/* error codes */
+#define CAL_OK 0
+#define CAL_EINVAL (-1)      /* bad scalar argument / unsupported shape */
+#define CAL_ENULL (-2)       /* required pointer is NULL */
+#define CAL_EALIGN (-3)      /* pointer not 16-byte aligned */
+#define CAL_ECAPACITY (-4)   /* workspace too small for the capacities */
+#define CAL_EUNSUPPORTED (-5)
+
+/* model kind */
+#define CAL_MODEL_GCN 0      /* CausalGCN, model.py:12-164 */
+#define CAL_MODEL_GAT 1      /* CausalGAT, model.py:315-450 */
+
+/* Model hyper-parameters: the `args` fields the reference models read
+ * (model.py:24-37,65-77; opts.py:32-52) plus the loss weights of
+ * train_causal.py:183 (opts.py:43-45). */
+typedef struct {
+  int32_t model;               /* CAL_MODEL_* */
+  int32_t num_features;        /* F */
+  int32_t hidden;              /* H: multiple of 32, 32..256 */
+  int32_t num_classes;         /* C: 2..32 */
+  int32_t layers;              /* L: 1..CAL_MAX_LAYERS */
+  int32_t heads;               /* GAT heads (model.py:319), H % heads == 0 */
+  int32_t cat;                 /* args.cat_or_add == "cat" (model.py:65-75) */
+  int32_t without_node_attention; /* model.py:106-107 */
+  int32_t without_edge_attention; /* model.py:99-100 */
+  float gat_dropout;           /* model.py:320,340 */
+  float bn_eps;                /* 1e-5 */
+  float bn_momentum;           /* 0.1 */
+  float w_c, w_o, w_co;        /* loss weights args.c / args.o / args.co */
+} cal_model_desc;
+
+/* Capacities a workspace is sized for. */
+typedef struct {
+  int32_t max_nodes;
+  int32_t max_edges;           /* edge_index columns before self-loop surgery */
+  int32_t max_graphs;
+  int32_t reserved;
+} cal_caps;
+
+/* Offsets (in floats) of every parameter inside the flat parameter buffer;
+ * the flat gradient buffer uses the same offsets.  Names follow the
+ * reference state_dict (model.py:38-75, gcn_conv.py:30-35).  Index 0/1/2 of
+ * the fc* arrays = the c / o / co readout (model.py:55-75). -1 = absent. */
+typedef struct {
+  int64_t bn_feat_w, bn_feat_b;
+  int64_t conv_feat_w, conv_feat_b;
+  int64_t bns_conv_w[CAL_MAX_LAYERS], bns_conv_b[CAL_MAX_LAYERS];
+  int64_t convs_w[CAL_MAX_LAYERS], convs_b[CAL_MAX_LAYERS], convs_att[CAL_MAX_LAYERS];
+  int64_t edge_att_w, edge_att_b, node_att_w, node_att_b;
+  int64_t bnc_w, bnc_b, bno_w, bno_b;
+  int64_t context_w, context_b, objects_w, objects_b;
+  int64_t fc1_bn_w[3], fc1_bn_b[3], fc1_w[3], fc1_b[3];
+  int64_t fc2_bn_w[3], fc2_bn_b[3], fc2_w[3], fc2_b[3];
+  int64_t total;               /* number of floats in the flat buffer */
+} cal_param_offsets;
+
+/* BatchNorm running statistics (torch BatchNorm1d buffers).  BN ids:
+ * 0 = bn_feat, 1..L = bns_conv[i], L+1 = bnc, L+2 = bno,
+ * L+3+h = fc1_bn_{c,o,co}, L+6+h = fc2_bn_{c,o,co}. */
+typedef struct {
+  int64_t running_mean[CAL_MAX_BN];   /* offsets in floats into bn_buffers */
+  int64_t running_var[CAL_MAX_BN];
+} cal_bn_offsets;
+
+/* One mini-batch (PyG Batch fields read at model.py:87-89 and
+ * train_causal.py:176), all device pointers. */
+typedef struct {
+  const int32_t* dims;         /* int32[4] = {N, E, B, 0} */
+  const float* feat;           /* f32[N,F]  data.x / data.feat */
+  const int64_t* edge_index;   /* i64[2,E]  row 0 = source, row 1 = target; rows are E apart */
+  const int64_t* batch;        /* i64[N]    non-decreasing graph id */
+  const int64_t* y;            /* i64[B]    labels (may be NULL for forward-only) */
+  const int32_t* perm;         /* i32[B]    random_idx of model.py:152 (NULL = identity) */
+  const float* gat_keep;       /* f32[L,E+N,heads] GAT dropout keep-mask scaled 1/(1-p), or NULL */
+  int64_t edge_stride;         /* elements between edge_index[0,0] and edge_index[1,0] */
+} cal_batch;
+
+/* Named workspace regions (for tests / debugging / saved activations). */
+enum cal_ws_region {
+  CAL_WS_STATUS = 0,   /* int32[4]: [0] = status bits */
+  CAL_WS_IN_PTR, CAL_WS_IN_SRC, CAL_WS_IN_EID, CAL_WS_OUT_PTR, CAL_WS_OUT_DST, CAL_WS_OUT_EID,
+  CAL_WS_GRAPH_PTR, CAL_WS_NORM_IN, CAL_WS_NORM_OUT,
+  CAL_WS_X,            /* f32[L+1][maxN][H]: x_1 .. x_{L+1} */
+  CAL_WS_T,            /* f32[2][maxN][H]: transformed features (t_c, t_o kept for backward) */
+  CAL_WS_XCO,          /* f32[2][maxN][H]: relu(context/objects conv) */
+  CAL_WS_NODE_ATT,     /* f32[maxN][2] */
+  CAL_WS_EDGE_ATT,     /* f32[maxE][2] */
+  CAL_WS_WNORM_IN,     /* f32[2][maxE+maxN] */
+  CAL_WS_POOLED,       /* f32[3][maxB][2H]: xc_g, xo_g, mix */
+  CAL_WS_LOGP,         /* f32[3][maxB][C]: the three outputs (log-probabilities) */
+  CAL_WS_LOSS,         /* f32[8]: loss, c_loss, o_loss, co_loss, correct_o, correct_c, correct_co, 0 */
+  CAL_WS_BN_AFFINE,    /* f32[CAL_MAX_BN][4][256]: scale, shift, mean, rstd per BN */
+  CAL_WS_REGION_COUNT
+};
+
+/* flags for cal_causal_forward */
+#define CAL_F_TRAIN 1        /* BatchNorm batch statistics + running-stat update; GAT dropout */
+#define CAL_F_LOSS 2         /* also evaluate train_causal.py:178-186 (needs batch.y) */
+
+int cal_abi_version(void);
+const char* cal_error_string(int code);
+
+/* Size in bytes of the workspace for a model at given capacities; the offset /
+ * size of one named region inside it (returns CAL_EINVAL for unknown ids). */
+size_t cal_workspace_bytes(const cal_model_desc* m, const cal_caps* caps);
+int cal_workspace_region(const cal_model_desc* m, const cal_caps* caps, int region,
+                         size_t* offset_bytes, size_t* size_bytes);
+
+/* Structure preparation, once per batch (replaces the per-layer work of
+ * GCNConv.norm, gcn_conv.py:44-70, and the implicit graph segmentation of
+ * global_add_pool, model.py:115): int64 -> int32, self-loop removal, one
+ * appended self loop per node, stable CSR by target and by source, the
+ * unweighted symmetric normalisation, graph_ptr.  Zeroes the status word. */
+int cal_prep(const cal_model_desc* m, const cal_caps* caps, const cal_batch* b,
+             void* workspace, size_t ws_bytes, void* stream);
+
+/* CausalGCN.forward / CausalGAT.forward (model.py:85-122 / 380-409).  Requires
+ * cal_prep on the same workspace.  Outputs land in CAL_WS_LOGP (and are copied
+ * to `out_logp` f32[3][B][C] if non-NULL).  With CAL_F_LOSS the loss parts and
+ * correct counts land in CAL_WS_LOSS.  With CAL_F_TRAIN the activations needed
+ * by cal_causal_backward stay in the workspace. */
+int cal_causal_forward(const cal_model_desc* m, const cal_caps* caps, const cal_param_offsets* po,
+                       const cal_bn_offsets* bo, const float* params, float* bn_buffers,
+                       int64_t* bn_num_batches_tracked, const cal_batch* b, int flags,
+                       float* out_logp, void* workspace, size_t ws_bytes, void* stream);
+
+/* Backward of the above (autograd of loss.backward(), train_causal.py:187).
+ * `grad_logp` f32[3][B][C] = dL/d(outputs); NULL means "use the loss evaluated
+ * by the forward with CAL_F_LOSS".  Writes (not accumulates) every parameter
+ * gradient into `grads` (flat, same offsets as params). */
+int cal_causal_backward(const cal_model_desc* m, const cal_caps* caps, const cal_param_offsets* po,
+                        const float* params, const cal_batch* b, const float* grad_logp,
+                        float* grads, void* workspace, size_t ws_bytes, void* stream);
+
+/* torch.optim.Adam step on a flat buffer (train_causal.py:21,192):
+ * m,v moments; `step` is the 1-based step count held on the device;
+ * grad_scale multiplies the gradient first (1/world_size after all-reduce). */
+int cal_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                  int64_t n, const int32_t* step, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, float grad_scale, void* stream);
+int cal_adam_tick(int32_t* step, void* stream);   /* ++*step on the device */
+
+/* ---- operator-level entry points (used by the unit parity tests) ---- */
+
+/* GCNConv.forward, gcn_conv.py:72-104, on prepared structure:
+ * out = [relu]( sum_{e: col_e = i} norm_e * (x W)[row_e] + bias ).
+ * `edge_weight` f32[E] (may be NULL = unweighted) follows gcn_conv.py:44-70. */
+int cal_gcn_conv_forward(const cal_model_desc* m, const cal_caps* caps, const cal_batch* b,
+                         const float* x, int in_channels, const float* weight, const float* bias,
+                         const float* edge_weight, int relu, float* out,
+                         void* workspace, size_t ws_bytes, void* stream);
+
+/* global_add_pool, model.py:115-116: out[b] = sum_{batch_n = b} x[n]. */
+int cal_global_add_pool(const cal_model_desc* m, const cal_caps* caps, const cal_batch* b,
+                        const float* x, float* out, void* workspace, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAL_B200_H */
