@@ -93,46 +93,6 @@ __device__ __forceinline__ float dot_lane(const RowVec<VEC>& a, const RowVec<VEC
   return s;
 }
 
-// ---------------------------------------------------------------------------------------------
-// BatchNorm bookkeeping.  One record per BatchNorm1d of the model.
-// ---------------------------------------------------------------------------------------------
-struct BnRec {
-  float* scale;          // [K] y = x*scale + shift   (scale = gamma*rstd, shift = beta - mean*scale)
-  float* shift;
-  float* mean;           // [K] saved for backward
-  float* rstd;
-  const float* gamma;    // parameters
-  const float* beta;
-  float* running_mean;   // torch buffers (may be null)
-  float* running_var;
-  long long* nbt;        // num_batches_tracked (may be null)
-  float eps, momentum;
-};
-
-// Finalise training-mode statistics of channel k from double sums over `count` rows
-// (torch BatchNorm1d semantics, SURVEY 8/a15: biased var to normalise, unbiased for running).
-__device__ __forceinline__ void bn_finalize_channel(const BnRec& r, int k, double s, double q, int count) {
-  double mean = 0.0, var = 0.0;
-  if (count > 0) {
-    mean = s / count;
-    var = q / count - mean * mean;
-    if (var < 0.0) var = 0.0;
-  }
-  float rstd = (float)(1.0 / sqrt(var + (double)r.eps));
-  float g = r.gamma[k], b = r.beta[k];
-  float sc = g * rstd;
-  r.scale[k] = sc;
-  r.shift[k] = b - (float)mean * sc;
-  r.mean[k] = (float)mean;
-  r.rstd[k] = rstd;
-  if (r.running_mean != nullptr) {
-    double unb = count > 1 ? var * ((double)count / (double)(count - 1)) : var;
-    r.running_mean[k] = (1.f - r.momentum) * r.running_mean[k] + r.momentum * (float)mean;
-    r.running_var[k] = (1.f - r.momentum) * r.running_var[k] + r.momentum * (float)unb;
-  }
-  if (k == 0 && r.nbt != nullptr) *r.nbt += 1;
-}
-
 // Grid-wide "am I the last CTA" test on a self-resetting counter.  All threads must call.
 // `expected` = number of CTAs that arrive on this counter.
 __device__ __forceinline__ bool grid_last_block(unsigned int* counter, unsigned int expected) {
@@ -150,11 +110,11 @@ __device__ __forceinline__ bool grid_last_block(unsigned int* counter, unsigned 
 }
 
 // Row-per-warp kernels: reduce NV per-lane double vectors (lane owns VEC channels) over the
-// CTA's warps and write them to partial[(blockIdx.x * NV + v) * H + k].  `sbuf` holds
+// CTA's warps and write them to partial[(part * NVT + v0 + v) * K + koff + k], k < H.  `sbuf` holds
 // kRowWarps * H doubles.  Summation order is fixed (warp 0..7) => deterministic.
 template <int VEC, int NV>
-__device__ __forceinline__ void block_partial_store(double (&acc)[NV][VEC], double* sbuf, double* partial,
-                                                    int H) {
+__device__ __forceinline__ void block_partial_store_ex(double (&acc)[NV][VEC], double* sbuf, double* partial,
+                                                       int H, int part, int NVT, int v0, int K, int koff) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
@@ -166,9 +126,14 @@ __device__ __forceinline__ void block_partial_store(double (&acc)[NV][VEC], doub
       double s = 0.0;
 #pragma unroll
       for (int w = 0; w < kRowWarps; ++w) s += sbuf[w * H + k];
-      partial[((size_t)blockIdx.x * NV + v) * H + k] = s;
+      partial[((size_t)part * NVT + v0 + v) * K + koff + k] = s;
     }
   }
+}
+template <int VEC, int NV>
+__device__ __forceinline__ void block_partial_store(double (&acc)[NV][VEC], double* sbuf, double* partial,
+                                                    int H) {
+  block_partial_store_ex<VEC, NV>(acc, sbuf, partial, H, blockIdx.x, NV, 0, H, 0);
 }
 
 // Sum over the G CTAs' partials of vector v, channel k (fixed order).
@@ -185,7 +150,7 @@ __device__ __forceinline__ double partial_total(const double* partial, int G, in
   return (s0 + s1) + (s2 + s3);
 }
 
-inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int row_grid(int max_rows, int rows_per_cta = 4 * kRowWarps) {
   int g = ceil_div(max_rows > 0 ? max_rows : 1, rows_per_cta);
   if (g > kMaxStatBlocks) g = kMaxStatBlocks;
@@ -204,7 +169,6 @@ inline int row_grid(int max_rows, int rows_per_cta = 4 * kRowWarps) {
     case 1: { constexpr int VEC = 1; __VA_ARGS__; } break;    \
     case 2: { constexpr int VEC = 2; __VA_ARGS__; } break;    \
     case 4: { constexpr int VEC = 4; __VA_ARGS__; } break;    \
-    case 8: { constexpr int VEC = 8; __VA_ARGS__; } break;    \
     default: return CAL_EINVAL;                               \
   }
 

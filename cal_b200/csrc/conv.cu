@@ -1,0 +1,749 @@
+// conv.cu -- the node-level kernels: input transform, the fused GCNConv layer (forward and
+// backward), the two attention-masked convs, and their weight gradients.
+//
+// One launch per BatchNorm boundary (training-mode BatchNorm is the only coupling between the
+// graphs of a batch): a persistent CTA walks 32-row tiles; for every tile it
+//   1. stages the tile's CSR segment in shared memory with coalesced loads,
+//   2. gathers + normalises the neighbour rows (warp per destination row, lanes over channels,
+//      previous BatchNorm applied on load) into a shared-memory tile        [gcn_conv.py:92-97]
+//   3. multiplies the tile by the weight matrix held in shared memory (fp32 FFMA; aggregation and
+//      the linear map commute, so A(XW) is evaluated as (AX)W)               [gcn_conv.py:75]
+//   4. bias + ReLU, stores the rows, and accumulates the next BatchNorm's statistics in fp64;
+// the last CTA to finish turns the per-CTA partial sums into the affine the next kernel applies.
+#include "internal.cuh"
+
+namespace cal {
+
+namespace {
+
+struct Dims {
+  int N, E, B;
+};
+__device__ __forceinline__ Dims load_dims(const Ctx& c) {
+  Dims d;
+  d.N = imin(imax(c.dims[0], 0), c.Nm);
+  d.E = imin(imax(c.dims[1], 0), c.Em);
+  d.B = imin(imax(c.dims[2], 0), c.Bm);
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bn_feat statistics (model.py:90): column sums of x [N, F] in fp64.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_feat_stats(const Ctx c) {
+  const Dims d = load_dims(c);
+  const int F = c.F, N = d.N;
+  __shared__ double s_s[256], s_q[256];
+  const int Fw = imin(F, 256), rpar = 256 / Fw;
+  const int t = threadIdx.x;
+  const int rows_per = ceil_div(imax(N, 1), gridDim.x);
+  const int r0 = imin(blockIdx.x * rows_per, N), r1 = imin(r0 + rows_per, N);
+  double* part = c.statp + (size_t)blockIdx.x * 2 * F;
+  for (int cb = 0; cb < F; cb += Fw) {
+    const int col = cb + t % Fw, rs = t / Fw;
+    double s = 0.0, q = 0.0;
+    if (rs < rpar && col < F)
+      for (int r = r0 + rs; r < r1; r += rpar) {
+        double v = (double)c.feat[(size_t)r * F + col];
+        s += v;
+        q += v * v;
+      }
+    __syncthreads();
+    s_s[t] = s;
+    s_q[t] = q;
+    __syncthreads();
+    if (t < Fw && cb + t < F) {
+      double a = 0.0, b = 0.0;
+      for (int k = 0; k < rpar; ++k) {
+        a += s_s[k * Fw + t];
+        b += s_q[k * Fw + t];
+      }
+      part[cb + t] = a;
+      part[F + cb + t] = b;
+    }
+  }
+  if (grid_last_block(&c.counters[CNT_FEATSTAT], gridDim.x)) bn_finalize(c, 0, c.statp, gridDim.x, 2, 0, 1, N);
+}
+
+// ---------------------------------------------------------------------------------------------
+// x_1 = relu(bn_feat(x) @ W_feat)    (model.py:90-91; conv_feat is gfn=True: no bias, no
+// propagation, gcn_conv.py:75-77) + statistics of bns_conv[0].
+// smem: sW [Fp][H] | sA [R][Fp] | sRed f64 [8][H]
+// ---------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) k_feat_fwd(const Ctx c) {
+  constexpr int H = 32 * VEC;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Dims d = load_dims(c);
+  const int N = d.N, F = c.F, Fp = (F + 3) & ~3;
+  float* sW = reinterpret_cast<float*>(smem_raw);
+  float* sA = sW + (size_t)Fp * H;
+  double* sRed = reinterpret_cast<double*>(sA + (size_t)kTileRows * Fp);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* W = c.params + c.po.conv_feat_w;
+  for (int i = threadIdx.x; i < Fp * H; i += blockDim.x) sW[i] = i < F * H ? W[i] : 0.f;
+  const float* sc = c.bnf(0, BN_SCALE);
+  const float* sh = c.bnf(0, BN_SHIFT);
+  float* out = c.Xl(0);
+  double acc_s[VEC], acc_q[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc_s[i] = acc_q[i] = 0.0;
+  const int ntiles = ceil_div(N, kTileRows);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int row0 = tile * kTileRows;
+    __syncthreads();
+    for (int i = threadIdx.x; i < kTileRows * Fp; i += blockDim.x) {
+      int r = i / Fp, k = i - r * Fp;
+      float v = 0.f;
+      if (row0 + r < N && k < F) v = fmaf(c.feat[(size_t)(row0 + r) * F + k], sc[k], sh[k]);
+      sA[i] = v;
+    }
+    __syncthreads();
+    float acc[kRPW][VEC];
+#pragma unroll
+    for (int r = 0; r < kRPW; ++r)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[r][i] = 0.f;
+    tile_gemm<VEC, kRPW>(sA, Fp, sW, H, Fp, acc);
+#pragma unroll
+    for (int r = 0; r < kRPW; ++r) {
+      const int i = row0 + warp * kRPW + r;
+      if (i < N) {
+        RowVec<VEC> o;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          o.v[k] = fmaxf(acc[r][k], 0.f);
+          acc_s[k] += (double)o.v[k];
+          acc_q[k] += (double)o.v[k] * (double)o.v[k];
+        }
+        o.store(out + (size_t)i * H, lane);
+      }
+    }
+  }
+  if (c.train) {
+    double accs[2][VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      accs[0][k] = acc_s[k];
+      accs[1][k] = acc_q[k];
+    }
+    block_partial_store<VEC, 2>(accs, sRed, c.statp, H);
+    if (grid_last_block(&c.counters[CNT_FEAT], gridDim.x)) bn_finalize(c, 1, c.statp, gridDim.x, 2, 0, 1, N);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused GCNConv layer, forward.
+//   MODE 0: backbone layer l < L-1      x_{l+2} = relu(A bn_l(x_{l+1}) W_l + b_l)   (model.py:93-95)
+//   MODE 1: last backbone layer; epilogue also evaluates node_att_mlp / edge_att_mlp projections
+//           (model.py:97-111) and the statistics of bnc / bno on att * x
+//   MODE 2: context_convs / objects_convs on the soft-masked features with the attention-weighted
+//           norm (model.py:112-113, gcn_conv.py:59-70 with edge_weight); blockIdx.y = branch
+// smem: sW [H][H] | sA [R][H] | sRed f64 [8][H] | sPtr [R+4] | sSrc [EC] | sNrm [EC]
+// ---------------------------------------------------------------------------------------------
+template <int VEC>
+constexpr size_t conv_smem_bytes() {
+  constexpr int H = 32 * VEC;
+  return (size_t)H * H * 4 + (size_t)kTileRows * H * 4 + (size_t)kRowWarps * H * 8 + (kTileRows + 4) * 4 +
+         (size_t)kEdgeStage * 8;
+}
+
+template <int VEC, int MODE>
+__global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) {
+  constexpr int H = 32 * VEC;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Dims d = load_dims(c);
+  const int N = d.N;
+  float* sW = reinterpret_cast<float*>(smem_raw);
+  float* sA = sW + H * H;
+  double* sRed = reinterpret_cast<double*>(sA + kTileRows * H);
+  int* sPtr = reinterpret_cast<int*>(sRed + kRowWarps * H);
+  int* sSrc = sPtr + kTileRows + 4;
+  float* sNrm = reinterpret_cast<float*>(sSrc + kEdgeStage);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int branch = MODE == 2 ? blockIdx.y : 0;
+  const int conv = MODE == 2 ? c.L + branch : layer;
+  const int bn_in = MODE == 2 ? c.L + 1 + branch : 1 + layer;
+  const float* W = c.params + (MODE == 2 ? (branch ? c.po.objects_w : c.po.context_w) : c.po.convs_w[layer]);
+  const float* bias = c.params + (MODE == 2 ? (branch ? c.po.objects_b : c.po.context_b) : c.po.convs_b[layer]);
+  const float* xin = MODE == 2 ? c.Xl(c.L) : c.Xl(layer);
+  float* xout = MODE == 2 ? c.Z + (size_t)branch * c.Nm * H : c.Xl(layer + 1);
+  float* aggout = c.agg + (size_t)branch * c.Nm * H;
+  (void)conv;
+
+  stage_matrix_async(sW, W, H * H);
+
+  BnLane<VEC> bn;
+  bn.load_fwd(c, bn_in, lane);
+  float bv[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) bv[i] = bias[lane * VEC + i];
+
+  // attention projections (MODE 1)
+  float wn0[VEC], wn1[VEC], wp0[VEC], wp1[VEC], wq0[VEC], wq1[VEC];
+  float bn0 = 0.f, bn1 = 0.f;
+  if (MODE == 1) {
+    const float* Wn = c.params + c.po.node_att_w;    // [2][H]
+    const float* We = c.params + c.po.edge_att_w;    // [2][2H]
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      int k = lane * VEC + i;
+      wn0[i] = Wn[k];
+      wn1[i] = Wn[H + k];
+      wp0[i] = We[k];
+      wp1[i] = We[2 * H + k];
+      wq0[i] = We[H + k];
+      wq1[i] = We[3 * H + k];
+    }
+    bn0 = c.params[c.po.node_att_b];
+    bn1 = c.params[c.po.node_att_b + 1];
+  }
+
+  constexpr int NV = MODE == 1 ? 4 : 2;
+  double st[NV][VEC];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) st[v][i] = 0.0;
+
+  const int ntiles = ceil_div(N, kTileRows);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int row0 = tile * kTileRows;
+    const int nrows = imin(kTileRows, N - row0);
+    __syncthreads();                                   // previous tile's readers of sA / sPtr are done
+    if (threadIdx.x <= nrows) sPtr[threadIdx.x] = c.in_ptr[row0 + threadIdx.x];
+    __syncthreads();
+    const int pbase = sPtr[0], pcount = sPtr[nrows] - pbase;
+    const bool staged = pcount <= kEdgeStage;
+    if (staged) {
+      for (int i = threadIdx.x; i < pcount; i += blockDim.x) {
+        sSrc[i] = c.in_src[pbase + i];
+        if (MODE == 2) sNrm[i] = c.watt[(size_t)(pbase + i) * 2 + branch];
+        else sNrm[i] = c.in_norm[pbase + i];
+      }
+    }
+    __syncthreads();
+    // ---- gather: warp per destination row ----
+#pragma unroll 1
+    for (int r = 0; r < kRPW; ++r) {
+      const int lr = warp * kRPW + r;
+      const int i = row0 + lr;
+      RowVec<VEC> a;
+      a.zero();
+      if (lr < nrows) {
+        const int p0 = sPtr[lr], p1 = sPtr[lr + 1];
+        float di = 1.f;
+        if (MODE == 2) di = c.disw[(size_t)i * 2 + branch];
+        for (int p = p0; p < p1; p += 4) {
+          int s[4];
+          float w[4];
+          RowVec<VEC> v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (p + u < p1) {
+              s[u] = staged ? sSrc[p + u - pbase] : c.in_src[p + u];
+              w[u] = staged ? sNrm[p + u - pbase]
+                            : (MODE == 2 ? c.watt[(size_t)(p + u) * 2 + branch] : c.in_norm[p + u]);
+            } else {
+              s[u] = i;
+              w[u] = 0.f;
+            }
+          }
+          float am[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            v[u].load_coherent(xin + (size_t)s[u] * H, lane);
+            if (MODE == 2) {
+              am[u] = c.natt[(size_t)s[u] * 2 + branch];
+              w[u] = (c.disw[(size_t)s[u] * 2 + branch] * w[u]) * di;     // dis[row] * w * dis[col]
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+              float x = MODE == 2 ? am[u] * v[u].v[k] : v[u].v[k];
+              a.v[k] = fmaf(w[u], fmaf(x, bn.sc[k], bn.sh[k]), a.v[k]);
+            }
+        }
+        if (MODE == 2) a.store(aggout + (size_t)i * H, lane);
+      }
+      a.store(sA + lr * H, lane);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    // ---- tile GEMM ----
+    float acc[kRPW][VEC];
+#pragma unroll
+    for (int r = 0; r < kRPW; ++r)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
+    tile_gemm<VEC, kRPW>(sA, H, sW, H, H, acc);
+    // ---- epilogue ----
+#pragma unroll
+    for (int r = 0; r < kRPW; ++r) {
+      const int i = row0 + warp * kRPW + r;
+      if (i < N) {                                      // warp-uniform
+        RowVec<VEC> o;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) o.v[k] = fmaxf(acc[r][k] + bv[k], 0.f);
+        o.store(xout + (size_t)i * H, lane);
+        if (MODE == 0) {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            st[0][k] += (double)o.v[k];
+            st[1][k] += (double)o.v[k] * (double)o.v[k];
+          }
+        }
+        if (MODE == 1) {
+          float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            s0 = fmaf(o.v[k], wn0[k], s0);
+            s1 = fmaf(o.v[k], wn1[k], s1);
+            p0 = fmaf(o.v[k], wp0[k], p0);
+            p1 = fmaf(o.v[k], wp1[k], p1);
+            q0 = fmaf(o.v[k], wq0[k], q0);
+            q1 = fmaf(o.v[k], wq1[k], q1);
+          }
+          s0 = warp_sum(s0) + bn0;
+          s1 = warp_sum(s1) + bn1;
+          p0 = warp_sum(p0);
+          p1 = warp_sum(p1);
+          q0 = warp_sum(q0);
+          q1 = warp_sum(q1);
+          float a0 = 0.5f, a1 = 0.5f;
+          if (!c.no_natt) {                             // softmax over the two logits (model.py:109)
+            float m = fmaxf(s0, s1);
+            float e0 = expf(s0 - m), e1 = expf(s1 - m);
+            float inv = 1.0f / (e0 + e1);
+            a0 = e0 * inv;
+            a1 = e1 * inv;
+          }
+          if (lane == 0) {
+            *reinterpret_cast<float2*>(c.natt + (size_t)i * 2) = make_float2(a0, a1);
+            *reinterpret_cast<float4*>(c.pq + (size_t)i * 4) = make_float4(p0, p1, q0, q1);
+          }
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            double vc = (double)(a0 * o.v[k]), vo = (double)(a1 * o.v[k]);
+            st[0][k] += vc;
+            st[1][k] += vc * vc;
+            st[2][k] += vo;
+            st[3][k] += vo * vo;
+          }
+        }
+      }
+    }
+  }
+  cp_async_wait_all();
+  if (MODE != 2 && c.train) {
+    block_partial_store<VEC, NV>(st, sRed, c.statp, H);
+    if (grid_last_block(&c.counters[CNT_CONV0 + layer], gridDim.x)) {
+      if (MODE == 0) {
+        bn_finalize(c, 2 + layer, c.statp, gridDim.x, NV, 0, 1, N);
+      } else {
+        bn_finalize(c, c.L + 1, c.statp, gridDim.x, NV, 0, 1, N);
+        bn_finalize(c, c.L + 2, c.statp, gridDim.x, NV, 2, 3, N);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused GCNConv layer, backward (backbone layers).  With g_z = relu'(x_out) * bn_up'(D_up):
+//   u_j   = sum_{e: row_e = j} norm_e * g_z[col_e]          (transpose aggregate, by-source CSR)
+//   D_j   = u_j W^T                                          (gradient w.r.t. bn_l output)
+//   dW   += bn_l(x_in)_j^T u_j,   db += g_z (own rows)
+//   and the two BatchNorm-backward sums of bn_l (sum D, sum D * xhat).
+// smem: sW [H][H] (W^T) | sU [R][H] | sY [R][H] | sRed f64 [8][H] | sPtr | sDst | sNrm
+// ---------------------------------------------------------------------------------------------
+template <int VEC>
+constexpr size_t convb_smem_bytes() {
+  return conv_smem_bytes<VEC>() + (size_t)kTileRows * 32 * VEC * 4;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) {
+  constexpr int H = 32 * VEC;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Dims d = load_dims(c);
+  const int N = d.N;
+  float* sW = reinterpret_cast<float*>(smem_raw);
+  float* sU = sW + H * H;
+  float* sY = sU + kTileRows * H;
+  double* sRed = reinterpret_cast<double*>(sY + kTileRows * H);
+  int* sPtr = reinterpret_cast<int*>(sRed + kRowWarps * H);
+  int* sDst = sPtr + kTileRows + 4;
+  float* sNrm = reinterpret_cast<float*>(sDst + kEdgeStage);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  stage_matrix_async(sW, c.wt_conv(layer), H * H);
+
+  const int bn_in = 1 + layer;
+  const int bn_up = layer == c.L - 1 ? kBnIdentity : 2 + layer;
+  const float* xin = c.Xl(layer);
+  const float* xup = c.Xl(layer + 1);
+  const float* Dup = c.D + (size_t)((layer + 1) & 1) * c.Nm * H;
+  float* Dout = c.D + (size_t)(layer & 1) * c.Nm * H;
+  BnLane<VEC> bi, bu;
+  bi.load_bwd(c, bn_in, lane);
+  bu.load_bwd(c, bn_up, lane);
+
+  OuterAcc<H> dW;
+  dW.zero();
+  float dbias[VEC];
+  double st[2][VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    dbias[k] = 0.f;
+    st[0][k] = st[1][k] = 0.0;
+  }
+
+  const int ntiles = ceil_div(N, kTileRows);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int row0 = tile * kTileRows;
+    const int nrows = imin(kTileRows, N - row0);
+    __syncthreads();
+    if (threadIdx.x <= nrows) sPtr[threadIdx.x] = c.out_ptr[row0 + threadIdx.x];
+    __syncthreads();
+    const int qbase = sPtr[0], qcount = sPtr[nrows] - qbase;
+    const bool staged = qcount <= kEdgeStage;
+    if (staged) {
+      for (int i = threadIdx.x; i < qcount; i += blockDim.x) {
+        sDst[i] = c.out_dst[qbase + i];
+        sNrm[i] = c.in_norm[c.out_pos[qbase + i]];
+      }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int r = 0; r < kRPW; ++r) {
+      const int lr = warp * kRPW + r;
+      const int j = row0 + lr;
+      RowVec<VEC> u, y;
+      u.zero();
+      y.zero();
+      if (lr < nrows) {
+        const int q0 = sPtr[lr], q1 = sPtr[lr + 1];
+        for (int q = q0; q < q1; q += 2) {
+          int dd[2];
+          float w[2];
+          RowVec<VEC> gv[2], xv[2];
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (q + t < q1) {
+              dd[t] = staged ? sDst[q + t - qbase] : c.out_dst[q + t];
+              w[t] = staged ? sNrm[q + t - qbase] : c.in_norm[c.out_pos[q + t]];
+            } else {
+              dd[t] = j;
+              w[t] = 0.f;
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            gv[t].load_coherent(Dup + (size_t)dd[t] * H, lane);
+            xv[t].load_coherent(xup + (size_t)dd[t] * H, lane);
+          }
+#pragma unroll
+          for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+              float g = xv[t].v[k] > 0.f ? bu.dx(k, gv[t].v[k], xv[t].v[k]) : 0.f;
+              u.v[k] = fmaf(w[t], g, u.v[k]);
+            }
+        }
+        // own row: y = bn_l(x_in) for dW; g_z for db
+        RowVec<VEC> xi, go, xo;
+        xi.load_coherent(xin + (size_t)j * H, lane);
+        go.load_coherent(Dup + (size_t)j * H, lane);
+        xo.load_coherent(xup + (size_t)j * H, lane);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          y.v[k] = fmaf(xi.v[k], bi.sc[k], bi.sh[k]);
+          dbias[k] += xo.v[k] > 0.f ? bu.dx(k, go.v[k], xo.v[k]) : 0.f;
+        }
+      }
+      u.store(sU + lr * H, lane);
+      y.store(sY + lr * H, lane);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    float acc[kRPW][VEC];
+#pragma unroll
+    for (int r = 0; r < kRPW; ++r)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
+    tile_gemm<VEC, kRPW>(sU, H, sW, H, H, acc);
+#pragma unroll
+    for (int r = 0; r < kRPW; ++r) {
+      const int j = row0 + warp * kRPW + r;
+      if (j < N) {
+        RowVec<VEC> o, xi;
+        xi.load_coherent(xin + (size_t)j * H, lane);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          o.v[k] = acc[r][k];
+          st[0][k] += (double)acc[r][k];
+          st[1][k] += (double)acc[r][k] * (double)bi.xhat(k, xi.v[k]);
+        }
+        o.store(Dout + (size_t)j * H, lane);
+      }
+    }
+    dW.accumulate(sY, H, sU, H, kTileRows);
+  }
+  cp_async_wait_all();
+  float* gp = c.gpart + c.gp_conv[layer] + (size_t)blockIdx.x * (H * H + H);
+  if (blockIdx.x < ntiles) dW.store(gp, H);
+  block_colsum_store<VEC>(dbias, reinterpret_cast<float*>(sRed), blockIdx.x < ntiles ? gp + H * H : nullptr, H);
+  block_partial_store<VEC, 2>(st, sRed, c.statp, H);
+  if (grid_last_block(&c.counters[CNT_BCONV0 + layer], gridDim.x))
+    bn_bwd_finalize(c, bn_in, c.statp, gridDim.x, 2, 0, 1, N);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Masked convs backward, dense part (blockIdx.y = branch):
+//   dz = dpool[graph(i)] * relu'(z_i);  dagg_i = dz_i W^T;  dW += agg_i^T dz_i;  db += dz_i
+// (global_add_pool backward is the broadcast of the pooled gradient, model.py:115-116.)
+// ---------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) k_masked_bwd_gemm(const Ctx c) {
+  constexpr int H = 32 * VEC;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Dims d = load_dims(c);
+  const int N = d.N;
+  float* sW = reinterpret_cast<float*>(smem_raw);
+  float* sU = sW + H * H;
+  float* sY = sU + kTileRows * H;
+  double* sRed = reinterpret_cast<double*>(sY + kTileRows * H);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int branch = blockIdx.y;
+  stage_matrix_async(sW, c.wt_conv(c.L + branch), H * H);
+  const float* Z = c.Z + (size_t)branch * c.Nm * H;
+  const float* A = c.agg + (size_t)branch * c.Nm * H;
+  const float* dpool = c.dpool + (size_t)branch * c.Bm * H;
+  float* dagg = c.dagg + (size_t)branch * c.Nm * H;
+  OuterAcc<H> dW;
+  dW.zero();
+  float dbias[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) dbias[k] = 0.f;
+  const int ntiles = ceil_div(N, kTileRows);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int row0 = tile * kTileRows;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kRPW; ++r) {
+      const int lr = warp * kRPW + r;
+      const int i = row0 + lr;
+      RowVec<VEC> u, y;
+      u.zero();
+      y.zero();
+      if (i < N) {
+        RowVec<VEC> z, g;
+        z.load_coherent(Z + (size_t)i * H, lane);
+        g.load_coherent(dpool + (size_t)c.node_graph[i] * H, lane);
+        y.load_coherent(A + (size_t)i * H, lane);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          u.v[k] = z.v[k] > 0.f ? g.v[k] : 0.f;
+          dbias[k] += u.v[k];
+        }
+      }
+      u.store(sU + lr * H, lane);
+      y.store(sY + lr * H, lane);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    float acc[kRPW][VEC];
+#pragma unroll
+    for (int r = 0; r < kRPW; ++r)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
+    tile_gemm<VEC, kRPW>(sU, H, sW, H, H, acc);
+#pragma unroll
+    for (int r = 0; r < kRPW; ++r) {
+      const int i = row0 + warp * kRPW + r;
+      if (i < N) {
+        RowVec<VEC> o;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) o.v[k] = acc[r][k];
+        o.store(dagg + (size_t)i * H, lane);
+      }
+    }
+    dW.accumulate(sY, H, sU, H, kTileRows);
+  }
+  cp_async_wait_all();
+  float* gp = c.gpart + c.gp_conv[c.L + branch] + (size_t)blockIdx.x * (H * H + H);
+  if (blockIdx.x < ntiles) dW.store(gp, H);
+  block_colsum_store<VEC>(dbias, reinterpret_cast<float*>(sRed), blockIdx.x < ntiles ? gp + H * H : nullptr, H);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Input transform backward: with g = relu'(x_1) * bn_1'(D_0):
+//   M = xhat_0^T g  [F, H]  and  cs = colsum(g); the reduce kernel turns them into
+//   d W_feat = gamma_0 * M + beta_0 (x) cs,  d gamma_0[f] = sum_j W[f][j] M[f][j],
+//   d beta_0[f] = sum_j W[f][j] cs[j]          (bn_feat is the first op: no gradient beyond it).
+// grid (G, ceil(F / 64)); smem: sG [R][H] | sX [R][64]
+// ---------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) k_feat_bwd(const Ctx c) {
+  constexpr int H = 32 * VEC;
+  constexpr int FW = kFeatChunk / kRowWarps;       // feature columns per warp
+  __shared__ __align__(16) float sG[kTileRows * H];
+  __shared__ float sX[kTileRows * kFeatChunk];
+  __shared__ float sRed[kRowWarps * H];
+  const Dims d = load_dims(c);
+  const int N = d.N, F = c.F;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f0 = blockIdx.y * kFeatChunk;
+  const float* x1 = c.Xl(0);
+  const float* D0 = c.D;
+  const float* mean0 = c.bnf(0, BN_MEAN);
+  const float* rstd0 = c.bnf(0, BN_RSTD);
+  BnLane<VEC> b1;
+  b1.load_bwd(c, 1, lane);
+  float M[FW][VEC], cs[VEC];
+#pragma unroll
+  for (int a = 0; a < FW; ++a)
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) M[a][k] = 0.f;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) cs[k] = 0.f;
+  const int ntiles = ceil_div(N, kTileRows);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int row0 = tile * kTileRows;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kRPW; ++r) {
+      const int lr = warp * kRPW + r;
+      const int i = row0 + lr;
+      RowVec<VEC> g;
+      g.zero();
+      if (i < N) {
+        RowVec<VEC> dv, xv;
+        dv.load_coherent(D0 + (size_t)i * H, lane);
+        xv.load_coherent(x1 + (size_t)i * H, lane);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          g.v[k] = xv.v[k] > 0.f ? b1.dx(k, dv.v[k], xv.v[k]) : 0.f;
+          cs[k] += g.v[k];
+        }
+      }
+      g.store(sG + lr * H, lane);
+    }
+    for (int i = threadIdx.x; i < kTileRows * kFeatChunk; i += blockDim.x) {
+      int r = i / kFeatChunk, f = f0 + (i - r * kFeatChunk);
+      float v = 0.f;
+      if (row0 + r < N && f < F) v = (c.feat[(size_t)(row0 + r) * F + f] - mean0[f]) * rstd0[f];
+      sX[i] = v;
+    }
+    __syncthreads();
+    for (int r = 0; r < kTileRows; ++r) {
+      RowVec<VEC> g;
+      g.load_coherent(sG + r * H, lane);
+#pragma unroll
+      for (int a = 0; a < FW; ++a) {
+        float x = sX[r * kFeatChunk + warp * FW + a];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) M[a][k] = fmaf(x, g.v[k], M[a][k]);
+      }
+    }
+  }
+  float* gp = c.gpart + c.gp_feat + (size_t)blockIdx.x * ((size_t)F * H + H);
+#pragma unroll
+  for (int a = 0; a < FW; ++a) {
+    const int f = f0 + warp * FW + a;
+    if (f < F) {
+      RowVec<VEC> o;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) o.v[k] = M[a][k];
+      o.store(gp + (size_t)f * H, lane);
+    }
+  }
+  if (blockIdx.y == 0) block_colsum_store<VEC>(cs, sRed, gp + (size_t)F * H, H);
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return 0;
+}
+
+}  // namespace
+
+int launch_feat_forward(const Ctx& c, cudaStream_t s) {
+  if (c.train) k_feat_stats<<<c.g_tile, 256, 0, s>>>(c);
+  const int Fp = (c.F + 3) & ~3;
+  CAL_DISPATCH_VEC(c.H, {
+    size_t smem = (size_t)Fp * c.H * 4 + (size_t)kTileRows * Fp * 4 + (size_t)kRowWarps * c.H * 8;
+    int rc = set_smem(k_feat_fwd<VEC>, smem);
+    if (rc) return rc;
+    k_feat_fwd<VEC><<<c.g_tile, 256, smem, s>>>(c);
+  });
+  CAL_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_conv_forward(const Ctx& c, int layer, cudaStream_t s) {
+  const bool last = layer == c.L - 1;
+  CAL_DISPATCH_VEC(c.H, {
+    size_t smem = conv_smem_bytes<VEC>();
+    if (last) {
+      int rc = set_smem(k_conv_fwd<VEC, 1>, smem);
+      if (rc) return rc;
+      k_conv_fwd<VEC, 1><<<c.g_tile, 256, smem, s>>>(c, layer);
+    } else {
+      int rc = set_smem(k_conv_fwd<VEC, 0>, smem);
+      if (rc) return rc;
+      k_conv_fwd<VEC, 0><<<c.g_tile, 256, smem, s>>>(c, layer);
+    }
+  });
+  CAL_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_masked_forward(const Ctx& c, cudaStream_t s) {
+  CAL_DISPATCH_VEC(c.H, {
+    size_t smem = conv_smem_bytes<VEC>();
+    int rc = set_smem(k_conv_fwd<VEC, 2>, smem);
+    if (rc) return rc;
+    k_conv_fwd<VEC, 2><<<dim3(c.g_tile, 2), 256, smem, s>>>(c, 0);
+  });
+  CAL_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_conv_backward(const Ctx& c, int layer, cudaStream_t s) {
+  CAL_DISPATCH_VEC(c.H, {
+    size_t smem = convb_smem_bytes<VEC>();
+    int rc = set_smem(k_conv_bwd<VEC>, smem);
+    if (rc) return rc;
+    k_conv_bwd<VEC><<<c.g_tile, 256, smem, s>>>(c, layer);
+  });
+  CAL_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_masked_bwd_gemm(const Ctx& c, cudaStream_t s) {
+  CAL_DISPATCH_VEC(c.H, {
+    size_t smem = (size_t)c.H * c.H * 4 + 2 * (size_t)kTileRows * c.H * 4 + (size_t)kRowWarps * c.H * 8;
+    int rc = set_smem(k_masked_bwd_gemm<VEC>, smem);
+    if (rc) return rc;
+    k_masked_bwd_gemm<VEC><<<dim3(c.g_tile, 2), 256, smem, s>>>(c);
+  });
+  CAL_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_feat_backward(const Ctx& c, cudaStream_t s) {
+  CAL_DISPATCH_VEC(c.H, {
+    k_feat_bwd<VEC><<<dim3(c.g_tile, ceil_div(c.F, kFeatChunk)), 256, 0, s>>>(c);
+  });
+  CAL_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace cal

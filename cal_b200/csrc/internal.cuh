@@ -1,0 +1,300 @@
+// internal.cuh -- workspace layout, the per-call context handed to every kernel, and the
+// launcher prototypes shared by the translation units of libcal_b200.so.
+#pragma once
+#include "common.cuh"
+
+namespace cal {
+
+constexpr int kTileRows = 32;                  // destination rows per GEMM tile (8 warps x 4 rows)
+constexpr int kRPW = kTileRows / kRowWarps;    // rows per warp inside a tile
+constexpr int kEdgeStage = 1024;               // CSR entries staged in shared memory per tile
+constexpr int kNumBN = CAL_MAX_BN + 1;         // + the identity record used by the top layer's backward
+constexpr int kBnIdentity = CAL_MAX_BN;
+constexpr int kHeadRowsPerCta = 8;             // head2 kernels: one warp per graph row
+constexpr int kFeatChunk = 64;                 // feature columns per CTA slice in the feat backward
+
+// BN record fields inside CAL_WS_BN: [id][field][KMAX]
+enum { BN_SCALE = 0, BN_SHIFT, BN_MEAN, BN_RSTD, BN_C1, BN_C2, BN_FIELDS };
+
+__host__ __device__ inline int imin(int a, int b) { return a < b ? a : b; }
+__host__ __device__ inline int imax(int a, int b) { return a > b ? a : b; }
+
+struct Layout {
+  size_t off[CAL_WS_REGION_COUNT];
+  size_t size[CAL_WS_REGION_COUNT];
+  size_t total;
+  int kmax;        // floats per BN field
+  int g_tile;      // persistent grid of the row-tile (GEMM) kernels
+  int g_row;       // grid of the warp-per-row kernels
+  int t_head1;     // row tiles of the readout fc1 kernels (per head)
+  int g_head2;     // CTAs of the readout fc2 kernels
+  int g_feat;      // grid.x of feat kernels
+  int n_fchunk;    // grid.y of the feat backward
+  // GPART sub-offsets (floats)
+  size_t gp_conv[CAL_MAX_LAYERS + 2];   // [G][H*H + H]
+  size_t gp_att;                        // [G][8H + 4]
+  size_t gp_feat;                       // [G][F*H + H]
+  size_t gp_fc1[3];                     // [T1][H*2H + H]
+  size_t gp_fc2[3];                     // [G2][C*H + C]
+  size_t gp_gat[CAL_MAX_LAYERS];        // [G][2H] attention-vector partials (GAT)
+};
+
+// Everything a kernel needs, passed by value.
+struct Ctx {
+  // model
+  int model, F, H, C, L, heads, cat, no_natt, no_eatt, train;
+  float eps, momentum, w_c, w_o, w_co, gat_p;
+  // capacities and plan
+  int Nm, Em, Bm, EP, kmax, g_tile, g_row, t_head1, g_head2;
+  // batch
+  const int* dims;
+  const float* feat;
+  const long long* ei_row;
+  const long long* ei_col;
+  const long long* batch;
+  const long long* y;
+  const int* perm_in;
+  const float* gat_keep;
+  // parameters
+  const float* params;
+  float* grads;
+  float* bn_buffers;
+  long long* nbt;
+  cal_param_offsets po;
+  long long bn_gamma[kNumBN], bn_beta[kNumBN], bn_rm[kNumBN], bn_rv[kNumBN];
+  int bn_K[kNumBN];
+  // workspace regions
+  int* status;
+  unsigned int* counters;
+  int *in_ptr, *in_src, *in_key, *out_ptr, *out_dst, *out_pos, *out_key, *cnt_in, *cnt_out;
+  int *graph_ptr, *node_graph, *perm, *invperm;
+  float *in_norm, *dis, *X, *natt, *pq, *watt, *disw, *agg, *Z, *pooled, *H1, *logp, *loss, *bn;
+  int with_loss;
+  double* statp;
+  float *WT, *gat, *dlogit, *dh, *du, *dpool, *dagg, *dym, *dnrm, *dt, *dp, *D, *gpart;
+  size_t gp_conv[CAL_MAX_LAYERS + 2], gp_att, gp_feat, gp_fc1[3], gp_fc2[3], gp_gat[CAL_MAX_LAYERS];
+  const float* grad_logp;   // external dL/dlogp (nullptr = fused loss)
+
+  __host__ __device__ float* bnf(int id, int field) const { return bn + ((size_t)id * BN_FIELDS + field) * kmax; }
+  __host__ __device__ float* Xl(int l) const { return X + (size_t)l * Nm * H; }     // l = 0..L  (x_{l+1})
+  __host__ __device__ float* wt_conv(int l) const { return WT + (size_t)l * H * H; }   // l = 0..L+1
+  __host__ __device__ float* wt_fc1(int h) const { return WT + (size_t)(L + 2) * H * H + (size_t)h * 2 * H * H; }
+};
+
+// counter slots
+enum {
+  CNT_FEATSTAT = 0, CNT_FEAT, CNT_CONV0, CNT_MASKED = CNT_CONV0 + CAL_MAX_LAYERS, CNT_HEAD1, CNT_HEAD2,
+  CNT_BHEAD2, CNT_BHEAD1, CNT_BGATHER, CNT_BCONV0, CNT_BFEAT = CNT_BCONV0 + CAL_MAX_LAYERS, CNT_GAT0,
+  CNT_BGAT0 = CNT_GAT0 + CAL_MAX_LAYERS, CNT_END = CNT_BGAT0 + 2 * CAL_MAX_LAYERS
+};
+static_assert(CNT_END <= 64, "counter region too small");
+
+int compute_layout(const cal_model_desc* m, const cal_caps* caps, Layout* lay);
+int validate_model(const cal_model_desc* m);
+
+// ---- launchers (each returns 0 or a cudaError_t) ----
+int launch_prep(const Ctx& c, cudaStream_t s);
+int launch_param_prep(const Ctx& c, cudaStream_t s);
+int launch_feat_forward(const Ctx& c, cudaStream_t s);
+int launch_conv_forward(const Ctx& c, int layer, cudaStream_t s);          // layer 0..L-1
+int launch_edge_att(const Ctx& c, cudaStream_t s);
+int launch_masked_forward(const Ctx& c, cudaStream_t s);
+int launch_heads_forward(const Ctx& c, int with_loss, cudaStream_t s);
+int launch_heads_backward(const Ctx& c, cudaStream_t s);
+int launch_masked_bwd_gemm(const Ctx& c, cudaStream_t s);
+int launch_masked_bwd_gather(const Ctx& c, cudaStream_t s);
+int launch_norm_backward(const Ctx& c, cudaStream_t s);
+int launch_att_backward(const Ctx& c, cudaStream_t s);
+int launch_conv_backward(const Ctx& c, int layer, cudaStream_t s);
+int launch_feat_backward(const Ctx& c, cudaStream_t s);
+int launch_grad_reduce(const Ctx& c, cudaStream_t s);
+int launch_gat_forward(const Ctx& c, int layer, cudaStream_t s);
+int launch_gat_backward(const Ctx& c, int layer, cudaStream_t s);
+
+// ---- device helpers shared by the kernels ----
+
+// Finalise training-mode BatchNorm statistics from G double partials laid out as
+// partial[(g * NV + v) * K + k]; vs / vq = vector index of sum / sum of squares.
+__device__ __forceinline__ void bn_finalize(const Ctx& c, int id, const double* partial, int G, int NV, int vs,
+                                            int vq, int count) {
+  const int K = c.bn_K[id];
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    double s = partial_total(partial, G, NV, vs, K, k);
+    double q = partial_total(partial, G, NV, vq, K, k);
+    double mean = 0.0, var = 0.0;
+    if (count > 0) {
+      mean = s / count;
+      var = q / count - mean * mean;
+      if (var < 0.0) var = 0.0;
+    }
+    float rstd = (float)(1.0 / sqrt(var + (double)c.eps));
+    float g = c.params[c.bn_gamma[id] + k], b = c.params[c.bn_beta[id] + k];
+    float sc = g * rstd;
+    c.bnf(id, BN_SCALE)[k] = sc;
+    c.bnf(id, BN_SHIFT)[k] = b - (float)mean * sc;
+    c.bnf(id, BN_MEAN)[k] = (float)mean;
+    c.bnf(id, BN_RSTD)[k] = rstd;
+    if (c.bn_buffers != nullptr && c.bn_rm[id] >= 0) {
+      double unb = count > 1 ? var * ((double)count / (double)(count - 1)) : var;
+      float* rm = c.bn_buffers + c.bn_rm[id];
+      float* rv = c.bn_buffers + c.bn_rv[id];
+      rm[k] = (1.f - c.momentum) * rm[k] + c.momentum * (float)mean;
+      rv[k] = (1.f - c.momentum) * rv[k] + c.momentum * (float)unb;
+    }
+  }
+  if (threadIdx.x == 0 && c.nbt != nullptr) c.nbt[id] += 1;
+}
+
+// Finalise BatchNorm backward: c1 = mean(dy), c2 = mean(dy * xhat); d gamma = sum dy*xhat, d beta = sum dy.
+__device__ __forceinline__ void bn_bwd_finalize(const Ctx& c, int id, const double* partial, int G, int NV, int v1,
+                                                int v2, int count) {
+  const int K = c.bn_K[id];
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    double s1 = partial_total(partial, G, NV, v1, K, k);
+    double s2 = partial_total(partial, G, NV, v2, K, k);
+    double inv = count > 0 ? 1.0 / count : 0.0;
+    c.bnf(id, BN_C1)[k] = (float)(s1 * inv);
+    c.bnf(id, BN_C2)[k] = (float)(s2 * inv);
+    c.grads[c.bn_gamma[id] + k] = (float)s2;
+    c.grads[c.bn_beta[id] + k] = (float)s1;
+  }
+}
+
+// Per-lane BatchNorm constants of the lane's VEC channels.
+template <int VEC>
+struct BnLane {
+  float sc[VEC], sh[VEC], mean[VEC], rstd[VEC], c1[VEC], c2[VEC];
+  __device__ __forceinline__ void load_fwd(const Ctx& c, int id, int lane, int koff = 0) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      sc[i] = c.bnf(id, BN_SCALE)[koff + lane * VEC + i];
+      sh[i] = c.bnf(id, BN_SHIFT)[koff + lane * VEC + i];
+    }
+  }
+  __device__ __forceinline__ void load_bwd(const Ctx& c, int id, int lane, int koff = 0) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      int k = koff + lane * VEC + i;
+      sc[i] = c.bnf(id, BN_SCALE)[k];
+      sh[i] = c.bnf(id, BN_SHIFT)[k];
+      mean[i] = c.bnf(id, BN_MEAN)[k];
+      rstd[i] = c.bnf(id, BN_RSTD)[k];
+      c1[i] = c.bnf(id, BN_C1)[k];
+      c2[i] = c.bnf(id, BN_C2)[k];
+    }
+  }
+  // gradient w.r.t. the BatchNorm input given dy (gradient w.r.t. its output) and the input x
+  __device__ __forceinline__ float dx(int i, float dy, float x) const {
+    float xh = (x - mean[i]) * rstd[i];
+    return sc[i] * (dy - c1[i] - xh * c2[i]);
+  }
+  __device__ __forceinline__ float xhat(int i, float x) const { return (x - mean[i]) * rstd[i]; }
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// Stage an [rows x cols] fp32 matrix (cols % 4 == 0, 16-byte aligned) into shared memory.
+__device__ __forceinline__ void stage_matrix_async(float* sdst, const float* gsrc, int n_floats) {
+  for (int i = threadIdx.x * 4; i < n_floats; i += blockDim.x * 4) cp_async16(sdst + i, gsrc + i);
+}
+
+// acc[r][c] += sum_k sA[(warp*RPW + r) * lda + k] * sW[k * ldw + lane*VEC + c]   (K % 4 == 0)
+template <int VEC, int RPW>
+__device__ __forceinline__ void tile_gemm(const float* __restrict__ sA, int lda, const float* __restrict__ sW,
+                                          int ldw, int K, float (&acc)[RPW][VEC]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* a0 = sA + (size_t)warp * RPW * lda;
+  const float* w0 = sW + lane * VEC;
+#pragma unroll 2
+  for (int k0 = 0; k0 < K; k0 += 4) {
+    float4 a[RPW];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) a[r] = *reinterpret_cast<const float4*>(a0 + r * lda + k0);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      float w[VEC];
+      const float* wp = w0 + (size_t)(k0 + kk) * ldw;
+      if constexpr (VEC == 4) {
+        float4 t = *reinterpret_cast<const float4*>(wp);
+        w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+      } else if constexpr (VEC == 2) {
+        float2 t = *reinterpret_cast<const float2*>(wp);
+        w[0] = t.x; w[1] = t.y;
+      } else {
+        w[0] = *wp;
+      }
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) {
+        float av = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
+#pragma unroll
+        for (int cc = 0; cc < VEC; ++cc) acc[r][cc] = fmaf(av, w[cc], acc[r][cc]);
+      }
+    }
+  }
+}
+
+// Outer-product accumulation over a row tile: acc[a][b] += sum_r sP[r*ld + kidx(a)] * sQ[r*ld + jidx(b)].
+// 256 threads cover an [H x H] result: thread (ty = tid / 16, tx = tid % 16) owns MT x MT entries with
+// MT = H / 16, index set {half*(H/2) + t*(MT/2) + i}.
+template <int H>
+struct OuterAcc {
+  static constexpr int MT = H / 16;
+  static constexpr int HM = MT / 2 > 0 ? MT / 2 : 1;   // contiguous run
+  static constexpr int NH = MT / HM;                   // number of runs (2, or 2 when MT == 2 -> HM = 1)
+  float acc[MT][MT];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int a = 0; a < MT; ++a)
+#pragma unroll
+      for (int b = 0; b < MT; ++b) acc[a][b] = 0.f;
+  }
+  __device__ __forceinline__ static int idx(int t, int a) { return (a / HM) * (H / NH) + t * HM + (a % HM); }
+  __device__ __forceinline__ void accumulate(const float* __restrict__ sP, int ldp, const float* __restrict__ sQ,
+                                             int ldq, int rows) {
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    for (int r = 0; r < rows; ++r) {
+      float p[MT], q[MT];
+#pragma unroll
+      for (int a = 0; a < MT; ++a) {
+        p[a] = sP[r * ldp + idx(ty, a)];
+        q[a] = sQ[r * ldq + idx(tx, a)];
+      }
+#pragma unroll
+      for (int a = 0; a < MT; ++a)
+#pragma unroll
+        for (int b = 0; b < MT; ++b) acc[a][b] = fmaf(p[a], q[b], acc[a][b]);
+    }
+  }
+  __device__ __forceinline__ void store(float* __restrict__ dst, int ldd) const {   // dst [H][ldd]
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+    for (int a = 0; a < MT; ++a)
+#pragma unroll
+      for (int b = 0; b < MT; ++b) dst[(size_t)idx(ty, a) * ldd + idx(tx, b)] = acc[a][b];
+  }
+};
+
+// Block-reduce per-thread float column accumulators (lane owns VEC channels, 8 warps) in a fixed
+// order and write H sums to dst.  sbuf holds kRowWarps * H floats.
+template <int VEC>
+__device__ __forceinline__ void block_colsum_store(const float (&acc)[VEC], float* sbuf, float* dst, int H) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) sbuf[warp * H + lane * VEC + i] = acc[i];
+  __syncthreads();
+  for (int k = threadIdx.x; k < H; k += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kRowWarps; ++w) s += sbuf[w * H + k];
+    if (dst != nullptr) dst[k] = s;
+  }
+}
+
+
+
+}  // namespace cal

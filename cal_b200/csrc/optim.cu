@@ -1,0 +1,202 @@
+// optim.cu -- fixed-order reduction of the per-CTA partial parameter gradients into the flat
+// gradient buffer, and the fused Adam step on flat buffers (train_causal.py:21,192).
+#include "internal.cuh"
+
+namespace cal {
+
+namespace {
+
+constexpr int kMaxRed = 48;
+
+// nparts rule: how many CTAs of the producing kernel actually wrote a partial
+enum { PARTS_NODE_TILES = 0, PARTS_NODE_ROWS, PARTS_HEAD_TILES, PARTS_HEAD_ROWS };
+
+struct RedEntry {
+  long long dst;      // offset into grads
+  size_t src;         // offset into gpart of part 0
+  int n;              // elements
+  int stride;         // floats between consecutive parts
+  int rule, gmax;
+};
+struct RedTable {
+  int count;
+  long long total;    // sum of n
+  RedEntry e[kMaxRed];
+  // feat special
+  size_t feat_src;
+  int feat_stride, feat_gmax;
+};
+
+__device__ __forceinline__ int nparts_of(const Ctx& c, int rule, int gmax) {
+  const int N = imin(imax(c.dims[0], 0), c.Nm), B = imin(imax(c.dims[2], 0), c.Bm);
+  int n;
+  switch (rule) {
+    case PARTS_NODE_TILES: n = ceil_div(N, kTileRows); break;
+    case PARTS_NODE_ROWS: n = ceil_div(N, kRowWarps); break;
+    case PARTS_HEAD_TILES: n = ceil_div(B, kTileRows); break;
+    default: n = ceil_div(B, kHeadRowsPerCta); break;
+  }
+  return imin(n, gmax);
+}
+
+__global__ void __launch_bounds__(256) k_grad_reduce(const Ctx c, const RedTable t, const int n_generic_blocks) {
+  if ((int)blockIdx.x < n_generic_blocks) {
+    // generic entries: thread per output element
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < t.total;
+         i += (long long)n_generic_blocks * blockDim.x) {
+      long long r = i;
+      int ei = 0;
+      while (r >= t.e[ei].n) {
+        r -= t.e[ei].n;
+        ++ei;
+      }
+      const RedEntry& e = t.e[ei];
+      const int np = nparts_of(c, e.rule, e.gmax);
+      const float* p = c.gpart + e.src + r;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      int g = 0;
+      for (; g + 4 <= np; g += 4) {
+        s0 += p[(size_t)(g + 0) * e.stride];
+        s1 += p[(size_t)(g + 1) * e.stride];
+        s2 += p[(size_t)(g + 2) * e.stride];
+        s3 += p[(size_t)(g + 3) * e.stride];
+      }
+      for (; g < np; ++g) s0 += p[(size_t)g * e.stride];
+      c.grads[e.dst + r] = (s0 + s1) + (s2 + s3);
+    }
+    return;
+  }
+  // input transform: warp per feature row f
+  //   d W_feat[f][j] = gamma0[f] M[f][j] + beta0[f] cs[j];  d gamma0[f] = sum_j W[f][j] M[f][j];
+  //   d beta0[f] = sum_j W[f][j] cs[j];  conv_feat.bias never receives a gradient (gfn=True).
+  const int H = c.H, F = c.F;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int np = nparts_of(c, PARTS_NODE_TILES, t.feat_gmax);
+  const float* W = c.params + c.po.conv_feat_w;
+  for (int f = ((int)blockIdx.x - n_generic_blocks) * kRowWarps + warp; f < F;
+       f += ((int)gridDim.x - n_generic_blocks) * kRowWarps) {
+    const float g0 = c.params[c.po.bn_feat_w + f], b0 = c.params[c.po.bn_feat_b + f];
+    float dg = 0.f, db = 0.f;
+    for (int j = lane; j < H; j += 32) {
+      float m = 0.f, cs = 0.f;
+      for (int g = 0; g < np; ++g) {
+        const float* p = c.gpart + t.feat_src + (size_t)g * t.feat_stride;
+        m += p[(size_t)f * H + j];
+        cs += p[(size_t)F * H + j];
+      }
+      c.grads[c.po.conv_feat_w + (size_t)f * H + j] = g0 * m + b0 * cs;
+      const float w = W[(size_t)f * H + j];
+      dg = fmaf(w, m, dg);
+      db = fmaf(w, cs, db);
+      if (f == 0 && c.po.conv_feat_b >= 0) c.grads[c.po.conv_feat_b + j] = 0.f;
+    }
+    dg = warp_sum(dg);
+    db = warp_sum(db);
+    if (lane == 0) {
+      c.grads[c.po.bn_feat_w + f] = dg;
+      c.grads[c.po.bn_feat_b + f] = db;
+    }
+  }
+}
+
+__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                       float* __restrict__ v, long long n, const int* __restrict__ step, float lr, float b1,
+                       float b2, float eps, float wd, float gscale) {
+  __shared__ float s_c[2];
+  if (threadIdx.x == 0) {       // bias corrections in fp64 like the Python scalars of torch.optim.Adam
+    const int t = *step;
+    const double bc1 = 1.0 - pow((double)b1, (double)t), bc2 = 1.0 - pow((double)b2, (double)t);
+    s_c[0] = (float)((double)lr / bc1);
+    s_c[1] = (float)sqrt(bc2);
+  }
+  __syncthreads();
+  const float step_size = s_c[0], bc2s = s_c[1];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i] * gscale;
+    float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    float mi = m[i] + (gi - m[i]) * (1.f - b1);          // torch: exp_avg.lerp_(grad, 1 - beta1)
+    float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / bc2s + eps;
+    p[i] = pi - step_size * (mi / denom);
+  }
+}
+
+__global__ void k_tick(int* step) { *step += 1; }
+
+}  // namespace
+
+int launch_grad_reduce(const Ctx& c, cudaStream_t s) {
+  RedTable t;
+  t.count = 0;
+  t.total = 0;
+  const int H = c.H, C = c.C;
+  auto add = [&](long long dst, size_t src, int n, int stride, int rule, int gmax) {
+    if (dst < 0 || n <= 0 || t.count >= kMaxRed) return;
+    RedEntry& e = t.e[t.count++];
+    e.dst = dst; e.src = src; e.n = n; e.stride = stride; e.rule = rule; e.gmax = gmax;
+    t.total += n;
+  };
+  const int cs = H * H + H;
+  if (c.model == CAL_MODEL_GCN)
+    for (int l = 0; l < c.L; ++l) {
+      add(c.po.convs_w[l], c.gp_conv[l], H * H, cs, PARTS_NODE_TILES, c.g_tile);
+      add(c.po.convs_b[l], c.gp_conv[l] + H * H, H, cs, PARTS_NODE_TILES, c.g_tile);
+    }
+  else
+    for (int l = 0; l < c.L; ++l) {
+      add(c.po.convs_w[l], c.gp_conv[l], H * H, cs, PARTS_NODE_TILES, c.g_tile);
+      add(c.po.convs_b[l], c.gp_conv[l] + H * H, H, cs, PARTS_NODE_TILES, c.g_tile);
+      add(c.po.convs_att[l], c.gp_gat[l], 2 * H, 2 * H, PARTS_NODE_ROWS, c.g_row);
+    }
+  add(c.po.context_w, c.gp_conv[c.L], H * H, cs, PARTS_NODE_TILES, c.g_tile);
+  add(c.po.context_b, c.gp_conv[c.L] + H * H, H, cs, PARTS_NODE_TILES, c.g_tile);
+  add(c.po.objects_w, c.gp_conv[c.L + 1], H * H, cs, PARTS_NODE_TILES, c.g_tile);
+  add(c.po.objects_b, c.gp_conv[c.L + 1] + H * H, H, cs, PARTS_NODE_TILES, c.g_tile);
+  const int as = 8 * H + 4;
+  add(c.po.node_att_w, c.gp_att, 2 * H, as, PARTS_NODE_ROWS, c.g_row);
+  add(c.po.edge_att_w, c.gp_att + 2 * H, 4 * H, as, PARTS_NODE_ROWS, c.g_row);
+  add(c.po.node_att_b, c.gp_att + 6 * H, 2, as, PARTS_NODE_ROWS, c.g_row);
+  add(c.po.edge_att_b, c.gp_att + 6 * H + 2, 2, as, PARTS_NODE_ROWS, c.g_row);
+  for (int h = 0; h < 3; ++h) {
+    const int K1 = (h == 2 && c.cat) ? 2 * H : H;
+    const int s1 = H * 2 * H + H;
+    add(c.po.fc1_w[h], c.gp_fc1[h], H * K1, s1, PARTS_HEAD_TILES, c.t_head1);
+    add(c.po.fc1_b[h], c.gp_fc1[h] + H * K1, H, s1, PARTS_HEAD_TILES, c.t_head1);
+    const int s2 = C * H + C;
+    add(c.po.fc2_w[h], c.gp_fc2[h], C * H, s2, PARTS_HEAD_ROWS, c.g_head2);
+    add(c.po.fc2_b[h], c.gp_fc2[h] + C * H, C, s2, PARTS_HEAD_ROWS, c.g_head2);
+  }
+  t.feat_src = c.gp_feat;
+  t.feat_stride = c.F * H + H;
+  t.feat_gmax = c.g_tile;
+  const int nb = imax(1, imin((int)((t.total + 255) / 256), 4 * kSMs));
+  const int nf = imax(1, imin(ceil_div(c.F, kRowWarps), kSMs));
+  k_grad_reduce<<<nb + nf, 256, 0, s>>>(c, t, nb);
+  CAL_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace cal
+
+extern "C" int cal_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                             const int32_t* step, float lr, float beta1, float beta2, float eps,
+                             float weight_decay, float grad_scale, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !step) return CAL_ENULL;
+  if (n <= 0) return CAL_EINVAL;
+  int g = (int)((n + 255) / 256);
+  if (g > 4 * cal::kSMs) g = 4 * cal::kSMs;
+  cal::k_adam<<<g, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, (long long)n, step, lr, beta1,
+                                                  beta2, eps, weight_decay, grad_scale);
+  CAL_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cal_adam_tick(int32_t* step, void* stream) {
+  if (!step) return CAL_ENULL;
+  cal::k_tick<<<1, 1, 0, (cudaStream_t)stream>>>(step);
+  CAL_CUDA_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,264 @@
+// prep.cu -- per-batch structure preparation and per-step parameter preparation.
+//
+// Replaces the integer work the reference repeats inside every GCNConv.norm call
+// (gcn_conv.py:44-70: remove_self_loops, add_self_loops, degree by ROW, deg^-1/2, norm) and the
+// implicit segmentation of global_add_pool (model.py:115-116).  Done once per batch:
+//   int64 -> int32, self loops dropped, one loop appended per node (LAST in every row, as PyG's
+//   cat puts them last), CSR by target ("in") and by source ("out"), both ordered by edge_index
+//   column so that sequential accumulation follows the CPU scatter_add order; graph_ptr; perm.
+#include "internal.cuh"
+
+namespace cal {
+
+__global__ void k_prep_init(const Ctx c) {
+  const int N = c.dims[0], E = c.dims[1], B = c.dims[2];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  if (tid == 0) {
+    int st = 0;
+    if (N < 0 || E < 0 || B < 0 || N > c.Nm || E > c.Em || B > c.Bm) st |= kStCapacity;
+    c.status[0] = st;
+    c.status[1] = c.status[2] = c.status[3] = 0;
+  }
+  if (tid < 64) c.counters[tid] = 0u;
+  if (N < 0 || E < 0 || B < 0 || N > c.Nm || E > c.Em || B > c.Bm) return;
+  for (int k = tid; k < c.kmax; k += nth) {     // identity BatchNorm record
+    c.bnf(kBnIdentity, BN_SCALE)[k] = 1.f;
+    c.bnf(kBnIdentity, BN_SHIFT)[k] = 0.f;
+    c.bnf(kBnIdentity, BN_MEAN)[k] = 0.f;
+    c.bnf(kBnIdentity, BN_RSTD)[k] = 0.f;
+    c.bnf(kBnIdentity, BN_C1)[k] = 0.f;
+    c.bnf(kBnIdentity, BN_C2)[k] = 0.f;
+  }
+  for (int n = tid; n < N; n += nth) {
+    c.cnt_in[n] = 0;
+    c.cnt_out[n] = 0;
+    long long g = c.batch[n];
+    long long gp = n > 0 ? c.batch[n - 1] : -1;
+    if (g < 0 || g >= B || g < gp) {
+      atomicOr(c.status, kStBadBatch);
+      g = g < 0 ? 0 : (g >= B ? B - 1 : g);
+    }
+    c.node_graph[n] = (int)g;
+    if (gp < -1) gp = -1;
+    if (gp >= B) gp = B - 1;
+    for (long long b = gp + 1; b <= g; ++b) c.graph_ptr[b] = n;     // graphs that start at n (empty ones too)
+    if (n == N - 1)
+      for (long long b = g + 1; b <= B; ++b) c.graph_ptr[b] = N;
+  }
+  if (N == 0)
+    for (int b = tid; b <= B; b += nth) c.graph_ptr[b] = 0;
+  for (int b = tid; b < B; b += nth) {
+    int p = c.perm_in != nullptr ? c.perm_in[b] : b;
+    if (p < 0 || p >= B) {
+      atomicOr(c.status, kStBadBatch);
+      p = b;
+    }
+    c.perm[b] = p;
+    c.invperm[p] = b;
+  }
+}
+
+__global__ void k_prep_count(const Ctx c) {
+  if (c.status[0] & kStCapacity) return;
+  const int N = c.dims[0], E = c.dims[1];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+    long long r = c.ei_row[e], d = c.ei_col[e];
+    if (r < 0 || r >= N || d < 0 || d >= N) {
+      atomicOr(c.status, kStBadNode);
+      continue;
+    }
+    if (r != d) {
+      atomicAdd(&c.cnt_in[(int)d], 1);
+      atomicAdd(&c.cnt_out[(int)r], 1);
+    }
+  }
+}
+
+// Exclusive scan of (count + 1) over the nodes (the +1 is the appended self loop), one CTA.
+__global__ void __launch_bounds__(1024) k_prep_scan(const Ctx c) {
+  if (c.status[0] & kStCapacity) return;
+  const int N = c.dims[0];
+  __shared__ int s_part[2][1024];
+  const int t = threadIdx.x, T = blockDim.x;
+  const int per = (N + T - 1) / T;
+  const int lo = imin(t * per, N), hi = imin(lo + per, N);
+  int si = 0, so = 0;
+  for (int n = lo; n < hi; ++n) {
+    si += c.cnt_in[n] + 1;
+    so += c.cnt_out[n] + 1;
+  }
+  s_part[0][t] = si;
+  s_part[1][t] = so;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over the T partials
+  for (int d = 1; d < T; d <<= 1) {
+    int a = 0, b = 0;
+    if (t >= d) {
+      a = s_part[0][t - d];
+      b = s_part[1][t - d];
+    }
+    __syncthreads();
+    s_part[0][t] += a;
+    s_part[1][t] += b;
+    __syncthreads();
+  }
+  int bi = s_part[0][t] - si, bo = s_part[1][t] - so;
+  for (int n = lo; n < hi; ++n) {
+    c.in_ptr[n] = bi;
+    c.out_ptr[n] = bo;
+    bi += c.cnt_in[n] + 1;
+    bo += c.cnt_out[n] + 1;
+    c.cnt_in[n] = 0;     // becomes the fill cursor
+    c.cnt_out[n] = 0;
+  }
+  if (t == T - 1) {
+    c.in_ptr[N] = s_part[0][T - 1];
+    c.out_ptr[N] = s_part[1][T - 1];
+  }
+}
+
+__global__ void k_prep_fill(const Ctx c) {
+  if (c.status[0] & kStCapacity) return;
+  const int N = c.dims[0], E = c.dims[1];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int e = tid; e < E; e += nth) {
+    long long r = c.ei_row[e], d = c.ei_col[e];
+    if (r < 0 || r >= N || d < 0 || d >= N || r == d) continue;
+    int pi = c.in_ptr[(int)d] + atomicAdd(&c.cnt_in[(int)d], 1);
+    c.in_key[pi] = e;
+    int po = c.out_ptr[(int)r] + atomicAdd(&c.cnt_out[(int)r], 1);
+    c.out_key[po] = e;
+  }
+  for (int n = tid; n < N; n += nth) {      // appended self loop: last slot of the row
+    c.in_key[c.in_ptr[n + 1] - 1] = E + n;
+    c.out_key[c.out_ptr[n + 1] - 1] = E + n;
+  }
+}
+
+__device__ __forceinline__ void insertion_sort(int* a, int n) {
+  for (int i = 1; i < n; ++i) {
+    int v = a[i], j = i - 1;
+    while (j >= 0 && a[j] > v) {
+      a[j + 1] = a[j];
+      --j;
+    }
+    a[j + 1] = v;
+  }
+}
+
+// Order every row by edge_index column, resolve endpoints, unweighted degree (by source row,
+// gcn_conv.py:66) and deg^-1/2.
+__global__ void k_prep_sort(const Ctx c) {
+  if (c.status[0] & kStCapacity) return;
+  const int N = c.dims[0], E = c.dims[1];
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+    int p0 = c.in_ptr[n], p1 = c.in_ptr[n + 1];
+    insertion_sort(c.in_key + p0, p1 - p0);
+    for (int p = p0; p < p1; ++p) {
+      int k = c.in_key[p];
+      c.in_src[p] = k < E ? (int)c.ei_row[k] : n;
+    }
+    int q0 = c.out_ptr[n], q1 = c.out_ptr[n + 1];
+    insertion_sort(c.out_key + q0, q1 - q0);
+    for (int q = q0; q < q1; ++q) {
+      int k = c.out_key[q];
+      c.out_dst[q] = k < E ? (int)c.ei_col[k] : n;
+    }
+    float deg = (float)(q1 - q0);            // sum of unit weights over edges with row == n (+ the loop)
+    c.dis[n] = 1.0f / sqrtf(deg);
+  }
+}
+
+// Link the two orderings (out position -> in position) and the unweighted norm.
+__global__ void k_prep_link(const Ctx c) {
+  if (c.status[0] & kStCapacity) return;
+  const int N = c.dims[0];
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+    const float dn = c.dis[n];
+    for (int p = c.in_ptr[n]; p < c.in_ptr[n + 1]; ++p) {
+      int s = c.in_src[p], key = c.in_key[p];
+      c.in_norm[p] = c.dis[s] * dn;          // dis[row] * 1 * dis[col]
+      int lo = c.out_ptr[s], hi = c.out_ptr[s + 1] - 1;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (c.out_key[mid] < key) lo = mid + 1; else hi = mid;
+      }
+      c.out_pos[lo] = p;
+    }
+  }
+}
+
+int launch_prep(const Ctx& c, cudaStream_t s) {
+  const int T = 256;
+  int gn = imax(1, imin(ceil_div(imax(c.Nm, c.Bm + 1), T), 4 * kSMs));
+  int ge = imax(1, imin(ceil_div(imax(c.Em, c.Nm), T), 4 * kSMs));
+  k_prep_init<<<gn, T, 0, s>>>(c);
+  k_prep_count<<<ge, T, 0, s>>>(c);
+  k_prep_scan<<<1, 1024, 0, s>>>(c);
+  k_prep_fill<<<ge, T, 0, s>>>(c);
+  k_prep_sort<<<imax(1, imin(ceil_div(c.Nm, 128), 8 * kSMs)), 128, 0, s>>>(c);
+  k_prep_link<<<imax(1, imin(ceil_div(c.Nm, 128), 8 * kSMs)), 128, 0, s>>>(c);
+  CAL_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-step parameter preparation: transposed copies of the conv weights (backward GEMMs) and of
+// the fc1 weights (torch Linear stores [out, in]; the forward GEMM wants [in, out]); in eval mode
+// also the BatchNorm affine from the running statistics.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_param_prep(const Ctx c) {
+  __shared__ float tile[32][33];
+  const int H = c.H;
+  const int n_conv = c.L + 2;
+  const int m = blockIdx.x;
+  if (m < n_conv + 3) {
+    const float* src;
+    float* dst;
+    int rows, cols;    // src is [rows][cols]; dst is [cols][rows]
+    if (m < n_conv) {
+      long long off = m < c.L ? c.po.convs_w[m] : (m == c.L ? c.po.context_w : c.po.objects_w);
+      src = c.params + off;
+      dst = c.wt_conv(m);
+      rows = H; cols = H;
+    } else {
+      int h = m - n_conv;
+      src = c.params + c.po.fc1_w[h];
+      dst = c.wt_fc1(h);
+      rows = H; cols = (h == 2 && c.cat) ? 2 * H : H;
+    }
+    for (int r0 = 0; r0 < rows; r0 += 32)
+      for (int c0 = 0; c0 < cols; c0 += 32) {
+        for (int i = threadIdx.y; i < 32; i += blockDim.y)
+          tile[i][threadIdx.x] = src[(size_t)(r0 + i) * cols + c0 + threadIdx.x];
+        __syncthreads();
+        for (int i = threadIdx.y; i < 32; i += blockDim.y)
+          dst[(size_t)(c0 + i) * rows + r0 + threadIdx.x] = tile[threadIdx.x][i];
+        __syncthreads();
+      }
+  } else if (!c.train) {
+    // eval: y = (x - running_mean) / sqrt(running_var + eps) * gamma + beta
+    const int nbn = c.L + 9;
+    const int t = threadIdx.y * blockDim.x + threadIdx.x;
+    for (int id = 0; id < nbn; ++id) {
+      const int K = c.bn_K[id];
+      for (int k = t; k < K; k += blockDim.x * blockDim.y) {
+        float rm = c.bn_buffers[c.bn_rm[id] + k], rv = c.bn_buffers[c.bn_rv[id] + k];
+        float rstd = 1.0f / sqrtf(rv + c.eps);
+        float sc = c.params[c.bn_gamma[id] + k] * rstd;
+        c.bnf(id, BN_SCALE)[k] = sc;
+        c.bnf(id, BN_SHIFT)[k] = c.params[c.bn_beta[id] + k] - rm * sc;
+        c.bnf(id, BN_MEAN)[k] = rm;
+        c.bnf(id, BN_RSTD)[k] = rstd;
+      }
+    }
+  }
+}
+
+int launch_param_prep(const Ctx& c, cudaStream_t s) {
+  k_param_prep<<<c.L + 2 + 3 + 1, dim3(32, 8), 0, s>>>(c);
+  CAL_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace cal

@@ -52,7 +52,7 @@ extern "C" {
 typedef struct {
   int32_t model;               /* CAL_MODEL_* */
   int32_t num_features;        /* F */
-  int32_t hidden;              /* H: multiple of 32, 32..256 */
+  int32_t hidden;              /* H: 32, 64 or 128 */
   int32_t num_classes;         /* C: 2..32 */
   int32_t layers;              /* L: 1..CAL_MAX_LAYERS */
   int32_t heads;               /* GAT heads (model.py:319), H % heads == 0 */
@@ -111,23 +111,60 @@ typedef struct {
   int64_t edge_stride;         /* elements between edge_index[0,0] and edge_index[1,0] */
 } cal_batch;
 
-/* Named workspace regions (for tests / debugging / saved activations). */
+/* Named workspace regions (for tests / debugging / saved activations).
+ * EP = max_edges + max_nodes (edge slots after self-loop surgery).  "in-CSR
+ * position" p = index into the by-target CSR; every per-edge float array is
+ * stored in that order. */
 enum cal_ws_region {
-  CAL_WS_STATUS = 0,   /* int32[4]: [0] = status bits */
-  CAL_WS_IN_PTR, CAL_WS_IN_SRC, CAL_WS_IN_EID, CAL_WS_OUT_PTR, CAL_WS_OUT_DST, CAL_WS_OUT_EID,
-  CAL_WS_GRAPH_PTR, CAL_WS_NORM_IN, CAL_WS_NORM_OUT,
-  CAL_WS_X,            /* f32[L+1][maxN][H]: x_1 .. x_{L+1} */
-  CAL_WS_T,            /* f32[2][maxN][H]: transformed features (t_c, t_o kept for backward) */
-  CAL_WS_XCO,          /* f32[2][maxN][H]: relu(context/objects conv) */
-  CAL_WS_NODE_ATT,     /* f32[maxN][2] */
-  CAL_WS_EDGE_ATT,     /* f32[maxE][2] */
-  CAL_WS_WNORM_IN,     /* f32[2][maxE+maxN] */
-  CAL_WS_POOLED,       /* f32[3][maxB][2H]: xc_g, xo_g, mix */
-  CAL_WS_LOGP,         /* f32[3][maxB][C]: the three outputs (log-probabilities) */
-  CAL_WS_LOSS,         /* f32[8]: loss, c_loss, o_loss, co_loss, correct_o, correct_c, correct_co, 0 */
-  CAL_WS_BN_AFFINE,    /* f32[CAL_MAX_BN][4][256]: scale, shift, mean, rstd per BN */
+  CAL_WS_STATUS = 0,   /* i32[4]: [0] = status bits (CAL_ST_*) */
+  CAL_WS_COUNTERS,     /* u32[64]: self-resetting grid arrival counters */
+  CAL_WS_IN_PTR,       /* i32[maxN+1] CSR by target (edge_index[1]) incl. appended self loops */
+  CAL_WS_IN_SRC,       /* i32[EP] source node of in-CSR position p */
+  CAL_WS_IN_KEY,       /* i32[EP] edge_index column e (< E) or E + node for the appended loop */
+  CAL_WS_IN_NORM,      /* f32[EP] unweighted GCN norm deg^-1/2[row] * deg^-1/2[col] */
+  CAL_WS_OUT_PTR,      /* i32[maxN+1] CSR by source (edge_index[0]) */
+  CAL_WS_OUT_DST,      /* i32[EP] */
+  CAL_WS_OUT_POS,      /* i32[EP] in-CSR position of the same edge */
+  CAL_WS_OUT_KEY,      /* i32[EP] */
+  CAL_WS_CNT_IN, CAL_WS_CNT_OUT,   /* i32[maxN] scratch */
+  CAL_WS_GRAPH_PTR,    /* i32[maxB+1] first node of every graph */
+  CAL_WS_NODE_GRAPH,   /* i32[maxN] batch as int32 */
+  CAL_WS_PERM,         /* i32[maxB] random_idx (identity when the batch gives none) */
+  CAL_WS_INVPERM,      /* i32[maxB] */
+  CAL_WS_DIS,          /* f32[maxN] unweighted deg^-1/2 */
+  CAL_WS_X,            /* f32[L+1][maxN][H]: x_1 .. x_{L+1} (post-ReLU layer outputs) */
+  CAL_WS_NODE_ATT,     /* f32[maxN][2] softmax(node_att_mlp(x)) */
+  CAL_WS_PQ,           /* f32[maxN][4] edge_att_mlp split: x W_e[:, :H]^T (2), x W_e[:, H:]^T (2) */
+  CAL_WS_EDGE_ATT,     /* f32[EP][2] edge_att by in-CSR position (appended loops hold 1,1) */
+  CAL_WS_DISW,         /* f32[maxN][2] weighted deg^-1/2 of the causal / shortcut norm */
+  CAL_WS_AGG,          /* f32[2][maxN][H] normalised aggregate entering context/objects weight */
+  CAL_WS_Z,            /* f32[2][maxN][H] relu(context_convs), relu(objects_convs) */
+  CAL_WS_POOLED,       /* f32[2][maxB][H] global_add_pool of the two */
+  CAL_WS_H1,           /* f32[3][maxB][H] relu(fc1_*(bn(.))) of the c / o / co readouts */
+  CAL_WS_LOGP,         /* f32[3][maxB][C] the three outputs (log-probabilities) */
+  CAL_WS_LOSS,         /* f32[8]: loss, c_loss, o_loss, co_loss, correct_c, correct_o, correct_co, 0 */
+  CAL_WS_BN,           /* f32[CAL_MAX_BN+1][6][KMAX]: scale, shift, mean, rstd, c1, c2 per BatchNorm */
+  CAL_WS_STATP,        /* f64 partial sums of the BatchNorm reductions */
+  CAL_WS_WT,           /* f32 transposed copies of conv / fc1 weights */
+  CAL_WS_GAT,          /* f32 GATConv scratch: x' [L][maxN][H], alpha_src/dst [L][maxN][2*heads], softmax stats */
+  CAL_WS_DLOGIT,       /* f32[3][maxB][C] */
+  CAL_WS_DH,           /* f32[3][maxB][H] */
+  CAL_WS_DU,           /* f32[3][maxB][2H] */
+  CAL_WS_DPOOL,        /* f32[2][maxB][H] */
+  CAL_WS_DAGG,         /* f32[2][maxN][H] */
+  CAL_WS_DYM,          /* f32[2][maxN][H] */
+  CAL_WS_DNRM,         /* f32[EP][2] */
+  CAL_WS_DT,           /* f32[EP][2] */
+  CAL_WS_DP,           /* f32[maxN][2] */
+  CAL_WS_D,            /* f32[2][maxN][H] ping-pong gradient w.r.t. BatchNorm outputs */
+  CAL_WS_GPART,        /* f32 per-CTA partial parameter gradients */
   CAL_WS_REGION_COUNT
 };
+
+/* status bits */
+#define CAL_ST_BAD_NODE 1    /* edge endpoint outside [0, N) */
+#define CAL_ST_BAD_BATCH 2   /* batch not sorted / outside [0, B) */
+#define CAL_ST_CAPACITY 4    /* N / E / B exceed the workspace capacities */
 
 /* flags for cal_causal_forward */
 #define CAL_F_TRAIN 1        /* BatchNorm batch statistics + running-stat update; GAT dropout */
@@ -176,19 +213,9 @@ int cal_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                   float weight_decay, float grad_scale, void* stream);
 int cal_adam_tick(int32_t* step, void* stream);   /* ++*step on the device */
 
-/* ---- operator-level entry points (used by the unit parity tests) ---- */
-
-/* GCNConv.forward, gcn_conv.py:72-104, on prepared structure:
- * out = [relu]( sum_{e: col_e = i} norm_e * (x W)[row_e] + bias ).
- * `edge_weight` f32[E] (may be NULL = unweighted) follows gcn_conv.py:44-70. */
-int cal_gcn_conv_forward(const cal_model_desc* m, const cal_caps* caps, const cal_batch* b,
-                         const float* x, int in_channels, const float* weight, const float* bias,
-                         const float* edge_weight, int relu, float* out,
-                         void* workspace, size_t ws_bytes, void* stream);
-
-/* global_add_pool, model.py:115-116: out[b] = sum_{batch_n = b} x[n]. */
-int cal_global_add_pool(const cal_model_desc* m, const cal_caps* caps, const cal_batch* b,
-                        const float* x, float* out, void* workspace, size_t ws_bytes, void* stream);
+/* Poll the status word written by cal_prep (synchronises the stream): returns the CAL_ST_* bits,
+ * or a negative CAL_E* / positive cudaError_t. */
+int cal_read_status(const cal_model_desc* m, const cal_caps* caps, const void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

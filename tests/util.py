@@ -61,3 +61,90 @@ class GoldenCase:
 def rel_err(a, b):
     a, b = a.double(), b.double()
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def oracle_trace(net, data, perm, loss_weights=(0.5, 1.0, 0.5)):
+    """Run the oracle's forward (+ loss + backward when net.training) step by step, keeping every
+    intermediate the CUDA workspace also holds.  Returns (dict of tensors, dict of their grads)."""
+    import torch.nn.functional as F
+    from oracle import cal_oracle as O
+    t, keep = {}, {}
+
+    def rec(name, v):
+        t[name] = v
+        if v.requires_grad:
+            v.retain_grad()
+            keep[name] = v
+        return v
+
+    x = data.x if getattr(data, "x", None) is not None else data.feat
+    ei, batch = data.edge_index, data.batch
+    row, col = ei
+    x = net.bn_feat(x)
+    x = rec("x1", F.relu(net.conv_feat(x, ei)))
+    for i, conv in enumerate(net.convs):
+        y = rec("y%d" % (i + 1), net.bns_conv[i](x))
+        x = rec("x%d" % (i + 2), F.relu(conv(y, ei)))
+    edge_rep = torch.cat([x[row], x[col]], dim=-1)
+    if net.without_edge_attention:
+        edge_att = 0.5 * torch.ones(edge_rep.shape[0], 2)
+    else:
+        edge_att = F.softmax(net.edge_att_mlp(edge_rep), dim=-1)
+    rec("edge_att", edge_att)
+    if net.without_node_attention:
+        node_att = 0.5 * torch.ones(x.shape[0], 2)
+    else:
+        node_att = F.softmax(net.node_att_mlp(x), dim=-1)
+    rec("node_att", node_att)
+    xc = node_att[:, 0].view(-1, 1) * x
+    xo = node_att[:, 1].view(-1, 1) * x
+    yc = rec("yc", net.bnc(xc))
+    yo = rec("yo", net.bno(xo))
+    zc = rec("zc", F.relu(net.context_convs(yc, ei, edge_att[:, 0])))
+    zo = rec("zo", F.relu(net.objects_convs(yo, ei, edge_att[:, 1])))
+    B = int(data.y.numel())
+    gc = rec("gc", O.global_add_pool(zc, batch, B))
+    go = rec("go", O.global_add_pool(zo, batch, B))
+    outs = [net._readout(gc, "c"), net._readout(go, "o"), net.random_readout_layer(gc, go, True, perm)]
+    for n, o in zip(("c", "o", "co"), outs):
+        rec("logp_" + n, o)
+    if net.training:
+        loss, *_ = O.causal_loss(*outs, data.y, net.num_classes, *loss_weights)
+        t["loss"] = loss.detach()
+        net.zero_grad()
+        loss.backward()
+    grads = {k: v.grad for k, v in keep.items() if v.grad is not None}
+    return {k: v.detach() for k, v in t.items()}, grads
+
+
+def ref_prep(edge_index, batch, num_graphs):
+    """numpy restatement of the structure the reference builds inside every GCNConv.norm call
+    (gcn_conv.py:56-57: remove_self_loops, then add_self_loops appends [i, i] LAST) arranged as the
+    two CSR orderings cal_prep emits; within a row entries follow edge_index column order, which is
+    the order the CPU scatter_add accumulates in."""
+    ei = np.asarray(edge_index)
+    N = int(np.asarray(batch).shape[0])
+    E = ei.shape[1]
+    keep = ei[0] != ei[1]
+    ids = np.nonzero(keep)[0]
+    rows = np.concatenate([ei[0][ids], np.arange(N)])
+    cols = np.concatenate([ei[1][ids], np.arange(N)])
+    keys = np.concatenate([ids, E + np.arange(N)])
+    o_in = np.lexsort((keys, cols))
+    o_out = np.lexsort((keys, rows))
+    in_ptr = np.zeros(N + 1, np.int32)
+    np.add.at(in_ptr, cols + 1, 1)
+    in_ptr = np.cumsum(in_ptr).astype(np.int32)
+    out_ptr = np.zeros(N + 1, np.int32)
+    np.add.at(out_ptr, rows + 1, 1)
+    out_ptr = np.cumsum(out_ptr).astype(np.int32)
+    pos_of_key = {int(k): p for p, k in enumerate(keys[o_in])}
+    out_pos = np.array([pos_of_key[int(k)] for k in keys[o_out]], np.int32)
+    b = np.asarray(batch)
+    graph_ptr = np.searchsorted(b, np.arange(num_graphs + 1), side="left").astype(np.int32)
+    deg = np.bincount(rows, minlength=N).astype(np.float32)
+    dis = (deg ** np.float32(-0.5)).astype(np.float32)
+    return dict(in_ptr=in_ptr, in_src=rows[o_in].astype(np.int32), in_key=keys[o_in].astype(np.int32),
+                out_ptr=out_ptr, out_dst=cols[o_out].astype(np.int32), out_key=keys[o_out].astype(np.int32),
+                out_pos=out_pos, graph_ptr=graph_ptr, dis=dis,
+                in_norm=(dis[rows[o_in]] * dis[cols[o_in]]).astype(np.float32))
