@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""Benchmark of the CAL hot path: graphs/sec of one CausalGCN training step
+(prep + forward + KL/NLL loss + backward + [gradient all-reduce] + Adam; train_causal.py:171-192)
+on synthetic SPMotif-style batches (BASELINE.json configs[1]: bias 0.9, 3 layers, hidden 128,
+batch 128 per GPU, fp32).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+
+Prints ONE JSON line (rank 0).  `value` = whole-job graphs/s with the packed batches resident in
+HBM; `e2e` = the same through Trainer.step_host with pinned HOST batches (H2D copy of every batch
+and D2H read of the loss parts inside the timed region); `roofline` = the dominant kernel's
+algorithmic bytes / its live CUDA-event duration against the measured HBM peak; `cpu_baseline` =
+the oracle timed on this box's host cores."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "graphs_per_sec_train_step"
+UNIT = "graphs/s"
+L2_BYTES = 126 * 2 ** 20
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="cal_b200", choices=["cal_b200", "reference"])
+    ap.add_argument("--workload", default="spmotif", choices=["spmotif", "spmotif_refsize", "mutag", "large"])
+    ap.add_argument("--model", default="CausalGCN", choices=["CausalGCN", "CausalGAT"])
+    ap.add_argument("--batch", type=int, default=0, help="graphs per GPU per step (default: the workload's)")
+    ap.add_argument("--pool", type=int, default=0, help="distinct graphs generated per rank")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue kernels eagerly instead of CUDA-graph replay")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--stages", action="store_true", help="also print the per-stage timing table to stderr")
+    ap.add_argument("--resident", type=int, default=0, help="number of distinct device-resident batches (default: > L2)")
+    ap.add_argument("--no-stage-timing", action="store_true", help="skip the live per-stage timing / roofline")
+    return ap.parse_args()
+
+
+def model_args(hidden=128, layers=3):
+    return argparse.Namespace(layers=layers, hidden=hidden, with_random=True, without_node_attention=False,
+                              without_edge_attention=False, fc_num="222", cat_or_add="add", c=0.5, o=1.0, co=0.5,
+                              eval_random=False)
+
+
+def build_batches(workload, batch_size, n_batches, pool, seed):
+    """`n_batches` distinct batches, each `batch_size` graphs sampled (without replacement inside a
+    batch) from a pool of `pool` seeded SPMotif-style graphs."""
+    from cal_b200.data import CONFIGS, Batch, make_dataset
+    cfg = dict(CONFIGS[workload])
+    cfg.pop("batch_size")
+    ds = make_dataset(pool, seed=seed, bias=0.9, **cfg)
+    rng = np.random.RandomState(seed + 1)
+    out = []
+    for _ in range(n_batches):
+        idx = rng.choice(pool, size=batch_size, replace=False)
+        out.append(Batch.from_data_list([ds[i] for i in idx]))
+    return out, cfg
+
+
+class ClockSampler:
+    """SM clock / throttle reasons sampled with NVML while the timed region runs."""
+
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index, period=0.02):
+        self.index, self.period = index, period
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+
+    def summary(self):
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
+
+
+def visible_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic bytes (DESIGN.md "Kernels and rooflines")
+# ------------------------------------------------------------------------------------------------
+
+def algorithmic_bytes(stage, N, E1, B, H, F, C, L, P):
+    """Bytes a stage must move at minimum for a batch with N nodes, E1 = kept edges + N appended
+    self loops, B graphs.  fp32 activations, int32 CSR.  One neighbour row per edge per propagate."""
+    NH, EH = 4 * N * H, 4 * E1 * H
+    if stage == "prep":
+        return 16 * (E1 - N) + 8 * N + 4 * 7 * E1 + 4 * 6 * N           # edge_index + batch in; 2 CSRs + norm out
+    if stage == "param_prep":
+        return 8 * ((L + 2) * H * H + 3 * H * H)
+    if stage == "feat":
+        return 4 * N * F + NH + 4 * F * H
+    if stage.startswith("layer_") and not stage.endswith("_bwd"):
+        return EH + NH + 12 * E1 + 4 * N + 4 * H * H
+    if stage == "edge_att":
+        return 16 * N + 16 * E1 + 8 * E1 + 8 * E1 + 8 * N
+    if stage == "masked_convs":
+        return 2 * (EH + 2 * NH + 12 * E1 + 4 * N + 4 * H * H)
+    if stage == "readout":
+        return 2 * NH + 8 * B * H * 4 + 3 * 4 * H * H
+    if stage == "readout_bwd":
+        return 12 * B * H * 4 + 3 * 8 * H * H
+    if stage == "masked_gemm_bwd":
+        return 2 * (3 * NH + 8 * H * H)
+    if stage == "masked_gather_bwd":
+        return 2 * (EH + 2 * NH + 16 * E1)
+    if stage == "norm_bwd":
+        return 2 * 40 * E1
+    if stage == "att_bwd":
+        return 4 * NH + 8 * E1
+    if stage.endswith("_bwd") and stage.startswith("layer_"):
+        return EH + 4 * NH + 8 * E1 + 8 * H * H
+    if stage == "feat_bwd":
+        return 2 * NH + 4 * N * F + 4 * F * H
+    if stage == "grad_reduce":
+        return 8 * P
+    if stage == "adam":
+        return 28 * P
+    return 0
+
+
+def step_algorithmic_bytes(N, E1, B, H, F, L, P):
+    """A = 16(L+3)NH + 8H(L+2)E' + 8HE' + (4NF + 16E + 8N + 8B) + 12P + 32BH."""
+    E = E1 - N
+    return 16 * (L + 3) * N * H + 8 * H * (L + 2) * E1 + 8 * H * E1 + (4 * N * F + 16 * E + 8 * N + 8 * B) + 12 * P + 32 * B * H
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (reference op order) on the host cores
+# ------------------------------------------------------------------------------------------------
+
+def cpu_train_steps(batches, F, C, hidden, layers, steps, warmup, seconds=None, threads=None, model="CausalGCN"):
+    """Times oracle train steps (forward + loss + backward + torch Adam).  -> (graphs/s, steps, s, threads)."""
+    import random
+    from oracle import cal_oracle
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(666)
+    random.seed(666)
+    args = model_args(hidden, layers)
+    net = getattr(cal_oracle, model)(F, C, args)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    i = 0
+    for _ in range(warmup):
+        cal_oracle.train_step(net, batches[i % len(batches)])
+        opt.step()
+        i += 1
+    graphs, done = 0, 0
+    t0 = time.perf_counter()
+    while True:
+        b = batches[i % len(batches)]
+        cal_oracle.train_step(net, b)
+        opt.step()
+        graphs += int(b.num_graphs)
+        done += 1
+        i += 1
+        el = time.perf_counter() - t0
+        if (steps is not None and done >= steps) or (seconds is not None and el >= seconds):
+            break
+    return graphs / el, done, el, torch.get_num_threads()
+
+
+def run_reference(a, rank, world):
+    """`--impl reference`: the reference's own CPU implementation of the path.  torch_geometric /
+    torch_scatter are not installable in this image, so the timed code is the oracle
+    port, which replays the reference's op sequence (index_select -> mul -> index_add_, norm
+    recomputed in every GCNConv) with all host threads.  Rank 0 only."""
+    if rank != 0:
+        return
+    from cal_b200.data import CONFIGS
+    bs = a.batch or CONFIGS[a.workload]["batch_size"]
+    batches, cfg = build_batches(a.workload, bs, 16, max(a.pool, 16 * bs), 666)
+    F, C = batches[0].feat.size(1), cfg["num_classes"]
+    cores = os.cpu_count() or 1
+    gps, done, el, thr = cpu_train_steps(batches, F, C, 128, 3, a.steps, a.warmup, threads=cores, model=a.model)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gps, "unit": UNIT, "n_gpus": a.gpus, "steps": done,
+        "warmup": a.warmup, "ms_per_step": 1e3 * el / done, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, bs, batches, "host memory (CPU run)"),
+        "cpu_baseline": {"value": gps, "unit": UNIT, "cores": thr, "kind": "port",
+                         "sample": "%d train steps of %d graphs, %d torch threads" % (done, bs, thr)},
+        "e2e": {"value": gps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a, bs, batches, residency):
+    n = float(np.mean([b.batch.numel() for b in batches]))
+    e = float(np.mean([b.edge_index.size(1) for b in batches]))
+    return {"workload": "%s SPMotif-style synthetic (bias 0.9), %s 3 layers hidden 128, batch %d per GPU"
+                        % (a.workload, a.model, bs),
+            "model_step": "prep + forward + KL/NLL loss + backward + grad all-reduce (N>1) + Adam",
+            "avg_nodes_per_batch": n, "avg_edge_columns_per_batch": e, "graphs_per_batch": bs,
+            "features": int(batches[0].feat.size(1)), "hidden": 128, "layers": 3, "parallelism": "dp%d" % a.gpus,
+            "cache": residency}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+
+def run_gpu(a, rank, local_rank, world):
+    import cal_b200
+    from cal_b200.data import CONFIGS
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the cal_b200 arm has no CPU fallback); use --impl reference")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    bs = a.batch or CONFIGS[a.workload]["batch_size"]
+    # enough distinct resident batches that the inputs of the timed region exceed L2 (no batch is
+    # reused within ~L2 worth of input bytes) -- the "inputs larger than L2" timing rule
+    probe, cfg = build_batches(a.workload, bs, 2, 4 * bs, 666 + rank)
+    caps_probe = cal_b200.batch_caps(probe, slack=1.15)
+    lay_probe = cal_b200.PackedLayout(*caps_probe, probe[0].feat.size(1))
+    n_res = a.resident or int(min(max(L2_BYTES // lay_probe.nbytes + 8, 16), 1024))
+    pool = a.pool or max(8192, 4 * bs)
+    batches, cfg = build_batches(a.workload, bs, n_res, pool, 666 + rank)
+    F, C = int(batches[0].feat.size(1)), cfg["num_classes"]
+    torch.manual_seed(666)
+    import random
+    random.seed(666 + rank)
+    if a.model == "CausalGCN":
+        net = cal_b200.CausalGCN(F, C, model_args()).to(dev)
+    else:
+        net = cal_b200.CausalGAT(F, C, model_args()).to(dev)
+    net.train()
+    tr = cal_b200.Trainer(net, cal_b200.batch_caps(batches), lr=1e-3, process_group=True if world > 1 else None,
+                          use_graph=not a.no_graph)
+    hosts = [tr.pack(b) for b in batches[:min(64, n_res)]]               # pinned host copies (e2e)
+    resident = [tr.pack(b).to(dev) for b in batches]
+    resident_bytes = sum(int(r.numel()) for r in resident)
+    graphs_per_step = bs
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # capture one graph per resident batch (outside the timed region), then W warm-up steps
+    for r in resident:
+        tr.step(r)
+    for i in range(a.warmup):
+        tr.step(resident[i % n_res])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(visible_gpu_index(local_rank)) as clk:
+        barrier()
+        e0.record()
+        for i in range(a.steps):
+            tr.step(resident[(a.warmup + i) % n_res])
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = a.steps * graphs_per_step * world / (ms * 1e-3)
+    loss_after = tr.metrics().cpu().tolist()
+    launches = int(tr.launches_per_step) * a.steps
+
+    # ---- end to end: pinned host batch -> H2D -> step -> loss parts D2H, every step ----
+    e2e = None
+    if not a.no_e2e:
+        for i in range(max(3, a.warmup // 2)):
+            tr.step_host(hosts[i % len(hosts)])
+        barrier()
+        e0.record()
+        for i in range(a.steps):
+            tr.step_host(hosts[i % len(hosts)], sync=True)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e = float(t.item())
+        e2e = {"value": a.steps * graphs_per_step * world / (ms_e * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(tr.layout.nbytes), "d2h_bytes_per_step": 32,
+               "ms_per_step": ms_e / a.steps,
+               "api": "Trainer.step_host(pinned packed batch): cudaMemcpyAsync H2D + captured step + loss D2H + stream sync"}
+
+    # ---- live per-stage timing + roofline of the dominant kernel (rank 0) ----
+    roofline, stage_tab = None, None
+    if rank == 0 and not a.no_stage_timing:
+        b0 = batches[0]
+        st = tr.profile_stages(resident[0], reps=20)
+        eng = tr.eng
+        N = int(b0.batch.numel())
+        ei = b0.edge_index
+        E1 = int((ei[0] != ei[1]).sum()) + N
+        P = int(eng.total)
+        stage_tab = []
+        for name, nl, t_ms in st:
+            ab = algorithmic_bytes(name, N, E1, bs, eng.H, eng.F, eng.C, eng.L, P)
+            stage_tab.append({"stage": name, "launches": nl, "us": 1e3 * t_ms, "alg_bytes": ab,
+                              "gbs": ab / (t_ms * 1e-3) / 1e9 if t_ms > 0 else None})
+        top = max(stage_tab, key=lambda r: r["us"])
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        A_step = step_algorithmic_bytes(N, E1, bs, eng.H, eng.F, eng.L, P)
+        roofline = {"bound": "hbm", "kernel": top["stage"], "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": top["gbs"] / peak, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
+                    "kernel_us": top["us"], "kernel_alg_bytes": top["alg_bytes"],
+                    "step_alg_bytes": A_step, "step_achieved_gbs": A_step * a.steps / (ms * 1e-3) / 1e9 / 1.0,
+                    "step_frac": A_step * a.steps / (ms * 1e-3) / 1e9 / peak,
+                    "sum_stage_us": sum(r["us"] for r in stage_tab)}
+        if a.stages:
+            for r in stage_tab:
+                print("%-20s launches %d  %8.2f us  %10d B  %8.1f GB/s" % (r["stage"], r["launches"], r["us"],
+                                                                          r["alg_bytes"], r["gbs"] or 0), file=sys.stderr)
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        gps, done, el, thr = cpu_train_steps(batches[:16], F, C, 128, 3, None, 3, seconds=a.cpu_seconds, threads=cores,
+                                             model=a.model)
+        cpu = {"value": gps, "unit": UNIT, "cores": thr, "kind": "port",
+               "sample": "%d oracle train steps of %d graphs in %.1f s (same workload, %d torch threads)" % (done, bs, el, thr)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a, bs, batches,
+                                      "inputs larger than L2: %d distinct resident batches (%.0f MB) cycled; "
+                                      "workspace reused" % (n_res, resident_bytes / 2 ** 20)),
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
+            "launches_per_step": int(tr.launches_per_step), "cuda_graph": not a.no_graph,
+            "roofline": roofline, "cpu_baseline": cpu, "stages": stage_tab,
+            "loss_after": loss_after[:4],
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+    if world != a.gpus and world == 1 and a.gpus > 1:
+        raise SystemExit("bench.py: --gpus %d needs a torchrun launch (WORLD_SIZE=%d)" % (a.gpus, world))
+    run_gpu(a, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -28,7 +28,14 @@ WS = {n: i for i, n in enumerate(WS_REGIONS)}
 EXPORTS = [
     "cal_abi_version", "cal_error_string", "cal_workspace_bytes", "cal_workspace_region", "cal_prep",
     "cal_causal_forward", "cal_causal_backward", "cal_adam_step", "cal_adam_tick", "cal_read_status",
+    "cal_launch_count", "cal_stage_count", "cal_stage_name",
 ]
+CAL_PASS_FORWARD, CAL_PASS_BACKWARD = 0, 1
+
+
+def stages_flag(lo, hi):
+    """CAL_F_STAGES(lo, hi) of include/cal_b200.h."""
+    return ((lo + 1) << 8) | ((hi + 1) << 16)
 
 
 class ModelDesc(C.Structure):
@@ -106,11 +113,16 @@ def load():
                                        C.c_void_p, C.c_size_t, C.c_void_p]
     lib.cal_causal_backward.restype = C.c_int
     lib.cal_causal_backward.argtypes = [P(ModelDesc), P(Caps), P(ParamOffsets), C.c_void_p, P(Batch),
-                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+                                        C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.cal_adam_step.restype = C.c_int
     lib.cal_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
-                                  C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                  C.c_float, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                   C.c_void_p]
+    lib.cal_launch_count.restype = C.c_uint64
+    lib.cal_stage_count.restype = C.c_int
+    lib.cal_stage_count.argtypes = [P(ModelDesc), C.c_int]
+    lib.cal_stage_name.restype = C.c_char_p
+    lib.cal_stage_name.argtypes = [P(ModelDesc), C.c_int, C.c_int]
     lib.cal_adam_tick.restype = C.c_int
     lib.cal_adam_tick.argtypes = [C.c_void_p, C.c_void_p]
     lib.cal_read_status.restype = C.c_int

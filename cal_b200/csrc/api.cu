@@ -1,10 +1,16 @@
 // api.cu -- the C ABI of libcal_b200.so (include/cal_b200.h): argument checks, context
 // construction and the launch sequences of the forward and backward passes.
+#include <stdio.h>
 #include <string.h>
+
+#include <atomic>
 
 #include "internal.cuh"
 
 namespace cal {
+
+static std::atomic<unsigned long long> g_launches{0};
+void note_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 namespace {
 
@@ -14,6 +20,14 @@ __global__ void k_copy_logp(const Ctx c, float* __restrict__ out) {
     const int h = i / (B * C), r = i - h * B * C;
     out[i] = c.logp[(size_t)h * c.Bm * C + r];
   }
+}
+
+// CAL_F_STAGES(lo, hi) -> [lo, hi] clipped to the pass; absent -> unchanged (whole pass)
+void stage_range(int flags, int* lo, int* hi) {
+  const int a = (flags >> 8) & 0xff, b = (flags >> 16) & 0xff;
+  if (a == 0 && b == 0) return;
+  if (a > 0) *lo = imax(*lo, a - 1);
+  if (b > 0) *hi = imin(*hi, b - 1);
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -184,6 +198,36 @@ extern "C" {
 
 int cal_abi_version(void) { return CAL_ABI_VERSION; }
 
+uint64_t cal_launch_count(void) { return (uint64_t)g_launches.load(std::memory_order_relaxed); }
+
+int cal_stage_count(const cal_model_desc* m, int pass) {
+  if (validate_model(m) != CAL_OK) return CAL_EINVAL;
+  if (pass == CAL_PASS_FORWARD) return m->layers + 6;
+  if (pass == CAL_PASS_BACKWARD) return m->layers + 7;
+  return CAL_EINVAL;
+}
+
+const char* cal_stage_name(const cal_model_desc* m, int pass, int stage) {
+  static thread_local char buf[32];
+  if (validate_model(m) != CAL_OK || stage < 0) return "";
+  const int L = m->layers;
+  if (pass == CAL_PASS_FORWARD) {
+    if (stage == 0) return "param_prep";
+    if (stage == 1) return "feat";
+    if (stage < 2 + L) { snprintf(buf, sizeof buf, "layer_%d", stage - 2); return buf; }
+    const char* tail[] = {"edge_att", "masked_convs", "readout", "copy_out"};
+    return stage - 2 - L < 4 ? tail[stage - 2 - L] : "";
+  }
+  if (pass == CAL_PASS_BACKWARD) {
+    const char* head[] = {"readout_bwd", "masked_gemm_bwd", "masked_gather_bwd", "norm_bwd", "att_bwd"};
+    if (stage < 5) return head[stage];
+    if (stage < 5 + L) { snprintf(buf, sizeof buf, "layer_%d_bwd", L - 1 - (stage - 5)); return buf; }
+    if (stage == 5 + L) return "feat_bwd";
+    if (stage == 6 + L) return "grad_reduce";
+  }
+  return "";
+}
+
 const char* cal_error_string(int code) {
   if (code > 0) return cudaGetErrorString((cudaError_t)code);
   switch (code) {
@@ -257,24 +301,28 @@ int cal_causal_forward(const cal_model_desc* m, const cal_caps* caps, const cal_
   c.train = train;
   c.with_loss = (flags & CAL_F_LOSS) != 0;
   cudaStream_t s = (cudaStream_t)stream;
-  if ((rc = launch_param_prep(c, s)) != 0) return rc;
-  if ((rc = launch_feat_forward(c, s)) != 0) return rc;
-  for (int l = 0; l < c.L; ++l) {
-    rc = c.model == CAL_MODEL_GAT ? launch_gat_forward(c, l, s) : launch_conv_forward(c, l, s);
+  const int L = c.L;
+  int lo = 0, hi = L + 5;
+  stage_range(flags, &lo, &hi);
+  for (int st = lo; st <= hi; ++st) {
+    if (st == 0) rc = launch_param_prep(c, s);
+    else if (st == 1) rc = launch_feat_forward(c, s);
+    else if (st < 2 + L) rc = c.model == CAL_MODEL_GAT ? launch_gat_forward(c, st - 2, s) : launch_conv_forward(c, st - 2, s);
+    else if (st == 2 + L) rc = launch_edge_att(c, s);
+    else if (st == 3 + L) rc = launch_masked_forward(c, s);
+    else if (st == 4 + L) rc = launch_heads_forward(c, c.with_loss, s);
+    else if (st == 5 + L && out_logp != nullptr) {
+      k_copy_logp<<<imax(1, imin(ceil_div(3 * c.Bm * c.C, 256), kSMs)), 256, 0, s>>>(c, out_logp);
+      note_launches(1);
+      CAL_CUDA_CHECK_LAUNCH();
+    }
     if (rc != 0) return rc;
-  }
-  if ((rc = launch_edge_att(c, s)) != 0) return rc;
-  if ((rc = launch_masked_forward(c, s)) != 0) return rc;
-  if ((rc = launch_heads_forward(c, c.with_loss, s)) != 0) return rc;
-  if (out_logp != nullptr) {
-    k_copy_logp<<<imax(1, imin(ceil_div(3 * c.Bm * c.C, 256), kSMs)), 256, 0, s>>>(c, out_logp);
-    CAL_CUDA_CHECK_LAUNCH();
   }
   return CAL_OK;
 }
 
 int cal_causal_backward(const cal_model_desc* m, const cal_caps* caps, const cal_param_offsets* po,
-                        const float* params, const cal_batch* b, const float* grad_logp, float* grads,
+                        const float* params, const cal_batch* b, const float* grad_logp, float* grads, int flags,
                         void* workspace, size_t ws_bytes, void* stream) {
   int rc = validate_model(m);
   if (rc != CAL_OK) return rc;
@@ -291,17 +339,22 @@ int cal_causal_backward(const cal_model_desc* m, const cal_caps* caps, const cal
   c.train = 1;
   c.grad_logp = grad_logp;
   cudaStream_t s = (cudaStream_t)stream;
-  if ((rc = launch_heads_backward(c, s)) != 0) return rc;
-  if ((rc = launch_masked_bwd_gemm(c, s)) != 0) return rc;
-  if ((rc = launch_masked_bwd_gather(c, s)) != 0) return rc;
-  if ((rc = launch_norm_backward(c, s)) != 0) return rc;
-  if ((rc = launch_att_backward(c, s)) != 0) return rc;
-  for (int l = c.L - 1; l >= 0; --l) {
-    rc = c.model == CAL_MODEL_GAT ? launch_gat_backward(c, l, s) : launch_conv_backward(c, l, s);
+  const int L = c.L;
+  int lo = 0, hi = L + 6;
+  stage_range(flags, &lo, &hi);
+  for (int st = lo; st <= hi; ++st) {
+    if (st == 0) rc = launch_heads_backward(c, s);
+    else if (st == 1) rc = launch_masked_bwd_gemm(c, s);
+    else if (st == 2) rc = launch_masked_bwd_gather(c, s);
+    else if (st == 3) rc = launch_norm_backward(c, s);
+    else if (st == 4) rc = launch_att_backward(c, s);
+    else if (st < 5 + L) {
+      const int l = L - 1 - (st - 5);
+      rc = c.model == CAL_MODEL_GAT ? launch_gat_backward(c, l, s) : launch_conv_backward(c, l, s);
+    } else if (st == 5 + L) rc = launch_feat_backward(c, s);
+    else if (st == 6 + L) rc = launch_grad_reduce(c, s);
     if (rc != 0) return rc;
   }
-  if ((rc = launch_feat_backward(c, s)) != 0) return rc;
-  if ((rc = launch_grad_reduce(c, s)) != 0) return rc;
   return CAL_OK;
 }
 

@@ -306,24 +306,28 @@ __global__ void __launch_bounds__(256) k_att_bwd(const Ctx c) {
 
 int launch_edge_att(const Ctx& c, cudaStream_t s) {
   k_edge_att<<<imax(1, imin(ceil_div(c.Nm, 128), 8 * kSMs)), 128, 0, s>>>(c);
+  note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }
 
 int launch_masked_bwd_gather(const Ctx& c, cudaStream_t s) {
   CAL_DISPATCH_VEC(c.H, { k_masked_bwd_gather<VEC><<<dim3(c.g_row / 2 > 0 ? c.g_row / 2 : 1, 2), 256, 0, s>>>(c); });
+  note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }
 
 int launch_norm_backward(const Ctx& c, cudaStream_t s) {
   k_norm_bwd<<<imax(1, imin(ceil_div(c.Nm, 128), 8 * kSMs)), 128, 0, s>>>(c);
+  note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }
 
 int launch_att_backward(const Ctx& c, cudaStream_t s) {
   CAL_DISPATCH_VEC(c.H, { k_att_bwd<VEC><<<c.g_row, 256, 0, s>>>(c); });
+  note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }

@@ -676,6 +676,7 @@ int set_smem(K kernel, size_t bytes) {
 
 int launch_feat_forward(const Ctx& c, cudaStream_t s) {
   if (c.train) k_feat_stats<<<c.g_tile, 256, 0, s>>>(c);
+  note_launches(c.train ? 2 : 1);
   const int Fp = (c.F + 3) & ~3;
   CAL_DISPATCH_VEC(c.H, {
     size_t smem = (size_t)Fp * c.H * 4 + (size_t)kTileRows * Fp * 4 + (size_t)kRowWarps * c.H * 8;
@@ -701,6 +702,7 @@ int launch_conv_forward(const Ctx& c, int layer, cudaStream_t s) {
       k_conv_fwd<VEC, 0><<<c.g_tile, 256, smem, s>>>(c, layer);
     }
   });
+  note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }
@@ -712,6 +714,7 @@ int launch_masked_forward(const Ctx& c, cudaStream_t s) {
     if (rc) return rc;
     k_conv_fwd<VEC, 2><<<dim3(c.g_tile, 2), 256, smem, s>>>(c, 0);
   });
+  note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }
@@ -723,6 +726,7 @@ int launch_conv_backward(const Ctx& c, int layer, cudaStream_t s) {
     if (rc) return rc;
     k_conv_bwd<VEC><<<c.g_tile, 256, smem, s>>>(c, layer);
   });
+  note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }
@@ -734,6 +738,7 @@ int launch_masked_bwd_gemm(const Ctx& c, cudaStream_t s) {
     if (rc) return rc;
     k_masked_bwd_gemm<VEC><<<dim3(c.g_tile, 2), 256, smem, s>>>(c);
   });
+  note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }
@@ -742,6 +747,7 @@ int launch_feat_backward(const Ctx& c, cudaStream_t s) {
   CAL_DISPATCH_VEC(c.H, {
     k_feat_bwd<VEC><<<dim3(c.g_tile, ceil_div(c.F, kFeatChunk)), 256, 0, s>>>(c);
   });
+  note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }

@@ -495,6 +495,7 @@ int launch_heads_forward(const Ctx& c, int with_loss, cudaStream_t s) {
     k_head1_fwd<VEC><<<dim3(c.t_head1, 3), 256, smem, s>>>(c);
     k_head2_fwd<VEC><<<dim3(c.g_head2, 3), 256, 0, s>>>(c);
   });
+  note_launches(3);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }
@@ -509,6 +510,7 @@ int launch_heads_backward(const Ctx& c, cudaStream_t s) {
     k_head1_bwd<VEC><<<dim3(c.t_head1, 3), 256, smem, s>>>(c);
     k_dpool<VEC><<<ceil_div(c.Bm, kRowWarps), 256, 0, s>>>(c);
   });
+  note_launches(3);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }

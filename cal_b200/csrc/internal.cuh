@@ -89,6 +89,7 @@ enum {
 };
 static_assert(CNT_END <= 64, "counter region too small");
 
+void note_launches(int n);     // bumps the process-wide counter behind cal_launch_count()
 int compute_layout(const cal_model_desc* m, const cal_caps* caps, Layout* lay);
 int validate_model(const cal_model_desc* m);
 

@@ -100,11 +100,12 @@ __global__ void __launch_bounds__(256) k_grad_reduce(const Ctx c, const RedTable
 }
 
 __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                       float* __restrict__ v, long long n, const int* __restrict__ step, float lr, float b1,
-                       float b2, float eps, float wd, float gscale) {
+                       float* __restrict__ v, long long n, const int* __restrict__ step, float lr,
+                       const float* __restrict__ lr_dev, float b1, float b2, float eps, float wd, float gscale) {
   __shared__ float s_c[2];
   if (threadIdx.x == 0) {       // bias corrections in fp64 like the Python scalars of torch.optim.Adam
     const int t = *step;
+    if (lr_dev != nullptr) lr = *lr_dev;
     const double bc1 = 1.0 - pow((double)b1, (double)t), bc2 = 1.0 - pow((double)b2, (double)t);
     s_c[0] = (float)((double)lr / bc1);
     s_c[1] = (float)sqrt(bc2);
@@ -175,6 +176,7 @@ int launch_grad_reduce(const Ctx& c, cudaStream_t s) {
   const int nb = imax(1, imin((int)((t.total + 255) / 256), 4 * kSMs));
   const int nf = imax(1, imin(ceil_div(c.F, kRowWarps), kSMs));
   k_grad_reduce<<<nb + nf, 256, 0, s>>>(c, t, nb);
+  note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }
@@ -182,14 +184,15 @@ int launch_grad_reduce(const Ctx& c, cudaStream_t s) {
 }  // namespace cal
 
 extern "C" int cal_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
-                             const int32_t* step, float lr, float beta1, float beta2, float eps,
-                             float weight_decay, float grad_scale, void* stream) {
+                             const int32_t* step, float lr, const float* lr_device, float beta1, float beta2,
+                             float eps, float weight_decay, float grad_scale, void* stream) {
   if (!params || !grads || !exp_avg || !exp_avg_sq || !step) return CAL_ENULL;
   if (n <= 0) return CAL_EINVAL;
   int g = (int)((n + 255) / 256);
   if (g > 4 * cal::kSMs) g = 4 * cal::kSMs;
-  cal::k_adam<<<g, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, (long long)n, step, lr, beta1,
-                                                  beta2, eps, weight_decay, grad_scale);
+  cal::k_adam<<<g, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, (long long)n, step, lr, lr_device,
+                                                  beta1, beta2, eps, weight_decay, grad_scale);
+  cal::note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }
@@ -197,6 +200,7 @@ extern "C" int cal_adam_step(float* params, const float* grads, float* exp_avg, 
 extern "C" int cal_adam_tick(int32_t* step, void* stream) {
   if (!step) return CAL_ENULL;
   cal::k_tick<<<1, 1, 0, (cudaStream_t)stream>>>(step);
+  cal::note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }

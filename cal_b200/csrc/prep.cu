@@ -198,6 +198,7 @@ int launch_prep(const Ctx& c, cudaStream_t s) {
   k_prep_fill<<<ge, T, 0, s>>>(c);
   k_prep_sort<<<imax(1, imin(ceil_div(c.Nm, 128), 8 * kSMs)), 128, 0, s>>>(c);
   k_prep_link<<<imax(1, imin(ceil_div(c.Nm, 128), 8 * kSMs)), 128, 0, s>>>(c);
+  note_launches(6);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }
@@ -257,6 +258,7 @@ __global__ void k_param_prep(const Ctx c) {
 
 int launch_param_prep(const Ctx& c, cudaStream_t s) {
   k_param_prep<<<c.L + 2 + 3 + 1, dim3(32, 8), 0, s>>>(c);
+  note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }

@@ -81,6 +81,16 @@ def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
+def flat_offsets(module):
+    """Offsets (in floats) of every parameter of ``module`` inside the flat parameter / gradient
+    buffer, in ``named_parameters()`` order, each tensor padded to 16 bytes.  -> (dict, total)."""
+    offs, total = {}, 0
+    for n, p in module.named_parameters():
+        offs[n] = total
+        total += _round_up(p.numel(), 4)
+    return offs, total
+
+
 class _Staged:
     """Device-side view of one mini-batch handed to the C ABI."""
     __slots__ = ("N", "E", "B", "cbatch", "keep", "gen")
@@ -127,10 +137,7 @@ class Engine:
     def _flatten(self):
         m, dev = self.module, self.device
         named = list(m.named_parameters())
-        offs, total = {}, 0
-        for n, p in named:
-            offs[n] = total
-            total += _round_up(p.numel(), 4)             # keep every tensor 16-byte aligned
+        offs, total = flat_offsets(m)                     # every tensor stays 16-byte aligned
         flat = torch.zeros(total, dtype=torch.float32, device=dev)
         for n, p in named:
             v = flat[offs[n]:offs[n] + p.numel()].view(p.shape)
@@ -200,17 +207,21 @@ class Engine:
         c = self.caps
         if c is not None and N <= c.max_nodes and E <= c.max_edges and B <= c.max_graphs:
             return False
-        caps = _lib.Caps()
         grow = lambda need, cur, q: max(cur, _round_up(int(need * 1.25) + 1, q))
-        caps.max_nodes = grow(N, c.max_nodes if c else 0, 256)
-        caps.max_edges = grow(E, c.max_edges if c else 0, 256)
-        caps.max_graphs = grow(B, c.max_graphs if c else 0, 32) if c else _round_up(max(B, 1), 32)
+        return self.set_caps(grow(N, c.max_nodes if c else 0, 256), grow(E, c.max_edges if c else 0, 256),
+                             grow(B, c.max_graphs if c else 0, 32) if c else _round_up(max(B, 1), 32))
+
+    def set_caps(self, max_nodes, max_edges, max_graphs):
+        """(Re)allocate the workspace for explicit capacities (invalidates captured CUDA graphs)."""
+        caps = _lib.Caps()
+        caps.max_nodes, caps.max_edges, caps.max_graphs = int(max_nodes), int(max_edges), int(max_graphs)
         nbytes = self.lib.cal_workspace_bytes(C.byref(self.desc), C.byref(caps))
         if nbytes == 0:
             raise _lib.CalError("cal_b200: unsupported model configuration (hidden must be 32/64/128, "
                                 "2 <= classes <= 32, features <= 512)")
         self.ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
         self.caps, self.ws_bytes = caps, nbytes
+        self._regions = {}
         ring_elems = 4 + caps.max_graphs
         self._ring = torch.zeros(self.RING, ring_elems, dtype=torch.int32).pin_memory()
         self._meta_dev = torch.zeros(ring_elems, dtype=torch.int32, device=self.device)
@@ -219,10 +230,13 @@ class Engine:
 
     def region(self, name, dtype=torch.float32):
         """A named workspace region as a flat tensor view (tests / debugging)."""
-        off, size = C.c_size_t(), C.c_size_t()
-        _lib.check(self.lib.cal_workspace_region(C.byref(self.desc), C.byref(self.caps), WS[name],
-                                                 C.byref(off), C.byref(size)), "cal_workspace_region")
-        return self.ws[off.value:off.value + size.value].view(dtype)
+        v = self._regions.get((name, dtype))
+        if v is None:
+            off, size = C.c_size_t(), C.c_size_t()
+            _lib.check(self.lib.cal_workspace_region(C.byref(self.desc), C.byref(self.caps), WS[name],
+                                                     C.byref(off), C.byref(size)), "cal_workspace_region")
+            v = self._regions[(name, dtype)] = self.ws[off.value:off.value + size.value].view(dtype)
+        return v
 
     # ---- batches ----
     def stage(self, data, perm=None, gat_keep=None):
@@ -273,8 +287,10 @@ class Engine:
         _lib.check(self.lib.cal_prep(C.byref(self.desc), C.byref(self.caps), C.byref(st.cbatch),
                                      self.ws.data_ptr(), self.ws_bytes, self._stream()), "cal_prep")
 
-    def forward(self, st, train, with_loss=False, copy_out=True):
+    def forward(self, st, train, with_loss=False, copy_out=True, stages=None):
         flags = (_lib.CAL_F_TRAIN if train else 0) | (_lib.CAL_F_LOSS if with_loss else 0)
+        if stages is not None:
+            flags |= _lib.stages_flag(*stages)
         self.gen += 1
         st.gen = self.gen
         _lib.check(self.lib.cal_causal_forward(
@@ -286,7 +302,7 @@ class Engine:
             return self.out_logp[:3 * st.B * self.C].view(3, st.B, self.C)
         return None
 
-    def backward(self, st, grad_logp=None):
+    def backward(self, st, grad_logp=None, stages=None):
         if st.gen != self.gen:
             raise _lib.CalError("cal_b200: backward through a stale forward (the workspace holds the "
                                 "activations of the most recent forward only)")
@@ -296,7 +312,8 @@ class Engine:
             gp = grad_logp.data_ptr()
         _lib.check(self.lib.cal_causal_backward(
             C.byref(self.desc), C.byref(self.caps), C.byref(self.po), self.flat.data_ptr(), C.byref(st.cbatch),
-            gp, self.flat_grad.data_ptr(), self.ws.data_ptr(), self.ws_bytes, self._stream()),
+            gp, self.flat_grad.data_ptr(), _lib.stages_flag(*stages) if stages is not None else 0,
+            self.ws.data_ptr(), self.ws_bytes, self._stream()),
             "cal_causal_backward")
 
     def status(self):
@@ -309,8 +326,12 @@ class Engine:
         """f32[7] device view: loss, c_loss, o_loss, co_loss, correct_c, correct_o, correct_co."""
         return self.region("LOSS")[:7]
 
+    def loss_parts_full(self):
+        return self.region("LOSS")[:8]
+
     # ---- fused Adam on the flat buffers (train_causal.py:21,192) ----
-    def adam_step(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+    def adam_step(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0, lr_device=None):
+        """``lr_device`` (f32[1] device tensor) overrides ``lr`` so captured graphs follow a schedule."""
         if self.opt_state is None:
             self.opt_state = (torch.zeros_like(self.flat), torch.zeros_like(self.flat),
                               torch.zeros(1, dtype=torch.int32, device=self.device))
@@ -318,8 +339,14 @@ class Engine:
         s = self._stream()
         _lib.check(self.lib.cal_adam_tick(step.data_ptr(), s), "cal_adam_tick")
         _lib.check(self.lib.cal_adam_step(self.flat.data_ptr(), self.flat_grad.data_ptr(), m.data_ptr(),
-                                          v.data_ptr(), self.total, step.data_ptr(), lr, betas[0], betas[1],
-                                          eps, weight_decay, grad_scale, s), "cal_adam_step")
+                                          v.data_ptr(), self.total, step.data_ptr(), float(lr),
+                                          lr_device.data_ptr() if lr_device is not None else 0,
+                                          betas[0], betas[1], eps, weight_decay, grad_scale, s), "cal_adam_step")
+
+    def stage_names(self, backward=False):
+        p = _lib.CAL_PASS_BACKWARD if backward else _lib.CAL_PASS_FORWARD
+        n = self.lib.cal_stage_count(C.byref(self.desc), p)
+        return [self.lib.cal_stage_name(C.byref(self.desc), p, i).decode() for i in range(n)]
 
 
 class _CausalFn(torch.autograd.Function):

@@ -169,9 +169,25 @@ enum cal_ws_region {
 /* flags for cal_causal_forward */
 #define CAL_F_TRAIN 1        /* BatchNorm batch statistics + running-stat update; GAT dropout */
 #define CAL_F_LOSS 2         /* also evaluate train_causal.py:178-186 (needs batch.y) */
+/* Run only stages [lo, hi] of the pass (see cal_stage_count / cal_stage_name); flags without a
+ * range run the whole pass.  Used for per-operator tests and live per-kernel timing. */
+#define CAL_F_STAGES(lo, hi) ((((lo) + 1) << 8) | (((hi) + 1) << 16))
+#define CAL_PASS_FORWARD 0
+#define CAL_PASS_BACKWARD 1
 
 int cal_abi_version(void);
 const char* cal_error_string(int code);
+
+/* Number of kernels this library has launched in this process (monotonic; the difference
+ * around a call is that call's launch count). */
+uint64_t cal_launch_count(void);
+
+/* The operators ("stages") a pass is made of, in execution order, and their names:
+ * forward  = param_prep, feat, layer_0 .. layer_{L-1}, edge_att, masked_convs, readout, copy_out
+ * backward = readout_bwd, masked_gemm_bwd, masked_gather_bwd, norm_bwd, att_bwd,
+ *            layer_{L-1}_bwd .. layer_0_bwd, feat_bwd, grad_reduce */
+int cal_stage_count(const cal_model_desc* m, int pass);
+const char* cal_stage_name(const cal_model_desc* m, int pass, int stage);
 
 /* Size in bytes of the workspace for a model at given capacities; the offset /
  * size of one named region inside it (returns CAL_EINVAL for unknown ids). */
@@ -200,17 +216,19 @@ int cal_causal_forward(const cal_model_desc* m, const cal_caps* caps, const cal_
 /* Backward of the above (autograd of loss.backward(), train_causal.py:187).
  * `grad_logp` f32[3][B][C] = dL/d(outputs); NULL means "use the loss evaluated
  * by the forward with CAL_F_LOSS".  Writes (not accumulates) every parameter
- * gradient into `grads` (flat, same offsets as params). */
+ * gradient into `grads` (flat, same offsets as params).  `flags`: 0 or CAL_F_STAGES(lo, hi). */
 int cal_causal_backward(const cal_model_desc* m, const cal_caps* caps, const cal_param_offsets* po,
                         const float* params, const cal_batch* b, const float* grad_logp,
-                        float* grads, void* workspace, size_t ws_bytes, void* stream);
+                        float* grads, int flags, void* workspace, size_t ws_bytes, void* stream);
 
 /* torch.optim.Adam step on a flat buffer (train_causal.py:21,192):
  * m,v moments; `step` is the 1-based step count held on the device;
+ * `lr_device` (f32[1], device) overrides `lr` when non-NULL so that a captured CUDA graph follows
+ * the per-epoch learning-rate schedule (train_causal.py:22,29);
  * grad_scale multiplies the gradient first (1/world_size after all-reduce). */
 int cal_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
-                  int64_t n, const int32_t* step, float lr, float beta1, float beta2, float eps,
-                  float weight_decay, float grad_scale, void* stream);
+                  int64_t n, const int32_t* step, float lr, const float* lr_device, float beta1,
+                  float beta2, float eps, float weight_decay, float grad_scale, void* stream);
 int cal_adam_tick(int32_t* step, void* stream);   /* ++*step on the device */
 
 /* Poll the status word written by cal_prep (synchronises the stream): returns the CAL_ST_* bits,

@@ -1,0 +1,389 @@
+"""Parity of the CUDA path (through the nn.Module drop-in and the C ABI underneath it) against
+the oracle and the golden vectors frozen from the unmodified reference model code.
+
+Tolerances (BASELINE.json north_star: "within 1e-5 relative fp32 tolerance (bit-exact for
+edge_index/batch indexing)"):
+  * integer structure (CSR pointers, orderings, graph_ptr): bit-exact;
+  * forward outputs / loss: max-norm relative error < 1e-5 against the fp32 oracle;
+  * parameter gradients: < 1e-5 against the fp32 golden/oracle OR against the fp64 oracle (the
+    arbiter: two different fp32 summation orders of a gradient reduction can differ from each
+    other by more than either differs from the exact value)."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from tests.util import (GoldenCase, clone_to_cuda, golden_names, grad_or_zero, random_case, ref_prep,  # noqa: E402
+                        rel_err)
+
+TOL = 1e-5
+DEV = "cuda:0"
+
+
+def _mods():
+    import cal_b200
+    from oracle import cal_oracle
+    return cal_b200, cal_oracle
+
+
+def _oracle_step(net, b, perm, dtype=torch.float32):
+    """Oracle forward + loss + backward; returns (outs, losses, grads) as CPU tensors of `dtype`."""
+    _, O = _mods()
+    n2 = copy.deepcopy(net).to(dtype)
+    bb = copy.copy(b)
+    bb.feat = b.feat.to(dtype)
+    outs, losses, correct_o = O.train_step(n2, bb, perm=perm)
+    grads = {n: grad_or_zero(p).detach() for n, p in n2.named_parameters()}
+    return [o.detach() for o in outs], [float(l) for l in losses], grads, n2, correct_o
+
+
+def _check_grads(gpu_grads, g32, g64):
+    worst = 0.0
+    for n, want in g32.items():
+        got = gpu_grads[n].cpu()
+        e32, e64 = rel_err(got, want), rel_err(got, g64[n])
+        err = min(e32, e64)
+        worst = max(worst, err)
+        assert err < TOL, "grad %s: rel err %.3e vs fp32 oracle, %.3e vs fp64 oracle" % (n, e32, e64)
+    return worst
+
+
+GCN_GOLDEN = [n for n in golden_names() if n.startswith("gcn")]
+ALL_GOLDEN = golden_names()
+
+
+@pytest.mark.parametrize("name", ALL_GOLDEN)
+def test_prep_structure_bit_exact(name):
+    """cal_prep (gcn_conv.py:56-70 structure work + graph segmentation) is bit-exact."""
+    M, _ = _mods()
+    gc = GoldenCase(name)
+    b = gc.batch()
+    net = gc.build(M).to(DEV)
+    eng = net.engine
+    st = eng.stage(b.to(DEV))
+    eng.prep(st)
+    torch.cuda.synchronize()
+    assert eng.status() == 0
+    N, E, B = b.batch.numel(), b.edge_index.size(1), b.y.numel()
+    rp = ref_prep(b.edge_index.numpy(), b.batch.numpy(), B)
+    EPn = int(rp["in_ptr"][-1])
+    for k, n in (("IN_PTR", N + 1), ("IN_SRC", EPn), ("IN_KEY", EPn), ("OUT_PTR", N + 1), ("OUT_DST", EPn),
+                 ("OUT_KEY", EPn), ("OUT_POS", EPn), ("GRAPH_PTR", B + 1)):
+        got = eng.region(k, torch.int32)[:n].cpu().numpy()
+        assert np.array_equal(got, rp[k.lower()]), k
+    # 1/sqrt(deg) of small integers and its products: identical fp32 arithmetic
+    assert np.array_equal(eng.region("DIS")[:N].cpu().numpy(), rp["dis"])
+    assert np.array_equal(eng.region("IN_NORM")[:EPn].cpu().numpy(), rp["in_norm"])
+
+
+@pytest.mark.parametrize("name", GCN_GOLDEN)
+def test_module_matches_reference_golden(name):
+    """The nn.Module drop-in against vectors frozen from the reference's own model.py."""
+    M, O = _mods()
+    gc = GoldenCase(name)
+    net = gc.build(M).to(DEV)
+    b = gc.batch().to(DEV)
+    if not gc.train:
+        with torch.no_grad():
+            outs = net(b, eval_random=False)
+        for got, want in zip(outs, gc.outs):
+            assert rel_err(got.cpu(), want) < TOL
+        return
+    outs = net(b, eval_random=True, perm=gc.perm.tolist())
+    loss, c_loss, o_loss, co_loss = O.causal_loss(*outs, b.y, net.num_classes)
+    loss.backward()
+    torch.cuda.synchronize()
+    for got, want in zip(outs, gc.outs):
+        assert rel_err(got.detach().cpu(), want) < TOL
+    for got, want in zip((loss, c_loss, o_loss, co_loss), gc.loss):
+        assert abs(float(got) - want) < TOL * max(1.0, abs(want))
+    # gradients: fp32 golden, fp64 oracle as arbiter
+    ora = gc.build(O)
+    _, _, g64, _, _ = _oracle_step(ora, gc.batch(), gc.perm, torch.float64)
+    gpu = {n: grad_or_zero(p) for n, p in net.named_parameters()}
+    _check_grads(gpu, gc.grads, g64)
+    assert net.conv_feat.bias.grad is None            # gfn=True: bias unused (gcn_conv.py:76-77)
+    sd = net.state_dict()
+    for k, want in gc.after.items():                  # BatchNorm running statistics after the step
+        assert rel_err(sd[k].double().cpu(), want.double()) < TOL, k
+
+
+CASES = [
+    dict(seed=1, hidden=32, layers=3, batch_size=12),
+    dict(seed=2, hidden=64, layers=2, batch_size=33, cat="cat"),
+    dict(seed=3, hidden=128, layers=3, batch_size=128),                       # cfg 1/2 shapes
+    dict(seed=4, hidden=128, layers=3, batch_size=96, classes=2),             # last batch of an epoch
+    dict(seed=5, hidden=128, layers=1, batch_size=1),                         # single graph
+    dict(seed=6, hidden=32, layers=3, batch_size=7, avg_nodes=8),             # tiny graphs
+    dict(seed=7, hidden=64, layers=3, batch_size=16, features=109, classes=2),   # cfg 3 feature width
+    dict(seed=8, hidden=128, layers=3, batch_size=24, features=64, avg_nodes=200, ba_m=2, noise=0.0),  # cfg 5 graphs
+    dict(seed=9, hidden=32, layers=2, batch_size=10, without_node_attention=True),
+    dict(seed=10, hidden=32, layers=2, batch_size=10, without_edge_attention=True),
+    dict(seed=11, hidden=32, layers=8, batch_size=5),                         # CAL_MAX_LAYERS
+    dict(seed=12, hidden=128, layers=3, batch_size=256, avg_nodes=30),        # > 148 row tiles: persistent loop
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "s%d" % c["seed"])
+def test_train_step_matches_oracle(case):
+    M, O = _mods()
+    ora, b, perm = random_case(**case)
+    outs32, loss32, g32, ora_after, _ = _oracle_step(ora, b, perm, torch.float32)
+    _, _, g64, _, _ = _oracle_step(ora, b, perm, torch.float64)
+    net = clone_to_cuda(ora, M)
+    bd = b.to(DEV)
+    outs = net(bd, eval_random=True, perm=perm.tolist())
+    loss, *_ = O.causal_loss(*outs, bd.y, net.num_classes)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert net.engine.status() == 0
+    for got, want in zip(outs, outs32):
+        assert rel_err(got.detach().cpu(), want) < TOL
+    assert abs(float(loss) - loss32[0]) < TOL * max(1.0, abs(loss32[0]))
+    _check_grads({n: grad_or_zero(p) for n, p in net.named_parameters()}, g32, g64)
+    sd, sd_ref = net.state_dict(), ora_after.state_dict()
+    for k in sd_ref:
+        if "running" in k:
+            assert rel_err(sd[k].cpu(), sd_ref[k]) < TOL, k
+        if "num_batches" in k:
+            assert int(sd[k]) == int(sd_ref[k]), k
+
+
+def test_fused_loss_matches_train_causal():
+    """CAL_F_LOSS: loss parts and correct counts of train_causal.py:178-186 computed on the device."""
+    M, O = _mods()
+    ora, b, perm = random_case(seed=21, hidden=64, batch_size=40)
+    outs32, loss32, _, _, correct_o = _oracle_step(ora, b, perm)
+    net = clone_to_cuda(ora, M)
+    eng = net.engine
+    st = eng.stage(b.to(DEV), perm=perm.tolist())
+    eng.prep(st)
+    eng.forward(st, train=True, with_loss=True)
+    torch.cuda.synchronize()
+    lp = eng.loss_parts().cpu()
+    for i in range(4):
+        assert abs(float(lp[i]) - loss32[i]) < TOL * max(1.0, abs(loss32[i]))
+    y = b.y.view(-1)
+    for h in range(3):
+        assert int(lp[4 + h]) == int(outs32[h].max(1)[1].eq(y).sum())
+    assert int(lp[5]) == correct_o
+    # backward from the fused loss == backward from torch's loss on the outputs
+    eng.backward(st, None)
+    g_fused = eng.flat_grad.clone()
+    outs = net(b.to(DEV), eval_random=True, perm=perm.tolist())
+    net.zero_grad()
+    O.causal_loss(*outs, b.to(DEV).y, net.num_classes)[0].backward()
+    torch.cuda.synchronize()
+    for n, p in net.named_parameters():
+        o = eng.param_offs[n]
+        got = g_fused[o:o + p.numel()].view(p.shape)
+        assert rel_err(got.cpu(), grad_or_zero(p).cpu()) < TOL, n
+
+
+def test_eval_forward_uses_running_stats():
+    M, O = _mods()
+    ora, b, perm = random_case(seed=31, hidden=128, batch_size=20)
+    # make the running statistics non-trivial: one oracle train step first
+    O.train_step(ora, b, perm=perm)
+    ora.eval()
+    with torch.no_grad():
+        want = ora(b, eval_random=False)
+    net = clone_to_cuda(ora, M)
+    with torch.no_grad():
+        got = net(b.to(DEV), eval_random=False)
+    for g, w in zip(got, want):
+        assert rel_err(g.cpu(), w) < TOL
+
+
+def test_deterministic_and_stagewise_identical():
+    """No float atomics anywhere: two runs are bit-identical, and so is a run issued one stage at
+    a time through CAL_F_STAGES."""
+    M, _ = _mods()
+    ora, b, perm = random_case(seed=41, hidden=128, batch_size=64)
+    net = clone_to_cuda(ora, M)
+    eng = net.engine
+    bd = b.to(DEV)
+    res = []
+    for mode in ("whole", "whole", "staged"):
+        st = eng.stage(bd, perm=perm.tolist())
+        eng.prep(st)
+        if mode == "whole":
+            out = eng.forward(st, train=True, with_loss=True).clone()
+            eng.backward(st, None)
+        else:
+            nf, nb = len(eng.stage_names()), len(eng.stage_names(backward=True))
+            for i in range(nf):
+                out = eng.forward(st, train=True, with_loss=True, stages=(i, i))
+            out = out.clone()
+            for i in range(nb):
+                eng.backward(st, None, stages=(i, i))
+        torch.cuda.synchronize()
+        res.append((out.cpu(), eng.flat_grad.cpu().clone()))
+    for o, g in res[1:]:
+        assert torch.equal(o, res[0][0])
+        assert torch.equal(g, res[0][1])
+    names = eng.stage_names() + eng.stage_names(backward=True)
+    assert names[0] == "param_prep" and names[-1] == "grad_reduce" and "layer_2_bwd" in names
+
+
+def test_structure_oddities_and_status_word():
+    """Self loops, duplicate and one-way edges, isolated nodes, E = 0; bad inputs raise status bits."""
+    M, O = _mods()
+    ora, b, perm = random_case(seed=51, hidden=32, batch_size=6)
+    N = b.batch.numel()
+    extra = torch.tensor([[0, 1, 1, 2, 0], [0, 1, 2, 2, 3]])            # loops, dup, one-way
+    b.edge_index = torch.cat([b.edge_index[:, :5], extra, b.edge_index[:, 5:], b.edge_index[:, :3]], dim=1)
+    keep = (b.edge_index[0] != N - 1) & (b.edge_index[1] != N - 1)      # isolate the last node
+    b.edge_index = b.edge_index[:, keep].contiguous()
+    outs32, loss32, g32, _, _ = _oracle_step(ora, b, perm)
+    _, _, g64, _, _ = _oracle_step(ora, b, perm, torch.float64)
+    net = clone_to_cuda(ora, M)
+    outs = net(b.to(DEV), eval_random=True, perm=perm.tolist())
+    O.causal_loss(*outs, b.to(DEV).y, net.num_classes)[0].backward()
+    torch.cuda.synchronize()
+    for got, want in zip(outs, outs32):
+        assert rel_err(got.detach().cpu(), want) < TOL
+    _check_grads({n: grad_or_zero(p) for n, p in net.named_parameters()}, g32, g64)
+    # no edges at all
+    b0 = copy.copy(b)
+    b0.edge_index = torch.zeros(2, 0, dtype=torch.long)
+    ora.eval()
+    with torch.no_grad():
+        want = ora(b0, eval_random=False)
+    net.eval()
+    with torch.no_grad():
+        got = net(b0.to(DEV), eval_random=False)
+    for g, w in zip(got, want):
+        assert rel_err(g.cpu(), w) < TOL
+    # status word
+    eng = net.engine
+    bad = copy.copy(b)
+    bad.edge_index = b.edge_index.clone()
+    bad.edge_index[1, 0] = N + 5
+    eng.prep(eng.stage(bad.to(DEV)))
+    assert eng.status() & M._lib.CAL_ST_BAD_NODE
+    bad = copy.copy(b)
+    bad.batch = b.batch.flip(0).contiguous()
+    eng.prep(eng.stage(bad.to(DEV)))
+    assert eng.status() & M._lib.CAL_ST_BAD_BATCH
+    eng.prep(eng.stage(b.to(DEV)))
+    assert eng.status() == 0
+
+
+def test_abi_argument_errors_on_device():
+    import ctypes as C
+    M, _ = _mods()
+    L = M._lib
+    ora, b, perm = random_case(seed=61, hidden=32, batch_size=4)
+    net = clone_to_cuda(ora, M)
+    eng = net.engine
+    st = eng.stage(b.to(DEV))
+    lib, s = eng.lib, eng._stream()
+    args = lambda ws, nbytes: (C.byref(eng.desc), C.byref(eng.caps), C.byref(st.cbatch), ws, nbytes, s)
+    assert lib.cal_prep(*args(0, eng.ws_bytes)) == -2                          # CAL_ENULL
+    assert lib.cal_prep(*args(eng.ws.data_ptr() + 4, eng.ws_bytes)) == -3      # CAL_EALIGN
+    assert lib.cal_prep(*args(eng.ws.data_ptr(), eng.ws_bytes - 1)) == -4      # CAL_ECAPACITY
+    assert lib.cal_prep(*args(eng.ws.data_ptr(), eng.ws_bytes)) == 0
+    # a batch larger than the workspace capacities is reported through the status word
+    ora2, big, _ = random_case(seed=62, hidden=32, batch_size=4, avg_nodes=25)
+    caps = (8, 8, 4)
+    eng.set_caps(*caps)
+    lay = M.PackedLayout(64, 256, 4, eng.F)   # pack with a larger layout than the engine's caps
+    host = torch.zeros(lay.nbytes, dtype=torch.uint8)
+    small = random_case(seed=63, hidden=32, batch_size=2, avg_nodes=12)[1]
+    lay.pack(small, host)
+    dev = host.to(DEV)
+    cb = lay.cbatch(dev.data_ptr())
+    assert lib.cal_prep(C.byref(eng.desc), C.byref(eng.caps), C.byref(cb), eng.ws.data_ptr(), eng.ws_bytes, s) == 0
+    assert eng.status() & L.CAL_ST_CAPACITY
+
+
+def test_trainer_graph_replay_matches_oracle_trajectory():
+    """5 optimizer steps: Trainer (captured CUDA graph, fused loss, fused Adam) vs oracle + torch Adam."""
+    M, O = _mods()
+    ora, b0, _ = random_case(seed=71, hidden=64, batch_size=32)
+    batches = [b0] + [random_case(seed=72 + i, hidden=64, batch_size=32)[1] for i in range(2)]
+    g = torch.Generator().manual_seed(5)
+    perms = [torch.randperm(32, generator=g) for _ in range(5)]
+    net = clone_to_cuda(ora, M)
+    tr = M.Trainer(net, M.batch_caps(batches), lr=1e-3)
+    tr_e = M.Trainer(clone_to_cuda(ora, M), M.batch_caps(batches), lr=1e-3, use_graph=False)
+    opt = torch.optim.Adam(ora.parameters(), lr=1e-3)
+    dev_batches = {}
+    for step in range(5):
+        b, perm = batches[step % 3], perms[step]
+        _, losses, _ = O.train_step(ora, b, perm=perm)
+        opt.step()
+        host = tr.pack(b, perm=perm.tolist())
+        res = tr.step_host(host).clone()
+        res_e = tr_e.step_host(host).clone()
+        assert torch.equal(res, res_e), "graph replay and eager issue differ"
+        assert abs(float(res[0]) - float(losses[0])) < 1e-4 * max(1.0, abs(float(losses[0])))
+    torch.cuda.synchronize()
+    for (n, p), (_, q) in zip(net.named_parameters(), ora.named_parameters()):
+        assert rel_err(p.detach().cpu(), q.detach()) < 1e-4, n
+    assert tr.launches_per_step == tr_e.launches_per_step and tr.launches_per_step > 0
+    assert len(tr._graphs) == 1               # one captured graph served all host batches
+
+
+def test_full_size_properties_cfg1():
+    """BASELINE.json cfg 1/2 size (B=128, H=128, L=3): size-independent properties + oracle."""
+    M, O = _mods()
+    ora, b, perm = random_case(seed=81, hidden=128, layers=3, batch_size=128)
+    net = clone_to_cuda(ora, M)
+    eng = net.engine
+    bd = b.to(DEV)
+    st = eng.stage(bd, perm=perm.tolist())
+    eng.prep(st)
+    out = eng.forward(st, train=True, with_loss=True)
+    torch.cuda.synchronize()
+    N, B, H = b.batch.numel(), 128, 128
+    Nm, Bm = eng.caps.max_nodes, eng.caps.max_graphs
+    # in-CSR and out-CSR hold the same edge multiset; out_pos is a permutation of the slots
+    EPn = int(eng.region("IN_PTR", torch.int32)[N])
+    assert EPn == int(eng.region("OUT_PTR", torch.int32)[N])
+    pos = eng.region("OUT_POS", torch.int32)[:EPn].cpu().numpy()
+    assert np.array_equal(np.sort(pos), np.arange(EPn))
+    ik = eng.region("IN_KEY", torch.int32)[:EPn].cpu().numpy()
+    ok = eng.region("OUT_KEY", torch.int32)[:EPn].cpu().numpy()
+    assert np.array_equal(ik[pos], ok)
+    # checksum of checksums: sum over graphs of the pooled embeddings == column sums of Z
+    Z = eng.region("Z").view(2, Nm, H)[:, :N].double()
+    P = eng.region("POOLED").view(2, Bm, H)[:, :B].double()
+    assert rel_err(P.sum(1).cpu(), Z.sum(1).cpu()) < 1e-6
+    # the attention masks are 2-way softmaxes
+    na = eng.region("NODE_ATT").view(Nm, 2)[:N]
+    assert float((na.sum(1) - 1).abs().max()) < 1e-6
+    # log-probabilities normalise
+    assert float((out.exp().sum(-1) - 1).abs().max()) < 1e-5
+    # and the oracle agrees at this size
+    outs32, loss32, g32, _, _ = _oracle_step(ora, b, perm)
+    for h in range(3):
+        assert rel_err(out[h].cpu(), outs32[h]) < TOL
+    eng.backward(st, None)
+    torch.cuda.synchronize()
+    _, _, g64, _, _ = _oracle_step(ora, b, perm, torch.float64)
+    gpu = {}
+    for n, p in net.named_parameters():
+        o = eng.param_offs[n]
+        gpu[n] = eng.flat_grad[o:o + p.numel()].view(p.shape)
+    _check_grads(gpu, g32, g64)
+
+
+def test_full_size_cfg5_shapes():
+    """BASELINE.json cfg 5 per-GPU shapes (B=512, ~200 nodes / ~800 edge columns per graph, F=64)."""
+    M, O = _mods()
+    ora, b, perm = random_case(seed=91, hidden=128, layers=3, batch_size=512, features=64, avg_nodes=200,
+                               ba_m=2, noise=0.0)
+    outs32, loss32, g32, _, _ = _oracle_step(ora, b, perm)
+    _, _, g64, _, _ = _oracle_step(ora, b, perm, torch.float64)
+    net = clone_to_cuda(ora, M)
+    outs = net(b.to(DEV), eval_random=True, perm=perm.tolist())
+    O.causal_loss(*outs, b.to(DEV).y, net.num_classes)[0].backward()
+    torch.cuda.synchronize()
+    for got, want in zip(outs, outs32):
+        assert rel_err(got.detach().cpu(), want) < TOL
+    _check_grads({n: grad_or_zero(p) for n, p in net.named_parameters()}, g32, g64)

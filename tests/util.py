@@ -148,3 +148,50 @@ def ref_prep(edge_index, batch, num_graphs):
                 out_ptr=out_ptr, out_dst=cols[o_out].astype(np.int32), out_key=keys[o_out].astype(np.int32),
                 out_pos=out_pos, graph_ptr=graph_ptr, dis=dis,
                 in_norm=(dis[rows[o_in]] * dis[cols[o_in]]).astype(np.float32))
+
+
+# ----------------------------------------------------------------------------------------------
+# seeded random cases (oracle vs CUDA on identical inputs)
+# ----------------------------------------------------------------------------------------------
+
+def random_case(seed=0, kind="CausalGCN", hidden=32, features=10, classes=4, layers=3, cat="add",
+                batch_size=12, avg_nodes=25, ba_m=1, noise=0.1, dropout=0.0, gaussian_feat=None, **arg_over):
+    """(oracle model, CPU batch, perm): a seeded model with every 1-d parameter moved off its init
+    (so all gradient paths are exercised) and one SPMotif-style batch."""
+    from cal_b200.data import make_batches
+    from oracle import cal_oracle
+    args = make_args(cat_or_add=cat, layers=layers, hidden=hidden, **arg_over)
+    fd = features if (gaussian_feat if gaussian_feat is not None else features != 10) else None
+    b = make_batches("spmotif", num_batches=1, seed=seed, batch_size=batch_size, avg_nodes=avg_nodes,
+                     ba_m=ba_m, noise=noise, feature_dim=fd, num_classes=classes)[0]
+    g = torch.Generator().manual_seed(seed + 1)
+    if fd is None:
+        b.feat = b.feat + 0.25 * torch.randn(b.feat.shape, generator=g)
+    torch.manual_seed(seed + 2)
+    if kind == "CausalGCN":
+        net = cal_oracle.CausalGCN(b.feat.size(1), classes, args)
+    else:
+        net = cal_oracle.CausalGAT(b.feat.size(1), classes, args, dropout=dropout)
+    with torch.no_grad():
+        for _, p in net.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+    perm = torch.randperm(batch_size, generator=g)
+    return net, b, perm
+
+
+def clone_to_cuda(oracle_net, module, device="cuda:0"):
+    """A cal_b200 module with the oracle's constructor arguments and state_dict."""
+    from oracle import cal_oracle
+    F_in = oracle_net.bn_feat.num_features
+    if isinstance(oracle_net, cal_oracle.CausalGCN):
+        net = module.CausalGCN(F_in, oracle_net.num_classes, oracle_net.args)
+    else:
+        net = module.CausalGAT(F_in, oracle_net.num_classes, oracle_net.args, dropout=oracle_net.dropout)
+    net.load_state_dict(oracle_net.state_dict(), strict=True)
+    net.train(oracle_net.training)
+    return net.to(device)
+
+
+def grad_or_zero(p):
+    return p.grad if p.grad is not None else torch.zeros_like(p)
