@@ -273,21 +273,22 @@ class Trainer:
         cb = self.layout.cbatch(packed_dev.data_ptr())
         if keep is not None:
             cb.gat_keep = keep.data_ptr()
-        d, caps, s = C.byref(eng.desc), C.byref(eng.caps), eng._stream()
+        d, caps = C.byref(eng.desc), C.byref(eng.caps)
         ws, nb = eng.ws.data_ptr(), eng.ws_bytes
+        # NB: the stream is looked up at issue time -- inside torch.cuda.graph it is the capture stream
 
         def fwd(i):
             _lib.check(lib.cal_causal_forward(d, caps, C.byref(eng.po), C.byref(eng.bo), eng.flat.data_ptr(),
                                               eng.bn_buf.data_ptr(), eng.nbt.data_ptr(), C.byref(cb),
-                                              _lib.CAL_F_TRAIN | _lib.CAL_F_LOSS | _lib.stages_flag(i, i), 0, ws, nb, s),
-                       "cal_causal_forward")
+                                              _lib.CAL_F_TRAIN | _lib.CAL_F_LOSS | _lib.stages_flag(i, i), 0, ws, nb,
+                                              eng._stream()), "cal_causal_forward")
 
         def bwd(i):
             _lib.check(lib.cal_causal_backward(d, caps, C.byref(eng.po), eng.flat.data_ptr(), C.byref(cb), 0,
-                                               eng.flat_grad.data_ptr(), _lib.stages_flag(i, i), ws, nb, s),
-                       "cal_causal_backward")
+                                               eng.flat_grad.data_ptr(), _lib.stages_flag(i, i), ws, nb,
+                                               eng._stream()), "cal_causal_backward")
 
-        jobs = [("prep", lambda: _lib.check(lib.cal_prep(d, caps, C.byref(cb), ws, nb, s), "cal_prep"))]
+        jobs = [("prep", lambda: _lib.check(lib.cal_prep(d, caps, C.byref(cb), ws, nb, eng._stream()), "cal_prep"))]
         jobs += [(n, (lambda i=i: fwd(i))) for i, n in enumerate(eng.stage_names()) if n != "copy_out"]
         jobs += [(n, (lambda i=i: bwd(i))) for i, n in enumerate(eng.stage_names(backward=True))]
         jobs += [("adam", lambda: eng.adam_step(0.0, self.betas, self.eps, self.weight_decay, 1.0, lr_device=self.lr_dev))]
