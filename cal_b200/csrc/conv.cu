@@ -179,32 +179,8 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
 #pragma unroll
   for (int i = 0; i < VEC; ++i) bv[i] = bias[lane * VEC + i];
 
-  // attention projections (MODE 1)
-  float wn0[VEC], wn1[VEC], wp0[VEC], wp1[VEC], wq0[VEC], wq1[VEC];
-  float bn0 = 0.f, bn1 = 0.f;
-  if (MODE == 1) {
-    const float* Wn = c.params + c.po.node_att_w;    // [2][H]
-    const float* We = c.params + c.po.edge_att_w;    // [2][2H]
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      int k = lane * VEC + i;
-      wn0[i] = Wn[k];
-      wn1[i] = Wn[H + k];
-      wp0[i] = We[k];
-      wp1[i] = We[2 * H + k];
-      wq0[i] = We[H + k];
-      wq1[i] = We[3 * H + k];
-    }
-    bn0 = c.params[c.po.node_att_b];
-    bn1 = c.params[c.po.node_att_b + 1];
-  }
-
-  constexpr int NV = MODE == 1 ? 4 : 2;
-  double st[NV][VEC];
-#pragma unroll
-  for (int v = 0; v < NV; ++v)
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) st[v][i] = 0.0;
+  LayerEpilogue<VEC, MODE == 1> epi;
+  epi.init(c, lane);
 
   const int ntiles = ceil_div(N, kTileRows);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -288,66 +264,12 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
 #pragma unroll
         for (int k = 0; k < VEC; ++k) o.v[k] = fmaxf(acc[r][k] + bv[k], 0.f);
         o.store(xout + (size_t)i * H, lane);
-        if (MODE == 0) {
-#pragma unroll
-          for (int k = 0; k < VEC; ++k) {
-            st[0][k] += (double)o.v[k];
-            st[1][k] += (double)o.v[k] * (double)o.v[k];
-          }
-        }
-        if (MODE == 1) {
-          float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll
-          for (int k = 0; k < VEC; ++k) {
-            s0 = fmaf(o.v[k], wn0[k], s0);
-            s1 = fmaf(o.v[k], wn1[k], s1);
-            p0 = fmaf(o.v[k], wp0[k], p0);
-            p1 = fmaf(o.v[k], wp1[k], p1);
-            q0 = fmaf(o.v[k], wq0[k], q0);
-            q1 = fmaf(o.v[k], wq1[k], q1);
-          }
-          s0 = warp_sum(s0) + bn0;
-          s1 = warp_sum(s1) + bn1;
-          p0 = warp_sum(p0);
-          p1 = warp_sum(p1);
-          q0 = warp_sum(q0);
-          q1 = warp_sum(q1);
-          float a0 = 0.5f, a1 = 0.5f;
-          if (!c.no_natt) {                             // softmax over the two logits (model.py:109)
-            float m = fmaxf(s0, s1);
-            float e0 = expf(s0 - m), e1 = expf(s1 - m);
-            float inv = 1.0f / (e0 + e1);
-            a0 = e0 * inv;
-            a1 = e1 * inv;
-          }
-          if (lane == 0) {
-            *reinterpret_cast<float2*>(c.natt + (size_t)i * 2) = make_float2(a0, a1);
-            *reinterpret_cast<float4*>(c.pq + (size_t)i * 4) = make_float4(p0, p1, q0, q1);
-          }
-#pragma unroll
-          for (int k = 0; k < VEC; ++k) {
-            double vc = (double)(a0 * o.v[k]), vo = (double)(a1 * o.v[k]);
-            st[0][k] += vc;
-            st[1][k] += vc * vc;
-            st[2][k] += vo;
-            st[3][k] += vo * vo;
-          }
-        }
+        if (MODE != 2) epi.row(c, i, o.v, lane);
       }
     }
   }
   cp_async_wait_all();
-  if (MODE != 2 && c.train) {
-    block_partial_store<VEC, NV>(st, sRed, c.statp, H);
-    if (grid_last_block(&c.counters[CNT_CONV0 + layer], gridDim.x)) {
-      if (MODE == 0) {
-        bn_finalize(c, 2 + layer, c.statp, gridDim.x, NV, 0, 1, N);
-      } else {
-        bn_finalize(c, c.L + 1, c.statp, gridDim.x, NV, 0, 1, N);
-        bn_finalize(c, c.L + 2, c.statp, gridDim.x, NV, 2, 3, N);
-      }
-    }
-  }
+  if (MODE != 2) epi.finish(c, layer, sRed, &c.counters[CNT_CONV0 + layer], N);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -665,7 +587,7 @@ __global__ void __launch_bounds__(256) k_feat_bwd(const Ctx c) {
 
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024) {
+  if (bytes > 32 * 1024) {       // static shared memory counts against the 48 KB default too
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
   }

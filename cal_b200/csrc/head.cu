@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(256) k_dpool(const Ctx c) {
 
 template <typename K>
 int set_smem_h(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024) {
+  if (bytes > 32 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
   }

@@ -92,6 +92,7 @@ static_assert(CNT_END <= 64, "counter region too small");
 void note_launches(int n);     // bumps the process-wide counter behind cal_launch_count()
 int compute_layout(const cal_model_desc* m, const cal_caps* caps, Layout* lay);
 int validate_model(const cal_model_desc* m);
+size_t gat_workspace_floats(int Nm, int EP, int H, int L, int heads);
 
 // ---- launchers (each returns 0 or a cudaError_t) ----
 int launch_prep(const Ctx& c, cudaStream_t s);
@@ -190,6 +191,104 @@ struct BnLane {
     return sc[i] * (dy - c1[i] - xh * c2[i]);
   }
   __device__ __forceinline__ float xhat(int i, float x) const { return (x - mean[i]) * rstd[i]; }
+};
+
+// Epilogue shared by the backbone layer kernels (GCNConv and GATConv): given a finished output row
+// o = relu(conv(x) + b) it accumulates the statistics of the BatchNorm that consumes the row
+// (fp64 sum / sum of squares); for the LAST backbone layer (LASTL) it instead evaluates the
+// node attention softmax(node_att_mlp(o)) (model.py:109), the per-node halves p, q of
+// edge_att_mlp([x_row || x_col]) (model.py:97-102), and the statistics of bnc / bno on att * o.
+template <int VEC, bool LASTL>
+struct LayerEpilogue {
+  static constexpr int NV = LASTL ? 4 : 2;
+  double st[NV][VEC];
+  float wn0[VEC], wn1[VEC], wp0[VEC], wp1[VEC], wq0[VEC], wq1[VEC];
+  float bn0, bn1;
+  __device__ __forceinline__ void init(const Ctx& c, int lane) {
+    constexpr int H = 32 * VEC;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) st[v][i] = 0.0;
+    bn0 = bn1 = 0.f;
+    if (LASTL) {
+      const float* Wn = c.params + c.po.node_att_w;    // [2][H]
+      const float* We = c.params + c.po.edge_att_w;    // [2][2H]
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        int k = lane * VEC + i;
+        wn0[i] = Wn[k];
+        wn1[i] = Wn[H + k];
+        wp0[i] = We[k];
+        wp1[i] = We[2 * H + k];
+        wq0[i] = We[H + k];
+        wq1[i] = We[3 * H + k];
+      }
+      bn0 = c.params[c.po.node_att_b];
+      bn1 = c.params[c.po.node_att_b + 1];
+    }
+  }
+  // all 32 lanes of the warp call this for node i (warp-uniform)
+  __device__ __forceinline__ void row(const Ctx& c, int i, const float (&o)[VEC], int lane) {
+    if (!LASTL) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        st[0][k] += (double)o[k];
+        st[1][k] += (double)o[k] * (double)o[k];
+      }
+      return;
+    }
+    float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      s0 = fmaf(o[k], wn0[k], s0);
+      s1 = fmaf(o[k], wn1[k], s1);
+      p0 = fmaf(o[k], wp0[k], p0);
+      p1 = fmaf(o[k], wp1[k], p1);
+      q0 = fmaf(o[k], wq0[k], q0);
+      q1 = fmaf(o[k], wq1[k], q1);
+    }
+    s0 = warp_sum(s0) + bn0;
+    s1 = warp_sum(s1) + bn1;
+    p0 = warp_sum(p0);
+    p1 = warp_sum(p1);
+    q0 = warp_sum(q0);
+    q1 = warp_sum(q1);
+    float a0 = 0.5f, a1 = 0.5f;
+    if (!c.no_natt) {                             // softmax over the two logits (model.py:109)
+      float m = fmaxf(s0, s1);
+      float e0 = expf(s0 - m), e1 = expf(s1 - m);
+      float inv = 1.0f / (e0 + e1);
+      a0 = e0 * inv;
+      a1 = e1 * inv;
+    }
+    if (lane == 0) {
+      *reinterpret_cast<float2*>(c.natt + (size_t)i * 2) = make_float2(a0, a1);
+      *reinterpret_cast<float4*>(c.pq + (size_t)i * 4) = make_float4(p0, p1, q0, q1);
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      double vc = (double)(a0 * o[k]), vo = (double)(a1 * o[k]);
+      st[0][k] += vc;
+      st[1][k] += vc * vc;
+      st[2][k] += vo;
+      st[3][k] += vo * vo;
+    }
+  }
+  // per-CTA partials + last-CTA BatchNorm finalisation; all threads of the CTA call this
+  __device__ __forceinline__ void finish(const Ctx& c, int layer, double* sRed, unsigned int* counter, int N) {
+    constexpr int H = 32 * VEC;
+    if (!c.train) return;
+    block_partial_store<VEC, NV>(st, sRed, c.statp, H);
+    if (grid_last_block(counter, gridDim.x)) {
+      if (!LASTL) {
+        bn_finalize(c, 2 + layer, c.statp, gridDim.x, NV, 0, 1, N);
+      } else {
+        bn_finalize(c, c.L + 1, c.statp, gridDim.x, NV, 0, 1, N);
+        bn_finalize(c, c.L + 2, c.statp, gridDim.x, NV, 2, 3, N);
+      }
+    }
+  }
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {

@@ -13,7 +13,7 @@ int validate_model(const cal_model_desc* m) {
   if (m->num_classes < 2 || m->num_classes > 32) return CAL_EUNSUPPORTED;
   if (m->layers < 1 || m->layers > CAL_MAX_LAYERS) return CAL_EINVAL;
   if (m->model == CAL_MODEL_GAT) {
-    if (m->heads < 1 || m->heads > 8 || m->hidden % m->heads != 0) return CAL_EINVAL;
+    if (m->heads != 1 && m->heads != 2 && m->heads != 4 && m->heads != 8) return CAL_EINVAL;
     if (!(m->gat_dropout >= 0.f && m->gat_dropout < 1.f)) return CAL_EINVAL;
   }
   return CAL_OK;
@@ -68,11 +68,8 @@ int compute_layout(const cal_model_desc* m, const cal_caps* caps, Layout* lay) {
   sz[CAL_WS_BN] = (size_t)kNumBN * BN_FIELDS * lay->kmax * 4;
   sz[CAL_WS_STATP] = (size_t)imax(kMaxStatBlocks, 3 * lay->g_head2) * 4 * lay->kmax * 8;
   sz[CAL_WS_WT] = ((L + 2) * H * H + 3 * 2 * H * H) * 4;
-  if (m->model == CAL_MODEL_GAT) {
-    // per layer: x' [Nm][H], alpha_src [Nm][heads], alpha_dst [Nm][heads], row max [Nm][heads],
-    // row denom [Nm][heads], d alpha_src / d alpha_dst [Nm][heads] x 2, dx' [Nm][H] (shared)
-    sz[CAL_WS_GAT] = (L * (Nm * H + 4 * Nm * 8) + Nm * H + 2 * Nm * 8) * 4;
-  }
+  if (m->model == CAL_MODEL_GAT)
+    sz[CAL_WS_GAT] = gat_workspace_floats((int)Nm, (int)EP, (int)H, (int)L, m->heads) * 4;
   sz[CAL_WS_DLOGIT] = 3 * Bm * C * 4;
   sz[CAL_WS_DH] = 3 * Bm * H * 4;
   sz[CAL_WS_DU] = 3 * Bm * 2 * H * 4;
@@ -103,7 +100,7 @@ int compute_layout(const cal_model_desc* m, const cal_caps* caps, Layout* lay) {
   }
   for (size_t l = 0; l < L; ++l) {
     lay->gp_gat[l] = gp;
-    if (m->model == CAL_MODEL_GAT) gp += (size_t)lay->g_row * 2 * H;
+    if (m->model == CAL_MODEL_GAT) gp += G * 2 * H;
   }
   sz[CAL_WS_GPART] = gp * 4;
 

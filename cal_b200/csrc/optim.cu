@@ -150,7 +150,7 @@ int launch_grad_reduce(const Ctx& c, cudaStream_t s) {
     for (int l = 0; l < c.L; ++l) {
       add(c.po.convs_w[l], c.gp_conv[l], H * H, cs, PARTS_NODE_TILES, c.g_tile);
       add(c.po.convs_b[l], c.gp_conv[l] + H * H, H, cs, PARTS_NODE_TILES, c.g_tile);
-      add(c.po.convs_att[l], c.gp_gat[l], 2 * H, 2 * H, PARTS_NODE_ROWS, c.g_row);
+      add(c.po.convs_att[l], c.gp_gat[l], 2 * H, 2 * H, PARTS_NODE_TILES, c.g_tile);
     }
   add(c.po.context_w, c.gp_conv[c.L], H * H, cs, PARTS_NODE_TILES, c.g_tile);
   add(c.po.context_b, c.gp_conv[c.L] + H * H, H, cs, PARTS_NODE_TILES, c.g_tile);

@@ -269,7 +269,7 @@ class Engine:
         cb = _lib.Batch()
         cb.dims = self._meta_dev.data_ptr()
         cb.feat = x.data_ptr()
-        cb.edge_index = ei.data_ptr() if E > 0 else 0
+        cb.edge_index = ei.data_ptr() if E > 0 else bvec.data_ptr()     # never read when E == 0, but not NULL
         cb.edge_stride = E
         cb.batch = bvec.data_ptr()
         cb.y = y.data_ptr() if y is not None else 0

@@ -55,7 +55,7 @@ typedef struct {
   int32_t hidden;              /* H: 32, 64 or 128 */
   int32_t num_classes;         /* C: 2..32 */
   int32_t layers;              /* L: 1..CAL_MAX_LAYERS */
-  int32_t heads;               /* GAT heads (model.py:319), H % heads == 0 */
+  int32_t heads;               /* GAT heads (model.py:319): 1, 2, 4 or 8 */
   int32_t cat;                 /* args.cat_or_add == "cat" (model.py:65-75) */
   int32_t without_node_attention; /* model.py:106-107 */
   int32_t without_edge_attention; /* model.py:99-100 */
@@ -107,7 +107,8 @@ typedef struct {
   const int64_t* batch;        /* i64[N]    non-decreasing graph id */
   const int64_t* y;            /* i64[B]    labels (may be NULL for forward-only) */
   const int32_t* perm;         /* i32[B]    random_idx of model.py:152 (NULL = identity) */
-  const float* gat_keep;       /* f32[L,E+N,heads] GAT dropout keep-mask scaled 1/(1-p), or NULL */
+  const float* gat_keep;       /* f32[L][E+N][heads] GATConv attention-dropout keep mask scaled by 1/(1-p), or NULL;
+                                  row e < E = edge_index column e, row E+n = the self loop appended for node n */
   int64_t edge_stride;         /* elements between edge_index[0,0] and edge_index[1,0] */
 } cal_batch;
 
@@ -146,7 +147,7 @@ enum cal_ws_region {
   CAL_WS_BN,           /* f32[CAL_MAX_BN+1][6][KMAX]: scale, shift, mean, rstd, c1, c2 per BatchNorm */
   CAL_WS_STATP,        /* f64 partial sums of the BatchNorm reductions */
   CAL_WS_WT,           /* f32 transposed copies of conv / fc1 weights */
-  CAL_WS_GAT,          /* f32 GATConv scratch: x' [L][maxN][H], alpha_src/dst [L][maxN][2*heads], softmax stats */
+  CAL_WS_GAT,          /* f32 GATConv: per layer x' [maxN][H], a_src / a_dst [maxN][heads], alpha [EP][heads]; then dz [EP][heads], d a_dst [maxN][heads] */
   CAL_WS_DLOGIT,       /* f32[3][maxB][C] */
   CAL_WS_DH,           /* f32[3][maxB][H] */
   CAL_WS_DU,           /* f32[3][maxB][2H] */
