@@ -141,6 +141,10 @@ int build_ctx(const cal_model_desc* m, const cal_caps* caps, const cal_param_off
   c.loss = REG(float, CAL_WS_LOSS);
   c.bn = REG(float, CAL_WS_BN);
   c.statp = REG(double, CAL_WS_STATP);
+  c.gsum = c.statp + lay.statp_legacy;
+  c.gs_n = lay.gs_n;
+  c.gs_stride = lay.gs_stride;
+  c.gs_cnt = c.counters + 64;
   c.WT = REG(float, CAL_WS_WT);
   c.gat = REG(float, CAL_WS_GAT);
   c.dlogit = REG(float, CAL_WS_DLOGIT);

@@ -57,6 +57,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256) k_masked_bwd_gather(const Ctx c) {
   constexpr int H = 32 * VEC;
   __shared__ double sRed[kRowWarps * H];
+  __shared__ double sTot[2 * H];
   const int N = clampN(c);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k = blockIdx.y;
@@ -116,11 +117,8 @@ __global__ void __launch_bounds__(256) k_masked_bwd_gather(const Ctx c) {
       st[1][i] += (double)dy.v[i] * (double)xh.v[i];
     }
   }
-  block_partial_store_ex<VEC, 2>(st, sRed, c.statp, H, blockIdx.x, 4, 2 * k, H, 0);
-  if (grid_last_block(&c.counters[CNT_BGATHER], gridDim.x * gridDim.y)) {
-    bn_bwd_finalize(c, c.L + 1, c.statp, gridDim.x, 4, 0, 1, N);
-    bn_bwd_finalize(c, c.L + 2, c.statp, gridDim.x, 4, 2, 3, N);
-  }
+  block_totals<VEC, 2>(st, sRed, sTot, H, 0, H, 0);
+  if (grid_sum(c, k, sTot, 2 * H, gridDim.x, blockIdx.x)) bn_bwd_finalize_tot(c, bn_id, sTot, sTot + H, N);
 }
 
 // ---------------------------------------------------------------------------------------------

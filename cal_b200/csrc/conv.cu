@@ -34,11 +34,11 @@ __global__ void __launch_bounds__(256) k_feat_stats(const Ctx c) {
   const Dims d = load_dims(c);
   const int F = c.F, N = d.N;
   __shared__ double s_s[256], s_q[256];
+  __shared__ double sTot[2 * 512];                 // F <= 512 (validate_model)
   const int Fw = imin(F, 256), rpar = 256 / Fw;
   const int t = threadIdx.x;
   const int rows_per = ceil_div(imax(N, 1), gridDim.x);
   const int r0 = imin(blockIdx.x * rows_per, N), r1 = imin(r0 + rows_per, N);
-  double* part = c.statp + (size_t)blockIdx.x * 2 * F;
   for (int cb = 0; cb < F; cb += Fw) {
     const int col = cb + t % Fw, rs = t / Fw;
     double s = 0.0, q = 0.0;
@@ -58,11 +58,12 @@ __global__ void __launch_bounds__(256) k_feat_stats(const Ctx c) {
         a += s_s[k * Fw + t];
         b += s_q[k * Fw + t];
       }
-      part[cb + t] = a;
-      part[F + cb + t] = b;
+      sTot[cb + t] = a;
+      sTot[F + cb + t] = b;
     }
   }
-  if (grid_last_block(&c.counters[CNT_FEATSTAT], gridDim.x)) bn_finalize(c, 0, c.statp, gridDim.x, 2, 0, 1, N);
+  __syncthreads();
+  if (grid_sum(c, 0, sTot, 2 * F, gridDim.x, blockIdx.x)) bn_finalize_tot(c, 0, sTot, sTot + F, N);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -74,6 +75,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256) k_feat_fwd(const Ctx c) {
   constexpr int H = 32 * VEC;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double sTot[4 * H];
   const Dims d = load_dims(c);
   const int N = d.N, F = c.F, Fp = (F + 3) & ~3;
   float* sW = reinterpret_cast<float*>(smem_raw);
@@ -127,8 +129,8 @@ __global__ void __launch_bounds__(256) k_feat_fwd(const Ctx c) {
       accs[0][k] = acc_s[k];
       accs[1][k] = acc_q[k];
     }
-    block_partial_store<VEC, 2>(accs, sRed, c.statp, H);
-    if (grid_last_block(&c.counters[CNT_FEAT], gridDim.x)) bn_finalize(c, 1, c.statp, gridDim.x, 2, 0, 1, N);
+    block_totals<VEC, 2>(accs, sRed, sTot, H, 0, H, 0);
+    if (grid_sum(c, 0, sTot, 2 * H, gridDim.x, blockIdx.x)) bn_finalize_tot(c, 1, sTot, sTot + H, N);
   }
 }
 
@@ -152,6 +154,7 @@ template <int VEC, int MODE>
 __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) {
   constexpr int H = 32 * VEC;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double sTot[MODE == 2 ? 1 : 4 * H];
   const Dims d = load_dims(c);
   const int N = d.N;
   float* sW = reinterpret_cast<float*>(smem_raw);
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
     }
   }
   cp_async_wait_all();
-  if (MODE != 2) epi.finish(c, layer, sRed, &c.counters[CNT_CONV0 + layer], N);
+  if (MODE != 2) epi.finish(c, layer, sRed, sTot, N);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -289,6 +292,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) {
   constexpr int H = 32 * VEC;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double sTot[2 * H];
   const Dims d = load_dims(c);
   const int N = d.N;
   float* sW = reinterpret_cast<float*>(smem_raw);
@@ -417,9 +421,8 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
   float* gp = c.gpart + c.gp_conv[layer] + (size_t)blockIdx.x * (H * H + H);
   if (blockIdx.x < ntiles) dW.store(gp, H);
   block_colsum_store<VEC>(dbias, reinterpret_cast<float*>(sRed), blockIdx.x < ntiles ? gp + H * H : nullptr, H);
-  block_partial_store<VEC, 2>(st, sRed, c.statp, H);
-  if (grid_last_block(&c.counters[CNT_BCONV0 + layer], gridDim.x))
-    bn_bwd_finalize(c, bn_in, c.statp, gridDim.x, 2, 0, 1, N);
+  block_totals<VEC, 2>(st, sRed, sTot, H, 0, H, 0);
+  if (grid_sum(c, 0, sTot, 2 * H, gridDim.x, blockIdx.x)) bn_bwd_finalize_tot(c, bn_in, sTot, sTot + H, N);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -143,6 +143,7 @@ template <int VEC, bool LASTL>
 __global__ void __launch_bounds__(256) k_gat_agg(const Ctx c, const int layer) {
   constexpr int H = 32 * VEC;
   __shared__ double sRed[kRowWarps * H];
+  __shared__ double sTot[4 * H];
   const int N = clampN(c);
   const int EN = imin(imax(c.dims[1], 0), c.Em) + N;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(256) k_gat_agg(const Ctx c, const int layer) {
     o.store(xout + (size_t)i * H, lane);
     epi.row(c, i, o.v, lane);
   }
-  epi.finish(c, layer, sRed, &c.counters[CNT_GAT0 + layer], N);
+  epi.finish(c, layer, sRed, sTot, N);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -265,6 +266,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256) k_gat_bwd_node(const Ctx c, const int layer) {
   constexpr int H = 32 * VEC;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double sTot[2 * H];
   const int N = clampN(c);
   const int EN = imin(imax(c.dims[1], 0), c.Em) + N;
   float* sW = reinterpret_cast<float*>(smem_raw);
@@ -398,9 +400,8 @@ __global__ void __launch_bounds__(256) k_gat_bwd_node(const Ctx c, const int lay
       }
     }
   }
-  block_partial_store<VEC, 2>(st, sRed, c.statp, H);
-  if (grid_last_block(&c.counters[CNT_BGAT0 + layer], gridDim.x))
-    bn_bwd_finalize(c, bn_in, c.statp, gridDim.x, 2, 0, 1, N);
+  block_totals<VEC, 2>(st, sRed, sTot, H, 0, H, 0);
+  if (grid_sum(c, 0, sTot, 2 * H, gridDim.x, blockIdx.x)) bn_bwd_finalize_tot(c, bn_in, sTot, sTot + H, N);
 }
 
 template <typename K>

@@ -12,6 +12,9 @@ constexpr int kNumBN = CAL_MAX_BN + 1;         // + the identity record used by 
 constexpr int kBnIdentity = CAL_MAX_BN;
 constexpr int kHeadRowsPerCta = 8;             // head2 kernels: one warp per graph row
 constexpr int kFeatChunk = 64;                 // feature columns per CTA slice in the feat backward
+constexpr int kGsGroup = 8;                    // CTAs per first-level group of the hierarchical grid sum
+constexpr int kGsSites = 3;                    // independent grid sums that may be in flight in one kernel
+constexpr int kGsCounters = 64;                // counters per site: [0] top level, [1 + group] first level
 
 // BN record fields inside CAL_WS_BN: [id][field][KMAX]
 enum { BN_SCALE = 0, BN_SHIFT, BN_MEAN, BN_RSTD, BN_C1, BN_C2, BN_FIELDS };
@@ -24,6 +27,8 @@ struct Layout {
   size_t size[CAL_WS_REGION_COUNT];
   size_t total;
   int kmax;        // floats per BN field
+  size_t statp_legacy, gs_stride;   // doubles
+  int gs_n;
   int g_tile;      // persistent grid of the row-tile (GEMM) kernels
   int g_row;       // grid of the warp-per-row kernels
   int t_head1;     // row tiles of the readout fc1 kernels (per head)
@@ -71,6 +76,10 @@ struct Ctx {
   float *in_norm, *dis, *X, *natt, *pq, *watt, *disw, *agg, *Z, *pooled, *H1, *logp, *loss, *bn;
   int with_loss;
   double* statp;
+  double* gsum;             // hierarchical grid-sum scratch: [kGsSites][(Gmax + Gmax/8 + 1) * gs_n] doubles
+  unsigned int* gs_cnt;     // [kGsSites][kGsCounters]
+  int gs_n;                 // doubles per CTA vector slot (4 * kmax)
+  size_t gs_stride;         // doubles per site
   float *WT, *gat, *dlogit, *dh, *du, *dpool, *dagg, *dym, *dnrm, *dt, *dp, *D, *gpart;
   size_t gp_conv[CAL_MAX_LAYERS + 2], gp_att, gp_feat, gp_fc1[3], gp_fc2[3], gp_gat[CAL_MAX_LAYERS];
   const float* grad_logp;   // external dL/dlogp (nullptr = fused loss)
@@ -115,14 +124,106 @@ int launch_gat_backward(const Ctx& c, int layer, cudaStream_t s);
 
 // ---- device helpers shared by the kernels ----
 
-// Finalise training-mode BatchNorm statistics from G double partials laid out as
-// partial[(g * NV + v) * K + k]; vs / vq = vector index of sum / sum of squares.
-__device__ __forceinline__ void bn_finalize(const Ctx& c, int id, const double* partial, int G, int NV, int vs,
-                                            int vq, int count) {
+// ---------------------------------------------------------------------------------------------
+// Hierarchical, deterministic cross-CTA sum of per-CTA fp64 vectors.
+// Every participating CTA (rank in [0, G)) holds its own totals in shared memory sTot[0..n).
+// Level 1: CTAs are grouped by 8; the last CTA of a group to arrive sums the group's vectors in
+// rank order.  Level 2: the last group leader to arrive sums the group vectors in group order.
+// Returns true in exactly ONE CTA, whose sTot then holds the grid totals.  Latency = two L2
+// round trips of at most 8 / ceil(G/8) independent loads per thread, instead of one CTA walking
+// G partials.  Counters reset themselves (CUDA-graph replay safe).  All threads must call.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool grid_sum(const Ctx& c, int site, double* sTot, int n, int G, int rank) {
+  __shared__ int s_flag;
+  double* l0 = c.gsum + (size_t)site * c.gs_stride;
+  double* l1 = l0 + (size_t)kMaxStatBlocks * c.gs_n;
+  unsigned int* cnt = c.gs_cnt + site * kGsCounters;
+  const int t = threadIdx.x, T = blockDim.x;
+  if (G <= 1) return true;
+  const int grp = rank / kGsGroup, ngrp = (G + kGsGroup - 1) / kGsGroup;
+  const int gsize = imin(kGsGroup, G - grp * kGsGroup);
+  for (int i = t; i < n; i += T) l0[(size_t)rank * n + i] = sTot[i];
+  __threadfence();
+  __syncthreads();
+  if (t == 0) {
+    const unsigned int old = atomicAdd(&cnt[1 + grp], 1u);
+    s_flag = (old == (unsigned int)gsize - 1u);
+    if (s_flag) cnt[1 + grp] = 0u;
+  }
+  __syncthreads();
+  if (!s_flag) return false;
+  __threadfence();
+  for (int i = t; i < n; i += T) {
+    double v[kGsGroup];
+#pragma unroll
+    for (int m = 0; m < kGsGroup; ++m)
+      v[m] = m < gsize ? __ldcg(&l0[(size_t)(grp * kGsGroup + m) * n + i]) : 0.0;
+    double sum = v[0];
+#pragma unroll
+    for (int m = 1; m < kGsGroup; ++m) sum += v[m];
+    if (ngrp == 1) sTot[i] = sum;
+    else l1[(size_t)grp * n + i] = sum;
+  }
+  if (ngrp == 1) {
+    __syncthreads();
+    return true;
+  }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) {
+    const unsigned int old = atomicAdd(&cnt[0], 1u);
+    s_flag = (old == (unsigned int)ngrp - 1u);
+    if (s_flag) cnt[0] = 0u;
+  }
+  __syncthreads();
+  if (!s_flag) return false;
+  __threadfence();
+  for (int i = t; i < n; i += T) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int g = 0;
+    for (; g + 4 <= ngrp; g += 4) {
+      s0 += __ldcg(&l1[(size_t)(g + 0) * n + i]);
+      s1 += __ldcg(&l1[(size_t)(g + 1) * n + i]);
+      s2 += __ldcg(&l1[(size_t)(g + 2) * n + i]);
+      s3 += __ldcg(&l1[(size_t)(g + 3) * n + i]);
+    }
+    for (; g < ngrp; ++g) s0 += __ldcg(&l1[(size_t)g * n + i]);
+    sTot[i] = (s0 + s1) + (s2 + s3);
+  }
+  __syncthreads();
+  return true;
+}
+
+// Cross-warp reduction of per-lane fp64 accumulators (lane owns VEC channels, 8 warps) into the
+// CTA totals sTot[(v0 + v) * K + koff + k].  sbuf holds kRowWarps * H doubles.  Fixed order.
+template <int VEC, int NV>
+__device__ __forceinline__ void block_totals(double (&acc)[NV][VEC], double* sbuf, double* sTot, int H, int v0,
+                                             int K, int koff) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) sbuf[warp * H + lane * VEC + i] = acc[v][i];
+    __syncthreads();
+    for (int k = threadIdx.x; k < H; k += blockDim.x) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < kRowWarps; ++w) s += sbuf[w * H + k];
+      sTot[(size_t)(v0 + v) * K + koff + k] = s;
+    }
+  }
+  __syncthreads();
+}
+
+// Training-mode BatchNorm statistics from grid totals (sum[k], sumsq[k] in shared memory): the
+// affine the next kernel applies, the saved mean / rstd, and the running-statistics update
+// (biased variance to normalise, unbiased for running_var, momentum; torch BatchNorm1d).
+__device__ __forceinline__ void bn_finalize_tot(const Ctx& c, int id, const double* sum, const double* sumsq,
+                                                int count) {
   const int K = c.bn_K[id];
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    double s = partial_total(partial, G, NV, vs, K, k);
-    double q = partial_total(partial, G, NV, vq, K, k);
+    const double s = sum[k], q = sumsq[k];
     double mean = 0.0, var = 0.0;
     if (count > 0) {
       mean = s / count;
@@ -147,19 +248,45 @@ __device__ __forceinline__ void bn_finalize(const Ctx& c, int id, const double* 
   if (threadIdx.x == 0 && c.nbt != nullptr) c.nbt[id] += 1;
 }
 
-// Finalise BatchNorm backward: c1 = mean(dy), c2 = mean(dy * xhat); d gamma = sum dy*xhat, d beta = sum dy.
-__device__ __forceinline__ void bn_bwd_finalize(const Ctx& c, int id, const double* partial, int G, int NV, int v1,
-                                                int v2, int count) {
+// BatchNorm backward from grid totals: c1 = mean(dy), c2 = mean(dy * xhat); d gamma = sum dy*xhat,
+// d beta = sum dy.
+__device__ __forceinline__ void bn_bwd_finalize_tot(const Ctx& c, int id, const double* sum_dy,
+                                                    const double* sum_dyx, int count) {
   const int K = c.bn_K[id];
+  const double inv = count > 0 ? 1.0 / count : 0.0;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    double s1 = partial_total(partial, G, NV, v1, K, k);
-    double s2 = partial_total(partial, G, NV, v2, K, k);
-    double inv = count > 0 ? 1.0 / count : 0.0;
+    const double s1 = sum_dy[k], s2 = sum_dyx[k];
     c.bnf(id, BN_C1)[k] = (float)(s1 * inv);
     c.bnf(id, BN_C2)[k] = (float)(s2 * inv);
     c.grads[c.bn_gamma[id] + k] = (float)s2;
     c.grads[c.bn_beta[id] + k] = (float)s1;
   }
+}
+
+// Legacy single-level variants (readout kernels: a handful of partials).
+__device__ __forceinline__ void bn_finalize(const Ctx& c, int id, const double* partial, int G, int NV, int vs,
+                                            int vq, int count) {
+  __shared__ double s_sum[2][2 * kMaxH];
+  const int K = c.bn_K[id];
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    s_sum[0][k] = partial_total(partial, G, NV, vs, K, k);
+    s_sum[1][k] = partial_total(partial, G, NV, vq, K, k);
+  }
+  __syncthreads();
+  bn_finalize_tot(c, id, s_sum[0], s_sum[1], count);
+}
+__device__ __forceinline__ void bn_bwd_finalize(const Ctx& c, int id, const double* partial, int G, int NV, int v1,
+                                                int v2, int count) {
+  __shared__ double s_sum[2][2 * kMaxH];
+  const int K = c.bn_K[id];
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    s_sum[0][k] = partial_total(partial, G, NV, v1, K, k);
+    s_sum[1][k] = partial_total(partial, G, NV, v2, K, k);
+  }
+  __syncthreads();
+  bn_bwd_finalize_tot(c, id, s_sum[0], s_sum[1], count);
 }
 
 // Per-lane BatchNorm constants of the lane's VEC channels.
@@ -275,17 +402,18 @@ struct LayerEpilogue {
       st[3][k] += vo * vo;
     }
   }
-  // per-CTA partials + last-CTA BatchNorm finalisation; all threads of the CTA call this
-  __device__ __forceinline__ void finish(const Ctx& c, int layer, double* sRed, unsigned int* counter, int N) {
+  // CTA totals -> hierarchical grid sum -> BatchNorm finalisation by the one CTA that ends up
+  // with the grid totals; all threads of the CTA call this
+  __device__ __forceinline__ void finish(const Ctx& c, int layer, double* sRed, double* sTot, int N) {
     constexpr int H = 32 * VEC;
     if (!c.train) return;
-    block_partial_store<VEC, NV>(st, sRed, c.statp, H);
-    if (grid_last_block(counter, gridDim.x)) {
+    block_totals<VEC, NV>(st, sRed, sTot, H, 0, H, 0);
+    if (grid_sum(c, 0, sTot, NV * H, gridDim.x, blockIdx.x)) {
       if (!LASTL) {
-        bn_finalize(c, 2 + layer, c.statp, gridDim.x, NV, 0, 1, N);
+        bn_finalize_tot(c, 2 + layer, sTot, sTot + H, N);
       } else {
-        bn_finalize(c, c.L + 1, c.statp, gridDim.x, NV, 0, 1, N);
-        bn_finalize(c, c.L + 2, c.statp, gridDim.x, NV, 2, 3, N);
+        bn_finalize_tot(c, c.L + 1, sTot, sTot + H, N);
+        bn_finalize_tot(c, c.L + 2, sTot + 2 * H, sTot + 3 * H, N);
       }
     }
   }

@@ -38,7 +38,7 @@ int compute_layout(const cal_model_desc* m, const cal_caps* caps, Layout* lay) {
 
   size_t sz[CAL_WS_REGION_COUNT] = {0};
   sz[CAL_WS_STATUS] = 4 * 4;
-  sz[CAL_WS_COUNTERS] = 64 * 4;
+  sz[CAL_WS_COUNTERS] = (64 + kGsSites * kGsCounters) * 4;
   sz[CAL_WS_IN_PTR] = (Nm + 1) * 4;
   sz[CAL_WS_IN_SRC] = EP * 4;
   sz[CAL_WS_IN_KEY] = EP * 4;
@@ -66,7 +66,11 @@ int compute_layout(const cal_model_desc* m, const cal_caps* caps, Layout* lay) {
   sz[CAL_WS_LOGP] = 3 * Bm * C * 4;
   sz[CAL_WS_LOSS] = (8 + 6 * (size_t)lay->g_head2) * 4;
   sz[CAL_WS_BN] = (size_t)kNumBN * BN_FIELDS * lay->kmax * 4;
-  sz[CAL_WS_STATP] = (size_t)imax(kMaxStatBlocks, 3 * lay->g_head2) * 4 * lay->kmax * 8;
+  // legacy single-level partials (readout kernels) + the hierarchical grid-sum scratch
+  lay->statp_legacy = (size_t)imax(kMaxStatBlocks, 3 * lay->g_head2) * 4 * lay->kmax;
+  lay->gs_n = 4 * lay->kmax;
+  lay->gs_stride = (size_t)(kMaxStatBlocks + kMaxStatBlocks / kGsGroup + 1) * lay->gs_n;
+  sz[CAL_WS_STATP] = (lay->statp_legacy + kGsSites * lay->gs_stride) * 8;
   sz[CAL_WS_WT] = ((L + 2) * H * H + 3 * 2 * H * H) * 4;
   if (m->model == CAL_MODEL_GAT)
     sz[CAL_WS_GAT] = gat_workspace_floats((int)Nm, (int)EP, (int)H, (int)L, m->heads) * 4;

@@ -19,7 +19,7 @@ __global__ void k_prep_init(const Ctx c) {
     c.status[0] = st;
     c.status[1] = c.status[2] = c.status[3] = 0;
   }
-  if (tid < 64) c.counters[tid] = 0u;
+  if (tid < 64 + kGsSites * kGsCounters) c.counters[tid] = 0u;
   if (N < 0 || E < 0 || B < 0 || N > c.Nm || E > c.Em || B > c.Bm) return;
   for (int k = tid; k < c.kmax; k += nth) {     // identity BatchNorm record
     c.bnf(kBnIdentity, BN_SCALE)[k] = 1.f;
@@ -208,35 +208,43 @@ int launch_prep(const Ctx& c, cudaStream_t s) {
 // the fc1 weights (torch Linear stores [out, in]; the forward GEMM wants [in, out]); in eval mode
 // also the BatchNorm affine from the running statistics.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_param_prep(const Ctx c) {
+__global__ void k_param_prep(const Ctx c, const int n_tiles) {
   __shared__ float tile[32][33];
-  const int H = c.H;
+  const int H = c.H, hb = H / 32;
   const int n_conv = c.L + 2;
-  const int m = blockIdx.x;
-  if (m < n_conv + 3) {
+  int m = blockIdx.x;
+  if (m < n_tiles) {
+    // decode (matrix, 32x32 tile): conv matrices first (hb*hb tiles each), then the three fc1 weights
     const float* src;
     float* dst;
-    int rows, cols;    // src is [rows][cols]; dst is [cols][rows]
-    if (m < n_conv) {
-      long long off = m < c.L ? c.po.convs_w[m] : (m == c.L ? c.po.context_w : c.po.objects_w);
+    int rows, cols, t;    // src is [rows][cols]; dst is [cols][rows]
+    if (m < n_conv * hb * hb) {
+      const int mat = m / (hb * hb);
+      t = m - mat * hb * hb;
+      long long off = mat < c.L ? c.po.convs_w[mat] : (mat == c.L ? c.po.context_w : c.po.objects_w);
       src = c.params + off;
-      dst = c.wt_conv(m);
+      dst = c.wt_conv(mat);
       rows = H; cols = H;
     } else {
-      int h = m - n_conv;
+      m -= n_conv * hb * hb;
+      int h = 0;
+      for (; h < 3; ++h) {
+        const int nt = hb * (((h == 2 && c.cat) ? 2 * H : H) / 32);
+        if (m < nt) break;
+        m -= nt;
+      }
+      t = m;
       src = c.params + c.po.fc1_w[h];
       dst = c.wt_fc1(h);
       rows = H; cols = (h == 2 && c.cat) ? 2 * H : H;
     }
-    for (int r0 = 0; r0 < rows; r0 += 32)
-      for (int c0 = 0; c0 < cols; c0 += 32) {
-        for (int i = threadIdx.y; i < 32; i += blockDim.y)
-          tile[i][threadIdx.x] = src[(size_t)(r0 + i) * cols + c0 + threadIdx.x];
-        __syncthreads();
-        for (int i = threadIdx.y; i < 32; i += blockDim.y)
-          dst[(size_t)(c0 + i) * rows + r0 + threadIdx.x] = tile[threadIdx.x][i];
-        __syncthreads();
-      }
+    const int ct = cols / 32;
+    const int r0 = (t / ct) * 32, c0 = (t % ct) * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y)
+      tile[i][threadIdx.x] = src[(size_t)(r0 + i) * cols + c0 + threadIdx.x];
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y)
+      dst[(size_t)(c0 + i) * rows + r0 + threadIdx.x] = tile[threadIdx.x][i];
   } else if (!c.train) {
     // eval: y = (x - running_mean) / sqrt(running_var + eps) * gamma + beta
     const int nbn = c.L + 9;
@@ -257,7 +265,9 @@ __global__ void k_param_prep(const Ctx c) {
 }
 
 int launch_param_prep(const Ctx& c, cudaStream_t s) {
-  k_param_prep<<<c.L + 2 + 3 + 1, dim3(32, 8), 0, s>>>(c);
+  const int hb = c.H / 32;
+  const int n_tiles = (c.L + 2) * hb * hb + 2 * hb * hb + hb * ((c.cat ? 2 * c.H : c.H) / 32);
+  k_param_prep<<<n_tiles + 1, dim3(32, 8), 0, s>>>(c, n_tiles);
   note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;

@@ -118,7 +118,7 @@ typedef struct {
  * stored in that order. */
 enum cal_ws_region {
   CAL_WS_STATUS = 0,   /* i32[4]: [0] = status bits (CAL_ST_*) */
-  CAL_WS_COUNTERS,     /* u32[64]: self-resetting grid arrival counters */
+  CAL_WS_COUNTERS,     /* u32[64 + 3 * 64]: self-resetting grid arrival counters */
   CAL_WS_IN_PTR,       /* i32[maxN+1] CSR by target (edge_index[1]) incl. appended self loops */
   CAL_WS_IN_SRC,       /* i32[EP] source node of in-CSR position p */
   CAL_WS_IN_KEY,       /* i32[EP] edge_index column e (< E) or E + node for the appended loop */
@@ -145,7 +145,7 @@ enum cal_ws_region {
   CAL_WS_LOGP,         /* f32[3][maxB][C] the three outputs (log-probabilities) */
   CAL_WS_LOSS,         /* f32[8]: loss, c_loss, o_loss, co_loss, correct_c, correct_o, correct_co, 0 */
   CAL_WS_BN,           /* f32[CAL_MAX_BN+1][6][KMAX]: scale, shift, mean, rstd, c1, c2 per BatchNorm */
-  CAL_WS_STATP,        /* f64 partial sums of the BatchNorm reductions */
+  CAL_WS_STATP,        /* f64 scratch of the cross-CTA BatchNorm reductions (hierarchical grid sum) */
   CAL_WS_WT,           /* f32 transposed copies of conv / fc1 weights */
   CAL_WS_GAT,          /* f32 GATConv: per layer x' [maxN][H], a_src / a_dst [maxN][heads], alpha [EP][heads]; then dz [EP][heads], d a_dst [maxN][heads] */
   CAL_WS_DLOGIT,       /* f32[3][maxB][C] */
