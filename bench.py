@@ -279,6 +279,10 @@ def run_gpu(a, rank, local_rank, world):
     caps_probe = cal_b200.batch_caps(probe, slack=1.15)
     lay_probe = cal_b200.PackedLayout(*caps_probe, probe[0].feat.size(1))
     n_res = a.resident or int(min(max(L2_BYTES // lay_probe.nbytes + 8, 16), 1024))
+    if dist is not None:                      # every rank must issue the same number of collectives
+        t = torch.tensor([n_res], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        n_res = int(t.item())
     pool = a.pool or max(8192, 4 * bs)
     batches, cfg = build_batches(a.workload, bs, n_res, pool, 666 + rank)
     F, C = int(batches[0].feat.size(1)), cfg["num_classes"]

@@ -136,6 +136,8 @@ class Trainer:
         self.with_random = bool(model._shuffles(True)) if with_random is None else with_random
         self._is_gat = eng.is_gat
         self._warm = False
+        self._update_graph = None
+        self._update_launches = 0
 
     # ---- batches ----
     def set_lr(self, lr):
@@ -164,24 +166,29 @@ class Trainer:
         return self.pack(data, perm=perm).to(self.device, non_blocking=False)
 
     # ---- the step ----
-    def _issue(self, base_ptr, gat_keep=None):
+    def _issue(self, base_ptr, gat_keep=None, part="all"):
+        """Enqueue the step on the current stream.  part: "all", or "compute" (prep + forward + loss +
+        backward) / "update" (gradient all-reduce + Adam) for the two-graph data-parallel replay."""
         eng, lib = self.eng, self.eng.lib
-        cb = self.layout.cbatch(base_ptr)
-        if gat_keep is not None:
-            cb.gat_keep = gat_keep.data_ptr()
-        s = eng._stream()
-        d, caps = C.byref(eng.desc), C.byref(eng.caps)
-        _lib.check(lib.cal_prep(d, caps, C.byref(cb), eng.ws.data_ptr(), eng.ws_bytes, s), "cal_prep")
-        _lib.check(lib.cal_causal_forward(d, caps, C.byref(eng.po), C.byref(eng.bo), eng.flat.data_ptr(),
-                                          eng.bn_buf.data_ptr(), eng.nbt.data_ptr(), C.byref(cb),
-                                          _lib.CAL_F_TRAIN | _lib.CAL_F_LOSS, 0, eng.ws.data_ptr(), eng.ws_bytes, s),
-                   "cal_causal_forward")
-        _lib.check(lib.cal_causal_backward(d, caps, C.byref(eng.po), eng.flat.data_ptr(), C.byref(cb), 0,
-                                           eng.flat_grad.data_ptr(), 0, eng.ws.data_ptr(), eng.ws_bytes, s),
-                   "cal_causal_backward")
-        scale = allreduce_flat_grads(eng.flat_grad, self.pg) if self.world > 1 else 1.0
-        eng.adam_step(0.0, self.betas, self.eps, self.weight_decay, scale, lr_device=self.lr_dev)
-        eng.gen += 1
+        if part in ("all", "compute"):
+            cb = self.layout.cbatch(base_ptr)
+            if gat_keep is not None:
+                cb.gat_keep = gat_keep.data_ptr()
+            s = eng._stream()
+            d, caps = C.byref(eng.desc), C.byref(eng.caps)
+            _lib.check(lib.cal_prep(d, caps, C.byref(cb), eng.ws.data_ptr(), eng.ws_bytes, s), "cal_prep")
+            _lib.check(lib.cal_causal_forward(d, caps, C.byref(eng.po), C.byref(eng.bo), eng.flat.data_ptr(),
+                                              eng.bn_buf.data_ptr(), eng.nbt.data_ptr(), C.byref(cb),
+                                              _lib.CAL_F_TRAIN | _lib.CAL_F_LOSS, 0, eng.ws.data_ptr(), eng.ws_bytes, s),
+                       "cal_causal_forward")
+            _lib.check(lib.cal_causal_backward(d, caps, C.byref(eng.po), eng.flat.data_ptr(), C.byref(cb), 0,
+                                               eng.flat_grad.data_ptr(), 0, eng.ws.data_ptr(), eng.ws_bytes, s),
+                       "cal_causal_backward")
+            eng.gen += 1
+        if part in ("all", "allreduce"):
+            self._scale = allreduce_flat_grads(eng.flat_grad, self.pg) if self.world > 1 else 1.0
+        if part in ("all", "update"):
+            eng.adam_step(0.0, self.betas, self.eps, self.weight_decay, 1.0 / self.world, lr_device=self.lr_dev)
 
     def _gat_keep_for(self, key):
         """Attention-dropout keep mask of CausalGAT (model.py:340 dropout=0.2), regenerated on the
@@ -218,15 +225,36 @@ class Trainer:
                 self._graphs.pop(next(iter(self._graphs)))
             if not self._warm:
                 self._warmup(packed_dev, keep)
-            g = torch.cuda.CUDAGraph()
-            c0 = self.eng.lib.cal_launch_count()
-            with torch.cuda.graph(g, stream=self._capture_stream()):
-                self._issue(key, keep)
-            self.launches_per_step = int(self.eng.lib.cal_launch_count() - c0) + (1 if self.world > 1 else 0)
+            count = self.eng.lib.cal_launch_count
+            c0 = count()
+            if self.world == 1:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self._capture_stream()):
+                    self._issue(key, keep)
+                g = (g, None)
+                self.launches_per_step = int(count() - c0)
+            else:
+                # data parallel: the NCCL all-reduce is issued eagerly between two captured graphs
+                # (compute | update); the update graph is shared by every batch
+                ga = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(ga, stream=self._capture_stream()):
+                    self._issue(key, keep, part="compute")
+                n_compute = int(count() - c0)
+                if self._update_graph is None:
+                    c1 = count()
+                    self._update_graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self._update_graph, stream=self._capture_stream()):
+                        self._issue(key, keep, part="update")
+                    self._update_launches = int(count() - c1)
+                g = (ga, self._update_graph)
+                self.launches_per_step = n_compute + 1 + self._update_launches     # + the NCCL all-reduce kernel
             self._graphs[key] = (g, packed_dev)
         else:
             g = g[0]
-        g.replay()
+        g[0].replay()
+        if g[1] is not None:
+            self._issue(key, keep, part="allreduce")
+            g[1].replay()
 
     def _capture_stream(self):
         if not hasattr(self, "_cap_stream"):

@@ -1,0 +1,80 @@
+"""Data-parallel training on >= 2 GPUs (NCCL): every rank steps its own shard through the captured
+CUDA graph, the flat gradient buffer is all-reduced inside the step, and afterwards
+  * all ranks hold bit-identical parameters,
+  * the parameters match the oracle emulation: per-rank batches, gradients averaged, torch Adam
+    (BatchNorm statistics stay per rank -- plain DDP semantics)."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from tests.util import clone_to_cuda, random_case, rel_err  # noqa: E402
+
+STEPS = 3
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _rank_batches(rank):
+    return [random_case(seed=300 + 10 * rank + i, hidden=64, batch_size=24)[1] for i in range(2)]
+
+
+def _worker(rank, world, port, out_dir, use_graph):
+    import torch.distributed as dist
+    import cal_b200
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    ora, _, _ = random_case(seed=299, hidden=64, batch_size=24)          # identical replica on every rank
+    net = clone_to_cuda(ora, cal_b200, device="cuda:%d" % rank)
+    batches = _rank_batches(rank)
+    caps = cal_b200.batch_caps([b for r in range(world) for b in _rank_batches(r)])
+    tr = cal_b200.Trainer(net, caps, lr=1e-3, process_group=True, use_graph=use_graph)
+    for s in range(STEPS):
+        b = batches[s % 2]
+        tr.step_host(tr.pack(b, perm=list(range(b.num_graphs))))
+    torch.cuda.synchronize()
+    torch.save({n: p.detach().cpu() for n, p in net.named_parameters()}, os.path.join(out_dir, "p%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("use_graph", [True, False], ids=["graph", "eager"])
+def test_dp_world2_matches_oracle_average(tmp_path, use_graph):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import copy
+    import torch.multiprocessing as mp
+    from oracle import cal_oracle as O
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), use_graph), nprocs=world, join=True)
+    got = [torch.load(os.path.join(tmp_path, "p%d.pt" % r)) for r in range(world)]
+    for n in got[0]:
+        assert torch.equal(got[0][n], got[1][n]), "rank parameters diverged: " + n
+    # oracle emulation: one replica per rank (own BatchNorm statistics), shared averaged gradients
+    ora, _, _ = random_case(seed=299, hidden=64, batch_size=24)
+    reps = [copy.deepcopy(ora) for _ in range(world)]
+    opts = [torch.optim.Adam(r.parameters(), lr=1e-3) for r in reps]
+    data = [_rank_batches(r) for r in range(world)]
+    for s in range(STEPS):
+        for r in range(world):
+            b = data[r][s % 2]
+            O.train_step(reps[r], b, perm=torch.arange(b.num_graphs))
+        for ps in zip(*[list(r.parameters()) for r in reps]):
+            gs = [p.grad if p.grad is not None else torch.zeros_like(p) for p in ps]
+            avg = sum(gs) / world
+            for p in ps:
+                p.grad = avg.clone()
+        for o in opts:
+            o.step()
+    for n, p in reps[0].named_parameters():
+        assert rel_err(got[0][n], p.detach()) < 1e-4, n
