@@ -19,6 +19,17 @@ namespace {
 struct Dims {
   int N, E, B;
 };
+
+// Optional per-phase cycle counters (CTA 0, thread 0) for latency analysis: -DCAL_PHASE_TIMING.
+#ifdef CAL_PHASE_TIMING
+#define PT_DECL long long pt_t0 = clock64(); int pt_i = 0; long long pt_v[12];
+#define PT_MARK() do { long long t_ = clock64(); if (pt_i < 12) pt_v[pt_i++] = t_ - pt_t0; pt_t0 = t_; } while (0)
+#define PT_DUMP(c, base) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) for (int q_ = 0; q_ < pt_i; ++q_) (c).status[(base) + q_] = (int)pt_v[q_]; } while (0)
+#else
+#define PT_DECL
+#define PT_MARK()
+#define PT_DUMP(c, base)
+#endif
 __device__ __forceinline__ Dims load_dims(const Ctx& c) {
   Dims d;
   d.N = imin(imax(c.dims[0], 0), c.Nm);
@@ -149,6 +160,13 @@ constexpr size_t conv_smem_bytes() {
   return (size_t)H * H * 4 + (size_t)kTileRows * H * 4 + (size_t)kRowWarps * H * 8 + (kTileRows + 4) * 4 +
          (size_t)kEdgeStage * 8;
 }
+// forward layers: sW [H][H] | sA [R][H] | sRed f64 [8][H] | sPtr [R+4] | sX [stage][H] | sXn | sXa | sXs [stage]
+template <int VEC>
+constexpr size_t convf_smem_bytes(int stage_rows) {
+  constexpr int H = 32 * VEC;
+  return (size_t)H * H * 4 + (size_t)kTileRows * H * 4 + (size_t)kRowWarps * H * 8 + (kTileRows + 4) * 4 +
+         (size_t)stage_rows * (H * 4 + 12);
+}
 
 template <int VEC, int MODE>
 __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) {
@@ -161,8 +179,11 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
   float* sA = sW + H * H;
   double* sRed = reinterpret_cast<double*>(sA + kTileRows * H);
   int* sPtr = reinterpret_cast<int*>(sRed + kRowWarps * H);
-  int* sSrc = sPtr + kTileRows + 4;
-  float* sNrm = reinterpret_cast<float*>(sSrc + kEdgeStage);
+  constexpr int kStage = MODE == 2 ? kStageMasked : kStageFwd;
+  float* sX = reinterpret_cast<float*>(sPtr + kTileRows + 4);   // [kStage][H] staged neighbour rows (16-byte aligned)
+  float* sXn = sX + (size_t)kStage * H;                // [kStage] per-entry norm factor
+  float* sXa = sXn + kStage;                           // [kStage] per-entry node attention (MODE 2)
+  int* sXs = reinterpret_cast<int*>(sXa + kStage);     // [kStage] source node of the entry
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int branch = MODE == 2 ? blockIdx.y : 0;
   const int conv = MODE == 2 ? c.L + branch : layer;
@@ -185,72 +206,107 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
   LayerEpilogue<VEC, MODE == 1> epi;
   epi.init(c, lane);
 
+  PT_DECL
   const int ntiles = ceil_div(N, kTileRows);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int row0 = tile * kTileRows;
     const int nrows = imin(kTileRows, N - row0);
     __syncthreads();                                   // previous tile's readers of sA / sPtr are done
+    PT_MARK();                                         // 0: prologue (params, BN record, W issue)
     if (threadIdx.x <= nrows) sPtr[threadIdx.x] = c.in_ptr[row0 + threadIdx.x];
     __syncthreads();
-    const int pbase = sPtr[0], pcount = sPtr[nrows] - pbase;
-    const bool staged = pcount <= kEdgeStage;
-    if (staged) {
-      for (int i = threadIdx.x; i < pcount; i += blockDim.x) {
-        sSrc[i] = c.in_src[pbase + i];
-        if (MODE == 2) sNrm[i] = c.watt[(size_t)(pbase + i) * 2 + branch];
-        else sNrm[i] = c.in_norm[pbase + i];
-      }
-    }
-    __syncthreads();
-    // ---- gather: warp per destination row ----
-#pragma unroll 1
-    for (int r = 0; r < kRPW; ++r) {
-      const int lr = warp * kRPW + r;
-      const int i = row0 + lr;
-      RowVec<VEC> a;
-      a.zero();
-      if (lr < nrows) {
-        const int p0 = sPtr[lr], p1 = sPtr[lr + 1];
-        float di = 1.f;
-        if (MODE == 2) di = c.disw[(size_t)i * 2 + branch];
-        for (int p = p0; p < p1; p += 4) {
-          int s[4];
-          float w[4];
-          RowVec<VEC> v[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (p + u < p1) {
-              s[u] = staged ? sSrc[p + u - pbase] : c.in_src[p + u];
-              w[u] = staged ? sNrm[p + u - pbase]
-                            : (MODE == 2 ? c.watt[(size_t)(p + u) * 2 + branch] : c.in_norm[p + u]);
-            } else {
-              s[u] = i;
-              w[u] = 0.f;
-            }
+    PT_MARK();                                         // 1: CSR pointers
+    // ---- gather: the neighbour rows of a batch of target rows are staged in shared memory with
+    // one bulk copy per CSR entry (all in flight at once), then summed warp-per-row from SMEM ----
+    for (int rb = 0; rb < nrows;) {
+      int re = rb;
+      while (re < nrows && sPtr[re + 1] - sPtr[rb] <= kStage) ++re;
+      const bool direct = re == rb;                    // a single row with more in-edges than the stage holds
+      if (direct) re = rb + 1;
+      const int pb = sPtr[rb], cnt = sPtr[re] - pb;
+      if (!direct) {
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
+          const int src = c.in_src[pb + e];
+          sXs[e] = src;
+          if (MODE == 2) {
+            sXn[e] = c.disw[(size_t)src * 2 + branch] * c.watt[(size_t)(pb + e) * 2 + branch];
+            sXa[e] = c.natt[(size_t)src * 2 + branch];
+          } else {
+            sXn[e] = c.in_norm[pb + e];
           }
-          float am[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            v[u].load_coherent(xin + (size_t)s[u] * H, lane);
-            if (MODE == 2) {
-              am[u] = c.natt[(size_t)s[u] * 2 + branch];
-              w[u] = (c.disw[(size_t)s[u] * 2 + branch] * w[u]) * di;     // dis[row] * w * dis[col]
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
+        }
+        __syncthreads();
+        // one 16-byte cp.async per lane and row: a warp moves one neighbour row per instruction and
+        // every row of the batch is in flight at once
+        for (int e = warp; e < cnt; e += kRowWarps)
+          if (lane < H / 4) cp_async16(sX + (size_t)e * H + lane * 4, xin + (size_t)sXs[e] * H + lane * 4);
+        cp_async_wait_all();
+        __syncthreads();
+        for (int lr = rb + warp; lr < re; lr += kRowWarps) {
+          const int i = row0 + lr;
+          const int e0 = sPtr[lr] - pb, e1 = sPtr[lr + 1] - pb;
+          float di = 1.f;
+          if (MODE == 2) di = c.disw[(size_t)i * 2 + branch];
+          RowVec<VEC> a;
+          a.zero();
+          for (int e = e0; e < e1; ++e) {
+            RowVec<VEC> v;
+            v.load_coherent(sX + (size_t)e * H, lane);
+            const float w = MODE == 2 ? sXn[e] * di : sXn[e];            // dis[row] * w * dis[col]
+            const float am = MODE == 2 ? sXa[e] : 1.f;
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {
-              float x = MODE == 2 ? am[u] * v[u].v[k] : v[u].v[k];
-              a.v[k] = fmaf(w[u], fmaf(x, bn.sc[k], bn.sh[k]), a.v[k]);
+              float x = MODE == 2 ? am * v.v[k] : v.v[k];
+              a.v[k] = fmaf(w, fmaf(x, bn.sc[k], bn.sh[k]), a.v[k]);
             }
+          }
+          if (MODE == 2) a.store(aggout + (size_t)i * H, lane);
+          a.store(sA + lr * H, lane);
         }
-        if (MODE == 2) a.store(aggout + (size_t)i * H, lane);
+        __syncthreads();                               // the stage is rewritten by the next batch
+      } else {
+        if (warp == 0) {                               // hub row: gather straight from global memory
+          const int lr = rb, i = row0 + lr;
+          float di = 1.f;
+          if (MODE == 2) di = c.disw[(size_t)i * 2 + branch];
+          RowVec<VEC> a;
+          a.zero();
+          for (int p = sPtr[lr]; p < sPtr[lr + 1]; ++p) {
+            const int src = c.in_src[p];
+            RowVec<VEC> v;
+            v.load_coherent(xin + (size_t)src * H, lane);
+            float w = MODE == 2 ? c.watt[(size_t)p * 2 + branch] : c.in_norm[p];
+            float am = 1.f;
+            if (MODE == 2) {
+              am = c.natt[(size_t)src * 2 + branch];
+              w = (c.disw[(size_t)src * 2 + branch] * w) * di;
+            }
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+              float x = MODE == 2 ? am * v.v[k] : v.v[k];
+              a.v[k] = fmaf(w, fmaf(x, bn.sc[k], bn.sh[k]), a.v[k]);
+            }
+          }
+          if (MODE == 2) a.store(aggout + (size_t)i * H, lane);
+          a.store(sA + lr * H, lane);
+        }
       }
-      a.store(sA + lr * H, lane);
+      rb = re;
     }
+    if (warp * kRPW + kRPW > nrows) {                  // zero the rows of a ragged last tile
+      for (int r = 0; r < kRPW; ++r) {
+        const int lr = warp * kRPW + r;
+        if (lr >= nrows) {
+          RowVec<VEC> z;
+          z.zero();
+          z.store(sA + lr * H, lane);
+        }
+      }
+    }
+    PT_MARK();                                         // 3: gather (this warp)
     cp_async_wait_all();
     __syncthreads();
+    PT_MARK();                                         // 4: wait for W + all warps
     // ---- tile GEMM ----
     float acc[kRPW][VEC];
 #pragma unroll
@@ -258,6 +314,7 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
     tile_gemm<VEC, kRPW>(sA, H, sW, H, H, acc);
+    PT_MARK();                                         // 5: GEMM
     // ---- epilogue ----
 #pragma unroll
     for (int r = 0; r < kRPW; ++r) {
@@ -272,7 +329,10 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
     }
   }
   cp_async_wait_all();
+  PT_MARK();                                           // 6: epilogue stores
   if (MODE != 2) epi.finish(c, layer, sRed, sTot, N);
+  PT_MARK();                                           // 7: totals + grid sum + finalize
+  PT_DUMP(c, 16);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -283,9 +343,12 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
 //   and the two BatchNorm-backward sums of bn_l (sum D, sum D * xhat).
 // smem: sW [H][H] (W^T) | sU [R][H] | sY [R][H] | sRed f64 [8][H] | sPtr | sDst | sNrm
 // ---------------------------------------------------------------------------------------------
+// sW [H][H] | sU [R][H] | sY [R][H] | sRed f64 [8][H] | sPtr [R+4] | sXD [stage][H] | sXX [stage][H] | sXn | sXs [stage]
 template <int VEC>
 constexpr size_t convb_smem_bytes() {
-  return conv_smem_bytes<VEC>() + (size_t)kTileRows * 32 * VEC * 4;
+  constexpr int H = 32 * VEC;
+  return (size_t)H * H * 4 + 2 * (size_t)kTileRows * H * 4 + (size_t)kRowWarps * H * 8 + (kTileRows + 4) * 4 +
+         (size_t)kStageBwd * (2 * H * 4 + 8);
 }
 
 template <int VEC>
@@ -300,8 +363,10 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
   float* sY = sU + kTileRows * H;
   double* sRed = reinterpret_cast<double*>(sY + kTileRows * H);
   int* sPtr = reinterpret_cast<int*>(sRed + kRowWarps * H);
-  int* sDst = sPtr + kTileRows + 4;
-  float* sNrm = reinterpret_cast<float*>(sDst + kEdgeStage);
+  float* sXD = reinterpret_cast<float*>(sPtr + kTileRows + 4);   // [kStageBwd][H] staged D_up rows
+  float* sXX = sXD + (size_t)kStageBwd * H;                       // [kStageBwd][H] staged x_up rows
+  float* sXn = sXX + (size_t)kStageBwd * H;                       // [kStageBwd] norm of the entry
+  int* sXs = reinterpret_cast<int*>(sXn + kStageBwd);             // [kStageBwd] target node of the entry
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   stage_matrix_async(sW, c.wt_conv(layer), H * H);
@@ -326,80 +391,111 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
     st[0][k] = st[1][k] = 0.0;
   }
 
+  PT_DECL
   const int ntiles = ceil_div(N, kTileRows);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int row0 = tile * kTileRows;
     const int nrows = imin(kTileRows, N - row0);
     __syncthreads();
+    PT_MARK();                                         // 0: prologue
     if (threadIdx.x <= nrows) sPtr[threadIdx.x] = c.out_ptr[row0 + threadIdx.x];
     __syncthreads();
-    const int qbase = sPtr[0], qcount = sPtr[nrows] - qbase;
-    const bool staged = qcount <= kEdgeStage;
-    if (staged) {
-      for (int i = threadIdx.x; i < qcount; i += blockDim.x) {
-        sDst[i] = c.out_dst[qbase + i];
-        sNrm[i] = c.in_norm[c.out_pos[qbase + i]];
-      }
-    }
-    __syncthreads();
-#pragma unroll 1
-    for (int r = 0; r < kRPW; ++r) {
-      const int lr = warp * kRPW + r;
-      const int j = row0 + lr;
-      RowVec<VEC> u, y;
-      u.zero();
-      y.zero();
-      if (lr < nrows) {
-        const int q0 = sPtr[lr], q1 = sPtr[lr + 1];
-        for (int q = q0; q < q1; q += 2) {
-          int dd[2];
-          float w[2];
-          RowVec<VEC> gv[2], xv[2];
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            if (q + t < q1) {
-              dd[t] = staged ? sDst[q + t - qbase] : c.out_dst[q + t];
-              w[t] = staged ? sNrm[q + t - qbase] : c.in_norm[c.out_pos[q + t]];
-            } else {
-              dd[t] = j;
-              w[t] = 0.f;
-            }
+    PT_MARK();                                         // 1: CSR pointers
+    // ---- transpose gather: D_up and x_up rows of every out-edge of a batch of source rows are
+    // staged with bulk copies; g_z = relu'(x_up) * bn_up'(D_up) is formed while summing ----
+    for (int rb = 0; rb < nrows;) {
+      int re = rb;
+      while (re < nrows && sPtr[re + 1] - sPtr[rb] <= kStageBwd) ++re;
+      const bool direct = re == rb;
+      if (direct) re = rb + 1;
+      const int qb = sPtr[rb], cnt = sPtr[re] - qb;
+      if (!direct) {
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
+          sXs[e] = c.out_dst[qb + e];
+          sXn[e] = c.in_norm[c.out_pos[qb + e]];
+        }
+        __syncthreads();
+        for (int e = warp; e < cnt; e += kRowWarps)
+          if (lane < H / 4) {
+            const size_t off = (size_t)sXs[e] * H + lane * 4;
+            cp_async16(sXD + (size_t)e * H + lane * 4, Dup + off);
+            cp_async16(sXX + (size_t)e * H + lane * 4, xup + off);
           }
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            gv[t].load_coherent(Dup + (size_t)dd[t] * H, lane);
-            xv[t].load_coherent(xup + (size_t)dd[t] * H, lane);
-          }
-#pragma unroll
-          for (int t = 0; t < 2; ++t)
+        cp_async_wait_all();
+        __syncthreads();
+        for (int lr = rb + warp; lr < re; lr += kRowWarps) {
+          const int j = row0 + lr;
+          const int e0 = sPtr[lr] - qb, e1 = sPtr[lr + 1] - qb;
+          RowVec<VEC> u, y, xi;
+          u.zero();
+          xi.load_coherent(xin + (size_t)j * H, lane);
+          for (int e = e0; e < e1; ++e) {
+            RowVec<VEC> gv, xv;
+            gv.load_coherent(sXD + (size_t)e * H, lane);
+            xv.load_coherent(sXX + (size_t)e * H, lane);
+            const float w = sXn[e];
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {
-              float g = xv[t].v[k] > 0.f ? bu.dx(k, gv[t].v[k], xv[t].v[k]) : 0.f;
-              u.v[k] = fmaf(w[t], g, u.v[k]);
+              const float g = xv.v[k] > 0.f ? bu.dx(k, gv.v[k], xv.v[k]) : 0.f;
+              u.v[k] = fmaf(w, g, u.v[k]);
+              if (e == e1 - 1) dbias[k] += g;          // the appended self loop is the row's last out-entry
             }
-        }
-        // own row: y = bn_l(x_in) for dW; g_z for db
-        RowVec<VEC> xi, go, xo;
-        xi.load_coherent(xin + (size_t)j * H, lane);
-        go.load_coherent(Dup + (size_t)j * H, lane);
-        xo.load_coherent(xup + (size_t)j * H, lane);
+          }
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-          y.v[k] = fmaf(xi.v[k], bi.sc[k], bi.sh[k]);
-          dbias[k] += xo.v[k] > 0.f ? bu.dx(k, go.v[k], xo.v[k]) : 0.f;
+          for (int k = 0; k < VEC; ++k) y.v[k] = fmaf(xi.v[k], bi.sc[k], bi.sh[k]);
+          u.store(sU + lr * H, lane);
+          y.store(sY + lr * H, lane);
+        }
+        __syncthreads();
+      } else {
+        if (warp == 0) {                               // hub row: straight from global memory
+          const int lr = rb, j = row0 + lr;
+          RowVec<VEC> u, y, xi;
+          u.zero();
+          xi.load_coherent(xin + (size_t)j * H, lane);
+          for (int q = sPtr[lr]; q < sPtr[lr + 1]; ++q) {
+            const int dd = c.out_dst[q];
+            const float w = c.in_norm[c.out_pos[q]];
+            RowVec<VEC> gv, xv;
+            gv.load_coherent(Dup + (size_t)dd * H, lane);
+            xv.load_coherent(xup + (size_t)dd * H, lane);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+              const float g = xv.v[k] > 0.f ? bu.dx(k, gv.v[k], xv.v[k]) : 0.f;
+              u.v[k] = fmaf(w, g, u.v[k]);
+              if (q == sPtr[lr + 1] - 1) dbias[k] += g;
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) y.v[k] = fmaf(xi.v[k], bi.sc[k], bi.sh[k]);
+          u.store(sU + lr * H, lane);
+          y.store(sY + lr * H, lane);
         }
       }
-      u.store(sU + lr * H, lane);
-      y.store(sY + lr * H, lane);
+      rb = re;
     }
+    if (warp * kRPW + kRPW > nrows) {                  // zero the rows of a ragged last tile
+      for (int r = 0; r < kRPW; ++r) {
+        const int lr = warp * kRPW + r;
+        if (lr >= nrows) {
+          RowVec<VEC> z;
+          z.zero();
+          z.store(sU + lr * H, lane);
+          z.store(sY + lr * H, lane);
+        }
+      }
+    }
+    PT_MARK();                                         // 2: staging + gather (this warp)
     cp_async_wait_all();
     __syncthreads();
+    PT_MARK();                                         // 3: wait W + all warps
     float acc[kRPW][VEC];
 #pragma unroll
     for (int r = 0; r < kRPW; ++r)
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
     tile_gemm<VEC, kRPW>(sU, H, sW, H, H, acc);
+    PT_MARK();                                         // 4: GEMM dX
 #pragma unroll
     for (int r = 0; r < kRPW; ++r) {
       const int j = row0 + warp * kRPW + r;
@@ -415,14 +511,19 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
         o.store(Dout + (size_t)j * H, lane);
       }
     }
+    PT_MARK();                                         // 5: dX stores
     dW.accumulate(sY, H, sU, H, kTileRows);
+    PT_MARK();                                         // 6: dW outer products
   }
   cp_async_wait_all();
   float* gp = c.gpart + c.gp_conv[layer] + (size_t)blockIdx.x * (H * H + H);
   if (blockIdx.x < ntiles) dW.store(gp, H);
   block_colsum_store<VEC>(dbias, reinterpret_cast<float*>(sRed), blockIdx.x < ntiles ? gp + H * H : nullptr, H);
+  PT_MARK();                                           // 7: dW / db partial stores
   block_totals<VEC, 2>(st, sRed, sTot, H, 0, H, 0);
   if (grid_sum(c, 0, sTot, 2 * H, gridDim.x, blockIdx.x)) bn_bwd_finalize_tot(c, bn_in, sTot, sTot + H, N);
+  PT_MARK();                                           // 8: totals + grid sum + finalize
+  PT_DUMP(c, 32);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -616,7 +717,7 @@ int launch_feat_forward(const Ctx& c, cudaStream_t s) {
 int launch_conv_forward(const Ctx& c, int layer, cudaStream_t s) {
   const bool last = layer == c.L - 1;
   CAL_DISPATCH_VEC(c.H, {
-    size_t smem = conv_smem_bytes<VEC>();
+    size_t smem = convf_smem_bytes<VEC>(kStageFwd);
     if (last) {
       int rc = set_smem(k_conv_fwd<VEC, 1>, smem);
       if (rc) return rc;
@@ -634,7 +735,7 @@ int launch_conv_forward(const Ctx& c, int layer, cudaStream_t s) {
 
 int launch_masked_forward(const Ctx& c, cudaStream_t s) {
   CAL_DISPATCH_VEC(c.H, {
-    size_t smem = conv_smem_bytes<VEC>();
+    size_t smem = convf_smem_bytes<VEC>(kStageMasked);
     int rc = set_smem(k_conv_fwd<VEC, 2>, smem);
     if (rc) return rc;
     k_conv_fwd<VEC, 2><<<dim3(c.g_tile, 2), 256, smem, s>>>(c, 0);

@@ -7,7 +7,10 @@ namespace cal {
 
 constexpr int kTileRows = 32;                  // destination rows per GEMM tile (8 warps x 4 rows)
 constexpr int kRPW = kTileRows / kRowWarps;    // rows per warp inside a tile
-constexpr int kEdgeStage = 1024;               // CSR entries staged in shared memory per tile
+constexpr int kEdgeStage = 1024;               // CSR entries staged in shared memory per tile (legacy direct path)
+constexpr int kStageFwd = 96;                  // neighbour rows staged in shared memory per row batch (forward layers)
+constexpr int kStageMasked = 40;               // ... masked convs (2 CTAs per SM)
+constexpr int kStageBwd = 96;                  // ... backward layers (two rows per entry)
 constexpr int kNumBN = CAL_MAX_BN + 1;         // + the identity record used by the top layer's backward
 constexpr int kBnIdentity = CAL_MAX_BN;
 constexpr int kHeadRowsPerCta = 8;             // head2 kernels: one warp per graph row
@@ -419,6 +422,34 @@ struct LayerEpilogue {
   }
 };
 
+// ---- TMA-style bulk copies (cp.async.bulk, SASS UBLKCP) completed through an mbarrier ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared, `bytes` % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(sdst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
@@ -431,37 +462,57 @@ __device__ __forceinline__ void stage_matrix_async(float* sdst, const float* gsr
 }
 
 // acc[r][c] += sum_k sA[(warp*RPW + r) * lda + k] * sW[k * ldw + lane*VEC + c]   (K % 4 == 0)
+// The operands of the next 4-k step are loaded into registers while the current step's FMAs
+// issue (the CTA runs 2 warps per scheduler, too few to hide shared-memory latency otherwise).
+template <int VEC>
+__device__ __forceinline__ void load_w4(const float* __restrict__ wp, int ldw, float (&w)[4][VEC]) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const float* q = wp + (size_t)kk * ldw;
+    if constexpr (VEC == 4) {
+      float4 t = *reinterpret_cast<const float4*>(q);
+      w[kk][0] = t.x; w[kk][1] = t.y; w[kk][2] = t.z; w[kk][3] = t.w;
+    } else if constexpr (VEC == 2) {
+      float2 t = *reinterpret_cast<const float2*>(q);
+      w[kk][0] = t.x; w[kk][1] = t.y;
+    } else {
+      w[kk][0] = *q;
+    }
+  }
+}
+
 template <int VEC, int RPW>
 __device__ __forceinline__ void tile_gemm(const float* __restrict__ sA, int lda, const float* __restrict__ sW,
                                           int ldw, int K, float (&acc)[RPW][VEC]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* a0 = sA + (size_t)warp * RPW * lda;
   const float* w0 = sW + lane * VEC;
+  float4 a[RPW], an[RPW];
+  float w[4][VEC], wn[4][VEC];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) a[r] = *reinterpret_cast<const float4*>(a0 + r * lda);
+  load_w4<VEC>(w0, ldw, w);
 #pragma unroll 2
   for (int k0 = 0; k0 < K; k0 += 4) {
-    float4 a[RPW];
+    const int kn = k0 + 4 < K ? k0 + 4 : k0;           // last step reloads itself (harmless)
 #pragma unroll
-    for (int r = 0; r < RPW; ++r) a[r] = *reinterpret_cast<const float4*>(a0 + r * lda + k0);
+    for (int r = 0; r < RPW; ++r) an[r] = *reinterpret_cast<const float4*>(a0 + r * lda + kn);
+    load_w4<VEC>(w0 + (size_t)kn * ldw, ldw, wn);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      float w[VEC];
-      const float* wp = w0 + (size_t)(k0 + kk) * ldw;
-      if constexpr (VEC == 4) {
-        float4 t = *reinterpret_cast<const float4*>(wp);
-        w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
-      } else if constexpr (VEC == 2) {
-        float2 t = *reinterpret_cast<const float2*>(wp);
-        w[0] = t.x; w[1] = t.y;
-      } else {
-        w[0] = *wp;
-      }
 #pragma unroll
       for (int r = 0; r < RPW; ++r) {
         float av = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
 #pragma unroll
-        for (int cc = 0; cc < VEC; ++cc) acc[r][cc] = fmaf(av, w[cc], acc[r][cc]);
+        for (int cc = 0; cc < VEC; ++cc) acc[r][cc] = fmaf(av, w[kk][cc], acc[r][cc]);
       }
     }
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) a[r] = an[r];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+      for (int cc = 0; cc < VEC; ++cc) w[kk][cc] = wn[kk][cc];
   }
 }
 
@@ -481,28 +532,59 @@ struct OuterAcc {
       for (int b = 0; b < MT; ++b) acc[a][b] = 0.f;
   }
   __device__ __forceinline__ static int idx(int t, int a) { return (a / HM) * (H / NH) + t * HM + (a % HM); }
+  // contiguous run of HM floats starting at element idx(t, run * HM); 16-byte aligned when HM == 4
+  __device__ __forceinline__ static void load_runs(const float* __restrict__ row, int t, float (&v)[MT]) {
+#pragma unroll
+    for (int run = 0; run < NH; ++run) {
+      const float* p = row + idx(t, run * HM);
+      if constexpr (HM == 4) {
+        float4 q = *reinterpret_cast<const float4*>(p);
+        v[run * HM] = q.x; v[run * HM + 1] = q.y; v[run * HM + 2] = q.z; v[run * HM + 3] = q.w;
+      } else if constexpr (HM == 2) {
+        float2 q = *reinterpret_cast<const float2*>(p);
+        v[run * HM] = q.x; v[run * HM + 1] = q.y;
+      } else {
+        v[run * HM] = *p;
+      }
+    }
+  }
   __device__ __forceinline__ void accumulate(const float* __restrict__ sP, int ldp, const float* __restrict__ sQ,
                                              int ldq, int rows) {
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    float p[MT], q[MT], pn[MT], qn[MT];
+    load_runs(sP, ty, p);
+    load_runs(sQ, tx, q);
     for (int r = 0; r < rows; ++r) {
-      float p[MT], q[MT];
-#pragma unroll
-      for (int a = 0; a < MT; ++a) {
-        p[a] = sP[r * ldp + idx(ty, a)];
-        q[a] = sQ[r * ldq + idx(tx, a)];
-      }
+      const int rn = r + 1 < rows ? r + 1 : r;
+      load_runs(sP + (size_t)rn * ldp, ty, pn);
+      load_runs(sQ + (size_t)rn * ldq, tx, qn);
 #pragma unroll
       for (int a = 0; a < MT; ++a)
 #pragma unroll
         for (int b = 0; b < MT; ++b) acc[a][b] = fmaf(p[a], q[b], acc[a][b]);
+#pragma unroll
+      for (int a = 0; a < MT; ++a) {
+        p[a] = pn[a];
+        q[a] = qn[a];
+      }
     }
   }
-  __device__ __forceinline__ void store(float* __restrict__ dst, int ldd) const {   // dst [H][ldd]
+  __device__ __forceinline__ void store(float* __restrict__ dst, int ldd) const {   // dst [H][ldd], 16-byte aligned rows
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
 #pragma unroll
     for (int a = 0; a < MT; ++a)
 #pragma unroll
-      for (int b = 0; b < MT; ++b) dst[(size_t)idx(ty, a) * ldd + idx(tx, b)] = acc[a][b];
+      for (int run = 0; run < NH; ++run) {
+        float* p = dst + (size_t)idx(ty, a) * ldd + idx(tx, run * HM);
+        if constexpr (HM == 4) {
+          *reinterpret_cast<float4*>(p) = make_float4(acc[a][run * HM], acc[a][run * HM + 1], acc[a][run * HM + 2],
+                                                      acc[a][run * HM + 3]);
+        } else if constexpr (HM == 2) {
+          *reinterpret_cast<float2*>(p) = make_float2(acc[a][run * HM], acc[a][run * HM + 1]);
+        } else {
+          *p = acc[a][run * HM];
+        }
+      }
   }
 };
 

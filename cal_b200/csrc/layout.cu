@@ -37,7 +37,7 @@ int compute_layout(const cal_model_desc* m, const cal_caps* caps, Layout* lay) {
   const size_t G = lay->g_tile;
 
   size_t sz[CAL_WS_REGION_COUNT] = {0};
-  sz[CAL_WS_STATUS] = 4 * 4;
+  sz[CAL_WS_STATUS] = 64 * 4;       // [0] status bits; [16..] optional phase-timing slots (CAL_PHASE_TIMING builds)
   sz[CAL_WS_COUNTERS] = (64 + kGsSites * kGsCounters) * 4;
   sz[CAL_WS_IN_PTR] = (Nm + 1) * 4;
   sz[CAL_WS_IN_SRC] = EP * 4;

@@ -100,11 +100,14 @@ __global__ void __launch_bounds__(256) k_grad_reduce(const Ctx c, const RedTable
 }
 
 __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                       float* __restrict__ v, long long n, const int* __restrict__ step, float lr,
-                       const float* __restrict__ lr_dev, float b1, float b2, float eps, float wd, float gscale) {
+                       float* __restrict__ v, long long n, int* __restrict__ step, unsigned int* __restrict__ done,
+                       float lr, const float* __restrict__ lr_dev, float b1, float b2, float eps, float wd,
+                       float gscale) {
   __shared__ float s_c[2];
+  __shared__ int s_t;
   if (threadIdx.x == 0) {       // bias corrections in fp64 like the Python scalars of torch.optim.Adam
-    const int t = *step;
+    const int t = *reinterpret_cast<volatile int*>(step) + (done != nullptr ? 1 : 0);   // 1-based step of this update
+    s_t = t;
     if (lr_dev != nullptr) lr = *lr_dev;
     const double bc1 = 1.0 - pow((double)b1, (double)t), bc2 = 1.0 - pow((double)b2, (double)t);
     s_c[0] = (float)((double)lr / bc1);
@@ -122,6 +125,17 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
     v[i] = vi;
     float denom = sqrtf(vi) / bc2s + eps;
     p[i] = pi - step_size * (mi / denom);
+  }
+  // fused tick: every CTA has read *step before it arrives here, so the last one may advance it
+  if (done != nullptr) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(done, 1u) == gridDim.x - 1u) {
+        *done = 0u;
+        *step = s_t;
+      }
+    }
   }
 }
 
@@ -184,14 +198,16 @@ int launch_grad_reduce(const Ctx& c, cudaStream_t s) {
 }  // namespace cal
 
 extern "C" int cal_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
-                             const int32_t* step, float lr, const float* lr_device, float beta1, float beta2,
+                             int32_t* step, float lr, const float* lr_device, float beta1, float beta2,
                              float eps, float weight_decay, float grad_scale, void* stream) {
   if (!params || !grads || !exp_avg || !exp_avg_sq || !step) return CAL_ENULL;
   if (n <= 0) return CAL_EINVAL;
   int g = (int)((n + 255) / 256);
   if (g > 4 * cal::kSMs) g = 4 * cal::kSMs;
-  cal::k_adam<<<g, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, (long long)n, step, lr, lr_device,
-                                                  beta1, beta2, eps, weight_decay, grad_scale);
+  // step[0] = number of updates applied so far (advanced by this call); step[1] = arrival counter
+  cal::k_adam<<<g, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, (long long)n, step,
+                                                  reinterpret_cast<unsigned int*>(step + 1), lr, lr_device, beta1,
+                                                  beta2, eps, weight_decay, grad_scale);
   cal::note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;

@@ -334,10 +334,9 @@ class Engine:
         """``lr_device`` (f32[1] device tensor) overrides ``lr`` so captured graphs follow a schedule."""
         if self.opt_state is None:
             self.opt_state = (torch.zeros_like(self.flat), torch.zeros_like(self.flat),
-                              torch.zeros(1, dtype=torch.int32, device=self.device))
+                              torch.zeros(2, dtype=torch.int32, device=self.device))
         m, v, step = self.opt_state
         s = self._stream()
-        _lib.check(self.lib.cal_adam_tick(step.data_ptr(), s), "cal_adam_tick")
         _lib.check(self.lib.cal_adam_step(self.flat.data_ptr(), self.flat_grad.data_ptr(), m.data_ptr(),
                                           v.data_ptr(), self.total, step.data_ptr(), float(lr),
                                           lr_device.data_ptr() if lr_device is not None else 0,

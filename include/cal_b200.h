@@ -222,15 +222,16 @@ int cal_causal_backward(const cal_model_desc* m, const cal_caps* caps, const cal
                         const float* params, const cal_batch* b, const float* grad_logp,
                         float* grads, int flags, void* workspace, size_t ws_bytes, void* stream);
 
-/* torch.optim.Adam step on a flat buffer (train_causal.py:21,192):
- * m,v moments; `step` is the 1-based step count held on the device;
+/* torch.optim.Adam step on a flat buffer (train_causal.py:21,192): m, v moments;
+ * `step` is a device int32[2], zero-initialised by the caller: step[0] = number of updates applied so
+ * far (this call applies update step[0] + 1 and advances it), step[1] = scratch;
  * `lr_device` (f32[1], device) overrides `lr` when non-NULL so that a captured CUDA graph follows
  * the per-epoch learning-rate schedule (train_causal.py:22,29);
  * grad_scale multiplies the gradient first (1/world_size after all-reduce). */
 int cal_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
-                  int64_t n, const int32_t* step, float lr, const float* lr_device, float beta1,
+                  int64_t n, int32_t* step, float lr, const float* lr_device, float beta1,
                   float beta2, float eps, float weight_decay, float grad_scale, void* stream);
-int cal_adam_tick(int32_t* step, void* stream);   /* ++*step on the device */
+int cal_adam_tick(int32_t* step, void* stream);   /* ++step[0] on the device (manual stepping) */
 
 /* Poll the status word written by cal_prep (synchronises the stream): returns the CAL_ST_* bits,
  * or a negative CAL_E* / positive cudaError_t. */

@@ -1,0 +1,21 @@
+"""GPU experiment (needs a -DCAL_PHASE_TIMING build): per-phase cycle counts of CTA 0 of
+k_conv_fwd (status[16..]) and k_conv_bwd (status[32..]) at cfg-1 shapes."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import cal_b200
+from bench import build_batches, model_args
+batches, cfg = build_batches("spmotif", 128, 4, 1024, 666)
+torch.manual_seed(666)
+net = cal_b200.CausalGCN(10, 4, model_args()).cuda().train()
+tr = cal_b200.Trainer(net, cal_b200.batch_caps(batches), use_graph=False)
+dev = [tr.upload(b) for b in batches]
+for i in range(6):
+    tr.step(dev[i % 4])
+torch.cuda.synchronize()
+st = tr.eng.region("STATUS", torch.int32).cpu().tolist()
+names_f = ["prologue", "csr ptr", "csr seg", "gather", "wait W/sync", "gemm", "epilogue", "reduce+finalize"]
+names_b = ["prologue", "csr ptr", "stage+gather", "wait W/sync", "gemm dX", "dX store", "dW outer", "dW store", "reduce+finalize"]
+print("k_conv_fwd (last launched = MODE 2 masked, no reduce) cycles:", list(zip(names_f, st[16:24])), "sum", sum(st[16:24]))
+print("k_conv_bwd (layer 0) cycles:", list(zip(names_b, st[32:41])), "sum", sum(st[32:41]))
