@@ -22,6 +22,7 @@ WS_REGIONS = [
     "OUT_KEY", "CNT_IN", "CNT_OUT", "GRAPH_PTR", "NODE_GRAPH", "PERM", "INVPERM", "DIS", "X",
     "NODE_ATT", "PQ", "EDGE_ATT", "DISW", "AGG", "Z", "POOLED", "H1", "LOGP", "LOSS", "BN", "STATP",
     "WT", "GAT", "DLOGIT", "DH", "DU", "DPOOL", "DAGG", "DYM", "DNRM", "DT", "DP", "D", "GPART",
+    "OUT_NORM", "EDGE_WN", "EDGE_NA",
 ]
 WS = {n: i for i, n in enumerate(WS_REGIONS)}
 

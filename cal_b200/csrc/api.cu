@@ -15,6 +15,7 @@ void note_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::mem
 namespace {
 
 __global__ void k_copy_logp(const Ctx c, float* __restrict__ out) {
+  pdl_sync();
   const int B = imin(imax(c.dims[2], 0), c.Bm), C = c.C;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * B * C; i += gridDim.x * blockDim.x) {
     const int h = i / (B * C), r = i - h * B * C;
@@ -158,6 +159,9 @@ int build_ctx(const cal_model_desc* m, const cal_caps* caps, const cal_param_off
   c.dp = REG(float, CAL_WS_DP);
   c.D = REG(float, CAL_WS_D);
   c.gpart = REG(float, CAL_WS_GPART);
+  c.out_norm = REG(float, CAL_WS_OUT_NORM);
+  c.edge_wn = REG(float, CAL_WS_EDGE_WN);
+  c.edge_na = REG(float, CAL_WS_EDGE_NA);
 #undef REG
   for (int l = 0; l < CAL_MAX_LAYERS + 2; ++l) c.gp_conv[l] = lay.gp_conv[l];
   c.gp_att = lay.gp_att;
@@ -316,7 +320,7 @@ int cal_causal_forward(const cal_model_desc* m, const cal_caps* caps, const cal_
     else if (st == 3 + L) rc = launch_masked_forward(c, s);
     else if (st == 4 + L) rc = launch_heads_forward(c, c.with_loss, s);
     else if (st == 5 + L && out_logp != nullptr) {
-      k_copy_logp<<<imax(1, imin(ceil_div(3 * c.Bm * c.C, 256), kSMs)), 256, 0, s>>>(c, out_logp);
+      launch_k(k_copy_logp, dim3(imax(1, imin(ceil_div(3 * c.Bm * c.C, 256), kSMs))), dim3(256), 0, s, c, out_logp);
       note_launches(1);
       CAL_CUDA_CHECK_LAUNCH();
     }

@@ -18,6 +18,7 @@ namespace {
 __device__ __forceinline__ int clampN(const Ctx& c) { return imin(imax(c.dims[0], 0), c.Nm); }
 
 __global__ void __launch_bounds__(128) k_edge_att(const Ctx c) {
+  pdl_sync();
   const int N = clampN(c);
   const float be0 = c.params[c.po.edge_att_b], be1 = c.params[c.po.edge_att_b + 1];
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
@@ -43,7 +44,16 @@ __global__ void __launch_bounds__(128) k_edge_att(const Ctx c) {
     *reinterpret_cast<float2*>(c.watt + (size_t)c.out_pos[q1] * 2) = make_float2(1.f, 1.f);
     deg0 += 1.f;
     deg1 += 1.f;
-    *reinterpret_cast<float2*>(c.disw + (size_t)n * 2) = make_float2(1.0f / sqrtf(deg0), 1.0f / sqrtf(deg1));
+    const float2 dn = make_float2(1.0f / sqrtf(deg0), 1.0f / sqrtf(deg1));
+    *reinterpret_cast<float2*>(c.disw + (size_t)n * 2) = dn;
+    // per-entry factors of the masked convs' gather (so that it needs no per-source lookups)
+    const float2 an = *reinterpret_cast<const float2*>(c.natt + (size_t)n * 2);
+    for (int q = q0; q <= q1; ++q) {
+      const int pos = c.out_pos[q];
+      const float2 w = *reinterpret_cast<const float2*>(c.watt + (size_t)pos * 2);
+      *reinterpret_cast<float2*>(c.edge_wn + (size_t)pos * 2) = make_float2(dn.x * w.x, dn.y * w.y);
+      *reinterpret_cast<float2*>(c.edge_na + (size_t)pos * 2) = an;
+    }
   }
 }
 
@@ -55,6 +65,7 @@ __global__ void __launch_bounds__(128) k_edge_att(const Ctx c) {
 // ---------------------------------------------------------------------------------------------
 template <int VEC>
 __global__ void __launch_bounds__(256) k_masked_bwd_gather(const Ctx c) {
+  pdl_sync();
   constexpr int H = 32 * VEC;
   __shared__ double sRed[kRowWarps * H];
   __shared__ double sTot[2 * H];
@@ -126,6 +137,7 @@ __global__ void __launch_bounds__(256) k_masked_bwd_gather(const Ctx c) {
 // node d w_e (both branches), the edge softmax backward dt_e, and dp[n] = sum_e dt_e.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_norm_bwd(const Ctx c) {
+  pdl_sync();
   const int N = clampN(c);
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
     const int q0 = c.out_ptr[n], q1 = c.out_ptr[n + 1] - 1;
@@ -187,6 +199,7 @@ __global__ void __launch_bounds__(128) k_norm_bwd(const Ctx c) {
 // ---------------------------------------------------------------------------------------------
 template <int VEC>
 __global__ void __launch_bounds__(256) k_att_bwd(const Ctx c) {
+  pdl_sync();
   constexpr int H = 32 * VEC;
   __shared__ float sRed[kRowWarps * H];
   __shared__ float sScal[kRowWarps][4];
@@ -303,28 +316,28 @@ __global__ void __launch_bounds__(256) k_att_bwd(const Ctx c) {
 }  // namespace
 
 int launch_edge_att(const Ctx& c, cudaStream_t s) {
-  k_edge_att<<<imax(1, imin(ceil_div(c.Nm, 128), 8 * kSMs)), 128, 0, s>>>(c);
+  launch_k(k_edge_att, dim3(imax(1, imin(ceil_div(c.Nm, 128), 8 * kSMs))), dim3(128), 0, s, c);
   note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }
 
 int launch_masked_bwd_gather(const Ctx& c, cudaStream_t s) {
-  CAL_DISPATCH_VEC(c.H, { k_masked_bwd_gather<VEC><<<dim3(c.g_row / 2 > 0 ? c.g_row / 2 : 1, 2), 256, 0, s>>>(c); });
+  CAL_DISPATCH_VEC(c.H, { launch_k(k_masked_bwd_gather<VEC>, dim3(c.g_row / 2 > 0 ? c.g_row / 2 : 1, 2), dim3(256), 0, s, c); });
   note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }
 
 int launch_norm_backward(const Ctx& c, cudaStream_t s) {
-  k_norm_bwd<<<imax(1, imin(ceil_div(c.Nm, 128), 8 * kSMs)), 128, 0, s>>>(c);
+  launch_k(k_norm_bwd, dim3(imax(1, imin(ceil_div(c.Nm, 128), 8 * kSMs))), dim3(128), 0, s, c);
   note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }
 
 int launch_att_backward(const Ctx& c, cudaStream_t s) {
-  CAL_DISPATCH_VEC(c.H, { k_att_bwd<VEC><<<c.g_row, 256, 0, s>>>(c); });
+  CAL_DISPATCH_VEC(c.H, { launch_k(k_att_bwd<VEC>, dim3(c.g_row), dim3(256), 0, s, c); });
   note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;

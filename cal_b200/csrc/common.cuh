@@ -150,6 +150,35 @@ __device__ __forceinline__ double partial_total(const double* partial, int G, in
   return (s0 + s1) + (s2 + s3);
 }
 
+// ---- programmatic dependent launch (PDL) ----
+// Every kernel is launched with programmatic stream serialization: it may be scheduled as soon as
+// its predecessor has passed its own dependency wait, so launch latency and the independent part
+// of its prologue (weight staging) overlap the predecessor's tail.  Protocol used by all kernels:
+//   [prologue that reads nothing written by the immediate predecessor]
+//   pdl_wait();      // predecessor grid complete and flushed (hence, transitively, all earlier ones)
+//   pdl_trigger();   // successor may be scheduled now
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() {
+  pdl_wait();
+  pdl_trigger();
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface in cudaGetLastError()
+}
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int row_grid(int max_rows, int rows_per_cta = 4 * kRowWarps) {
   int g = ceil_div(max_rows > 0 ? max_rows : 1, rows_per_cta);

@@ -42,6 +42,7 @@ __device__ __forceinline__ Dims load_dims(const Ctx& c) {
 // bn_feat statistics (model.py:90): column sums of x [N, F] in fp64.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_feat_stats(const Ctx c) {
+  pdl_sync();
   const Dims d = load_dims(c);
   const int F = c.F, N = d.N;
   __shared__ double s_s[256], s_q[256];
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(256) k_feat_fwd(const Ctx c) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* W = c.params + c.po.conv_feat_w;
   for (int i = threadIdx.x; i < Fp * H; i += blockDim.x) sW[i] = i < F * H ? W[i] : 0.f;
+  pdl_sync();                                        // everything below may read the predecessor's output
   const float* sc = c.bnf(0, BN_SCALE);
   const float* sh = c.bnf(0, BN_SHIFT);
   float* out = c.Xl(0);
@@ -196,6 +198,7 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
   (void)conv;
 
   stage_matrix_async(sW, W, H * H);
+  pdl_sync();                                        // everything below may read the predecessor's output
 
   BnLane<VEC> bn;
   bn.load_fwd(c, bn_in, lane);
@@ -229,8 +232,8 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
           const int src = c.in_src[pb + e];
           sXs[e] = src;
           if (MODE == 2) {
-            sXn[e] = c.disw[(size_t)src * 2 + branch] * c.watt[(size_t)(pb + e) * 2 + branch];
-            sXa[e] = c.natt[(size_t)src * 2 + branch];
+            sXn[e] = c.edge_wn[(size_t)(pb + e) * 2 + branch];         // dis_w[source] * edge_att
+            sXa[e] = c.edge_na[(size_t)(pb + e) * 2 + branch];         // node_att[source]
           } else {
             sXn[e] = c.in_norm[pb + e];
           }
@@ -370,6 +373,7 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   stage_matrix_async(sW, c.wt_conv(layer), H * H);
+  pdl_sync();                                        // everything below may read the predecessor's output
 
   const int bn_in = 1 + layer;
   const int bn_up = layer == c.L - 1 ? kBnIdentity : 2 + layer;
@@ -412,7 +416,7 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
       if (!direct) {
         for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
           sXs[e] = c.out_dst[qb + e];
-          sXn[e] = c.in_norm[c.out_pos[qb + e]];
+          sXn[e] = c.out_norm[qb + e];
         }
         __syncthreads();
         for (int e = warp; e < cnt; e += kRowWarps)
@@ -455,7 +459,7 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
           xi.load_coherent(xin + (size_t)j * H, lane);
           for (int q = sPtr[lr]; q < sPtr[lr + 1]; ++q) {
             const int dd = c.out_dst[q];
-            const float w = c.in_norm[c.out_pos[q]];
+            const float w = c.out_norm[q];
             RowVec<VEC> gv, xv;
             gv.load_coherent(Dup + (size_t)dd * H, lane);
             xv.load_coherent(xup + (size_t)dd * H, lane);
@@ -544,6 +548,7 @@ __global__ void __launch_bounds__(256) k_masked_bwd_gemm(const Ctx c) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int branch = blockIdx.y;
   stage_matrix_async(sW, c.wt_conv(c.L + branch), H * H);
+  pdl_sync();                                        // everything below may read the predecessor's output
   const float* Z = c.Z + (size_t)branch * c.Nm * H;
   const float* A = c.agg + (size_t)branch * c.Nm * H;
   const float* dpool = c.dpool + (size_t)branch * c.Bm * H;
@@ -613,6 +618,7 @@ __global__ void __launch_bounds__(256) k_masked_bwd_gemm(const Ctx c) {
 // ---------------------------------------------------------------------------------------------
 template <int VEC>
 __global__ void __launch_bounds__(256) k_feat_bwd(const Ctx c) {
+  pdl_sync();
   constexpr int H = 32 * VEC;
   constexpr int FW = kFeatChunk / kRowWarps;       // feature columns per warp
   __shared__ __align__(16) float sG[kTileRows * H];
@@ -701,14 +707,14 @@ int set_smem(K kernel, size_t bytes) {
 }  // namespace
 
 int launch_feat_forward(const Ctx& c, cudaStream_t s) {
-  if (c.train) k_feat_stats<<<c.g_tile, 256, 0, s>>>(c);
+  if (c.train) launch_k(k_feat_stats, dim3(c.g_tile), dim3(256), 0, s, c);
   note_launches(c.train ? 2 : 1);
   const int Fp = (c.F + 3) & ~3;
   CAL_DISPATCH_VEC(c.H, {
     size_t smem = (size_t)Fp * c.H * 4 + (size_t)kTileRows * Fp * 4 + (size_t)kRowWarps * c.H * 8;
     int rc = set_smem(k_feat_fwd<VEC>, smem);
     if (rc) return rc;
-    k_feat_fwd<VEC><<<c.g_tile, 256, smem, s>>>(c);
+    launch_k(k_feat_fwd<VEC>, dim3(c.g_tile), dim3(256), smem, s, c);
   });
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
@@ -721,11 +727,11 @@ int launch_conv_forward(const Ctx& c, int layer, cudaStream_t s) {
     if (last) {
       int rc = set_smem(k_conv_fwd<VEC, 1>, smem);
       if (rc) return rc;
-      k_conv_fwd<VEC, 1><<<c.g_tile, 256, smem, s>>>(c, layer);
+      launch_k(k_conv_fwd<VEC, 1>, dim3(c.g_tile), dim3(256), smem, s, c, layer);
     } else {
       int rc = set_smem(k_conv_fwd<VEC, 0>, smem);
       if (rc) return rc;
-      k_conv_fwd<VEC, 0><<<c.g_tile, 256, smem, s>>>(c, layer);
+      launch_k(k_conv_fwd<VEC, 0>, dim3(c.g_tile), dim3(256), smem, s, c, layer);
     }
   });
   note_launches(1);
@@ -738,7 +744,7 @@ int launch_masked_forward(const Ctx& c, cudaStream_t s) {
     size_t smem = convf_smem_bytes<VEC>(kStageMasked);
     int rc = set_smem(k_conv_fwd<VEC, 2>, smem);
     if (rc) return rc;
-    k_conv_fwd<VEC, 2><<<dim3(c.g_tile, 2), 256, smem, s>>>(c, 0);
+    launch_k(k_conv_fwd<VEC, 2>, dim3(c.g_tile, 2), dim3(256), smem, s, c, 0);
   });
   note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
@@ -750,7 +756,7 @@ int launch_conv_backward(const Ctx& c, int layer, cudaStream_t s) {
     size_t smem = convb_smem_bytes<VEC>();
     int rc = set_smem(k_conv_bwd<VEC>, smem);
     if (rc) return rc;
-    k_conv_bwd<VEC><<<c.g_tile, 256, smem, s>>>(c, layer);
+    launch_k(k_conv_bwd<VEC>, dim3(c.g_tile), dim3(256), smem, s, c, layer);
   });
   note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
@@ -762,7 +768,7 @@ int launch_masked_bwd_gemm(const Ctx& c, cudaStream_t s) {
     size_t smem = (size_t)c.H * c.H * 4 + 2 * (size_t)kTileRows * c.H * 4 + (size_t)kRowWarps * c.H * 8;
     int rc = set_smem(k_masked_bwd_gemm<VEC>, smem);
     if (rc) return rc;
-    k_masked_bwd_gemm<VEC><<<dim3(c.g_tile, 2), 256, smem, s>>>(c);
+    launch_k(k_masked_bwd_gemm<VEC>, dim3(c.g_tile, 2), dim3(256), smem, s, c);
   });
   note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
@@ -771,7 +777,7 @@ int launch_masked_bwd_gemm(const Ctx& c, cudaStream_t s) {
 
 int launch_feat_backward(const Ctx& c, cudaStream_t s) {
   CAL_DISPATCH_VEC(c.H, {
-    k_feat_bwd<VEC><<<dim3(c.g_tile, ceil_div(c.F, kFeatChunk)), 256, 0, s>>>(c);
+    launch_k(k_feat_bwd<VEC>, dim3(c.g_tile, ceil_div(c.F, kFeatChunk)), dim3(256), 0, s, c);
   });
   note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();

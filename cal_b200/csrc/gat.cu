@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(256) k_gat_lin(const Ctx c, const int layer) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GatBufs g = gat_bufs(c, layer);
   stage_matrix_async(sW, c.params + c.po.convs_w[layer], H * H);
+  pdl_sync();                                        // everything below may read the predecessor's output
   BnLane<VEC> bn;
   bn.load_fwd(c, 1 + layer, lane);
   float ai[VEC], aj[VEC];
@@ -141,6 +142,7 @@ __device__ __forceinline__ float keep_of(const Ctx& c, int layer, int EN, int ke
 // ---------------------------------------------------------------------------------------------
 template <int VEC, bool LASTL>
 __global__ void __launch_bounds__(256) k_gat_agg(const Ctx c, const int layer) {
+  pdl_sync();
   constexpr int H = 32 * VEC;
   __shared__ double sRed[kRowWarps * H];
   __shared__ double sTot[4 * H];
@@ -202,6 +204,7 @@ __global__ void __launch_bounds__(256) k_gat_agg(const Ctx c, const int layer) {
 // ---------------------------------------------------------------------------------------------
 template <int VEC>
 __global__ void __launch_bounds__(256) k_gat_bwd_edge(const Ctx c, const int layer) {
+  pdl_sync();
   constexpr int H = 32 * VEC;
   const int N = clampN(c);
   const int EN = imin(imax(c.dims[1], 0), c.Em) + N;
@@ -279,6 +282,7 @@ __global__ void __launch_bounds__(256) k_gat_bwd_node(const Ctx c, const int lay
   const int heads = c.heads, lph = 32 / heads, head = lane / lph;
 
   stage_matrix_async(sW, c.wt_conv(layer), H * H);
+  pdl_sync();                                        // everything below may read the predecessor's output
 
   const int bn_in = 1 + layer;
   const int bn_up = layer == c.L - 1 ? kBnIdentity : 2 + layer;
@@ -426,9 +430,9 @@ int launch_gat_forward(const Ctx& c, int layer, cudaStream_t s) {
     size_t smem = (size_t)c.H * c.H * 4 + (size_t)kTileRows * c.H * 4;
     int rc = set_smem_g(k_gat_lin<VEC>, smem);
     if (rc) return rc;
-    k_gat_lin<VEC><<<c.g_tile, 256, smem, s>>>(c, layer);
-    if (last) k_gat_agg<VEC, true><<<c.g_row, 256, 0, s>>>(c, layer);
-    else k_gat_agg<VEC, false><<<c.g_row, 256, 0, s>>>(c, layer);
+    launch_k(k_gat_lin<VEC>, dim3(c.g_tile), dim3(256), smem, s, c, layer);
+    if (last) launch_k(k_gat_agg<VEC, true>, dim3(c.g_row), dim3(256), 0, s, c, layer);
+    else launch_k(k_gat_agg<VEC, false>, dim3(c.g_row), dim3(256), 0, s, c, layer);
   });
   note_launches(2);
   CAL_CUDA_CHECK_LAUNCH();
@@ -437,11 +441,11 @@ int launch_gat_forward(const Ctx& c, int layer, cudaStream_t s) {
 
 int launch_gat_backward(const Ctx& c, int layer, cudaStream_t s) {
   CAL_DISPATCH_VEC(c.H, {
-    k_gat_bwd_edge<VEC><<<c.g_row, 256, 0, s>>>(c, layer);
+    launch_k(k_gat_bwd_edge<VEC>, dim3(c.g_row), dim3(256), 0, s, c, layer);
     size_t smem = gatb_smem_bytes<VEC>();
     int rc = set_smem_g(k_gat_bwd_node<VEC>, smem);
     if (rc) return rc;
-    k_gat_bwd_node<VEC><<<c.g_tile, 256, smem, s>>>(c, layer);
+    launch_k(k_gat_bwd_node<VEC>, dim3(c.g_tile), dim3(256), smem, s, c, layer);
   });
   note_launches(2);
   CAL_CUDA_CHECK_LAUNCH();

@@ -16,6 +16,7 @@ __device__ __forceinline__ int clampB(const Ctx& c) { return imin(imax(c.dims[2]
 
 template <int VEC>
 __global__ void __launch_bounds__(256) k_pool(const Ctx c) {
+  pdl_sync();
   constexpr int H = 32 * VEC;
   __shared__ float sRed[2][kRowWarps][H];
   const int B = clampB(c);
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(256) k_head1_fwd(const Ctx c) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bn1 = c.L + 3 + h;
   stage_matrix_async(sW, c.wt_fc1(h), K1 * H);
+  pdl_sync();                                        // everything below may read the predecessor's output
 
   if (c.train) {
     // bn1 statistics over all B rows (every CTA of this head computes them; tile 0 publishes)
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(256) k_head1_fwd(const Ctx c) {
 // fc2 + log_softmax + loss: warp per graph row, blockIdx.y = head.
 template <int VEC>
 __global__ void __launch_bounds__(256) k_head2_fwd(const Ctx c) {
+  pdl_sync();
   constexpr int H = 32 * VEC;
   __shared__ float sLoss[kRowWarps][2];
   const int B = clampB(c);
@@ -256,6 +259,7 @@ __global__ void __launch_bounds__(256) k_head2_fwd(const Ctx c) {
 // fc2 / log_softmax / bn2 backward: warp per graph row, blockIdx.y = head.
 template <int VEC>
 __global__ void __launch_bounds__(256) k_head2_bwd(const Ctx c) {
+  pdl_sync();
   constexpr int H = 32 * VEC;
   __shared__ __align__(16) float sH2[kHeadRowsPerCta][H];
   __shared__ float sDl[kHeadRowsPerCta][32];
@@ -350,6 +354,7 @@ __global__ void __launch_bounds__(256) k_head1_bwd(const Ctx c) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bn1 = c.L + 3 + h, bn2 = c.L + 6 + h;
   stage_matrix_async(sW, c.params + c.po.fc1_w[h], H * K1);
+  pdl_sync();                                        // everything below may read the predecessor's output
   BnLane<VEC> b2;
   b2.load_bwd(c, bn2, lane);
   const float* H1 = c.H1 + (size_t)h * c.Bm * H;
@@ -432,6 +437,7 @@ __global__ void __launch_bounds__(256) k_head1_bwd(const Ctx c) {
 // routed through the inverse permutation (model.py:152-157).
 template <int VEC>
 __global__ void __launch_bounds__(256) k_dpool(const Ctx c) {
+  pdl_sync();
   constexpr int H = 32 * VEC;
   const int B = clampB(c);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -488,12 +494,12 @@ int launch_heads_forward(const Ctx& c, int with_loss, cudaStream_t s) {
   (void)with_loss;
   const int H = c.H, K1m = c.cat ? 2 * H : H;
   CAL_DISPATCH_VEC(c.H, {
-    k_pool<VEC><<<c.Bm, 256, 0, s>>>(c);
+    launch_k(k_pool<VEC>, dim3(c.Bm), dim3(256), 0, s, c);
     size_t smem = (size_t)K1m * H * 4 + (size_t)kTileRows * K1m * 4 + (size_t)kRowWarps * H * 8 + 2 * K1m * 4 + 512 * 8;
     int rc = set_smem_h(k_head1_fwd<VEC>, smem);
     if (rc) return rc;
-    k_head1_fwd<VEC><<<dim3(c.t_head1, 3), 256, smem, s>>>(c);
-    k_head2_fwd<VEC><<<dim3(c.g_head2, 3), 256, 0, s>>>(c);
+    launch_k(k_head1_fwd<VEC>, dim3(c.t_head1, 3), dim3(256), smem, s, c);
+    launch_k(k_head2_fwd<VEC>, dim3(c.g_head2, 3), dim3(256), 0, s, c);
   });
   note_launches(3);
   CAL_CUDA_CHECK_LAUNCH();
@@ -503,12 +509,12 @@ int launch_heads_forward(const Ctx& c, int with_loss, cudaStream_t s) {
 int launch_heads_backward(const Ctx& c, cudaStream_t s) {
   const int H = c.H, K1m = c.cat ? 2 * H : H;
   CAL_DISPATCH_VEC(c.H, {
-    k_head2_bwd<VEC><<<dim3(c.g_head2, 3), 256, 0, s>>>(c);
+    launch_k(k_head2_bwd<VEC>, dim3(c.g_head2, 3), dim3(256), 0, s, c);
     size_t smem = (size_t)H * K1m * 4 + (size_t)kTileRows * H * 4 + (size_t)kTileRows * K1m * 4 + (size_t)kRowWarps * H * 8;
     int rc = set_smem_h(k_head1_bwd<VEC>, smem);
     if (rc) return rc;
-    k_head1_bwd<VEC><<<dim3(c.t_head1, 3), 256, smem, s>>>(c);
-    k_dpool<VEC><<<ceil_div(c.Bm, kRowWarps), 256, 0, s>>>(c);
+    launch_k(k_head1_bwd<VEC>, dim3(c.t_head1, 3), dim3(256), smem, s, c);
+    launch_k(k_dpool<VEC>, dim3(ceil_div(c.Bm, kRowWarps)), dim3(256), 0, s, c);
   });
   note_launches(3);
   CAL_CUDA_CHECK_LAUNCH();

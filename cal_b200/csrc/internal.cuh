@@ -8,9 +8,9 @@ namespace cal {
 constexpr int kTileRows = 32;                  // destination rows per GEMM tile (8 warps x 4 rows)
 constexpr int kRPW = kTileRows / kRowWarps;    // rows per warp inside a tile
 constexpr int kEdgeStage = 1024;               // CSR entries staged in shared memory per tile (legacy direct path)
-constexpr int kStageFwd = 96;                  // neighbour rows staged in shared memory per row batch (forward layers)
+constexpr int kStageFwd = 128;                 // neighbour rows staged in shared memory per row batch (forward layers)
 constexpr int kStageMasked = 40;               // ... masked convs (2 CTAs per SM)
-constexpr int kStageBwd = 96;                  // ... backward layers (two rows per entry)
+constexpr int kStageBwd = 112;                 // ... backward layers (two rows per entry)
 constexpr int kNumBN = CAL_MAX_BN + 1;         // + the identity record used by the top layer's backward
 constexpr int kBnIdentity = CAL_MAX_BN;
 constexpr int kHeadRowsPerCta = 8;             // head2 kernels: one warp per graph row
@@ -77,6 +77,7 @@ struct Ctx {
   int *in_ptr, *in_src, *in_key, *out_ptr, *out_dst, *out_pos, *out_key, *cnt_in, *cnt_out;
   int *graph_ptr, *node_graph, *perm, *invperm;
   float *in_norm, *dis, *X, *natt, *pq, *watt, *disw, *agg, *Z, *pooled, *H1, *logp, *loss, *bn;
+  float *out_norm, *edge_wn, *edge_na;
   int with_loss;
   double* statp;
   double* gsum;             // hierarchical grid-sum scratch: [kGsSites][(Gmax + Gmax/8 + 1) * gs_n] doubles

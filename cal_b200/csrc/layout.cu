@@ -84,6 +84,9 @@ int compute_layout(const cal_model_desc* m, const cal_caps* caps, Layout* lay) {
   sz[CAL_WS_DT] = EP * 2 * 4;
   sz[CAL_WS_DP] = Nm * 2 * 4;
   sz[CAL_WS_D] = 2 * Nm * H * 4;
+  sz[CAL_WS_OUT_NORM] = EP * 4;
+  sz[CAL_WS_EDGE_WN] = EP * 2 * 4;
+  sz[CAL_WS_EDGE_NA] = EP * 2 * 4;
 
   size_t gp = 0;
   for (size_t l = 0; l < L + 2; ++l) {

@@ -40,6 +40,7 @@ __device__ __forceinline__ int nparts_of(const Ctx& c, int rule, int gmax) {
 }
 
 __global__ void __launch_bounds__(256) k_grad_reduce(const Ctx c, const RedTable t, const int n_generic_blocks) {
+  pdl_sync();
   if ((int)blockIdx.x < n_generic_blocks) {
     // generic entries: thread per output element
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < t.total;
@@ -103,6 +104,7 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
                        float* __restrict__ v, long long n, int* __restrict__ step, unsigned int* __restrict__ done,
                        float lr, const float* __restrict__ lr_dev, float b1, float b2, float eps, float wd,
                        float gscale) {
+  pdl_sync();
   __shared__ float s_c[2];
   __shared__ int s_t;
   if (threadIdx.x == 0) {       // bias corrections in fp64 like the Python scalars of torch.optim.Adam
@@ -139,7 +141,8 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
   }
 }
 
-__global__ void k_tick(int* step) { *step += 1; }
+__global__ void k_tick(int* step) {
+  pdl_sync(); *step += 1; }
 
 }  // namespace
 
@@ -189,7 +192,7 @@ int launch_grad_reduce(const Ctx& c, cudaStream_t s) {
   t.feat_gmax = c.g_tile;
   const int nb = imax(1, imin((int)((t.total + 255) / 256), 4 * kSMs));
   const int nf = imax(1, imin(ceil_div(c.F, kRowWarps), kSMs));
-  k_grad_reduce<<<nb + nf, 256, 0, s>>>(c, t, nb);
+  launch_k(k_grad_reduce, dim3(nb + nf), dim3(256), 0, s, c, t, nb);
   note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
@@ -205,7 +208,7 @@ extern "C" int cal_adam_step(float* params, const float* grads, float* exp_avg, 
   int g = (int)((n + 255) / 256);
   if (g > 4 * cal::kSMs) g = 4 * cal::kSMs;
   // step[0] = number of updates applied so far (advanced by this call); step[1] = arrival counter
-  cal::k_adam<<<g, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, (long long)n, step,
+  cal::launch_k(cal::k_adam, dim3(g), dim3(256), 0, (cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, (long long)n, step,
                                                   reinterpret_cast<unsigned int*>(step + 1), lr, lr_device, beta1,
                                                   beta2, eps, weight_decay, grad_scale);
   cal::note_launches(1);
@@ -215,7 +218,7 @@ extern "C" int cal_adam_step(float* params, const float* grads, float* exp_avg, 
 
 extern "C" int cal_adam_tick(int32_t* step, void* stream) {
   if (!step) return CAL_ENULL;
-  cal::k_tick<<<1, 1, 0, (cudaStream_t)stream>>>(step);
+  cal::launch_k(cal::k_tick, dim3(1), dim3(1), 0, (cudaStream_t)stream, step);
   cal::note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;

@@ -11,6 +11,7 @@
 namespace cal {
 
 __global__ void k_prep_init(const Ctx c) {
+  pdl_sync();
   const int N = c.dims[0], E = c.dims[1], B = c.dims[2];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   if (tid == 0) {
@@ -59,6 +60,7 @@ __global__ void k_prep_init(const Ctx c) {
 }
 
 __global__ void k_prep_count(const Ctx c) {
+  pdl_sync();
   if (c.status[0] & kStCapacity) return;
   const int N = c.dims[0], E = c.dims[1];
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
@@ -76,6 +78,7 @@ __global__ void k_prep_count(const Ctx c) {
 
 // Exclusive scan of (count + 1) over the nodes (the +1 is the appended self loop), one CTA.
 __global__ void __launch_bounds__(1024) k_prep_scan(const Ctx c) {
+  pdl_sync();
   if (c.status[0] & kStCapacity) return;
   const int N = c.dims[0];
   __shared__ int s_part[2][1024];
@@ -118,6 +121,7 @@ __global__ void __launch_bounds__(1024) k_prep_scan(const Ctx c) {
 }
 
 __global__ void k_prep_fill(const Ctx c) {
+  pdl_sync();
   if (c.status[0] & kStCapacity) return;
   const int N = c.dims[0], E = c.dims[1];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
@@ -149,6 +153,7 @@ __device__ __forceinline__ void insertion_sort(int* a, int n) {
 // Order every row by edge_index column, resolve endpoints, unweighted degree (by source row,
 // gcn_conv.py:66) and deg^-1/2.
 __global__ void k_prep_sort(const Ctx c) {
+  pdl_sync();
   if (c.status[0] & kStCapacity) return;
   const int N = c.dims[0], E = c.dims[1];
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
@@ -171,19 +176,22 @@ __global__ void k_prep_sort(const Ctx c) {
 
 // Link the two orderings (out position -> in position) and the unweighted norm.
 __global__ void k_prep_link(const Ctx c) {
+  pdl_sync();
   if (c.status[0] & kStCapacity) return;
   const int N = c.dims[0];
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
     const float dn = c.dis[n];
     for (int p = c.in_ptr[n]; p < c.in_ptr[n + 1]; ++p) {
       int s = c.in_src[p], key = c.in_key[p];
-      c.in_norm[p] = c.dis[s] * dn;          // dis[row] * 1 * dis[col]
+      const float nrm = c.dis[s] * dn;       // dis[row] * 1 * dis[col]
+      c.in_norm[p] = nrm;
       int lo = c.out_ptr[s], hi = c.out_ptr[s + 1] - 1;
       while (lo < hi) {
         int mid = (lo + hi) >> 1;
         if (c.out_key[mid] < key) lo = mid + 1; else hi = mid;
       }
       c.out_pos[lo] = p;
+      c.out_norm[lo] = nrm;
     }
   }
 }
@@ -192,12 +200,12 @@ int launch_prep(const Ctx& c, cudaStream_t s) {
   const int T = 256;
   int gn = imax(1, imin(ceil_div(imax(c.Nm, c.Bm + 1), T), 4 * kSMs));
   int ge = imax(1, imin(ceil_div(imax(c.Em, c.Nm), T), 4 * kSMs));
-  k_prep_init<<<gn, T, 0, s>>>(c);
-  k_prep_count<<<ge, T, 0, s>>>(c);
-  k_prep_scan<<<1, 1024, 0, s>>>(c);
-  k_prep_fill<<<ge, T, 0, s>>>(c);
-  k_prep_sort<<<imax(1, imin(ceil_div(c.Nm, 128), 8 * kSMs)), 128, 0, s>>>(c);
-  k_prep_link<<<imax(1, imin(ceil_div(c.Nm, 128), 8 * kSMs)), 128, 0, s>>>(c);
+  launch_k(k_prep_init, dim3(gn), dim3(T), 0, s, c);
+  launch_k(k_prep_count, dim3(ge), dim3(T), 0, s, c);
+  launch_k(k_prep_scan, dim3(1), dim3(1024), 0, s, c);
+  launch_k(k_prep_fill, dim3(ge), dim3(T), 0, s, c);
+  launch_k(k_prep_sort, dim3(imax(1, imin(ceil_div(c.Nm, 128), 8 * kSMs))), dim3(128), 0, s, c);
+  launch_k(k_prep_link, dim3(imax(1, imin(ceil_div(c.Nm, 128), 8 * kSMs))), dim3(128), 0, s, c);
   note_launches(6);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
@@ -209,6 +217,7 @@ int launch_prep(const Ctx& c, cudaStream_t s) {
 // also the BatchNorm affine from the running statistics.
 // ---------------------------------------------------------------------------------------------
 __global__ void k_param_prep(const Ctx c, const int n_tiles) {
+  pdl_sync();
   __shared__ float tile[32][33];
   const int H = c.H, hb = H / 32;
   const int n_conv = c.L + 2;
@@ -267,7 +276,7 @@ __global__ void k_param_prep(const Ctx c, const int n_tiles) {
 int launch_param_prep(const Ctx& c, cudaStream_t s) {
   const int hb = c.H / 32;
   const int n_tiles = (c.L + 2) * hb * hb + 2 * hb * hb + hb * ((c.cat ? 2 * c.H : c.H) / 32);
-  k_param_prep<<<n_tiles + 1, dim3(32, 8), 0, s>>>(c, n_tiles);
+  launch_k(k_param_prep, dim3(n_tiles + 1), dim3(32, 8), 0, s, c, n_tiles);
   note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;

@@ -159,6 +159,9 @@ enum cal_ws_region {
   CAL_WS_DP,           /* f32[maxN][2] */
   CAL_WS_D,            /* f32[2][maxN][H] ping-pong gradient w.r.t. BatchNorm outputs */
   CAL_WS_GPART,        /* f32 per-CTA partial parameter gradients */
+  CAL_WS_OUT_NORM,     /* f32[EP] unweighted norm by out-CSR position (= IN_NORM[OUT_POS]) */
+  CAL_WS_EDGE_WN,      /* f32[EP][2] dis_w[source] * edge_att by in-CSR position (weighted norm without the target factor) */
+  CAL_WS_EDGE_NA,      /* f32[EP][2] node_att[source] by in-CSR position */
   CAL_WS_REGION_COUNT
 };
 
