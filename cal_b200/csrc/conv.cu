@@ -20,16 +20,7 @@ struct Dims {
   int N, E, B;
 };
 
-// Optional per-phase cycle counters (CTA 0, thread 0) for latency analysis: -DCAL_PHASE_TIMING.
-#ifdef CAL_PHASE_TIMING
-#define PT_DECL long long pt_t0 = clock64(); int pt_i = 0; long long pt_v[12];
-#define PT_MARK() do { long long t_ = clock64(); if (pt_i < 12) pt_v[pt_i++] = t_ - pt_t0; pt_t0 = t_; } while (0)
-#define PT_DUMP(c, base) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) for (int q_ = 0; q_ < pt_i; ++q_) (c).status[(base) + q_] = (int)pt_v[q_]; } while (0)
-#else
-#define PT_DECL
-#define PT_MARK()
-#define PT_DUMP(c, base)
-#endif
+
 __device__ __forceinline__ Dims load_dims(const Ctx& c) {
   Dims d;
   d.N = imin(imax(c.dims[0], 0), c.Nm);

@@ -1,16 +1,29 @@
 // head.cu -- global_add_pool, the random-intervention mix, the three readout MLPs, the loss, and
 // their backward passes (model.py:115-164, train_causal.py:178-186).
 //
-//   pool : xc_g[b] = sum_{batch_n = b} zc[n], xo_g likewise (CTA per graph, fixed order, no atomics)
-//   head1: u_c = xc_g, u_o = xo_g, u_co = xc_g[perm] (+ or ||) xo_g;  h1 = relu(fc1(bn1(u)))
-//   head2: logp = log_softmax(fc2(bn2(h1)));  KL(uniform || c) batchmean, NLL(o), NLL(co)
-// BatchNorm over the B graph rows: bn1 statistics are recomputed by every head1 CTA from the
-// pooled rows (B x H values, L2 resident); bn2 statistics use the partial-sum / last-CTA scheme.
+//   pool   : xc_g[b] = sum_{batch_n = b} zc[n], xo_g likewise (CTA per graph, fixed order, no atomics)
+//   readout: u_c = xc_g, u_o = xo_g, u_co = xc_g[perm] (+ or ||) xo_g;
+//            logp = log_softmax(fc2(bn2(relu(fc1(bn1(u)))))); KL(uniform || c) batchmean, NLL(o), NLL(co)
+//
+// One thread-block CLUSTER of 8 CTAs per readout head.  CTA j of a cluster owns a 1/8 COLUMN slice
+// and all B graph rows of it, so every BatchNorm over the B rows (bn1 on the input slice, bn2 on the
+// hidden slice) and every bias / BatchNorm / fc2 / fc1 weight-gradient reduction over rows is local
+// to one CTA -- no cross-CTA partial sums, no serial tails.  The two places where columns mix (fc1:
+// K split over the input slices; fc1 backward: K split over the hidden slices) exchange their
+// [rows x H] partial products through distributed shared memory (reduce-scatter by column slice).
+// Parameter gradients of the readout are written straight into the flat gradient buffer.
+#include <cooperative_groups.h>
+
 #include "internal.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace cal {
 
 namespace {
+
+constexpr int kRC = 8;            // CTAs per cluster = column slices
+constexpr int kChunk = 128;       // graph rows per GEMM / exchange chunk
 
 __device__ __forceinline__ int clampB(const Ctx& c) { return imin(imax(c.dims[2], 0), c.Bm); }
 
@@ -61,380 +74,553 @@ __device__ __forceinline__ float head_input(const Ctx& c, int h, int b, int k, i
   return gc[(size_t)c.perm[b] * H + k] + go[(size_t)b * H + k];
 }
 
-// smem: sW [K1][H] | sA [R][K1] | sRed f64 [8][H] | sSc [K1] | sSh [K1] | sSum f64 [2][256]
-template <int VEC>
-__global__ void __launch_bounds__(256) k_head1_fwd(const Ctx c) {
-  constexpr int H = 32 * VEC;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int B = clampB(c);
-  const int h = blockIdx.y, tile = blockIdx.x;
-  const int row0 = tile * kTileRows;
-  if (row0 >= B) return;
-  const int K1 = (h == 2 && c.cat) ? 2 * H : H;
-  float* sW = reinterpret_cast<float*>(smem_raw);
-  float* sA = sW + (size_t)K1 * H;
-  double* sRed = reinterpret_cast<double*>(sA + (size_t)kTileRows * K1);
-  float* sSc = reinterpret_cast<float*>(sRed + kRowWarps * H);
-  float* sSh = sSc + K1;
-  double* sSum = reinterpret_cast<double*>(sSh + K1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bn1 = c.L + 3 + h;
-  stage_matrix_async(sW, c.wt_fc1(h), K1 * H);
-  pdl_sync();                                        // everything below may read the predecessor's output
-
-  if (c.train) {
-    // bn1 statistics over all B rows (every CTA of this head computes them; tile 0 publishes)
-    const int rpar = 256 / K1 > 0 ? 256 / K1 : 1;
-    const int col = threadIdx.x % K1, rs = threadIdx.x / K1;
-    double s = 0.0, q = 0.0;
-    if (rs < rpar)
-      for (int b = rs; b < B; b += rpar) {
-        double v = (double)head_input(c, h, b, col, H);
-        s += v;
-        q += v * v;
-      }
-    sSum[threadIdx.x] = s;
-    sSum[256 + threadIdx.x] = q;
-    __syncthreads();
-    if (threadIdx.x < K1) {
-      double a = 0.0, bq = 0.0;
-      for (int r = 0; r < rpar; ++r) {
-        a += sSum[r * K1 + threadIdx.x];
-        bq += sSum[256 + r * K1 + threadIdx.x];
-      }
-      const int k = threadIdx.x;
-      double mean = a / B, var = bq / B - mean * mean;
-      if (var < 0.0) var = 0.0;
-      float rstd = (float)(1.0 / sqrt(var + (double)c.eps));
-      float g = c.params[c.bn_gamma[bn1] + k], be = c.params[c.bn_beta[bn1] + k];
-      float sc = g * rstd, sh = be - (float)mean * sc;
-      sSc[k] = sc;
-      sSh[k] = sh;
-      if (tile == 0) {
-        c.bnf(bn1, BN_SCALE)[k] = sc;
-        c.bnf(bn1, BN_SHIFT)[k] = sh;
-        c.bnf(bn1, BN_MEAN)[k] = (float)mean;
-        c.bnf(bn1, BN_RSTD)[k] = rstd;
-        if (c.bn_buffers != nullptr) {
-          double unb = B > 1 ? var * ((double)B / (double)(B - 1)) : var;
-          float* rm = c.bn_buffers + c.bn_rm[bn1];
-          float* rv = c.bn_buffers + c.bn_rv[bn1];
-          rm[k] = (1.f - c.momentum) * rm[k] + c.momentum * (float)mean;
-          rv[k] = (1.f - c.momentum) * rv[k] + c.momentum * (float)unb;
-        }
-      }
-    }
-    if (tile == 0 && threadIdx.x == 0 && c.nbt != nullptr) c.nbt[bn1] += 1;
-  } else {
-    for (int k = threadIdx.x; k < K1; k += blockDim.x) {
-      sSc[k] = c.bnf(bn1, BN_SCALE)[k];
-      sSh[k] = c.bnf(bn1, BN_SHIFT)[k];
-    }
+// Column sums over the B rows of two per-element quantities, for `ncols` (4, 8, 16 or 32) columns,
+// in fp64.  f(b, col, v0, v1) yields the two values.  256 threads = ncols columns x (256 / ncols)
+// row parts; fixed order => deterministic.  Results in out0[col], out1[col] (shared memory).
+template <typename F>
+__device__ __forceinline__ void column_sums2(int B, int ncols, double* scratch /*[2][256]*/, double* out0,
+                                             double* out1, F f) {
+  const int t = threadIdx.x;
+  const int nparts = 256 / ncols;
+  const int col = t % ncols, part = t / ncols;
+  double s0 = 0.0, s1 = 0.0;
+  for (int b = part; b < B; b += nparts) {
+    float v0, v1;
+    f(b, col, v0, v1);
+    s0 += (double)v0;
+    s1 += (double)v1;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kTileRows * K1; i += blockDim.x) {
-    const int r = i / K1, k = i - r * K1;
-    float v = 0.f;
-    if (row0 + r < B) v = fmaf(head_input(c, h, row0 + r, k, H), sSc[k], sSh[k]);
-    sA[i] = v;
+  scratch[t] = s0;
+  scratch[256 + t] = s1;
+  __syncthreads();
+  if (t < ncols) {
+    double a = 0.0, bq = 0.0;
+    for (int p = 0; p < nparts; ++p) {
+      a += scratch[p * ncols + t];
+      bq += scratch[256 + p * ncols + t];
+    }
+    out0[t] = a;
+    out1[t] = bq;
+  }
+  __syncthreads();
+}
+
+struct ReadoutSmem {
+  size_t off_u, off_w, off_p, off_h, off_x, off_du, off_lg, off_misc, total;   // bytes
+};
+// Shared-memory layout of the readout kernels for Bp rows (multiple of kChunk), hidden H, KSm =
+// widest input slice, C classes.
+__host__ __device__ inline ReadoutSmem readout_smem(int Bp, int H, int KSm, int C, bool backward) {
+  const int HS = H / kRC;
+  ReadoutSmem s;
+  size_t o = 0;
+  s.off_u = o;    o += (size_t)Bp * KSm * 4;                            // input slice (raw / normalised)
+  s.off_w = o;    o += (size_t)(backward ? HS * 2 * H : KSm * H) * 4;   // fc1 weight slice
+  s.off_p = o;    o += (size_t)imax(kChunk * H, Bp * C) * 4;            // partial products / partial logits / d logits
+  s.off_h = o;    o += (size_t)Bp * HS * 4;                             // hidden slice
+  s.off_x = o;    o += backward ? (size_t)Bp * HS * 4 : 0;              // backward: u = d(fc1 out) slice
+  s.off_du = o;   o += backward ? (size_t)Bp * KSm * 4 : 0;             // backward: gathered d(bn1 out) slice
+  s.off_lg = o;   o += backward ? 0 : (size_t)Bp * C * 4;               // forward: summed logits (CTA 0)
+  s.off_misc = o; o += 2 * 256 * 8 + 256 * 8 + 512 * 4;                 // fp64 scratch | fp64 sums [4][64] | float consts [16][32]
+  s.total = o;
+  return s;
+}
+
+// training-mode BatchNorm over the B local rows of `ncols` columns (global column k0 + t):
+// scale / shift into sc / sh, the record into the workspace, running statistics updated.
+__device__ __forceinline__ void bn_local_finalize(const Ctx& c, int id, int k0, int ncols, int B, const double* sum,
+                                                  const double* sq, float* sc, float* sh) {
+  const int t = threadIdx.x;
+  if (t < ncols) {
+    const int k = k0 + t;
+    double mean = B > 0 ? sum[t] / B : 0.0, var = B > 0 ? sq[t] / B - mean * mean : 0.0;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)c.eps));
+    const float s = c.params[c.bn_gamma[id] + k] * rstd;
+    const float o = c.params[c.bn_beta[id] + k] - (float)mean * s;
+    sc[t] = s;
+    sh[t] = o;
+    c.bnf(id, BN_SCALE)[k] = s;
+    c.bnf(id, BN_SHIFT)[k] = o;
+    c.bnf(id, BN_MEAN)[k] = (float)mean;
+    c.bnf(id, BN_RSTD)[k] = rstd;
+    if (c.bn_buffers != nullptr && c.bn_rm[id] >= 0) {
+      const double unb = B > 1 ? var * ((double)B / (double)(B - 1)) : var;
+      float* rm = c.bn_buffers + c.bn_rm[id];
+      float* rv = c.bn_buffers + c.bn_rv[id];
+      rm[k] = (1.f - c.momentum) * rm[k] + c.momentum * (float)mean;
+      rv[k] = (1.f - c.momentum) * rv[k] + c.momentum * (float)unb;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Readout forward.  grid (8, 3), cluster (8, 1, 1): blockIdx.y = head (c, o, co), blockIdx.x = slice.
+// ---------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_fwd(const Ctx c) {
+  constexpr int H = 32 * VEC, HS = H / kRC, CT = H / 16;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cg::cluster_group cl = cg::this_cluster();
+  const int B = clampB(c);
+  const int h = blockIdx.y, j = blockIdx.x;
+  const int K1 = (h == 2 && c.cat) ? 2 * H : H, KS = K1 / kRC;
+  const int Bp = ceil_div(imax(c.Bm, 1), kChunk) * kChunk;
+  const ReadoutSmem L = readout_smem(Bp, H, c.cat ? 2 * HS : HS, c.C, false);
+  float* sU = reinterpret_cast<float*>(smem_raw + L.off_u);
+  float* sW = reinterpret_cast<float*>(smem_raw + L.off_w);
+  float* sP = reinterpret_cast<float*>(smem_raw + L.off_p);
+  float* sH = reinterpret_cast<float*>(smem_raw + L.off_h);
+  float* sLg = reinterpret_cast<float*>(smem_raw + L.off_lg);
+  double* scratch = reinterpret_cast<double*>(smem_raw + L.off_misc);
+  double* sum = scratch + 512;                        // [64]
+  double* sq = sum + 64;                              // [64]
+  float* fc = reinterpret_cast<float*>(scratch + 512 + 256);
+  float* sc1 = fc;                                    // [32] each
+  float* sh1 = fc + 32;
+  float* sc2 = fc + 64;
+  float* sh2 = fc + 96;
+  const int t = threadIdx.x;
+  const int k0 = j * KS, m0 = j * HS;
+  const int bn1 = c.L + 3 + h, bn2 = c.L + 6 + h;
+  const int C = c.C;
+
+  // fc1 weight slice, transposed copy [K1][H] made by k_param_prep: rows k0 .. k0 + KS
+  PT_DECL
+  stage_matrix_async(sW, c.wt_fc1(h) + (size_t)k0 * H, KS * H);
+  pdl_sync();
+  PT_MARK();                                           // 0: dependency wait
+
+  // ---- input slice + bn1 (all B rows are here: the statistics are local) ----
+  for (int i = t; i < Bp * KS; i += 256) {
+    const int b = i / KS, k = i - b * KS;
+    sU[i] = b < B ? head_input(c, h, b, k0 + k, H) : 0.f;
+  }
+  __syncthreads();
+  PT_MARK();                                           // 1: input slice loaded
+  if (c.train) {
+    column_sums2(B, KS, scratch, sum, sq, [&](int b, int col, float& v0, float& v1) {
+      const float v = sU[b * KS + col];
+      v0 = v;
+      v1 = v * v;
+    });
+    bn_local_finalize(c, bn1, k0, KS, B, sum, sq, sc1, sh1);
+    if (j == 0 && t == 0 && c.nbt != nullptr) {
+      c.nbt[bn1] += 1;
+      c.nbt[bn2] += 1;
+    }
+  } else if (t < KS) {
+    sc1[t] = c.bnf(bn1, BN_SCALE)[k0 + t];
+    sh1[t] = c.bnf(bn1, BN_SHIFT)[k0 + t];
+  }
+  __syncthreads();
+  for (int i = t; i < Bp * KS; i += 256) {
+    const int b = i / KS, k = i - b * KS;
+    sU[i] = b < B ? fmaf(sU[i], sc1[k], sh1[k]) : 0.f;
   }
   cp_async_wait_all();
   __syncthreads();
-  float acc[kRPW][VEC];
-#pragma unroll
-  for (int r = 0; r < kRPW; ++r)
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
-  tile_gemm<VEC, kRPW>(sA, K1, sW, H, K1, acc);
+  PT_MARK();                                           // 2: bn1 + normalise + W
+
+  // ---- fc1: K split over the input slices; reduce-scatter of the partial products by hidden slice ----
   const float* b1 = c.params + c.po.fc1_b[h];
   float* H1 = c.H1 + (size_t)h * c.Bm * H;
-  double st[2][VEC];
+  const int tx = t & 15, ty = t >> 4;
+  for (int r0 = 0; r0 < B; r0 += kChunk) {
+    float acc[8][CT];
 #pragma unroll
-  for (int k = 0; k < VEC; ++k) st[0][k] = st[1][k] = 0.0;
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-  for (int r = 0; r < kRPW; ++r) {
-    const int b = row0 + warp * kRPW + r;
-    if (b < B) {
-      RowVec<VEC> o;
+      for (int q = 0; q < CT; ++q) acc[i][q] = 0.f;
+    for (int k = 0; k < KS; ++k) {
+      float a[8], w[CT];
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        o.v[k] = fmaxf(acc[r][k] + b1[lane * VEC + k], 0.f);
-        st[0][k] += (double)o.v[k];
-        st[1][k] += (double)o.v[k] * (double)o.v[k];
-      }
-      o.store(H1 + (size_t)b * H, lane);
+      for (int i = 0; i < 8; ++i) a[i] = sU[(size_t)(r0 + ty * 8 + i) * KS + k];
+#pragma unroll
+      for (int q = 0; q < CT; ++q) w[q] = sW[(size_t)k * H + tx * CT + q];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int q = 0; q < CT; ++q) acc[i][q] = fmaf(a[i], w[q], acc[i][q]);
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int q = 0; q < CT; ++q) sP[(size_t)(ty * 8 + i) * H + tx * CT + q] = acc[i][q];
+    PT_MARK();                                         // 3: partial GEMM
+    cl.sync();
+    PT_MARK();                                         // 4: cluster sync
+    {
+      constexpr int F4 = HS / 4;                       // float4 per row of the slice
+      const float* rp[kRC];
+#pragma unroll
+      for (int q = 0; q < kRC; ++q) rp[q] = cl.map_shared_rank(sP, q);
+      for (int i = t; i < kChunk * F4; i += 256) {
+        const int r = i / F4, m = (i - r * F4) * 4;
+        float4 v[kRC];
+#pragma unroll
+        for (int q = 0; q < kRC; ++q) v[q] = *reinterpret_cast<const float4*>(rp[q] + (size_t)r * H + m0 + m);
+        float4 s = v[0];
+#pragma unroll
+        for (int q = 1; q < kRC; ++q) {
+          s.x += v[q].x; s.y += v[q].y; s.z += v[q].z; s.w += v[q].w;
+        }
+        const int b = r0 + r;
+        const float4 bb = *reinterpret_cast<const float4*>(b1 + m0 + m);
+        float4 o = make_float4(fmaxf(s.x + bb.x, 0.f), fmaxf(s.y + bb.y, 0.f), fmaxf(s.z + bb.z, 0.f),
+                               fmaxf(s.w + bb.w, 0.f));
+        if (b >= B) o = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(sH + (size_t)b * HS + m) = o;
+        if (b < B) *reinterpret_cast<float4*>(H1 + (size_t)b * H + m0 + m) = o;
+      }
+    }
+    cl.sync();
   }
-  if (c.train) {
-    const int T1 = ceil_div(B, kTileRows);
-    block_partial_store_ex<VEC, 2>(st, sRed, c.statp, H, h * T1 + tile, 2, 0, H, 0);
-    if (grid_last_block(&c.counters[CNT_HEAD1], 3 * T1))
-      for (int hh = 0; hh < 3; ++hh)
-        bn_finalize(c, c.L + 6 + hh, c.statp + (size_t)hh * T1 * 2 * H, T1, 2, 0, 1, B);
-  }
-}
 
-// fc2 + log_softmax + loss: warp per graph row, blockIdx.y = head.
-template <int VEC>
-__global__ void __launch_bounds__(256) k_head2_fwd(const Ctx c) {
-  pdl_sync();
-  constexpr int H = 32 * VEC;
-  __shared__ float sLoss[kRowWarps][2];
-  const int B = clampB(c);
-  const int h = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * kHeadRowsPerCta + warp;
-  const int C = c.C;
-  const int nct = ceil_div(B, kHeadRowsPerCta);
-  if (blockIdx.x >= nct) return;
-  float loss_row = 0.f, correct = 0.f;
-  if (b < B) {
-    BnLane<VEC> bn;
-    bn.load_fwd(c, c.L + 6 + h, lane);
-    RowVec<VEC> x;
-    x.load_coherent(c.H1 + ((size_t)h * c.Bm + b) * H, lane);
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) x.v[k] = fmaf(x.v[k], bn.sc[k], bn.sh[k]);
-    const float* W2 = c.params + c.po.fc2_w[h];      // [C][H]
-    const float* b2 = c.params + c.po.fc2_b[h];
-    float mine = -INFINITY;                           // lane `cls` keeps logit[cls]
-    for (int cls = 0; cls < C; ++cls) {
-      RowVec<VEC> w;
-      w.load(W2 + (size_t)cls * H, lane);
-      float v = warp_sum(dot_lane<VEC>(x, w)) + b2[cls];
-      if (lane == cls) mine = v;
-    }
-    float m = mine;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    float e = lane < C ? expf(mine - m) : 0.f;
-    float se = warp_sum(e);
-    float lp = mine - m - logf(se);
-    if (lane < C) c.logp[((size_t)h * c.Bm + b) * C + lane] = lp;
-    if (c.with_loss && c.y != nullptr) {
-      const long long yb = c.y[b];
-      // argmax (first maximal index)
-      int am = lane < C && mine == m ? lane : 1 << 30;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) am = min(am, __shfl_xor_sync(0xffffffffu, am, o));
-      correct = (long long)am == yb ? 1.f : 0.f;
-      if (h == 0) {
-        float s = warp_sum(lane < C ? lp : 0.f);
-        loss_row = -logf((float)C) - s / (float)C;   // sum_j (1/C) (log(1/C) - logp_j)
-      } else {
-        float pick = (yb >= 0 && yb < C && lane == (int)yb) ? lp : 0.f;
-        loss_row = -warp_sum(pick);
-      }
-    }
+  PT_MARK();                                           // 5: reduce-scatter + sync
+  // ---- bn2 on the hidden slice (local) ----
+  if (c.train) {
+    column_sums2(B, HS, scratch, sum, sq, [&](int b, int col, float& v0, float& v1) {
+      const float v = sH[b * HS + col];
+      v0 = v;
+      v1 = v * v;
+    });
+    bn_local_finalize(c, bn2, m0, HS, B, sum, sq, sc2, sh2);
+  } else if (t < HS) {
+    sc2[t] = c.bnf(bn2, BN_SCALE)[m0 + t];
+    sh2[t] = c.bnf(bn2, BN_SHIFT)[m0 + t];
   }
-  if (c.with_loss) {
-    if (lane == 0) {
-      sLoss[warp][0] = loss_row;
-      sLoss[warp][1] = correct;
+  __syncthreads();
+
+  PT_MARK();                                           // 6: bn2
+  // ---- fc2: partial logits of the slice, summed over the cluster by CTA 0 ----
+  const float* W2 = c.params + c.po.fc2_w[h];          // [C][H]
+  float* sL = sP;                                      // [B][C]
+  for (int i = t; i < B * C; i += 256) {
+    const int b = i / C, cls = i - b * C;
+    float s = 0.f;
+    for (int m = 0; m < HS; ++m)
+      s = fmaf(fmaf(sH[(size_t)b * HS + m], sc2[m], sh2[m]), W2[(size_t)cls * H + m0 + m], s);
+    sL[i] = s;
+  }
+  cl.sync();
+  PT_MARK();                                           // 7: partial logits + sync
+  if (j == 0) {
+    const float* b2 = c.params + c.po.fc2_b[h];
+    for (int i = t; i < B * C; i += 256) {
+      const int cls = i % C;
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < kRC; ++q) s += cl.map_shared_rank(sL, q)[i];
+      sLg[i] = s + b2[cls];
     }
     __syncthreads();
-    float* lossp = c.loss + 8;                        // [3][2][g_head2]
-    if (threadIdx.x < 2) {
-      float s = 0.f;
-      for (int w = 0; w < kRowWarps; ++w) s += sLoss[w][threadIdx.x];
-      lossp[((size_t)h * 2 + threadIdx.x) * c.g_head2 + blockIdx.x] = s;
-    }
-    if (grid_last_block(&c.counters[CNT_HEAD2], 3 * nct)) {
-      if (threadIdx.x < 6) {
-        float s = 0.f;
-        for (int g = 0; g < nct; ++g) s += lossp[(size_t)threadIdx.x * c.g_head2 + g];
-        const int hh = threadIdx.x >> 1;
-        if (threadIdx.x & 1) c.loss[4 + hh] = s;      // correct counts c / o / co
-        else c.loss[1 + hh] = B > 0 ? s / (float)B : 0.f;
+    float loss_part = 0.f, correct_part = 0.f;
+    for (int b = t; b < B; b += 256) {
+      float m = -INFINITY;
+      int am = 0;
+      for (int cls = 0; cls < C; ++cls) {
+        const float v = sLg[b * C + cls];
+        if (v > m) {
+          m = v;
+          am = cls;
+        }
       }
+      float se = 0.f;
+      for (int cls = 0; cls < C; ++cls) se += expf(sLg[b * C + cls] - m);
+      const float lse = logf(se);
+      float slp = 0.f, picked = 0.f;
+      const long long yb = (c.with_loss && c.y != nullptr) ? c.y[b] : -1;
+      for (int cls = 0; cls < C; ++cls) {
+        const float lp = sLg[b * C + cls] - m - lse;
+        c.logp[((size_t)h * c.Bm + b) * C + cls] = lp;
+        slp += lp;
+        if ((long long)cls == yb) picked = lp;
+      }
+      if (c.with_loss) {
+        loss_part += h == 0 ? -logf((float)C) - slp / (float)C : -picked;   // KL(uniform || .) row / NLL row
+        correct_part += (long long)am == yb ? 1.f : 0.f;
+      }
+    }
+    if (c.with_loss) {
+      float* red = reinterpret_cast<float*>(scratch);   // deterministic block reduction (fixed order)
       __syncthreads();
-      if (threadIdx.x == 0) {
-        c.loss[0] = c.w_c * c.loss[1] + c.w_o * c.loss[2] + c.w_co * c.loss[3];
-        c.loss[7] = 0.f;
+      red[t] = loss_part;
+      red[256 + t] = correct_part;
+      __syncthreads();
+      if (t < 2) {
+        float s = 0.f;
+        for (int i = 0; i < 256; ++i) s += red[t * 256 + i];
+        if (t == 0) c.loss[1 + h] = B > 0 ? s / (float)B : 0.f;
+        else c.loss[4 + h] = s;
+      }
+      if (grid_last_block(&c.counters[CNT_HEAD2], 3)) {
+        if (t == 0) {
+          const volatile float* lv = c.loss;
+          c.loss[0] = c.w_c * lv[1] + c.w_o * lv[2] + c.w_co * lv[3];
+          c.loss[7] = 0.f;
+        }
       }
     }
   }
+  PT_MARK();                                           // 8: CTA 0 tail (logits, log-softmax, loss)
+  cl.sync();                                           // remote partial logits stay alive until CTA 0 is done
+  PT_MARK();                                           // 9: final cluster sync
+  PT_DUMP(c, 64);
 }
 
-// fc2 / log_softmax / bn2 backward: warp per graph row, blockIdx.y = head.
+// ---------------------------------------------------------------------------------------------
+// Readout backward.  Same grid / cluster.  CTA j owns hidden slice m0 .. m0+HS (fc2, bn2, fc1 bias,
+// rows of the fc1 weight) and input slice k0 .. k0+KS (bn1, columns of d fc1 weight, d input).
+// ---------------------------------------------------------------------------------------------
 template <int VEC>
-__global__ void __launch_bounds__(256) k_head2_bwd(const Ctx c) {
-  pdl_sync();
-  constexpr int H = 32 * VEC;
-  __shared__ __align__(16) float sH2[kHeadRowsPerCta][H];
-  __shared__ float sDl[kHeadRowsPerCta][32];
-  __shared__ double sRed[kRowWarps * H];
-  const int B = clampB(c);
-  const int h = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * kHeadRowsPerCta + warp;
-  const int C = c.C;
-  const int nct = ceil_div(B, kHeadRowsPerCta);
-  if (blockIdx.x >= nct) return;
-  const int bn2 = c.L + 6 + h;
-  double st[2][VEC];
-#pragma unroll
-  for (int k = 0; k < VEC; ++k) st[0][k] = st[1][k] = 0.0;
-  RowVec<VEC> h2;
-  h2.zero();
-  float dl = 0.f;
-  if (b < B) {
-    BnLane<VEC> bn;
-    bn.load_bwd(c, bn2, lane);
-    RowVec<VEC> x;
-    x.load_coherent(c.H1 + ((size_t)h * c.Bm + b) * H, lane);
-    const float lp = lane < C ? c.logp[((size_t)h * c.Bm + b) * C + lane] : 0.f;
-    float dlp = 0.f;
-    if (c.grad_logp != nullptr) {
-      if (lane < C) dlp = c.grad_logp[((size_t)h * B + b) * C + lane];
-    } else if (lane < C) {
-      const long long yb = c.y != nullptr ? c.y[b] : -1;
-      if (h == 0) dlp = -c.w_c / ((float)C * (float)B);
-      else if ((long long)lane == yb) dlp = -(h == 1 ? c.w_o : c.w_co) / (float)B;
-    }
-    const float sd = warp_sum(dlp);
-    dl = lane < C ? dlp - expf(lp) * sd : 0.f;        // d logits
-    const float* W2 = c.params + c.po.fc2_w[h];
-    RowVec<VEC> dh;
-    dh.zero();
-    for (int cls = 0; cls < C; ++cls) {
-      const float dv = __shfl_sync(0xffffffffu, dl, cls);
-      RowVec<VEC> w;
-      w.load(W2 + (size_t)cls * H, lane);
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) dh.v[k] = fmaf(dv, w.v[k], dh.v[k]);
-    }
-    dh.store(c.dh + ((size_t)h * c.Bm + b) * H, lane);
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      h2.v[k] = fmaf(x.v[k], bn.sc[k], bn.sh[k]);
-      st[0][k] += (double)dh.v[k];
-      st[1][k] += (double)dh.v[k] * (double)bn.xhat(k, x.v[k]);
-    }
-  }
-  h2.store(&sH2[warp][0], lane);
-  sDl[warp][lane] = dl;
-  __syncthreads();
-  // fc2 weight / bias gradient partials of this CTA's 8 rows
-  float* gp = c.gpart + c.gp_fc2[h] + (size_t)blockIdx.x * (C * H + C);
-  for (int t = threadIdx.x; t < C * H; t += blockDim.x) {
-    const int cls = t / H, k = t - cls * H;
-    float s = 0.f;
-#pragma unroll
-    for (int r = 0; r < kHeadRowsPerCta; ++r) s = fmaf(sDl[r][cls], sH2[r][k], s);
-    gp[t] = s;
-  }
-  if (threadIdx.x < C) {
-    float s = 0.f;
-#pragma unroll
-    for (int r = 0; r < kHeadRowsPerCta; ++r) s += sDl[r][threadIdx.x];
-    gp[C * H + threadIdx.x] = s;
-  }
-  block_partial_store_ex<VEC, 2>(st, sRed, c.statp, H, h * nct + blockIdx.x, 2, 0, H, 0);
-  if (grid_last_block(&c.counters[CNT_BHEAD2], 3 * nct))
-    for (int hh = 0; hh < 3; ++hh)
-      bn_bwd_finalize(c, c.L + 6 + hh, c.statp + (size_t)hh * nct * 2 * H, nct, 2, 0, 1, B);
-}
-
-// fc1 / bn1 backward on a 32-row tile, blockIdx.y = head.
-// smem: sW [H][K1] (fc1 weight as stored) | sU [R][H] | sY [R][K1] | sRed f64 [8][H]
-template <int VEC>
-__global__ void __launch_bounds__(256) k_head1_bwd(const Ctx c) {
-  constexpr int H = 32 * VEC;
+__global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_bwd(const Ctx c) {
+  constexpr int H = 32 * VEC, HS = H / kRC;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  cg::cluster_group cl = cg::this_cluster();
   const int B = clampB(c);
-  const int h = blockIdx.y, tile = blockIdx.x;
-  const int row0 = tile * kTileRows;
-  if (row0 >= B) return;
-  const int K1 = (h == 2 && c.cat) ? 2 * H : H;
-  float* sW = reinterpret_cast<float*>(smem_raw);
-  float* sU = sW + (size_t)H * K1;
-  float* sY = sU + kTileRows * H;
-  double* sRed = reinterpret_cast<double*>(sY + (size_t)kTileRows * K1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, j = blockIdx.x;
+  const int K1 = (h == 2 && c.cat) ? 2 * H : H, KS = K1 / kRC;
+  const int Bp = ceil_div(imax(c.Bm, 1), kChunk) * kChunk;
+  const ReadoutSmem L = readout_smem(Bp, H, c.cat ? 2 * HS : HS, c.C, true);
+  float* sUin = reinterpret_cast<float*>(smem_raw + L.off_u);     // [Bp][KS] raw input slice
+  float* sW = reinterpret_cast<float*>(smem_raw + L.off_w);       // [HS][K1] rows m0.. of the fc1 weight
+  float* sP = reinterpret_cast<float*>(smem_raw + L.off_p);       // d logits / partial products / all-gathered u
+  float* sH = reinterpret_cast<float*>(smem_raw + L.off_h);       // [Bp][HS] h1 slice
+  float* sX = reinterpret_cast<float*>(smem_raw + L.off_x);       // [Bp][HS] d h2 -> u slice
+  float* sDU = reinterpret_cast<float*>(smem_raw + L.off_du);     // [Bp][KS] d(bn1 out) slice
+  double* scratch = reinterpret_cast<double*>(smem_raw + L.off_misc);
+  double* s1 = scratch + 512;                         // [64]
+  double* s2 = s1 + 64;                               // [64]
+  float* fc = reinterpret_cast<float*>(scratch + 512 + 256);
+  float *f_sc2 = fc, *f_sh2 = fc + 32, *f_mean2 = fc + 64, *f_rstd2 = fc + 96;       // hidden slice constants
+  float *f_sc1 = fc + 128, *f_sh1 = fc + 160, *f_mean1 = fc + 192, *f_rstd1 = fc + 224;   // input slice constants
+  float *c1 = fc + 256, *c2 = fc + 288;
+  const int t = threadIdx.x;
+  const int k0 = j * KS, m0 = j * HS;
   const int bn1 = c.L + 3 + h, bn2 = c.L + 6 + h;
-  stage_matrix_async(sW, c.params + c.po.fc1_w[h], H * K1);
-  pdl_sync();                                        // everything below may read the predecessor's output
-  BnLane<VEC> b2;
-  b2.load_bwd(c, bn2, lane);
-  const float* H1 = c.H1 + (size_t)h * c.Bm * H;
-  const float* dh = c.dh + (size_t)h * c.Bm * H;
-  float dbias[VEC];
-#pragma unroll
-  for (int k = 0; k < VEC; ++k) dbias[k] = 0.f;
-#pragma unroll
-  for (int r = 0; r < kRPW; ++r) {
-    const int lr = warp * kRPW + r, b = row0 + lr;
-    RowVec<VEC> u;
-    u.zero();
-    if (b < B) {
-      RowVec<VEC> x, g;
-      x.load_coherent(H1 + (size_t)b * H, lane);
-      g.load_coherent(dh + (size_t)b * H, lane);
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        u.v[k] = x.v[k] > 0.f ? b2.dx(k, g.v[k], x.v[k]) : 0.f;
-        dbias[k] += u.v[k];
-      }
+  const int C = c.C;
+
+  PT_DECL
+  stage_matrix_async(sW, c.params + c.po.fc1_w[h] + (size_t)m0 * K1, HS * K1);
+  pdl_sync();
+  PT_MARK();                                           // 0: dependency wait
+
+  // ---- d logits for all rows (every CTA: B * C values) ----
+  float* sDl = sP;
+  for (int b = t; b < B; b += 256) {
+    const long long yb = c.y != nullptr ? c.y[b] : -1;
+    float sd = 0.f;
+    for (int cls = 0; cls < C; ++cls) {
+      float dlp;
+      if (c.grad_logp != nullptr) dlp = c.grad_logp[((size_t)h * B + b) * C + cls];
+      else if (h == 0) dlp = -c.w_c / ((float)C * (float)B);
+      else dlp = (long long)cls == yb ? -(h == 1 ? c.w_o : c.w_co) / (float)B : 0.f;
+      sDl[b * C + cls] = dlp;
+      sd += dlp;
     }
-    u.store(sU + lr * H, lane);
+    for (int cls = 0; cls < C; ++cls) {
+      const float lp = c.logp[((size_t)h * c.Bm + b) * C + cls];
+      sDl[b * C + cls] -= expf(lp) * sd;
+    }
   }
-  const float* sc1 = c.bnf(bn1, BN_SCALE);
-  const float* sh1 = c.bnf(bn1, BN_SHIFT);
-  for (int i = threadIdx.x; i < kTileRows * K1; i += blockDim.x) {
-    const int r = i / K1, k = i - r * K1;
-    float v = 0.f;
-    if (row0 + r < B) v = fmaf(head_input(c, h, row0 + r, k, H), sc1[k], sh1[k]);
-    sY[i] = v;
+  // ---- hidden slice, input slice, their BatchNorm records ----
+  const float* H1 = c.H1 + (size_t)h * c.Bm * H;
+  for (int i = t; i < Bp * HS; i += 256) {
+    const int b = i / HS, m = i - b * HS;
+    sH[i] = b < B ? H1[(size_t)b * H + m0 + m] : 0.f;
   }
+  for (int i = t; i < Bp * KS; i += 256) {
+    const int b = i / KS, k = i - b * KS;
+    sUin[i] = b < B ? head_input(c, h, b, k0 + k, H) : 0.f;
+  }
+  if (t < HS) {
+    f_sc2[t] = c.bnf(bn2, BN_SCALE)[m0 + t];
+    f_sh2[t] = c.bnf(bn2, BN_SHIFT)[m0 + t];
+    f_mean2[t] = c.bnf(bn2, BN_MEAN)[m0 + t];
+    f_rstd2[t] = c.bnf(bn2, BN_RSTD)[m0 + t];
+  }
+  if (t < KS) {
+    f_sc1[t] = c.bnf(bn1, BN_SCALE)[k0 + t];
+    f_sh1[t] = c.bnf(bn1, BN_SHIFT)[k0 + t];
+    f_mean1[t] = c.bnf(bn1, BN_MEAN)[k0 + t];
+    f_rstd1[t] = c.bnf(bn1, BN_RSTD)[k0 + t];
+  }
+  __syncthreads();
+  PT_MARK();                                           // 1: d logits, slices, constants
+
+  // ---- fc2 backward on the slice: d W2[:, slice], d b2, d h2 = dl W2 ----
+  const float* W2 = c.params + c.po.fc2_w[h];
+  for (int task = t; task < C * HS; task += 256) {
+    const int cls = task / HS, m = task - cls * HS;
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s = fmaf(sDl[b * C + cls], fmaf(sH[b * HS + m], f_sc2[m], f_sh2[m]), s);
+    c.grads[c.po.fc2_w[h] + (size_t)cls * H + m0 + m] = s;
+  }
+  if (j == 0 && t < C) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += sDl[b * C + t];
+    c.grads[c.po.fc2_b[h] + t] = s;
+  }
+  for (int i = t; i < Bp * HS; i += 256) {
+    const int b = i / HS, m = i - b * HS;
+    float s = 0.f;
+    if (b < B)
+      for (int cls = 0; cls < C; ++cls) s = fmaf(sDl[b * C + cls], W2[(size_t)cls * H + m0 + m], s);
+    sX[i] = s;
+  }
+  __syncthreads();
+  PT_MARK();                                           // 2: fc2 backward
+  // ---- bn2 backward (local) -> u = relu'(h1) * bn2'(d h2);  d gamma2, d beta2, d b1 ----
+  column_sums2(B, HS, scratch, s1, s2, [&](int b, int col, float& v0, float& v1) {
+    const float dy = sX[b * HS + col];
+    v0 = dy;
+    v1 = dy * ((sH[b * HS + col] - f_mean2[col]) * f_rstd2[col]);
+  });
+  if (t < HS) {
+    const double inv = B > 0 ? 1.0 / B : 0.0;
+    c1[t] = (float)(s1[t] * inv);
+    c2[t] = (float)(s2[t] * inv);
+    c.grads[c.bn_gamma[bn2] + m0 + t] = (float)s2[t];
+    c.grads[c.bn_beta[bn2] + m0 + t] = (float)s1[t];
+  }
+  __syncthreads();
+  for (int i = t; i < Bp * HS; i += 256) {
+    const int b = i / HS, m = i - b * HS;
+    float u = 0.f;
+    if (b < B) {
+      const float x = sH[i];
+      const float xh = (x - f_mean2[m]) * f_rstd2[m];
+      u = x > 0.f ? f_sc2[m] * (sX[i] - c1[m] - xh * c2[m]) : 0.f;
+    }
+    sX[i] = u;
+  }
+  __syncthreads();
+  column_sums2(B, HS, scratch, s1, s2, [&](int b, int col, float& v0, float& v1) {
+    v0 = sX[b * HS + col];
+    v1 = 0.f;
+  });
+  if (t < HS) c.grads[c.po.fc1_b[h] + m0 + t] = (float)s1[t];
   cp_async_wait_all();
   __syncthreads();
-  float* gp = c.gpart + c.gp_fc1[h] + (size_t)tile * (H * 2 * H + H);
-  const int T1 = ceil_div(B, kTileRows);
-  const int nhalf = K1 / H;
-  for (int half = 0; half < nhalf; ++half) {
-    // du'[b][half*H + j] = sum_k dh1[b][k] W1[k][half*H + j]
-    float acc[kRPW][VEC];
+  PT_MARK();                                           // 3: bn2 backward, u, d b1
+
+  // ---- fc1 backward, d input: K split over the hidden slices, reduce-scatter by input slice ----
+  const int rchunk = K1 > H ? kChunk / 2 : kChunk;     // rows per exchange chunk (sP holds rchunk x K1 floats)
+  const int tx = t & 15, ty = t >> 4;
+  const int rt = rchunk / 16, ctb = K1 / 16;           // rows / columns per thread
+  for (int r0 = 0; r0 < B; r0 += rchunk) {
+    for (int ci = 0; ci < ctb; ci += 8) {              // register tile rt x 8 (rt <= 8)
+      float acc[8][8];
 #pragma unroll
-    for (int r = 0; r < kRPW; ++r)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
-    tile_gemm<VEC, kRPW>(sU, H, sW + half * H, K1, H, acc);
-    BnLane<VEC> b1;
-    b1.load_bwd(c, bn1, lane, half * H);
-    double st[2][VEC];
+        for (int q = 0; q < 8; ++q) acc[i][q] = 0.f;
+      for (int m = 0; m < HS; ++m) {
+        float a[8], w[8];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) st[0][k] = st[1][k] = 0.0;
+        for (int i = 0; i < 8; ++i) a[i] = i < rt ? sX[(size_t)(r0 + ty * rt + i) * HS + m] : 0.f;
 #pragma unroll
-    for (int r = 0; r < kRPW; ++r) {
-      const int b = row0 + warp * kRPW + r;
-      if (b < B) {
-        RowVec<VEC> o;
+        for (int q = 0; q < 8; ++q) w[q] = ci + q < ctb ? sW[(size_t)m * K1 + tx * ctb + ci + q] : 0.f;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-          o.v[k] = acc[r][k];
-          const float uin = head_input(c, h, b, half * H + lane * VEC + k, H);
-          st[0][k] += (double)acc[r][k];
-          st[1][k] += (double)acc[r][k] * (double)b1.xhat(k, uin);
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[i][q] = fmaf(a[i], w[q], acc[i][q]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (i < rt && ci + q < ctb) sP[(size_t)(ty * rt + i) * K1 + tx * ctb + ci + q] = acc[i][q];
+    }
+    cl.sync();
+    {
+      const int F4 = KS / 4;
+      const float* rp[kRC];
+#pragma unroll
+      for (int q = 0; q < kRC; ++q) rp[q] = cl.map_shared_rank(sP, q);
+      for (int i = t; i < rchunk * F4; i += 256) {
+        const int r = i / F4, k = (i - r * F4) * 4;
+        float4 v[kRC];
+#pragma unroll
+        for (int q = 0; q < kRC; ++q) v[q] = *reinterpret_cast<const float4*>(rp[q] + (size_t)r * K1 + k0 + k);
+        float4 sm = v[0];
+#pragma unroll
+        for (int q = 1; q < kRC; ++q) {
+          sm.x += v[q].x; sm.y += v[q].y; sm.z += v[q].z; sm.w += v[q].w;
         }
-        o.store(c.du + ((size_t)h * c.Bm + b) * 2 * H + half * H, lane);
+        if (r0 + r >= B) sm = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(sDU + (size_t)(r0 + r) * KS + k) = sm;
       }
     }
-    block_partial_store_ex<VEC, 2>(st, sRed, c.statp + (size_t)h * T1 * 4 * H, H, tile, 2, 0, K1, half * H);
-    // dW1[k_out][half*H + j] = sum_b dh1[b][k_out] * y1[b][half*H + j]
-    OuterAcc<H> dW;
-    dW.zero();
-    dW.accumulate(sU, H, sY + half * H, K1, kTileRows);
-    dW.store(gp + half * H, K1);
+    cl.sync();
   }
-  block_colsum_store<VEC>(dbias, reinterpret_cast<float*>(sRed), gp + H * K1, H);
-  if (grid_last_block(&c.counters[CNT_BHEAD1], 3 * T1))
-    for (int hh = 0; hh < 3; ++hh)
-      bn_bwd_finalize(c, c.L + 3 + hh, c.statp + (size_t)hh * T1 * 4 * H, T1, 2, 0, 1, B);
+  PT_MARK();                                           // 4: d input GEMM + exchange
+  // ---- bn1 backward on the input slice (local): d gamma1, d beta1, d input ----
+  column_sums2(B, KS, scratch, s1, s2, [&](int b, int col, float& v0, float& v1) {
+    const float dy = sDU[b * KS + col];
+    v0 = dy;
+    v1 = dy * ((sUin[b * KS + col] - f_mean1[col]) * f_rstd1[col]);
+  });
+  if (t < KS) {
+    const double inv = B > 0 ? 1.0 / B : 0.0;
+    c1[t] = (float)(s1[t] * inv);
+    c2[t] = (float)(s2[t] * inv);
+    c.grads[c.bn_gamma[bn1] + k0 + t] = (float)s2[t];
+    c.grads[c.bn_beta[bn1] + k0 + t] = (float)s1[t];
+  }
+  __syncthreads();
+  for (int i = t; i < B * KS; i += 256) {
+    const int b = i / KS, k = i - b * KS;
+    const float xh = (sUin[i] - f_mean1[k]) * f_rstd1[k];
+    c.du[((size_t)h * c.Bm + b) * 2 * H + k0 + k] = f_sc1[k] * (sDU[i] - c1[k] - xh * c2[k]);
+  }
+  PT_MARK();                                           // 5: bn1 backward + d input store
+  // ---- d W1[:, input slice] = sum_b u[b][:] (x) y1[b][slice]: all-gather u by 128-row chunks ----
+  {
+    const int ki = t % KS, kg = t / KS, ng = 256 / KS;   // thread owns input column ki, hidden rows kg + ng * a
+    float acc[16];
+#pragma unroll
+    for (int a = 0; a < 16; ++a) acc[a] = 0.f;
+    float* sUall = sP;                                 // [kChunk][H]
+    for (int r0 = 0; r0 < B; r0 += kChunk) {
+      __syncthreads();
+      {
+        const float* rp[kRC];
+#pragma unroll
+        for (int q = 0; q < kRC; ++q) rp[q] = cl.map_shared_rank(sX, q);
+        constexpr int F4 = H / 4;
+#pragma unroll 4
+        for (int i = t; i < kChunk * F4; i += 256) {
+          const int r = i / F4, m = (i - r * F4) * 4;
+          const int q = m / HS;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r0 + r < B) v = *reinterpret_cast<const float4*>(rp[q] + (size_t)(r0 + r) * HS + (m - q * HS));
+          *reinterpret_cast<float4*>(sUall + (size_t)r * H + m) = v;
+        }
+      }
+      __syncthreads();
+      const int rows = imin(kChunk, B - r0);
+      for (int r = 0; r < rows; ++r) {
+        const float y1 = fmaf(sUin[(size_t)(r0 + r) * KS + ki], f_sc1[ki], f_sh1[ki]);
+#pragma unroll
+        for (int a = 0; a < 16; ++a)
+          if (kg + ng * a < H) acc[a] = fmaf(sUall[(size_t)r * H + kg + ng * a], y1, acc[a]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 16; ++a)
+      if (kg + ng * a < H) c.grads[c.po.fc1_w[h] + (size_t)(kg + ng * a) * K1 + k0 + ki] = acc[a];
+  }
+  PT_MARK();                                           // 6: d W1
+  cl.sync();                                           // peers may still be reading this CTA's u slice
+  PT_MARK();                                           // 7: final cluster sync
+  PT_DUMP(c, 80);
 }
 
-// Gradient w.r.t. the pooled embeddings: bn1 backward of the three readouts, the c <- co path
-// routed through the inverse permutation (model.py:152-157).
+// Gradient w.r.t. the pooled embeddings from the d-input rows of the three readouts; the c <- co
+// path is routed through the inverse permutation (model.py:152-157).
 template <int VEC>
 __global__ void __launch_bounds__(256) k_dpool(const Ctx c) {
   pdl_sync();
@@ -443,37 +629,17 @@ __global__ void __launch_bounds__(256) k_dpool(const Ctx c) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * kRowWarps + warp;
   if (b >= B) return;
-  const float* gc = c.pooled;
-  const float* go = c.pooled + (size_t)c.Bm * H;
-  BnLane<VEC> bc, bo, bco, bco2;
-  bc.load_bwd(c, c.L + 3, lane);
-  bo.load_bwd(c, c.L + 4, lane);
-  bco.load_bwd(c, c.L + 5, lane);
-  if (c.cat) bco2.load_bwd(c, c.L + 5, lane, H);
   const int bi = c.invperm[b];       // co row that consumed xc_g[b]
-  RowVec<VEC> xc, xo, dc, dO, dco_c, dco_o, xo_bi, xc_pb;
-  xc.load_coherent(gc + (size_t)b * H, lane);
-  xo.load_coherent(go + (size_t)b * H, lane);
+  RowVec<VEC> dc, dO, dco_c, dco_o;
   dc.load_coherent(c.du + ((size_t)0 * c.Bm + b) * 2 * H, lane);
   dO.load_coherent(c.du + ((size_t)1 * c.Bm + b) * 2 * H, lane);
   dco_c.load_coherent(c.du + ((size_t)2 * c.Bm + bi) * 2 * H, lane);
-  xo_bi.load_coherent(go + (size_t)bi * H, lane);
-  xc_pb.load_coherent(gc + (size_t)c.perm[b] * H, lane);
   dco_o.load_coherent(c.du + ((size_t)2 * c.Bm + b) * 2 * H + (c.cat ? H : 0), lane);
   RowVec<VEC> oc, oo;
 #pragma unroll
   for (int k = 0; k < VEC; ++k) {
-    float g_c = bc.dx(k, dc.v[k], xc.v[k]);
-    float g_o = bo.dx(k, dO.v[k], xo.v[k]);
-    if (c.cat) {
-      g_c += bco.dx(k, dco_c.v[k], xc.v[k]);
-      g_o += bco2.dx(k, dco_o.v[k], xo.v[k]);
-    } else {
-      g_c += bco.dx(k, dco_c.v[k], xc.v[k] + xo_bi.v[k]);
-      g_o += bco.dx(k, dco_o.v[k], xc_pb.v[k] + xo.v[k]);
-    }
-    oc.v[k] = g_c;
-    oo.v[k] = g_o;
+    oc.v[k] = dc.v[k] + dco_c.v[k];
+    oo.v[k] = dO.v[k] + dco_o.v[k];
   }
   oc.store(c.dpool + (size_t)b * H, lane);
   oo.store(c.dpool + ((size_t)c.Bm + b) * H, lane);
@@ -490,33 +656,34 @@ int set_smem_h(K kernel, size_t bytes) {
 
 }  // namespace
 
+size_t readout_smem_bytes(int Bm, int H, int cat, int C, int backward) {
+  const int Bp = ceil_div(imax(Bm, 1), kChunk) * kChunk;
+  return readout_smem(Bp, H, (cat ? 2 : 1) * (H / kRC), C, backward != 0).total;
+}
+
 int launch_heads_forward(const Ctx& c, int with_loss, cudaStream_t s) {
   (void)with_loss;
-  const int H = c.H, K1m = c.cat ? 2 * H : H;
   CAL_DISPATCH_VEC(c.H, {
     launch_k(k_pool<VEC>, dim3(c.Bm), dim3(256), 0, s, c);
-    size_t smem = (size_t)K1m * H * 4 + (size_t)kTileRows * K1m * 4 + (size_t)kRowWarps * H * 8 + 2 * K1m * 4 + 512 * 8;
-    int rc = set_smem_h(k_head1_fwd<VEC>, smem);
+    const size_t smem = readout_smem_bytes(c.Bm, c.H, c.cat, c.C, 0);
+    int rc = set_smem_h(k_readout_fwd<VEC>, smem);
     if (rc) return rc;
-    launch_k(k_head1_fwd<VEC>, dim3(c.t_head1, 3), dim3(256), smem, s, c);
-    launch_k(k_head2_fwd<VEC>, dim3(c.g_head2, 3), dim3(256), 0, s, c);
+    launch_k(k_readout_fwd<VEC>, dim3(kRC, 3), dim3(256), smem, s, c);
   });
-  note_launches(3);
+  note_launches(2);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }
 
 int launch_heads_backward(const Ctx& c, cudaStream_t s) {
-  const int H = c.H, K1m = c.cat ? 2 * H : H;
   CAL_DISPATCH_VEC(c.H, {
-    launch_k(k_head2_bwd<VEC>, dim3(c.g_head2, 3), dim3(256), 0, s, c);
-    size_t smem = (size_t)H * K1m * 4 + (size_t)kTileRows * H * 4 + (size_t)kTileRows * K1m * 4 + (size_t)kRowWarps * H * 8;
-    int rc = set_smem_h(k_head1_bwd<VEC>, smem);
+    const size_t smem = readout_smem_bytes(c.Bm, c.H, c.cat, c.C, 1);
+    int rc = set_smem_h(k_readout_bwd<VEC>, smem);
     if (rc) return rc;
-    launch_k(k_head1_bwd<VEC>, dim3(c.t_head1, 3), dim3(256), smem, s, c);
+    launch_k(k_readout_bwd<VEC>, dim3(kRC, 3), dim3(256), smem, s, c);
     launch_k(k_dpool<VEC>, dim3(ceil_div(c.Bm, kRowWarps)), dim3(256), 0, s, c);
   });
-  note_launches(3);
+  note_launches(2);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }

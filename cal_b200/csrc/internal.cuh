@@ -106,6 +106,7 @@ void note_launches(int n);     // bumps the process-wide counter behind cal_laun
 int compute_layout(const cal_model_desc* m, const cal_caps* caps, Layout* lay);
 int validate_model(const cal_model_desc* m);
 size_t gat_workspace_floats(int Nm, int EP, int H, int L, int heads);
+size_t readout_smem_bytes(int Bm, int H, int cat, int C, int backward);
 
 // ---- launchers (each returns 0 or a cudaError_t) ----
 int launch_prep(const Ctx& c, cudaStream_t s);
@@ -422,6 +423,17 @@ struct LayerEpilogue {
     }
   }
 };
+
+// Optional per-phase cycle counters (CTA 0, thread 0) for latency analysis: -DCAL_PHASE_TIMING.
+#ifdef CAL_PHASE_TIMING
+#define PT_DECL long long pt_t0 = clock64(); int pt_i = 0; long long pt_v[16];
+#define PT_MARK() do { long long t_ = clock64(); if (pt_i < 16) pt_v[pt_i++] = t_ - pt_t0; pt_t0 = t_; } while (0)
+#define PT_DUMP(c, base) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) for (int q_ = 0; q_ < pt_i; ++q_) (c).status[(base) + q_] = (int)pt_v[q_]; } while (0)
+#else
+#define PT_DECL
+#define PT_MARK()
+#define PT_DUMP(c, base)
+#endif
 
 // ---- TMA-style bulk copies (cp.async.bulk, SASS UBLKCP) completed through an mbarrier ----
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }

@@ -24,6 +24,10 @@ int compute_layout(const cal_model_desc* m, const cal_caps* caps, Layout* lay) {
   if (rc != CAL_OK) return rc;
   if (caps == nullptr) return CAL_ENULL;
   if (caps->max_nodes < 1 || caps->max_edges < 0 || caps->max_graphs < 1) return CAL_EINVAL;
+  // the readout kernels keep all graph rows of a column slice in one CTA's shared memory
+  if (readout_smem_bytes(caps->max_graphs, m->hidden, m->cat != 0, m->num_classes, 1) > 225 * 1024 ||
+      readout_smem_bytes(caps->max_graphs, m->hidden, m->cat != 0, m->num_classes, 0) > 225 * 1024)
+    return CAL_EUNSUPPORTED;
   const size_t Nm = caps->max_nodes, Em = caps->max_edges, Bm = caps->max_graphs, EP = Em + Nm;
   const size_t H = m->hidden, F = m->num_features, C = m->num_classes, L = m->layers;
   const size_t Fp = align_up(F, 4);
@@ -37,7 +41,7 @@ int compute_layout(const cal_model_desc* m, const cal_caps* caps, Layout* lay) {
   const size_t G = lay->g_tile;
 
   size_t sz[CAL_WS_REGION_COUNT] = {0};
-  sz[CAL_WS_STATUS] = 64 * 4;       // [0] status bits; [16..] optional phase-timing slots (CAL_PHASE_TIMING builds)
+  sz[CAL_WS_STATUS] = 128 * 4;       // [0] status bits; [16..] optional phase-timing slots (CAL_PHASE_TIMING builds)
   sz[CAL_WS_COUNTERS] = (64 + kGsSites * kGsCounters) * 4;
   sz[CAL_WS_IN_PTR] = (Nm + 1) * 4;
   sz[CAL_WS_IN_SRC] = EP * 4;

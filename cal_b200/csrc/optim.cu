@@ -178,15 +178,8 @@ int launch_grad_reduce(const Ctx& c, cudaStream_t s) {
   add(c.po.edge_att_w, c.gp_att + 2 * H, 4 * H, as, PARTS_NODE_ROWS, c.g_row);
   add(c.po.node_att_b, c.gp_att + 6 * H, 2, as, PARTS_NODE_ROWS, c.g_row);
   add(c.po.edge_att_b, c.gp_att + 6 * H + 2, 2, as, PARTS_NODE_ROWS, c.g_row);
-  for (int h = 0; h < 3; ++h) {
-    const int K1 = (h == 2 && c.cat) ? 2 * H : H;
-    const int s1 = H * 2 * H + H;
-    add(c.po.fc1_w[h], c.gp_fc1[h], H * K1, s1, PARTS_HEAD_TILES, c.t_head1);
-    add(c.po.fc1_b[h], c.gp_fc1[h] + H * K1, H, s1, PARTS_HEAD_TILES, c.t_head1);
-    const int s2 = C * H + C;
-    add(c.po.fc2_w[h], c.gp_fc2[h], C * H, s2, PARTS_HEAD_ROWS, c.g_head2);
-    add(c.po.fc2_b[h], c.gp_fc2[h] + C * H, C, s2, PARTS_HEAD_ROWS, c.g_head2);
-  }
+  // (the readout parameters get their gradients straight from k_readout_bwd)
+  (void)C;
   t.feat_src = c.gp_feat;
   t.feat_stride = c.F * H + H;
   t.feat_gmax = c.g_tile;

@@ -19,3 +19,5 @@ names_f = ["prologue", "csr ptr", "csr seg", "gather", "wait W/sync", "gemm", "e
 names_b = ["prologue", "csr ptr", "stage+gather", "wait W/sync", "gemm dX", "dX store", "dW outer", "dW store", "reduce+finalize"]
 print("k_conv_fwd (last launched = MODE 2 masked, no reduce) cycles:", list(zip(names_f, st[16:24])), "sum", sum(st[16:24]))
 print("k_conv_bwd (layer 0) cycles:", list(zip(names_b, st[32:41])), "sum", sum(st[32:41]))
+print("k_readout_fwd (head 0, slice 0) cycles:", st[64:74], "sum", sum(st[64:74]))
+print("k_readout_bwd (head 0, slice 0) cycles:", st[80:88], "sum", sum(st[80:88]))
