@@ -107,7 +107,7 @@ __device__ __forceinline__ void column_sums2(int B, int ncols, double* scratch /
 }
 
 struct ReadoutSmem {
-  size_t off_u, off_w, off_p, off_h, off_x, off_du, off_lg, off_misc, total;   // bytes
+  size_t off_u, off_w, off_p, off_h, off_x, off_du, off_lg, off_w2, off_misc, total;   // bytes
 };
 // Shared-memory layout of the readout kernels for Bp rows (multiple of kChunk), hidden H, KSm =
 // widest input slice, C classes.
@@ -122,6 +122,8 @@ __host__ __device__ inline ReadoutSmem readout_smem(int Bp, int H, int KSm, int 
   s.off_x = o;    o += backward ? (size_t)Bp * HS * 4 : 0;              // backward: u = d(fc1 out) slice
   s.off_du = o;   o += backward ? (size_t)Bp * KSm * 4 : 0;             // backward: gathered d(bn1 out) slice
   s.off_lg = o;   o += backward ? 0 : (size_t)Bp * C * 4;               // forward: summed logits (CTA 0)
+  s.off_w2 = o;   o += (size_t)C * HS * 4;                              // fc2 weight slice [C][HS]
+  o = (o + 15) & ~(size_t)15;
   s.off_misc = o; o += 2 * 256 * 8 + 256 * 8 + 512 * 4;                 // fp64 scratch | fp64 sums [4][64] | float consts [16][32]
   s.total = o;
   return s;
@@ -129,16 +131,18 @@ __host__ __device__ inline ReadoutSmem readout_smem(int Bp, int H, int KSm, int 
 
 // training-mode BatchNorm over the B local rows of `ncols` columns (global column k0 + t):
 // scale / shift into sc / sh, the record into the workspace, running statistics updated.
+// gamma / beta / old running statistics were prefetched into shared memory (g, be, rm0, rv0).
 __device__ __forceinline__ void bn_local_finalize(const Ctx& c, int id, int k0, int ncols, int B, const double* sum,
-                                                  const double* sq, float* sc, float* sh) {
+                                                  const double* sq, const float* g, const float* be,
+                                                  const float* rm0, const float* rv0, float* sc, float* sh) {
   const int t = threadIdx.x;
   if (t < ncols) {
     const int k = k0 + t;
     double mean = B > 0 ? sum[t] / B : 0.0, var = B > 0 ? sq[t] / B - mean * mean : 0.0;
     if (var < 0.0) var = 0.0;
     const float rstd = (float)(1.0 / sqrt(var + (double)c.eps));
-    const float s = c.params[c.bn_gamma[id] + k] * rstd;
-    const float o = c.params[c.bn_beta[id] + k] - (float)mean * s;
+    const float s = g[t] * rstd;
+    const float o = be[t] - (float)mean * s;
     sc[t] = s;
     sh[t] = o;
     c.bnf(id, BN_SCALE)[k] = s;
@@ -147,12 +151,42 @@ __device__ __forceinline__ void bn_local_finalize(const Ctx& c, int id, int k0, 
     c.bnf(id, BN_RSTD)[k] = rstd;
     if (c.bn_buffers != nullptr && c.bn_rm[id] >= 0) {
       const double unb = B > 1 ? var * ((double)B / (double)(B - 1)) : var;
-      float* rm = c.bn_buffers + c.bn_rm[id];
-      float* rv = c.bn_buffers + c.bn_rv[id];
-      rm[k] = (1.f - c.momentum) * rm[k] + c.momentum * (float)mean;
-      rv[k] = (1.f - c.momentum) * rv[k] + c.momentum * (float)unb;
+      c.bn_buffers[c.bn_rm[id] + k] = (1.f - c.momentum) * rm0[t] + c.momentum * (float)mean;
+      c.bn_buffers[c.bn_rv[id] + k] = (1.f - c.momentum) * rv0[t] + c.momentum * (float)unb;
     }
   }
+}
+
+// loads `n` elements f(idx) -> dst[idx] with 8 independent loads in flight per thread
+template <typename F>
+__device__ __forceinline__ void load_batched(float* dst, int n, F f) {
+  for (int base = 0; base < n; base += 8 * 256) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + (int)threadIdx.x + 256 * u;
+      v[u] = idx < n ? f(idx) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + (int)threadIdx.x + 256 * u;
+      if (idx < n) dst[idx] = v[u];
+    }
+  }
+}
+
+// deterministic block sum of one float per thread (256 threads): xor-shuffle tree inside each warp,
+// then the 8 warp totals in order.  Result valid in thread 0.  sbuf: 8 floats of shared memory.
+__device__ __forceinline__ float block_sum256(float v, float* sbuf) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sbuf[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < 8; ++w) s += sbuf[w];
+  return s;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -176,27 +210,53 @@ __global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_fwd
   double* scratch = reinterpret_cast<double*>(smem_raw + L.off_misc);
   double* sum = scratch + 512;                        // [64]
   double* sq = sum + 64;                              // [64]
+  float* sW2 = reinterpret_cast<float*>(smem_raw + L.off_w2);   // [C][HS] fc2 weight slice
   float* fc = reinterpret_cast<float*>(scratch + 512 + 256);
-  float* sc1 = fc;                                    // [32] each
-  float* sh1 = fc + 32;
-  float* sc2 = fc + 64;
-  float* sh2 = fc + 96;
+  float *sc1 = fc, *sh1 = fc + 32, *sc2 = fc + 64, *sh2 = fc + 96;          // [32] each
+  float *g1 = fc + 128, *be1 = fc + 160, *g2 = fc + 192, *be2 = fc + 224;   // BatchNorm weights of the slices
+  float *b1s = fc + 256, *rm1 = fc + 288, *rv1 = fc + 320, *rm2 = fc + 352, *rv2 = fc + 384, *b2s = fc + 416;
   const int t = threadIdx.x;
   const int k0 = j * KS, m0 = j * HS;
   const int bn1 = c.L + 3 + h, bn2 = c.L + 6 + h;
   const int C = c.C;
 
+  // ---- before the dependency wait: everything that only reads parameters / BatchNorm buffers ----
   // fc1 weight slice, transposed copy [K1][H] made by k_param_prep: rows k0 .. k0 + KS
   PT_DECL
   stage_matrix_async(sW, c.wt_fc1(h) + (size_t)k0 * H, KS * H);
+  if (t < KS) {
+    g1[t] = c.params[c.bn_gamma[bn1] + k0 + t];
+    be1[t] = c.params[c.bn_beta[bn1] + k0 + t];
+    if (c.bn_buffers != nullptr && c.bn_rm[bn1] >= 0) {
+      rm1[t] = c.bn_buffers[c.bn_rm[bn1] + k0 + t];
+      rv1[t] = c.bn_buffers[c.bn_rv[bn1] + k0 + t];
+    }
+  } else if (t >= 32 && t < 32 + HS) {
+    const int m = t - 32;
+    g2[m] = c.params[c.bn_gamma[bn2] + m0 + m];
+    be2[m] = c.params[c.bn_beta[bn2] + m0 + m];
+    b1s[m] = c.params[c.po.fc1_b[h] + m0 + m];
+    if (c.bn_buffers != nullptr && c.bn_rm[bn2] >= 0) {
+      rm2[m] = c.bn_buffers[c.bn_rm[bn2] + m0 + m];
+      rv2[m] = c.bn_buffers[c.bn_rv[bn2] + m0 + m];
+    }
+  } else if (t >= 64 && t < 64 + C) {
+    b2s[t - 64] = c.params[c.po.fc2_b[h] + t - 64];
+  }
+  for (int i = t; i < C * HS; i += 256) sW2[i] = c.params[c.po.fc2_w[h] + (size_t)(i / HS) * H + m0 + (i % HS)];
+  long long y0 = -1, y1 = -1;                          // labels of the rows CTA 0 scores (input data)
+  if (j == 0 && c.with_loss && c.y != nullptr) {
+    if (t < B) y0 = c.y[t];
+    if (t + 256 < B) y1 = c.y[t + 256];
+  }
   pdl_sync();
   PT_MARK();                                           // 0: dependency wait
 
   // ---- input slice + bn1 (all B rows are here: the statistics are local) ----
-  for (int i = t; i < Bp * KS; i += 256) {
+  load_batched(sU, Bp * KS, [&](int i) {
     const int b = i / KS, k = i - b * KS;
-    sU[i] = b < B ? head_input(c, h, b, k0 + k, H) : 0.f;
-  }
+    return b < B ? head_input(c, h, b, k0 + k, H) : 0.f;
+  });
   __syncthreads();
   PT_MARK();                                           // 1: input slice loaded
   if (c.train) {
@@ -205,7 +265,7 @@ __global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_fwd
       v0 = v;
       v1 = v * v;
     });
-    bn_local_finalize(c, bn1, k0, KS, B, sum, sq, sc1, sh1);
+    bn_local_finalize(c, bn1, k0, KS, B, sum, sq, g1, be1, rm1, rv1, sc1, sh1);
     if (j == 0 && t == 0 && c.nbt != nullptr) {
       c.nbt[bn1] += 1;
       c.nbt[bn2] += 1;
@@ -224,21 +284,33 @@ __global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_fwd
   PT_MARK();                                           // 2: bn1 + normalise + W
 
   // ---- fc1: K split over the input slices; reduce-scatter of the partial products by hidden slice ----
-  const float* b1 = c.params + c.po.fc1_b[h];
   float* H1 = c.H1 + (size_t)h * c.Bm * H;
   const int tx = t & 15, ty = t >> 4;
+  // thread (ty, tx): rows ty*8 .. +8 of the chunk; columns in NG groups of GW: group g starts at
+  // g * (H / NG) + tx * GW, so the 16 lanes of a half-warp read one contiguous run per group
+  constexpr int GW = CT >= 4 ? 4 : CT, NG = CT / GW;
   for (int r0 = 0; r0 < B; r0 += kChunk) {
     float acc[8][CT];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int q = 0; q < CT; ++q) acc[i][q] = 0.f;
+#pragma unroll 4
     for (int k = 0; k < KS; ++k) {
       float a[8], w[CT];
 #pragma unroll
       for (int i = 0; i < 8; ++i) a[i] = sU[(size_t)(r0 + ty * 8 + i) * KS + k];
 #pragma unroll
-      for (int q = 0; q < CT; ++q) w[q] = sW[(size_t)k * H + tx * CT + q];
+      for (int g = 0; g < NG; ++g) {
+        const float* wp = sW + (size_t)k * H + g * (H / NG) + tx * GW;
+        if constexpr (GW == 4) {
+          const float4 v = *reinterpret_cast<const float4*>(wp);
+          w[g * 4] = v.x; w[g * 4 + 1] = v.y; w[g * 4 + 2] = v.z; w[g * 4 + 3] = v.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < GW; ++e) w[g * GW + e] = wp[e];
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -247,7 +319,15 @@ __global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_fwd
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int q = 0; q < CT; ++q) sP[(size_t)(ty * 8 + i) * H + tx * CT + q] = acc[i][q];
+      for (int g = 0; g < NG; ++g) {
+        float* pp = sP + (size_t)(ty * 8 + i) * H + g * (H / NG) + tx * GW;
+        if constexpr (GW == 4) {
+          *reinterpret_cast<float4*>(pp) = make_float4(acc[i][g * 4], acc[i][g * 4 + 1], acc[i][g * 4 + 2], acc[i][g * 4 + 3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < GW; ++e) pp[e] = acc[i][g * GW + e];
+        }
+      }
     PT_MARK();                                         // 3: partial GEMM
     cl.sync();
     PT_MARK();                                         // 4: cluster sync
@@ -267,7 +347,7 @@ __global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_fwd
           s.x += v[q].x; s.y += v[q].y; s.z += v[q].z; s.w += v[q].w;
         }
         const int b = r0 + r;
-        const float4 bb = *reinterpret_cast<const float4*>(b1 + m0 + m);
+        const float4 bb = *reinterpret_cast<const float4*>(b1s + m);
         float4 o = make_float4(fmaxf(s.x + bb.x, 0.f), fmaxf(s.y + bb.y, 0.f), fmaxf(s.z + bb.z, 0.f),
                                fmaxf(s.w + bb.w, 0.f));
         if (b >= B) o = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -286,7 +366,7 @@ __global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_fwd
       v0 = v;
       v1 = v * v;
     });
-    bn_local_finalize(c, bn2, m0, HS, B, sum, sq, sc2, sh2);
+    bn_local_finalize(c, bn2, m0, HS, B, sum, sq, g2, be2, rm2, rv2, sc2, sh2);
   } else if (t < HS) {
     sc2[t] = c.bnf(bn2, BN_SCALE)[m0 + t];
     sh2[t] = c.bnf(bn2, BN_SHIFT)[m0 + t];
@@ -295,25 +375,28 @@ __global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_fwd
 
   PT_MARK();                                           // 6: bn2
   // ---- fc2: partial logits of the slice, summed over the cluster by CTA 0 ----
-  const float* W2 = c.params + c.po.fc2_w[h];          // [C][H]
   float* sL = sP;                                      // [B][C]
   for (int i = t; i < B * C; i += 256) {
     const int b = i / C, cls = i - b * C;
     float s = 0.f;
-    for (int m = 0; m < HS; ++m)
-      s = fmaf(fmaf(sH[(size_t)b * HS + m], sc2[m], sh2[m]), W2[(size_t)cls * H + m0 + m], s);
+#pragma unroll
+    for (int m = 0; m < HS; ++m) s = fmaf(fmaf(sH[(size_t)b * HS + m], sc2[m], sh2[m]), sW2[cls * HS + m], s);
     sL[i] = s;
   }
   cl.sync();
   PT_MARK();                                           // 7: partial logits + sync
   if (j == 0) {
-    const float* b2 = c.params + c.po.fc2_b[h];
-    for (int i = t; i < B * C; i += 256) {
-      const int cls = i % C;
-      float s = 0.f;
+    const float* rl[kRC];
 #pragma unroll
-      for (int q = 0; q < kRC; ++q) s += cl.map_shared_rank(sL, q)[i];
-      sLg[i] = s + b2[cls];
+    for (int q = 0; q < kRC; ++q) rl[q] = cl.map_shared_rank(sL, q);
+    for (int i = t; i < B * C; i += 256) {
+      float v[kRC];
+#pragma unroll
+      for (int q = 0; q < kRC; ++q) v[q] = rl[q][i];
+      float s = v[0];
+#pragma unroll
+      for (int q = 1; q < kRC; ++q) s += v[q];
+      sLg[i] = s + b2s[i % C];
     }
     __syncthreads();
     float loss_part = 0.f, correct_part = 0.f;
@@ -331,7 +414,7 @@ __global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_fwd
       for (int cls = 0; cls < C; ++cls) se += expf(sLg[b * C + cls] - m);
       const float lse = logf(se);
       float slp = 0.f, picked = 0.f;
-      const long long yb = (c.with_loss && c.y != nullptr) ? c.y[b] : -1;
+      const long long yb = b == t ? y0 : (b == t + 256 ? y1 : ((c.with_loss && c.y != nullptr) ? c.y[b] : -1));
       for (int cls = 0; cls < C; ++cls) {
         const float lp = sLg[b * C + cls] - m - lse;
         c.logp[((size_t)h * c.Bm + b) * C + cls] = lp;
@@ -344,16 +427,12 @@ __global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_fwd
       }
     }
     if (c.with_loss) {
-      float* red = reinterpret_cast<float*>(scratch);   // deterministic block reduction (fixed order)
-      __syncthreads();
-      red[t] = loss_part;
-      red[256 + t] = correct_part;
-      __syncthreads();
-      if (t < 2) {
-        float s = 0.f;
-        for (int i = 0; i < 256; ++i) s += red[t * 256 + i];
-        if (t == 0) c.loss[1 + h] = B > 0 ? s / (float)B : 0.f;
-        else c.loss[4 + h] = s;
+      float* red = reinterpret_cast<float*>(scratch);
+      const float ls = block_sum256(loss_part, red);
+      const float cs = block_sum256(correct_part, red + 8);
+      if (t == 0) {
+        c.loss[1 + h] = B > 0 ? ls / (float)B : 0.f;
+        c.loss[4 + h] = cs;
       }
       if (grid_last_block(&c.counters[CNT_HEAD2], 3)) {
         if (t == 0) {
@@ -397,6 +476,7 @@ __global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_bwd
   float *f_sc2 = fc, *f_sh2 = fc + 32, *f_mean2 = fc + 64, *f_rstd2 = fc + 96;       // hidden slice constants
   float *f_sc1 = fc + 128, *f_sh1 = fc + 160, *f_mean1 = fc + 192, *f_rstd1 = fc + 224;   // input slice constants
   float *c1 = fc + 256, *c2 = fc + 288;
+  float* sW2 = reinterpret_cast<float*>(smem_raw + L.off_w2);     // [C][HS] fc2 weight slice
   const int t = threadIdx.x;
   const int k0 = j * KS, m0 = j * HS;
   const int bn1 = c.L + 3 + h, bn2 = c.L + 6 + h;
@@ -404,6 +484,7 @@ __global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_bwd
 
   PT_DECL
   stage_matrix_async(sW, c.params + c.po.fc1_w[h] + (size_t)m0 * K1, HS * K1);
+  for (int i = t; i < C * HS; i += 256) sW2[i] = c.params[c.po.fc2_w[h] + (size_t)(i / HS) * H + m0 + (i % HS)];
   pdl_sync();
   PT_MARK();                                           // 0: dependency wait
 
@@ -427,14 +508,14 @@ __global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_bwd
   }
   // ---- hidden slice, input slice, their BatchNorm records ----
   const float* H1 = c.H1 + (size_t)h * c.Bm * H;
-  for (int i = t; i < Bp * HS; i += 256) {
+  load_batched(sH, Bp * HS, [&](int i) {
     const int b = i / HS, m = i - b * HS;
-    sH[i] = b < B ? H1[(size_t)b * H + m0 + m] : 0.f;
-  }
-  for (int i = t; i < Bp * KS; i += 256) {
+    return b < B ? H1[(size_t)b * H + m0 + m] : 0.f;
+  });
+  load_batched(sUin, Bp * KS, [&](int i) {
     const int b = i / KS, k = i - b * KS;
-    sUin[i] = b < B ? head_input(c, h, b, k0 + k, H) : 0.f;
-  }
+    return b < B ? head_input(c, h, b, k0 + k, H) : 0.f;
+  });
   if (t < HS) {
     f_sc2[t] = c.bnf(bn2, BN_SCALE)[m0 + t];
     f_sh2[t] = c.bnf(bn2, BN_SHIFT)[m0 + t];
@@ -451,10 +532,10 @@ __global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_bwd
   PT_MARK();                                           // 1: d logits, slices, constants
 
   // ---- fc2 backward on the slice: d W2[:, slice], d b2, d h2 = dl W2 ----
-  const float* W2 = c.params + c.po.fc2_w[h];
   for (int task = t; task < C * HS; task += 256) {
     const int cls = task / HS, m = task - cls * HS;
     float s = 0.f;
+#pragma unroll 4
     for (int b = 0; b < B; ++b) s = fmaf(sDl[b * C + cls], fmaf(sH[b * HS + m], f_sc2[m], f_sh2[m]), s);
     c.grads[c.po.fc2_w[h] + (size_t)cls * H + m0 + m] = s;
   }
@@ -467,7 +548,7 @@ __global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_bwd
     const int b = i / HS, m = i - b * HS;
     float s = 0.f;
     if (b < B)
-      for (int cls = 0; cls < C; ++cls) s = fmaf(sDl[b * C + cls], W2[(size_t)cls * H + m0 + m], s);
+      for (int cls = 0; cls < C; ++cls) s = fmaf(sDl[b * C + cls], sW2[cls * HS + m], s);
     sX[i] = s;
   }
   __syncthreads();
@@ -511,28 +592,54 @@ __global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_bwd
   const int tx = t & 15, ty = t >> 4;
   const int rt = rchunk / 16, ctb = K1 / 16;           // rows / columns per thread
   for (int r0 = 0; r0 < B; r0 += rchunk) {
-    for (int ci = 0; ci < ctb; ci += 8) {              // register tile rt x 8 (rt <= 8)
-      float acc[8][8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int q = 0; q < 8; ++q) acc[i][q] = 0.f;
-      for (int m = 0; m < HS; ++m) {
-        float a[8], w[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = i < rt ? sX[(size_t)(r0 + ty * rt + i) * HS + m] : 0.f;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) w[q] = ci + q < ctb ? sW[(size_t)m * K1 + tx * ctb + ci + q] : 0.f;
+    if (ctb >= 4) {
+      // column groups of 4: group g starts at g * (K1 / ng) + tx * 4 (conflict-free float4 per half-warp)
+      const int ng = ctb / 4;
+      for (int g = 0; g < ng; ++g) {
+        float acc[8][4];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-          for (int q = 0; q < 8; ++q) acc[i][q] = fmaf(a[i], w[q], acc[i][q]);
+          for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
+        const float* wp = sW + g * (K1 / ng) + tx * 4;
+#pragma unroll 4
+        for (int m = 0; m < HS; ++m) {
+          float a[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] = i < rt ? sX[(size_t)(r0 + ty * rt + i) * HS + m] : 0.f;
+          const float4 w = *reinterpret_cast<const float4*>(wp + (size_t)m * K1);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            acc[i][0] = fmaf(a[i], w.x, acc[i][0]);
+            acc[i][1] = fmaf(a[i], w.y, acc[i][1]);
+            acc[i][2] = fmaf(a[i], w.z, acc[i][2]);
+            acc[i][3] = fmaf(a[i], w.w, acc[i][3]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i < rt)
+            *reinterpret_cast<float4*>(sP + (size_t)(ty * rt + i) * K1 + g * (K1 / ng) + tx * 4) =
+                make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      }
+    } else {
+      float acc[8][2];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = 0.f;
+      for (int m = 0; m < HS; ++m) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float a = i < rt ? sX[(size_t)(r0 + ty * rt + i) * HS + m] : 0.f;
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+            if (q < ctb) acc[i][q] = fmaf(a, sW[(size_t)m * K1 + tx * ctb + q], acc[i][q]);
+        }
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          if (i < rt && ci + q < ctb) sP[(size_t)(ty * rt + i) * K1 + tx * ctb + ci + q] = acc[i][q];
+        for (int q = 0; q < 2; ++q)
+          if (i < rt && q < ctb) sP[(size_t)(ty * rt + i) * K1 + tx * ctb + q] = acc[i][q];
     }
     cl.sync();
     {
@@ -579,11 +686,14 @@ __global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_bwd
   PT_MARK();                                           // 5: bn1 backward + d input store
   // ---- d W1[:, input slice] = sum_b u[b][:] (x) y1[b][slice]: all-gather u by 128-row chunks ----
   {
-    const int ki = t % KS, kg = t / KS, ng = 256 / KS;   // thread owns input column ki, hidden rows kg + ng * a
+    // thread owns input column ki and the NA = H * KS / 256 contiguous hidden rows kgrp * NA ..
+    const int ki = t % KS, kgrp = t / KS;
+    const int NA = (H * KS) / 256;                     // 8 (H=128), 16 (H=128, cat), 2 / 4 (H=64); 0 for H=32
     float acc[16];
 #pragma unroll
     for (int a = 0; a < 16; ++a) acc[a] = 0.f;
     float* sUall = sP;                                 // [kChunk][H]
+    const int ng = 256 / KS;
     for (int r0 = 0; r0 < B; r0 += kChunk) {
       __syncthreads();
       {
@@ -602,16 +712,39 @@ __global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_bwd
       }
       __syncthreads();
       const int rows = imin(kChunk, B - r0);
-      for (int r = 0; r < rows; ++r) {
-        const float y1 = fmaf(sUin[(size_t)(r0 + r) * KS + ki], f_sc1[ki], f_sh1[ki]);
+      if (NA >= 4) {
+        const float* up = sUall + kgrp * NA;
+#pragma unroll 4
+        for (int r = 0; r < rows; ++r) {
+          const float y1 = fmaf(sUin[(size_t)(r0 + r) * KS + ki], f_sc1[ki], f_sh1[ki]);
 #pragma unroll
-        for (int a = 0; a < 16; ++a)
-          if (kg + ng * a < H) acc[a] = fmaf(sUall[(size_t)r * H + kg + ng * a], y1, acc[a]);
+          for (int f = 0; f < 4; ++f)
+            if (f * 4 < NA) {
+              const float4 u = *reinterpret_cast<const float4*>(up + (size_t)r * H + f * 4);
+              acc[f * 4] = fmaf(u.x, y1, acc[f * 4]);
+              acc[f * 4 + 1] = fmaf(u.y, y1, acc[f * 4 + 1]);
+              acc[f * 4 + 2] = fmaf(u.z, y1, acc[f * 4 + 2]);
+              acc[f * 4 + 3] = fmaf(u.w, y1, acc[f * 4 + 3]);
+            }
+        }
+      } else {
+        for (int r = 0; r < rows; ++r) {
+          const float y1 = fmaf(sUin[(size_t)(r0 + r) * KS + ki], f_sc1[ki], f_sh1[ki]);
+#pragma unroll
+          for (int a = 0; a < 16; ++a)
+            if (kgrp + ng * a < H) acc[a] = fmaf(sUall[(size_t)r * H + kgrp + ng * a], y1, acc[a]);
+        }
       }
     }
+    if (NA >= 4) {
 #pragma unroll
-    for (int a = 0; a < 16; ++a)
-      if (kg + ng * a < H) c.grads[c.po.fc1_w[h] + (size_t)(kg + ng * a) * K1 + k0 + ki] = acc[a];
+      for (int a = 0; a < 16; ++a)
+        if (a < NA) c.grads[c.po.fc1_w[h] + (size_t)(kgrp * NA + a) * K1 + k0 + ki] = acc[a];
+    } else {
+#pragma unroll
+      for (int a = 0; a < 16; ++a)
+        if (kgrp + ng * a < H) c.grads[c.po.fc1_w[h] + (size_t)(kgrp + ng * a) * K1 + k0 + ki] = acc[a];
+    }
   }
   PT_MARK();                                           // 6: d W1
   cl.sync();                                           // peers may still be reading this CTA's u slice
