@@ -15,6 +15,7 @@ constexpr int kNumBN = CAL_MAX_BN + 1;         // + the identity record used by 
 constexpr int kBnIdentity = CAL_MAX_BN;
 constexpr int kHeadRowsPerCta = 8;             // head2 kernels: one warp per graph row
 constexpr int kFeatChunk = 64;                 // feature columns per CTA slice in the feat backward
+constexpr int kFeatBwdCtas = 32;               // row-slices (= partial gradients) of the feat backward
 constexpr int kGsGroup = 8;                    // CTAs per first-level group of the hierarchical grid sum
 constexpr int kGsSites = 3;                    // independent grid sums that may be in flight in one kernel
 constexpr int kGsCounters = 64;                // counters per site: [0] top level, [1 + group] first level
