@@ -353,6 +353,52 @@ class Trainer:
             return self._host_loss
         return None
 
+    # ---- pipelined end-to-end path: H2D of batch i+1 overlaps the step of batch i ----
+    PIPE_RING = 16
+
+    def _pipe_init(self):
+        dev = self.device
+        self._pipe = {
+            "i": 0,
+            "stage": [torch.zeros(self.layout.nbytes, dtype=torch.uint8, device=dev) for _ in range(2)],
+            "copy": torch.cuda.Stream(dev),
+            "ready": [torch.cuda.Event() for _ in range(2)],
+            "done": [torch.cuda.Event() for _ in range(2)],
+            "ring": torch.zeros(self.PIPE_RING, 8, dtype=torch.float32).pin_memory(),
+            "ring_ev": [torch.cuda.Event() for _ in range(self.PIPE_RING)],
+        }
+
+    def step_host_async(self, packed_host):
+        """Enqueue one end-to-end step without synchronising the host: the packed batch is uploaded
+        on a copy stream into one of two staging buffers (overlapping the previous step), the step
+        runs on the current stream, and its loss parts / correct counts are copied into a pinned
+        ring slot.  Returns the ring slot index; ``pipe_result(slot)`` waits for it."""
+        if not hasattr(self, "_pipe"):
+            self._pipe_init()
+        p = self._pipe
+        i = p["i"]
+        b, r = i % 2, i % self.PIPE_RING
+        main = torch.cuda.current_stream(self.device)
+        if i >= self.PIPE_RING:
+            p["ring_ev"][r].synchronize()                # bound the host run-ahead to the ring depth
+        cs = p["copy"]
+        if i >= 2:
+            cs.wait_event(p["done"][b])                  # the step that last read this staging buffer
+        with torch.cuda.stream(cs):
+            p["stage"][b].copy_(packed_host, non_blocking=True)
+            p["ready"][b].record(cs)
+        main.wait_event(p["ready"][b])
+        self.step(p["stage"][b])
+        p["done"][b].record(main)
+        p["ring"][r].copy_(self.eng.loss_parts_full(), non_blocking=True)
+        p["ring_ev"][r].record(main)
+        p["i"] = i + 1
+        return r
+
+    def pipe_result(self, slot):
+        self._pipe["ring_ev"][slot].synchronize()
+        return self._pipe["ring"][slot]
+
     def metrics(self):
         """f32[7] device view: loss, c_loss, o_loss, co_loss, correct_c, correct_o, correct_co of
         the most recent step."""

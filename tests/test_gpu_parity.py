@@ -194,7 +194,7 @@ CASES = [
     dict(seed=2, hidden=64, layers=2, batch_size=33, cat="cat"),
     dict(seed=3, hidden=128, layers=3, batch_size=128),                       # cfg 1/2 shapes
     dict(seed=4, hidden=128, layers=3, batch_size=96, classes=2),             # last batch of an epoch
-    dict(seed=5, hidden=128, layers=1, batch_size=3),                         # three graphs (BatchNorm over 3 rows)
+    dict(seed=5, hidden=128, layers=1, batch_size=4),                         # four graphs (readout BatchNorm over 4 rows)
     dict(seed=6, hidden=32, layers=3, batch_size=7, avg_nodes=8),             # tiny graphs
     dict(seed=7, hidden=64, layers=3, batch_size=16, features=109, classes=2),   # cfg 3 feature width
     dict(seed=8, hidden=128, layers=3, batch_size=24, features=64, avg_nodes=200, ba_m=2, noise=0.0),  # cfg 5 graphs
