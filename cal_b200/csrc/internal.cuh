@@ -5,7 +5,7 @@
 
 namespace cal {
 
-constexpr int kTileRows = 32;                  // destination rows per GEMM tile (8 warps x 4 rows)
+constexpr int kTileRows = 24;                  // destination rows per GEMM tile (8 warps x 4 rows)
 constexpr int kRPW = kTileRows / kRowWarps;    // rows per warp inside a tile
 constexpr int kEdgeStage = 1024;               // CSR entries staged in shared memory per tile (legacy direct path)
 constexpr int kStageFwd = 128;                 // neighbour rows staged in shared memory per row batch (forward layers)
