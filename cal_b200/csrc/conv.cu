@@ -30,46 +30,6 @@ __device__ __forceinline__ Dims load_dims(const Ctx& c) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// bn_feat statistics (model.py:90): column sums of x [N, F] in fp64.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_feat_stats(const Ctx c) {
-  pdl_sync();
-  const Dims d = load_dims(c);
-  const int F = c.F, N = d.N;
-  __shared__ double s_s[256], s_q[256];
-  __shared__ double sTot[2 * 512];                 // F <= 512 (validate_model)
-  const int Fw = imin(F, 256), rpar = 256 / Fw;
-  const int t = threadIdx.x;
-  const int rows_per = ceil_div(imax(N, 1), gridDim.x);
-  const int r0 = imin(blockIdx.x * rows_per, N), r1 = imin(r0 + rows_per, N);
-  for (int cb = 0; cb < F; cb += Fw) {
-    const int col = cb + t % Fw, rs = t / Fw;
-    double s = 0.0, q = 0.0;
-    if (rs < rpar && col < F)
-      for (int r = r0 + rs; r < r1; r += rpar) {
-        double v = (double)c.feat[(size_t)r * F + col];
-        s += v;
-        q += v * v;
-      }
-    __syncthreads();
-    s_s[t] = s;
-    s_q[t] = q;
-    __syncthreads();
-    if (t < Fw && cb + t < F) {
-      double a = 0.0, b = 0.0;
-      for (int k = 0; k < rpar; ++k) {
-        a += s_s[k * Fw + t];
-        b += s_q[k * Fw + t];
-      }
-      sTot[cb + t] = a;
-      sTot[F + cb + t] = b;
-    }
-  }
-  __syncthreads();
-  if (grid_sum(c, 0, sTot, 2 * F, gridDim.x, blockIdx.x)) bn_finalize_tot(c, 0, sTot, sTot + F, N);
-}
-
-// ---------------------------------------------------------------------------------------------
 // x_1 = relu(bn_feat(x) @ W_feat)    (model.py:90-91; conv_feat is gfn=True: no bias, no
 // propagation, gcn_conv.py:75-77) + statistics of bns_conv[0].
 // smem: sW [Fp][H] | sA [R][Fp] | sRed f64 [8][H]
@@ -88,8 +48,46 @@ __global__ void __launch_bounds__(256) k_feat_fwd(const Ctx c) {
   const float* W = c.params + c.po.conv_feat_w;
   for (int i = threadIdx.x; i < Fp * H; i += blockDim.x) sW[i] = i < F * H ? W[i] : 0.f;
   pdl_sync();                                        // everything below may read the predecessor's output
-  const float* sc = c.bnf(0, BN_SCALE);
-  const float* sh = c.bnf(0, BN_SHIFT);
+  // bn_feat (model.py:90): the column totals come from k_prep_init (statp[0 .. 2F)); every CTA turns
+  // them into the affine it applies, CTA 0 also publishes the record and the running statistics
+  float* sc = reinterpret_cast<float*>(sRed + kRowWarps * H);       // [Fp]
+  float* sh = sc + Fp;                                               // [Fp]
+  if (c.train) {
+    for (int k = threadIdx.x; k < F; k += blockDim.x) {
+      const double s = c.statp[k], q = c.statp[F + k];
+      double mean = 0.0, var = 0.0;
+      if (N > 0) {
+        mean = s / N;
+        var = q / N - mean * mean;
+        if (var < 0.0) var = 0.0;
+      }
+      const float rstd = (float)(1.0 / sqrt(var + (double)c.eps));
+      const float scale = c.params[c.bn_gamma[0] + k] * rstd;
+      const float shift = c.params[c.bn_beta[0] + k] - (float)mean * scale;
+      sc[k] = scale;
+      sh[k] = shift;
+      if (blockIdx.x == 0) {
+        c.bnf(0, BN_SCALE)[k] = scale;
+        c.bnf(0, BN_SHIFT)[k] = shift;
+        c.bnf(0, BN_MEAN)[k] = (float)mean;
+        c.bnf(0, BN_RSTD)[k] = rstd;
+        if (c.bn_buffers != nullptr && c.bn_rm[0] >= 0) {
+          const double unb = N > 1 ? var * ((double)N / (double)(N - 1)) : var;
+          float* rm = c.bn_buffers + c.bn_rm[0];
+          float* rv = c.bn_buffers + c.bn_rv[0];
+          rm[k] = (1.f - c.momentum) * rm[k] + c.momentum * (float)mean;
+          rv[k] = (1.f - c.momentum) * rv[k] + c.momentum * (float)unb;
+        }
+      }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && c.nbt != nullptr) c.nbt[0] += 1;
+  } else {
+    for (int k = threadIdx.x; k < F; k += blockDim.x) {
+      sc[k] = c.bnf(0, BN_SCALE)[k];
+      sh[k] = c.bnf(0, BN_SHIFT)[k];
+    }
+  }
+  __syncthreads();
   float* out = c.Xl(0);
   double acc_s[VEC], acc_q[VEC];
 #pragma unroll
@@ -698,11 +696,10 @@ int set_smem(K kernel, size_t bytes) {
 }  // namespace
 
 int launch_feat_forward(const Ctx& c, cudaStream_t s) {
-  if (c.train) launch_k(k_feat_stats, dim3(c.g_tile), dim3(256), 0, s, c);
-  note_launches(c.train ? 2 : 1);
+  note_launches(1);
   const int Fp = (c.F + 3) & ~3;
   CAL_DISPATCH_VEC(c.H, {
-    size_t smem = (size_t)Fp * c.H * 4 + (size_t)kTileRows * Fp * 4 + (size_t)kRowWarps * c.H * 8;
+    size_t smem = (size_t)Fp * c.H * 4 + (size_t)kTileRows * Fp * 4 + (size_t)kRowWarps * c.H * 8 + 2 * (size_t)Fp * 4;
     int rc = set_smem(k_feat_fwd<VEC>, smem);
     if (rc) return rc;
     launch_k(k_feat_fwd<VEC>, dim3(c.g_tile), dim3(256), smem, s, c);

@@ -10,18 +10,25 @@
 
 namespace cal {
 
-__global__ void k_prep_init(const Ctx c) {
+// Node pass + edge count + input-feature statistics in one launch:
+//   graph ids / graph_ptr / perm, status word, identity BatchNorm record;
+//   in- / out-degree counts of the kept edges (the count arrays are zero on entry: the workspace
+//   is zero-filled once by the caller and k_prep_link re-zeroes them after use);
+//   column sums / sums of squares of the input features (bn_feat, model.py:90) -> hierarchical grid
+//   sum -> totals in the workspace (statp[0 .. 2F)), turned into the BatchNorm affine by k_feat_fwd.
+__global__ void __launch_bounds__(256) k_prep_init(const Ctx c) {
   pdl_sync();
+  __shared__ double s_s[256], s_q[256];
+  __shared__ double sTot[2 * 512];               // F <= 512 (validate_model)
   const int N = c.dims[0], E = c.dims[1], B = c.dims[2];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const bool bad_caps = N < 0 || E < 0 || B < 0 || N > c.Nm || E > c.Em || B > c.Bm;
   if (tid == 0) {
-    int st = 0;
-    if (N < 0 || E < 0 || B < 0 || N > c.Nm || E > c.Em || B > c.Bm) st |= kStCapacity;
-    c.status[0] = st;
+    c.status[0] = bad_caps ? kStCapacity : 0;
     c.status[1] = c.status[2] = c.status[3] = 0;
   }
   if (tid < 64 + kGsSites * kGsCounters) c.counters[tid] = 0u;
-  if (N < 0 || E < 0 || B < 0 || N > c.Nm || E > c.Em || B > c.Bm) return;
+  if (bad_caps) return;
   for (int k = tid; k < c.kmax; k += nth) {     // identity BatchNorm record
     c.bnf(kBnIdentity, BN_SCALE)[k] = 1.f;
     c.bnf(kBnIdentity, BN_SHIFT)[k] = 0.f;
@@ -31,8 +38,6 @@ __global__ void k_prep_init(const Ctx c) {
     c.bnf(kBnIdentity, BN_C2)[k] = 0.f;
   }
   for (int n = tid; n < N; n += nth) {
-    c.cnt_in[n] = 0;
-    c.cnt_out[n] = 0;
     long long g = c.batch[n];
     long long gp = n > 0 ? c.batch[n - 1] : -1;
     if (g < 0 || g >= B || g < gp) {
@@ -57,13 +62,8 @@ __global__ void k_prep_init(const Ctx c) {
     c.perm[b] = p;
     c.invperm[p] = b;
   }
-}
-
-__global__ void k_prep_count(const Ctx c) {
-  pdl_sync();
-  if (c.status[0] & kStCapacity) return;
-  const int N = c.dims[0], E = c.dims[1];
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+  // ---- degree counts (gcn_conv.py:56: self loops are dropped) ----
+  for (int e = tid; e < E; e += nth) {
     long long r = c.ei_row[e], d = c.ei_col[e];
     if (r < 0 || r >= N || d < 0 || d >= N) {
       atomicOr(c.status, kStBadNode);
@@ -73,6 +73,39 @@ __global__ void k_prep_count(const Ctx c) {
       atomicAdd(&c.cnt_in[(int)d], 1);
       atomicAdd(&c.cnt_out[(int)r], 1);
     }
+  }
+  // ---- input-feature column statistics (fp64), this CTA's slice of the rows ----
+  {
+    const int F = c.F, t = threadIdx.x;
+    const int Fw = imin(F, 256), rpar = 256 / Fw;
+    const int rows_per = ceil_div(imax(N, 1), gridDim.x);
+    const int r0 = imin(blockIdx.x * rows_per, N), r1 = imin(r0 + rows_per, N);
+    for (int cb = 0; cb < F; cb += Fw) {
+      const int col = cb + t % Fw, rs = t / Fw;
+      double s = 0.0, q = 0.0;
+      if (rs < rpar && col < F)
+        for (int r = r0 + rs; r < r1; r += rpar) {
+          double v = (double)c.feat[(size_t)r * F + col];
+          s += v;
+          q += v * v;
+        }
+      __syncthreads();
+      s_s[t] = s;
+      s_q[t] = q;
+      __syncthreads();
+      if (t < Fw && cb + t < F) {
+        double a = 0.0, b = 0.0;
+        for (int k = 0; k < rpar; ++k) {
+          a += s_s[k * Fw + t];
+          b += s_q[k * Fw + t];
+        }
+        sTot[cb + t] = a;
+        sTot[F + cb + t] = b;
+      }
+    }
+    __syncthreads();
+    if (grid_sum(c, 0, sTot, 2 * F, gridDim.x, blockIdx.x))
+      for (int k = t; k < 2 * F; k += blockDim.x) c.statp[k] = sTot[k];
   }
 }
 
@@ -180,6 +213,8 @@ __global__ void k_prep_link(const Ctx c) {
   if (c.status[0] & kStCapacity) return;
   const int N = c.dims[0];
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+    c.cnt_in[n] = 0;                            // ready for the next batch (k_prep_init counts into them)
+    c.cnt_out[n] = 0;
     const float dn = c.dis[n];
     for (int p = c.in_ptr[n]; p < c.in_ptr[n + 1]; ++p) {
       int s = c.in_src[p], key = c.in_key[p];
@@ -198,15 +233,14 @@ __global__ void k_prep_link(const Ctx c) {
 
 int launch_prep(const Ctx& c, cudaStream_t s) {
   const int T = 256;
-  int gn = imax(1, imin(ceil_div(imax(c.Nm, c.Bm + 1), T), 4 * kSMs));
+  int gi = imax(1, imin(ceil_div(imax(imax(c.Nm, c.Bm + 1), c.Em), T), kMaxStatBlocks));
   int ge = imax(1, imin(ceil_div(imax(c.Em, c.Nm), T), 4 * kSMs));
-  launch_k(k_prep_init, dim3(gn), dim3(T), 0, s, c);
-  launch_k(k_prep_count, dim3(ge), dim3(T), 0, s, c);
+  launch_k(k_prep_init, dim3(gi), dim3(T), 0, s, c);
   launch_k(k_prep_scan, dim3(1), dim3(1024), 0, s, c);
   launch_k(k_prep_fill, dim3(ge), dim3(T), 0, s, c);
   launch_k(k_prep_sort, dim3(imax(1, imin(ceil_div(c.Nm, 128), 8 * kSMs))), dim3(128), 0, s, c);
   launch_k(k_prep_link, dim3(imax(1, imin(ceil_div(c.Nm, 128), 8 * kSMs))), dim3(128), 0, s, c);
-  note_launches(6);
+  note_launches(5);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }

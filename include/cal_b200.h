@@ -16,6 +16,8 @@
  *  - Batch sizes live in DEVICE memory (`dims`: int32[4] = {N nodes,
  *    E edge_index columns, B graphs, 0}) so that one captured CUDA graph
  *    serves every batch that fits the capacities in `cal_caps`.
+ *  - The workspace must be zero-filled ONCE after allocation (cal_prep keeps its degree counters
+ *    zero between calls instead of clearing them at the start of every call).
  *  - Data-dependent violations (node id out of range, `batch` not sorted)
  *    are reported through the int32 status word at workspace region
  *    CAL_WS_STATUS (0 = ok), not through the return value.
