@@ -398,8 +398,17 @@ def run_gpu(a, rank, local_rank, world):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         A_step = step_algorithmic_bytes(N, E1, bs, eng.H, eng.F, eng.L, P)
+        # DRAM traffic of the same kernel from the committed ncu --set full capture (profiles/ncu_traffic.json)
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if tj.get("workload") == a.workload and a.model == "CausalGCN" and top["stage"] in tj["kernels"]:
+                k = tj["kernels"][top["stage"]]
+                traffic = int(k["dram_read"]) + int(k["dram_write"])
+        except Exception:
+            traffic = None
         roofline = {"bound": "hbm", "kernel": top["stage"], "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": top["gbs"] / peak, "traffic": None,
+                    "frac": top["gbs"] / peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
                     "kernel_us": top["us"], "kernel_alg_bytes": top["alg_bytes"], "kernel_share_of_step": top["share_of_step"],
                     "step_alg_bytes": A_step, "step_achieved_gbs": A_step * a.steps / (ms * 1e-3) / 1e9 / 1.0,

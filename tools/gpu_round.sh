@@ -14,3 +14,8 @@ NCUARGS="--resident 2 --steps 2 --warmup 1 --no-graph --no-e2e --no-cpu-baseline
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py $NCUARGS > gpurun_out/${TAG}_ncu_launch.log 2>&1; echo "ncu launches rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_conv_(fwd|bwd)' -s 8 -c 6 -f -o gpurun_out/${TAG}_prof_conv python bench.py $NCUARGS > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la gpurun_out | tail -12
+# other configurations (BASELINE.json configs[2] and configs[4] shapes), single GPU, no CPU leg
+timeout 300 python bench.py --workload large --steps 30 --warmup 5 --no-cpu-baseline --stages > gpurun_out/${TAG}_bench_large.json 2> gpurun_out/${TAG}_bench_large_stages.txt; echo "bench large rc=$?"
+tail -c 1800 gpurun_out/${TAG}_bench_large_stages.txt
+timeout 300 python bench.py --workload mutag --model CausalGAT --steps 200 --warmup 20 --no-cpu-baseline --stages > gpurun_out/${TAG}_bench_gat.json 2> gpurun_out/${TAG}_bench_gat_stages.txt; echo "bench gat rc=$?"
+tail -c 1800 gpurun_out/${TAG}_bench_gat_stages.txt
