@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--stages", action="store_true", help="also print the per-stage timing table to stderr")
     ap.add_argument("--resident", type=int, default=0, help="number of distinct device-resident batches (default: > L2)")
+    ap.add_argument("--collective", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N>1 gradient exchange: NVLink peer push fused with Adam, or ncclAllReduce")
     ap.add_argument("--no-stage-timing", action="store_true", help="skip the live per-stage timing / roofline")
     return ap.parse_args()
 
@@ -295,7 +297,7 @@ def run_gpu(a, rank, local_rank, world):
         net = cal_b200.CausalGAT(F, C, model_args()).to(dev)
     net.train()
     tr = cal_b200.Trainer(net, cal_b200.batch_caps(batches), lr=1e-3, process_group=True if world > 1 else None,
-                          use_graph=not a.no_graph)
+                          use_graph=not a.no_graph, collective=a.collective)
     hosts = [tr.pack(b) for b in batches[:min(64, n_res)]]               # pinned host copies (e2e)
     resident = [tr.pack(b).to(dev) for b in batches]
     resident_bytes = sum(int(r.numel()) for r in resident)
@@ -419,6 +421,47 @@ def run_gpu(a, rank, local_rank, world):
                 print("%-20s launches %d  %8.2f us  %10d B  %8.1f GB/s" % (r["stage"], r["launches"], r["us"],
                                                                           r["alg_bytes"], r["gbs"] or 0), file=sys.stderr)
 
+    # ---- device-resident epochs: the dataset lives in HBM, cal_collate builds
+    # every mini-batch on the GPU, one captured graph (collate + step) serves the whole epoch; per
+    # epoch the host uploads the shuffled order and the random-intervention permutations, per step nothing
+    if e2e is not None:
+        from cal_b200.data import make_dataset
+        dcfg = dict(cfg)
+        ds = make_dataset(pool, seed=666 + rank, bias=0.9, **dcfg)
+        store = cal_b200.GraphStore(ds, dev)
+        tr2 = cal_b200.Trainer(net, store.caps(bs), lr=1e-3, process_group=True if world > 1 else None,
+                               use_graph=not a.no_graph, collective=a.collective)
+        rng = np.random.RandomState(777 + rank)
+        per_epoch = len(ds) // bs
+        def run_epochs(n_steps):
+            done = 0
+            while done < n_steps:
+                order = rng.permutation(len(ds))[:per_epoch * bs]
+                tr2.begin_epoch(store, order, bs)
+                k = min(per_epoch, n_steps - done)
+                for _ in range(k):
+                    tr2.step_epoch()
+                done += k
+            return tr2.end_epoch()
+        run_epochs(max(3, a.warmup))
+        barrier()
+        e0.record()
+        m_ep = run_epochs(a.steps)
+        e1.record()
+        barrier()
+        tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_e = float(tt.item())
+        e2e["device_resident_epoch"] = {
+            "value": a.steps * graphs_per_step * world / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e / a.steps,
+            "h2d_bytes_per_step": int((4 * per_epoch * bs + (4 * per_epoch * bs if tr2.with_random else 0)) / per_epoch),
+            "d2h_bytes_per_epoch": 32, "graphs_in_store": len(ds), "steps_per_epoch": per_epoch,
+            "api": "Trainer.begin_epoch(store, order) + step_epoch(): cal_collate on the GPU + the step in one captured "
+                   "graph; per epoch the shuffled order and the random-intervention permutations are uploaded, epoch "
+                   "metrics are accumulated on the device and read once (end_epoch)",
+            "last_epoch_metrics": m_ep}
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -437,6 +480,8 @@ def run_gpu(a, rank, local_rank, world):
                                       "workspace reused" % (n_res, resident_bytes / 2 ** 20)),
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
             "launches_per_step": int(tr.launches_per_step), "cuda_graph": not a.no_graph,
+            "collective": {"none": "none (1 GPU)", "nccl": "ncclAllReduce of the flat gradient buffer between a compute and an update graph",
+                           "peer": "NVLink peer-memory push of the gradient chunks fused with Adam (cal_dp_adam_step), one captured graph per step"}[tr.collective],
             "roofline": roofline, "cpu_baseline": cpu, "stages": stage_tab,
             "loss_after": loss_after[:4],
         }

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcal_b200.so")
+# CAL_B200_LIB: an alternative build of the same library (instrumented -DCAL_PHASE_TIMING builds)
+LIB_PATH = os.environ.get("CAL_B200_LIB") or os.path.join(HERE, "libcal_b200.so")
 
 CAL_MAX_LAYERS = 8
 CAL_MAX_BN = 1 + CAL_MAX_LAYERS + 2 + 6
@@ -30,7 +31,10 @@ EXPORTS = [
     "cal_abi_version", "cal_error_string", "cal_workspace_bytes", "cal_workspace_region", "cal_prep",
     "cal_causal_forward", "cal_causal_backward", "cal_adam_step", "cal_adam_tick", "cal_read_status",
     "cal_launch_count", "cal_stage_count", "cal_stage_name",
+    "cal_dp_region_bytes", "cal_dp_alloc", "cal_dp_free", "cal_dp_export", "cal_dp_import", "cal_dp_unmap",
+    "cal_dp_adam_step", "cal_dp_read_error", "cal_collate", "cal_collate_flush",
 ]
+CAL_MAX_WORLD, CAL_DP_HANDLE_BYTES = 16, 64
 CAL_PASS_FORWARD, CAL_PASS_BACKWARD = 0, 1
 
 
@@ -81,6 +85,16 @@ class Batch(C.Structure):
                 ("gat_keep", C.c_void_p), ("edge_stride", C.c_int64)]
 
 
+class GraphStoreDesc(C.Structure):
+    _fields_ = [("num_graphs", C.c_int32), ("num_features", C.c_int32), ("node_ptr", C.c_void_p),
+                ("edge_ptr", C.c_void_p), ("feat", C.c_void_p), ("edge_src", C.c_void_p),
+                ("edge_dst", C.c_void_p), ("y", C.c_void_p)]
+
+
+class DpComm(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("region", C.c_void_p * CAL_MAX_WORLD)]
+
+
 class CalError(RuntimeError):
     pass
 
@@ -128,6 +142,29 @@ def load():
     lib.cal_adam_tick.argtypes = [C.c_void_p, C.c_void_p]
     lib.cal_read_status.restype = C.c_int
     lib.cal_read_status.argtypes = [P(ModelDesc), P(Caps), C.c_void_p, C.c_void_p]
+    lib.cal_collate.restype = C.c_int
+    lib.cal_collate.argtypes = [P(GraphStoreDesc), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                P(Caps), P(Batch), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.cal_collate_flush.restype = C.c_int
+    lib.cal_collate_flush.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.cal_dp_region_bytes.restype = C.c_size_t
+    lib.cal_dp_region_bytes.argtypes = [C.c_int32, C.c_int64]
+    lib.cal_dp_alloc.restype = C.c_int
+    lib.cal_dp_alloc.argtypes = [C.c_int32, C.c_size_t, P(C.c_void_p)]
+    lib.cal_dp_free.restype = C.c_int
+    lib.cal_dp_free.argtypes = [C.c_void_p]
+    lib.cal_dp_export.restype = C.c_int
+    lib.cal_dp_export.argtypes = [C.c_void_p, C.c_char_p]
+    lib.cal_dp_import.restype = C.c_int
+    lib.cal_dp_import.argtypes = [C.c_int32, C.c_char_p, P(C.c_void_p)]
+    lib.cal_dp_unmap.restype = C.c_int
+    lib.cal_dp_unmap.argtypes = [C.c_void_p]
+    lib.cal_dp_adam_step.restype = C.c_int
+    lib.cal_dp_adam_step.argtypes = [P(DpComm), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                     C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_float, C.c_float,
+                                     C.c_float, C.c_void_p]
+    lib.cal_dp_read_error.restype = C.c_int
+    lib.cal_dp_read_error.argtypes = [P(DpComm), C.c_void_p]
     if lib.cal_abi_version() != 1:
         raise CalError("cal_b200: ABI version mismatch")
     _lib = lib

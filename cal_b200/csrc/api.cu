@@ -245,6 +245,7 @@ const char* cal_error_string(int code) {
     case CAL_EALIGN: return "pointer or offset not 16-byte aligned";
     case CAL_ECAPACITY: return "workspace too small for the requested capacities";
     case CAL_EUNSUPPORTED: return "unsupported model configuration";
+    case CAL_ETIMEOUT: return "data-parallel exchange timed out waiting for a peer";
     default: return "unknown error";
   }
 }

@@ -231,7 +231,355 @@ __global__ void k_prep_link(const Ctx c) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small batches (the whole CSR fits one SM's shared memory; cfg 1: N ~ 3 200, E' ~ 10 400): the
+// five kernels above collapse into ONE launch of G + kPrepS CTAs.
+//   CTAs [0, G): input-feature statistics (+ housekeeping).
+//   CTAs [G, G + kPrepS), the structure CTAs: EACH builds both complete CSRs in its own shared
+//   memory -- edges packed to 2 x u16, shared-memory atomics for the degree counts and fill
+//   cursors, a shuffle scan, per-row insertion sort; redundant work, but it only costs shared-memory
+//   cycles and needs no inter-CTA communication -- and then writes only ITS slice of the nodes
+//   (and of their in- / out-rows) to global memory, so the store bandwidth of kPrepS SMs is used.
+// Same results as the multi-kernel path (the row order is fixed by the sort, not by the atomics).
+// smem (4-byte words): cnt_in [Nm] | cnt_out [Nm] | in_ptr [Nm+1] | out_ptr [Nm+1] | dis [Nm] |
+//                      in_key [EP] | out_key [EP] | edges [Em]
+// ---------------------------------------------------------------------------------------------
+constexpr int kPrepT = 1024;
+constexpr int kPrepS = 8;
+constexpr size_t kPrepSmallMaxSmem = 225 * 1024;
+constexpr size_t kPrepStatSmem = (2 * kPrepT + 2 * 512) * sizeof(double);
+inline size_t prep_small_smem(int Nm, int Em) {
+  const size_t b = 4 * ((size_t)5 * Nm + 2 * (size_t)(Em + Nm) + (size_t)Em + 8);
+  return b > kPrepStatSmem ? b : kPrepStatSmem;
+}
+
+__global__ void __launch_bounds__(kPrepT) k_prep_small(const Ctx c) {
+  pdl_sync();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_status, s_wi[32], s_wo[32];
+  const int t = threadIdx.x, T = kPrepT;
+  const int N = c.dims[0], E = c.dims[1], B = c.dims[2];
+  const bool bad_caps = N < 0 || E < 0 || B < 0 || N > c.Nm || E > c.Em || B > c.Bm;
+  const int G = gridDim.x - kPrepS;
+  if ((int)blockIdx.x < G) {
+    // ---- housekeeping + input-feature column statistics (fp64), this CTA's slice of the rows ----
+    const int tid = blockIdx.x * T + t, nth = G * T;
+    PT_DECL
+    if (tid < 64) c.counters[tid] = 0u;
+    if (bad_caps) return;
+    for (int k = tid; k < c.kmax; k += nth) {     // identity BatchNorm record
+      c.bnf(kBnIdentity, BN_SCALE)[k] = 1.f;
+      c.bnf(kBnIdentity, BN_SHIFT)[k] = 0.f;
+      c.bnf(kBnIdentity, BN_MEAN)[k] = 0.f;
+      c.bnf(kBnIdentity, BN_RSTD)[k] = 0.f;
+      c.bnf(kBnIdentity, BN_C1)[k] = 0.f;
+      c.bnf(kBnIdentity, BN_C2)[k] = 0.f;
+    }
+    double* s_s = reinterpret_cast<double*>(smem_raw);     // [T]   (the statistics CTAs use the dynamic
+    double* s_q = s_s + kPrepT;                            // [T]    region for their scratch)
+    double* sTot = s_q + kPrepT;                           // [2 * 512]: F <= 512 (validate_model)
+    const int F = c.F;
+    const int Fw = imin(F, T), rpar = T / Fw;
+    const int rows_per = ceil_div(imax(N, 1), G);
+    const int r0 = imin(blockIdx.x * rows_per, N), r1 = imin(r0 + rows_per, N);
+    for (int cb = 0; cb < F; cb += Fw) {
+      const int col = cb + t % Fw, rs = t / Fw;
+      double s = 0.0, q = 0.0;
+      if (rs < rpar && col < F)
+        for (int r = r0 + rs; r < r1; r += rpar) {
+          double v = (double)c.feat[(size_t)r * F + col];
+          s += v;
+          q += v * v;
+        }
+      __syncthreads();
+      s_s[t] = s;
+      s_q[t] = q;
+      __syncthreads();
+      // fixed-order two-level sum of the rpar row parts: 8 slices, then the 8 slice sums
+      const int sl = t / Fw, cc = t % Fw;
+      const int per_sl = ceil_div(rpar, 8);
+      double a = 0.0, b = 0.0;
+      if (sl < 8)
+        for (int k = sl * per_sl; k < imin(rpar, (sl + 1) * per_sl); ++k) {
+          a += s_s[k * Fw + cc];
+          b += s_q[k * Fw + cc];
+        }
+      __syncthreads();
+      if (sl < 8) {
+        s_s[t] = a;
+        s_q[t] = b;
+      }
+      __syncthreads();
+      if (t < Fw && cb + t < F) {
+        a = b = 0.0;
+        for (int k = 0; k < 8 && k * Fw + t < T; ++k) {
+          a += s_s[k * Fw + t];
+          b += s_q[k * Fw + t];
+        }
+        sTot[cb + t] = a;
+        sTot[F + cb + t] = b;
+      }
+    }
+    __syncthreads();
+    PT_MARK();                                         // 0: wait + column sums
+    const bool fin = grid_sum(c, 0, sTot, 2 * F, G, blockIdx.x);
+    if (fin)
+      for (int k = t; k < 2 * F; k += T) c.statp[k] = sTot[k];
+    PT_MARK();                                         // 1: grid sum
+#ifdef CAL_PHASE_TIMING
+    if (t == 0 && (blockIdx.x == 0 || fin)) for (int q_ = 0; q_ < pt_i; ++q_) c.status[(fin ? 116 : 112) + q_] = (int)pt_v[q_];
+#endif
+    return;
+  }
+  // ---- a structure CTA ----
+  const int sj = (int)blockIdx.x - G;            // slice index
+  if (bad_caps) {
+    if (sj == 0 && t == 0) {
+      c.status[0] = kStCapacity;
+      c.status[1] = c.status[2] = c.status[3] = 0;
+    }
+    return;
+  }
+  const int Nm = c.Nm, EP = c.EP;
+  int* s_cin = reinterpret_cast<int*>(smem_raw);
+  int* s_cout = s_cin + Nm;
+  int* s_iptr = s_cout + Nm;
+  int* s_optr = s_iptr + Nm + 1;
+  float* s_dis = reinterpret_cast<float*>(s_optr + Nm + 1);
+  int* s_ikey = reinterpret_cast<int*>(s_dis + Nm);
+  int* s_okey = s_ikey + EP;
+  unsigned int* s_edge = reinterpret_cast<unsigned int*>(s_okey + EP);     // (row << 16) | col; 0xffffffff = dropped
+  const int lane = t & 31, warp = t >> 5;
+  PT_DECL
+  if (t == 0) s_status = 0;
+  for (int n = t; n < N; n += T) s_cin[n] = s_cout[n] = 0;
+  __syncthreads();
+  PT_MARK();                                           // 0: dependency wait + zero
+  // 0. edges -> shared memory (8 independent 8-byte load pairs in flight per thread) + degree counts
+  //    (gcn_conv.py:56: self loops are dropped)
+  constexpr int kEU = 8;
+  for (int e0 = 0; e0 < E; e0 += kEU * T) {
+    long long r[kEU], d[kEU];
+#pragma unroll
+    for (int u = 0; u < kEU; ++u) {
+      const int e = e0 + u * T + t;
+      r[u] = e < E ? c.ei_row[e] : 0;
+      d[u] = e < E ? c.ei_col[e] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < kEU; ++u) {
+      const int e = e0 + u * T + t;
+      if (e >= E) continue;
+      unsigned int pk = 0xffffffffu;
+      if (r[u] < 0 || r[u] >= N || d[u] < 0 || d[u] >= N) {
+        atomicOr(&s_status, kStBadNode);
+      } else if (r[u] != d[u]) {
+        pk = ((unsigned int)r[u] << 16) | (unsigned int)d[u];
+        atomicAdd(&s_cin[(int)d[u]], 1);
+        atomicAdd(&s_cout[(int)r[u]], 1);
+      }
+      s_edge[e] = pk;
+    }
+  }
+  PT_MARK();                                           // 1: edges + counts
+  // graph ids / graph_ptr / perm: this CTA's slice of the nodes; slice 0 also checks all of `batch`
+  const int nper = ceil_div(imax(N, 1), kPrepS);
+  const int nlo = imin(sj * nper, N), nhi = imin(nlo + nper, N);
+  {
+    constexpr int kNU = 4;
+    const int a0 = sj == 0 ? 0 : nlo, a1 = sj == 0 ? N : nhi;
+    for (int b0 = a0; b0 < a1; b0 += kNU * T) {
+      long long gq[kNU], gpq[kNU];
+#pragma unroll
+      for (int u = 0; u < kNU; ++u) {
+        const int n = b0 + u * T + t;
+        gq[u] = n < a1 ? c.batch[n] : 0;
+        gpq[u] = (n < a1 && n > 0) ? c.batch[n - 1] : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < kNU; ++u) {
+        const int n = b0 + u * T + t;
+        if (n >= a1) continue;
+        long long g = gq[u], gp = gpq[u];
+        if (g < 0 || g >= B || g < gp) {
+          atomicOr(&s_status, kStBadBatch);
+          g = g < 0 ? 0 : (g >= B ? B - 1 : g);
+        }
+        if (n < nlo || n >= nhi) continue;
+        c.node_graph[n] = (int)g;
+        if (gp < -1) gp = -1;
+        if (gp >= B) gp = B - 1;
+        for (long long b = gp + 1; b <= g; ++b) c.graph_ptr[b] = n;     // graphs that start at n (empty ones too)
+        if (n == N - 1)
+          for (long long b = g + 1; b <= B; ++b) c.graph_ptr[b] = N;
+      }
+    }
+  }
+  if (sj == 0) {
+    if (N == 0)
+      for (int b = t; b <= B; b += T) c.graph_ptr[b] = 0;
+    for (int b = t; b < B; b += T) {
+      int p = c.perm_in != nullptr ? c.perm_in[b] : b;
+      if (p < 0 || p >= B) {
+        atomicOr(&s_status, kStBadBatch);
+        p = b;
+      }
+      c.perm[b] = p;
+      c.invperm[p] = b;
+    }
+  }
+  __syncthreads();
+  PT_MARK();                                           // 2: node pass
+  // 1. exclusive scan of (count + 1) in chunks of T nodes (node = chunk * T + t: conflict-free)
+  {
+    int carry_i = 0, carry_o = 0;
+    for (int n0 = 0; n0 < N; n0 += T) {
+      const int n = n0 + t;
+      const int vi = n < N ? s_cin[n] + 1 : 0, vo = n < N ? s_cout[n] + 1 : 0;
+      int xi = vi, xo = vo;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, xi, o), b = __shfl_up_sync(0xffffffffu, xo, o);
+        if (lane >= o) {
+          xi += a;
+          xo += b;
+        }
+      }
+      if (lane == 31) {
+        s_wi[warp] = xi;
+        s_wo[warp] = xo;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        int a = s_wi[lane], b = s_wo[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int a2 = __shfl_up_sync(0xffffffffu, a, o), b2 = __shfl_up_sync(0xffffffffu, b, o);
+          if (lane >= o) {
+            a += a2;
+            b += b2;
+          }
+        }
+        s_wi[lane] = a;
+        s_wo[lane] = b;
+      }
+      __syncthreads();
+      if (n < N) {
+        s_iptr[n] = carry_i + (warp > 0 ? s_wi[warp - 1] : 0) + xi - vi;
+        s_optr[n] = carry_o + (warp > 0 ? s_wo[warp - 1] : 0) + xo - vo;
+        s_dis[n] = 1.0f / sqrtf((float)vo);            // deg^-1/2, degree by source row incl. the loop (gcn_conv.py:66)
+        s_cin[n] = 0;     // becomes the fill cursor
+        s_cout[n] = 0;
+      }
+      carry_i += s_wi[31];
+      carry_o += s_wo[31];
+      __syncthreads();
+    }
+    if (t == 0) {
+      s_iptr[N] = carry_i;
+      s_optr[N] = carry_o;
+    }
+  }
+  __syncthreads();
+  PT_MARK();                                           // 3: scan
+  // 2. fill in arrival order (arbitrary); the appended self loop takes the last slot of its row
+  for (int e = t; e < E; e += T) {
+    const unsigned int pk = s_edge[e];
+    if (pk == 0xffffffffu) continue;
+    const int r = (int)(pk >> 16), d = (int)(pk & 0xffffu);
+    s_ikey[s_iptr[d] + atomicAdd(&s_cin[d], 1)] = e;
+    s_okey[s_optr[r] + atomicAdd(&s_cout[r], 1)] = e;
+  }
+  for (int n = t; n < N; n += T) {
+    s_ikey[s_iptr[n + 1] - 1] = E + n;
+    s_okey[s_optr[n + 1] - 1] = E + n;
+  }
+  __syncthreads();
+  PT_MARK();                                           // 4: fill
+  // 3. this CTA's slice -> global memory.  Rows are ordered by edge_index column WITHOUT sorting: the
+  //    final slot of an entry is its row start + the number of smaller keys in its (short) row, counted
+  //    entry-parallel, so a hub row costs its length per thread instead of its length squared in one.
+  for (int n = nlo + t; n < nhi; n += T) {
+    c.in_ptr[n] = s_iptr[n];
+    c.out_ptr[n] = s_optr[n];
+    c.dis[n] = s_dis[n];
+  }
+  if (sj == kPrepS - 1 && t == 0) {
+    c.in_ptr[N] = s_iptr[N];
+    c.out_ptr[N] = s_optr[N];
+  }
+  {
+    const int pb = s_iptr[nlo], pe = s_iptr[nhi];
+    for (int u = pb + t; u < pe; u += T) {
+      const int key = s_ikey[u];
+      int n, src;
+      if (key < E) {
+        const unsigned int pk = s_edge[key];
+        src = (int)(pk >> 16);
+        n = (int)(pk & 0xffffu);
+      } else {
+        n = src = key - E;
+      }
+      const int a = s_iptr[n], b = s_iptr[n + 1];
+      int rank = 0;
+      for (int v = a; v < b; ++v) rank += s_ikey[v] < key;
+      const int p = a + rank;
+      c.in_key[p] = key;
+      c.in_src[p] = src;
+      c.in_norm[p] = s_dis[src] * s_dis[n];           // dis[row] * 1 * dis[col]
+    }
+    const int qb = s_optr[nlo], qe = s_optr[nhi];
+    for (int u = qb + t; u < qe; u += T) {
+      const int key = s_okey[u];
+      int n, dst;
+      if (key < E) {
+        const unsigned int pk = s_edge[key];
+        n = (int)(pk >> 16);
+        dst = (int)(pk & 0xffffu);
+      } else {
+        n = dst = key - E;
+      }
+      const int a = s_optr[n], b = s_optr[n + 1];
+      int rank = 0;
+      for (int v = a; v < b; ++v) rank += s_okey[v] < key;
+      const int a2 = s_iptr[dst], b2 = s_iptr[dst + 1];
+      int rank2 = 0;
+      for (int v = a2; v < b2; ++v) rank2 += s_ikey[v] < key;
+      const int q = a + rank;
+      c.out_key[q] = key;
+      c.out_dst[q] = dst;
+      c.out_pos[q] = a2 + rank2;                      // in-CSR position of the same edge
+      c.out_norm[q] = s_dis[n] * s_dis[dst];
+    }
+  }
+  if (sj == 0) {
+    __syncthreads();
+    PT_MARK();                                         // 5: slice write-out
+    if (t == 0) {
+      c.status[0] = s_status;
+      c.status[1] = c.status[2] = c.status[3] = 0;
+    }
+#ifdef CAL_PHASE_TIMING
+    if (t == 0) for (int q_ = 0; q_ < pt_i; ++q_) c.status[96 + q_] = (int)pt_v[q_];
+#endif
+  }
+}
+
 int launch_prep(const Ctx& c, cudaStream_t s) {
+  const size_t small = prep_small_smem(c.Nm, c.Em);
+  if (small <= kPrepSmallMaxSmem && c.Nm < 65535) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(k_prep_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrepSmallMaxSmem);
+      if (e != cudaSuccess) return (int)e;
+      attr_set = true;
+    }
+    const int G = imax(1, imin(ceil_div(c.Nm, 128), 64));
+    launch_k(k_prep_small, dim3(G + kPrepS), dim3(kPrepT), small, s, c);
+    note_launches(1);
+    CAL_CUDA_CHECK_LAUNCH();
+    return 0;
+  }
   const int T = 256;
   int gi = imax(1, imin(ceil_div(imax(imax(c.Nm, c.Bm + 1), c.Em), T), kMaxStatBlocks));
   int ge = imax(1, imin(ceil_div(imax(c.Em, c.Nm), T), 4 * kSMs));

@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["PackedLayout", "Trainer", "batch_caps", "allreduce_flat_grads"]
+__all__ = ["PackedLayout", "Trainer", "batch_caps", "allreduce_flat_grads", "PeerExchange", "GraphStore"]
 
 
 def _up(x, m):
@@ -44,6 +44,131 @@ def allreduce_flat_grads(flat_grad, group=None):
     if world > 1:
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
     return 1.0 / world
+
+
+class GraphStore:
+    """A dataset resident in device memory for ``cal_collate`` (csrc/collate.cu): all graphs back
+    to back -- ``node_ptr`` / ``edge_ptr`` i32[G+1], ``feat`` f32[sum n, F], graph-local
+    ``edge_src`` / ``edge_dst`` i32[sum e], ``y`` i64[G].  Replaces the per-step host collate of
+    the reference's DataLoader (train_causal.py:13-15,171-176)."""
+
+    def __init__(self, graphs, device):
+        graphs = list(graphs)
+        self.device = torch.device(device)
+        self.num_graphs = len(graphs)
+        feat = lambda d: d.x if getattr(d, "x", None) is not None else d.feat
+        n = np.array([int(feat(d).size(0)) for d in graphs], dtype=np.int64)
+        e = np.array([int(d.edge_index.size(1)) for d in graphs], dtype=np.int64)
+        if n.sum() >= 2 ** 31 or e.sum() >= 2 ** 31:
+            raise _lib.CalError("cal_b200: GraphStore is limited to 2^31 nodes / edge columns")
+        self.node_counts, self.edge_counts = n, e
+        self.F = int(feat(graphs[0]).size(1)) if graphs else 0
+        to = lambda t: t.to(self.device)
+        self.node_ptr = to(torch.from_numpy(np.concatenate([[0], np.cumsum(n)]).astype(np.int32)))
+        self.edge_ptr = to(torch.from_numpy(np.concatenate([[0], np.cumsum(e)]).astype(np.int32)))
+        self.feat = to(torch.cat([feat(d).float() for d in graphs]).contiguous())
+        ei = torch.cat([d.edge_index for d in graphs], dim=1)
+        self.edge_src = to(ei[0].to(torch.int32).contiguous())
+        self.edge_dst = to(ei[1].to(torch.int32).contiguous())
+        self.y = to(torch.cat([d.y.view(-1)[:1] for d in graphs]).long().contiguous())
+        d = _lib.GraphStoreDesc()
+        d.num_graphs, d.num_features = self.num_graphs, self.F
+        d.node_ptr, d.edge_ptr = self.node_ptr.data_ptr(), self.edge_ptr.data_ptr()
+        d.feat, d.edge_src, d.edge_dst, d.y = (self.feat.data_ptr(), self.edge_src.data_ptr(),
+                                               self.edge_dst.data_ptr(), self.y.data_ptr())
+        self.desc = d
+
+    def caps(self, graphs_per_step, order=None):
+        """Capacities covering every step of ``order`` (default: the worst ``graphs_per_step``
+        graphs of the dataset, which covers any order)."""
+        B = int(graphs_per_step)
+        if order is None:
+            n = int(np.sort(self.node_counts)[::-1][:B].sum())
+            e = int(np.sort(self.edge_counts)[::-1][:B].sum())
+        else:
+            o = np.asarray(order)
+            pad = (-len(o)) % B
+            nn = np.concatenate([self.node_counts[o], np.zeros(pad, dtype=np.int64)]).reshape(-1, B).sum(1)
+            ee = np.concatenate([self.edge_counts[o], np.zeros(pad, dtype=np.int64)]).reshape(-1, B).sum(1)
+            n, e = int(nn.max()), int(ee.max())
+        return _up(n, 32), _up(max(e, 1), 32), _up(B, 8)
+
+
+class PeerExchange:
+    """NVLink peer-memory gradient exchange fused with Adam (``cal_dp_adam_step``, csrc/comm.cu).
+
+    One exchange region per rank, allocated by the library, exported as a CUDA IPC handle and mapped
+    by every peer; the 64-byte handles travel through ``torch.distributed.all_gather_object`` (plumbing
+    only -- no collective runs per step).  Raises ``CalError`` when the peers cannot map each other
+    (different nodes, IPC disabled); the Trainer then keeps the NCCL all-reduce."""
+
+    def __init__(self, lib, device, n_floats, group=None):
+        import torch.distributed as dist
+        self.lib = lib
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > _lib.CAL_MAX_WORLD:
+            raise _lib.CalError("cal_b200: peer exchange supports at most %d ranks" % _lib.CAL_MAX_WORLD)
+        self.device = torch.device(device)
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        nbytes = lib.cal_dp_region_bytes(self.world, int(n_floats))
+        if nbytes == 0:
+            raise _lib.CalError("cal_b200: cal_dp_region_bytes rejected world=%d n=%d" % (self.world, n_floats))
+        mine = C.c_void_p()
+        self._mine, self._mapped = None, []
+        ok, handle = 1, b"\0" * _lib.CAL_DP_HANDLE_BYTES
+        rc = lib.cal_dp_alloc(dev_index, nbytes, C.byref(mine))
+        if rc == 0:
+            self._mine = mine.value
+            buf = C.create_string_buffer(_lib.CAL_DP_HANDLE_BYTES)
+            rc = lib.cal_dp_export(mine, buf)
+            handle = buf.raw
+        ok = int(rc == 0)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (ok, dev_index, handle), group=group)
+        comm = _lib.DpComm()
+        comm.world, comm.rank = self.world, self.rank
+        err = None if all(g[0] for g in gathered) else "a rank could not allocate / export its exchange region"
+        if err is None:
+            for q, (_ok, _dev, h) in enumerate(gathered):
+                if q == self.rank:
+                    comm.region[q] = self._mine
+                    continue
+                m = C.c_void_p()
+                rc = lib.cal_dp_import(dev_index, h, C.byref(m))
+                if rc != 0:
+                    err = "cudaIpcOpenMemHandle of rank %d's region failed: %s" % (q, lib.cal_error_string(rc).decode())
+                    break
+                self._mapped.append(m.value)
+                comm.region[q] = m.value
+        flags = [None] * self.world
+        dist.all_gather_object(flags, err is None, group=group)       # all ranks agree on the outcome
+        if not all(flags):
+            self.close()
+            raise _lib.CalError("cal_b200: peer exchange unavailable (%s)" % (err or "a peer failed to map this rank"))
+        self.comm = comm
+        self.nbytes = nbytes
+
+    def adam_step(self, eng, lr, betas, eps, weight_decay, lr_device=None):
+        if eng.opt_state is None:
+            eng.opt_state = (torch.zeros_like(eng.flat), torch.zeros_like(eng.flat),
+                             torch.zeros(2, dtype=torch.int32, device=eng.device))
+        m, v, step = eng.opt_state
+        _lib.check(self.lib.cal_dp_adam_step(C.byref(self.comm), eng.flat.data_ptr(), eng.flat_grad.data_ptr(),
+                                             m.data_ptr(), v.data_ptr(), eng.total, step.data_ptr(), float(lr),
+                                             lr_device.data_ptr() if lr_device is not None else 0,
+                                             betas[0], betas[1], eps, weight_decay, eng._stream()), "cal_dp_adam_step")
+
+    def check(self, eng):
+        """Raise if an exchange timed out waiting for a peer (synchronises)."""
+        _lib.check(self.lib.cal_dp_read_error(C.byref(self.comm), eng._stream()), "cal_dp_adam_step (peer exchange)")
+
+    def close(self):
+        for m in self._mapped:
+            self.lib.cal_dp_unmap(m)
+        self._mapped = []
+        if self._mine:
+            self.lib.cal_dp_free(self._mine)
+            self._mine = None
 
 
 class PackedLayout:
@@ -112,7 +237,7 @@ class Trainer:
     scales by 1/world_size.  BatchNorm statistics stay per rank."""
 
     def __init__(self, model, caps, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
-                 process_group=None, use_graph=True, with_random=None, max_graphs_cached=1024):
+                 process_group=None, use_graph=True, with_random=None, max_graphs_cached=1024, collective="auto"):
         self.model = model
         self.eng = model.engine
         eng = self.eng
@@ -128,6 +253,22 @@ class Trainer:
             import torch.distributed as dist
             self.pg = dist.group.WORLD if process_group is True else process_group
             self.world = dist.get_world_size(self.pg)
+        # the gradient exchange: "peer" = NVLink peer-memory push fused with Adam (one captured graph per
+        # step, no collective launch), "nccl" = ncclAllReduce between a compute and an update graph,
+        # "auto" = peer when the ranks can map each other's memory, else nccl
+        self.peer = None
+        self.collective = "none"
+        if self.world > 1:
+            if collective not in ("auto", "peer", "nccl"):
+                raise _lib.CalError("cal_b200: collective must be 'auto', 'peer' or 'nccl'")
+            self.collective = "nccl"
+            if collective in ("auto", "peer"):
+                try:
+                    self.peer = PeerExchange(eng.lib, self.device, eng.total, self.pg)
+                    self.collective = "peer"
+                except _lib.CalError:
+                    if collective == "peer":
+                        raise
         self._graphs = {}
         self._max_graphs = max_graphs_cached
         self.staging = torch.zeros(self.layout.nbytes, dtype=torch.uint8, device=self.device)
@@ -185,6 +326,10 @@ class Trainer:
                                                eng.flat_grad.data_ptr(), 0, eng.ws.data_ptr(), eng.ws_bytes, s),
                        "cal_causal_backward")
             eng.gen += 1
+        if self.peer is not None:
+            if part in ("all", "update"):
+                self.peer.adam_step(eng, 0.0, self.betas, self.eps, self.weight_decay, lr_device=self.lr_dev)
+            return
         if part in ("all", "allreduce"):
             self._scale = allreduce_flat_grads(eng.flat_grad, self.pg) if self.world > 1 else 1.0
         if part in ("all", "update"):
@@ -216,7 +361,8 @@ class Trainer:
         if not self.use_graph:
             c0 = self.eng.lib.cal_launch_count()
             self._issue(packed_dev.data_ptr(), keep)
-            self.launches_per_step = int(self.eng.lib.cal_launch_count() - c0) + (1 if self.world > 1 else 0)
+            self.launches_per_step = int(self.eng.lib.cal_launch_count() - c0) + (
+                1 if self.world > 1 and self.peer is None else 0)
             return
         key = packed_dev.data_ptr()
         g = self._graphs.get(key)
@@ -227,7 +373,7 @@ class Trainer:
                 self._warmup(packed_dev, keep)
             count = self.eng.lib.cal_launch_count
             c0 = count()
-            if self.world == 1:
+            if self.world == 1 or self.peer is not None:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=self._capture_stream()):
                     self._issue(key, keep)
@@ -398,6 +544,113 @@ class Trainer:
     def pipe_result(self, slot):
         self._pipe["ring_ev"][slot].synchronize()
         return self._pipe["ring"][slot]
+
+    # ---- device-resident epochs: collate on the GPU, one captured graph for every step ----
+    def begin_epoch(self, store, order, graphs_per_step, perms="draw"):
+        """Upload the epoch's graph order (and the random-intervention permutations, drawn on the
+        host with Python's RNG like model.py:147-152) and rewind the device cursor.  Afterwards
+        ``step_epoch()`` runs one training step per call with no host -> device traffic."""
+        if store.F != self.eng.F:
+            raise _lib.CalError("cal_b200: store has %d features, model expects %d" % (store.F, self.eng.F))
+        B = int(graphs_per_step)
+        order = np.asarray(order, dtype=np.int32)
+        n_steps = -(-len(order) // B)
+        need = store.caps(B, order)
+        caps = self.eng.caps
+        if need[0] > caps.max_nodes or need[1] > caps.max_edges or B > caps.max_graphs:
+            raise _lib.CalError("cal_b200: epoch needs capacities %s, trainer has (%d, %d, %d)"
+                                % (need, caps.max_nodes, caps.max_edges, caps.max_graphs))
+        ep = getattr(self, "_epoch", None)
+        if ep is None or ep["B"] != B or ep["store"] is not store or ep["cap"] < len(order):
+            cap = max(len(order), 1)
+            ep = self._epoch = {
+                "B": B, "store": store, "cap": cap,
+                "order": torch.zeros(cap, dtype=torch.int32, device=self.device),
+                "perm": torch.zeros(-(-cap // B) * B, dtype=torch.int32, device=self.device),
+                "pos": torch.zeros(4, dtype=torch.int32, device=self.device),
+                "acc": torch.zeros(8, dtype=torch.float32, device=self.device),
+                "graph": None,
+            }
+        ep["n"], ep["steps"], ep["done"] = len(order), n_steps, 0
+        ep["order"][:len(order)].copy_(torch.from_numpy(order), non_blocking=True)
+        ep["with_perm"] = False
+        if isinstance(perms, str):                  # "draw"
+            perms = None
+            if self.with_random:
+                perms = np.zeros((n_steps, B), dtype=np.int32)
+                for s in range(n_steps):
+                    bn = min(B, len(order) - s * B)
+                    perms[s, :bn] = self.draw_perm(bn)
+        if perms is not None:
+            pp = np.ascontiguousarray(np.asarray(perms, dtype=np.int32)).reshape(-1)
+            ep["perm"][:pp.size].copy_(torch.from_numpy(pp), non_blocking=True)
+            ep["with_perm"] = True
+        ep["pos"].zero_()
+        ep["acc"].zero_()
+        return n_steps
+
+    def _issue_collate(self, ep):
+        eng = self.eng
+        cb = self.layout.cbatch(self.staging.data_ptr())
+        _lib.check(eng.lib.cal_collate(C.byref(ep["store"].desc), ep["order"].data_ptr(), ep["n"], ep["pos"].data_ptr(),
+                                       ep["B"], ep["perm"].data_ptr() if ep["with_perm"] else 0, C.byref(eng.caps),
+                                       C.byref(cb), 1, eng.loss_parts_full().data_ptr(), ep["acc"].data_ptr(),
+                                       eng._stream()), "cal_collate")
+
+    def step_epoch(self):
+        """One training step on the next ``graphs_per_step`` graphs of the epoch (asynchronous)."""
+        ep = self._epoch
+        if ep["done"] >= ep["steps"]:
+            raise _lib.CalError("cal_b200: the epoch is exhausted (call begin_epoch)")
+        ep["done"] += 1
+        keep = self._gat_keep_for(None)
+        if keep is not None:
+            self._refresh_keep()
+        if not self.use_graph:
+            self._issue_collate(ep)
+            self._issue(self.staging.data_ptr(), keep)
+            return
+        key = (ep["n"], ep["with_perm"])
+        if ep["graph"] is None or ep["graph"][0] != key:
+            if not self._warm:
+                pos = ep["pos"].clone()
+                self._issue_collate(ep)
+                self._warmup(self.staging, keep)
+                ep["pos"].copy_(pos)
+                ep["acc"].zero_()
+            if self.world > 1 and self.peer is None:
+                # NCCL between two captured graphs (see step()): collate + compute | all-reduce | update
+                ga = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(ga, stream=self._capture_stream()):
+                    self._issue_collate(ep)
+                    self._issue(self.staging.data_ptr(), keep, part="compute")
+                gb = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gb, stream=self._capture_stream()):
+                    self._issue(self.staging.data_ptr(), keep, part="update")
+                ep["graph"] = (key, ga, gb)
+            else:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self._capture_stream()):
+                    self._issue_collate(ep)
+                    self._issue(self.staging.data_ptr(), keep)
+                ep["graph"] = (key, g, None)
+        _, ga, gb = ep["graph"]
+        ga.replay()
+        if gb is not None:
+            self._issue(self.staging.data_ptr(), keep, part="allreduce")
+            gb.replay()
+
+    def end_epoch(self):
+        """Epoch metrics like train_causal.py:186-196 (synchronises): dict of mean losses and accuracies."""
+        ep = self._epoch
+        eng = self.eng
+        cb = self.layout.cbatch(self.staging.data_ptr())
+        _lib.check(eng.lib.cal_collate_flush(eng.loss_parts_full().data_ptr(), cb.dims, ep["pos"].data_ptr(),
+                                             ep["acc"].data_ptr(), eng._stream()), "cal_collate_flush")
+        a = ep["acc"].cpu().tolist()
+        n = max(a[7], 1.0)
+        return {"graphs": int(a[7]), "loss": a[0] / n, "c_loss": a[1] / n, "o_loss": a[2] / n, "co_loss": a[3] / n,
+                "acc_c": a[4] / n, "acc_o": a[5] / n, "acc_co": a[6] / n}
 
     def metrics(self):
         """f32[7] device view: loss, c_loss, o_loss, co_loss, correct_c, correct_o, correct_co of

@@ -43,6 +43,7 @@ extern "C" {
 #define CAL_EALIGN (-3)      /* pointer not 16-byte aligned */
 #define CAL_ECAPACITY (-4)   /* workspace too small for the capacities */
 #define CAL_EUNSUPPORTED (-5)
+#define CAL_ETIMEOUT (-6)    /* a data-parallel peer did not deliver its gradients in time */
 
 /* model kind */
 #define CAL_MODEL_GCN 0      /* CausalGCN, model.py:12-164 */
@@ -237,6 +238,69 @@ int cal_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                   int64_t n, int32_t* step, float lr, const float* lr_device, float beta1,
                   float beta2, float eps, float weight_decay, float grad_scale, void* stream);
 int cal_adam_tick(int32_t* step, void* stream);   /* ++step[0] on the device (manual stepping) */
+
+/* ---- mini-batch collation on the device ---------------------------------------------------------
+ * Replaces the host-side collate of the reference's loader (torch_geometric DataLoader ->
+ * Batch.from_data_list, train_causal.py:13-15,171-176): node features concatenated, edge_index
+ * offset by the running node count, `batch` = graph id per node, `y` concatenated.  The dataset is
+ * uploaded once (all graphs back to back, graph-local node ids in the edge lists). */
+typedef struct {
+  int32_t num_graphs, num_features;
+  const int32_t* node_ptr;     /* i32[G+1] first node of every graph */
+  const int32_t* edge_ptr;     /* i32[G+1] first edge_index column of every graph */
+  const float* feat;           /* f32[node_ptr[G], F] */
+  const int32_t* edge_src;     /* i32[edge_ptr[G]] edge_index[0] of every graph, graph-local ids */
+  const int32_t* edge_dst;     /* i32[edge_ptr[G]] edge_index[1] */
+  const int64_t* y;            /* i64[G] */
+} cal_graph_store;
+
+/* Collate the graphs order[pos[0] .. pos[0] + graphs_per_step) (fewer at the end of `order`) into the
+ * buffers `out` points at (they are WRITTEN: dims, perm, feat, edge_index, batch, y; capacities from
+ * `caps`; out->edge_stride >= caps->max_edges).  `order` i32[n_order] and `pos` i32[4] (zero-initialised
+ * cursor, may be NULL = offset 0) live in device memory; with `advance` != 0 the cursor moves on by
+ * the number of graphs taken, so replaying one captured CUDA graph walks through the epoch.
+ * `perm_pool` i32[steps][graphs_per_step] (or NULL = identity): random_idx of model.py:147-152 for
+ * every step of the epoch, drawn on the host like the reference does.  `acc` f32[8] (or NULL, then
+ * `prev_loss` is NULL too): epoch sums -- before the new batch is written, the previous step's
+ * CAL_WS_LOSS (`prev_loss`) is added as sum over graphs of loss / c / o / co, the three correct
+ * counts and the number of graphs (train_causal.py:186-191); cal_collate_flush adds the last step. */
+int cal_collate(const cal_graph_store* store, const int32_t* order, int32_t n_order, int32_t* pos,
+                int32_t graphs_per_step, const int32_t* perm_pool, const cal_caps* caps,
+                const cal_batch* out, int advance, const float* prev_loss, float* acc, void* stream);
+int cal_collate_flush(const float* prev_loss, const int32_t* dims, int32_t* pos, float* acc, void* stream);
+
+/* ---- data-parallel gradient exchange over NVLink peer memory ---------------------------------
+ * The reference trains in ONE process (train_causal.py:171-192: loss.backward(); optimizer.step());
+ * its data-parallel form is DDP's gradient all-reduce between the two.  Here that pair -- sum of the
+ * flat gradient buffer over the ranks, then Adam on the mean -- is ONE kernel per rank that pushes
+ * its gradient chunks into its peers' exchange regions over NVLink, waits per chunk, sums the copies
+ * in rank order (bit-identical replicas) and applies the update (cal_b200/csrc/comm.cu).
+ *
+ * Set-up, once per process group (one process per GPU, all on one node):
+ *   bytes = cal_dp_region_bytes(world, n);  cal_dp_alloc(device, bytes, &mine);
+ *   cal_dp_export(mine, handle)  -> send the 64 handle bytes to every peer (any transport);
+ *   cal_dp_import(device, peer_handle, &region[q]) for q != rank;  region[rank] = mine.
+ * These are the only entry points that allocate (the region must be a whole cudaMalloc allocation
+ * to be exportable) and that synchronise.  cal_dp_adam_step itself is asynchronous and CUDA-graph
+ * capturable; every rank must issue the same sequence of cal_dp_adam_step calls.  `n` % 4 == 0. */
+#define CAL_MAX_WORLD 16
+#define CAL_DP_HANDLE_BYTES 64
+typedef struct {
+  int32_t world, rank;
+  void* region[CAL_MAX_WORLD];   /* region[q] = rank q's exchange region as mapped in THIS process */
+} cal_dp_comm;
+size_t cal_dp_region_bytes(int32_t world, int64_t n);
+int cal_dp_alloc(int32_t device, size_t bytes, void** region);
+int cal_dp_free(void* region);
+int cal_dp_export(void* region, unsigned char handle[CAL_DP_HANDLE_BYTES]);
+int cal_dp_import(int32_t device, const unsigned char handle[CAL_DP_HANDLE_BYTES], void** mapped);
+int cal_dp_unmap(void* mapped);
+/* = cal_adam_step on the rank-ordered mean of the `world` gradient buffers (arguments as there). */
+int cal_dp_adam_step(const cal_dp_comm* comm, float* params, const float* grads, float* exp_avg,
+                     float* exp_avg_sq, int64_t n, int32_t* step, float lr, const float* lr_device,
+                     float beta1, float beta2, float eps, float weight_decay, void* stream);
+/* 0, or CAL_ETIMEOUT if an exchange gave up waiting for a peer (synchronises the stream). */
+int cal_dp_read_error(const cal_dp_comm* comm, void* stream);
 
 /* Poll the status word written by cal_prep (synchronises the stream): returns the CAL_ST_* bits,
  * or a negative CAL_E* / positive cudaError_t. */

@@ -28,7 +28,7 @@ def _rank_batches(rank):
     return [random_case(seed=300 + 10 * rank + i, hidden=64, batch_size=24)[1] for i in range(2)]
 
 
-def _worker(rank, world, port, out_dir, use_graph):
+def _worker(rank, world, port, out_dir, use_graph, collective="nccl"):
     import torch.distributed as dist
     import cal_b200
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
@@ -38,25 +38,30 @@ def _worker(rank, world, port, out_dir, use_graph):
     net = clone_to_cuda(ora, cal_b200, device="cuda:%d" % rank)
     batches = _rank_batches(rank)
     caps = cal_b200.batch_caps([b for r in range(world) for b in _rank_batches(r)])
-    tr = cal_b200.Trainer(net, caps, lr=1e-3, process_group=True, use_graph=use_graph)
+    tr = cal_b200.Trainer(net, caps, lr=1e-3, process_group=True, use_graph=use_graph, collective=collective)
+    assert tr.collective == collective
     for s in range(STEPS):
         b = batches[s % 2]
         tr.step_host(tr.pack(b, perm=list(range(b.num_graphs))))
     torch.cuda.synchronize()
+    if tr.peer is not None:
+        tr.peer.check(tr.eng)                       # no exchange timed out
+        assert tr._update_graph is None              # one captured graph per step, no collective launch
     torch.save({n: p.detach().cpu() for n, p in net.named_parameters()}, os.path.join(out_dir, "p%d.pt" % rank))
     dist.barrier()
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("collective", ["nccl", "peer"])
 @pytest.mark.parametrize("use_graph", [True, False], ids=["graph", "eager"])
-def test_dp_world2_matches_oracle_average(tmp_path, use_graph):
+def test_dp_world2_matches_oracle_average(tmp_path, use_graph, collective):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     import copy
     import torch.multiprocessing as mp
     from oracle import cal_oracle as O
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), use_graph), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), use_graph, collective), nprocs=world, join=True)
     got = [torch.load(os.path.join(tmp_path, "p%d.pt" % r)) for r in range(world)]
     for n in got[0]:
         assert torch.equal(got[0][n], got[1][n]), "rank parameters diverged: " + n

@@ -146,3 +146,29 @@ def test_data_parallel_gradient_exchange_gloo_world2(tmp_path):
     assert not torch.equal(r0["local"], r1["local"])
     want = (r0["local"].double() + r1["local"].double()) / 2
     assert rel_err(r0["reduced"], want) < 1e-6
+
+
+def test_graph_store_layout_and_caps():
+    """GraphStore (the device-resident dataset behind cal_collate) built on the CPU: pointer arrays,
+    graph-local edge ids, and capacities that cover every step of an order."""
+    import numpy as np
+    import cal_b200 as M
+    ds = M.make_dataset(23, seed=4, avg_nodes=12)
+    st = M.GraphStore(ds, "cpu")
+    n = np.array([d.num_nodes for d in ds])
+    e = np.array([d.num_edges for d in ds])
+    assert st.node_ptr.tolist() == [0] + np.cumsum(n).tolist()
+    assert st.edge_ptr.tolist() == [0] + np.cumsum(e).tolist()
+    assert st.feat.shape == (int(n.sum()), ds[0].feat.size(1)) and st.y.tolist() == [int(d.y) for d in ds]
+    for g in (0, 7, 22):                                     # edges stay graph-local
+        s0, s1 = int(st.edge_ptr[g]), int(st.edge_ptr[g + 1])
+        assert torch.equal(st.edge_src[s0:s1].long(), ds[g].edge_index[0])
+        assert int(st.edge_dst[s0:s1].max()) < n[g]
+    order = np.random.RandomState(0).permutation(23)
+    B = 5
+    cn, ce, cb = st.caps(B, order)
+    for s in range(0, 23, B):
+        b = M.Batch.from_data_list([ds[i] for i in order[s:s + B]])
+        assert b.batch.numel() <= cn and b.edge_index.size(1) <= ce
+    wn, we, wb = st.caps(B)                                  # worst case covers any order
+    assert wn >= cn and we >= ce and wb == cb == 8

@@ -21,3 +21,6 @@ print("k_conv_fwd (last launched = MODE 2 masked, no reduce) cycles:", list(zip(
 print("k_conv_bwd (layer 0) cycles:", list(zip(names_b, st[32:41])), "sum", sum(st[32:41]))
 print("k_readout_fwd (head 0, slice 0) cycles:", st[64:74], "sum", sum(st[64:74]))
 print("k_readout_bwd (head 0, slice 0) cycles:", st[80:88], "sum", sum(st[80:88]))
+names_p = ["wait+zero", "edges+counts", "node pass", "scan", "fill", "sort", "write-out"]
+print("k_prep_small structure CTA (slice 0) cycles:", list(zip(names_p, st[96:103])), "sum", sum(st[96:103]))
+print("k_prep_small statistics CTA 0 [column sums, grid sum]:", st[112:114], " finishing CTA:", st[116:118])
