@@ -17,40 +17,79 @@ namespace {
 
 __device__ __forceinline__ int clampN(const Ctx& c) { return imin(imax(c.dims[0], 0), c.Nm); }
 
-__global__ void __launch_bounds__(128) k_edge_att(const Ctx c) {
+// Warp per source node, lanes over its out-edges: the dependent chain is out_ptr -> (out_dst, out_pos)
+// -> pq[dst], three L2 round trips per node regardless of its degree, and every lane keeps its
+// edge's weights in registers for the per-entry factors (no reload).
+__global__ void __launch_bounds__(256) k_edge_att(const Ctx c) {
   pdl_sync();
   const int N = clampN(c);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float be0 = c.params[c.po.edge_att_b], be1 = c.params[c.po.edge_att_b + 1];
-  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+  for (int n = blockIdx.x * kRowWarps + warp; n < N; n += gridDim.x * kRowWarps) {
     const float4 pn = *reinterpret_cast<const float4*>(c.pq + (size_t)n * 4);
+    const float2 an = *reinterpret_cast<const float2*>(c.natt + (size_t)n * 2);
     const int q0 = c.out_ptr[n], q1 = c.out_ptr[n + 1] - 1;       // last slot = appended loop
     float deg0 = 0.f, deg1 = 0.f;
-    for (int q = q0; q < q1; ++q) {
-      const int d = c.out_dst[q], pos = c.out_pos[q];
-      float w0 = 0.5f, w1 = 0.5f;
-      if (!c.no_eatt) {
-        const float4 pd = *reinterpret_cast<const float4*>(c.pq + (size_t)d * 4);
-        const float t0 = pn.x + pd.z + be0, t1 = pn.y + pd.w + be1;
-        const float m = fmaxf(t0, t1);
-        const float e0 = expf(t0 - m), e1 = expf(t1 - m);
-        const float inv = 1.0f / (e0 + e1);
-        w0 = e0 * inv;
-        w1 = e1 * inv;
+    if (q1 - q0 + 1 <= 32) {
+      // the common case: the whole row (loop included) in one pass, weights stay in registers
+      const int q = q0 + lane;
+      const bool live = q <= q1, loop = q == q1;
+      int pos = 0;
+      float w0 = 0.f, w1 = 0.f;
+      if (live) {
+        pos = c.out_pos[q];
+        w0 = w1 = loop ? 1.f : 0.5f;
+        if (!loop && !c.no_eatt) {
+          const int d = c.out_dst[q];
+          const float4 pd = *reinterpret_cast<const float4*>(c.pq + (size_t)d * 4);
+          const float t0 = pn.x + pd.z + be0, t1 = pn.y + pd.w + be1;
+          const float m = fmaxf(t0, t1);
+          const float e0 = expf(t0 - m), e1 = expf(t1 - m);
+          const float inv = 1.0f / (e0 + e1);
+          w0 = e0 * inv;
+          w1 = e1 * inv;
+        }
+      }
+      deg0 = warp_sum(w0);
+      deg1 = warp_sum(w1);
+      const float2 dn = make_float2(1.0f / sqrtf(deg0), 1.0f / sqrtf(deg1));
+      if (lane == 0) *reinterpret_cast<float2*>(c.disw + (size_t)n * 2) = dn;
+      if (live) {
+        *reinterpret_cast<float2*>(c.watt + (size_t)pos * 2) = make_float2(w0, w1);
+        // per-entry factors of the masked convs' gather (so that it needs no per-source lookups)
+        *reinterpret_cast<float2*>(c.edge_wn + (size_t)pos * 2) = make_float2(dn.x * w0, dn.y * w1);
+        *reinterpret_cast<float2*>(c.edge_na + (size_t)pos * 2) = an;
+      }
+      continue;
+    }
+    // hub row: two strided passes
+    for (int q = q0 + lane; q <= q1; q += 32) {
+      const int pos = c.out_pos[q];
+      float w0 = 1.f, w1 = 1.f;
+      if (q < q1) {
+        w0 = w1 = 0.5f;
+        if (!c.no_eatt) {
+          const int d = c.out_dst[q];
+          const float4 pd = *reinterpret_cast<const float4*>(c.pq + (size_t)d * 4);
+          const float t0 = pn.x + pd.z + be0, t1 = pn.y + pd.w + be1;
+          const float m = fmaxf(t0, t1);
+          const float e0 = expf(t0 - m), e1 = expf(t1 - m);
+          const float inv = 1.0f / (e0 + e1);
+          w0 = e0 * inv;
+          w1 = e1 * inv;
+        }
       }
       *reinterpret_cast<float2*>(c.watt + (size_t)pos * 2) = make_float2(w0, w1);
       deg0 += w0;
       deg1 += w1;
     }
-    *reinterpret_cast<float2*>(c.watt + (size_t)c.out_pos[q1] * 2) = make_float2(1.f, 1.f);
-    deg0 += 1.f;
-    deg1 += 1.f;
+    deg0 = warp_sum(deg0);
+    deg1 = warp_sum(deg1);
     const float2 dn = make_float2(1.0f / sqrtf(deg0), 1.0f / sqrtf(deg1));
-    *reinterpret_cast<float2*>(c.disw + (size_t)n * 2) = dn;
-    // per-entry factors of the masked convs' gather (so that it needs no per-source lookups)
-    const float2 an = *reinterpret_cast<const float2*>(c.natt + (size_t)n * 2);
-    for (int q = q0; q <= q1; ++q) {
+    if (lane == 0) *reinterpret_cast<float2*>(c.disw + (size_t)n * 2) = dn;
+    for (int q = q0 + lane; q <= q1; q += 32) {
       const int pos = c.out_pos[q];
-      const float2 w = *reinterpret_cast<const float2*>(c.watt + (size_t)pos * 2);
+      const float2 w = *reinterpret_cast<const float2*>(c.watt + (size_t)pos * 2);   // written by this lane above
       *reinterpret_cast<float2*>(c.edge_wn + (size_t)pos * 2) = make_float2(dn.x * w.x, dn.y * w.y);
       *reinterpret_cast<float2*>(c.edge_na + (size_t)pos * 2) = an;
     }
@@ -136,29 +175,37 @@ __global__ void __launch_bounds__(256) k_masked_bwd_gather(const Ctx c) {
 // Weighted-norm backward (thread per node): d deg^-1/2, d deg, then for every out-edge of the
 // node d w_e (both branches), the edge softmax backward dt_e, and dp[n] = sum_e dt_e.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_norm_bwd(const Ctx c) {
+// Warp per node, lanes over its out- and in-edges (three dependent L2 round trips per node).
+__global__ void __launch_bounds__(256) k_norm_bwd(const Ctx c) {
   pdl_sync();
   const int N = clampN(c);
-  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int n = blockIdx.x * kRowWarps + warp; n < N; n += gridDim.x * kRowWarps) {
     const int q0 = c.out_ptr[n], q1 = c.out_ptr[n + 1] - 1;
     const int p0 = c.in_ptr[n], p1 = c.in_ptr[n + 1] - 1;        // p1 = the appended loop
-    float dp0 = 0.f, dp1 = 0.f;
     if (c.no_eatt) {
-      for (int q = q0; q <= q1; ++q) *reinterpret_cast<float2*>(c.dt + (size_t)c.out_pos[q] * 2) = make_float2(0.f, 0.f);
-      *reinterpret_cast<float2*>(c.dp + (size_t)n * 2) = make_float2(0.f, 0.f);
+      for (int q = q0 + lane; q <= q1; q += 32)
+        *reinterpret_cast<float2*>(c.dt + (size_t)c.out_pos[q] * 2) = make_float2(0.f, 0.f);
+      if (lane == 0) *reinterpret_cast<float2*>(c.dp + (size_t)n * 2) = make_float2(0.f, 0.f);
       continue;
     }
     const float2 dn = *reinterpret_cast<const float2*>(c.disw + (size_t)n * 2);
+    // this lane's first out-edge stays in registers for the second half (rows longer than 32 reload)
+    int pos_r = -1;
+    float2 g_r = make_float2(0.f, 0.f), w_r = g_r, dsd_r = g_r;
     float dd0 = 0.f, dd1 = 0.f;                                   // d dis[n]
-    for (int q = q0; q < q1; ++q) {
+    for (int q = q0 + lane; q < q1; q += 32) {
       const int pos = c.out_pos[q], d = c.out_dst[q];
       const float2 g = *reinterpret_cast<const float2*>(c.dnrm + (size_t)pos * 2);
       const float2 w = *reinterpret_cast<const float2*>(c.watt + (size_t)pos * 2);
       const float2 dsd = *reinterpret_cast<const float2*>(c.disw + (size_t)d * 2);
+      if (q == q0 + lane) {
+        pos_r = pos; g_r = g; w_r = w; dsd_r = dsd;
+      }
       dd0 = fmaf(g.x * w.x, dsd.x, dd0);
       dd1 = fmaf(g.y * w.y, dsd.y, dd1);
     }
-    for (int p = p0; p < p1; ++p) {
+    for (int p = p0 + lane; p < p1; p += 32) {
       const int s = c.in_src[p];
       const float2 g = *reinterpret_cast<const float2*>(c.dnrm + (size_t)p * 2);
       const float2 w = *reinterpret_cast<const float2*>(c.watt + (size_t)p * 2);
@@ -166,18 +213,26 @@ __global__ void __launch_bounds__(128) k_norm_bwd(const Ctx c) {
       dd0 = fmaf(g.x * w.x, dss.x, dd0);
       dd1 = fmaf(g.y * w.y, dss.y, dd1);
     }
-    {
+    if (lane == 0) {
       const float2 g = *reinterpret_cast<const float2*>(c.dnrm + (size_t)p1 * 2);
       dd0 = fmaf(2.f * dn.x, g.x, dd0);
       dd1 = fmaf(2.f * dn.y, g.y, dd1);
     }
+    dd0 = warp_sum(dd0);
+    dd1 = warp_sum(dd1);
     const float ddeg0 = -0.5f * dn.x * dn.x * dn.x * dd0;         // d deg = -1/2 deg^-3/2 d dis
     const float ddeg1 = -0.5f * dn.y * dn.y * dn.y * dd1;
-    for (int q = q0; q < q1; ++q) {
-      const int pos = c.out_pos[q], d = c.out_dst[q];
-      const float2 g = *reinterpret_cast<const float2*>(c.dnrm + (size_t)pos * 2);
-      const float2 w = *reinterpret_cast<const float2*>(c.watt + (size_t)pos * 2);
-      const float2 dsd = *reinterpret_cast<const float2*>(c.disw + (size_t)d * 2);
+    float dp0 = 0.f, dp1 = 0.f;
+    for (int q = q0 + lane; q < q1; q += 32) {
+      int pos = pos_r;
+      float2 g = g_r, w = w_r, dsd = dsd_r;
+      if (q != q0 + lane) {
+        pos = c.out_pos[q];
+        const int d = c.out_dst[q];
+        g = *reinterpret_cast<const float2*>(c.dnrm + (size_t)pos * 2);
+        w = *reinterpret_cast<const float2*>(c.watt + (size_t)pos * 2);
+        dsd = *reinterpret_cast<const float2*>(c.disw + (size_t)d * 2);
+      }
       const float dw0 = fmaf(g.x * dn.x, dsd.x, ddeg0);
       const float dw1 = fmaf(g.y * dn.y, dsd.y, ddeg1);
       const float dot = w.x * dw0 + w.y * dw1;
@@ -186,8 +241,12 @@ __global__ void __launch_bounds__(128) k_norm_bwd(const Ctx c) {
       dp0 += dt0;
       dp1 += dt1;
     }
-    *reinterpret_cast<float2*>(c.dt + (size_t)c.out_pos[q1] * 2) = make_float2(0.f, 0.f);
-    *reinterpret_cast<float2*>(c.dp + (size_t)n * 2) = make_float2(dp0, dp1);
+    dp0 = warp_sum(dp0);
+    dp1 = warp_sum(dp1);
+    if (lane == 0) {
+      *reinterpret_cast<float2*>(c.dt + (size_t)c.out_pos[q1] * 2) = make_float2(0.f, 0.f);
+      *reinterpret_cast<float2*>(c.dp + (size_t)n * 2) = make_float2(dp0, dp1);
+    }
   }
 }
 
@@ -198,7 +257,7 @@ __global__ void __launch_bounds__(128) k_norm_bwd(const Ctx c) {
 // plus per-CTA partials of the node_att_mlp / edge_att_mlp gradients.
 // ---------------------------------------------------------------------------------------------
 template <int VEC>
-__global__ void __launch_bounds__(256) k_att_bwd(const Ctx c) {
+__global__ void __launch_bounds__(256, 2) k_att_bwd(const Ctx c) {
   pdl_sync();
   constexpr int H = 32 * VEC;
   __shared__ float sRed[kRowWarps * H];
@@ -316,21 +375,21 @@ __global__ void __launch_bounds__(256) k_att_bwd(const Ctx c) {
 }  // namespace
 
 int launch_edge_att(const Ctx& c, cudaStream_t s) {
-  launch_k(k_edge_att, dim3(imax(1, imin(ceil_div(c.Nm, 128), 8 * kSMs))), dim3(128), 0, s, c);
+  launch_k(k_edge_att, dim3(imax(1, imin(ceil_div(c.Nm, kRowWarps), 8 * kSMs))), dim3(256), 0, s, c);
   note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }
 
 int launch_masked_bwd_gather(const Ctx& c, cudaStream_t s) {
-  CAL_DISPATCH_VEC(c.H, { launch_k(k_masked_bwd_gather<VEC>, dim3(c.g_row / 2 > 0 ? c.g_row / 2 : 1, 2), dim3(256), 0, s, c); });
+  CAL_DISPATCH_VEC(c.H, { launch_k(k_masked_bwd_gather<VEC>, dim3(c.g_row, 2), dim3(256), 0, s, c); });
   note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }
 
 int launch_norm_backward(const Ctx& c, cudaStream_t s) {
-  launch_k(k_norm_bwd, dim3(imax(1, imin(ceil_div(c.Nm, 128), 8 * kSMs))), dim3(128), 0, s, c);
+  launch_k(k_norm_bwd, dim3(imax(1, imin(ceil_div(c.Nm, kRowWarps), 8 * kSMs))), dim3(256), 0, s, c);
   note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;

@@ -148,27 +148,27 @@ __global__ void __launch_bounds__(256) k_feat_fwd(const Ctx c) {
 template <int VEC>
 constexpr size_t conv_smem_bytes() {
   constexpr int H = 32 * VEC;
-  return (size_t)H * H * 4 + (size_t)kTileRows * H * 4 + (size_t)kRowWarps * H * 8 + (kTileRows + 4) * 4 +
+  return (size_t)H * H * 4 + (size_t)kTileRows * (H + kPad) * 4 + (size_t)kRowWarps * H * 8 + (kTileRows + 4) * 4 +
          (size_t)kEdgeStage * 8;
 }
 // forward layers: sW [H][H] | sA [R][H] | sRed f64 [8][H] | sPtr [R+4] | sX [stage][H] | sXn | sXa | sXs [stage]
 template <int VEC>
 constexpr size_t convf_smem_bytes(int stage_rows) {
   constexpr int H = 32 * VEC;
-  return (size_t)H * H * 4 + (size_t)kTileRows * H * 4 + (size_t)kRowWarps * H * 8 + (kTileRows + 4) * 4 +
+  return (size_t)H * H * 4 + (size_t)kTileRows * (H + kPad) * 4 + (size_t)kRowWarps * H * 8 + (kTileRows + 4) * 4 +
          (size_t)stage_rows * (H * 4 + 12);
 }
 
 template <int VEC, int MODE>
 __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) {
-  constexpr int H = 32 * VEC;
+  constexpr int H = 32 * VEC, LDA = H + kPad;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double sTot[MODE == 2 ? 1 : 4 * H];
   const Dims d = load_dims(c);
   const int N = d.N;
   float* sW = reinterpret_cast<float*>(smem_raw);
   float* sA = sW + H * H;
-  double* sRed = reinterpret_cast<double*>(sA + kTileRows * H);
+  double* sRed = reinterpret_cast<double*>(sA + kTileRows * LDA);
   int* sPtr = reinterpret_cast<int*>(sRed + kRowWarps * H);
   constexpr int kStage = MODE == 2 ? kStageMasked : kStageFwd;
   float* sX = reinterpret_cast<float*>(sPtr + kTileRows + 4);   // [kStage][H] staged neighbour rows (16-byte aligned)
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
             }
           }
           if (MODE == 2) a.store(aggout + (size_t)i * H, lane);
-          a.store(sA + lr * H, lane);
+          a.store(sA + lr * LDA, lane);
         }
         __syncthreads();                               // the stage is rewritten by the next batch
       } else {
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
             }
           }
           if (MODE == 2) a.store(aggout + (size_t)i * H, lane);
-          a.store(sA + lr * H, lane);
+          a.store(sA + lr * LDA, lane);
         }
       }
       rb = re;
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
         if (lr >= nrows) {
           RowVec<VEC> z;
           z.zero();
-          z.store(sA + lr * H, lane);
+          z.store(sA + lr * LDA, lane);
         }
       }
     }
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
     for (int r = 0; r < kRPW; ++r)
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
-    tile_gemm<VEC, kRPW>(sA, H, sW, H, H, acc);
+    tile_gemm<VEC, kRPW>(sA, LDA, sW, H, H, acc);
     PT_MARK();                                         // 5: GEMM
     // ---- epilogue ----
 #pragma unroll
@@ -328,6 +328,182 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
 }
 
 // ---------------------------------------------------------------------------------------------
+// context_convs and objects_convs (model.py:112-113) in ONE pass over the graph: both branches
+// aggregate the same neighbour rows x_{L+1}[src] -- they differ only in the node attention, the
+// BatchNorm affine (bnc / bno), the attention-weighted norm and the weight matrix -- so a CTA
+// stages every neighbour row once and feeds both accumulators, then runs the two tile GEMMs.
+// (The per-branch variant k_conv_fwd<MODE 2> needs 2 CTAs per SM, which leaves room for only 40
+// staged rows: 2-3 dependent staging rounds per tile.  Here one round of up to 128 rows does.)
+// smem: sW [2][H][H] | sA [2][R][H] | sPtr [R+4] | sX [stage][H] | sXn [stage][2] | sXa [stage][2] | sXs [stage]
+// ---------------------------------------------------------------------------------------------
+constexpr int kStageBoth = 128;
+template <int VEC>
+constexpr size_t masked_both_smem_bytes() {
+  constexpr int H = 32 * VEC;
+  return 2 * (size_t)H * H * 4 + 2 * (size_t)kTileRows * (H + kPad) * 4 + (kTileRows + 4) * 4 +
+         (size_t)kStageBoth * (H * 4 + 20);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) k_masked_fwd_both(const Ctx c) {
+  constexpr int H = 32 * VEC, LDA = H + kPad;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Dims d = load_dims(c);
+  const int N = d.N;
+  float* sW = reinterpret_cast<float*>(smem_raw);                 // [2][H][H]
+  float* sA = sW + 2 * H * H;                                     // [2][R][H]
+  int* sPtr = reinterpret_cast<int*>(sA + 2 * kTileRows * LDA);
+  float* sX = reinterpret_cast<float*>(sPtr + kTileRows + 4);     // [kStageBoth][H]
+  float2* sXn = reinterpret_cast<float2*>(sX + (size_t)kStageBoth * H);   // dis_w[source] * edge_att, both branches
+  float2* sXa = sXn + kStageBoth;                                 // node_att[source], both branches
+  int* sXs = reinterpret_cast<int*>(sXa + kStageBoth);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* xin = c.Xl(c.L);
+
+  stage_matrix_async(sW, c.params + c.po.context_w, H * H);
+  stage_matrix_async(sW + H * H, c.params + c.po.objects_w, H * H);
+  pdl_sync();                                        // everything below may read the predecessor's output
+
+  BnLane<VEC> bn0, bn1;
+  bn0.load_fwd(c, c.L + 1, lane);
+  bn1.load_fwd(c, c.L + 2, lane);
+  float bv0[VEC], bv1[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    bv0[i] = c.params[c.po.context_b + lane * VEC + i];
+    bv1[i] = c.params[c.po.objects_b + lane * VEC + i];
+  }
+  float* agg0 = c.agg;
+  float* agg1 = c.agg + (size_t)c.Nm * H;
+  float* z0 = c.Z;
+  float* z1 = c.Z + (size_t)c.Nm * H;
+  const float2* edge_wn = reinterpret_cast<const float2*>(c.edge_wn);
+  const float2* edge_na = reinterpret_cast<const float2*>(c.edge_na);
+  const float2* disw = reinterpret_cast<const float2*>(c.disw);
+
+  const int ntiles = ceil_div(N, kTileRows);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int row0 = tile * kTileRows;
+    const int nrows = imin(kTileRows, N - row0);
+    __syncthreads();                                   // previous tile's readers of sA / sPtr are done
+    if (threadIdx.x <= nrows) sPtr[threadIdx.x] = c.in_ptr[row0 + threadIdx.x];
+    __syncthreads();
+    for (int rb = 0; rb < nrows;) {
+      int re = rb;
+      while (re < nrows && sPtr[re + 1] - sPtr[rb] <= kStageBoth) ++re;
+      const bool direct = re == rb;                    // a single row with more in-edges than the stage holds
+      if (direct) re = rb + 1;
+      const int pb = sPtr[rb], cnt = sPtr[re] - pb;
+      if (!direct) {
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
+          sXs[e] = c.in_src[pb + e];
+          sXn[e] = edge_wn[pb + e];
+          sXa[e] = edge_na[pb + e];
+        }
+        __syncthreads();
+        for (int e = warp; e < cnt; e += kRowWarps)
+          if (lane < H / 4) cp_async16(sX + (size_t)e * H + lane * 4, xin + (size_t)sXs[e] * H + lane * 4);
+        float2 di_pre[kRPW];                           // target-side factors: in flight with the row copies
+#pragma unroll
+        for (int k = 0; k < kRPW; ++k) {
+          const int lr = rb + warp + k * kRowWarps;
+          di_pre[k] = lr < re ? disw[row0 + lr] : make_float2(0.f, 0.f);
+        }
+        cp_async_wait_all();
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kRPW; ++k) {
+          const int lr = rb + warp + k * kRowWarps;
+          if (lr >= re) break;
+          const int i = row0 + lr;
+          const int e0 = sPtr[lr] - pb, e1 = sPtr[lr + 1] - pb;
+          const float2 di = di_pre[k];
+          RowVec<VEC> a0, a1;
+          a0.zero();
+          a1.zero();
+          for (int e = e0; e < e1; ++e) {
+            RowVec<VEC> v;
+            v.load_coherent(sX + (size_t)e * H, lane);
+            const float2 wn = sXn[e], am = sXa[e];
+            const float w0 = wn.x * di.x, w1 = wn.y * di.y;              // dis[row] * w * dis[col]
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+              a0.v[k] = fmaf(w0, fmaf(am.x * v.v[k], bn0.sc[k], bn0.sh[k]), a0.v[k]);
+              a1.v[k] = fmaf(w1, fmaf(am.y * v.v[k], bn1.sc[k], bn1.sh[k]), a1.v[k]);
+            }
+          }
+          a0.store(agg0 + (size_t)i * H, lane);
+          a1.store(agg1 + (size_t)i * H, lane);
+          a0.store(sA + lr * LDA, lane);
+          a1.store(sA + (kTileRows + lr) * LDA, lane);
+        }
+        __syncthreads();                               // the stage is rewritten by the next batch
+      } else {
+        if (warp == 0) {                               // hub row: gather straight from global memory
+          const int lr = rb, i = row0 + lr;
+          const float2 di = disw[i];
+          RowVec<VEC> a0, a1;
+          a0.zero();
+          a1.zero();
+          for (int p = sPtr[lr]; p < sPtr[lr + 1]; ++p) {
+            const int src = c.in_src[p];
+            RowVec<VEC> v;
+            v.load_coherent(xin + (size_t)src * H, lane);
+            const float w0 = (c.disw[(size_t)src * 2] * c.watt[(size_t)p * 2]) * di.x;
+            const float w1 = (c.disw[(size_t)src * 2 + 1] * c.watt[(size_t)p * 2 + 1]) * di.y;
+            const float am0 = c.natt[(size_t)src * 2], am1 = c.natt[(size_t)src * 2 + 1];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+              a0.v[k] = fmaf(w0, fmaf(am0 * v.v[k], bn0.sc[k], bn0.sh[k]), a0.v[k]);
+              a1.v[k] = fmaf(w1, fmaf(am1 * v.v[k], bn1.sc[k], bn1.sh[k]), a1.v[k]);
+            }
+          }
+          a0.store(agg0 + (size_t)i * H, lane);
+          a1.store(agg1 + (size_t)i * H, lane);
+          a0.store(sA + lr * LDA, lane);
+          a1.store(sA + (kTileRows + lr) * LDA, lane);
+        }
+      }
+      rb = re;
+    }
+    if (warp * kRPW + kRPW > nrows) {                  // zero the rows of a ragged last tile
+      for (int r = 0; r < kRPW; ++r) {
+        const int lr = warp * kRPW + r;
+        if (lr >= nrows) {
+          RowVec<VEC> z;
+          z.zero();
+          z.store(sA + lr * LDA, lane);
+          z.store(sA + (kTileRows + lr) * LDA, lane);
+        }
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+#pragma unroll
+    for (int br = 0; br < 2; ++br) {
+      float acc[kRPW][VEC];
+#pragma unroll
+      for (int r = 0; r < kRPW; ++r)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
+      tile_gemm<VEC, kRPW>(sA + br * kTileRows * LDA, LDA, sW + br * H * H, H, H, acc);
+      float* zo = br ? z1 : z0;
+#pragma unroll
+      for (int r = 0; r < kRPW; ++r) {
+        const int i = row0 + warp * kRPW + r;
+        if (i < N) {                                    // warp-uniform
+          RowVec<VEC> o;
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) o.v[k] = fmaxf(acc[r][k] + (br ? bv1[k] : bv0[k]), 0.f);
+          o.store(zo + (size_t)i * H, lane);
+        }
+      }
+    }
+  }
+  cp_async_wait_all();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Fused GCNConv layer, backward (backbone layers).  With g_z = relu'(x_out) * bn_up'(D_up):
 //   u_j   = sum_{e: row_e = j} norm_e * g_z[col_e]          (transpose aggregate, by-source CSR)
 //   D_j   = u_j W^T                                          (gradient w.r.t. bn_l output)
@@ -339,21 +515,21 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
 template <int VEC>
 constexpr size_t convb_smem_bytes() {
   constexpr int H = 32 * VEC;
-  return (size_t)H * H * 4 + 2 * (size_t)kTileRows * H * 4 + (size_t)kRowWarps * H * 8 + (kTileRows + 4) * 4 +
+  return (size_t)H * H * 4 + 2 * (size_t)kTileRows * (H + kPad) * 4 + (size_t)kRowWarps * H * 8 + (kTileRows + 4) * 4 +
          (size_t)kStageBwd * (2 * H * 4 + 8);
 }
 
 template <int VEC>
 __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) {
-  constexpr int H = 32 * VEC;
+  constexpr int H = 32 * VEC, LDA = H + kPad;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double sTot[2 * H];
   const Dims d = load_dims(c);
   const int N = d.N;
   float* sW = reinterpret_cast<float*>(smem_raw);
   float* sU = sW + H * H;
-  float* sY = sU + kTileRows * H;
-  double* sRed = reinterpret_cast<double*>(sY + kTileRows * H);
+  float* sY = sU + kTileRows * LDA;
+  double* sRed = reinterpret_cast<double*>(sY + kTileRows * LDA);
   int* sPtr = reinterpret_cast<int*>(sRed + kRowWarps * H);
   float* sXD = reinterpret_cast<float*>(sPtr + kTileRows + 4);   // [kStageBwd][H] staged D_up rows
   float* sXX = sXD + (size_t)kStageBwd * H;                       // [kStageBwd][H] staged x_up rows
@@ -414,14 +590,24 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
             cp_async16(sXD + (size_t)e * H + lane * 4, Dup + off);
             cp_async16(sXX + (size_t)e * H + lane * 4, xup + off);
           }
+        RowVec<VEC> xi_pre[kRPW];                      // the rows' own inputs: in flight with the row copies
+#pragma unroll
+        for (int k = 0; k < kRPW; ++k) {
+          const int lr = rb + warp + k * kRowWarps;
+          if (lr < re) xi_pre[k].load_coherent(xin + (size_t)(row0 + lr) * H, lane);
+          else xi_pre[k].zero();
+        }
         cp_async_wait_all();
         __syncthreads();
-        for (int lr = rb + warp; lr < re; lr += kRowWarps) {
+#pragma unroll
+        for (int k = 0; k < kRPW; ++k) {
+          const int lr = rb + warp + k * kRowWarps;
+          if (lr >= re) break;
           const int j = row0 + lr;
           const int e0 = sPtr[lr] - qb, e1 = sPtr[lr + 1] - qb;
           RowVec<VEC> u, y, xi;
           u.zero();
-          xi.load_coherent(xin + (size_t)j * H, lane);
+          xi = xi_pre[k];
           for (int e = e0; e < e1; ++e) {
             RowVec<VEC> gv, xv;
             gv.load_coherent(sXD + (size_t)e * H, lane);
@@ -436,8 +622,8 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
           }
 #pragma unroll
           for (int k = 0; k < VEC; ++k) y.v[k] = fmaf(xi.v[k], bi.sc[k], bi.sh[k]);
-          u.store(sU + lr * H, lane);
-          y.store(sY + lr * H, lane);
+          u.store(sU + lr * LDA, lane);
+          y.store(sY + lr * LDA, lane);
         }
         __syncthreads();
       } else {
@@ -461,8 +647,8 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
           }
 #pragma unroll
           for (int k = 0; k < VEC; ++k) y.v[k] = fmaf(xi.v[k], bi.sc[k], bi.sh[k]);
-          u.store(sU + lr * H, lane);
-          y.store(sY + lr * H, lane);
+          u.store(sU + lr * LDA, lane);
+          y.store(sY + lr * LDA, lane);
         }
       }
       rb = re;
@@ -473,8 +659,8 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
         if (lr >= nrows) {
           RowVec<VEC> z;
           z.zero();
-          z.store(sU + lr * H, lane);
-          z.store(sY + lr * H, lane);
+          z.store(sU + lr * LDA, lane);
+          z.store(sY + lr * LDA, lane);
         }
       }
     }
@@ -482,19 +668,26 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
     cp_async_wait_all();
     __syncthreads();
     PT_MARK();                                         // 3: wait W + all warps
+    RowVec<VEC> xe[kRPW];                              // inputs of the rows this warp finishes: loaded under the GEMM
+#pragma unroll
+    for (int r = 0; r < kRPW; ++r) {
+      const int j = row0 + warp * kRPW + r;
+      if (j < N) xe[r].load_coherent(xin + (size_t)j * H, lane);
+      else xe[r].zero();
+    }
     float acc[kRPW][VEC];
 #pragma unroll
     for (int r = 0; r < kRPW; ++r)
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
-    tile_gemm<VEC, kRPW>(sU, H, sW, H, H, acc);
+    tile_gemm<VEC, kRPW>(sU, LDA, sW, H, H, acc);
     PT_MARK();                                         // 4: GEMM dX
 #pragma unroll
     for (int r = 0; r < kRPW; ++r) {
       const int j = row0 + warp * kRPW + r;
       if (j < N) {
         RowVec<VEC> o, xi;
-        xi.load_coherent(xin + (size_t)j * H, lane);
+        xi = xe[r];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
           o.v[k] = acc[r][k];
@@ -505,7 +698,7 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
       }
     }
     PT_MARK();                                         // 5: dX stores
-    dW.accumulate(sY, H, sU, H, kTileRows);
+    dW.accumulate(sY, LDA, sU, LDA, kTileRows);
     PT_MARK();                                         // 6: dW outer products
   }
   cp_async_wait_all();
@@ -526,14 +719,14 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
 // ---------------------------------------------------------------------------------------------
 template <int VEC>
 __global__ void __launch_bounds__(256) k_masked_bwd_gemm(const Ctx c) {
-  constexpr int H = 32 * VEC;
+  constexpr int H = 32 * VEC, LDA = H + kPad;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Dims d = load_dims(c);
   const int N = d.N;
   float* sW = reinterpret_cast<float*>(smem_raw);
   float* sU = sW + H * H;
-  float* sY = sU + kTileRows * H;
-  double* sRed = reinterpret_cast<double*>(sY + kTileRows * H);
+  float* sY = sU + kTileRows * LDA;
+  double* sRed = reinterpret_cast<double*>(sY + kTileRows * LDA);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int branch = blockIdx.y;
   stage_matrix_async(sW, c.wt_conv(c.L + branch), H * H);
@@ -569,8 +762,8 @@ __global__ void __launch_bounds__(256) k_masked_bwd_gemm(const Ctx c) {
           dbias[k] += u.v[k];
         }
       }
-      u.store(sU + lr * H, lane);
-      y.store(sY + lr * H, lane);
+      u.store(sU + lr * LDA, lane);
+      y.store(sY + lr * LDA, lane);
     }
     cp_async_wait_all();
     __syncthreads();
@@ -579,7 +772,7 @@ __global__ void __launch_bounds__(256) k_masked_bwd_gemm(const Ctx c) {
     for (int r = 0; r < kRPW; ++r)
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
-    tile_gemm<VEC, kRPW>(sU, H, sW, H, H, acc);
+    tile_gemm<VEC, kRPW>(sU, LDA, sW, H, H, acc);
 #pragma unroll
     for (int r = 0; r < kRPW; ++r) {
       const int i = row0 + warp * kRPW + r;
@@ -590,7 +783,7 @@ __global__ void __launch_bounds__(256) k_masked_bwd_gemm(const Ctx c) {
         o.store(dagg + (size_t)i * H, lane);
       }
     }
-    dW.accumulate(sY, H, sU, H, kTileRows);
+    dW.accumulate(sY, LDA, sU, LDA, kTileRows);
   }
   cp_async_wait_all();
   float* gp = c.gpart + c.gp_conv[c.L + branch] + (size_t)blockIdx.x * (H * H + H);
@@ -729,10 +922,10 @@ int launch_conv_forward(const Ctx& c, int layer, cudaStream_t s) {
 
 int launch_masked_forward(const Ctx& c, cudaStream_t s) {
   CAL_DISPATCH_VEC(c.H, {
-    size_t smem = convf_smem_bytes<VEC>(kStageMasked);
-    int rc = set_smem(k_conv_fwd<VEC, 2>, smem);
+    size_t smem = masked_both_smem_bytes<VEC>();
+    int rc = set_smem(k_masked_fwd_both<VEC>, smem);
     if (rc) return rc;
-    launch_k(k_conv_fwd<VEC, 2>, dim3(c.g_tile, 2), dim3(256), smem, s, c, 0);
+    launch_k(k_masked_fwd_both<VEC>, dim3(c.g_tile), dim3(256), smem, s, c);
   });
   note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
@@ -753,7 +946,7 @@ int launch_conv_backward(const Ctx& c, int layer, cudaStream_t s) {
 
 int launch_masked_bwd_gemm(const Ctx& c, cudaStream_t s) {
   CAL_DISPATCH_VEC(c.H, {
-    size_t smem = (size_t)c.H * c.H * 4 + 2 * (size_t)kTileRows * c.H * 4 + (size_t)kRowWarps * c.H * 8;
+    size_t smem = (size_t)c.H * c.H * 4 + 2 * (size_t)kTileRows * (c.H + kPad) * 4 + (size_t)kRowWarps * c.H * 8;
     int rc = set_smem(k_masked_bwd_gemm<VEC>, smem);
     if (rc) return rc;
     launch_k(k_masked_bwd_gemm<VEC>, dim3(c.g_tile, 2), dim3(256), smem, s, c);

@@ -530,6 +530,12 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ sA, int lda,
   }
 }
 
+// Row padding of the shared-memory activation tiles (floats): rows of consecutive tile rows start 4
+// banks apart.  (A column-slab mapping of this product -- warp w owns columns [16w, 16w+16) of all 24
+// rows, 7 instead of 19 shared-memory wavefronts per warp per 4-k step -- was measured on B200 and is
+// NOT faster: the loop is bound by FFMA issue with 2 warps per scheduler, not by LDS; profiles/README.md.)
+constexpr int kPad = 4;
+
 // Outer-product accumulation over a row tile: acc[a][b] += sum_r sP[r*ld + kidx(a)] * sQ[r*ld + jidx(b)].
 // 256 threads cover an [H x H] result: thread (ty = tid / 16, tx = tid % 16) owns MT x MT entries with
 // MT = H / 16, index set {half*(H/2) + t*(MT/2) + i}.

@@ -430,54 +430,45 @@ __global__ void __launch_bounds__(kPrepT) k_prep_small(const Ctx c) {
   }
   __syncthreads();
   PT_MARK();                                           // 2: node pass
-  // 1. exclusive scan of (count + 1) in chunks of T nodes (node = chunk * T + t: conflict-free)
+  // 1. exclusive scan of (count + 1) in chunks of T nodes (node = chunk * T + t: conflict-free); the
+  //    in- and out-counts travel packed in one word (both totals < 2^16, checked by the launcher)
   {
-    int carry_i = 0, carry_o = 0;
+    unsigned int carry = 0u;
     for (int n0 = 0; n0 < N; n0 += T) {
       const int n = n0 + t;
-      const int vi = n < N ? s_cin[n] + 1 : 0, vo = n < N ? s_cout[n] + 1 : 0;
-      int xi = vi, xo = vo;
+      const unsigned int v = n < N ? (unsigned int)(s_cin[n] + 1) | ((unsigned int)(s_cout[n] + 1) << 16) : 0u;
+      unsigned int x = v;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const int a = __shfl_up_sync(0xffffffffu, xi, o), b = __shfl_up_sync(0xffffffffu, xo, o);
-        if (lane >= o) {
-          xi += a;
-          xo += b;
-        }
+        const unsigned int a = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += a;
       }
-      if (lane == 31) {
-        s_wi[warp] = xi;
-        s_wo[warp] = xo;
-      }
+      if (lane == 31) s_wi[warp] = (int)x;
       __syncthreads();
       if (warp == 0) {
-        int a = s_wi[lane], b = s_wo[lane];
+        unsigned int a = (unsigned int)s_wi[lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-          const int a2 = __shfl_up_sync(0xffffffffu, a, o), b2 = __shfl_up_sync(0xffffffffu, b, o);
-          if (lane >= o) {
-            a += a2;
-            b += b2;
-          }
+          const unsigned int a2 = __shfl_up_sync(0xffffffffu, a, o);
+          if (lane >= o) a += a2;
         }
-        s_wi[lane] = a;
-        s_wo[lane] = b;
+        s_wo[lane] = (int)a;
       }
       __syncthreads();
       if (n < N) {
-        s_iptr[n] = carry_i + (warp > 0 ? s_wi[warp - 1] : 0) + xi - vi;
-        s_optr[n] = carry_o + (warp > 0 ? s_wo[warp - 1] : 0) + xo - vo;
-        s_dis[n] = 1.0f / sqrtf((float)vo);            // deg^-1/2, degree by source row incl. the loop (gcn_conv.py:66)
+        const unsigned int ex = carry + (warp > 0 ? (unsigned int)s_wo[warp - 1] : 0u) + x - v;
+        s_iptr[n] = (int)(ex & 0xffffu);
+        s_optr[n] = (int)(ex >> 16);
+        s_dis[n] = 1.0f / sqrtf((float)(v >> 16));     // deg^-1/2, degree by source row incl. the loop (gcn_conv.py:66)
         s_cin[n] = 0;     // becomes the fill cursor
         s_cout[n] = 0;
       }
-      carry_i += s_wi[31];
-      carry_o += s_wo[31];
+      carry += (unsigned int)s_wo[31];
       __syncthreads();
     }
     if (t == 0) {
-      s_iptr[N] = carry_i;
-      s_optr[N] = carry_o;
+      s_iptr[N] = (int)(carry & 0xffffu);
+      s_optr[N] = (int)(carry >> 16);
     }
   }
   __syncthreads();
@@ -567,7 +558,7 @@ __global__ void __launch_bounds__(kPrepT) k_prep_small(const Ctx c) {
 
 int launch_prep(const Ctx& c, cudaStream_t s) {
   const size_t small = prep_small_smem(c.Nm, c.Em);
-  if (small <= kPrepSmallMaxSmem && c.Nm < 65535) {
+  if (small <= kPrepSmallMaxSmem && c.EP < 65535) {
     static bool attr_set = false;
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(k_prep_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrepSmallMaxSmem);
