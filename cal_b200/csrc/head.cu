@@ -336,15 +336,26 @@ __global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_fwd
       const float* rp[kRC];
 #pragma unroll
       for (int q = 0; q < kRC; ++q) rp[q] = cl.map_shared_rank(sP, q);
-      for (int i = t; i < kChunk * F4; i += 256) {
-        const int r = i / F4, m = (i - r * F4) * 4;
-        float4 v[kRC];
+      constexpr int NI = (kChunk * F4 + 255) / 256;    // items per thread: every remote load in flight at once
+      float4 vv[NI][kRC];
 #pragma unroll
-        for (int q = 0; q < kRC; ++q) v[q] = *reinterpret_cast<const float4*>(rp[q] + (size_t)r * H + m0 + m);
-        float4 s = v[0];
+      for (int u = 0; u < NI; ++u) {
+        const int i = t + 256 * u;
+        const int r = i / F4, m = (i - r * F4) * 4;
+#pragma unroll
+        for (int q = 0; q < kRC; ++q)
+          vv[u][q] = i < kChunk * F4 ? *reinterpret_cast<const float4*>(rp[q] + (size_t)r * H + m0 + m)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < NI; ++u) {
+        const int i = t + 256 * u;
+        if (i >= kChunk * F4) break;
+        const int r = i / F4, m = (i - r * F4) * 4;
+        float4 s = vv[u][0];
 #pragma unroll
         for (int q = 1; q < kRC; ++q) {
-          s.x += v[q].x; s.y += v[q].y; s.z += v[q].z; s.w += v[q].w;
+          s.x += vv[u][q].x; s.y += vv[u][q].y; s.z += vv[u][q].z; s.w += vv[u][q].w;
         }
         const int b = r0 + r;
         const float4 bb = *reinterpret_cast<const float4*>(b1s + m);
@@ -532,17 +543,29 @@ __global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_bwd
   PT_MARK();                                           // 1: d logits, slices, constants
 
   // ---- fc2 backward on the slice: d W2[:, slice], d b2, d h2 = dl W2 ----
-  for (int task = t; task < C * HS; task += 256) {
-    const int cls = task / HS, m = task - cls * HS;
+  // four lanes share one (class, hidden column) dot product over the B rows, combined by a fixed
+  // xor-shuffle tree (deterministic); the trip count is uniform so every lane reaches the shuffles
+  for (int base = 0; base < C * HS; base += 64) {
+    const int task = base + (t >> 2), part = t & 3;
+    const bool live = task < C * HS;
+    const int cls = live ? task / HS : 0, m = live ? task - cls * HS : 0;
     float s = 0.f;
+    if (live) {
 #pragma unroll 4
-    for (int b = 0; b < B; ++b) s = fmaf(sDl[b * C + cls], fmaf(sH[b * HS + m], f_sc2[m], f_sh2[m]), s);
-    c.grads[c.po.fc2_w[h] + (size_t)cls * H + m0 + m] = s;
+      for (int b = part; b < B; b += 4) s = fmaf(sDl[b * C + cls], fmaf(sH[b * HS + m], f_sc2[m], f_sh2[m]), s);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (live && part == 0) c.grads[c.po.fc2_w[h] + (size_t)cls * H + m0 + m] = s;
   }
-  if (j == 0 && t < C) {
-    float s = 0.f;
-    for (int b = 0; b < B; ++b) s += sDl[b * C + t];
-    c.grads[c.po.fc2_b[h] + t] = s;
+  if (j == 0) {                                        // d b2: one warp per class, lanes over the rows
+    const int warp = t >> 5, lane = t & 31;
+    for (int cls = warp; cls < C; cls += 8) {
+      float s = 0.f;
+      for (int b = lane; b < B; b += 32) s += sDl[b * C + cls];
+      s = warp_sum(s);
+      if (lane == 0) c.grads[c.po.fc2_b[h] + cls] = s;
+    }
   }
   for (int i = t; i < Bp * HS; i += 256) {
     const int b = i / HS, m = i - b * HS;
@@ -701,13 +724,21 @@ __global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_bwd
 #pragma unroll
         for (int q = 0; q < kRC; ++q) rp[q] = cl.map_shared_rank(sX, q);
         constexpr int F4 = H / 4;
-#pragma unroll 4
-        for (int i = t; i < kChunk * F4; i += 256) {
+        constexpr int NI = kChunk * F4 / 256;          // float4 per thread: all remote loads in flight at once
+        float4 v[NI];
+#pragma unroll
+        for (int u = 0; u < NI; ++u) {
+          const int i = t + 256 * u;
           const int r = i / F4, m = (i - r * F4) * 4;
           const int q = m / HS;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (r0 + r < B) v = *reinterpret_cast<const float4*>(rp[q] + (size_t)(r0 + r) * HS + (m - q * HS));
-          *reinterpret_cast<float4*>(sUall + (size_t)r * H + m) = v;
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r0 + r < B) v[u] = *reinterpret_cast<const float4*>(rp[q] + (size_t)(r0 + r) * HS + (m - q * HS));
+        }
+#pragma unroll
+        for (int u = 0; u < NI; ++u) {
+          const int i = t + 256 * u;
+          const int r = i / F4, m = (i - r * F4) * 4;
+          *reinterpret_cast<float4*>(sUall + (size_t)r * H + m) = v[u];
         }
       }
       __syncthreads();

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) k_grad_reduce(const Ctx c, const RedTable
       if (live) {
         const float* p = c.gpart + e.src + el;
         int g = sub;
-#pragma unroll 2
+#pragma unroll 4                                          // 16 independent loads in flight per thread (latency-bound otherwise)
         for (; g + 3 * sp < np; g += 4 * sp) {
           s0 += p[(size_t)g * e.stride];
           s1 += p[(size_t)(g + sp) * e.stride];
