@@ -453,7 +453,20 @@ def run_gpu(a, rank, local_rank, world):
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_e = float(tt.item())
+        # what the reference's loader does per step on the host: collate (Batch.from_data_list) + packing
+        import time as _time
+        from cal_b200.data import Batch as _Batch
+        hc_buf = torch.zeros(tr2.layout.nbytes, dtype=torch.uint8).pin_memory()
+        t0 = _time.perf_counter()
+        n_hc = 0
+        while n_hc < 8 or _time.perf_counter() - t0 < 0.5:
+            ids = rng.permutation(len(ds))[:bs]
+            tr2.pack(_Batch.from_data_list([ds[i] for i in ids]), out=hc_buf)
+            n_hc += 1
+        host_collate_ms = (_time.perf_counter() - t0) / n_hc * 1e3
         e2e["device_resident_epoch"] = {
+            "host_collate_ms_per_batch": host_collate_ms,
+            "host_collate_bound_graphs_per_s": bs / (host_collate_ms * 1e-3),
             "value": a.steps * graphs_per_step * world / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e / a.steps,
             "h2d_bytes_per_step": int((4 * per_epoch * bs + (4 * per_epoch * bs if tr2.with_random else 0)) / per_epoch),
             "d2h_bytes_per_epoch": 32, "graphs_in_store": len(ds), "steps_per_epoch": per_epoch,

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("CAL_B200_LIB") or os.path.join(HERE, "libcal_b200.so"
 
 CAL_MAX_LAYERS = 8
 CAL_MAX_BN = 1 + CAL_MAX_LAYERS + 2 + 6
-CAL_MODEL_GCN, CAL_MODEL_GAT = 0, 1
+CAL_MODEL_GCN, CAL_MODEL_GAT, CAL_MODEL_GIN = 0, 1, 2
 CAL_F_TRAIN, CAL_F_LOSS = 1, 2
 CAL_ST_BAD_NODE, CAL_ST_BAD_BATCH, CAL_ST_CAPACITY = 1, 2, 4
 
@@ -72,6 +72,7 @@ class ParamOffsets(C.Structure):
                 ("fc1_w", C.c_int64 * 3), ("fc1_b", C.c_int64 * 3),
                 ("fc2_bn_w", C.c_int64 * 3), ("fc2_bn_b", C.c_int64 * 3),
                 ("fc2_w", C.c_int64 * 3), ("fc2_b", C.c_int64 * 3),
+                ("gin_w2", C.c_int64 * CAL_MAX_LAYERS), ("gin_b2", C.c_int64 * CAL_MAX_LAYERS),
                 ("total", C.c_int64)]
 
 

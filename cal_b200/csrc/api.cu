@@ -170,7 +170,10 @@ int build_ctx(const cal_model_desc* m, const cal_caps* caps, const cal_param_off
     c.gp_fc1[h] = lay.gp_fc1[h];
     c.gp_fc2[h] = lay.gp_fc2[h];
   }
-  for (int l = 0; l < CAL_MAX_LAYERS; ++l) c.gp_gat[l] = lay.gp_gat[l];
+  for (int l = 0; l < CAL_MAX_LAYERS; ++l) {
+    c.gp_gat[l] = lay.gp_gat[l];
+    c.gp_gin2[l] = lay.gp_gin2[l];
+  }
   return CAL_OK;
 }
 
@@ -185,6 +188,7 @@ int check_offsets(const cal_model_desc* m, const cal_param_offsets* po) {
   for (int l = 0; l < m->layers; ++l) {
     if (po->bns_conv_w[l] < 0 || po->bns_conv_b[l] < 0 || po->convs_w[l] < 0 || po->convs_b[l] < 0) return CAL_EINVAL;
     if (m->model == CAL_MODEL_GAT && po->convs_att[l] < 0) return CAL_EINVAL;
+    if (m->model == CAL_MODEL_GIN && (po->gin_w2[l] < 0 || po->gin_b2[l] < 0 || po->gin_w2[l] % 4 != 0)) return CAL_EINVAL;
     if (po->convs_w[l] % 4 != 0) return CAL_EALIGN;       // staged with 16-byte cp.async
   }
   if (po->context_w % 4 != 0 || po->objects_w % 4 != 0) return CAL_EALIGN;
@@ -316,7 +320,9 @@ int cal_causal_forward(const cal_model_desc* m, const cal_caps* caps, const cal_
   for (int st = lo; st <= hi; ++st) {
     if (st == 0) rc = launch_param_prep(c, s);
     else if (st == 1) rc = launch_feat_forward(c, s);
-    else if (st < 2 + L) rc = c.model == CAL_MODEL_GAT ? launch_gat_forward(c, st - 2, s) : launch_conv_forward(c, st - 2, s);
+    else if (st < 2 + L)
+      rc = c.model == CAL_MODEL_GAT ? launch_gat_forward(c, st - 2, s)
+                                    : (c.model == CAL_MODEL_GIN ? launch_gin_forward(c, st - 2, s) : launch_conv_forward(c, st - 2, s));
     else if (st == 2 + L) rc = launch_edge_att(c, s);
     else if (st == 3 + L) rc = launch_masked_forward(c, s);
     else if (st == 4 + L) rc = launch_heads_forward(c, c.with_loss, s);
@@ -359,7 +365,8 @@ int cal_causal_backward(const cal_model_desc* m, const cal_caps* caps, const cal
     else if (st == 4) rc = launch_att_backward(c, s);
     else if (st < 5 + L) {
       const int l = L - 1 - (st - 5);
-      rc = c.model == CAL_MODEL_GAT ? launch_gat_backward(c, l, s) : launch_conv_backward(c, l, s);
+      rc = c.model == CAL_MODEL_GAT ? launch_gat_backward(c, l, s)
+                                    : (c.model == CAL_MODEL_GIN ? launch_gin_backward(c, l, s) : launch_conv_backward(c, l, s));
     } else if (st == 5 + L) rc = launch_feat_backward(c, s);
     else if (st == 6 + L) rc = launch_grad_reduce(c, s);
     if (rc != 0) return rc;

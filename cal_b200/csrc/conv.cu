@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) k_feat_fwd(const Ctx c) {
       }
     }
   }
-  if (c.train) {
+  if (c.train && c.model != CAL_MODEL_GIN) {          // CausalGIN: no BatchNorm consumes x_1 (model.py:237-238)
     double accs[2][VEC];
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
@@ -143,6 +143,9 @@ __global__ void __launch_bounds__(256) k_feat_fwd(const Ctx c) {
 //           (model.py:97-111) and the statistics of bnc / bno on att * x
 //   MODE 2: context_convs / objects_convs on the soft-masked features with the attention-weighted
 //           norm (model.py:112-113, gcn_conv.py:59-70 with edge_weight); blockIdx.y = branch
+//   MODE 3: first half of a CausalGIN layer (model.py:187-193, PyG GINConv): h = (x_i + sum_j x_j) W1^T + b1,
+//           i.e. the same gather with unit weights and no BatchNorm on load, no ReLU; the epilogue
+//           accumulates the statistics of the layer's inner BatchNorm (BN id 1 + layer)
 // smem: sW [H][H] | sA [R][H] | sRed f64 [8][H] | sPtr [R+4] | sSrc [EC] | sNrm [EC]
 // ---------------------------------------------------------------------------------------------
 template <int VEC>
@@ -178,11 +181,12 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int branch = MODE == 2 ? blockIdx.y : 0;
   const int conv = MODE == 2 ? c.L + branch : layer;
-  const int bn_in = MODE == 2 ? c.L + 1 + branch : 1 + layer;
-  const float* W = c.params + (MODE == 2 ? (branch ? c.po.objects_w : c.po.context_w) : c.po.convs_w[layer]);
+  const int bn_in = MODE == 2 ? c.L + 1 + branch : (MODE == 3 ? kBnIdentity : 1 + layer);
+  const float* W = MODE == 3 ? c.wt_conv(layer)      // torch Linear stores [out, in]: the transposed copy is [in, out]
+                             : c.params + (MODE == 2 ? (branch ? c.po.objects_w : c.po.context_w) : c.po.convs_w[layer]);
   const float* bias = c.params + (MODE == 2 ? (branch ? c.po.objects_b : c.po.context_b) : c.po.convs_b[layer]);
   const float* xin = MODE == 2 ? c.Xl(c.L) : c.Xl(layer);
-  float* xout = MODE == 2 ? c.Z + (size_t)branch * c.Nm * H : c.Xl(layer + 1);
+  float* xout = MODE == 2 ? c.Z + (size_t)branch * c.Nm * H : (MODE == 3 ? c.gin_h(layer) : c.Xl(layer + 1));
   float* aggout = c.agg + (size_t)branch * c.Nm * H;
   (void)conv;
 
@@ -224,7 +228,7 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
             sXn[e] = c.edge_wn[(size_t)(pb + e) * 2 + branch];         // dis_w[source] * edge_att
             sXa[e] = c.edge_na[(size_t)(pb + e) * 2 + branch];         // node_att[source]
           } else {
-            sXn[e] = c.in_norm[pb + e];
+            sXn[e] = MODE == 3 ? 1.f : c.in_norm[pb + e];
           }
         }
         __syncthreads();
@@ -267,7 +271,7 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
             const int src = c.in_src[p];
             RowVec<VEC> v;
             v.load_coherent(xin + (size_t)src * H, lane);
-            float w = MODE == 2 ? c.watt[(size_t)p * 2 + branch] : c.in_norm[p];
+            float w = MODE == 2 ? c.watt[(size_t)p * 2 + branch] : (MODE == 3 ? 1.f : c.in_norm[p]);
             float am = 1.f;
             if (MODE == 2) {
               am = c.natt[(size_t)src * 2 + branch];
@@ -314,7 +318,7 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
       if (i < N) {                                      // warp-uniform
         RowVec<VEC> o;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) o.v[k] = fmaxf(acc[r][k] + bv[k], 0.f);
+        for (int k = 0; k < VEC; ++k) o.v[k] = MODE == 3 ? acc[r][k] + bv[k] : fmaxf(acc[r][k] + bv[k], 0.f);
         o.store(xout + (size_t)i * H, lane);
         if (MODE != 2) epi.row(c, i, o.v, lane);
       }
@@ -322,7 +326,7 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
   }
   cp_async_wait_all();
   PT_MARK();                                           // 6: epilogue stores
-  if (MODE != 2) epi.finish(c, layer, sRed, sTot, N);
+  if (MODE != 2) epi.finish(c, MODE == 3 ? layer - 1 : layer, sRed, sTot, N);    // MODE 3: BN id 2 + (layer - 1) = 1 + layer
   PT_MARK();                                           // 7: totals + grid sum + finalize
   PT_DUMP(c, 16);
 }
@@ -519,7 +523,7 @@ constexpr size_t convb_smem_bytes() {
          (size_t)kStageBwd * (2 * H * 4 + 8);
 }
 
-template <int VEC>
+template <int VEC, bool GIN>
 __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) {
   constexpr int H = 32 * VEC, LDA = H + kPad;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -537,14 +541,17 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
   int* sXs = reinterpret_cast<int*>(sXn + kStageBwd);             // [kStageBwd] target node of the entry
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  stage_matrix_async(sW, c.wt_conv(layer), H * H);
+  // GCN: D = U W^T needs the transposed copy; GIN: h = agg W1^T, so D = U W1 with W1 as stored ([out, in])
+  stage_matrix_async(sW, GIN ? c.params + c.po.convs_w[layer] : c.wt_conv(layer), H * H);
   pdl_sync();                                        // everything below may read the predecessor's output
 
-  const int bn_in = 1 + layer;
-  const int bn_up = layer == c.L - 1 ? kBnIdentity : 2 + layer;
+  // GIN (first half of the layer, model.py:187-193): upstream = the layer's inner BatchNorm applied to h;
+  // the rows of `Dup` already carry the ReLU mask (k_gin_b_bwd); no BatchNorm below, unit edge weights
+  const int bn_in = GIN ? kBnIdentity : 1 + layer;
+  const int bn_up = GIN ? 1 + layer : (layer == c.L - 1 ? kBnIdentity : 2 + layer);
   const float* xin = c.Xl(layer);
-  const float* xup = c.Xl(layer + 1);
-  const float* Dup = c.D + (size_t)((layer + 1) & 1) * c.Nm * H;
+  const float* xup = GIN ? c.gin_h(layer) : c.Xl(layer + 1);
+  const float* Dup = GIN ? c.gin_dr() : c.D + (size_t)((layer + 1) & 1) * c.Nm * H;
   float* Dout = c.D + (size_t)(layer & 1) * c.Nm * H;
   BnLane<VEC> bi, bu;
   bi.load_bwd(c, bn_in, lane);
@@ -581,7 +588,7 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
       if (!direct) {
         for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
           sXs[e] = c.out_dst[qb + e];
-          sXn[e] = c.out_norm[qb + e];
+          sXn[e] = GIN ? 1.f : c.out_norm[qb + e];
         }
         __syncthreads();
         for (int e = warp; e < cnt; e += kRowWarps)
@@ -615,7 +622,7 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
             const float w = sXn[e];
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {
-              const float g = xv.v[k] > 0.f ? bu.dx(k, gv.v[k], xv.v[k]) : 0.f;
+              const float g = (GIN || xv.v[k] > 0.f) ? bu.dx(k, gv.v[k], xv.v[k]) : 0.f;
               u.v[k] = fmaf(w, g, u.v[k]);
               if (e == e1 - 1) dbias[k] += g;          // the appended self loop is the row's last out-entry
             }
@@ -634,13 +641,13 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
           xi.load_coherent(xin + (size_t)j * H, lane);
           for (int q = sPtr[lr]; q < sPtr[lr + 1]; ++q) {
             const int dd = c.out_dst[q];
-            const float w = c.out_norm[q];
+            const float w = GIN ? 1.f : c.out_norm[q];
             RowVec<VEC> gv, xv;
             gv.load_coherent(Dup + (size_t)dd * H, lane);
             xv.load_coherent(xup + (size_t)dd * H, lane);
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {
-              const float g = xv.v[k] > 0.f ? bu.dx(k, gv.v[k], xv.v[k]) : 0.f;
+              const float g = (GIN || xv.v[k] > 0.f) ? bu.dx(k, gv.v[k], xv.v[k]) : 0.f;
               u.v[k] = fmaf(w, g, u.v[k]);
               if (q == sPtr[lr + 1] - 1) dbias[k] += g;
             }
@@ -691,14 +698,17 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
           o.v[k] = acc[r][k];
-          st[0][k] += (double)acc[r][k];
-          st[1][k] += (double)acc[r][k] * (double)bi.xhat(k, xi.v[k]);
+          if (!GIN) {
+            st[0][k] += (double)acc[r][k];
+            st[1][k] += (double)acc[r][k] * (double)bi.xhat(k, xi.v[k]);
+          }
         }
         o.store(Dout + (size_t)j * H, lane);
       }
     }
     PT_MARK();                                         // 5: dX stores
-    dW.accumulate(sY, LDA, sU, LDA, kTileRows);
+    if (GIN) dW.accumulate(sU, LDA, sY, LDA, kTileRows);      // torch Linear: d W1 [out, in]
+    else dW.accumulate(sY, LDA, sU, LDA, kTileRows);
     PT_MARK();                                         // 6: dW outer products
   }
   cp_async_wait_all();
@@ -706,8 +716,10 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
   if (blockIdx.x < ntiles) dW.store(gp, H);
   block_colsum_store<VEC>(dbias, reinterpret_cast<float*>(sRed), blockIdx.x < ntiles ? gp + H * H : nullptr, H);
   PT_MARK();                                           // 7: dW / db partial stores
-  block_totals<VEC, 2>(st, sRed, sTot, H, 0, H, 0);
-  if (grid_sum(c, 0, sTot, 2 * H, gridDim.x, blockIdx.x)) bn_bwd_finalize_tot(c, bn_in, sTot, sTot + H, N);
+  if (!GIN) {
+    block_totals<VEC, 2>(st, sRed, sTot, H, 0, H, 0);
+    if (grid_sum(c, 0, sTot, 2 * H, gridDim.x, blockIdx.x)) bn_bwd_finalize_tot(c, bn_in, sTot, sTot + H, N);
+  }
   PT_MARK();                                           // 8: totals + grid sum + finalize
   PT_DUMP(c, 32);
 }
@@ -792,6 +804,168 @@ __global__ void __launch_bounds__(256) k_masked_bwd_gemm(const Ctx c) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// CausalGIN layer, second half (model.py:187-193: ... BatchNorm1d -> ReLU -> Linear -> ReLU), dense:
+//   forward   x_{l+2} = relu(relu(bn(h)) W2^T + b2)           (h = first-half output, k_conv_fwd<MODE 3>)
+//   backward  u = relu'(x_{l+2}) * D_up;  d W2 += u^T relu(bn(h));  d b2 += u;
+//             d r = (u W2) * [bn(h) > 0]  -> gin_dr, + the inner BatchNorm's backward sums.
+// No BatchNorm follows a GIN layer, so only the LAST layer's forward has a statistics epilogue
+// (node / edge attention projections and bnc / bno, as in k_conv_fwd<MODE 1>).
+// smem: sW [H][H] | sA [R][LDA] (| sY [R][LDA]) | sRed f64 [8][H]
+// ---------------------------------------------------------------------------------------------
+template <int VEC, bool LASTL>
+__global__ void __launch_bounds__(256) k_gin_b_fwd(const Ctx c, const int layer) {
+  constexpr int H = 32 * VEC, LDA = H + kPad;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double sTot[LASTL ? 4 * H : 1];
+  const Dims d = load_dims(c);
+  const int N = d.N;
+  float* sW = reinterpret_cast<float*>(smem_raw);
+  float* sA = sW + H * H;
+  double* sRed = reinterpret_cast<double*>(sA + kTileRows * LDA);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  stage_matrix_async(sW, c.wt_gin2(layer), H * H);
+  pdl_sync();                                        // everything below may read the predecessor's output
+  BnLane<VEC> bn;
+  bn.load_fwd(c, 1 + layer, lane);
+  float bv[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) bv[i] = c.params[c.po.gin_b2[layer] + lane * VEC + i];
+  LayerEpilogue<VEC, LASTL> epi;
+  if (LASTL) epi.init(c, lane);
+  const float* hin = c.gin_h(layer);
+  float* xout = c.Xl(layer + 1);
+  const int ntiles = ceil_div(N, kTileRows);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int row0 = tile * kTileRows;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kRPW; ++r) {
+      const int lr = warp * kRPW + r, i = row0 + lr;
+      RowVec<VEC> a;
+      a.zero();
+      if (i < N) {
+        a.load_coherent(hin + (size_t)i * H, lane);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) a.v[k] = fmaxf(fmaf(a.v[k], bn.sc[k], bn.sh[k]), 0.f);
+      }
+      a.store(sA + lr * LDA, lane);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    float acc[kRPW][VEC];
+#pragma unroll
+    for (int r = 0; r < kRPW; ++r)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
+    tile_gemm<VEC, kRPW>(sA, LDA, sW, H, H, acc);
+#pragma unroll
+    for (int r = 0; r < kRPW; ++r) {
+      const int i = row0 + warp * kRPW + r;
+      if (i < N) {                                      // warp-uniform
+        RowVec<VEC> o;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) o.v[k] = fmaxf(acc[r][k] + bv[k], 0.f);
+        o.store(xout + (size_t)i * H, lane);
+        if (LASTL) epi.row(c, i, o.v, lane);
+      }
+    }
+  }
+  cp_async_wait_all();
+  if (LASTL) epi.finish(c, layer, sRed, sTot, N);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) k_gin_b_bwd(const Ctx c, const int layer) {
+  constexpr int H = 32 * VEC, LDA = H + kPad;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double sTot[2 * H];
+  const Dims d = load_dims(c);
+  const int N = d.N;
+  float* sW = reinterpret_cast<float*>(smem_raw);
+  float* sU = sW + H * H;
+  float* sY = sU + kTileRows * LDA;
+  double* sRed = reinterpret_cast<double*>(sY + kTileRows * LDA);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  stage_matrix_async(sW, c.params + c.po.gin_w2[layer], H * H);     // [out, in] as stored: d r = u W2
+  pdl_sync();                                        // everything below may read the predecessor's output
+  const int bn_id = 1 + layer;
+  BnLane<VEC> bn;
+  bn.load_bwd(c, bn_id, lane);                       // scale / shift / mean / rstd of the forward; c1 / c2 are produced here
+  const float* hin = c.gin_h(layer);
+  const float* xup = c.Xl(layer + 1);
+  const float* Dup = c.D + (size_t)((layer + 1) & 1) * c.Nm * H;
+  float* DR = c.gin_dr();
+  OuterAcc<H> dW;
+  dW.zero();
+  float dbias[VEC];
+  double st[2][VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    dbias[k] = 0.f;
+    st[0][k] = st[1][k] = 0.0;
+  }
+  const int ntiles = ceil_div(N, kTileRows);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int row0 = tile * kTileRows;
+    __syncthreads();
+    RowVec<VEC> hr[kRPW];                              // h rows of this warp: needed again after the GEMM
+#pragma unroll
+    for (int r = 0; r < kRPW; ++r) {
+      const int lr = warp * kRPW + r, i = row0 + lr;
+      RowVec<VEC> u, y;
+      u.zero();
+      y.zero();
+      hr[r].zero();
+      if (i < N) {
+        RowVec<VEC> xo, g;
+        xo.load_coherent(xup + (size_t)i * H, lane);
+        g.load_coherent(Dup + (size_t)i * H, lane);
+        hr[r].load_coherent(hin + (size_t)i * H, lane);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          u.v[k] = xo.v[k] > 0.f ? g.v[k] : 0.f;
+          y.v[k] = fmaxf(fmaf(hr[r].v[k], bn.sc[k], bn.sh[k]), 0.f);
+          dbias[k] += u.v[k];
+        }
+      }
+      u.store(sU + lr * LDA, lane);
+      y.store(sY + lr * LDA, lane);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    float acc[kRPW][VEC];
+#pragma unroll
+    for (int r = 0; r < kRPW; ++r)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
+    tile_gemm<VEC, kRPW>(sU, LDA, sW, H, H, acc);
+#pragma unroll
+    for (int r = 0; r < kRPW; ++r) {
+      const int i = row0 + warp * kRPW + r;
+      if (i < N) {
+        RowVec<VEC> o;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          const float yb = fmaf(hr[r].v[k], bn.sc[k], bn.sh[k]);
+          const float m = yb > 0.f ? acc[r][k] : 0.f;
+          o.v[k] = m;
+          st[0][k] += (double)m;
+          st[1][k] += (double)m * (double)bn.xhat(k, hr[r].v[k]);
+        }
+        o.store(DR + (size_t)i * H, lane);
+      }
+    }
+    dW.accumulate(sU, LDA, sY, LDA, kTileRows);        // torch Linear: d W2 [out, in]
+  }
+  cp_async_wait_all();
+  float* gp = c.gpart + c.gp_gin2[layer] + (size_t)blockIdx.x * (H * H + H);
+  if (blockIdx.x < ntiles) dW.store(gp, H);
+  block_colsum_store<VEC>(dbias, reinterpret_cast<float*>(sRed), blockIdx.x < ntiles ? gp + H * H : nullptr, H);
+  block_totals<VEC, 2>(st, sRed, sTot, H, 0, H, 0);
+  if (grid_sum(c, 0, sTot, 2 * H, gridDim.x, blockIdx.x)) bn_bwd_finalize_tot(c, bn_id, sTot, sTot + H, N);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Input transform backward: with g = relu'(x_1) * bn_1'(D_0):
 //   M = xhat_0^T g  [F, H]  and  cs = colsum(g); the reduce kernel turns them into
 //   d W_feat = gamma_0 * M + beta_0 (x) cs,  d gamma_0[f] = sum_j W[f][j] M[f][j],
@@ -815,7 +989,7 @@ __global__ void __launch_bounds__(256) k_feat_bwd(const Ctx c) {
   const float* mean0 = c.bnf(0, BN_MEAN);
   const float* rstd0 = c.bnf(0, BN_RSTD);
   BnLane<VEC> b1;
-  b1.load_bwd(c, 1, lane);
+  b1.load_bwd(c, c.model == CAL_MODEL_GIN ? kBnIdentity : 1, lane);     // CausalGIN has no BatchNorm on x_1 (model.py:237-238)
   float M[FW][VEC], cs[VEC];
 #pragma unroll
   for (int a = 0; a < FW; ++a)
@@ -935,11 +1109,50 @@ int launch_masked_forward(const Ctx& c, cudaStream_t s) {
 int launch_conv_backward(const Ctx& c, int layer, cudaStream_t s) {
   CAL_DISPATCH_VEC(c.H, {
     size_t smem = convb_smem_bytes<VEC>();
-    int rc = set_smem(k_conv_bwd<VEC>, smem);
+    int rc = set_smem(k_conv_bwd<VEC, false>, smem);
     if (rc) return rc;
-    launch_k(k_conv_bwd<VEC>, dim3(c.g_tile), dim3(256), smem, s, c, layer);
+    launch_k(k_conv_bwd<VEC, false>, dim3(c.g_tile), dim3(256), smem, s, c, layer);
   });
   note_launches(1);
+  CAL_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_gin_forward(const Ctx& c, int layer, cudaStream_t s) {
+  const bool last = layer == c.L - 1;
+  CAL_DISPATCH_VEC(c.H, {
+    size_t smem = convf_smem_bytes<VEC>(kStageFwd);
+    int rc = set_smem(k_conv_fwd<VEC, 3>, smem);
+    if (rc) return rc;
+    launch_k(k_conv_fwd<VEC, 3>, dim3(c.g_tile), dim3(256), smem, s, c, layer);
+    smem = (size_t)c.H * c.H * 4 + (size_t)kTileRows * (c.H + kPad) * 4 + (size_t)kRowWarps * c.H * 8;
+    if (last) {
+      rc = set_smem(k_gin_b_fwd<VEC, true>, smem);
+      if (rc) return rc;
+      launch_k(k_gin_b_fwd<VEC, true>, dim3(c.g_tile), dim3(256), smem, s, c, layer);
+    } else {
+      rc = set_smem(k_gin_b_fwd<VEC, false>, smem);
+      if (rc) return rc;
+      launch_k(k_gin_b_fwd<VEC, false>, dim3(c.g_tile), dim3(256), smem, s, c, layer);
+    }
+  });
+  note_launches(2);
+  CAL_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_gin_backward(const Ctx& c, int layer, cudaStream_t s) {
+  CAL_DISPATCH_VEC(c.H, {
+    size_t smem = (size_t)c.H * c.H * 4 + 2 * (size_t)kTileRows * (c.H + kPad) * 4 + (size_t)kRowWarps * c.H * 8;
+    int rc = set_smem(k_gin_b_bwd<VEC>, smem);
+    if (rc) return rc;
+    launch_k(k_gin_b_bwd<VEC>, dim3(c.g_tile), dim3(256), smem, s, c, layer);
+    smem = convb_smem_bytes<VEC>();
+    rc = set_smem(k_conv_bwd<VEC, true>, smem);
+    if (rc) return rc;
+    launch_k(k_conv_bwd<VEC, true>, dim3(c.g_tile), dim3(256), smem, s, c, layer);
+  });
+  note_launches(2);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }

@@ -46,6 +46,7 @@ struct Layout {
   size_t gp_fc1[3];                     // [T1][H*2H + H]
   size_t gp_fc2[3];                     // [G2][C*H + C]
   size_t gp_gat[CAL_MAX_LAYERS];        // [G][2H] attention-vector partials (GAT)
+  size_t gp_gin2[CAL_MAX_LAYERS];       // [G][H*H + H] second Linear of a GIN layer
 };
 
 // Everything a kernel needs, passed by value.
@@ -87,12 +88,17 @@ struct Ctx {
   size_t gs_stride;         // doubles per site
   float *WT, *gat, *dlogit, *dh, *du, *dpool, *dagg, *dym, *dnrm, *dt, *dp, *D, *gpart;
   size_t gp_conv[CAL_MAX_LAYERS + 2], gp_att, gp_feat, gp_fc1[3], gp_fc2[3], gp_gat[CAL_MAX_LAYERS];
+  size_t gp_gin2[CAL_MAX_LAYERS];
   const float* grad_logp;   // external dL/dlogp (nullptr = fused loss)
 
   __host__ __device__ float* bnf(int id, int field) const { return bn + ((size_t)id * BN_FIELDS + field) * kmax; }
   __host__ __device__ float* Xl(int l) const { return X + (size_t)l * Nm * H; }     // l = 0..L  (x_{l+1})
   __host__ __device__ float* wt_conv(int l) const { return WT + (size_t)l * H * H; }   // l = 0..L+1
   __host__ __device__ float* wt_fc1(int h) const { return WT + (size_t)(L + 2) * H * H + (size_t)h * 2 * H * H; }
+  // CausalGIN: transposed nn.3 weights; h (nn.0 output) of every layer; masked gradient w.r.t. relu(bn(h))
+  __host__ __device__ float* wt_gin2(int l) const { return WT + (size_t)(L + 2) * H * H + (size_t)3 * 2 * H * H + (size_t)l * H * H; }
+  __host__ __device__ float* gin_h(int l) const { return gat + (size_t)l * Nm * H; }
+  __host__ __device__ float* gin_dr() const { return gat + (size_t)L * Nm * H; }
 };
 
 // counter slots
@@ -127,6 +133,8 @@ int launch_feat_backward(const Ctx& c, cudaStream_t s);
 int launch_grad_reduce(const Ctx& c, cudaStream_t s);
 int launch_gat_forward(const Ctx& c, int layer, cudaStream_t s);
 int launch_gat_backward(const Ctx& c, int layer, cudaStream_t s);
+int launch_gin_forward(const Ctx& c, int layer, cudaStream_t s);
+int launch_gin_backward(const Ctx& c, int layer, cudaStream_t s);
 
 // ---- device helpers shared by the kernels ----
 

@@ -7,7 +7,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int validate_model(const cal_model_desc* m) {
   if (m == nullptr) return CAL_ENULL;
-  if (m->model != CAL_MODEL_GCN && m->model != CAL_MODEL_GAT) return CAL_EINVAL;
+  if (m->model != CAL_MODEL_GCN && m->model != CAL_MODEL_GAT && m->model != CAL_MODEL_GIN) return CAL_EINVAL;
   if (m->hidden != 32 && m->hidden != 64 && m->hidden != 128) return CAL_EUNSUPPORTED;
   if (m->num_features < 1 || m->num_features > 512) return CAL_EUNSUPPORTED;
   if (m->num_classes < 2 || m->num_classes > 32) return CAL_EUNSUPPORTED;
@@ -75,7 +75,8 @@ int compute_layout(const cal_model_desc* m, const cal_caps* caps, Layout* lay) {
   lay->gs_n = 4 * lay->kmax;
   lay->gs_stride = (size_t)(kMaxStatBlocks + kMaxStatBlocks / kGsGroup + 1) * lay->gs_n;
   sz[CAL_WS_STATP] = (lay->statp_legacy + kGsSites * lay->gs_stride) * 8;
-  sz[CAL_WS_WT] = ((L + 2) * H * H + 3 * 2 * H * H) * 4;
+  sz[CAL_WS_WT] = ((L + 2) * H * H + 3 * 2 * H * H + (m->model == CAL_MODEL_GIN ? L * H * H : 0)) * 4;
+  if (m->model == CAL_MODEL_GIN) sz[CAL_WS_GAT] = (L + 1) * Nm * H * 4;
   if (m->model == CAL_MODEL_GAT)
     sz[CAL_WS_GAT] = gat_workspace_floats((int)Nm, (int)EP, (int)H, (int)L, m->heads) * 4;
   sz[CAL_WS_DLOGIT] = 3 * Bm * C * 4;
@@ -112,6 +113,10 @@ int compute_layout(const cal_model_desc* m, const cal_caps* caps, Layout* lay) {
   for (size_t l = 0; l < L; ++l) {
     lay->gp_gat[l] = gp;
     if (m->model == CAL_MODEL_GAT) gp += G * 2 * H;
+  }
+  for (size_t l = 0; l < L; ++l) {
+    lay->gp_gin2[l] = gp;
+    if (m->model == CAL_MODEL_GIN) gp += G * (H * H + H);
   }
   sz[CAL_WS_GPART] = gp * 4;
 

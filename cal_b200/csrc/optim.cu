@@ -209,6 +209,13 @@ int launch_grad_reduce(const Ctx& c, cudaStream_t s) {
       add(c.po.convs_w[l], c.gp_conv[l], H * H, cs, PARTS_NODE_TILES, c.g_tile);
       add(c.po.convs_b[l], c.gp_conv[l] + H * H, H, cs, PARTS_NODE_TILES, c.g_tile);
     }
+  else if (c.model == CAL_MODEL_GIN)
+    for (int l = 0; l < c.L; ++l) {
+      add(c.po.convs_w[l], c.gp_conv[l], H * H, cs, PARTS_NODE_TILES, c.g_tile);
+      add(c.po.convs_b[l], c.gp_conv[l] + H * H, H, cs, PARTS_NODE_TILES, c.g_tile);
+      add(c.po.gin_w2[l], c.gp_gin2[l], H * H, cs, PARTS_NODE_TILES, c.g_tile);
+      add(c.po.gin_b2[l], c.gp_gin2[l] + H * H, H, cs, PARTS_NODE_TILES, c.g_tile);
+    }
   else
     for (int l = 0; l < c.L; ++l) {
       add(c.po.convs_w[l], c.gp_conv[l], H * H, cs, PARTS_NODE_TILES, c.g_tile);

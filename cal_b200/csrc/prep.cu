@@ -607,7 +607,7 @@ __global__ void k_param_prep(const Ctx c, const int n_tiles) {
       src = c.params + off;
       dst = c.wt_conv(mat);
       rows = H; cols = H;
-    } else {
+    } else if (m < n_conv * hb * hb + 2 * hb * hb + hb * ((c.cat ? 2 * H : H) / 32)) {
       m -= n_conv * hb * hb;
       int h = 0;
       for (; h < 3; ++h) {
@@ -619,6 +619,13 @@ __global__ void k_param_prep(const Ctx c, const int n_tiles) {
       src = c.params + c.po.fc1_w[h];
       dst = c.wt_fc1(h);
       rows = H; cols = (h == 2 && c.cat) ? 2 * H : H;
+    } else {                                           // CausalGIN: the second Linear of every layer
+      m -= n_conv * hb * hb + 2 * hb * hb + hb * ((c.cat ? 2 * H : H) / 32);
+      const int l = m / (hb * hb);
+      t = m - l * hb * hb;
+      src = c.params + c.po.gin_w2[l];
+      dst = c.wt_gin2(l);
+      rows = H; cols = H;
     }
     const int ct = cols / 32;
     const int r0 = (t / ct) * 32, c0 = (t % ct) * 32;
@@ -648,7 +655,8 @@ __global__ void k_param_prep(const Ctx c, const int n_tiles) {
 
 int launch_param_prep(const Ctx& c, cudaStream_t s) {
   const int hb = c.H / 32;
-  const int n_tiles = (c.L + 2) * hb * hb + 2 * hb * hb + hb * ((c.cat ? 2 * c.H : c.H) / 32);
+  const int n_tiles = (c.L + 2) * hb * hb + 2 * hb * hb + hb * ((c.cat ? 2 * c.H : c.H) / 32) +
+                      (c.model == CAL_MODEL_GIN ? c.L * hb * hb : 0);
   launch_k(k_param_prep, dim3(n_tiles + 1), dim3(32, 8), 0, s, c, n_tiles);
   note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();

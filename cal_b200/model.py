@@ -25,7 +25,7 @@ from torch.nn import BatchNorm1d, Linear, Parameter
 from . import _lib
 from ._lib import WS
 
-__all__ = ["CausalGCN", "CausalGAT", "GCNConv", "GATConv", "Engine"]
+__all__ = ["CausalGCN", "CausalGAT", "CausalGIN", "GCNConv", "GATConv", "GINConv", "Engine"]
 
 
 def _glorot(t):
@@ -73,6 +73,22 @@ class GATConv(nn.Module):
         raise RuntimeError("cal_b200.GATConv is executed inside CausalGAT.forward")
 
 
+class GINConv(nn.Module):
+    """Parameter holder for PyG-1.x ``GINConv(nn, eps=0, train_eps=False)`` (model.py:187-193): the
+    wrapped ``nn`` (Linear -> BatchNorm1d -> ReLU -> Linear -> ReLU) and the ``eps`` buffer PyG keeps
+    in the ``state_dict``.  Executed inside CausalGIN.forward by the fused CUDA layer kernels."""
+
+    def __init__(self, nn_module, eps=0.0, train_eps=False):
+        super().__init__()
+        if train_eps or float(eps) != 0.0:
+            raise NotImplementedError("cal_b200.GINConv: eps = 0, train_eps = False (what CausalGIN uses)")
+        self.nn = nn_module
+        self.register_buffer("eps", torch.tensor([float(eps)]))
+
+    def forward(self, *a, **k):
+        raise RuntimeError("cal_b200.GINConv is executed inside CausalGIN.forward")
+
+
 # ----------------------------------------------------------------------------------------------
 # Engine: flat buffers, workspace, C-ABI calls
 # ----------------------------------------------------------------------------------------------
@@ -112,8 +128,9 @@ class Engine:
         L, H = len(m.convs), m.hidden
         self.L, self.H, self.C, self.F = L, H, m.num_classes, m.num_features
         self.is_gat = isinstance(m, CausalGAT)
+        self.is_gin = isinstance(m, CausalGIN)
         d = _lib.ModelDesc()
-        d.model = _lib.CAL_MODEL_GAT if self.is_gat else _lib.CAL_MODEL_GCN
+        d.model = _lib.CAL_MODEL_GAT if self.is_gat else (_lib.CAL_MODEL_GIN if self.is_gin else _lib.CAL_MODEL_GCN)
         d.num_features, d.hidden, d.num_classes, d.layers = self.F, H, self.C, L
         d.heads = m.head if self.is_gat else 1
         d.cat = int(m.args.cat_or_add == "cat")
@@ -159,6 +176,11 @@ class Engine:
         po.bn_feat_w, po.bn_feat_b = g("bn_feat.weight"), g("bn_feat.bias")
         po.conv_feat_w, po.conv_feat_b = g("conv_feat.weight"), g("conv_feat.bias")
         for i in range(self.L):
+            if self.is_gin:                                # convs.i.nn = Linear, BatchNorm1d, ReLU, Linear, ReLU
+                po.bns_conv_w[i], po.bns_conv_b[i] = g("convs.%d.nn.1.weight" % i), g("convs.%d.nn.1.bias" % i)
+                po.convs_w[i], po.convs_b[i] = g("convs.%d.nn.0.weight" % i), g("convs.%d.nn.0.bias" % i)
+                po.gin_w2[i], po.gin_b2[i] = g("convs.%d.nn.3.weight" % i), g("convs.%d.nn.3.bias" % i)
+                continue
             po.bns_conv_w[i], po.bns_conv_b[i] = g("bns_conv.%d.weight" % i), g("bns_conv.%d.bias" % i)
             po.convs_w[i], po.convs_b[i] = g("convs.%d.weight" % i), g("convs.%d.bias" % i)
             po.convs_att[i] = g("convs.%d.att" % i, -1)
@@ -175,8 +197,9 @@ class Engine:
         po.total = total
         self.po = po
         # BatchNorm buffers, in BN-id order (include/cal_b200.h)
-        bns = [m.bn_feat] + list(m.bns_conv) + [m.bnc, m.bno, m.fc1_bn_c, m.fc1_bn_o, m.fc1_bn_co,
-                                                m.fc2_bn_c, m.fc2_bn_o, m.fc2_bn_co]
+        inner = [conv.nn[1] for conv in m.convs] if self.is_gin else list(m.bns_conv)
+        bns = [m.bn_feat] + inner + [m.bnc, m.bno, m.fc1_bn_c, m.fc1_bn_o, m.fc1_bn_co,
+                                     m.fc2_bn_c, m.fc2_bn_o, m.fc2_bn_co]
         bo = _lib.BnOffsets()
         tot = 0
         for i, bn in enumerate(bns):
@@ -490,6 +513,41 @@ class CausalGCN(_CausalBase):
 
     def _shuffles(self, eval_random):                      # model.py:149-151
         return bool(self.with_random and eval_random)
+
+
+class CausalGIN(_CausalBase):
+    """Drop-in for the reference ``CausalGIN`` (model.py:166-313): same constructor, same
+    ``state_dict`` keys (``convs.i.nn.{0,1,3}.*``, ``convs.i.eps``), ``forward(data, eval_random=True,
+    train_type="base")``."""
+
+    def __init__(self, num_features, num_classes, args, gfn=False, edge_norm=True):
+        super().__init__()
+        if gfn or not edge_norm:
+            raise NotImplementedError("cal_b200.CausalGIN: gfn=False, edge_norm=True only (the reference defaults)")
+        hidden = args.hidden
+        self.args = args
+        self.hidden, self.num_features = hidden, num_features
+        self.dropout = 0.0
+        self.without_node_attention = False
+        self.without_edge_attention = False
+        self.num_classes = num_classes
+        self.fc_num = getattr(args, "fc_num", "222")
+        self.bn_feat = BatchNorm1d(num_features)
+        self.conv_feat = GCNConv(num_features, hidden, gfn=True)
+        self.bns_conv = nn.ModuleList()                    # stays empty (model.py:185)
+        self.convs = nn.ModuleList()
+        for _ in range(args.layers):
+            self.convs.append(GINConv(nn.Sequential(Linear(hidden, hidden), BatchNorm1d(hidden), nn.ReLU(),
+                                                    Linear(hidden, hidden), nn.ReLU())))
+        self._build_tail(hidden, num_classes)
+
+    def _shuffles(self, eval_random):                      # model.py:296-297
+        return bool(eval_random)
+
+    def forward(self, data, eval_random=True, train_type="base", perm=None):
+        if train_type != "base":
+            raise NotImplementedError("cal_b200.CausalGIN: train_type='irm' (raw logits, model.py:288-289) is not built")
+        return super().forward(data, eval_random=eval_random, perm=perm)
 
 
 class CausalGAT(_CausalBase):

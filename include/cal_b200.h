@@ -48,6 +48,7 @@ extern "C" {
 /* model kind */
 #define CAL_MODEL_GCN 0      /* CausalGCN, model.py:12-164 */
 #define CAL_MODEL_GAT 1      /* CausalGAT, model.py:315-450 */
+#define CAL_MODEL_GIN 2      /* CausalGIN, model.py:166-313: layers = GINConv(Linear-BN-ReLU-Linear-ReLU), no bns_conv */
 
 /* Model hyper-parameters: the `args` fields the reference models read
  * (model.py:24-37,65-77; opts.py:32-52) plus the loss weights of
@@ -90,12 +91,15 @@ typedef struct {
   int64_t context_w, context_b, objects_w, objects_b;
   int64_t fc1_bn_w[3], fc1_bn_b[3], fc1_w[3], fc1_b[3];
   int64_t fc2_bn_w[3], fc2_bn_b[3], fc2_w[3], fc2_b[3];
+  /* CausalGIN (model.py:187-193), layer i = convs.i.nn: convs_w/convs_b = nn.0 (Linear, [out, in] like
+   * every torch Linear), bns_conv_w/bns_conv_b = nn.1 (the BatchNorm inside the layer), and: */
+  int64_t gin_w2[CAL_MAX_LAYERS], gin_b2[CAL_MAX_LAYERS];   /* nn.3 (Linear) */
   int64_t total;               /* number of floats in the flat buffer */
 } cal_param_offsets;
 
 /* BatchNorm running statistics (torch BatchNorm1d buffers).  BN ids:
  * 0 = bn_feat, 1..L = bns_conv[i], L+1 = bnc, L+2 = bno,
- * L+3+h = fc1_bn_{c,o,co}, L+6+h = fc2_bn_{c,o,co}. */
+ * L+3+h = fc1_bn_{c,o,co}, L+6+h = fc2_bn_{c,o,co}.  CausalGIN: 1..L = convs[i].nn[1]. */
 typedef struct {
   int64_t running_mean[CAL_MAX_BN];   /* offsets in floats into bn_buffers */
   int64_t running_var[CAL_MAX_BN];
@@ -150,7 +154,8 @@ enum cal_ws_region {
   CAL_WS_BN,           /* f32[CAL_MAX_BN+1][6][KMAX]: scale, shift, mean, rstd, c1, c2 per BatchNorm */
   CAL_WS_STATP,        /* f64 scratch of the cross-CTA BatchNorm reductions (hierarchical grid sum) */
   CAL_WS_WT,           /* f32 transposed copies of conv / fc1 weights */
-  CAL_WS_GAT,          /* f32 GATConv: per layer x' [maxN][H], a_src / a_dst [maxN][heads], alpha [EP][heads]; then dz [EP][heads], d a_dst [maxN][heads] */
+  CAL_WS_GAT,          /* f32 backbone scratch.  CausalGIN: h [L][maxN][H] (nn.0 output, before the inner BatchNorm), then d r [maxN][H];
+                          GATConv: per layer x' [maxN][H], a_src / a_dst [maxN][heads], alpha [EP][heads]; then dz [EP][heads], d a_dst [maxN][heads] */
   CAL_WS_DLOGIT,       /* f32[3][maxB][C] */
   CAL_WS_DH,           /* f32[3][maxB][H] */
   CAL_WS_DU,           /* f32[3][maxB][2H] */

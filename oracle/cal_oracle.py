@@ -1,4 +1,4 @@
-"""CPU restatement of the CAL hot path (CausalGCN / CausalGAT fwd + loss + bwd).
+"""CPU restatement of the CAL hot path (CausalGCN / CausalGAT / CausalGIN fwd + loss + bwd).
 
 TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.  Pure PyTorch on the
 CPU, no dependency on torch_geometric / torch_scatter (neither is installable
@@ -269,11 +269,7 @@ class _CausalBase(nn.Module):
         x = data.x if getattr(data, "x", None) is not None else data.feat
         edge_index, batch = data.edge_index, data.batch
         row, col = edge_index
-        x = self.bn_feat(x)
-        x = _relu(self.conv_feat(x, edge_index), "x1")
-        for i, conv in enumerate(self.convs):
-            x = self.bns_conv[i](x)
-            x = _relu(conv(x, edge_index), "x%d" % (i + 2))
+        x = self.backbone(x, edge_index)
         edge_rep = torch.cat([x[row], x[col]], dim=-1)
         if self.without_edge_attention:
             edge_att = 0.5 * torch.ones(edge_rep.shape[0], 2, dtype=x.dtype, device=x.device)
@@ -295,6 +291,14 @@ class _CausalBase(nn.Module):
         xo_logis = self._readout(xo, "o")
         xco_logis = self.random_readout_layer(xc, xo, eval_random, perm)
         return xc_logis, xo_logis, xco_logis
+
+    def backbone(self, x, edge_index):            # model.py:90-95 / 385-390
+        x = self.bn_feat(x)
+        x = _relu(self.conv_feat(x, edge_index), "x1")
+        for i, conv in enumerate(self.convs):
+            x = self.bns_conv[i](x)
+            x = _relu(conv(x, edge_index), "x%d" % (i + 2))
+        return x
 
     def _readout(self, x, tag):                   # model.py:125-143
         x = getattr(self, "fc1_bn_" + tag)(x)
@@ -374,6 +378,63 @@ class CausalGAT(_CausalBase):
 
     def _shuffles(self, eval_random):             # model.py:435
         return bool(eval_random)
+
+
+class GINConv(nn.Module):
+    """torch_geometric.nn.GINConv, 1.x semantics (call site model.py:187-193):
+    out = nn((1 + eps) * x + sum_{j in N(i)} x_j), eps = 0, self loops removed first."""
+
+    def __init__(self, nn_module, eps=0.0):
+        super().__init__()
+        self.nn = nn_module
+        self.register_buffer("eps", torch.tensor([float(eps)]))     # PyG 1.x keeps eps as a buffer (train_eps=False)
+
+    def aggregate(self, x, edge_index):
+        edge_index, _ = remove_self_loops(edge_index)
+        return (1 + self.eps) * x + propagate_add(edge_index, x, None, x.size(0))
+
+    def forward(self, x, edge_index):
+        return self.nn(self.aggregate(x, edge_index))
+
+
+class CausalGIN(_CausalBase):
+    """model.py:166-313.  Backbone layer = GINConv(Linear -> BatchNorm1d -> ReLU -> Linear -> ReLU)
+    (model.py:187-193); no BatchNorm between the layers (bns_conv stays empty, model.py:185,237-238);
+    the permutation is drawn whenever eval_random is set (model.py:296-297); no ablation switches."""
+
+    def __init__(self, num_features, num_classes, args, gfn=False, edge_norm=True):
+        super().__init__()
+        hidden = args.hidden
+        self.args = args
+        self.dropout = 0.0
+        self.without_node_attention = False
+        self.without_edge_attention = False
+        GConv = partial(GCNConv, edge_norm=edge_norm, gfn=gfn)
+        self.num_classes = num_classes
+        self.fc_num = args.fc_num
+        self.bn_feat = BatchNorm1d(num_features)
+        self.conv_feat = GCNConv(num_features, hidden, gfn=True)
+        self.bns_conv = nn.ModuleList()
+        self.convs = nn.ModuleList()
+        for _ in range(args.layers):
+            self.convs.append(GINConv(nn.Sequential(Linear(hidden, hidden), BatchNorm1d(hidden), nn.ReLU(),
+                                                    Linear(hidden, hidden), nn.ReLU())))
+        self._build_tail(hidden, num_classes, GConv)
+
+    def _shuffles(self, eval_random):             # model.py:296-297
+        return bool(eval_random)
+
+    def backbone(self, x, edge_index):
+        """model.py:233-238 with the two ReLUs of every layer routed through the test hook
+        (tags "r{i+1}" = after the inner BatchNorm, "x{i+2}" = layer output)."""
+        x = self.bn_feat(x)
+        x = _relu(self.conv_feat(x, edge_index), "x1")
+        for i, conv in enumerate(self.convs):
+            lin1, bn, _, lin2, _ = conv.nn
+            h = lin1(conv.aggregate(x, edge_index))
+            r = _relu(bn(h), "r%d" % (i + 1))
+            x = _relu(lin2(r), "x%d" % (i + 2))
+        return x
 
 
 # --------------------------------------------------------------------------

@@ -23,7 +23,12 @@ def global_mean_pool(x, batch, size=None):
 class GINConv(MessagePassing):
     def __init__(self, nn, eps=0, train_eps=False):
         super().__init__("add")
-        self.nn, self.eps = nn, eps
+        self.nn = nn
+        self.initial_eps = eps
+        if train_eps:                              # PyG 1.x: a Parameter when trained, else a buffer
+            self.eps = Parameter(torch.Tensor([eps]))
+        else:
+            self.register_buffer("eps", torch.Tensor([eps]))
 
     def forward(self, x, edge_index):
         edge_index, _ = remove_self_loops(edge_index)

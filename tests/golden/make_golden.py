@@ -50,6 +50,9 @@ CASES = {
     "gcn_eval_h32": ("CausalGCN", "spmotif", 10, dict(), False, {}),
     "gat_add_h32": ("CausalGAT", "mutag", 10, dict(layers=2), True, dict(dropout=0.0)),
     "gat_eval_h32": ("CausalGAT", "mutag", 7, dict(layers=2), False, dict(dropout=0.2)),
+    "gin_add_h32": ("CausalGIN", "spmotif", 11, dict(layers=2), True, {}),
+    "gin_cat_h64": ("CausalGIN", "spmotif", 8, dict(layers=3, hidden=64, cat_or_add="cat"), True, {}),
+    "gin_eval_h32": ("CausalGIN", "spmotif", 9, dict(layers=2), False, {}),
 }
 
 
@@ -137,5 +140,5 @@ def run_case(name):
 
 
 if __name__ == "__main__":
-    for n in CASES:
+    for n in (sys.argv[1:] or CASES):
         run_case(n)

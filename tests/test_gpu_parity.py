@@ -57,6 +57,15 @@ def _gpu_relu_masks(eng, N, B):
     m["zc"], m["zo"] = (Z[0, :N] > 0).cpu(), (Z[1, :N] > 0).cpu()
     for h, t in enumerate(("c", "o", "co")):
         m["h1_" + t] = (H1[h, :B] > 0).cpu()
+    if getattr(eng, "is_gin", False):
+        # CausalGIN: the ReLU inside every layer acts on bn(h); the kernels evaluate fmaf(h, scale, shift) > 0,
+        # whose sign is the sign of the exact value
+        kmax = -(-max(-(-eng.F // 4) * 4, 2 * H) // 32) * 32
+        hbuf = eng.region("GAT")[:L * Nm * H].view(L, Nm, H)
+        rec = eng.region("BN").view(-1, 6, kmax)
+        for l in range(L):
+            sc, sh = rec[1 + l, 0, :H].double(), rec[1 + l, 1, :H].double()
+            m["r%d" % (l + 1)] = ((hbuf[l, :N].double() * sc + sh) > 0).cpu()
     return m
 
 
@@ -227,6 +236,32 @@ def _gat_masks(ora, b, seed, p_drop):
         keyed[l, ids] = m[:ids.numel()]
         keyed[l, E:] = m[ids.numel():]
     return keyed
+
+
+GIN_CASES = [
+    dict(seed=201, kind="CausalGIN", hidden=32, layers=2, batch_size=10),
+    dict(seed=202, kind="CausalGIN", hidden=128, layers=3, batch_size=128),                     # cfg 1 shapes
+    dict(seed=203, kind="CausalGIN", hidden=64, layers=3, batch_size=21, cat="cat", features=109, classes=2),
+    dict(seed=204, kind="CausalGIN", hidden=128, layers=1, batch_size=5),
+    dict(seed=205, kind="CausalGIN", hidden=32, layers=4, batch_size=9, avg_nodes=60, ba_m=2),
+]
+
+
+@pytest.mark.parametrize("case", GIN_CASES, ids=lambda c: "s%d" % c["seed"])
+def test_gin_train_step_matches_oracle(case):
+    """CausalGIN (model.py:166-313): GINConv(Linear-BN-ReLU-Linear-ReLU) backbone; then eval mode."""
+    M, O = _mods()
+    ora, b, perm = random_case(**case)
+    net = clone_to_cuda(ora, M)
+    _, ora_after = _step_and_compare(net, ora, b, perm, M, O)
+    ora_after.eval()
+    with torch.no_grad():
+        want = ora_after(b, eval_random=False)
+    net2 = clone_to_cuda(ora_after, M)
+    with torch.no_grad():
+        got = net2(b.to(DEV), eval_random=False)
+    for gg, w in zip(got, want):
+        assert rel_err(gg.cpu(), w) < TOL
 
 
 GAT_CASES = [

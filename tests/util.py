@@ -50,6 +50,8 @@ class GoldenCase:
         F_in = self.z["feat"].shape[1]
         if self.kind == "CausalGCN":
             net = module.CausalGCN(F_in, self.num_classes, self.args)
+        elif self.kind == "CausalGIN":
+            net = module.CausalGIN(F_in, self.num_classes, self.args)
         else:
             net = module.CausalGAT(F_in, self.num_classes, self.args, dropout=self.dropout)
         missing = net.load_state_dict(self.params, strict=True)
@@ -170,6 +172,8 @@ def random_case(seed=0, kind="CausalGCN", hidden=32, features=10, classes=4, lay
     torch.manual_seed(seed + 2)
     if kind == "CausalGCN":
         net = cal_oracle.CausalGCN(b.feat.size(1), classes, args)
+    elif kind == "CausalGIN":
+        net = cal_oracle.CausalGIN(b.feat.size(1), classes, args)
     else:
         net = cal_oracle.CausalGAT(b.feat.size(1), classes, args, dropout=dropout)
     with torch.no_grad():
@@ -186,6 +190,8 @@ def clone_to_cuda(oracle_net, module, device="cuda:0"):
     F_in = oracle_net.bn_feat.num_features
     if isinstance(oracle_net, cal_oracle.CausalGCN):
         net = module.CausalGCN(F_in, oracle_net.num_classes, oracle_net.args)
+    elif isinstance(oracle_net, cal_oracle.CausalGIN):
+        net = module.CausalGIN(F_in, oracle_net.num_classes, oracle_net.args)
     else:
         net = module.CausalGAT(F_in, oracle_net.num_classes, oracle_net.args, dropout=oracle_net.dropout)
     net.load_state_dict(oracle_net.state_dict(), strict=True)
