@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="cal_b200", choices=["cal_b200", "reference"])
     ap.add_argument("--workload", default="spmotif", choices=["spmotif", "spmotif_refsize", "mutag", "large"])
-    ap.add_argument("--model", default="CausalGCN", choices=["CausalGCN", "CausalGAT"])
+    ap.add_argument("--model", default="CausalGCN", choices=["CausalGCN", "CausalGAT", "CausalGIN"])
     ap.add_argument("--batch", type=int, default=0, help="graphs per GPU per step (default: the workload's)")
     ap.add_argument("--pool", type=int, default=0, help="distinct graphs generated per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -273,6 +273,8 @@ def run_gpu(a, rank, local_rank, world):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     bs = a.batch or CONFIGS[a.workload]["batch_size"]
     # enough distinct resident batches that the inputs of the timed region exceed L2 (no batch is
@@ -293,6 +295,8 @@ def run_gpu(a, rank, local_rank, world):
     random.seed(666 + rank)
     if a.model == "CausalGCN":
         net = cal_b200.CausalGCN(F, C, model_args()).to(dev)
+    elif a.model == "CausalGIN":
+        net = cal_b200.CausalGIN(F, C, model_args()).to(dev)
     else:
         net = cal_b200.CausalGAT(F, C, model_args()).to(dev)
     net.train()

@@ -19,3 +19,5 @@ timeout 300 python bench.py --workload large --steps 30 --warmup 5 --no-cpu-base
 tail -c 1800 gpurun_out/${TAG}_bench_large_stages.txt
 timeout 300 python bench.py --workload mutag --model CausalGAT --steps 200 --warmup 20 --no-cpu-baseline --stages > gpurun_out/${TAG}_bench_gat.json 2> gpurun_out/${TAG}_bench_gat_stages.txt; echo "bench gat rc=$?"
 tail -c 1800 gpurun_out/${TAG}_bench_gat_stages.txt
+timeout 300 python bench.py --model CausalGIN --steps 200 --warmup 20 --no-cpu-baseline --stages > gpurun_out/${TAG}_bench_gin.json 2> gpurun_out/${TAG}_bench_gin_stages.txt; echo "bench gin rc=$?"
+tail -c 1800 gpurun_out/${TAG}_bench_gin_stages.txt
