@@ -97,15 +97,17 @@ __device__ __forceinline__ float dot_lane(const RowVec<VEC>& a, const RowVec<VEC
 // `expected` = number of CTAs that arrive on this counter.
 __device__ __forceinline__ bool grid_last_block(unsigned int* counter, unsigned int expected) {
   __shared__ int s_last;
-  __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0) {             // one thread fences on both sides of the atomic (cooperative-groups pattern)
+    __threadfence();
     unsigned int t = atomicAdd(counter, 1u);
     s_last = (t == expected - 1u);
-    if (s_last) *counter = 0u;        // ready for the next launch (graph replay safe)
+    if (s_last) {
+      *counter = 0u;                  // ready for the next launch (graph replay safe)
+      __threadfence();
+    }
   }
   __syncthreads();
-  if (s_last) __threadfence();
   return s_last != 0;
 }
 

@@ -131,8 +131,9 @@ __global__ void __launch_bounds__(256) k_feat_fwd(const Ctx c) {
       accs[0][k] = acc_s[k];
       accs[1][k] = acc_q[k];
     }
+    const BnPre pre = bn_prefetch(c, 1);
     block_totals<VEC, 2>(accs, sRed, sTot, H, 0, H, 0);
-    if (grid_sum(c, 0, sTot, 2 * H, gridDim.x, blockIdx.x)) bn_finalize_tot(c, 1, sTot, sTot + H, N);
+    if (grid_sum(c, 0, sTot, 2 * H, gridDim.x, blockIdx.x)) bn_finalize_tot(c, 1, sTot, sTot + H, N, &pre);
   }
 }
 

@@ -157,16 +157,21 @@ __device__ __forceinline__ bool grid_sum(const Ctx& c, int site, double* sTot, i
   const int grp = rank / kGsGroup, ngrp = (G + kGsGroup - 1) / kGsGroup;
   const int gsize = imin(kGsGroup, G - grp * kGsGroup);
   for (int i = t; i < n; i += T) l0[(size_t)rank * n + i] = sTot[i];
-  __threadfence();
+  // publish / observe like a cooperative-groups grid barrier: the CTA barrier orders the CTA's stores
+  // before thread 0's device-scope fence (cumulative), the fence after the atomic orders the other
+  // CTAs' stores before the loads below -- ONE thread fences instead of all 256
   __syncthreads();
   if (t == 0) {
+    __threadfence();
     const unsigned int old = atomicAdd(&cnt[1 + grp], 1u);
     s_flag = (old == (unsigned int)gsize - 1u);
-    if (s_flag) cnt[1 + grp] = 0u;
+    if (s_flag) {
+      cnt[1 + grp] = 0u;
+      __threadfence();
+    }
   }
   __syncthreads();
   if (!s_flag) return false;
-  __threadfence();
   for (int i = t; i < n; i += T) {
     double v[kGsGroup];
 #pragma unroll
@@ -182,16 +187,18 @@ __device__ __forceinline__ bool grid_sum(const Ctx& c, int site, double* sTot, i
     __syncthreads();
     return true;
   }
-  __threadfence();
   __syncthreads();
   if (t == 0) {
+    __threadfence();
     const unsigned int old = atomicAdd(&cnt[0], 1u);
     s_flag = (old == (unsigned int)ngrp - 1u);
-    if (s_flag) cnt[0] = 0u;
+    if (s_flag) {
+      cnt[0] = 0u;
+      __threadfence();
+    }
   }
   __syncthreads();
   if (!s_flag) return false;
-  __threadfence();
   for (int i = t; i < n; i += T) {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int g = 0;
@@ -233,9 +240,28 @@ __device__ __forceinline__ void block_totals(double (&acc)[NV][VEC], double* sbu
 // Training-mode BatchNorm statistics from grid totals (sum[k], sumsq[k] in shared memory): the
 // affine the next kernel applies, the saved mean / rstd, and the running-statistics update
 // (biased variance to normalise, unbiased for running_var, momentum; torch BatchNorm1d).
+// The finishing CTA's parameter / running-statistic loads, issued BEFORE the grid sum by every CTA
+// (L2 hits, 4 registers) so that they are not one more dependent round trip on the serial tail.
+struct BnPre {
+  float g, b, rm, rv;
+};
+__device__ __forceinline__ BnPre bn_prefetch(const Ctx& c, int id) {
+  BnPre p = {1.f, 0.f, 0.f, 1.f};
+  const int k = threadIdx.x;
+  if (k < c.bn_K[id]) {
+    p.g = c.params[c.bn_gamma[id] + k];
+    p.b = c.params[c.bn_beta[id] + k];
+    if (c.bn_buffers != nullptr && c.bn_rm[id] >= 0) {
+      p.rm = c.bn_buffers[c.bn_rm[id] + k];
+      p.rv = c.bn_buffers[c.bn_rv[id] + k];
+    }
+  }
+  return p;
+}
 __device__ __forceinline__ void bn_finalize_tot(const Ctx& c, int id, const double* sum, const double* sumsq,
-                                                int count) {
+                                                int count, const BnPre* pre = nullptr) {
   const int K = c.bn_K[id];
+  const bool use_pre = pre != nullptr && K <= (int)blockDim.x;      // then k == threadIdx.x below
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     const double s = sum[k], q = sumsq[k];
     double mean = 0.0, var = 0.0;
@@ -245,7 +271,7 @@ __device__ __forceinline__ void bn_finalize_tot(const Ctx& c, int id, const doub
       if (var < 0.0) var = 0.0;
     }
     float rstd = (float)(1.0 / sqrt(var + (double)c.eps));
-    float g = c.params[c.bn_gamma[id] + k], b = c.params[c.bn_beta[id] + k];
+    float g = use_pre ? pre->g : c.params[c.bn_gamma[id] + k], b = use_pre ? pre->b : c.params[c.bn_beta[id] + k];
     float sc = g * rstd;
     c.bnf(id, BN_SCALE)[k] = sc;
     c.bnf(id, BN_SHIFT)[k] = b - (float)mean * sc;
@@ -255,8 +281,8 @@ __device__ __forceinline__ void bn_finalize_tot(const Ctx& c, int id, const doub
       double unb = count > 1 ? var * ((double)count / (double)(count - 1)) : var;
       float* rm = c.bn_buffers + c.bn_rm[id];
       float* rv = c.bn_buffers + c.bn_rv[id];
-      rm[k] = (1.f - c.momentum) * rm[k] + c.momentum * (float)mean;
-      rv[k] = (1.f - c.momentum) * rv[k] + c.momentum * (float)unb;
+      rm[k] = (1.f - c.momentum) * (use_pre ? pre->rm : rm[k]) + c.momentum * (float)mean;
+      rv[k] = (1.f - c.momentum) * (use_pre ? pre->rv : rv[k]) + c.momentum * (float)unb;
     }
   }
   if (threadIdx.x == 0 && c.nbt != nullptr) c.nbt[id] += 1;
@@ -421,13 +447,15 @@ struct LayerEpilogue {
   __device__ __forceinline__ void finish(const Ctx& c, int layer, double* sRed, double* sTot, int N) {
     constexpr int H = 32 * VEC;
     if (!c.train) return;
+    const BnPre p0 = bn_prefetch(c, LASTL ? c.L + 1 : 2 + layer);
+    const BnPre p1 = LASTL ? bn_prefetch(c, c.L + 2) : p0;
     block_totals<VEC, NV>(st, sRed, sTot, H, 0, H, 0);
     if (grid_sum(c, 0, sTot, NV * H, gridDim.x, blockIdx.x)) {
       if (!LASTL) {
-        bn_finalize_tot(c, 2 + layer, sTot, sTot + H, N);
+        bn_finalize_tot(c, 2 + layer, sTot, sTot + H, N, &p0);
       } else {
-        bn_finalize_tot(c, c.L + 1, sTot, sTot + H, N);
-        bn_finalize_tot(c, c.L + 2, sTot + 2 * H, sTot + 3 * H, N);
+        bn_finalize_tot(c, c.L + 1, sTot, sTot + H, N, &p0);
+        bn_finalize_tot(c, c.L + 2, sTot + 2 * H, sTot + 3 * H, N, &p1);
       }
     }
   }

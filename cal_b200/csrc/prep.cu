@@ -241,15 +241,15 @@ __global__ void k_prep_link(const Ctx c) {
 //   cycles and needs no inter-CTA communication -- and then writes only ITS slice of the nodes
 //   (and of their in- / out-rows) to global memory, so the store bandwidth of kPrepS SMs is used.
 // Same results as the multi-kernel path (the row order is fixed by the sort, not by the atomics).
-// smem (4-byte words): cnt_in [Nm] | cnt_out [Nm] | in_ptr [Nm+1] | out_ptr [Nm+1] | dis [Nm] |
-//                      in_key [EP] | out_key [EP] | edges [Em]
+// smem: cnt_in [Nm] | cnt_out [Nm] | in_ptr [Nm+1] | out_ptr [Nm+1] | dis [Nm] | edges [Em] (4-byte words) |
+//       in_key [EP] | out_key [EP] (u16: keys are edge_index columns or E + node, all < 65535)
 // ---------------------------------------------------------------------------------------------
 constexpr int kPrepT = 1024;
 constexpr int kPrepS = 8;
 constexpr size_t kPrepSmallMaxSmem = 225 * 1024;
 constexpr size_t kPrepStatSmem = (2 * kPrepT + 2 * 512) * sizeof(double);
 inline size_t prep_small_smem(int Nm, int Em) {
-  const size_t b = 4 * ((size_t)5 * Nm + 2 * (size_t)(Em + Nm) + (size_t)Em + 8);
+  const size_t b = 4 * ((size_t)5 * Nm + (size_t)(Em + Nm) + (size_t)Em + 8);      // keys are u16 (E' < 65535)
   return b > kPrepStatSmem ? b : kPrepStatSmem;
 }
 
@@ -346,9 +346,9 @@ __global__ void __launch_bounds__(kPrepT) k_prep_small(const Ctx c) {
   int* s_iptr = s_cout + Nm;
   int* s_optr = s_iptr + Nm + 1;
   float* s_dis = reinterpret_cast<float*>(s_optr + Nm + 1);
-  int* s_ikey = reinterpret_cast<int*>(s_dis + Nm);
-  int* s_okey = s_ikey + EP;
-  unsigned int* s_edge = reinterpret_cast<unsigned int*>(s_okey + EP);     // (row << 16) | col; 0xffffffff = dropped
+  unsigned int* s_edge = reinterpret_cast<unsigned int*>(s_dis + Nm);      // (row << 16) | col; 0xffffffff = dropped
+  unsigned short* s_ikey = reinterpret_cast<unsigned short*>(s_edge + c.Em);
+  unsigned short* s_okey = s_ikey + EP;
   const int lane = t & 31, warp = t >> 5;
   PT_DECL
   if (t == 0) s_status = 0;
@@ -478,12 +478,12 @@ __global__ void __launch_bounds__(kPrepT) k_prep_small(const Ctx c) {
     const unsigned int pk = s_edge[e];
     if (pk == 0xffffffffu) continue;
     const int r = (int)(pk >> 16), d = (int)(pk & 0xffffu);
-    s_ikey[s_iptr[d] + atomicAdd(&s_cin[d], 1)] = e;
-    s_okey[s_optr[r] + atomicAdd(&s_cout[r], 1)] = e;
+    s_ikey[s_iptr[d] + atomicAdd(&s_cin[d], 1)] = (unsigned short)e;
+    s_okey[s_optr[r] + atomicAdd(&s_cout[r], 1)] = (unsigned short)e;
   }
   for (int n = t; n < N; n += T) {
-    s_ikey[s_iptr[n + 1] - 1] = E + n;
-    s_okey[s_optr[n + 1] - 1] = E + n;
+    s_ikey[s_iptr[n + 1] - 1] = (unsigned short)(E + n);
+    s_okey[s_optr[n + 1] - 1] = (unsigned short)(E + n);
   }
   __syncthreads();
   PT_MARK();                                           // 4: fill
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(kPrepT) k_prep_small(const Ctx c) {
   {
     const int pb = s_iptr[nlo], pe = s_iptr[nhi];
     for (int u = pb + t; u < pe; u += T) {
-      const int key = s_ikey[u];
+      const int key = (int)s_ikey[u];
       int n, src;
       if (key < E) {
         const unsigned int pk = s_edge[key];
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(kPrepT) k_prep_small(const Ctx c) {
       }
       const int a = s_iptr[n], b = s_iptr[n + 1];
       int rank = 0;
-      for (int v = a; v < b; ++v) rank += s_ikey[v] < key;
+      for (int v = a; v < b; ++v) rank += (int)s_ikey[v] < key;
       const int p = a + rank;
       c.in_key[p] = key;
       c.in_src[p] = src;
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(kPrepT) k_prep_small(const Ctx c) {
     }
     const int qb = s_optr[nlo], qe = s_optr[nhi];
     for (int u = qb + t; u < qe; u += T) {
-      const int key = s_okey[u];
+      const int key = (int)s_okey[u];
       int n, dst;
       if (key < E) {
         const unsigned int pk = s_edge[key];
@@ -532,10 +532,10 @@ __global__ void __launch_bounds__(kPrepT) k_prep_small(const Ctx c) {
       }
       const int a = s_optr[n], b = s_optr[n + 1];
       int rank = 0;
-      for (int v = a; v < b; ++v) rank += s_okey[v] < key;
+      for (int v = a; v < b; ++v) rank += (int)s_okey[v] < key;
       const int a2 = s_iptr[dst], b2 = s_iptr[dst + 1];
       int rank2 = 0;
-      for (int v = a2; v < b2; ++v) rank2 += s_ikey[v] < key;
+      for (int v = a2; v < b2; ++v) rank2 += (int)s_ikey[v] < key;
       const int q = a + rank;
       c.out_key[q] = key;
       c.out_dst[q] = dst;
