@@ -131,9 +131,14 @@ __global__ void __launch_bounds__(256) k_feat_fwd(const Ctx c) {
       accs[0][k] = acc_s[k];
       accs[1][k] = acc_q[k];
     }
-    const BnPre pre = bn_prefetch(c, 1);
-    block_totals<VEC, 2>(accs, sRed, sTot, H, 0, H, 0);
-    if (grid_sum(c, 0, sTot, 2 * H, gridDim.x, blockIdx.x)) bn_finalize_tot(c, 1, sTot, sTot + H, N, &pre);
+    if (bn_consumer_side(c)) {                         // layer 0 sums the group vectors and finalises bns_conv[0]
+      block_totals<VEC, 2>(accs, sRed, sTot, H, 0, H, 0);
+      grid_sum_groups(c, bn_site(1), sTot, 2 * H, gridDim.x, blockIdx.x);
+    } else {
+      const BnPre pre = bn_prefetch(c, 1);
+      block_totals<VEC, 2>(accs, sRed, sTot, H, 0, H, 0);
+      if (grid_sum(c, 0, sTot, 2 * H, gridDim.x, blockIdx.x)) bn_finalize_tot(c, 1, sTot, sTot + H, N, &pre);
+    }
   }
 }
 
@@ -192,10 +197,25 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
   (void)conv;
 
   stage_matrix_async(sW, W, H * H);
+  // backbone layers in training: the BatchNorm on the input is finalised HERE from the group sums the
+  // previous kernel left behind (bn_from_groups); its parameters are fetched before the dependency wait
+  __shared__ float s_aff[(MODE == 0 || MODE == 1) ? 2 * H : 1];
+  const bool cs = (MODE == 0 || MODE == 1) && bn_consumer_side(c);
+  BnPre pre_in = {1.f, 0.f, 0.f, 1.f};
+  if (cs) pre_in = bn_prefetch(c, bn_in);
   pdl_sync();                                        // everything below may read the predecessor's output
 
   BnLane<VEC> bn;
-  bn.load_fwd(c, bn_in, lane);
+  if (cs) {
+    bn_from_groups(c, bn_site(bn_in), bn_in, c.g_tile, 2 * H, 0, N, pre_in, sTot, s_aff, s_aff + H, blockIdx.x == 0);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      bn.sc[i] = s_aff[lane * VEC + i];
+      bn.sh[i] = s_aff[H + lane * VEC + i];
+    }
+  } else {
+    bn.load_fwd(c, bn_in, lane);
+  }
   float bv[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) bv[i] = bias[lane * VEC + i];
@@ -367,11 +387,32 @@ __global__ void __launch_bounds__(256) k_masked_fwd_both(const Ctx c) {
 
   stage_matrix_async(sW, c.params + c.po.context_w, H * H);
   stage_matrix_async(sW + H * H, c.params + c.po.objects_w, H * H);
+  __shared__ double s_scr[2 * H];
+  __shared__ float s_aff[4 * H];
+  const bool cs = bn_consumer_side(c);               // bnc / bno finalised here from the last layer's group sums
+  BnPre pre0 = {1.f, 0.f, 0.f, 1.f}, pre1 = pre0;
+  if (cs) {
+    pre0 = bn_prefetch(c, c.L + 1);
+    pre1 = bn_prefetch(c, c.L + 2);
+  }
   pdl_sync();                                        // everything below may read the predecessor's output
 
   BnLane<VEC> bn0, bn1;
-  bn0.load_fwd(c, c.L + 1, lane);
-  bn1.load_fwd(c, c.L + 2, lane);
+  if (cs) {
+    const int site = bn_site(c.L + 1);
+    bn_from_groups(c, site, c.L + 1, c.g_tile, 4 * H, 0, N, pre0, s_scr, s_aff, s_aff + H, blockIdx.x == 0);
+    bn_from_groups(c, site, c.L + 2, c.g_tile, 4 * H, 2 * H, N, pre1, s_scr, s_aff + 2 * H, s_aff + 3 * H, blockIdx.x == 0);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      bn0.sc[i] = s_aff[lane * VEC + i];
+      bn0.sh[i] = s_aff[H + lane * VEC + i];
+      bn1.sc[i] = s_aff[2 * H + lane * VEC + i];
+      bn1.sh[i] = s_aff[3 * H + lane * VEC + i];
+    }
+  } else {
+    bn0.load_fwd(c, c.L + 1, lane);
+    bn1.load_fwd(c, c.L + 2, lane);
+  }
   float bv0[VEC], bv1[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
@@ -817,7 +858,8 @@ template <int VEC, bool LASTL>
 __global__ void __launch_bounds__(256) k_gin_b_fwd(const Ctx c, const int layer) {
   constexpr int H = 32 * VEC, LDA = H + kPad;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ double sTot[LASTL ? 4 * H : 1];
+  __shared__ double sTot[LASTL ? 4 * H : 2 * H];
+  __shared__ float s_aff[2 * H];
   const Dims d = load_dims(c);
   const int N = d.N;
   float* sW = reinterpret_cast<float*>(smem_raw);
@@ -825,9 +867,21 @@ __global__ void __launch_bounds__(256) k_gin_b_fwd(const Ctx c, const int layer)
   double* sRed = reinterpret_cast<double*>(sA + kTileRows * LDA);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   stage_matrix_async(sW, c.wt_gin2(layer), H * H);
+  const bool cs = bn_consumer_side(c);               // the layer's inner BatchNorm is finalised here
+  BnPre pre_in = {1.f, 0.f, 0.f, 1.f};
+  if (cs) pre_in = bn_prefetch(c, 1 + layer);
   pdl_sync();                                        // everything below may read the predecessor's output
   BnLane<VEC> bn;
-  bn.load_fwd(c, 1 + layer, lane);
+  if (cs) {
+    bn_from_groups(c, bn_site(1 + layer), 1 + layer, c.g_tile, 2 * H, 0, N, pre_in, sTot, s_aff, s_aff + H, blockIdx.x == 0);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      bn.sc[i] = s_aff[lane * VEC + i];
+      bn.sh[i] = s_aff[H + lane * VEC + i];
+    }
+  } else {
+    bn.load_fwd(c, 1 + layer, lane);
+  }
   float bv[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) bv[i] = c.params[c.po.gin_b2[layer] + lane * VEC + i];

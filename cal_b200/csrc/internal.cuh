@@ -17,7 +17,7 @@ constexpr int kHeadRowsPerCta = 8;             // head2 kernels: one warp per gr
 constexpr int kFeatChunk = 64;                 // feature columns per CTA slice in the feat backward
 constexpr int kFeatBwdCtas = 32;               // row-slices (= partial gradients) of the feat backward
 constexpr int kGsGroup = 8;                    // CTAs per first-level group of the hierarchical grid sum
-constexpr int kGsSites = 3;                    // independent grid sums that may be in flight in one kernel
+constexpr int kGsSites = 5;                    // grid-sum scratch sites: 0-2 in-kernel sums, 3-4 consumer-side BatchNorm hand-over (alternating)
 constexpr int kGsCounters = 64;                // counters per site: [0] top level, [1 + group] first level
 
 // BN record fields inside CAL_WS_BN: [id][field][KMAX]
@@ -215,6 +215,133 @@ __device__ __forceinline__ bool grid_sum(const Ctx& c, int site, double* sTot, i
   return true;
 }
 
+// The finishing CTA's parameter / running-statistic loads, issued BEFORE the grid sum by every CTA
+// (L2 hits, 4 registers) so that they are not one more dependent round trip on the serial tail.
+struct BnPre {
+  float g, b, rm, rv;
+};
+__device__ __forceinline__ BnPre bn_prefetch(const Ctx& c, int id) {
+  BnPre p = {1.f, 0.f, 0.f, 1.f};
+  const int k = threadIdx.x;
+  if (k < c.bn_K[id]) {
+    p.g = c.params[c.bn_gamma[id] + k];
+    p.b = c.params[c.bn_beta[id] + k];
+    if (c.bn_buffers != nullptr && c.bn_rm[id] >= 0) {
+      p.rm = c.bn_buffers[c.bn_rm[id] + k];
+      p.rv = c.bn_buffers[c.bn_rv[id] + k];
+    }
+  }
+  return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Consumer-side BatchNorm hand-over (forward chain of CausalGCN / CausalGIN).  The producing kernel
+// stops after the FIRST level of the tree: the last CTA of every group of 8 leaves the group's sums
+// in l1[group]; nobody waits for the whole grid and nobody finalises.  The consuming kernel starts
+// after the producer has completed (programmatic dependency), so every one of its CTAs sums the
+// <= 37 group vectors itself -- independent loads, one L2 round trip, the same order as grid_sum's
+// second level (bit-identical totals) -- and turns them into the affine it applies; CTA 0 also
+// publishes the record (the backward pass reads it) and updates the running statistics.
+// This removes the second atomic phase and the serial finalisation from the producer's tail.
+// Sites 3 / 4 alternate along the chain (site = 3 + (first BN id & 1)) so that a kernel never
+// writes the scratch its own late CTAs may still be reading.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int bn_site(int first_id) { return 3 + (first_id & 1); }
+
+__device__ __forceinline__ void grid_sum_groups(const Ctx& c, int site, const double* sTot, int n, int G, int rank) {
+  __shared__ int s_gflag;
+  double* l0 = c.gsum + (size_t)site * c.gs_stride;
+  double* l1 = l0 + (size_t)kMaxStatBlocks * c.gs_n;
+  unsigned int* cnt = c.gs_cnt + site * kGsCounters;
+  const int t = threadIdx.x, T = blockDim.x;
+  const int grp = rank / kGsGroup;
+  const int gsize = imin(kGsGroup, G - grp * kGsGroup);
+  if (gsize == 1) {                                    // a group of one: its sums are the group sums
+    for (int i = t; i < n; i += T) l1[(size_t)grp * n + i] = sTot[i];
+    return;
+  }
+  for (int i = t; i < n; i += T) l0[(size_t)rank * n + i] = sTot[i];
+  __syncthreads();
+  if (t == 0) {
+    __threadfence();
+    const unsigned int old = atomicAdd(&cnt[1 + grp], 1u);
+    s_gflag = (old == (unsigned int)gsize - 1u);
+    if (s_gflag) {
+      cnt[1 + grp] = 0u;
+      __threadfence();
+    }
+  }
+  __syncthreads();
+  if (!s_gflag) return;
+  for (int i = t; i < n; i += T) {
+    double v[kGsGroup];
+#pragma unroll
+    for (int m = 0; m < kGsGroup; ++m)
+      v[m] = m < gsize ? __ldcg(&l0[(size_t)(grp * kGsGroup + m) * n + i]) : 0.0;
+    double sum = v[0];
+#pragma unroll
+    for (int m = 1; m < kGsGroup; ++m) sum += v[m];
+    l1[(size_t)grp * n + i] = sum;
+  }
+}
+
+// G / n_prod: grid size and vector length of the producer; the sums of BatchNorm `id` start at voff
+// ([sum (K) | sum of squares (K)]).  scratch: >= 2K doubles of shared memory; s_sc / s_sh: K floats.
+// All threads call; K <= blockDim.x.
+__device__ __forceinline__ void bn_from_groups(const Ctx& c, int site, int id, int G, int n_prod, int voff, int count,
+                                               const BnPre& pre, double* scratch, float* s_sc, float* s_sh,
+                                               bool publish) {
+  const int K = c.bn_K[id];
+  const double* l1 = c.gsum + (size_t)site * c.gs_stride + (size_t)kMaxStatBlocks * c.gs_n;
+  const int ngrp = (G + kGsGroup - 1) / kGsGroup;
+  const int t = threadIdx.x, T = blockDim.x;
+  for (int v = t; v < 2 * K; v += T) {
+    const double* p = l1 + voff + v;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int g = 0;
+    for (; g + 4 <= ngrp; g += 4) {
+      s0 += __ldcg(p + (size_t)(g + 0) * n_prod);
+      s1 += __ldcg(p + (size_t)(g + 1) * n_prod);
+      s2 += __ldcg(p + (size_t)(g + 2) * n_prod);
+      s3 += __ldcg(p + (size_t)(g + 3) * n_prod);
+    }
+    for (; g < ngrp; ++g) s0 += __ldcg(p + (size_t)g * n_prod);
+    scratch[v] = ngrp == 1 ? s0 : (s0 + s1) + (s2 + s3);
+  }
+  __syncthreads();
+  if (t < K) {
+    const double s = scratch[t], q = scratch[K + t];
+    double mean = 0.0, var = 0.0;
+    if (count > 0) {
+      mean = s / count;
+      var = q / count - mean * mean;
+      if (var < 0.0) var = 0.0;
+    }
+    const float rstd = (float)(1.0 / sqrt(var + (double)c.eps));
+    const float sc = pre.g * rstd;
+    const float sh = pre.b - (float)mean * sc;
+    s_sc[t] = sc;
+    s_sh[t] = sh;
+    if (publish) {
+      c.bnf(id, BN_SCALE)[t] = sc;
+      c.bnf(id, BN_SHIFT)[t] = sh;
+      c.bnf(id, BN_MEAN)[t] = (float)mean;
+      c.bnf(id, BN_RSTD)[t] = rstd;
+      if (c.bn_buffers != nullptr && c.bn_rm[id] >= 0) {
+        const double unb = count > 1 ? var * ((double)count / (double)(count - 1)) : var;
+        c.bn_buffers[c.bn_rm[id] + t] = (1.f - c.momentum) * pre.rm + c.momentum * (float)mean;
+        c.bn_buffers[c.bn_rv[id] + t] = (1.f - c.momentum) * pre.rv + c.momentum * (float)unb;
+      }
+    }
+  }
+  if (publish && t == 0 && c.nbt != nullptr) c.nbt[id] += 1;
+  __syncthreads();
+}
+
+// true: this model's forward chain hands BatchNorm statistics over consumer-side (the GATConv
+// kernels still read the finalised record)
+__device__ __forceinline__ bool bn_consumer_side(const Ctx& c) { return c.train && c.model != CAL_MODEL_GAT; }
+
 // Cross-warp reduction of per-lane fp64 accumulators (lane owns VEC channels, 8 warps) into the
 // CTA totals sTot[(v0 + v) * K + koff + k].  sbuf holds kRowWarps * H doubles.  Fixed order.
 template <int VEC, int NV>
@@ -240,24 +367,6 @@ __device__ __forceinline__ void block_totals(double (&acc)[NV][VEC], double* sbu
 // Training-mode BatchNorm statistics from grid totals (sum[k], sumsq[k] in shared memory): the
 // affine the next kernel applies, the saved mean / rstd, and the running-statistics update
 // (biased variance to normalise, unbiased for running_var, momentum; torch BatchNorm1d).
-// The finishing CTA's parameter / running-statistic loads, issued BEFORE the grid sum by every CTA
-// (L2 hits, 4 registers) so that they are not one more dependent round trip on the serial tail.
-struct BnPre {
-  float g, b, rm, rv;
-};
-__device__ __forceinline__ BnPre bn_prefetch(const Ctx& c, int id) {
-  BnPre p = {1.f, 0.f, 0.f, 1.f};
-  const int k = threadIdx.x;
-  if (k < c.bn_K[id]) {
-    p.g = c.params[c.bn_gamma[id] + k];
-    p.b = c.params[c.bn_beta[id] + k];
-    if (c.bn_buffers != nullptr && c.bn_rm[id] >= 0) {
-      p.rm = c.bn_buffers[c.bn_rm[id] + k];
-      p.rv = c.bn_buffers[c.bn_rv[id] + k];
-    }
-  }
-  return p;
-}
 __device__ __forceinline__ void bn_finalize_tot(const Ctx& c, int id, const double* sum, const double* sumsq,
                                                 int count, const BnPre* pre = nullptr) {
   const int K = c.bn_K[id];
@@ -447,6 +556,11 @@ struct LayerEpilogue {
   __device__ __forceinline__ void finish(const Ctx& c, int layer, double* sRed, double* sTot, int N) {
     constexpr int H = 32 * VEC;
     if (!c.train) return;
+    if (bn_consumer_side(c)) {                         // the next kernel sums the group vectors and finalises
+      block_totals<VEC, NV>(st, sRed, sTot, H, 0, H, 0);
+      grid_sum_groups(c, bn_site(LASTL ? c.L + 1 : 2 + layer), sTot, NV * H, gridDim.x, blockIdx.x);
+      return;
+    }
     const BnPre p0 = bn_prefetch(c, LASTL ? c.L + 1 : 2 + layer);
     const BnPre p1 = LASTL ? bn_prefetch(c, c.L + 2) : p0;
     block_totals<VEC, NV>(st, sRed, sTot, H, 0, H, 0);
