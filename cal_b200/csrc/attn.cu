@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256) k_masked_bwd_gather(const Ctx c) {
     }
   }
   block_totals<VEC, 2>(st, sRed, sTot, H, 0, H, 0);
-  if (grid_sum(c, k, sTot, 2 * H, gridDim.x, blockIdx.x)) bn_bwd_finalize_tot(c, bn_id, sTot, sTot + H, N);
+  grid_sum_groups(c, k, sTot, 2 * H, gridDim.x, blockIdx.x);       // k_att_bwd finalises bnc / bno (site = branch)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -271,6 +271,20 @@ __global__ void __launch_bounds__(256, 2) k_att_bwd(const Ctx c) {
   BnLane<VEC> bc, bo;
   bc.load_bwd(c, c.L + 1, lane);
   bo.load_bwd(c, c.L + 2, lane);
+  {
+    // backward sums of bnc / bno: group vectors left by k_masked_bwd_gather (sites 0 / 1, grid g_row)
+    __shared__ double s_scr[2 * H];
+    __shared__ float s_c[4 * H];
+    bn_bwd_from_groups(c, 0, c.L + 1, c.g_row, 2 * H, 0, N, s_scr, s_c, s_c + H, blockIdx.x == 0);
+    bn_bwd_from_groups(c, 1, c.L + 2, c.g_row, 2 * H, 0, N, s_scr, s_c + 2 * H, s_c + 3 * H, blockIdx.x == 0);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      bc.c1[i] = s_c[lane * VEC + i];
+      bc.c2[i] = s_c[H + lane * VEC + i];
+      bo.c1[i] = s_c[2 * H + lane * VEC + i];
+      bo.c2[i] = s_c[3 * H + lane * VEC + i];
+    }
+  }
   float wn0[VEC], wn1[VEC], wp0[VEC], wp1[VEC], wq0[VEC], wq1[VEC];
   {
     const float* Wn = c.params + c.po.node_att_w;

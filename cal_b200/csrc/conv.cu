@@ -598,6 +598,17 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
   BnLane<VEC> bi, bu;
   bi.load_bwd(c, bn_in, lane);
   bu.load_bwd(c, bn_up, lane);
+  if (bn_up != kBnIdentity) {
+    // the upstream BatchNorm's backward sums arrive as group vectors (k_conv_bwd of the layer above, or
+    // k_gin_b_bwd): every CTA turns them into c1 / c2, CTA 0 publishes d gamma / d beta
+    __shared__ float s_c[2 * H];
+    bn_bwd_from_groups(c, bn_site(bn_up), bn_up, c.g_tile, 2 * H, 0, N, sTot, s_c, s_c + H, blockIdx.x == 0);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      bu.c1[i] = s_c[lane * VEC + i];
+      bu.c2[i] = s_c[H + lane * VEC + i];
+    }
+  }
 
   OuterAcc<H> dW;
   dW.zero();
@@ -758,9 +769,9 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
   if (blockIdx.x < ntiles) dW.store(gp, H);
   block_colsum_store<VEC>(dbias, reinterpret_cast<float*>(sRed), blockIdx.x < ntiles ? gp + H * H : nullptr, H);
   PT_MARK();                                           // 7: dW / db partial stores
-  if (!GIN) {
+  if (!GIN) {                                          // group sums only: the kernel below finalises (bn_bwd_from_groups)
     block_totals<VEC, 2>(st, sRed, sTot, H, 0, H, 0);
-    if (grid_sum(c, 0, sTot, 2 * H, gridDim.x, blockIdx.x)) bn_bwd_finalize_tot(c, bn_in, sTot, sTot + H, N);
+    grid_sum_groups(c, bn_site(bn_in), sTot, 2 * H, gridDim.x, blockIdx.x);
   }
   PT_MARK();                                           // 8: totals + grid sum + finalize
   PT_DUMP(c, 32);
@@ -1017,7 +1028,7 @@ __global__ void __launch_bounds__(256) k_gin_b_bwd(const Ctx c, const int layer)
   if (blockIdx.x < ntiles) dW.store(gp, H);
   block_colsum_store<VEC>(dbias, reinterpret_cast<float*>(sRed), blockIdx.x < ntiles ? gp + H * H : nullptr, H);
   block_totals<VEC, 2>(st, sRed, sTot, H, 0, H, 0);
-  if (grid_sum(c, 0, sTot, 2 * H, gridDim.x, blockIdx.x)) bn_bwd_finalize_tot(c, bn_id, sTot, sTot + H, N);
+  grid_sum_groups(c, bn_site(bn_id), sTot, 2 * H, gridDim.x, blockIdx.x);      // k_conv_bwd<GIN> finalises
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1045,6 +1056,18 @@ __global__ void __launch_bounds__(256) k_feat_bwd(const Ctx c) {
   const float* rstd0 = c.bnf(0, BN_RSTD);
   BnLane<VEC> b1;
   b1.load_bwd(c, c.model == CAL_MODEL_GIN ? kBnIdentity : 1, lane);     // CausalGIN has no BatchNorm on x_1 (model.py:237-238)
+  if (c.model == CAL_MODEL_GCN) {
+    // bns_conv[0]'s backward sums arrive as group vectors from k_conv_bwd(layer 0); CTA (0, 0) publishes
+    __shared__ double s_scr[2 * H];
+    __shared__ float s_c[2 * H];
+    bn_bwd_from_groups(c, bn_site(1), 1, c.g_tile, 2 * H, 0, imin(imax(c.dims[0], 0), c.Nm), s_scr, s_c, s_c + H,
+                       blockIdx.x == 0 && blockIdx.y == 0);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      b1.c1[i] = s_c[lane * VEC + i];
+      b1.c2[i] = s_c[H + lane * VEC + i];
+    }
+  }
   float M[FW][VEC], cs[VEC];
 #pragma unroll
   for (int a = 0; a < FW; ++a)

@@ -338,6 +338,45 @@ __device__ __forceinline__ void bn_from_groups(const Ctx& c, int site, int id, i
   __syncthreads();
 }
 
+// The same hand-over for the BatchNorm BACKWARD sums (sum dy | sum dy * xhat): c1 = mean(dy),
+// c2 = mean(dy * xhat) into shared memory for this CTA; CTA `publish` writes d gamma / d beta and the record.
+__device__ __forceinline__ void bn_bwd_from_groups(const Ctx& c, int site, int id, int G, int n_prod, int voff,
+                                                   int count, double* scratch, float* s_c1, float* s_c2,
+                                                   bool publish) {
+  const int K = c.bn_K[id];
+  const double* l1 = c.gsum + (size_t)site * c.gs_stride + (size_t)kMaxStatBlocks * c.gs_n;
+  const int ngrp = (G + kGsGroup - 1) / kGsGroup;
+  const int t = threadIdx.x, T = blockDim.x;
+  for (int v = t; v < 2 * K; v += T) {
+    const double* p = l1 + voff + v;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int g = 0;
+    for (; g + 4 <= ngrp; g += 4) {
+      s0 += __ldcg(p + (size_t)(g + 0) * n_prod);
+      s1 += __ldcg(p + (size_t)(g + 1) * n_prod);
+      s2 += __ldcg(p + (size_t)(g + 2) * n_prod);
+      s3 += __ldcg(p + (size_t)(g + 3) * n_prod);
+    }
+    for (; g < ngrp; ++g) s0 += __ldcg(p + (size_t)g * n_prod);
+    scratch[v] = ngrp == 1 ? s0 : (s0 + s1) + (s2 + s3);
+  }
+  __syncthreads();
+  if (t < K) {
+    const double inv = count > 0 ? 1.0 / count : 0.0;
+    const double a = scratch[t], b = scratch[K + t];
+    const float c1 = (float)(a * inv), c2 = (float)(b * inv);
+    s_c1[t] = c1;
+    s_c2[t] = c2;
+    if (publish) {
+      c.bnf(id, BN_C1)[t] = c1;
+      c.bnf(id, BN_C2)[t] = c2;
+      c.grads[c.bn_gamma[id] + t] = (float)b;
+      c.grads[c.bn_beta[id] + t] = (float)a;
+    }
+  }
+  __syncthreads();
+}
+
 // true: this model's forward chain hands BatchNorm statistics over consumer-side (the GATConv
 // kernels still read the finalised record)
 __device__ __forceinline__ bool bn_consumer_side(const Ctx& c) { return c.train && c.model != CAL_MODEL_GAT; }
