@@ -273,10 +273,10 @@ __global__ void __launch_bounds__(256, 2) k_att_bwd(const Ctx c) {
   bo.load_bwd(c, c.L + 2, lane);
   {
     // backward sums of bnc / bno: group vectors left by k_masked_bwd_gather (sites 0 / 1, grid g_row)
-    __shared__ double s_scr[2 * H];
+    __shared__ double s_scr[4 * H];
     __shared__ float s_c[4 * H];
-    bn_bwd_from_groups(c, 0, c.L + 1, c.g_row, 2 * H, 0, N, s_scr, s_c, s_c + H, blockIdx.x == 0);
-    bn_bwd_from_groups(c, 1, c.L + 2, c.g_row, 2 * H, 0, N, s_scr, s_c + 2 * H, s_c + 3 * H, blockIdx.x == 0);
+    bn_bwd_from_groups2(c, 0, c.L + 1, 1, c.L + 2, c.g_row, 2 * H, N, s_scr, s_c, s_c + H, s_c + 2 * H, s_c + 3 * H,
+                        blockIdx.x == 0);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       bc.c1[i] = s_c[lane * VEC + i];

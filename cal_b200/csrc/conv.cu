@@ -387,21 +387,21 @@ __global__ void __launch_bounds__(256) k_masked_fwd_both(const Ctx c) {
 
   stage_matrix_async(sW, c.params + c.po.context_w, H * H);
   stage_matrix_async(sW + H * H, c.params + c.po.objects_w, H * H);
-  __shared__ double s_scr[2 * H];
+  __shared__ double s_scr[4 * H];
   __shared__ float s_aff[4 * H];
   const bool cs = bn_consumer_side(c);               // bnc / bno finalised here from the last layer's group sums
   BnPre pre0 = {1.f, 0.f, 0.f, 1.f}, pre1 = pre0;
   if (cs) {
     pre0 = bn_prefetch(c, c.L + 1);
-    pre1 = bn_prefetch(c, c.L + 2);
+    pre1 = bn_prefetch(c, c.L + 2, H);               // threads [H, 2H) finalise bno
   }
   pdl_sync();                                        // everything below may read the predecessor's output
 
   BnLane<VEC> bn0, bn1;
   if (cs) {
     const int site = bn_site(c.L + 1);
-    bn_from_groups(c, site, c.L + 1, c.g_tile, 4 * H, 0, N, pre0, s_scr, s_aff, s_aff + H, blockIdx.x == 0);
-    bn_from_groups(c, site, c.L + 2, c.g_tile, 4 * H, 2 * H, N, pre1, s_scr, s_aff + 2 * H, s_aff + 3 * H, blockIdx.x == 0);
+    bn_from_groups2(c, site, c.L + 1, 0, site, c.L + 2, 2 * H, c.g_tile, 4 * H, N, pre0, pre1, s_scr, s_aff, s_aff + H,
+                    s_aff + 2 * H, s_aff + 3 * H, blockIdx.x == 0);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       bn0.sc[i] = s_aff[lane * VEC + i];

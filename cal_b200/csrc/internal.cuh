@@ -220,10 +220,10 @@ __device__ __forceinline__ bool grid_sum(const Ctx& c, int site, double* sTot, i
 struct BnPre {
   float g, b, rm, rv;
 };
-__device__ __forceinline__ BnPre bn_prefetch(const Ctx& c, int id) {
+__device__ __forceinline__ BnPre bn_prefetch(const Ctx& c, int id, int t0 = 0) {     // channel threadIdx.x - t0
   BnPre p = {1.f, 0.f, 0.f, 1.f};
-  const int k = threadIdx.x;
-  if (k < c.bn_K[id]) {
+  const int k = (int)threadIdx.x - t0;
+  if (k >= 0 && k < c.bn_K[id]) {
     p.g = c.params[c.bn_gamma[id] + k];
     p.b = c.params[c.bn_beta[id] + k];
     if (c.bn_buffers != nullptr && c.bn_rm[id] >= 0) {
@@ -285,32 +285,57 @@ __device__ __forceinline__ void grid_sum_groups(const Ctx& c, int site, const do
   }
 }
 
-// G / n_prod: grid size and vector length of the producer; the sums of BatchNorm `id` start at voff
-// ([sum (K) | sum of squares (K)]).  scratch: >= 2K doubles of shared memory; s_sc / s_sh: K floats.
-// All threads call; K <= blockDim.x.
-__device__ __forceinline__ void bn_from_groups(const Ctx& c, int site, int id, int G, int n_prod, int voff, int count,
-                                               const BnPre& pre, double* scratch, float* s_sc, float* s_sh,
-                                               bool publish) {
-  const int K = c.bn_K[id];
-  const double* l1 = c.gsum + (size_t)site * c.gs_stride + (size_t)kMaxStatBlocks * c.gs_n;
+// Sum of the group vectors, value v of [voff, voff + nvals), second-level order of grid_sum.
+__device__ __forceinline__ double gs_group_total(const double* p, int ngrp, int n_prod) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int g = 0;
+  for (; g + 4 <= ngrp; g += 4) {
+    s0 += __ldcg(p + (size_t)(g + 0) * n_prod);
+    s1 += __ldcg(p + (size_t)(g + 1) * n_prod);
+    s2 += __ldcg(p + (size_t)(g + 2) * n_prod);
+    s3 += __ldcg(p + (size_t)(g + 3) * n_prod);
+  }
+  for (; g < ngrp; ++g) s0 += __ldcg(p + (size_t)g * n_prod);
+  return ngrp == 1 ? s0 : (s0 + s1) + (s2 + s3);
+}
+__device__ __forceinline__ const double* gs_l1(const Ctx& c, int site) {
+  return c.gsum + (size_t)site * c.gs_stride + (size_t)kMaxStatBlocks * c.gs_n;
+}
+// two vectors at once (both sets of loads in flight together): A -> scrA[0 .. nvals), B -> scrB[0 .. nvals)
+__device__ __forceinline__ void gs_sum_pair(const Ctx& c, int siteA, int voffA, int siteB, int voffB, int G, int n_prod,
+                                            int nvals, double* scrA, double* scrB) {
   const int ngrp = (G + kGsGroup - 1) / kGsGroup;
-  const int t = threadIdx.x, T = blockDim.x;
-  for (int v = t; v < 2 * K; v += T) {
-    const double* p = l1 + voff + v;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  const double* la = gs_l1(c, siteA) + voffA;
+  const double* lb = gs_l1(c, siteB) + voffB;
+  for (int v = threadIdx.x; v < nvals; v += blockDim.x) {
+    const double* pa = la + v;
+    const double* pb = lb + v;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
     int g = 0;
     for (; g + 4 <= ngrp; g += 4) {
-      s0 += __ldcg(p + (size_t)(g + 0) * n_prod);
-      s1 += __ldcg(p + (size_t)(g + 1) * n_prod);
-      s2 += __ldcg(p + (size_t)(g + 2) * n_prod);
-      s3 += __ldcg(p + (size_t)(g + 3) * n_prod);
+      const double x0 = __ldcg(pa + (size_t)(g + 0) * n_prod), x1 = __ldcg(pa + (size_t)(g + 1) * n_prod);
+      const double x2 = __ldcg(pa + (size_t)(g + 2) * n_prod), x3 = __ldcg(pa + (size_t)(g + 3) * n_prod);
+      const double y0 = __ldcg(pb + (size_t)(g + 0) * n_prod), y1 = __ldcg(pb + (size_t)(g + 1) * n_prod);
+      const double y2 = __ldcg(pb + (size_t)(g + 2) * n_prod), y3 = __ldcg(pb + (size_t)(g + 3) * n_prod);
+      a0 += x0; a1 += x1; a2 += x2; a3 += x3;
+      b0 += y0; b1 += y1; b2 += y2; b3 += y3;
     }
-    for (; g < ngrp; ++g) s0 += __ldcg(p + (size_t)g * n_prod);
-    scratch[v] = ngrp == 1 ? s0 : (s0 + s1) + (s2 + s3);
+    for (; g < ngrp; ++g) {
+      a0 += __ldcg(pa + (size_t)g * n_prod);
+      b0 += __ldcg(pb + (size_t)g * n_prod);
+    }
+    scrA[v] = ngrp == 1 ? a0 : (a0 + a1) + (a2 + a3);
+    scrB[v] = ngrp == 1 ? b0 : (b0 + b1) + (b2 + b3);
   }
-  __syncthreads();
-  if (t < K) {
-    const double s = scratch[t], q = scratch[K + t];
+}
+
+// forward finalisation of BatchNorm `id` from its totals tot[0 .. 2K) by threads [t0, t0 + K)
+__device__ __forceinline__ void bn_fwd_finalize_smem(const Ctx& c, int id, int count, const BnPre& pre, const double* tot,
+                                                     float* s_sc, float* s_sh, bool publish, int t0) {
+  const int K = c.bn_K[id];
+  const int t = (int)threadIdx.x - t0;
+  if (t >= 0 && t < K) {
+    const double s = tot[t], q = tot[K + t];
     double mean = 0.0, var = 0.0;
     if (count > 0) {
       mean = s / count;
@@ -332,38 +357,17 @@ __device__ __forceinline__ void bn_from_groups(const Ctx& c, int site, int id, i
         c.bn_buffers[c.bn_rm[id] + t] = (1.f - c.momentum) * pre.rm + c.momentum * (float)mean;
         c.bn_buffers[c.bn_rv[id] + t] = (1.f - c.momentum) * pre.rv + c.momentum * (float)unb;
       }
+      if (t == 0 && c.nbt != nullptr) c.nbt[id] += 1;
     }
   }
-  if (publish && t == 0 && c.nbt != nullptr) c.nbt[id] += 1;
-  __syncthreads();
 }
-
-// The same hand-over for the BatchNorm BACKWARD sums (sum dy | sum dy * xhat): c1 = mean(dy),
-// c2 = mean(dy * xhat) into shared memory for this CTA; CTA `publish` writes d gamma / d beta and the record.
-__device__ __forceinline__ void bn_bwd_from_groups(const Ctx& c, int site, int id, int G, int n_prod, int voff,
-                                                   int count, double* scratch, float* s_c1, float* s_c2,
-                                                   bool publish) {
+__device__ __forceinline__ void bn_bwd_finalize_smem(const Ctx& c, int id, int count, const double* tot, float* s_c1,
+                                                     float* s_c2, bool publish, int t0) {
   const int K = c.bn_K[id];
-  const double* l1 = c.gsum + (size_t)site * c.gs_stride + (size_t)kMaxStatBlocks * c.gs_n;
-  const int ngrp = (G + kGsGroup - 1) / kGsGroup;
-  const int t = threadIdx.x, T = blockDim.x;
-  for (int v = t; v < 2 * K; v += T) {
-    const double* p = l1 + voff + v;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int g = 0;
-    for (; g + 4 <= ngrp; g += 4) {
-      s0 += __ldcg(p + (size_t)(g + 0) * n_prod);
-      s1 += __ldcg(p + (size_t)(g + 1) * n_prod);
-      s2 += __ldcg(p + (size_t)(g + 2) * n_prod);
-      s3 += __ldcg(p + (size_t)(g + 3) * n_prod);
-    }
-    for (; g < ngrp; ++g) s0 += __ldcg(p + (size_t)g * n_prod);
-    scratch[v] = ngrp == 1 ? s0 : (s0 + s1) + (s2 + s3);
-  }
-  __syncthreads();
-  if (t < K) {
+  const int t = (int)threadIdx.x - t0;
+  if (t >= 0 && t < K) {
     const double inv = count > 0 ? 1.0 / count : 0.0;
-    const double a = scratch[t], b = scratch[K + t];
+    const double a = tot[t], b = tot[K + t];
     const float c1 = (float)(a * inv), c2 = (float)(b * inv);
     s_c1[t] = c1;
     s_c2[t] = c2;
@@ -374,6 +378,58 @@ __device__ __forceinline__ void bn_bwd_from_groups(const Ctx& c, int site, int i
       c.grads[c.bn_beta[id] + t] = (float)a;
     }
   }
+}
+
+// G / n_prod: grid size and vector length of the producer; the sums of BatchNorm `id` start at voff
+// ([sum (K) | sum of squares (K)]).  scratch: >= 2K doubles of shared memory; s_sc / s_sh: K floats.
+// All threads call; K <= blockDim.x.  `pre`: THIS thread's prefetch, i.e. of channel threadIdx.x.
+__device__ __forceinline__ void bn_from_groups(const Ctx& c, int site, int id, int G, int n_prod, int voff, int count,
+                                               const BnPre& pre, double* scratch, float* s_sc, float* s_sh,
+                                               bool publish) {
+  const int K = c.bn_K[id];
+  const int ngrp = (G + kGsGroup - 1) / kGsGroup;
+  const double* l1 = gs_l1(c, site) + voff;
+  for (int v = threadIdx.x; v < 2 * K; v += blockDim.x) scratch[v] = gs_group_total(l1 + v, ngrp, n_prod);
+  __syncthreads();
+  bn_fwd_finalize_smem(c, id, count, pre, scratch, s_sc, s_sh, publish, 0);
+  __syncthreads();
+}
+// Two BatchNorms whose sums sit in the same producer (bnc | bno): one pass, one pair of barriers.
+// scratch: >= 4K doubles; threads [0, K) finalise A, [K, 2K) finalise B (2K <= blockDim.x);
+// `preA` must be the prefetch of channel threadIdx.x of A, `preB` of channel threadIdx.x - K of B.
+__device__ __forceinline__ void bn_from_groups2(const Ctx& c, int siteA, int idA, int voffA, int siteB, int idB,
+                                                int voffB, int G, int n_prod, int count, const BnPre& preA,
+                                                const BnPre& preB, double* scratch, float* s_scA, float* s_shA,
+                                                float* s_scB, float* s_shB, bool publish) {
+  const int K = c.bn_K[idA];
+  gs_sum_pair(c, siteA, voffA, siteB, voffB, G, n_prod, 2 * K, scratch, scratch + 2 * K);
+  __syncthreads();
+  bn_fwd_finalize_smem(c, idA, count, preA, scratch, s_scA, s_shA, publish, 0);
+  bn_fwd_finalize_smem(c, idB, count, preB, scratch + 2 * K, s_scB, s_shB, publish, K);
+  __syncthreads();
+}
+
+// The same hand-over for the BatchNorm BACKWARD sums (sum dy | sum dy * xhat): c1 = mean(dy),
+// c2 = mean(dy * xhat) into shared memory for this CTA; CTA `publish` writes d gamma / d beta and the record.
+__device__ __forceinline__ void bn_bwd_from_groups(const Ctx& c, int site, int id, int G, int n_prod, int voff,
+                                                   int count, double* scratch, float* s_c1, float* s_c2,
+                                                   bool publish) {
+  const int K = c.bn_K[id];
+  const int ngrp = (G + kGsGroup - 1) / kGsGroup;
+  const double* l1 = gs_l1(c, site) + voff;
+  for (int v = threadIdx.x; v < 2 * K; v += blockDim.x) scratch[v] = gs_group_total(l1 + v, ngrp, n_prod);
+  __syncthreads();
+  bn_bwd_finalize_smem(c, id, count, scratch, s_c1, s_c2, publish, 0);
+  __syncthreads();
+}
+__device__ __forceinline__ void bn_bwd_from_groups2(const Ctx& c, int siteA, int idA, int siteB, int idB, int G,
+                                                    int n_prod, int count, double* scratch, float* s_c1A, float* s_c2A,
+                                                    float* s_c1B, float* s_c2B, bool publish) {
+  const int K = c.bn_K[idA];
+  gs_sum_pair(c, siteA, 0, siteB, 0, G, n_prod, 2 * K, scratch, scratch + 2 * K);
+  __syncthreads();
+  bn_bwd_finalize_smem(c, idA, count, scratch, s_c1A, s_c2A, publish, 0);
+  bn_bwd_finalize_smem(c, idB, count, scratch + 2 * K, s_c1B, s_c2B, publish, K);
   __syncthreads();
 }
 
