@@ -723,6 +723,26 @@ __device__ __forceinline__ void stage_matrix_async(float* sdst, const float* gsr
 // acc[r][c] += sum_k sA[(warp*RPW + r) * lda + k] * sW[k * ldw + lane*VEC + c]   (K % 4 == 0)
 // The operands of the next 4-k step are loaded into registers while the current step's FMAs
 // issue (the CTA runs 2 warps per scheduler, too few to hide shared-memory latency otherwise).
+// Packed fp32 pairs (sm_100a FFMA2, PTX fma.rn.f32x2): two IEEE round-to-nearest FMAs per instruction, so
+// results are bit-identical to scalar fmaf while the FMA-bound inner loops need half the issue
+// slots.  ptxas folds the duplicated scalar into the instruction's broadcast operand (R.F32).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// c + (a, a) * b, element-wise
+__device__ __forceinline__ f32x2 ffma2_bcast(float a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  const f32x2 aa = pack2(a, a);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(aa), "l"(b), "l"(c));
+  return r;
+}
+
 template <int VEC>
 __device__ __forceinline__ void load_w4(const float* __restrict__ wp, int ldw, float (&w)[4][VEC]) {
 #pragma unroll
@@ -748,6 +768,13 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ sA, int lda,
   const float* w0 = sW + lane * VEC;
   float4 a[RPW], an[RPW];
   float w[4][VEC], wn[4][VEC];
+  f32x2 acc2[RPW][VEC / 2 > 0 ? VEC / 2 : 1];           // the accumulators as FFMA2 pairs (VEC even)
+  if constexpr (VEC % 2 == 0) {
+#pragma unroll
+    for (int r = 0; r < RPW; ++r)
+#pragma unroll
+      for (int cc = 0; cc < VEC / 2; ++cc) acc2[r][cc] = pack2(acc[r][2 * cc], acc[r][2 * cc + 1]);
+  }
 #pragma unroll
   for (int r = 0; r < RPW; ++r) a[r] = *reinterpret_cast<const float4*>(a0 + r * lda);
   load_w4<VEC>(w0, ldw, w);
@@ -762,8 +789,14 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ sA, int lda,
 #pragma unroll
       for (int r = 0; r < RPW; ++r) {
         float av = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
+        if constexpr (VEC % 2 == 0) {
 #pragma unroll
-        for (int cc = 0; cc < VEC; ++cc) acc[r][cc] = fmaf(av, w[kk][cc], acc[r][cc]);
+          for (int cc = 0; cc < VEC / 2; ++cc)
+            acc2[r][cc] = ffma2_bcast(av, pack2(w[kk][2 * cc], w[kk][2 * cc + 1]), acc2[r][cc]);
+        } else {
+#pragma unroll
+          for (int cc = 0; cc < VEC; ++cc) acc[r][cc] = fmaf(av, w[kk][cc], acc[r][cc]);
+        }
       }
     }
 #pragma unroll
@@ -772,6 +805,12 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ sA, int lda,
     for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
       for (int cc = 0; cc < VEC; ++cc) w[kk][cc] = wn[kk][cc];
+  }
+  if constexpr (VEC % 2 == 0) {
+#pragma unroll
+    for (int r = 0; r < RPW; ++r)
+#pragma unroll
+      for (int cc = 0; cc < VEC / 2; ++cc) unpack2(acc2[r][cc], acc[r][2 * cc], acc[r][2 * cc + 1]);
   }
 }
 
@@ -817,21 +856,41 @@ struct OuterAcc {
                                              int ldq, int rows) {
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     float p[MT], q[MT], pn[MT], qn[MT];
+    f32x2 acc2[MT][MT / 2 > 0 ? MT / 2 : 1];             // FFMA2 pairs over the column index (MT even)
+    if constexpr (MT % 2 == 0) {
+#pragma unroll
+      for (int a = 0; a < MT; ++a)
+#pragma unroll
+        for (int b = 0; b < MT / 2; ++b) acc2[a][b] = pack2(acc[a][2 * b], acc[a][2 * b + 1]);
+    }
     load_runs(sP, ty, p);
     load_runs(sQ, tx, q);
     for (int r = 0; r < rows; ++r) {
       const int rn = r + 1 < rows ? r + 1 : r;
       load_runs(sP + (size_t)rn * ldp, ty, pn);
       load_runs(sQ + (size_t)rn * ldq, tx, qn);
+      if constexpr (MT % 2 == 0) {
 #pragma unroll
-      for (int a = 0; a < MT; ++a)
+        for (int a = 0; a < MT; ++a)
 #pragma unroll
-        for (int b = 0; b < MT; ++b) acc[a][b] = fmaf(p[a], q[b], acc[a][b]);
+          for (int b = 0; b < MT / 2; ++b) acc2[a][b] = ffma2_bcast(p[a], pack2(q[2 * b], q[2 * b + 1]), acc2[a][b]);
+      } else {
+#pragma unroll
+        for (int a = 0; a < MT; ++a)
+#pragma unroll
+          for (int b = 0; b < MT; ++b) acc[a][b] = fmaf(p[a], q[b], acc[a][b]);
+      }
 #pragma unroll
       for (int a = 0; a < MT; ++a) {
         p[a] = pn[a];
         q[a] = qn[a];
       }
+    }
+    if constexpr (MT % 2 == 0) {
+#pragma unroll
+      for (int a = 0; a < MT; ++a)
+#pragma unroll
+        for (int b = 0; b < MT / 2; ++b) unpack2(acc2[a][b], acc[a][2 * b], acc[a][2 * b + 1]);
     }
   }
   __device__ __forceinline__ void store(float* __restrict__ dst, int ldd) const {   // dst [H][ldd], 16-byte aligned rows
