@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
     for (int r = 0; r < kRPW; ++r)
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
-    tile_gemm_auto<VEC, kRPW>(sA, LDA, sW, H, H, sX, LDA, acc);      // (the row stage is free: used to hand the tile back)
+    tile_gemm<VEC, kRPW>(sA, LDA, sW, H, H, acc);
     PT_MARK();                                         // 5: GEMM
     // ---- epilogue ----
 #pragma unroll
@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(256) k_masked_fwd_both(const Ctx c) {
       for (int r = 0; r < kRPW; ++r)
 #pragma unroll
         for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
-      tile_gemm_auto<VEC, kRPW>(sA + br * kTileRows * LDA, LDA, sW + br * H * H, H, H, sX + br * kTileRows * LDA, LDA, acc);
+      tile_gemm<VEC, kRPW>(sA + br * kTileRows * LDA, LDA, sW + br * H * H, H, H, acc);
       float* zo = br ? z1 : z0;
 #pragma unroll
       for (int r = 0; r < kRPW; ++r) {
@@ -740,7 +740,7 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
     for (int r = 0; r < kRPW; ++r)
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
-    tile_gemm_auto<VEC, kRPW>(sU, LDA, sW, H, H, sXD, LDA, acc);
+    tile_gemm<VEC, kRPW>(sU, LDA, sW, H, H, acc);
     PT_MARK();                                         // 4: GEMM dX
 #pragma unroll
     for (int r = 0; r < kRPW; ++r) {
@@ -792,7 +792,6 @@ __global__ void __launch_bounds__(256) k_masked_bwd_gemm(const Ctx c) {
   float* sU = sW + H * H;
   float* sY = sU + kTileRows * LDA;
   double* sRed = reinterpret_cast<double*>(sY + kTileRows * LDA);
-  float* sOut = reinterpret_cast<float*>(sRed + kRowWarps * H);      // [R][LDA] GEMM hand-back tile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int branch = blockIdx.y;
   stage_matrix_async(sW, c.wt_conv(c.L + branch), H * H);
@@ -838,7 +837,7 @@ __global__ void __launch_bounds__(256) k_masked_bwd_gemm(const Ctx c) {
     for (int r = 0; r < kRPW; ++r)
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
-    tile_gemm_auto<VEC, kRPW>(sU, LDA, sW, H, H, sOut, LDA, acc);
+    tile_gemm<VEC, kRPW>(sU, LDA, sW, H, H, acc);
 #pragma unroll
     for (int r = 0; r < kRPW; ++r) {
       const int i = row0 + warp * kRPW + r;
@@ -877,7 +876,6 @@ __global__ void __launch_bounds__(256) k_gin_b_fwd(const Ctx c, const int layer)
   float* sW = reinterpret_cast<float*>(smem_raw);
   float* sA = sW + H * H;
   double* sRed = reinterpret_cast<double*>(sA + kTileRows * LDA);
-  float* sOut = reinterpret_cast<float*>(sRed + kRowWarps * H);      // [R][LDA] GEMM hand-back tile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   stage_matrix_async(sW, c.wt_gin2(layer), H * H);
   const bool cs = bn_consumer_side(c);               // the layer's inner BatchNorm is finalised here
@@ -925,7 +923,7 @@ __global__ void __launch_bounds__(256) k_gin_b_fwd(const Ctx c, const int layer)
     for (int r = 0; r < kRPW; ++r)
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
-    tile_gemm_auto<VEC, kRPW>(sA, LDA, sW, H, H, sOut, LDA, acc);
+    tile_gemm<VEC, kRPW>(sA, LDA, sW, H, H, acc);
 #pragma unroll
     for (int r = 0; r < kRPW; ++r) {
       const int i = row0 + warp * kRPW + r;
@@ -953,7 +951,6 @@ __global__ void __launch_bounds__(256) k_gin_b_bwd(const Ctx c, const int layer)
   float* sU = sW + H * H;
   float* sY = sU + kTileRows * LDA;
   double* sRed = reinterpret_cast<double*>(sY + kTileRows * LDA);
-  float* sOut = reinterpret_cast<float*>(sRed + kRowWarps * H);      // [R][LDA] GEMM hand-back tile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   stage_matrix_async(sW, c.params + c.po.gin_w2[layer], H * H);     // [out, in] as stored: d r = u W2
   pdl_sync();                                        // everything below may read the predecessor's output
@@ -1007,7 +1004,7 @@ __global__ void __launch_bounds__(256) k_gin_b_bwd(const Ctx c, const int layer)
     for (int r = 0; r < kRPW; ++r)
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
-    tile_gemm_auto<VEC, kRPW>(sU, LDA, sW, H, H, sOut, LDA, acc);
+    tile_gemm<VEC, kRPW>(sU, LDA, sW, H, H, acc);
 #pragma unroll
     for (int r = 0; r < kRPW; ++r) {
       const int i = row0 + warp * kRPW + r;
@@ -1206,7 +1203,7 @@ int launch_gin_forward(const Ctx& c, int layer, cudaStream_t s) {
     int rc = set_smem(k_conv_fwd<VEC, 3>, smem);
     if (rc) return rc;
     launch_k(k_conv_fwd<VEC, 3>, dim3(c.g_tile), dim3(256), smem, s, c, layer);
-    smem = (size_t)c.H * c.H * 4 + 2 * (size_t)kTileRows * (c.H + kPad) * 4 + (size_t)kRowWarps * c.H * 8;
+    smem = (size_t)c.H * c.H * 4 + (size_t)kTileRows * (c.H + kPad) * 4 + (size_t)kRowWarps * c.H * 8;
     if (last) {
       rc = set_smem(k_gin_b_fwd<VEC, true>, smem);
       if (rc) return rc;
@@ -1224,7 +1221,7 @@ int launch_gin_forward(const Ctx& c, int layer, cudaStream_t s) {
 
 int launch_gin_backward(const Ctx& c, int layer, cudaStream_t s) {
   CAL_DISPATCH_VEC(c.H, {
-    size_t smem = (size_t)c.H * c.H * 4 + 3 * (size_t)kTileRows * (c.H + kPad) * 4 + (size_t)kRowWarps * c.H * 8;
+    size_t smem = (size_t)c.H * c.H * 4 + 2 * (size_t)kTileRows * (c.H + kPad) * 4 + (size_t)kRowWarps * c.H * 8;
     int rc = set_smem(k_gin_b_bwd<VEC>, smem);
     if (rc) return rc;
     launch_k(k_gin_b_bwd<VEC>, dim3(c.g_tile), dim3(256), smem, s, c, layer);
@@ -1240,7 +1237,7 @@ int launch_gin_backward(const Ctx& c, int layer, cudaStream_t s) {
 
 int launch_masked_bwd_gemm(const Ctx& c, cudaStream_t s) {
   CAL_DISPATCH_VEC(c.H, {
-    size_t smem = (size_t)c.H * c.H * 4 + 3 * (size_t)kTileRows * (c.H + kPad) * 4 + (size_t)kRowWarps * c.H * 8;
+    size_t smem = (size_t)c.H * c.H * 4 + 2 * (size_t)kTileRows * (c.H + kPad) * 4 + (size_t)kRowWarps * c.H * 8;
     int rc = set_smem(k_masked_bwd_gemm<VEC>, smem);
     if (rc) return rc;
     launch_k(k_masked_bwd_gemm<VEC>, dim3(c.g_tile, 2), dim3(256), smem, s, c);

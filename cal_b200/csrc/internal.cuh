@@ -814,99 +814,11 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ sA, int lda,
   }
 }
 
-// Row padding of the shared-memory activation tiles (floats): consecutive tile rows start 4 banks apart, so
-// the 8 row groups of tile_gemm_slab read conflict-free.
+// Row padding of the shared-memory activation tiles (floats): rows of consecutive tile rows start 4
+// banks apart.  (A column-slab mapping of this product -- warp w owns columns [16w, 16w+16) of all 24
+// rows, 7 instead of 19 shared-memory wavefronts per warp per 4-k step -- was measured on B200 and is
+// NOT faster: the loop is bound by FFMA issue with 2 warps per scheduler, not by LDS; profiles/README.md.)
 constexpr int kPad = 4;
-
-// The same product with a shared-memory-bandwidth friendly mapping.  tile_gemm gives every warp full
-// rows, so all 8 warps re-read the whole weight row for every k: 19 shared-memory wavefronts per warp
-// per 4-k step = 152 LSU cycles per step for the SM against 96 FMA-pipe cycles -- with FFMA2 halving
-// the issue pressure the loop is LSU-bound.  Here warp w owns the column slab [w * H/8, (w+1) * H/8) of
-// ALL 24 rows: lane (rg = lane / 4, cq = lane % 4) accumulates rows {rg, rg + 8, rg + 16} x VEC columns,
-// so per step a warp issues 3 conflict-free 128-byte activation loads (rows padded to lda = H + kPad)
-// and 4 64-byte weight loads: 7 wavefronts.  The result is handed back in the row-per-warp layout of
-// the epilogues through `sOut` ([R][ldo], must not alias sA / sW; all threads call; one
-// __syncthreads inside).  Accumulation order over k is tile_gemm's => bit-identical results.
-template <int VEC, int RPW>
-__device__ __forceinline__ void tile_gemm_slab(const float* __restrict__ sA, int lda, const float* __restrict__ sW,
-                                               int ldw, int K, float* __restrict__ sOut, int ldo,
-                                               float (&acc)[RPW][VEC]) {
-  static_assert(kRowWarps == 8 && VEC % 2 == 0, "8 row groups x 4 column quads; FFMA2 pairs");
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rg = lane >> 2, cq = lane & 3;
-  constexpr int CW = 4 * VEC;                          // columns per warp = H / 8
-  const float* a0 = sA + (size_t)rg * lda;
-  const float* w0 = sW + warp * CW + cq * VEC;
-  f32x2 c2[RPW][VEC / 2];
-#pragma unroll
-  for (int r = 0; r < RPW; ++r)
-#pragma unroll
-    for (int cc = 0; cc < VEC / 2; ++cc) c2[r][cc] = pack2(0.f, 0.f);
-  float4 a[RPW], an[RPW];
-  float w[4][VEC], wn[4][VEC];
-#pragma unroll
-  for (int r = 0; r < RPW; ++r) a[r] = *reinterpret_cast<const float4*>(a0 + (size_t)r * 8 * lda);
-  load_w4<VEC>(w0, ldw, w);
-#pragma unroll 2
-  for (int k0 = 0; k0 < K; k0 += 4) {
-    const int kn = k0 + 4 < K ? k0 + 4 : k0;           // last step reloads itself (harmless)
-#pragma unroll
-    for (int r = 0; r < RPW; ++r) an[r] = *reinterpret_cast<const float4*>(a0 + (size_t)r * 8 * lda + kn);
-    load_w4<VEC>(w0 + (size_t)kn * ldw, ldw, wn);
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-      for (int r = 0; r < RPW; ++r) {
-        const float av = kk == 0 ? a[r].x : kk == 1 ? a[r].y : kk == 2 ? a[r].z : a[r].w;
-#pragma unroll
-        for (int cc = 0; cc < VEC / 2; ++cc)
-          c2[r][cc] = ffma2_bcast(av, pack2(w[kk][2 * cc], w[kk][2 * cc + 1]), c2[r][cc]);
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < RPW; ++r) a[r] = an[r];
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-      for (int cc = 0; cc < VEC; ++cc) w[kk][cc] = wn[kk][cc];
-  }
-#pragma unroll
-  for (int r = 0; r < RPW; ++r) {
-    float* o = sOut + (size_t)(rg + 8 * r) * ldo + warp * CW + cq * VEC;
-    float v[VEC];
-#pragma unroll
-    for (int cc = 0; cc < VEC / 2; ++cc) unpack2(c2[r][cc], v[2 * cc], v[2 * cc + 1]);
-    if constexpr (VEC == 4) {
-      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-    } else {
-      *reinterpret_cast<float2*>(o) = make_float2(v[0], v[1]);
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < RPW; ++r) {
-    const float* o = sOut + (size_t)(warp * RPW + r) * ldo + lane * VEC;
-    if constexpr (VEC == 4) {
-      const float4 t = *reinterpret_cast<const float4*>(o);
-      acc[r][0] = t.x; acc[r][1] = t.y; acc[r][2] = t.z; acc[r][3] = t.w;
-    } else {
-      const float2 t = *reinterpret_cast<const float2*>(o);
-      acc[r][0] = t.x; acc[r][1] = t.y;
-    }
-  }
-}
-
-// Dispatch: the slab mapping for H = 64 / 128, the row mapping (scalar FFMA) for H = 32.
-template <int VEC, int RPW>
-__device__ __forceinline__ void tile_gemm_auto(const float* __restrict__ sA, int lda, const float* __restrict__ sW,
-                                               int ldw, int K, float* __restrict__ sOut, int ldo,
-                                               float (&acc)[RPW][VEC]) {
-  if constexpr (VEC % 2 == 0) {
-    tile_gemm_slab<VEC, RPW>(sA, lda, sW, ldw, K, sOut, ldo, acc);
-  } else {
-    tile_gemm<VEC, RPW>(sA, lda, sW, ldw, K, acc);
-  }
-}
 
 // Outer-product accumulation over a row tile: acc[a][b] += sum_r sP[r*ld + kidx(a)] * sQ[r*ld + jidx(b)].
 // 256 threads cover an [H x H] result: thread (ty = tid / 16, tx = tid % 16) owns MT x MT entries with
