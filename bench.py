@@ -245,7 +245,7 @@ def run_reference(a, rank, world):
         "e2e": {"value": gps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=OUT, flush=True)
 
 
 def workload_config(a, bs, batches, residency):
@@ -502,13 +502,22 @@ def run_gpu(a, rank, local_rank, world):
             "roofline": roofline, "cpu_baseline": cpu, "stages": stage_tab,
             "loss_after": loss_after[:4],
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=OUT, flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+OUT = sys.stdout
+
+
 def main():
+    # stdout carries exactly ONE JSON line: keep a private handle on it and point fd 1 at stderr, so that
+    # whatever a library writes to fd 1 (NCCL's "NCCL version ..." banner under torchrun) cannot precede it
+    global OUT
+    sys.stdout.flush()
+    OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -783,7 +783,7 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
 // (global_add_pool backward is the broadcast of the pooled gradient, model.py:115-116.)
 // ---------------------------------------------------------------------------------------------
 template <int VEC>
-__global__ void __launch_bounds__(256) k_masked_bwd_gemm(const Ctx c) {
+__global__ void __launch_bounds__(256, 2) k_masked_bwd_gemm(const Ctx c) {      // two branch CTAs per SM: <= 128 registers
   constexpr int H = 32 * VEC, LDA = H + kPad;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Dims d = load_dims(c);
@@ -798,7 +798,6 @@ __global__ void __launch_bounds__(256) k_masked_bwd_gemm(const Ctx c) {
   pdl_sync();                                        // everything below may read the predecessor's output
   const float* Z = c.Z + (size_t)branch * c.Nm * H;
   const float* A = c.agg + (size_t)branch * c.Nm * H;
-  const float* dpool = c.dpool + (size_t)branch * c.Bm * H;
   float* dagg = c.dagg + (size_t)branch * c.Nm * H;
   OuterAcc<H> dW;
   dW.zero();
@@ -819,7 +818,22 @@ __global__ void __launch_bounds__(256) k_masked_bwd_gemm(const Ctx c) {
       if (i < N) {
         RowVec<VEC> z, g;
         z.load_coherent(Z + (size_t)i * H, lane);
-        g.load_coherent(dpool + (size_t)c.node_graph[i] * H, lane);
+        // gradient of the pooled embedding of graph b, straight from the d-input rows of the three readouts
+        // (global_add_pool backward = broadcast, model.py:115-116; the c <- co path goes through the inverse
+        // permutation, model.py:152-157): no separate k_dpool launch
+        {
+          const int b = c.node_graph[i];
+          RowVec<VEC> g2;
+          if (branch == 0) {
+            g.load_coherent(c.du + ((size_t)0 * c.Bm + b) * 2 * H, lane);
+            g2.load_coherent(c.du + ((size_t)2 * c.Bm + c.invperm[b]) * 2 * H, lane);
+          } else {
+            g.load_coherent(c.du + ((size_t)1 * c.Bm + b) * 2 * H, lane);
+            g2.load_coherent(c.du + ((size_t)2 * c.Bm + b) * 2 * H + (c.cat ? H : 0), lane);
+          }
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) g.v[k] += g2.v[k];
+        }
         y.load_coherent(A + (size_t)i * H, lane);
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {

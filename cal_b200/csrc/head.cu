@@ -783,32 +783,6 @@ __global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_bwd
   PT_DUMP(c, 80);
 }
 
-// Gradient w.r.t. the pooled embeddings from the d-input rows of the three readouts; the c <- co
-// path is routed through the inverse permutation (model.py:152-157).
-template <int VEC>
-__global__ void __launch_bounds__(256) k_dpool(const Ctx c) {
-  pdl_sync();
-  constexpr int H = 32 * VEC;
-  const int B = clampB(c);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * kRowWarps + warp;
-  if (b >= B) return;
-  const int bi = c.invperm[b];       // co row that consumed xc_g[b]
-  RowVec<VEC> dc, dO, dco_c, dco_o;
-  dc.load_coherent(c.du + ((size_t)0 * c.Bm + b) * 2 * H, lane);
-  dO.load_coherent(c.du + ((size_t)1 * c.Bm + b) * 2 * H, lane);
-  dco_c.load_coherent(c.du + ((size_t)2 * c.Bm + bi) * 2 * H, lane);
-  dco_o.load_coherent(c.du + ((size_t)2 * c.Bm + b) * 2 * H + (c.cat ? H : 0), lane);
-  RowVec<VEC> oc, oo;
-#pragma unroll
-  for (int k = 0; k < VEC; ++k) {
-    oc.v[k] = dc.v[k] + dco_c.v[k];
-    oo.v[k] = dO.v[k] + dco_o.v[k];
-  }
-  oc.store(c.dpool + (size_t)b * H, lane);
-  oo.store(c.dpool + ((size_t)c.Bm + b) * H, lane);
-}
-
 template <typename K>
 int set_smem_h(K kernel, size_t bytes) {
   if (bytes > 32 * 1024) {
@@ -845,9 +819,8 @@ int launch_heads_backward(const Ctx& c, cudaStream_t s) {
     int rc = set_smem_h(k_readout_bwd<VEC>, smem);
     if (rc) return rc;
     launch_k(k_readout_bwd<VEC>, dim3(kRC, 3), dim3(256), smem, s, c);
-    launch_k(k_dpool<VEC>, dim3(ceil_div(c.Bm, kRowWarps)), dim3(256), 0, s, c);
   });
-  note_launches(2);
+  note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }

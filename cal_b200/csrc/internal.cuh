@@ -828,12 +828,29 @@ struct OuterAcc {
   static constexpr int MT = H / 16;
   static constexpr int HM = MT / 2 > 0 ? MT / 2 : 1;   // contiguous run
   static constexpr int NH = MT / HM;                   // number of runs (2, or 2 when MT == 2 -> HM = 1)
-  float acc[MT][MT];
+  static constexpr bool kPairs = MT % 2 == 0;          // accumulators live as FFMA2 pairs over the column index
+  f32x2 acc2[MT][kPairs ? MT / 2 : 1];
+  float acc1[kPairs ? 1 : MT][kPairs ? 1 : MT];
   __device__ __forceinline__ void zero() {
 #pragma unroll
-    for (int a = 0; a < MT; ++a)
+    for (int a = 0; a < MT; ++a) {
+      if constexpr (kPairs) {
 #pragma unroll
-      for (int b = 0; b < MT; ++b) acc[a][b] = 0.f;
+        for (int b = 0; b < MT / 2; ++b) acc2[a][b] = pack2(0.f, 0.f);
+      } else {
+#pragma unroll
+        for (int b = 0; b < MT; ++b) acc1[a][b] = 0.f;
+      }
+    }
+  }
+  __device__ __forceinline__ float get(int a, int b) const {
+    if constexpr (kPairs) {
+      float lo, hi;
+      unpack2(acc2[a][b >> 1], lo, hi);
+      return (b & 1) ? hi : lo;
+    } else {
+      return acc1[a][b];
+    }
   }
   __device__ __forceinline__ static int idx(int t, int a) { return (a / HM) * (H / NH) + t * HM + (a % HM); }
   // contiguous run of HM floats starting at element idx(t, run * HM); 16-byte aligned when HM == 4
@@ -856,20 +873,13 @@ struct OuterAcc {
                                              int ldq, int rows) {
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     float p[MT], q[MT], pn[MT], qn[MT];
-    f32x2 acc2[MT][MT / 2 > 0 ? MT / 2 : 1];             // FFMA2 pairs over the column index (MT even)
-    if constexpr (MT % 2 == 0) {
-#pragma unroll
-      for (int a = 0; a < MT; ++a)
-#pragma unroll
-        for (int b = 0; b < MT / 2; ++b) acc2[a][b] = pack2(acc[a][2 * b], acc[a][2 * b + 1]);
-    }
     load_runs(sP, ty, p);
     load_runs(sQ, tx, q);
     for (int r = 0; r < rows; ++r) {
       const int rn = r + 1 < rows ? r + 1 : r;
       load_runs(sP + (size_t)rn * ldp, ty, pn);
       load_runs(sQ + (size_t)rn * ldq, tx, qn);
-      if constexpr (MT % 2 == 0) {
+      if constexpr (kPairs) {
 #pragma unroll
         for (int a = 0; a < MT; ++a)
 #pragma unroll
@@ -878,19 +888,13 @@ struct OuterAcc {
 #pragma unroll
         for (int a = 0; a < MT; ++a)
 #pragma unroll
-          for (int b = 0; b < MT; ++b) acc[a][b] = fmaf(p[a], q[b], acc[a][b]);
+          for (int b = 0; b < MT; ++b) acc1[a][b] = fmaf(p[a], q[b], acc1[a][b]);
       }
 #pragma unroll
       for (int a = 0; a < MT; ++a) {
         p[a] = pn[a];
         q[a] = qn[a];
       }
-    }
-    if constexpr (MT % 2 == 0) {
-#pragma unroll
-      for (int a = 0; a < MT; ++a)
-#pragma unroll
-        for (int b = 0; b < MT / 2; ++b) unpack2(acc2[a][b], acc[a][2 * b], acc[a][2 * b + 1]);
     }
   }
   __device__ __forceinline__ void store(float* __restrict__ dst, int ldd) const {   // dst [H][ldd], 16-byte aligned rows
@@ -901,12 +905,12 @@ struct OuterAcc {
       for (int run = 0; run < NH; ++run) {
         float* p = dst + (size_t)idx(ty, a) * ldd + idx(tx, run * HM);
         if constexpr (HM == 4) {
-          *reinterpret_cast<float4*>(p) = make_float4(acc[a][run * HM], acc[a][run * HM + 1], acc[a][run * HM + 2],
-                                                      acc[a][run * HM + 3]);
+          *reinterpret_cast<float4*>(p) = make_float4(get(a, run * HM), get(a, run * HM + 1), get(a, run * HM + 2),
+                                                      get(a, run * HM + 3));
         } else if constexpr (HM == 2) {
-          *reinterpret_cast<float2*>(p) = make_float2(acc[a][run * HM], acc[a][run * HM + 1]);
+          *reinterpret_cast<float2*>(p) = make_float2(get(a, run * HM), get(a, run * HM + 1));
         } else {
-          *p = acc[a][run * HM];
+          *p = get(a, run * HM);
         }
       }
   }
