@@ -159,7 +159,7 @@ enum cal_ws_region {
   CAL_WS_DLOGIT,       /* f32[3][maxB][C] */
   CAL_WS_DH,           /* f32[3][maxB][H] */
   CAL_WS_DU,           /* f32[3][maxB][2H] */
-  CAL_WS_DPOOL,        /* f32[2][maxB][H] */
+  CAL_WS_DPOOL,        /* f32[2][maxB][H] (unused: the masked backward GEMM reads CAL_WS_DU directly) */
   CAL_WS_DAGG,         /* f32[2][maxN][H] */
   CAL_WS_DYM,          /* f32[2][maxN][H] */
   CAL_WS_DNRM,         /* f32[EP][2] */
