@@ -85,14 +85,6 @@ struct RowVec {
   }
 };
 
-template <int VEC>
-__device__ __forceinline__ float dot_lane(const RowVec<VEC>& a, const RowVec<VEC>& b) {
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) s = fmaf(a.v[i], b.v[i], s);
-  return s;
-}
-
 // Grid-wide "am I the last CTA" test on a self-resetting counter.  All threads must call.
 // `expected` = number of CTAs that arrive on this counter.
 __device__ __forceinline__ bool grid_last_block(unsigned int* counter, unsigned int expected) {
@@ -109,47 +101,6 @@ __device__ __forceinline__ bool grid_last_block(unsigned int* counter, unsigned 
   }
   __syncthreads();
   return s_last != 0;
-}
-
-// Row-per-warp kernels: reduce NV per-lane double vectors (lane owns VEC channels) over the
-// CTA's warps and write them to partial[(part * NVT + v0 + v) * K + koff + k], k < H.  `sbuf` holds
-// kRowWarps * H doubles.  Summation order is fixed (warp 0..7) => deterministic.
-template <int VEC, int NV>
-__device__ __forceinline__ void block_partial_store_ex(double (&acc)[NV][VEC], double* sbuf, double* partial,
-                                                       int H, int part, int NVT, int v0, int K, int koff) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) sbuf[warp * H + lane * VEC + i] = acc[v][i];
-    __syncthreads();
-    for (int k = threadIdx.x; k < H; k += blockDim.x) {
-      double s = 0.0;
-#pragma unroll
-      for (int w = 0; w < kRowWarps; ++w) s += sbuf[w * H + k];
-      partial[((size_t)part * NVT + v0 + v) * K + koff + k] = s;
-    }
-  }
-}
-template <int VEC, int NV>
-__device__ __forceinline__ void block_partial_store(double (&acc)[NV][VEC], double* sbuf, double* partial,
-                                                    int H) {
-  block_partial_store_ex<VEC, NV>(acc, sbuf, partial, H, blockIdx.x, NV, 0, H, 0);
-}
-
-// Sum over the G CTAs' partials of vector v, channel k (fixed order).
-__device__ __forceinline__ double partial_total(const double* partial, int G, int NV, int v, int H, int k) {
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  int g = 0;
-  for (; g + 4 <= G; g += 4) {
-    s0 += partial[((size_t)(g + 0) * NV + v) * H + k];
-    s1 += partial[((size_t)(g + 1) * NV + v) * H + k];
-    s2 += partial[((size_t)(g + 2) * NV + v) * H + k];
-    s3 += partial[((size_t)(g + 3) * NV + v) * H + k];
-  }
-  for (; g < G; ++g) s0 += partial[((size_t)g * NV + v) * H + k];
-  return (s0 + s1) + (s2 + s3);
 }
 
 // ---- programmatic dependent launch (PDL) ----

@@ -147,19 +147,12 @@ __global__ void __launch_bounds__(256) k_feat_fwd(const Ctx c) {
 //   MODE 0: backbone layer l < L-1      x_{l+2} = relu(A bn_l(x_{l+1}) W_l + b_l)   (model.py:93-95)
 //   MODE 1: last backbone layer; epilogue also evaluates node_att_mlp / edge_att_mlp projections
 //           (model.py:97-111) and the statistics of bnc / bno on att * x
-//   MODE 2: context_convs / objects_convs on the soft-masked features with the attention-weighted
-//           norm (model.py:112-113, gcn_conv.py:59-70 with edge_weight); blockIdx.y = branch
+//   (the two masked convs, model.py:112-113, have their own kernel below: k_masked_fwd_both)
 //   MODE 3: first half of a CausalGIN layer (model.py:187-193, PyG GINConv): h = (x_i + sum_j x_j) W1^T + b1,
 //           i.e. the same gather with unit weights and no BatchNorm on load, no ReLU; the epilogue
 //           accumulates the statistics of the layer's inner BatchNorm (BN id 1 + layer)
 // smem: sW [H][H] | sA [R][H] | sRed f64 [8][H] | sPtr [R+4] | sSrc [EC] | sNrm [EC]
 // ---------------------------------------------------------------------------------------------
-template <int VEC>
-constexpr size_t conv_smem_bytes() {
-  constexpr int H = 32 * VEC;
-  return (size_t)H * H * 4 + (size_t)kTileRows * (H + kPad) * 4 + (size_t)kRowWarps * H * 8 + (kTileRows + 4) * 4 +
-         (size_t)kEdgeStage * 8;
-}
 // forward layers: sW [H][H] | sA [R][H] | sRed f64 [8][H] | sPtr [R+4] | sX [stage][H] | sXn | sXa | sXs [stage]
 template <int VEC>
 constexpr size_t convf_smem_bytes(int stage_rows) {
@@ -172,29 +165,24 @@ template <int VEC, int MODE>
 __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) {
   constexpr int H = 32 * VEC, LDA = H + kPad;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ double sTot[MODE == 2 ? 1 : 4 * H];
+  __shared__ double sTot[4 * H];
   const Dims d = load_dims(c);
   const int N = d.N;
   float* sW = reinterpret_cast<float*>(smem_raw);
   float* sA = sW + H * H;
   double* sRed = reinterpret_cast<double*>(sA + kTileRows * LDA);
   int* sPtr = reinterpret_cast<int*>(sRed + kRowWarps * H);
-  constexpr int kStage = MODE == 2 ? kStageMasked : kStageFwd;
+  constexpr int kStage = kStageFwd;
   float* sX = reinterpret_cast<float*>(sPtr + kTileRows + 4);   // [kStage][H] staged neighbour rows (16-byte aligned)
   float* sXn = sX + (size_t)kStage * H;                // [kStage] per-entry norm factor
-  float* sXa = sXn + kStage;                           // [kStage] per-entry node attention (MODE 2)
-  int* sXs = reinterpret_cast<int*>(sXa + kStage);     // [kStage] source node of the entry
+  int* sXs = reinterpret_cast<int*>(sXn + kStage);     // [kStage] source node of the entry
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int branch = MODE == 2 ? blockIdx.y : 0;
-  const int conv = MODE == 2 ? c.L + branch : layer;
-  const int bn_in = MODE == 2 ? c.L + 1 + branch : (MODE == 3 ? kBnIdentity : 1 + layer);
+  const int bn_in = MODE == 3 ? kBnIdentity : 1 + layer;
   const float* W = MODE == 3 ? c.wt_conv(layer)      // torch Linear stores [out, in]: the transposed copy is [in, out]
-                             : c.params + (MODE == 2 ? (branch ? c.po.objects_w : c.po.context_w) : c.po.convs_w[layer]);
-  const float* bias = c.params + (MODE == 2 ? (branch ? c.po.objects_b : c.po.context_b) : c.po.convs_b[layer]);
-  const float* xin = MODE == 2 ? c.Xl(c.L) : c.Xl(layer);
-  float* xout = MODE == 2 ? c.Z + (size_t)branch * c.Nm * H : (MODE == 3 ? c.gin_h(layer) : c.Xl(layer + 1));
-  float* aggout = c.agg + (size_t)branch * c.Nm * H;
-  (void)conv;
+                             : c.params + c.po.convs_w[layer];
+  const float* bias = c.params + c.po.convs_b[layer];
+  const float* xin = c.Xl(layer);
+  float* xout = MODE == 3 ? c.gin_h(layer) : c.Xl(layer + 1);
 
   stage_matrix_async(sW, W, H * H);
   // backbone layers in training: the BatchNorm on the input is finalised HERE from the group sums the
@@ -245,12 +233,7 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
         for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
           const int src = c.in_src[pb + e];
           sXs[e] = src;
-          if (MODE == 2) {
-            sXn[e] = c.edge_wn[(size_t)(pb + e) * 2 + branch];         // dis_w[source] * edge_att
-            sXa[e] = c.edge_na[(size_t)(pb + e) * 2 + branch];         // node_att[source]
-          } else {
-            sXn[e] = MODE == 3 ? 1.f : c.in_norm[pb + e];
-          }
+          sXn[e] = MODE == 3 ? 1.f : c.in_norm[pb + e];
         }
         __syncthreads();
         // one 16-byte cp.async per lane and row: a warp moves one neighbour row per instruction and
@@ -260,51 +243,32 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
         cp_async_wait_all();
         __syncthreads();
         for (int lr = rb + warp; lr < re; lr += kRowWarps) {
-          const int i = row0 + lr;
           const int e0 = sPtr[lr] - pb, e1 = sPtr[lr + 1] - pb;
-          float di = 1.f;
-          if (MODE == 2) di = c.disw[(size_t)i * 2 + branch];
           RowVec<VEC> a;
           a.zero();
           for (int e = e0; e < e1; ++e) {
             RowVec<VEC> v;
             v.load_coherent(sX + (size_t)e * H, lane);
-            const float w = MODE == 2 ? sXn[e] * di : sXn[e];            // dis[row] * w * dis[col]
-            const float am = MODE == 2 ? sXa[e] : 1.f;
+            const float w = sXn[e];                                      // dis[row] * dis[col] (1 for GIN)
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-              float x = MODE == 2 ? am * v.v[k] : v.v[k];
-              a.v[k] = fmaf(w, fmaf(x, bn.sc[k], bn.sh[k]), a.v[k]);
-            }
+            for (int k = 0; k < VEC; ++k) a.v[k] = fmaf(w, fmaf(v.v[k], bn.sc[k], bn.sh[k]), a.v[k]);
           }
-          if (MODE == 2) a.store(aggout + (size_t)i * H, lane);
           a.store(sA + lr * LDA, lane);
         }
         __syncthreads();                               // the stage is rewritten by the next batch
       } else {
         if (warp == 0) {                               // hub row: gather straight from global memory
-          const int lr = rb, i = row0 + lr;
-          float di = 1.f;
-          if (MODE == 2) di = c.disw[(size_t)i * 2 + branch];
+          const int lr = rb;
           RowVec<VEC> a;
           a.zero();
           for (int p = sPtr[lr]; p < sPtr[lr + 1]; ++p) {
             const int src = c.in_src[p];
             RowVec<VEC> v;
             v.load_coherent(xin + (size_t)src * H, lane);
-            float w = MODE == 2 ? c.watt[(size_t)p * 2 + branch] : (MODE == 3 ? 1.f : c.in_norm[p]);
-            float am = 1.f;
-            if (MODE == 2) {
-              am = c.natt[(size_t)src * 2 + branch];
-              w = (c.disw[(size_t)src * 2 + branch] * w) * di;
-            }
+            const float w = MODE == 3 ? 1.f : c.in_norm[p];
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-              float x = MODE == 2 ? am * v.v[k] : v.v[k];
-              a.v[k] = fmaf(w, fmaf(x, bn.sc[k], bn.sh[k]), a.v[k]);
-            }
+            for (int k = 0; k < VEC; ++k) a.v[k] = fmaf(w, fmaf(v.v[k], bn.sc[k], bn.sh[k]), a.v[k]);
           }
-          if (MODE == 2) a.store(aggout + (size_t)i * H, lane);
           a.store(sA + lr * LDA, lane);
         }
       }
@@ -341,13 +305,13 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
 #pragma unroll
         for (int k = 0; k < VEC; ++k) o.v[k] = MODE == 3 ? acc[r][k] + bv[k] : fmaxf(acc[r][k] + bv[k], 0.f);
         o.store(xout + (size_t)i * H, lane);
-        if (MODE != 2) epi.row(c, i, o.v, lane);
+        epi.row(c, i, o.v, lane);
       }
     }
   }
   cp_async_wait_all();
   PT_MARK();                                           // 6: epilogue stores
-  if (MODE != 2) epi.finish(c, MODE == 3 ? layer - 1 : layer, sRed, sTot, N);    // MODE 3: BN id 2 + (layer - 1) = 1 + layer
+  epi.finish(c, MODE == 3 ? layer - 1 : layer, sRed, sTot, N);    // MODE 3: BN id 2 + (layer - 1) = 1 + layer
   PT_MARK();                                           // 7: totals + grid sum + finalize
   PT_DUMP(c, 16);
 }
@@ -357,8 +321,8 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
 // aggregate the same neighbour rows x_{L+1}[src] -- they differ only in the node attention, the
 // BatchNorm affine (bnc / bno), the attention-weighted norm and the weight matrix -- so a CTA
 // stages every neighbour row once and feeds both accumulators, then runs the two tile GEMMs.
-// (The per-branch variant k_conv_fwd<MODE 2> needs 2 CTAs per SM, which leaves room for only 40
-// staged rows: 2-3 dependent staging rounds per tile.  Here one round of up to 128 rows does.)
+// (A per-branch variant needs 2 CTAs per SM, which leaves room for only 40 staged rows: 2-3 dependent
+// staging rounds per tile, measured 13.9 us vs 12.0 us.  Here one round of up to 128 rows does.)
 // smem: sW [2][H][H] | sA [2][R][H] | sPtr [R+4] | sX [stage][H] | sXn [stage][2] | sXa [stage][2] | sXs [stage]
 // ---------------------------------------------------------------------------------------------
 constexpr int kStageBoth = 128;

@@ -7,15 +7,12 @@ namespace cal {
 
 constexpr int kTileRows = 24;                  // destination rows per GEMM tile (8 warps x 4 rows)
 constexpr int kRPW = kTileRows / kRowWarps;    // rows per warp inside a tile
-constexpr int kEdgeStage = 1024;               // CSR entries staged in shared memory per tile (legacy direct path)
 constexpr int kStageFwd = 128;                 // neighbour rows staged in shared memory per row batch (forward layers)
-constexpr int kStageMasked = 40;               // ... masked convs (2 CTAs per SM)
 constexpr int kStageBwd = 112;                 // ... backward layers (two rows per entry)
 constexpr int kNumBN = CAL_MAX_BN + 1;         // + the identity record used by the top layer's backward
 constexpr int kBnIdentity = CAL_MAX_BN;
 constexpr int kHeadRowsPerCta = 8;             // head2 kernels: one warp per graph row
 constexpr int kFeatChunk = 64;                 // feature columns per CTA slice in the feat backward
-constexpr int kFeatBwdCtas = 32;               // row-slices (= partial gradients) of the feat backward
 constexpr int kGsGroup = 8;                    // CTAs per first-level group of the hierarchical grid sum
 constexpr int kGsSites = 5;                    // grid-sum scratch sites: 0-2 in-kernel sums, 3-4 consumer-side BatchNorm hand-over (alternating)
 constexpr int kGsCounters = 64;                // counters per site: [0] top level, [1 + group] first level
@@ -505,32 +502,6 @@ __device__ __forceinline__ void bn_bwd_finalize_tot(const Ctx& c, int id, const 
     c.grads[c.bn_gamma[id] + k] = (float)s2;
     c.grads[c.bn_beta[id] + k] = (float)s1;
   }
-}
-
-// Legacy single-level variants (readout kernels: a handful of partials).
-__device__ __forceinline__ void bn_finalize(const Ctx& c, int id, const double* partial, int G, int NV, int vs,
-                                            int vq, int count) {
-  __shared__ double s_sum[2][2 * kMaxH];
-  const int K = c.bn_K[id];
-  __syncthreads();
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    s_sum[0][k] = partial_total(partial, G, NV, vs, K, k);
-    s_sum[1][k] = partial_total(partial, G, NV, vq, K, k);
-  }
-  __syncthreads();
-  bn_finalize_tot(c, id, s_sum[0], s_sum[1], count);
-}
-__device__ __forceinline__ void bn_bwd_finalize(const Ctx& c, int id, const double* partial, int G, int NV, int v1,
-                                                int v2, int count) {
-  __shared__ double s_sum[2][2 * kMaxH];
-  const int K = c.bn_K[id];
-  __syncthreads();
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    s_sum[0][k] = partial_total(partial, G, NV, v1, K, k);
-    s_sum[1][k] = partial_total(partial, G, NV, v2, K, k);
-  }
-  __syncthreads();
-  bn_bwd_finalize_tot(c, id, s_sum[0], s_sum[1], count);
 }
 
 // Per-lane BatchNorm constants of the lane's VEC channels.
