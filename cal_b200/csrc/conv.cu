@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(256) k_conv_fwd(const Ctx c, const int layer) 
     for (int r = 0; r < kRPW; ++r)
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
-    tile_gemm<VEC, kRPW>(sA, LDA, sW, H, H, acc);
+    tile_gemm_fast<VEC, kRPW>(sA, LDA, sW, H, H, sX, acc);           // (the row stage is free: partial tiles of the K-split)
     PT_MARK();                                         // 5: GEMM
     // ---- epilogue ----
 #pragma unroll
@@ -496,7 +496,8 @@ __global__ void __launch_bounds__(256) k_masked_fwd_both(const Ctx c) {
       for (int r = 0; r < kRPW; ++r)
 #pragma unroll
         for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
-      tile_gemm<VEC, kRPW>(sA + br * kTileRows * LDA, LDA, sW + br * H * H, H, H, acc);
+      if (br == 1) __syncthreads();                    // the partial tiles of branch 0 have been read back
+      tile_gemm_fast<VEC, kRPW>(sA + br * kTileRows * LDA, LDA, sW + br * H * H, H, H, sX, acc);
       float* zo = br ? z1 : z0;
 #pragma unroll
       for (int r = 0; r < kRPW; ++r) {

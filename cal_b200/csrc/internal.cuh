@@ -791,6 +791,88 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ sA, int lda,
 // NOT faster: the loop is bound by FFMA issue with 2 warps per scheduler, not by LDS; profiles/README.md.)
 constexpr int kPad = 4;
 
+// The same product, K-split (H = 128 only).  tile_gemm is bound by the shared-memory RETURN path: every
+// LDS.128 delivers 512 bytes per warp to the register file at 128 B/clk whatever it broadcasts, and a
+// 3 x 4 register tile needs 7 of them per 24 FFMA2 (measured: 24x128x128 MACs in ~6.1 k cycles with
+// every operand mapping, FFMA or FFMA2, 6 or 12 chains -- profiles/README.md).  Here the 8 warps form
+// 4 K-groups of 64 threads; inside a group thread (rb, cb) owns a 6 x 8 register tile (rows 6rb..6rb+5,
+// columns 4cb..4cb+3 and 64+4cb..64+4cb+3) over the group's 32 k: 14 LDS.128 per 96 FFMA2, half the
+// bytes per FMA, 24 independent accumulator pairs.  The 4 partial tiles meet in `sPart`
+// ([4][kTileRows][ldp], ldp >= H + kPad; must not alias sA / sW) and are added in group order while the
+// tile is handed back in the row-per-warp layout of the epilogues.  All threads call; one
+// __syncthreads inside.  (Sums of 4 x 32 consecutive k: deterministic, not bit-identical to tile_gemm.)
+__device__ __forceinline__ void tile_gemm_ksplit128(const float* __restrict__ sA, int lda, const float* __restrict__ sW,
+                                                    int ldw, float* __restrict__ sPart, int ldp,
+                                                    float (&acc)[kRPW][4]) {
+  static_assert(kTileRows == 24 && kRowWarps == 8, "4 K-groups x (4 row blocks x 16 column blocks)");
+  constexpr int H = 128, KG = H / 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kg = warp >> 1;
+  const int t64 = ((warp & 1) << 5) | lane;
+  const int rb = t64 >> 4, cb = t64 & 15;
+  const float* a0 = sA + (size_t)(6 * rb) * lda + kg * KG;
+  const float* w0 = sW + (size_t)(kg * KG) * ldw + 4 * cb;
+  f32x2 c2[6][4];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c2[i][j] = pack2(0.f, 0.f);
+#pragma unroll
+  for (int s = 0; s < KG / 4; ++s) {
+    float4 a[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + (size_t)i * lda + 4 * s);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float* wr = w0 + (size_t)(4 * s + kk) * ldw;
+      const float4 wa = *reinterpret_cast<const float4*>(wr);
+      const float4 wb = *reinterpret_cast<const float4*>(wr + 64);
+      const f32x2 p0 = pack2(wa.x, wa.y), p1 = pack2(wa.z, wa.w), p2 = pack2(wb.x, wb.y), p3 = pack2(wb.z, wb.w);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+        c2[i][0] = ffma2_bcast(av, p0, c2[i][0]);
+        c2[i][1] = ffma2_bcast(av, p1, c2[i][1]);
+        c2[i][2] = ffma2_bcast(av, p2, c2[i][2]);
+        c2[i][3] = ffma2_bcast(av, p3, c2[i][3]);
+      }
+    }
+  }
+  float* pt = sPart + (size_t)kg * kTileRows * ldp;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) unpack2(c2[i][j], v[2 * j], v[2 * j + 1]);
+    float* o = pt + (size_t)(6 * rb + i) * ldp + 4 * cb;
+    *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(o + 64) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kRPW; ++r) {
+    const float* o = sPart + (size_t)(warp * kRPW + r) * ldp + lane * 4;
+    float4 t = *reinterpret_cast<const float4*>(o);
+#pragma unroll
+    for (int g = 1; g < 4; ++g) {
+      const float4 u = *reinterpret_cast<const float4*>(o + (size_t)g * kTileRows * ldp);
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    acc[r][0] = t.x; acc[r][1] = t.y; acc[r][2] = t.z; acc[r][3] = t.w;
+  }
+}
+
+// H = 128: K-split; otherwise the row mapping.  sPart: [4][kTileRows][H + kPad] floats (H = 128 only).
+template <int VEC, int RPW>
+__device__ __forceinline__ void tile_gemm_fast(const float* __restrict__ sA, int lda, const float* __restrict__ sW,
+                                               int ldw, int K, float* __restrict__ sPart, float (&acc)[RPW][VEC]) {
+  if constexpr (VEC == 4 && RPW == kRPW) {
+    tile_gemm_ksplit128(sA, lda, sW, ldw, sPart, 32 * VEC + kPad, acc);
+  } else {
+    tile_gemm<VEC, RPW>(sA, lda, sW, ldw, K, acc);
+  }
+}
+
 // Outer-product accumulation over a row tile: acc[a][b] += sum_r sP[r*ld + kidx(a)] * sQ[r*ld + jidx(b)].
 // 256 threads cover an [H x H] result: thread (ty = tid / 16, tx = tid % 16) owns MT x MT entries with
 // MT = H / 16, index set {half*(H/2) + t*(MT/2) + i}.
