@@ -705,7 +705,7 @@ __global__ void __launch_bounds__(256) k_conv_bwd(const Ctx c, const int layer) 
     for (int r = 0; r < kRPW; ++r)
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
-    tile_gemm<VEC, kRPW>(sU, LDA, sW, H, H, acc);
+    tile_gemm_fast<VEC, kRPW>(sU, LDA, sW, H, H, sXD, acc);          // (the row stage is free: partial tiles of the K-split)
     PT_MARK();                                         // 4: GEMM dX
 #pragma unroll
     for (int r = 0; r < kRPW; ++r) {
@@ -855,6 +855,7 @@ __global__ void __launch_bounds__(256) k_gin_b_fwd(const Ctx c, const int layer)
   float* sW = reinterpret_cast<float*>(smem_raw);
   float* sA = sW + H * H;
   double* sRed = reinterpret_cast<double*>(sA + kTileRows * LDA);
+  float* sPart = reinterpret_cast<float*>(sRed + kRowWarps * H);     // [4][R][LDA] partial tiles of the K-split GEMM
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   stage_matrix_async(sW, c.wt_gin2(layer), H * H);
   const bool cs = bn_consumer_side(c);               // the layer's inner BatchNorm is finalised here
@@ -902,7 +903,7 @@ __global__ void __launch_bounds__(256) k_gin_b_fwd(const Ctx c, const int layer)
     for (int r = 0; r < kRPW; ++r)
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
-    tile_gemm<VEC, kRPW>(sA, LDA, sW, H, H, acc);
+    tile_gemm_fast<VEC, kRPW>(sA, LDA, sW, H, H, sPart, acc);
 #pragma unroll
     for (int r = 0; r < kRPW; ++r) {
       const int i = row0 + warp * kRPW + r;
@@ -930,6 +931,7 @@ __global__ void __launch_bounds__(256) k_gin_b_bwd(const Ctx c, const int layer)
   float* sU = sW + H * H;
   float* sY = sU + kTileRows * LDA;
   double* sRed = reinterpret_cast<double*>(sY + kTileRows * LDA);
+  float* sPart = reinterpret_cast<float*>(sRed + kRowWarps * H);     // [4][R][LDA] partial tiles of the K-split GEMM
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   stage_matrix_async(sW, c.params + c.po.gin_w2[layer], H * H);     // [out, in] as stored: d r = u W2
   pdl_sync();                                        // everything below may read the predecessor's output
@@ -983,7 +985,7 @@ __global__ void __launch_bounds__(256) k_gin_b_bwd(const Ctx c, const int layer)
     for (int r = 0; r < kRPW; ++r)
 #pragma unroll
       for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
-    tile_gemm<VEC, kRPW>(sU, LDA, sW, H, H, acc);
+    tile_gemm_fast<VEC, kRPW>(sU, LDA, sW, H, H, sPart, acc);
 #pragma unroll
     for (int r = 0; r < kRPW; ++r) {
       const int i = row0 + warp * kRPW + r;
@@ -1182,7 +1184,7 @@ int launch_gin_forward(const Ctx& c, int layer, cudaStream_t s) {
     int rc = set_smem(k_conv_fwd<VEC, 3>, smem);
     if (rc) return rc;
     launch_k(k_conv_fwd<VEC, 3>, dim3(c.g_tile), dim3(256), smem, s, c, layer);
-    smem = (size_t)c.H * c.H * 4 + (size_t)kTileRows * (c.H + kPad) * 4 + (size_t)kRowWarps * c.H * 8;
+    smem = (size_t)c.H * c.H * 4 + 5 * (size_t)kTileRows * (c.H + kPad) * 4 + (size_t)kRowWarps * c.H * 8;
     if (last) {
       rc = set_smem(k_gin_b_fwd<VEC, true>, smem);
       if (rc) return rc;
@@ -1200,7 +1202,7 @@ int launch_gin_forward(const Ctx& c, int layer, cudaStream_t s) {
 
 int launch_gin_backward(const Ctx& c, int layer, cudaStream_t s) {
   CAL_DISPATCH_VEC(c.H, {
-    size_t smem = (size_t)c.H * c.H * 4 + 2 * (size_t)kTileRows * (c.H + kPad) * 4 + (size_t)kRowWarps * c.H * 8;
+    size_t smem = (size_t)c.H * c.H * 4 + 6 * (size_t)kTileRows * (c.H + kPad) * 4 + (size_t)kRowWarps * c.H * 8;
     int rc = set_smem(k_gin_b_bwd<VEC>, smem);
     if (rc) return rc;
     launch_k(k_gin_b_bwd<VEC>, dim3(c.g_tile), dim3(256), smem, s, c, layer);
