@@ -20,7 +20,8 @@ import torch
 
 from . import _lib
 
-__all__ = ["PackedLayout", "Trainer", "batch_caps", "allreduce_flat_grads", "PeerExchange", "GraphStore"]
+__all__ = ["PackedLayout", "Trainer", "batch_caps", "allreduce_flat_grads", "PeerExchange", "GraphStore",
+           "epoch_order"]
 
 
 def _up(x, m):
@@ -33,6 +34,21 @@ def batch_caps(batches, slack=1.0):
     e = max(int(b.edge_index.size(1)) for b in batches)
     g = max(int(b.num_graphs) for b in batches)
     return _up(int(n * slack), 32), _up(max(int(e * slack), 1), 32), _up(g, 8)
+
+
+def epoch_order(num_graphs, epoch, seed=0, rank=0, world_size=1, graphs_per_step=None):
+    """This rank's graph order for one epoch (input of ``Trainer.begin_epoch``): the shuffle of the
+    reference's ``DataLoader(train_dataset, batch_size, shuffle=True)`` (train_causal.py:13-15), sharded
+    DistributedSampler-style -- every rank draws the SAME permutation from (seed, epoch) and takes
+    ``perm[rank::world_size]`` (SURVEY.md section 8e).  With ``graphs_per_step`` the shard is cut to a
+    whole number of steps common to all ranks, so every rank issues the same number of gradient
+    exchanges (a peer exchange / all-reduce with a missing rank would wait forever)."""
+    perm = np.random.RandomState((int(seed) * 1000003 + int(epoch)) % (2 ** 31 - 1)).permutation(int(num_graphs))
+    shard = perm[int(rank)::int(world_size)]
+    if graphs_per_step:
+        per_rank = int(num_graphs) // int(world_size)                 # the shortest shard
+        shard = shard[:per_rank // int(graphs_per_step) * int(graphs_per_step)]
+    return shard.astype(np.int32)
 
 
 def allreduce_flat_grads(flat_grad, group=None):

@@ -172,3 +172,36 @@ def test_graph_store_layout_and_caps():
         assert b.batch.numel() <= cn and b.edge_index.size(1) <= ce
     wn, we, wb = st.caps(B)                                  # worst case covers any order
     assert wn >= cn and we >= ce and wb == cb == 8
+
+
+def _order_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out = {}
+    for epoch in range(2):
+        o = cal_b200.epoch_order(203, epoch, seed=7, rank=rank, world_size=world, graphs_per_step=16)
+        steps = torch.tensor([len(o) // 16])
+        dist.all_reduce(steps, op=dist.ReduceOp.MIN)                 # what a rank would check before training
+        out[epoch] = (o, int(steps))
+    torch.save(out, os.path.join(out_dir, "o%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_epoch_order_shards_like_a_distributed_sampler_gloo_world2(tmp_path):
+    """The per-rank epoch order of the device-resident path: same permutation on every rank, disjoint
+    shards, the same number of whole steps everywhere, a new shuffle every epoch."""
+    import torch.multiprocessing as mp
+    mp.spawn(_order_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    r = [torch.load(os.path.join(tmp_path, "o%d.pt" % k), weights_only=False) for k in range(2)]
+    for epoch in range(2):
+        (a, sa), (b, sb) = r[0][epoch], r[1][epoch]
+        assert sa == sb == len(a) // 16 == len(b) // 16 == 6       # 203 // 2 = 101 graphs per rank -> 6 steps of 16
+        assert len(a) == len(b) == 96 and a.dtype == np.int32
+        assert not set(a.tolist()) & set(b.tolist())                # disjoint shards
+        full = np.random.RandomState((7 * 1000003 + epoch) % (2 ** 31 - 1)).permutation(203)
+        assert np.array_equal(a, full[0::2][:96]) and np.array_equal(b, full[1::2][:96])
+    assert not np.array_equal(r[0][0][0], r[0][1][0])               # reshuffled between epochs
+    solo = cal_b200.epoch_order(50, 3, seed=1)
+    assert sorted(solo.tolist()) == list(range(50))                 # one rank, no step cut: a plain permutation
