@@ -393,8 +393,8 @@ def run_gpu(a, rank, local_rank, world):
                    "k_conv_fwd" if n.startswith("layer_") else n)
             f = fam.setdefault(key, {"stage": key, "us": 0.0, "alg_bytes": 0, "launches": 0, "n": 0})
             f["us"] += r["us"]; f["alg_bytes"] += r["alg_bytes"]; f["launches"] += r["launches"]; f["n"] += 1
-        single = [f for f in fam.values() if f["launches"] == f["n"]]        # one kernel per issue
-        top = max(single, key=lambda f: f["us"])
+        # (a stage of two launches -- a GATConv / GINConv layer -- counts as one family, timed as a whole)
+        top = max(fam.values(), key=lambda f: f["us"])
         top = {"stage": top["stage"], "us": top["us"] / top["n"], "alg_bytes": top["alg_bytes"] // top["n"],
                "gbs": top["alg_bytes"] / (top["us"] * 1e-6) / 1e9, "share_of_step": top["us"] / sum(r["us"] for r in stage_tab)}
         peaks = {}
