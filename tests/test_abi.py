@@ -110,6 +110,38 @@ def test_host_side_argument_validation_no_launch():
     assert lib.cal_launch_count() == n0
 
 
+def test_collate_and_peer_exchange_argument_validation_no_launch():
+    """cal_collate / cal_dp_*: sizes and argument errors are decided on the host before any CUDA call."""
+    L, lib = _lib()
+    n0 = lib.cal_launch_count()
+    # exchange region: header + flags + 2 parities x world slots of the padded gradient
+    assert lib.cal_dp_region_bytes(0, 1000) == 0 and lib.cal_dp_region_bytes(L.CAL_MAX_WORLD + 1, 1000) == 0
+    assert lib.cal_dp_region_bytes(2, 0) == 0
+    n = 138660
+    n_pad = -(-n // (4 * 148)) * (4 * 148)
+    for w in (1, 2, 8):
+        flags = -(-(2 * w * 148 * 4) // 256) * 256
+        assert lib.cal_dp_region_bytes(w, n) == 256 + flags + 2 * w * n_pad * 4
+    comm = L.DpComm()
+    comm.world, comm.rank = 2, 0
+    assert lib.cal_dp_adam_step(None, 0, 0, 0, 0, 8, 0, 1e-3, 0, 0.9, 0.999, 1e-8, 0.0, 0) == -2
+    assert lib.cal_dp_adam_step(C.byref(comm), 0, 0, 0, 0, 8, 0, 1e-3, 0, 0.9, 0.999, 1e-8, 0.0, 0) == -2    # NULL buffers
+    comm.rank = 5
+    assert lib.cal_dp_adam_step(C.byref(comm), 16, 16, 16, 16, 8, 16, 1e-3, 0, 0.9, 0.999, 1e-8, 0.0, 0) == -1   # rank >= world
+    comm.rank = 0
+    assert lib.cal_dp_adam_step(C.byref(comm), 16, 16, 16, 16, 6, 16, 1e-3, 0, 0.9, 0.999, 1e-8, 0.0, 0) == -1   # n % 4 != 0
+    assert lib.cal_dp_adam_step(C.byref(comm), 16, 20, 16, 16, 8, 16, 1e-3, 0, 0.9, 0.999, 1e-8, 0.0, 0) == -3   # alignment
+    assert lib.cal_dp_adam_step(C.byref(comm), 16, 16, 16, 16, 8, 16, 1e-3, 0, 0.9, 0.999, 1e-8, 0.0, 0) == -2   # unmapped peer region
+    assert lib.cal_dp_export(None, None) == -2 and lib.cal_dp_free(None) == -2 and lib.cal_dp_unmap(None) == -2
+    assert "timed out" in lib.cal_error_string(-6).decode()
+    # collate
+    assert lib.cal_collate(None, 0, 0, 0, 4, 0, None, None, 0, 0, 0, 0) == -2
+    st, caps, out = L.GraphStoreDesc(), _caps(L), L.Batch()
+    assert lib.cal_collate(C.byref(st), 16, 4, 0, 4, 0, C.byref(caps), C.byref(out), 0, 0, 0, 0) == -2      # store arrays NULL
+    assert lib.cal_collate_flush(0, 0, 0, 0, 0) == -2
+    assert lib.cal_launch_count() == n0
+
+
 def test_product_has_no_cpu_fallback():
     """The module refuses to run off-GPU instead of silently falling back."""
     import torch
