@@ -83,7 +83,7 @@ class ClockSampler:
                0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
-    def __init__(self, index, period=0.02):
+    def __init__(self, index, period=0.002):
         self.index, self.period = index, period
         self.sm, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
@@ -101,11 +101,10 @@ class ClockSampler:
         nv = self.nv
         while not self._stop.is_set():
             try:
-                self.sm.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mhz = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                for bit, name in self.REASONS.items():
-                    if r & bit and name != "gpu_idle":
-                        self.reasons.add(name)
+                names = [name for bit, name in self.REASONS.items() if r & bit and name != "gpu_idle"]
+                self.sm.append((time.perf_counter(), mhz, names))
             except Exception:
                 pass
             self._stop.wait(self.period)
@@ -121,11 +120,16 @@ class ClockSampler:
         if self._t is not None:
             self._t.join()
 
-    def summary(self):
-        if not self.sm:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.sm)}
+    def summary(self, t0=None, t1=None):
+        """Median SM clock and the throttle reasons seen inside the host-time window [t0, t1] (the timed
+        region); `samples_total` counts every sample taken (warm-up included)."""
+        inside = [x for x in self.sm if t0 is None or (t0 <= x[0] <= t1)]
+        use = inside or self.sm
+        if not use:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "samples_total": 0}
+        return {"sm_mhz": float(np.median([x[1] for x in use])), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted({n for x in use for n in x[2]}), "samples": len(inside), "samples_total": len(self.sm),
+                "window": "timed region" if inside else "warm-up + timed region (no sample fell inside the timed region)"}
 
 
 def visible_gpu_index(local_rank):
@@ -231,7 +235,8 @@ def run_reference(a, rank, world):
         return
     from cal_b200.data import CONFIGS
     bs = a.batch or CONFIGS[a.workload]["batch_size"]
-    batches, cfg = build_batches(a.workload, bs, 16, max(a.pool, 16 * bs), 666)
+    # the first 16 batches of rank 0 of the GPU arm (same pool, same seeds)
+    batches, cfg = build_batches(a.workload, bs, 16, pool_size(a, bs), 666)
     F, C = batches[0].feat.size(1), cfg["num_classes"]
     cores = os.cpu_count() or 1
     gps, done, el, thr = cpu_train_steps(batches, F, C, 128, 3, a.steps, a.warmup, threads=cores, model=a.model)
@@ -239,7 +244,7 @@ def run_reference(a, rank, world):
         "impl": "reference", "metric": METRIC, "value": gps, "unit": UNIT, "n_gpus": a.gpus, "steps": done,
         "warmup": a.warmup, "ms_per_step": 1e3 * el / done, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(a, bs, batches, "host memory (CPU run)"),
+        "config": workload_config(a, bs, batches), "sample": sample_stats(batches, "host memory (CPU run)"),
         "cpu_baseline": {"value": gps, "unit": UNIT, "cores": thr, "kind": "port",
                          "sample": "%d train steps of %d graphs, %d torch threads" % (done, bs, thr)},
         "e2e": {"value": gps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -248,20 +253,88 @@ def run_reference(a, rank, world):
     print(json.dumps(line), file=OUT, flush=True)
 
 
-def workload_config(a, bs, batches, residency):
-    n = float(np.mean([b.batch.numel() for b in batches]))
-    e = float(np.mean([b.edge_index.size(1) for b in batches]))
+def workload_config(a, bs, batches):
+    """The workload both arms run -- byte-identical between `--impl cal_b200` and `--impl reference`
+    (per-sample statistics and the residency note live in the sibling `sample` key)."""
     return {"workload": "%s SPMotif-style synthetic (bias 0.9), %s 3 layers hidden 128, batch %d per GPU"
                         % (a.workload, a.model, bs),
             "model_step": "prep + forward + KL/NLL loss + backward + grad all-reduce (N>1) + Adam",
-            "avg_nodes_per_batch": n, "avg_edge_columns_per_batch": e, "graphs_per_batch": bs,
-            "features": int(batches[0].feat.size(1)), "hidden": 128, "layers": 3, "parallelism": "dp%d" % a.gpus,
-            "cache": residency}
+            "graphs_per_batch": bs, "features": int(batches[0].feat.size(1)), "hidden": 128, "layers": 3,
+            "generator": "cal_b200.data.make_dataset(pool=%d, seed=666 + rank, bias=0.9); batches drawn without "
+                         "replacement from the pool by RandomState(667 + rank)" % pool_size(a, bs),
+            "parallelism": "dp%d" % a.gpus}
+
+
+def pool_size(a, bs):
+    return a.pool or max(8192, 4 * bs)
+
+
+def sample_stats(batches, residency):
+    return {"batches": len(batches), "avg_nodes_per_batch": float(np.mean([b.batch.numel() for b in batches])),
+            "avg_edge_columns_per_batch": float(np.mean([b.edge_index.size(1) for b in batches])), "cache": residency}
 
 
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+
+def dp_verify(tr, packed_dev, dist, dev, world):
+    """Data-parallel correctness inside the driver's own multi-GPU run (SURVEY.md 8e parity rule):
+    (1) every rank's flat parameter buffer has the same raw bits (xor checksum + fp64 sum, all-gathered);
+    (2) one more step, recomputed independently: the ranks' local gradients are all-gathered, averaged
+        in rank order and pushed through torch.optim.Adam's update formula in fp64 from the saved state;
+        the parameters the fused exchange + Adam kernel produced must agree."""
+    eng = tr.eng
+    torch.cuda.synchronize(dev)
+
+    def checksum():
+        bits = eng.flat.view(torch.int32).clone()
+        n = 1
+        while n < bits.numel():
+            n *= 2
+        pad = torch.zeros(n, dtype=torch.int32, device=dev)
+        pad[:bits.numel()] = bits
+        while n > 1:
+            n //= 2
+            pad = pad[:n] ^ pad[n:2 * n]
+        t = torch.stack([pad[0].double(), eng.flat.double().sum()])
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [[float(v) for v in o.tolist()] for o in out]
+
+    cs0 = checksum()
+    p0 = eng.flat.clone()
+    m0, v0, step = [t.clone() for t in eng.opt_state]
+    t_next = int(step[0]) + 1
+    tr.step(packed_dev)
+    torch.cuda.synchronize(dev)
+    g = eng.flat_grad.clone()
+    if tr.collective == "peer":                      # flat_grad holds the local gradient
+        parts = [torch.zeros_like(g) for _ in range(world)]
+        dist.all_gather(parts, g)
+        acc = torch.zeros_like(g, dtype=torch.float64)
+        for q in range(world):
+            acc += parts[q].double()
+        gm = acc / world
+    else:                                            # ncclAllReduce summed it in place
+        gm = g.double() / world
+    b1, b2 = tr.betas
+    lr = float(tr.lr_dev.item())
+    m = m0.double() + (gm - m0.double()) * (1.0 - b1)
+    v = v0.double() * b2 + (1.0 - b2) * gm * gm
+    bc1, bc2 = 1.0 - b1 ** t_next, 1.0 - b2 ** t_next
+    want = p0.double() - (lr / bc1) * m / (v.sqrt() / (bc2 ** 0.5) + tr.eps)
+    err = float((want - eng.flat.double()).abs().max())
+    cs1 = checksum()
+    return {"replicas_bit_identical": all(c == cs0[0] for c in cs0) and all(c == cs1[0] for c in cs1),
+            "checksums_xor_sum_per_rank": cs1,
+            "adam_step_abs_err_vs_fp64_recomputation": err,
+            "adam_step_err_rel_to_update": err / max(float((want - p0.double()).abs().max()), 1e-30),
+            "adam_step_err_rel_to_params": err / max(float(want.abs().max()), 1e-30),
+            "how": "after the timed region: xor + fp64-sum checksum of the flat parameter buffer all-gathered over the "
+                   "ranks; then one extra step whose update is recomputed in fp64 from the all-gathered local gradients "
+                   "(rank-order mean) and the saved Adam state"}
+
 
 def run_gpu(a, rank, local_rank, world):
     import cal_b200
@@ -287,7 +360,7 @@ def run_gpu(a, rank, local_rank, world):
         t = torch.tensor([n_res], dtype=torch.int64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         n_res = int(t.item())
-    pool = a.pool or max(8192, 4 * bs)
+    pool = pool_size(a, bs)
     batches, cfg = build_batches(a.workload, bs, n_res, pool, 666 + rank)
     F, C = int(batches[0].feat.size(1)), cfg["num_classes"]
     torch.manual_seed(666)
@@ -315,17 +388,19 @@ def run_gpu(a, rank, local_rank, world):
     # capture one graph per resident batch (outside the timed region), then W warm-up steps
     for r in resident:
         tr.step(r)
-    for i in range(a.warmup):
-        tr.step(resident[i % n_res])
-    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # clocks are sampled (NVML, every 2 ms) from the warm-up on: a 20-step timed region is only ~3 ms long
     with ClockSampler(visible_gpu_index(local_rank)) as clk:
+        for i in range(max(a.warmup, 3)):
+            tr.step(resident[i % n_res])
         barrier()
+        t_begin = time.perf_counter()
         e0.record()
         for i in range(a.steps):
             tr.step(resident[(a.warmup + i) % n_res])
         e1.record()
         barrier()
+        t_end = time.perf_counter()
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -334,6 +409,7 @@ def run_gpu(a, rank, local_rank, world):
     value = a.steps * graphs_per_step * world / (ms * 1e-3)
     loss_after = tr.metrics().cpu().tolist()
     launches = int(tr.launches_per_step) * a.steps
+    dp_check = dp_verify(tr, resident[0], dist, dev, world) if dist is not None else None
 
     # ---- end to end: pinned host batch -> H2D -> step -> loss parts D2H, every step ----
     e2e = None
@@ -492,14 +568,14 @@ def run_gpu(a, rank, local_rank, world):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(a, bs, batches,
-                                      "inputs larger than L2: %d distinct resident batches (%.0f MB) cycled; "
-                                      "workspace reused" % (n_res, resident_bytes / 2 ** 20)),
-            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
+            "config": workload_config(a, bs, batches),
+            "sample": sample_stats(batches, "inputs larger than L2: %d distinct resident batches (%.0f MB) cycled; "
+                                            "workspace reused" % (n_res, resident_bytes / 2 ** 20)),
+            "clocks": clk.summary(t_begin, t_end), "e2e": e2e, "gpu_launches": launches,
             "launches_per_step": int(tr.launches_per_step), "cuda_graph": not a.no_graph,
             "collective": {"none": "none (1 GPU)", "nccl": "ncclAllReduce of the flat gradient buffer between a compute and an update graph",
                            "peer": "NVLink peer-memory push of the gradient chunks fused with Adam (cal_dp_adam_step), one captured graph per step"}[tr.collective],
-            "roofline": roofline, "cpu_baseline": cpu, "stages": stage_tab,
+            "dp_check": dp_check, "roofline": roofline, "cpu_baseline": cpu, "stages": stage_tab,
             "loss_after": loss_after[:4],
         }
         print(json.dumps(line), file=OUT, flush=True)

@@ -22,7 +22,7 @@ WS_REGIONS = [
     "STATUS", "COUNTERS", "IN_PTR", "IN_SRC", "IN_KEY", "IN_NORM", "OUT_PTR", "OUT_DST", "OUT_POS",
     "OUT_KEY", "CNT_IN", "CNT_OUT", "GRAPH_PTR", "NODE_GRAPH", "PERM", "INVPERM", "DIS", "X",
     "NODE_ATT", "PQ", "EDGE_ATT", "DISW", "AGG", "Z", "POOLED", "H1", "LOGP", "LOSS", "BN", "STATP",
-    "WT", "GAT", "DLOGIT", "DH", "DU", "DPOOL", "DAGG", "DYM", "DNRM", "DT", "DP", "D", "GPART",
+    "WT", "GAT", "DLOGIT", "DH", "DU", "DAGG", "DYM", "DNRM", "DT", "DP", "D", "GPART",
     "OUT_NORM", "EDGE_WN", "EDGE_NA",
 ]
 WS = {n: i for i, n in enumerate(WS_REGIONS)}
@@ -32,7 +32,7 @@ EXPORTS = [
     "cal_causal_forward", "cal_causal_backward", "cal_adam_step", "cal_adam_tick", "cal_read_status",
     "cal_launch_count", "cal_stage_count", "cal_stage_name",
     "cal_dp_region_bytes", "cal_dp_alloc", "cal_dp_free", "cal_dp_export", "cal_dp_import", "cal_dp_unmap",
-    "cal_dp_adam_step", "cal_dp_read_error", "cal_collate", "cal_collate_flush",
+    "cal_dp_adam_step", "cal_dp_read_error", "cal_collate", "cal_collate_flush", "cal_selftest_umma",
 ]
 CAL_MAX_WORLD, CAL_DP_HANDLE_BYTES = 16, 64
 CAL_PASS_FORWARD, CAL_PASS_BACKWARD = 0, 1
@@ -166,6 +166,9 @@ def load():
                                      C.c_float, C.c_void_p]
     lib.cal_dp_read_error.restype = C.c_int
     lib.cal_dp_read_error.argtypes = [P(DpComm), C.c_void_p]
+    lib.cal_selftest_umma.restype = C.c_int
+    lib.cal_selftest_umma.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                      C.c_void_p]
     if lib.cal_abi_version() != 1:
         raise CalError("cal_b200: ABI version mismatch")
     _lib = lib

@@ -151,7 +151,6 @@ int build_ctx(const cal_model_desc* m, const cal_caps* caps, const cal_param_off
   c.dlogit = REG(float, CAL_WS_DLOGIT);
   c.dh = REG(float, CAL_WS_DH);
   c.du = REG(float, CAL_WS_DU);
-  c.dpool = REG(float, CAL_WS_DPOOL);
   c.dagg = REG(float, CAL_WS_DAGG);
   c.dym = REG(float, CAL_WS_DYM);
   c.dnrm = REG(float, CAL_WS_DNRM);

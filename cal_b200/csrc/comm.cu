@@ -16,7 +16,11 @@
 //   Double buffering by parity makes a second barrier unnecessary: a peer can only push exchange
 //   s + 2 (same parity) after it has finished exchange s + 1, which needed this rank's pushes of
 //   s + 1, which this rank issues after its own exchange s kernel has completed.
-//   A bounded spin (kDpTimeoutNs) turns a lost peer into an error word instead of a hung GPU.
+//   The wait is bounded (CAL_DP_TIMEOUT_S, default 600 s, 0 = wait for ever like NCCL): a peer that never
+//   delivers makes the kernel record the error word and TRAP, so the rank fails loudly (every later CUDA
+//   call returns the launch failure) instead of updating its parameters from a stale slot and silently
+//   diverging from its peers.
+#include <stdlib.h>
 #include <string.h>
 
 #include "internal.cuh"
@@ -26,7 +30,6 @@ namespace cal {
 namespace {
 
 constexpr int kDpCtas = kSMs;                       // one chunk per SM
-constexpr unsigned long long kDpTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
 constexpr size_t kDpHeaderBytes = 256;
 
 struct DpHeader {
@@ -75,7 +78,8 @@ __global__ void __launch_bounds__(256) k_dp_adam(const DpPeers peers, const int 
                                                  float* __restrict__ p, const float* g, float* __restrict__ m,
                                                  float* __restrict__ v, const long long n, int* __restrict__ step,
                                                  float lr, const float* __restrict__ lr_dev, const float b1,
-                                                 const float b2, const float eps, const float wd) {
+                                                 const float b2, const float eps, const float wd,
+                                                 const unsigned long long timeout_ns) {
   __shared__ float s_c[2];
   __shared__ int s_t;
   __shared__ unsigned int s_seq;
@@ -84,8 +88,9 @@ __global__ void __launch_bounds__(256) k_dp_adam(const DpPeers peers, const int 
   const long long chunk = n_pad / kDpCtas;                         // floats, multiple of 4
   const long long c0 = (long long)blockIdx.x * chunk;
   const long long c1 = c0 + chunk < n ? c0 + chunk : n;            // n % 4 == 0 is checked on the host
-  if (threadIdx.x == 0) s_seq = *reinterpret_cast<volatile unsigned int*>(&hdr->seq) + 1u;
   pdl_sync();                                                      // the gradients are complete
+  // (hdr->seq is read AFTER the dependency wait: a directly preceding cal_dp_adam_step has then published it)
+  if (threadIdx.x == 0) s_seq = *reinterpret_cast<volatile unsigned int*>(&hdr->seq) + 1u;
   if (threadIdx.x == 0) {       // bias corrections in fp64 like the Python scalars of torch.optim.Adam
     const int t = *reinterpret_cast<volatile int*>(step) + 1;
     s_t = t;
@@ -117,9 +122,10 @@ __global__ void __launch_bounds__(256) k_dp_adam(const DpPeers peers, const int 
       if ((++spins & 1023u) == 0u) {
         const unsigned long long now = global_ns();
         if (t0 == 0) t0 = now;
-        else if (now - t0 > kDpTimeoutNs) {
-          hdr->error = 1u;
-          break;
+        else if (timeout_ns != 0ull && now - t0 > timeout_ns) {
+          *reinterpret_cast<volatile unsigned int*>(&hdr->error) = 1u;
+          __threadfence_system();
+          __trap();                                                  // never apply an update from a stale slot
         }
       }
     }
@@ -246,9 +252,14 @@ extern "C" int cal_dp_adam_step(const cal_dp_comm* comm, float* params, const fl
     peers.region[q] = q < comm->world ? comm->region[q] : nullptr;
     if (q < comm->world && peers.region[q] == nullptr) return CAL_ENULL;
   }
+  static const unsigned long long timeout_ns = [] {
+    const char* e = getenv("CAL_DP_TIMEOUT_S");
+    const double sec = e != nullptr ? atof(e) : 600.0;
+    return sec > 0.0 ? (unsigned long long)(sec * 1e9) : 0ull;
+  }();
   cal::launch_k(cal::k_dp_adam, dim3(cal::kDpCtas), dim3(256), 0, (cudaStream_t)stream, peers, (int)comm->world,
                 (int)comm->rank, params, grads, exp_avg, exp_avg_sq, (long long)n, step, lr, lr_device, beta1, beta2,
-                eps, weight_decay);
+                eps, weight_decay, timeout_ns);
   cal::note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;

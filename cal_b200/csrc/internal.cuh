@@ -83,7 +83,7 @@ struct Ctx {
   unsigned int* gs_cnt;     // [kGsSites][kGsCounters]
   int gs_n;                 // doubles per CTA vector slot (4 * kmax)
   size_t gs_stride;         // doubles per site
-  float *WT, *gat, *dlogit, *dh, *du, *dpool, *dagg, *dym, *dnrm, *dt, *dp, *D, *gpart;
+  float *WT, *gat, *dlogit, *dh, *du, *dagg, *dym, *dnrm, *dt, *dp, *D, *gpart;
   size_t gp_conv[CAL_MAX_LAYERS + 2], gp_att, gp_feat, gp_fc1[3], gp_fc2[3], gp_gat[CAL_MAX_LAYERS];
   size_t gp_gin2[CAL_MAX_LAYERS];
   const float* grad_logp;   // external dL/dlogp (nullptr = fused loss)
@@ -651,34 +651,6 @@ struct LayerEpilogue {
 #define PT_MARK()
 #define PT_DUMP(c, base)
 #endif
-
-// ---- TMA-style bulk copies (cp.async.bulk, SASS UBLKCP) completed through an mbarrier ----
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// global -> shared, `bytes` % 16 == 0, both addresses 16-byte aligned
-__device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                   smem_u32(sdst)),
-               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  unsigned ok;
-  do {
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);

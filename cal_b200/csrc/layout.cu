@@ -82,7 +82,6 @@ int compute_layout(const cal_model_desc* m, const cal_caps* caps, Layout* lay) {
   sz[CAL_WS_DLOGIT] = 3 * Bm * C * 4;
   sz[CAL_WS_DH] = 3 * Bm * H * 4;
   sz[CAL_WS_DU] = 3 * Bm * 2 * H * 4;
-  sz[CAL_WS_DPOOL] = 2 * Bm * H * 4;
   sz[CAL_WS_DAGG] = 2 * Nm * H * 4;
   sz[CAL_WS_DYM] = 2 * Nm * H * 4;
   sz[CAL_WS_DNRM] = EP * 2 * 4;

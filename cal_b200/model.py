@@ -149,6 +149,7 @@ class Engine:
         self._ring = None
         self._ring_i = 0
         self.opt_state = None
+        self._owner = None          # weakref to the Trainer whose captured CUDA graphs point into self.ws
 
     # ---- flat parameter / buffer storage ----
     def _flatten(self):
@@ -230,18 +231,32 @@ class Engine:
         c = self.caps
         if c is not None and N <= c.max_nodes and E <= c.max_edges and B <= c.max_graphs:
             return False
+        owner = self._owner() if self._owner is not None else None
+        if owner is not None and not owner._dead:
+            # growing would free the workspace baked into the Trainer's captured CUDA graphs (their
+            # replays would then read and write freed memory): the capacities are frozen
+            raise _lib.CalError(
+                "cal_b200: batch (N=%d, E=%d, B=%d) exceeds the capacities (N<=%d, E<=%d, B<=%d) frozen by the "
+                "Trainer that owns this model's workspace -- size the Trainer's caps to cover the evaluation "
+                "batches too (batch_caps(train_batches + eval_batches))" % (N, E, B, c.max_nodes, c.max_edges, c.max_graphs))
         grow = lambda need, cur, q: max(cur, _round_up(int(need * 1.25) + 1, q))
         return self.set_caps(grow(N, c.max_nodes if c else 0, 256), grow(E, c.max_edges if c else 0, 256),
                              grow(B, c.max_graphs if c else 0, 32) if c else _round_up(max(B, 1), 32))
 
     def set_caps(self, max_nodes, max_edges, max_graphs):
-        """(Re)allocate the workspace for explicit capacities (invalidates captured CUDA graphs)."""
+        """(Re)allocate the workspace for explicit capacities.  A Trainer that owned the previous
+        workspace is invalidated (its captured CUDA graphs point into freed memory): its next step raises."""
+        owner = self._owner() if self._owner is not None else None
+        if owner is not None:
+            owner._invalidate()
+        self._owner = None
         caps = _lib.Caps()
         caps.max_nodes, caps.max_edges, caps.max_graphs = int(max_nodes), int(max_edges), int(max_graphs)
         nbytes = self.lib.cal_workspace_bytes(C.byref(self.desc), C.byref(caps))
         if nbytes == 0:
-            raise _lib.CalError("cal_b200: unsupported model configuration (hidden must be 32/64/128, "
-                                "2 <= classes <= 32, features <= 512)")
+            raise _lib.CalError("cal_b200: unsupported model configuration or capacities (hidden must be 32/64/128, "
+                                "2 <= classes <= 32, features <= 512; max_graphs=%d may exceed what the readout "
+                                "kernels hold in one SM's shared memory)" % caps.max_graphs)
         self.ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
         self.caps, self.ws_bytes = caps, nbytes
         self._regions = {}

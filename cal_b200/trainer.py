@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import random
+import weakref
 
 import numpy as np
 import torch
@@ -42,7 +43,9 @@ def epoch_order(num_graphs, epoch, seed=0, rank=0, world_size=1, graphs_per_step
     DistributedSampler-style -- every rank draws the SAME permutation from (seed, epoch) and takes
     ``perm[rank::world_size]`` (SURVEY.md section 8e).  With ``graphs_per_step`` the shard is cut to a
     whole number of steps common to all ranks, so every rank issues the same number of gradient
-    exchanges (a peer exchange / all-reduce with a missing rank would wait forever)."""
+    exchanges (a peer exchange / all-reduce with a missing rank would wait forever).  NB: this drops the
+    partial tail batch of every epoch (like ``DataLoader(drop_last=True)``), unlike the reference's
+    single-process loader, which trains on the short last batch too."""
     perm = np.random.RandomState((int(seed) * 1000003 + int(epoch)) % (2 ** 31 - 1)).permutation(int(num_graphs))
     shard = perm[int(rank)::int(world_size)]
     if graphs_per_step:
@@ -258,7 +261,9 @@ class Trainer:
         self.eng = model.engine
         eng = self.eng
         self.device = eng.device
-        eng.set_caps(*caps)
+        self._dead = False
+        eng.set_caps(*caps)              # invalidates a Trainer that owned the previous workspace
+        eng._owner = weakref.ref(self)   # ... and freezes the capacities: Engine.ensure_caps raises instead of growing
         self.layout = PackedLayout(eng.caps.max_nodes, eng.caps.max_edges, eng.caps.max_graphs, eng.F)
         self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=self.device)
@@ -290,11 +295,27 @@ class Trainer:
         self.staging = torch.zeros(self.layout.nbytes, dtype=torch.uint8, device=self.device)
         self._host_loss = torch.zeros(8, dtype=torch.float32).pin_memory()
         self.launches_per_step = None
-        self.with_random = bool(model._shuffles(True)) if with_random is None else with_random
+        # train_causal.py:177 calls model(data, eval_random=args.with_random): no shuffle when args.with_random is off
+        self.with_random = (bool(getattr(model.args, "with_random", True)) and bool(model._shuffles(True))
+                            if with_random is None else with_random)
         self._is_gat = eng.is_gat
         self._warm = False
         self._update_graph = None
         self._update_launches = 0
+
+    def _invalidate(self):
+        """The engine's workspace was reallocated (Engine.set_caps / a newer Trainer): the captured
+        graphs of this Trainer point into freed memory and must never be replayed."""
+        self._dead = True
+        self._graphs = {}
+        self._update_graph = None
+        if getattr(self, "_epoch", None) is not None:
+            self._epoch["graph"] = None
+
+    def _check_alive(self):
+        if self._dead:
+            raise _lib.CalError("cal_b200: this Trainer's workspace was reallocated (Engine.set_caps or a newer "
+                                "Trainer on the same model); create a new Trainer")
 
     # ---- batches ----
     def set_lr(self, lr):
@@ -369,6 +390,7 @@ class Trainer:
 
     def step(self, packed_dev):
         """Enqueue one training step on a device-resident packed batch (asynchronous)."""
+        self._check_alive()
         if packed_dev.device != self.device:
             raise _lib.CalError("cal_b200: Trainer.step needs a device-resident packed batch (use step_host)")
         keep = self._gat_keep_for(None)
@@ -615,6 +637,7 @@ class Trainer:
 
     def step_epoch(self):
         """One training step on the next ``graphs_per_step`` graphs of the epoch (asynchronous)."""
+        self._check_alive()
         ep = self._epoch
         if ep["done"] >= ep["steps"]:
             raise _lib.CalError("cal_b200: the epoch is exhausted (call begin_epoch)")
@@ -664,9 +687,20 @@ class Trainer:
         _lib.check(eng.lib.cal_collate_flush(eng.loss_parts_full().data_ptr(), cb.dims, ep["pos"].data_ptr(),
                                              ep["acc"].data_ptr(), eng._stream()), "cal_collate_flush")
         a = ep["acc"].cpu().tolist()
+        self.check()
         n = max(a[7], 1.0)
         return {"graphs": int(a[7]), "loss": a[0] / n, "c_loss": a[1] / n, "o_loss": a[2] / n, "co_loss": a[3] / n,
                 "acc_c": a[4] / n, "acc_o": a[5] / n, "acc_co": a[6] / n}
+
+    def check(self):
+        """Raise on a data-dependent violation of the last step (status word: node id out of range, unsorted
+        ``batch``, capacity overflow) or a failed peer exchange.  Synchronises; called by ``end_epoch``."""
+        st = self.eng.status()
+        if st != 0:
+            raise _lib.CalError("cal_b200: the last step reported status bits 0x%x (1 = edge endpoint out of range, "
+                                "2 = batch vector not sorted, 4 = batch exceeds the workspace capacities)" % st)
+        if self.peer is not None:
+            self.peer.check(self.eng)
 
     def metrics(self):
         """f32[7] device view: loss, c_loss, o_loss, co_loss, correct_c, correct_o, correct_co of

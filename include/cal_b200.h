@@ -159,7 +159,6 @@ enum cal_ws_region {
   CAL_WS_DLOGIT,       /* f32[3][maxB][C] */
   CAL_WS_DH,           /* f32[3][maxB][H] */
   CAL_WS_DU,           /* f32[3][maxB][2H] */
-  CAL_WS_DPOOL,        /* f32[2][maxB][H] (unused: the masked backward GEMM reads CAL_WS_DU directly) */
   CAL_WS_DAGG,         /* f32[2][maxN][H] */
   CAL_WS_DYM,          /* f32[2][maxN][H] */
   CAL_WS_DNRM,         /* f32[EP][2] */
@@ -304,8 +303,20 @@ int cal_dp_unmap(void* mapped);
 int cal_dp_adam_step(const cal_dp_comm* comm, float* params, const float* grads, float* exp_avg,
                      float* exp_avg_sq, int64_t n, int32_t* step, float lr, const float* lr_device,
                      float beta1, float beta2, float eps, float weight_decay, void* stream);
-/* 0, or CAL_ETIMEOUT if an exchange gave up waiting for a peer (synchronises the stream). */
+/* A peer that does not deliver within CAL_DP_TIMEOUT_S seconds (environment, default 600; 0 = wait for ever)
+ * makes the kernel record an error word and trap: the rank fails with a launch error instead of
+ * applying an update from stale data.  Consecutive calls on one stream are safe (the exchange number is
+ * read after the programmatic dependency wait).
+ * cal_dp_read_error: 0, or CAL_ETIMEOUT if an exchange gave up waiting for a peer (synchronises the stream;
+ * after a trap it returns the CUDA launch failure). */
 int cal_dp_read_error(const cal_dp_comm* comm, void* stream);
+
+/* Self-test of the tensor-core building block (tcgen05.mma with the accumulator in TMEM, the operand
+ * layouts and precisions the readout kernels use): D[M,N] = A[M,K] * B[N,K]^T on one CTA.
+ * kind 0 = 3xTF32 (fp32-accurate split product), 1 = TF32, 2 = BF16; M <= 128, N <= 256; `variant`
+ * bit 0 selects the second of the two shared-memory core-matrix arrangements.  Device pointers. */
+int cal_selftest_umma(int kind, int M, int N, int K, const float* A, const float* B, float* D, int variant,
+                      void* stream);
 
 /* Poll the status word written by cal_prep (synchronises the stream): returns the CAL_ST_* bits,
  * or a negative CAL_E* / positive cudaError_t. */

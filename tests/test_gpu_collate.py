@@ -140,3 +140,32 @@ def test_epoch_on_device_equals_host_collated_steps():
     assert abs(m["loss"] - tot[0] / tot[7]) < 1e-5 * max(1.0, abs(tot[0] / tot[7]))
     assert abs(m["acc_o"] - tot[5] / tot[7]) < 1e-6 and abs(m["acc_co"] - tot[6] / tot[7]) < 1e-6
     assert tr_d._epoch["graph"] is not None                   # one captured graph served both epochs
+
+
+def test_trainer_freezes_capacities_eval_cannot_reallocate():
+    """a larger evaluation batch must not reallocate the workspace baked into the
+    Trainer's captured CUDA graphs.  Engine.ensure_caps raises a CalError instead; training goes on."""
+    import cal_b200
+    from cal_b200 import _lib
+    ora, b, perm = random_case(seed=401, hidden=32, batch_size=8)
+    big = random_case(seed=402, hidden=32, batch_size=24)[1]
+    net = clone_to_cuda(ora, cal_b200)
+    tr = cal_b200.Trainer(net, cal_b200.batch_caps([b]), lr=1e-3)
+    host = tr.pack(b, perm=perm.tolist())
+    r1 = tr.step_host(host).clone()
+    ws_ptr = tr.eng.ws.data_ptr()
+    with pytest.raises(_lib.CalError, match="frozen"):
+        tr.eval_batch(big.to(DEV))
+    assert tr.eng.ws.data_ptr() == ws_ptr                 # nothing was reallocated
+    outs = tr.eval_batch(b.to(DEV))                        # an evaluation batch that fits is fine
+    assert torch.isfinite(outs[0]).all()
+    r2 = tr.step_host(host).clone()                        # the captured graph still replays on live memory
+    assert torch.isfinite(r2).all() and float(r2[0]) != float(r1[0])
+    tr.check()
+    # a second Trainer on the same model takes the workspace over; the first one refuses to replay
+    tr2 = cal_b200.Trainer(net, cal_b200.batch_caps([b, big]), lr=1e-3)
+    with pytest.raises(_lib.CalError, match="reallocated"):
+        tr.step_host(host)
+    tr2.step_host(tr2.pack(big, perm=list(range(24))))
+    tr2.eval_batch(big.to(DEV))
+    tr2.check()

@@ -52,6 +52,43 @@ def _worker(rank, world, port, out_dir, use_graph, collective="nccl"):
     dist.destroy_process_group()
 
 
+def test_dp_adam_back_to_back_world1_matches_adam():
+    """cal_dp_adam_step twice in a row on one stream (world = 1: no peers, same kernel): the second
+    exchange must see the first one's exchange number (read after the dependency wait) -- same
+    parameters as two cal_adam_step calls, and the region's sequence counter has advanced by two."""
+    import ctypes as C
+    import cal_b200
+    from cal_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    n = 4 * 148 * 5 + 8
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(n, generator=g).to(dev)
+    grads = [torch.randn(n, generator=g).to(dev) for _ in range(2)]
+    nbytes = lib.cal_dp_region_bytes(1, n)
+    mine = C.c_void_p()
+    assert lib.cal_dp_alloc(0, nbytes, C.byref(mine)) == 0
+    comm = _lib.DpComm()
+    comm.world, comm.rank = 1, 0
+    comm.region[0] = mine.value
+    s = torch.cuda.current_stream().cuda_stream
+    pa, ma, va = p0.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    pb, mb, vb = p0.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    sa, sb = torch.zeros(2, dtype=torch.int32, device=dev), torch.zeros(2, dtype=torch.int32, device=dev)
+    for gk in grads:                                   # back to back, no other kernel in between
+        assert lib.cal_dp_adam_step(C.byref(comm), pa.data_ptr(), gk.data_ptr(), ma.data_ptr(), va.data_ptr(), n,
+                                    sa.data_ptr(), 1e-3, 0, 0.9, 0.999, 1e-8, 0.0, s) == 0
+    for gk in grads:
+        assert lib.cal_adam_step(pb.data_ptr(), gk.data_ptr(), mb.data_ptr(), vb.data_ptr(), n, sb.data_ptr(),
+                                 1e-3, 0, 0.9, 0.999, 1e-8, 0.0, 1.0, s) == 0
+    torch.cuda.synchronize()
+    assert lib.cal_dp_read_error(C.byref(comm), s) == 0
+    assert int(sa[0]) == 2 and int(sb[0]) == 2
+    for x, y in ((pa, pb), (ma, mb), (va, vb)):      # same formulas; the compiler may contract the FMAs differently
+        assert torch.allclose(x, y, rtol=2e-6, atol=1e-7)
+    lib.cal_dp_free(mine)
+
+
 @pytest.mark.parametrize("collective", ["nccl", "peer"])
 @pytest.mark.parametrize("use_graph", [True, False], ids=["graph", "eager"])
 def test_dp_world2_matches_oracle_average(tmp_path, use_graph, collective):

@@ -69,22 +69,23 @@ def _gpu_relu_masks(eng, N, B):
     return m
 
 
-def _close(got, w32, w64):
-    """Within TOL of the fp32 oracle, or of the exact (fp64) value, or -- where the fp32 oracle
-    itself is further than TOL from the exact value (ill-conditioned: BatchNorm over 2 rows,
-    100k-row reductions) -- no further from the exact value than 3x the fp32 oracle is."""
+def _close(got, w32, w64, illcond=False):
+    """Within TOL of the fp32 oracle, or of the exact (fp64) value, or -- only for the cases named
+    ill-conditioned (`illcond`: BatchNorm over <= 8 rows, 100k-row reductions), where the fp32 oracle
+    itself is further than TOL from the exact value -- no further from the exact value than 3x the
+    fp32 oracle is."""
     g = got.detach().cpu()
     e32, e64, ref = rel_err(g, w32), rel_err(g, w64), rel_err(w32, w64)
-    return (e32 < TOL or e64 < TOL or e64 <= 3.0 * ref), (e32, e64, ref)
+    return (e32 < TOL or e64 < TOL or (illcond and e64 <= 3.0 * ref)), (e32, e64, ref)
 
 
-def _check_outputs(outs, o32, o64):
+def _check_outputs(outs, o32, o64, illcond=False):
     for got, w32, w64 in zip(outs, o32, o64):
-        ok, e = _close(got, w32, w64)
+        ok, e = _close(got, w32, w64, illcond)
         assert ok, "output: rel err %.3e vs fp32 oracle, %.3e vs fp64 oracle (fp32 vs fp64 oracle %.3e)" % e
 
 
-def _step_and_compare(net, ora, b, perm, M, O, check_running=True):
+def _step_and_compare(net, ora, b, perm, M, O, check_running=True, illcond=False):
     """One training step through the nn.Module drop-in vs the oracle: outputs, loss, every
     parameter gradient (at the GPU's ReLU activation pattern, see cal_oracle.RELU_OVERRIDE),
     BatchNorm running statistics."""
@@ -99,39 +100,55 @@ def _step_and_compare(net, ora, b, perm, M, O, check_running=True):
     masks = _gpu_relu_masks(eng, N, B)
     o32f, loss32f, _, _, _ = _oracle_step(ora, b, perm, torch.float32)             # free-running reference
     o64f, _, _, _, _ = _oracle_step(ora, b, perm, torch.float64)
-    _check_outputs(outs, o32f, o64f)
+    _check_outputs(outs, o32f, o64f, illcond)
     assert abs(float(loss) - loss32f[0]) < 3 * TOL * max(1.0, abs(loss32f[0]))
     o32, _, g32, after, _ = _oracle_step(ora, b, perm, torch.float32, masks)       # same activation pattern
     _, _, g64, after64, _ = _oracle_step(ora, b, perm, torch.float64, masks)
-    _check_grads({n: grad_or_zero(p) for n, p in net.named_parameters()}, g32, g64)
+    _check_grads({n: grad_or_zero(p) for n, p in net.named_parameters()}, g32, g64, illcond)
     if check_running:
         sd, sd_ref, sd64 = net.state_dict(), after.state_dict(), after64.state_dict()
         for k in sd_ref:
             if "running" in k:
-                ok, e = _close(sd[k], sd_ref[k], sd64[k])
+                ok, e = _close(sd[k], sd_ref[k], sd64[k], illcond)
                 assert ok, "%s: rel err %.3e vs fp32 oracle, %.3e vs fp64 oracle (fp32 vs fp64 oracle %.3e)" % ((k,) + e)
             if "num_batches" in k:
                 assert int(sd[k]) == int(sd_ref[k]), k
     return outs, after
 
 
-def _check_grads(gpu_grads, g32, g64):
-    """Per parameter tensor, max-norm error relative to max(|ref|, 0.1 * the largest gradient entry
-    of the whole model): a gradient passes when it is within TOL of the fp32 reference, or of the
-    exact (fp64) value, or -- for ill-conditioned reductions such as BatchNorm backward over a
-    handful of rows, where the fp32 reference itself is further than TOL from the exact value --
-    no further from the exact value than 3x the fp32 reference's own error.  The scale floor keeps
-    two-element bias gradients that are cancelled sums of O(1) terms (node_att_mlp.bias) from
-    being judged at an absolute accuracy fp32 cannot deliver."""
+# Floor of the per-tensor error scale, as a fraction of the largest gradient entry of the whole model:
+# fp32 cancellation level.  A tensor whose largest entry is below FLOOR * gmax (two-element attention
+# biases that are cancelled sums of O(gmax) terms) is judged against that absolute level instead of its
+# own magnitude; every other tensor is judged relative to ITS OWN largest entry.
+GRAD_FLOOR = 1e-3
+
+
+def grad_errors(gpu_grads, g32, g64):
+    """Per parameter tensor: (name, |g64|max / gmax, e32, e64, ref) with the max-norm errors of the GPU
+    gradient against the fp32 and fp64 oracle and of the fp32 oracle against fp64, each divided by
+    max(|g64|max of THIS tensor, GRAD_FLOOR * gmax)."""
     gmax = max(float(v.abs().max()) for v in g64.values())
-    worst = 0.0
+    rows = []
     for n, want in g32.items():
         got = gpu_grads[n].detach().cpu().double()
         w32, w64 = want.double(), g64[n].double()
-        scale = max(float(w64.abs().max()), 0.1 * gmax, 1e-30)
-        e32, e64, ref_err = (float((got - w32).abs().max()) / scale, float((got - w64).abs().max()) / scale,
-                             float((w32 - w64).abs().max()) / scale)
-        ok = e32 < TOL or e64 < TOL or e64 <= 3.0 * ref_err
+        own = float(w64.abs().max())
+        scale = max(own, GRAD_FLOOR * gmax, 1e-30)
+        rows.append((n, own / max(gmax, 1e-30), float((got - w32).abs().max()) / scale,
+                     float((got - w64).abs().max()) / scale, float((w32 - w64).abs().max()) / scale))
+    return rows
+
+
+def _check_grads(gpu_grads, g32, g64, illcond=False):
+    """Every parameter gradient within TOL (per-tensor max-norm relative error, see grad_errors) of the
+    fp32 reference OR of the exact (fp64) value -- two fp32 summation orders of one reduction can differ
+    from each other by more than either differs from the exact value, so the fp64 oracle arbitrates.
+    `illcond` (named per case: BatchNorm statistics over <= 8 rows, reductions over > 100k rows) also
+    accepts a gradient that is no further from the exact value than 3x the fp32 reference's own error,
+    because there the fp32 reference itself is further than TOL from the exact value."""
+    worst = 0.0
+    for n, _rel, e32, e64, ref_err in grad_errors(gpu_grads, g32, g64):
+        ok = e32 < TOL or e64 < TOL or (illcond and e64 <= 3.0 * ref_err)
         worst = max(worst, min(e32, e64))
         assert ok, "grad %s: rel err %.3e vs fp32 oracle, %.3e vs fp64 oracle (fp32 oracle vs fp64: %.3e)" % (
             n, e32, e64, ref_err)
@@ -187,15 +204,22 @@ def test_module_matches_reference_golden(name):
         assert rel_err(got.detach().cpu(), want) < TOL
     for got, want in zip((loss, c_loss, o_loss, co_loss), gc.loss):
         assert abs(float(got) - want) < TOL * max(1.0, abs(want))
-    # gradients: fp32 golden, fp64 oracle as arbiter
+    # gradients: the fp32 golden (the reference's own autograd) and the fp64 oracle as arbiter, both
+    # FREE-RUNNING (no RELU_OVERRIDE): on the golden cases the ReLU patterns of the GPU and the reference agree
     ora = gc.build(O)
     _, _, g64, _, _ = _oracle_step(ora, gc.batch(), gc.perm, torch.float64)
     gpu = {n: grad_or_zero(p) for n, p in net.named_parameters()}
-    _check_grads(gpu, gc.grads, g64)
+    _check_grads(gpu, gc.grads, g64, illcond=gc.batch().y.numel() <= 8)
     assert net.conv_feat.bias.grad is None            # gfn=True: bias unused (gcn_conv.py:76-77)
     sd = net.state_dict()
     for k, want in gc.after.items():                  # BatchNorm running statistics after the step
         assert rel_err(sd[k].double().cpu(), want.double()) < TOL, k
+
+
+def _illcond(case):
+    """The named ill-conditioned cases: readout BatchNorm statistics over <= 8 graph rows (the fp32
+    reference's own gradients are then further than TOL from the exact value)."""
+    return case["batch_size"] <= 8
 
 
 CASES = [
@@ -218,7 +242,7 @@ CASES = [
 def test_train_step_matches_oracle(case):
     M, O = _mods()
     ora, b, perm = random_case(**case)
-    _step_and_compare(clone_to_cuda(ora, M), ora, b, perm, M, O)
+    _step_and_compare(clone_to_cuda(ora, M), ora, b, perm, M, O, illcond=_illcond(case))
 
 
 def _gat_masks(ora, b, seed, p_drop):
@@ -253,7 +277,7 @@ def test_gin_train_step_matches_oracle(case):
     M, O = _mods()
     ora, b, perm = random_case(**case)
     net = clone_to_cuda(ora, M)
-    _, ora_after = _step_and_compare(net, ora, b, perm, M, O)
+    _, ora_after = _step_and_compare(net, ora, b, perm, M, O, illcond=_illcond(case))
     ora_after.eval()
     with torch.no_grad():
         want = ora_after(b, eval_random=False)
@@ -283,7 +307,7 @@ def test_gat_train_step_matches_oracle(case):
     net = clone_to_cuda(ora, M)
     net.dropout_mask = keyed
     bd = b.to(DEV)
-    _, ora_after = _step_and_compare(net, ora, b, perm, M, O)
+    _, ora_after = _step_and_compare(net, ora, b, perm, M, O, illcond=_illcond(case))
     # eval mode: dropout off, running statistics
     ora_after.eval()
     with torch.no_grad():
@@ -382,7 +406,7 @@ def test_structure_oddities_and_status_word():
     keep = (b.edge_index[0] != N - 1) & (b.edge_index[1] != N - 1)      # isolate the last node
     b.edge_index = b.edge_index[:, keep].contiguous()
     net = clone_to_cuda(ora, M)
-    _, ora = _step_and_compare(net, ora, b, perm, M, O)      # ora: the oracle after the same step
+    _, ora = _step_and_compare(net, ora, b, perm, M, O, illcond=True)      # 6 graphs; ora: the oracle after the same step
     # no edges at all
     b0 = copy.copy(b)
     b0.edge_index = torch.zeros(2, 0, dtype=torch.long)
@@ -519,4 +543,4 @@ def test_full_size_cfg5_shapes():
     M, O = _mods()
     ora, b, perm = random_case(seed=91, hidden=128, layers=3, batch_size=512, features=64, avg_nodes=200,
                                ba_m=2, noise=0.0)
-    _step_and_compare(clone_to_cuda(ora, M), ora, b, perm, M, O)
+    _step_and_compare(clone_to_cuda(ora, M), ora, b, perm, M, O, illcond=True)      # BatchNorm sums over 103 788 rows

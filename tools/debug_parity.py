@@ -66,9 +66,8 @@ def main(name):
     print("loss gpu %.7f  oracle %.7f" % (float(loss), float(tr["loss"])))
     loss.backward()
     torch.cuda.synchronize()
-    DP = eng.region("DPOOL").view(2, Bm, H)
-    show("DPOOL[0] (d gc)", DP[0, :B], gr["gc"])
-    show("DPOOL[1] (d go)", DP[1, :B], gr["go"])
+    DU = eng.region("DU").view(3, Bm, 2 * H)           # d(readout inputs): head 0 = d gc (c head only), head 1 = d go
+    show("DU[0] (d gc, c head)", DU[0, :B, :H], gr["gc"])
     DY = eng.region("DYM").view(2, Nm, H)
     show("DYM[0] (d yc)", DY[0, :N], gr["yc"])
     show("DYM[1] (d yo)", DY[1, :N], gr["yo"])

@@ -1,5 +1,5 @@
 """GPU debugging aid: for seeded random cases compare the backward intermediates held in the
-workspace (DPOOL, DAGG via dW, DYM, D) with the oracle's autograd values."""
+workspace (DU, DAGG via dW, DYM, D) with the oracle's autograd values."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -25,8 +25,8 @@ def run(case):
         e = (got - want).abs()
         rows = (e.view(e.shape[0], -1).max(1)[0] > 1e-4 * want.abs().max()).nonzero().view(-1)
         print("  %-18s rel %.3e  bad rows %d %s" % (name, rel_err(got, want), rows.numel(), rows[:8].tolist()))
-    DP = eng.region("DPOOL").view(2, Bm, H)
-    show("DPOOL[0]", DP[0, :B], gr["gc"]); show("DPOOL[1]", DP[1, :B], gr["go"])
+    DU = eng.region("DU").view(3, Bm, 2 * H)
+    show("DU[0] (c head d gc)", DU[0, :B, :H], gr["gc"])
     DY = eng.region("DYM").view(2, Nm, H)
     show("DYM[0]", DY[0, :N], gr["yc"]); show("DYM[1]", DY[1, :N], gr["yo"])
     Z = eng.region("Z").view(2, Nm, H)
