@@ -13,7 +13,7 @@ namespace {
 constexpr int kKB = 32;   // K elements staged per block (3xTF32: A and B, hi and lo, 128 + 256 rows -> 96 KB)
 
 // kind: 0 = 3xTF32, 1 = TF32, 2 = BF16.  variant bit 0: core matrices contiguous along R instead of along K;
-// bit 1: instruction N rounded to a multiple of 8 instead of 16.
+// bit 1: instruction N rounded to a multiple of 8 instead of 16; bit 2 (with bit 0 clear): K chunks 144 bytes apart.
 __global__ void __launch_bounds__(128) k_selftest_umma(int kind, int M, int N, int K, const float* __restrict__ A,
                                                         const float* __restrict__ B, float* __restrict__ D, int variant) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -28,14 +28,15 @@ __global__ void __launch_bounds__(128) k_selftest_umma(int kind, int M, int N, i
   // byte strides of the canonical layout
   uint32_t lboA, sboA, lboB, sboB;
   if ((variant & 1) == 0) {
-    lboA = lboB = 128;
-    sboA = sboB = (uint32_t)KC * 128;
+    lboA = lboB = (variant & 4) ? 144 : 128;            // bit 2: chunk stride padded by 16 bytes (bank-conflict-free
+    sboA = sboB = (uint32_t)KC * lboA;                  // stores when a warp's lanes walk along K)
   } else {
     sboA = sboB = 128;
     lboA = (uint32_t)(MR / 8) * 128;
     lboB = (uint32_t)(NR / 8) * 128;
   }
-  const uint32_t bytesA = (uint32_t)MR * kKB * ES, bytesB = (uint32_t)NR * kKB * ES;
+  const uint32_t pad = (variant & 4) ? 9 : 8;           // eighths
+  const uint32_t bytesA = (uint32_t)MR * kKB * ES / 8 * pad, bytesB = (uint32_t)NR * kKB * ES / 8 * pad;
   unsigned char* sAh = smem;
   unsigned char* sAl = sAh + bytesA;
   unsigned char* sBh = sAl + bytesA;
@@ -139,7 +140,7 @@ extern "C" int cal_selftest_umma(int kind, int M, int N, int K, const float* A, 
   if (A == nullptr || B == nullptr || D == nullptr) return CAL_ENULL;
   if (kind < 0 || kind > 2 || M < 1 || M > 128 || N < 1 || N > 256 || K < 1 || K > 4096) return CAL_EINVAL;
   const int NR = (variant & 2) ? (N + 7) & ~7 : (N + 15) & ~15, ES = kind == 2 ? 2 : 4;
-  const size_t smem = 2 * (size_t)(128 + NR) * kKB * ES;
+  const size_t smem = 2 * (size_t)(128 + NR) * kKB * ES / 8 * ((variant & 4) ? 9 : 8);
   cudaError_t e = cudaFuncSetAttribute(k_selftest_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   k_selftest_umma<<<1, 128, smem, (cudaStream_t)stream>>>(kind, M, N, K, A, B, D, variant);

@@ -71,7 +71,7 @@ def _gpu_relu_masks(eng, N, B):
 
 def _close(got, w32, w64, illcond=False):
     """Within TOL of the fp32 oracle, or of the exact (fp64) value, or -- only for the cases named
-    ill-conditioned (`illcond`: BatchNorm over <= 8 rows, 100k-row reductions), where the fp32 oracle
+    ill-conditioned (`illcond`: BatchNorm over <= 10 rows, 100k-row reductions), where the fp32 oracle
     itself is further than TOL from the exact value -- no further from the exact value than 3x the
     fp32 oracle is."""
     g = got.detach().cpu()
@@ -116,24 +116,39 @@ def _step_and_compare(net, ora, b, perm, M, O, check_running=True, illcond=False
     return outs, after
 
 
-# Floor of the per-tensor error scale, as a fraction of the largest gradient entry of the whole model:
-# fp32 cancellation level.  A tensor whose largest entry is below FLOOR * gmax (two-element attention
-# biases that are cancelled sums of O(gmax) terms) is judged against that absolute level instead of its
-# own magnitude; every other tensor is judged relative to ITS OWN largest entry.
+# Per-tensor error scale.  A gradient tensor is judged relative to ITS OWN largest entry (of the exact,
+# fp64 value), with three named exceptions -- measured in profiles/grad_errors_r02.txt:
+#  * GRAD_FLOOR: a tensor whose largest entry is below 1e-3 of the model's largest gradient entry is judged
+#    against that absolute level (fp32 cancellation level of sums of O(gmax) terms);
+#  * ATT_BIAS_FLOOR: the two-element attention biases (node_att_mlp.bias, edge_att_mlp.bias) are the sum
+#    over ALL nodes / edges of softmax gradients that cancel to ~1e-3 gmax: floor 1e-2 gmax;
+#  * structurally zero gradients: a bias that feeds a BatchNorm directly (CausalGIN convs.i.nn.0.bias)
+#    has an exact gradient of 0 (|g64| ~ 1e-16 gmax); what any fp32 evaluation -- the reference's
+#    included -- returns is rounding noise.  Required: |got| <= ZERO_NOISE * gmax.
 GRAD_FLOOR = 1e-3
+ATT_BIAS_FLOOR = 1e-2
+ATT_BIASES = ("node_att_mlp.bias", "edge_att_mlp.bias")
+ZERO_EXACT = 1e-10
+ZERO_NOISE = 1e-6
 
 
 def grad_errors(gpu_grads, g32, g64):
     """Per parameter tensor: (name, |g64|max / gmax, e32, e64, ref) with the max-norm errors of the GPU
-    gradient against the fp32 and fp64 oracle and of the fp32 oracle against fp64, each divided by
-    max(|g64|max of THIS tensor, GRAD_FLOOR * gmax)."""
+    gradient against the fp32 and fp64 oracle and of the fp32 oracle against fp64, each divided by the
+    tensor's scale (see above).  For a structurally zero gradient e32 = e64 = |got|max / (ZERO_NOISE *
+    gmax) * TOL, i.e. it passes the TOL test exactly when the noise bound holds."""
     gmax = max(float(v.abs().max()) for v in g64.values())
     rows = []
     for n, want in g32.items():
         got = gpu_grads[n].detach().cpu().double()
         w32, w64 = want.double(), g64[n].double()
         own = float(w64.abs().max())
-        scale = max(own, GRAD_FLOOR * gmax, 1e-30)
+        if own <= ZERO_EXACT * gmax and gmax > 0:
+            e = float(got.abs().max()) / (ZERO_NOISE * gmax) * TOL
+            rows.append((n, own / gmax, e, e, float(w32.abs().max()) / (ZERO_NOISE * gmax) * TOL))
+            continue
+        floor = ATT_BIAS_FLOOR if n in ATT_BIASES else GRAD_FLOOR
+        scale = max(own, floor * gmax, 1e-30)
         rows.append((n, own / max(gmax, 1e-30), float((got - w32).abs().max()) / scale,
                      float((got - w64).abs().max()) / scale, float((w32 - w64).abs().max()) / scale))
     return rows
@@ -143,7 +158,7 @@ def _check_grads(gpu_grads, g32, g64, illcond=False):
     """Every parameter gradient within TOL (per-tensor max-norm relative error, see grad_errors) of the
     fp32 reference OR of the exact (fp64) value -- two fp32 summation orders of one reduction can differ
     from each other by more than either differs from the exact value, so the fp64 oracle arbitrates.
-    `illcond` (named per case: BatchNorm statistics over <= 8 rows, reductions over > 100k rows) also
+    `illcond` (named per case: BatchNorm statistics over <= 10 rows, reductions over > 100k rows) also
     accepts a gradient that is no further from the exact value than 3x the fp32 reference's own error,
     because there the fp32 reference itself is further than TOL from the exact value."""
     worst = 0.0
@@ -209,7 +224,7 @@ def test_module_matches_reference_golden(name):
     ora = gc.build(O)
     _, _, g64, _, _ = _oracle_step(ora, gc.batch(), gc.perm, torch.float64)
     gpu = {n: grad_or_zero(p) for n, p in net.named_parameters()}
-    _check_grads(gpu, gc.grads, g64, illcond=gc.batch().y.numel() <= 8)
+    _check_grads(gpu, gc.grads, g64, illcond=gc.batch().y.numel() <= 10)
     assert net.conv_feat.bias.grad is None            # gfn=True: bias unused (gcn_conv.py:76-77)
     sd = net.state_dict()
     for k, want in gc.after.items():                  # BatchNorm running statistics after the step
@@ -217,9 +232,10 @@ def test_module_matches_reference_golden(name):
 
 
 def _illcond(case):
-    """The named ill-conditioned cases: readout BatchNorm statistics over <= 8 graph rows (the fp32
-    reference's own gradients are then further than TOL from the exact value)."""
-    return case["batch_size"] <= 8
+    """The named ill-conditioned cases: readout BatchNorm statistics over <= 10 graph rows (the fp32
+    reference's own gradients are then up to ~2e-5 from the exact value: profiles/grad_errors_r02.txt,
+    seeds 5, 6, 11, 204, 205)."""
+    return case["batch_size"] <= 10
 
 
 CASES = [

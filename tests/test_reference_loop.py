@@ -95,6 +95,10 @@ def test_reference_loops_drive_the_cuda_modules(kind):
         for a, b in zip(g, w):
             assert abs(a - b) < 1e-4 * max(1.0, abs(b)), (got, want)
     for (n, p), (_, q) in zip(net.named_parameters(), ora.named_parameters()):
+        if kind == "CausalGIN" and n.endswith(".nn.0.bias"):
+            # a bias feeding a BatchNorm has an exact gradient of 0: every fp32 evaluation (the reference's too)
+            # returns rounding noise, which Adam normalises into +-lr steps -- the trajectories are not comparable
+            continue
         assert rel_err(p.detach().cpu(), q.detach()) < 2e-4, n      # 4 Adam steps from identical states
     sd, sr = net.state_dict(), ora.state_dict()
     for k in sr:

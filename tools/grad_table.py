@@ -5,7 +5,8 @@
 For every golden case (free-running reference gradients frozen from the unmodified reference model code)
 and every seeded case of tests/test_gpu_parity.py it prints, per parameter tensor, the tensor's largest
 gradient entry relative to the model's largest (|g|/gmax) and the max-norm errors -- divided by
-max(|g64|max of the tensor, GRAD_FLOOR * gmax), exactly the rule tests/test_gpu_parity.py asserts --
+the tensor's scale (tests/test_gpu_parity.py::grad_errors: its own largest entry, with the named floors), exactly
+the rule the tests assert --
 of the GPU gradient against the fp32 reference (e32), against the fp64 oracle (e64), and of the fp32
 reference against the fp64 oracle (ref).  A line is marked PASS when e32 < 1e-5 or e64 < 1e-5."""
 import os

@@ -41,7 +41,8 @@ def main():
             cfgs += [(kind, 128, 128, 128, variant), (kind, 128, 32, 32, variant), (kind, 100, 48, 40, variant)]
     cfgs += [(0, 128, 16, 128, 0), (0, 128, 24, 128, 0), (0, 128, 8, 128, 0), (0, 128, 200, 64, 0), (0, 128, 256, 256, 0),
              (0, 128, 128, 1024, 0), (2, 128, 128, 1024, 0), (0, 7, 5, 3, 0),
-             (0, 128, 24, 128, 2), (0, 128, 8, 64, 2), (0, 128, 40, 64, 2), (2, 128, 24, 64, 2)]
+             (0, 128, 24, 128, 2), (0, 128, 8, 64, 2), (0, 128, 40, 64, 2), (2, 128, 24, 64, 2),
+             (0, 128, 128, 128, 4), (0, 128, 32, 96, 4), (2, 128, 64, 128, 4), (0, 128, 24, 128, 6)]
     for c in cfgs:
         r = subprocess.run([sys.executable, os.path.abspath(__file__)] + [str(v) for v in c], capture_output=True, text=True,
                            timeout=120)
