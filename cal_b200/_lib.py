@@ -49,7 +49,7 @@ class ModelDesc(C.Structure):
                 ("cat", C.c_int32), ("without_node_attention", C.c_int32),
                 ("without_edge_attention", C.c_int32), ("gat_dropout", C.c_float),
                 ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
-                ("w_c", C.c_float), ("w_o", C.c_float), ("w_co", C.c_float)]
+                ("w_c", C.c_float), ("w_o", C.c_float), ("w_co", C.c_float), ("readout_bf16", C.c_int32)]
 
 
 class Caps(C.Structure):
@@ -169,7 +169,7 @@ def load():
     lib.cal_selftest_umma.restype = C.c_int
     lib.cal_selftest_umma.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                       C.c_void_p]
-    if lib.cal_abi_version() != 1:
+    if lib.cal_abi_version() != 2:
         raise CalError("cal_b200: ABI version mismatch")
     _lib = lib
     return lib

@@ -61,6 +61,7 @@ int build_ctx(const cal_model_desc* m, const cal_caps* caps, const cal_param_off
   c.w_o = m->w_o;
   c.w_co = m->w_co;
   c.gat_p = m->gat_dropout;
+  c.readout_bf16 = m->readout_bf16 != 0;
   c.Nm = caps->max_nodes;
   c.Em = caps->max_edges;
   c.Bm = caps->max_graphs;

@@ -13,6 +13,8 @@
 // [rows x H] partial products through distributed shared memory (reduce-scatter by column slice).
 // Parameter gradients of the readout are written straight into the flat gradient buffer.
 #include <cooperative_groups.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "internal.cuh"
 
@@ -799,8 +801,24 @@ size_t readout_smem_bytes(int Bm, int H, int cat, int C, int backward) {
   return readout_smem(Bp, H, (cat ? 2 : 1) * (H / kRC), C, backward != 0).total;
 }
 
+// CAL_READOUT=legacy (environment, read once): the fp32 FFMA cluster kernels below instead of the
+// tensor-core readout of head_tc.cu (kept for A/B measurements and for capacities beyond 512 graphs).
+static bool use_tc(const Ctx& c) {
+  static const bool legacy = [] {
+    const char* e = getenv("CAL_READOUT");
+    return e != nullptr && strcmp(e, "legacy") == 0;
+  }();
+  return !legacy && readout_tc_supported(c);
+}
+
 int launch_heads_forward(const Ctx& c, int with_loss, cudaStream_t s) {
   (void)with_loss;
+  if (use_tc(c)) {
+    CAL_DISPATCH_VEC(c.H, { launch_k(k_pool<VEC>, dim3(c.Bm), dim3(256), 0, s, c); });
+    note_launches(1);
+    CAL_CUDA_CHECK_LAUNCH();
+    return launch_readout_tc_forward(c, s);
+  }
   CAL_DISPATCH_VEC(c.H, {
     launch_k(k_pool<VEC>, dim3(c.Bm), dim3(256), 0, s, c);
     const size_t smem = readout_smem_bytes(c.Bm, c.H, c.cat, c.C, 0);
@@ -814,6 +832,7 @@ int launch_heads_forward(const Ctx& c, int with_loss, cudaStream_t s) {
 }
 
 int launch_heads_backward(const Ctx& c, cudaStream_t s) {
+  if (use_tc(c)) return launch_readout_tc_backward(c, s);
   CAL_DISPATCH_VEC(c.H, {
     const size_t smem = readout_smem_bytes(c.Bm, c.H, c.cat, c.C, 1);
     int rc = set_smem_h(k_readout_bwd<VEC>, smem);

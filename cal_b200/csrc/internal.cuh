@@ -49,7 +49,7 @@ struct Layout {
 // Everything a kernel needs, passed by value.
 struct Ctx {
   // model
-  int model, F, H, C, L, heads, cat, no_natt, no_eatt, train;
+  int model, F, H, C, L, heads, cat, no_natt, no_eatt, train, readout_bf16;
   float eps, momentum, w_c, w_o, w_co, gat_p;
   // capacities and plan
   int Nm, Em, Bm, EP, kmax, g_tile, g_row, t_head1, g_head2;
@@ -121,6 +121,9 @@ int launch_edge_att(const Ctx& c, cudaStream_t s);
 int launch_masked_forward(const Ctx& c, cudaStream_t s);
 int launch_heads_forward(const Ctx& c, int with_loss, cudaStream_t s);
 int launch_heads_backward(const Ctx& c, cudaStream_t s);
+bool readout_tc_supported(const Ctx& c);                                   // tensor-core readout (head_tc.cu)
+int launch_readout_tc_forward(const Ctx& c, cudaStream_t s);
+int launch_readout_tc_backward(const Ctx& c, cudaStream_t s);
 int launch_masked_bwd_gemm(const Ctx& c, cudaStream_t s);
 int launch_masked_bwd_gather(const Ctx& c, cudaStream_t s);
 int launch_norm_backward(const Ctx& c, cudaStream_t s);

@@ -141,6 +141,8 @@ class Engine:
         d.w_c = float(getattr(m.args, "c", 0.5))
         d.w_o = float(getattr(m.args, "o", 1.0))
         d.w_co = float(getattr(m.args, "co", 0.5))
+        # not a reference option: bf16 operands (fp32 accumulate) in the readout MLP GEMMs (BASELINE.json configs[4])
+        d.readout_bf16 = int(bool(getattr(m.args, "readout_bf16", False)))
         self.desc = d
         self._flatten()
         self.caps = None

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CAL_ABI_VERSION 1
+#define CAL_ABI_VERSION 2
 #define CAL_MAX_LAYERS 8
 #define CAL_MAX_BN (1 + CAL_MAX_LAYERS + 2 + 6)
 
@@ -67,6 +67,8 @@ typedef struct {
   float bn_eps;                /* 1e-5 */
   float bn_momentum;           /* 0.1 */
   float w_c, w_o, w_co;        /* loss weights args.c / args.o / args.co */
+  int32_t readout_bf16;        /* 0: readout MLP GEMMs as 3xTF32 on the tensor cores (fp32 accuracy, the 1e-5 parity path);
+                                  1: bf16 operands, fp32 accumulate (BASELINE.json configs[4] "bf16 MLP / fp32 aggregate") */
 } cal_model_desc;
 
 /* Capacities a workspace is sized for. */

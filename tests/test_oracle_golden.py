@@ -19,7 +19,7 @@ def test_oracle_matches_reference_golden(name):
         for got, want in zip(outs, gc.outs):
             assert rel_err(got.detach(), want) < TOL
         for got, want in zip(losses, gc.loss):
-            assert abs(float(got) - want) < 1e-6 * max(1.0, abs(want))
+            assert abs(float(got.detach()) - want) < TOL * max(1.0, abs(want))     # (threaded CPU reductions: order varies with load)
         for n, p in net.named_parameters():
             want = gc.grads[n]
             got = p.grad if p.grad is not None else torch.zeros_like(p)
