@@ -1,0 +1,65 @@
+// fsg.cuh -- shared definitions of the fused small-graph path (fsg.cu, fsg_prep in prep.cu).
+//
+// "Small graphs": every graph of the batch has at most kFsgRows nodes and kFsgEntries CSR entries (edges
+// after self-loop surgery), and the batch has at most kSMs row blocks.  Then a CTA owns a BLOCK of whole
+// graphs (<= kFsgRows rows) for the entire forward (backward) pass: message passing is local to the CTA's
+// shared memory, node transforms run on the tensor cores with the node rows on the MMA's N dimension,
+// and only the BatchNorm statistics cross CTAs (one in-kernel all-reduce per BatchNorm boundary).
+#pragma once
+#include "internal.cuh"
+
+namespace cal {
+
+constexpr int kFsgRows = 40;            // rows (nodes) per block: 5 groups of 8
+constexpr int kFsgEntries = 320;        // CSR entries per block
+constexpr int kFsgPhases = 24;          // all-reduce sites per launch
+constexpr int kFsgVec = 512;            // doubles per all-reduce vector slot
+constexpr int kFsgGroup = 8;            // CTAs per first-level group
+constexpr int kFsgMaxGroups = 20;
+constexpr int kFsgCntStride = 40;       // counters per phase: [0] second level, [1 + g] first level
+constexpr int kFsgImgPart = 16384;      // floats of one operand part (128 x 128)
+constexpr int kFsgImg = 2 * kFsgImgPart;   // hi | lo
+
+// the CAL_WS_FSG region (byte offsets)
+struct FsgLayout {
+  size_t plan, info, cnt, l0, l1, img, total;
+};
+__host__ __device__ inline size_t fsg_up(size_t x) { return (x + 255) & ~(size_t)255; }
+__host__ __device__ inline FsgLayout fsg_layout(int Bm, int L) {
+  FsgLayout f;
+  size_t o = 0;
+  f.plan = o;  o = fsg_up(o + 16);                                        // i32[4]: number of blocks, ok flag
+  f.info = o;  o = fsg_up(o + (size_t)(Bm > 0 ? Bm : 1) * 32);            // i32[8] per block
+  f.cnt = o;   o = fsg_up(o + (size_t)(kFsgPhases * kFsgCntStride + 8) * 4);
+  f.l0 = o;    o = fsg_up(o + (size_t)kSMs * kFsgVec * 8);
+  f.l1 = o;    o = fsg_up(o + (size_t)2 * kFsgMaxGroups * kFsgVec * 8);
+  f.img = o;   o = fsg_up(o + (size_t)((L + 2) * 2 + 1) * kFsgImg * 4);   // forward / backward image per conv matrix + feat
+  f.total = o;
+  return f;
+}
+
+struct FsgWs {
+  int* plan;
+  int* info;
+  unsigned int* cnt;
+  double* l0;
+  double* l1;
+  float* img;
+};
+__host__ __device__ inline FsgWs fsg_ws(const Ctx& c) {
+  const FsgLayout f = fsg_layout(c.Bm, c.L);
+  FsgWs w;
+  w.plan = reinterpret_cast<int*>(c.fsg + f.plan);
+  w.info = reinterpret_cast<int*>(c.fsg + f.info);
+  w.cnt = reinterpret_cast<unsigned int*>(c.fsg + f.cnt);
+  w.l0 = reinterpret_cast<double*>(c.fsg + f.l0);
+  w.l1 = reinterpret_cast<double*>(c.fsg + f.l1);
+  w.img = reinterpret_cast<float*>(c.fsg + f.img);
+  return w;
+}
+// weight-operand images: matrix j in [0, L+2) = convs[j] / context_convs / objects_convs
+__host__ __device__ inline float* fsg_img_fwd(const FsgWs& w, int j) { return w.img + (size_t)(2 * j) * kFsgImg; }
+__host__ __device__ inline float* fsg_img_bwd(const FsgWs& w, int j) { return w.img + (size_t)(2 * j + 1) * kFsgImg; }
+__host__ __device__ inline float* fsg_img_feat(const FsgWs& w, int L) { return w.img + (size_t)(2 * (L + 2)) * kFsgImg; }
+
+}  // namespace cal

@@ -801,23 +801,37 @@ size_t readout_smem_bytes(int Bm, int H, int cat, int C, int backward) {
   return readout_smem(Bp, H, (cat ? 2 : 1) * (H / kRC), C, backward != 0).total;
 }
 
-// CAL_READOUT=legacy (environment, read once): the fp32 FFMA cluster kernels below instead of the
-// tensor-core readout of head_tc.cu (kept for A/B measurements and for capacities beyond 512 graphs).
-static bool use_tc(const Ctx& c) {
-  static const bool legacy = [] {
+// Which readout kernels run: 2 = the resident-tile tensor-core kernels (head_tc2.cu: B <= 128, "add", C <= 8),
+// 1 = the streaming tensor-core kernels (head_tc.cu: B <= 512; slower, used when bf16 is requested outside
+// the envelope of 2), 0 = the fp32 FFMA cluster kernels below.  CAL_READOUT=legacy|tc1|tc2 (environment,
+// read once) forces a path for A/B measurements.
+static int readout_path(const Ctx& c) {
+  static const int forced = [] {
     const char* e = getenv("CAL_READOUT");
-    return e != nullptr && strcmp(e, "legacy") == 0;
+    if (e == nullptr) return -1;
+    if (strcmp(e, "legacy") == 0) return 0;
+    if (strcmp(e, "tc1") == 0) return 1;
+    if (strcmp(e, "tc2") == 0) return 2;
+    return -1;
   }();
-  return !legacy && readout_tc_supported(c);
+  const bool legacy_fits = readout_smem_bytes(c.Bm, c.H, c.cat, c.C, 1) <= 225 * 1024 &&
+                           readout_smem_bytes(c.Bm, c.H, c.cat, c.C, 0) <= 225 * 1024;
+  if (forced == 2 && readout_tc2_supported(c)) return 2;
+  if (forced == 1 && readout_tc_supported(c)) return 1;
+  if (forced == 0 && legacy_fits) return 0;
+  if (readout_tc2_supported(c)) return 2;
+  if ((c.readout_bf16 || !legacy_fits) && readout_tc_supported(c)) return 1;
+  return 0;
 }
 
 int launch_heads_forward(const Ctx& c, int with_loss, cudaStream_t s) {
   (void)with_loss;
-  if (use_tc(c)) {
+  const int path = readout_path(c);
+  if (path != 0) {
     CAL_DISPATCH_VEC(c.H, { launch_k(k_pool<VEC>, dim3(c.Bm), dim3(256), 0, s, c); });
     note_launches(1);
     CAL_CUDA_CHECK_LAUNCH();
-    return launch_readout_tc_forward(c, s);
+    return path == 2 ? launch_readout_tc2_forward(c, s) : launch_readout_tc_forward(c, s);
   }
   CAL_DISPATCH_VEC(c.H, {
     launch_k(k_pool<VEC>, dim3(c.Bm), dim3(256), 0, s, c);
@@ -832,7 +846,8 @@ int launch_heads_forward(const Ctx& c, int with_loss, cudaStream_t s) {
 }
 
 int launch_heads_backward(const Ctx& c, cudaStream_t s) {
-  if (use_tc(c)) return launch_readout_tc_backward(c, s);
+  const int path = readout_path(c);
+  if (path != 0) return path == 2 ? launch_readout_tc2_backward(c, s) : launch_readout_tc_backward(c, s);
   CAL_DISPATCH_VEC(c.H, {
     const size_t smem = readout_smem_bytes(c.Bm, c.H, c.cat, c.C, 1);
     int rc = set_smem_h(k_readout_bwd<VEC>, smem);

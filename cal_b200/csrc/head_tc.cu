@@ -231,7 +231,9 @@ __global__ void __launch_bounds__(kT, 1) k_readout_tc_fwd(const Ctx c) {
   for (int i = t; i < C * H; i += kT) sW2[i] = c.params[c.po.fc2_w[h] + i];
   const float* W1 = c.params + c.po.fc1_w[h];                         // [H][K1]
   umma::fence_before_sync();
+  PT_DECL
   pdl_sync();                                                         // everything below may read the predecessor's output
+  PT_MARK();                                                          // 0: dependency wait
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = tmem_slot;
@@ -239,6 +241,7 @@ __global__ void __launch_bounds__(kT, 1) k_readout_tc_fwd(const Ctx c) {
   for (int i = t; i < B; i += kT) sPerm[i] = c.perm[i];
   __syncthreads();
   HeadIn in = {c.pooled, c.pooled + (size_t)c.Bm * H, sPerm, h, H, c.cat};
+  PT_MARK();                                                          // 1: tmem + perm
 
   // ---- bn1: thread = input channel; statistics over the B graph rows in a fixed order ----
   if (t < K1) {
@@ -288,6 +291,7 @@ __global__ void __launch_bounds__(kT, 1) k_readout_tc_fwd(const Ctx c) {
     c.nbt[bn2] += 1;
   }
   __syncthreads();
+  PT_MARK();                                                          // 2: bn1 statistics
 
   // ---- fc1 on the tensor cores: a1^T[m][b] = sum_k W1[m][k] * y1[b][k], 128 graph rows per N block ----
   Pipe ps = {{0u, 0u}, 0u};
@@ -315,7 +319,9 @@ __global__ void __launch_bounds__(kT, 1) k_readout_tc_fwd(const Ctx c) {
           }
         });
   }
+  PT_MARK();                                                          // 3: fc1 staging + issue
   gemm_wait(bars, ps);
+  PT_MARK();                                                          // 4: fc1 MMA tail
 
   // ---- epilogue 1: thread = (hidden channel m, column half): bias + ReLU, save h1, bn2 statistics ----
   const int m = q * 32 + lane;
@@ -371,6 +377,7 @@ __global__ void __launch_bounds__(kT, 1) k_readout_tc_fwd(const Ctx c) {
     sh2[t] = sh;
   }
   __syncthreads();
+  PT_MARK();                                                          // 5: epilogue 1 + bn2
 
   // ---- epilogue 2: y2 = bn2(h1) as a [m][b] tile in shared memory (the ring is free), then
   //      fc2: logits[b][cls] = sum_m y2[m][b] * W2[cls][m] + b2[cls]  (C <= 32: 128 x C x 128 FMAs) ----
@@ -398,6 +405,7 @@ __global__ void __launch_bounds__(kT, 1) k_readout_tc_fwd(const Ctx c) {
     __syncthreads();
   }
 
+  PT_MARK();                                                          // 6: y2 tile + fc2
   // ---- log_softmax, outputs, loss parts (train_causal.py:178-186) ----
   float loss_part = 0.f, correct_part = 0.f;
   for (int b = t; b < B; b += kT) {
@@ -455,6 +463,8 @@ __global__ void __launch_bounds__(kT, 1) k_readout_tc_fwd(const Ctx c) {
       }
     }
   }
+  PT_MARK();                                                          // 7: log_softmax + loss
+  PT_DUMP(c, 64);
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
@@ -493,7 +503,9 @@ __global__ void __launch_bounds__(kT, 1) k_readout_tc_bwd(const Ctx c) {
   for (int i = t; i < C * H; i += kT) sW2[i] = c.params[c.po.fc2_w[h] + i];
   const float* W1 = c.params + c.po.fc1_w[h];                         // [H][K1]
   umma::fence_before_sync();
+  PT_DECL
   pdl_sync();
+  PT_MARK();                                                          // 0: dependency wait
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = tmem_slot;
@@ -524,6 +536,7 @@ __global__ void __launch_bounds__(kT, 1) k_readout_tc_bwd(const Ctx c) {
   }
   __syncthreads();
   HeadIn in = {c.pooled, c.pooled + (size_t)c.Bm * H, sPerm, h, H, c.cat};
+  PT_MARK();                                                          // 1: d logits
 
   // ---- fc2 / bn2 backward: thread = (hidden channel m, half of the graph rows), everything local ----
   const int m = q * 32 + lane;
@@ -604,6 +617,7 @@ __global__ void __launch_bounds__(kT, 1) k_readout_tc_bwd(const Ctx c) {
     if (half == 0 && live) c.grads[c.po.fc1_b[h] + m] = wr[m] + wr[128 + m];
   }
   __syncthreads();                                     // DH (global, written by this CTA) is visible to all its threads
+  PT_MARK();                                                          // 2: fc2 / bn2 backward, d a1
 
   // ---- d W1[m][k] = sum_b da1[b][m] * y1[b][k]: M = hidden channels, N = input channels, K = graph rows ----
   Pipe ps = {{0u, 0u}, 0u};
@@ -621,7 +635,9 @@ __global__ void __launch_bounds__(kT, 1) k_readout_tc_bwd(const Ctx c) {
           for (int e = 0; e < 4; ++e) v[e] = (kk < K1 && k + e < B) ? fmaf(in.at(k + e, kk), sc1[kk], sh1[kk]) : 0.f;
         });
   }
+  PT_MARK();                                                          // 3: d W1 staging + issue
   gemm_wait(bars, ps);
+  PT_MARK();                                                          // 4: d W1 MMA tail
   for (int kb = 0; kb < nkb; ++kb) {
 #pragma unroll
     for (int cc = 0; cc < 2; ++cc) {
@@ -638,6 +654,7 @@ __global__ void __launch_bounds__(kT, 1) k_readout_tc_bwd(const Ctx c) {
   }
   umma::fence_before_sync();                           // the accumulator columns are reused below
   __syncthreads();
+  PT_MARK();                                                          // 5: d W1 store
 
   // ---- d y1[b][k] = sum_m da1[b][m] * W1[m][k]: M = input channels (128 per pass), N = graph rows, K = hidden ----
   const int nblk = (B + 127) / 128;
@@ -660,7 +677,9 @@ __global__ void __launch_bounds__(kT, 1) k_readout_tc_bwd(const Ctx c) {
             }
           });
     }
+    PT_MARK();                                                        // 6: d y1 staging + issue
     gemm_wait(bars, ps);
+    PT_MARK();                                                        // 7: d y1 MMA tail
     // bn1 backward: thread = (input channel kk, column half), two passes over the accumulator
     const int kk = kb * 128 + m;
     const bool lk = kk < K1;
@@ -710,7 +729,9 @@ __global__ void __launch_bounds__(kT, 1) k_readout_tc_bwd(const Ctx c) {
     }
     umma::fence_before_sync();
     __syncthreads();
+    PT_MARK();                                                        // 8: bn1 backward + d u
   }
+  PT_DUMP(c, 80);
   if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
 }
 

@@ -124,6 +124,9 @@ int launch_heads_backward(const Ctx& c, cudaStream_t s);
 bool readout_tc_supported(const Ctx& c);                                   // tensor-core readout (head_tc.cu)
 int launch_readout_tc_forward(const Ctx& c, cudaStream_t s);
 int launch_readout_tc_backward(const Ctx& c, cudaStream_t s);
+bool readout_tc2_supported(const Ctx& c);                                  // resident-tile variant (head_tc2.cu)
+int launch_readout_tc2_forward(const Ctx& c, cudaStream_t s);
+int launch_readout_tc2_backward(const Ctx& c, cudaStream_t s);
 int launch_masked_bwd_gemm(const Ctx& c, cudaStream_t s);
 int launch_masked_bwd_gather(const Ctx& c, cudaStream_t s);
 int launch_norm_backward(const Ctx& c, cudaStream_t s);

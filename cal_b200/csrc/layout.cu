@@ -24,9 +24,11 @@ int compute_layout(const cal_model_desc* m, const cal_caps* caps, Layout* lay) {
   if (rc != CAL_OK) return rc;
   if (caps == nullptr) return CAL_ENULL;
   if (caps->max_nodes < 1 || caps->max_edges < 0 || caps->max_graphs < 1) return CAL_EINVAL;
-  // the readout kernels keep all graph rows of a column slice in one CTA's shared memory
-  if (readout_smem_bytes(caps->max_graphs, m->hidden, m->cat != 0, m->num_classes, 1) > 225 * 1024 ||
-      readout_smem_bytes(caps->max_graphs, m->hidden, m->cat != 0, m->num_classes, 0) > 225 * 1024)
+  // the FFMA readout kernels keep all graph rows of a column slice in one CTA's shared memory; beyond that
+  // the streaming tensor-core kernels (head_tc.cu) serve up to 512 graphs
+  if ((readout_smem_bytes(caps->max_graphs, m->hidden, m->cat != 0, m->num_classes, 1) > 225 * 1024 ||
+       readout_smem_bytes(caps->max_graphs, m->hidden, m->cat != 0, m->num_classes, 0) > 225 * 1024) &&
+      caps->max_graphs > 512)
     return CAL_EUNSUPPORTED;
   const size_t Nm = caps->max_nodes, Em = caps->max_edges, Bm = caps->max_graphs, EP = Em + Nm;
   const size_t H = m->hidden, F = m->num_features, C = m->num_classes, L = m->layers;

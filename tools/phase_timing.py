@@ -19,8 +19,11 @@ names_f = ["prologue", "csr ptr", "csr seg", "gather", "wait W/sync", "gemm", "e
 names_b = ["prologue", "csr ptr", "stage+gather", "wait W/sync", "gemm dX", "dX store", "dW outer", "dW store", "reduce+finalize"]
 print("k_conv_fwd (last launched = MODE 2 masked, no reduce) cycles:", list(zip(names_f, st[16:24])), "sum", sum(st[16:24]))
 print("k_conv_bwd (layer 0) cycles:", list(zip(names_b, st[32:41])), "sum", sum(st[32:41]))
-print("k_readout_fwd (head 0, slice 0) cycles:", st[64:74], "sum", sum(st[64:74]))
-print("k_readout_bwd (head 0, slice 0) cycles:", st[80:88], "sum", sum(st[80:88]))
+names_rf = ["dep wait", "tmem+perm", "bn1 stats", "fc1 stage+issue", "fc1 mma tail", "epi1+bn2", "y2+fc2", "softmax+loss"]
+names_rb = ["dep wait", "d logits", "fc2/bn2 bwd + da1", "dW1 stage+issue", "dW1 mma tail", "dW1 store", "dy1 stage+issue",
+            "dy1 mma tail", "bn1 bwd + du"]
+print("k_readout_tc_fwd (head 0) cycles:", list(zip(names_rf, st[64:72])), "sum", sum(st[64:72]))
+print("k_readout_tc_bwd (head 0) cycles:", list(zip(names_rb, st[80:89])), "sum", sum(st[80:89]))
 names_p = ["wait+zero", "edges+counts", "node pass", "scan", "fill", "sort", "write-out"]
 print("k_prep_small structure CTA (slice 0) cycles:", list(zip(names_p, st[96:103])), "sum", sum(st[96:103]))
 print("k_prep_small statistics CTA 0 [column sums, grid sum]:", st[112:114], " finishing CTA:", st[116:118])
