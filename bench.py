@@ -354,7 +354,7 @@ def run_gpu(a, rank, local_rank, world):
     # reused within ~L2 worth of input bytes) -- the "inputs larger than L2" timing rule
     probe, cfg = build_batches(a.workload, bs, 2, 4 * bs, 666 + rank)
     caps_probe = cal_b200.batch_caps(probe, slack=1.15)
-    lay_probe = cal_b200.PackedLayout(*caps_probe, probe[0].feat.size(1))
+    lay_probe = cal_b200.PackedLayout(*caps_probe[:3], probe[0].feat.size(1))
     n_res = a.resident or int(min(max(L2_BYTES // lay_probe.nbytes + 8, 16), 1024))
     if dist is not None:                      # every rank must issue the same number of collectives
         t = torch.tensor([n_res], dtype=torch.int64, device=dev)

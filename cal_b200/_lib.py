@@ -23,7 +23,7 @@ WS_REGIONS = [
     "OUT_KEY", "CNT_IN", "CNT_OUT", "GRAPH_PTR", "NODE_GRAPH", "PERM", "INVPERM", "DIS", "X",
     "NODE_ATT", "PQ", "EDGE_ATT", "DISW", "AGG", "Z", "POOLED", "H1", "LOGP", "LOSS", "BN", "STATP",
     "WT", "GAT", "DLOGIT", "DH", "DU", "DAGG", "DYM", "DNRM", "DT", "DP", "D", "GPART",
-    "OUT_NORM", "EDGE_WN", "EDGE_NA",
+    "OUT_NORM", "EDGE_WN", "EDGE_NA", "FSG",
 ]
 WS = {n: i for i, n in enumerate(WS_REGIONS)}
 
@@ -49,12 +49,12 @@ class ModelDesc(C.Structure):
                 ("cat", C.c_int32), ("without_node_attention", C.c_int32),
                 ("without_edge_attention", C.c_int32), ("gat_dropout", C.c_float),
                 ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
-                ("w_c", C.c_float), ("w_o", C.c_float), ("w_co", C.c_float), ("readout_bf16", C.c_int32)]
+                ("w_c", C.c_float), ("w_o", C.c_float), ("w_co", C.c_float), ("readout_bf16", C.c_int32), ("readout_tc", C.c_int32)]
 
 
 class Caps(C.Structure):
     _fields_ = [("max_nodes", C.c_int32), ("max_edges", C.c_int32), ("max_graphs", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("small_graphs", C.c_int32)]
 
 
 class ParamOffsets(C.Structure):

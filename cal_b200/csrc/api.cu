@@ -62,6 +62,7 @@ int build_ctx(const cal_model_desc* m, const cal_caps* caps, const cal_param_off
   c.w_co = m->w_co;
   c.gat_p = m->gat_dropout;
   c.readout_bf16 = m->readout_bf16 != 0;
+  c.readout_tc = m->readout_tc != 0;
   c.Nm = caps->max_nodes;
   c.Em = caps->max_edges;
   c.Bm = caps->max_graphs;
@@ -162,6 +163,9 @@ int build_ctx(const cal_model_desc* m, const cal_caps* caps, const cal_param_off
   c.out_norm = REG(float, CAL_WS_OUT_NORM);
   c.edge_wn = REG(float, CAL_WS_EDGE_WN);
   c.edge_na = REG(float, CAL_WS_EDGE_NA);
+  c.fsg = REG(unsigned char, CAL_WS_FSG);
+  c.fsg_on = m->model == CAL_MODEL_GCN && m->hidden == 128 && m->num_features <= 128 && caps->max_graphs <= kSMs &&
+             caps->small_graphs != 0;
 #undef REG
   for (int l = 0; l < CAL_MAX_LAYERS + 2; ++l) c.gp_conv[l] = lay.gp_conv[l];
   c.gp_att = lay.gp_att;
@@ -318,8 +322,13 @@ int cal_causal_forward(const cal_model_desc* m, const cal_caps* caps, const cal_
   int lo = 0, hi = L + 5;
   stage_range(flags, &lo, &hi);
   for (int st = lo; st <= hi; ++st) {
-    if (st == 0) rc = launch_param_prep(c, s);
-    else if (st == 1) rc = launch_feat_forward(c, s);
+    if (st == 0) {
+      rc = launch_param_prep(c, s);
+      if (rc == 0 && c.fsg_on) rc = launch_fsg_prep(c, s);
+    } else if (c.fsg_on && st >= 1 && st <= 3 + L) {
+      // fused small-graph path: stage "feat" runs the whole forward up to the pooled embeddings (fsg.cu)
+      if (st == 1) rc = launch_fsg_forward(c, s);
+    } else if (st == 1) rc = launch_feat_forward(c, s);
     else if (st < 2 + L)
       rc = c.model == CAL_MODEL_GAT ? launch_gat_forward(c, st - 2, s)
                                     : (c.model == CAL_MODEL_GIN ? launch_gin_forward(c, st - 2, s) : launch_conv_forward(c, st - 2, s));

@@ -1,0 +1,790 @@
+// fsg.cu -- the fused small-graph forward pass of CausalGCN (model.py:85-116): ONE persistent kernel from
+// the input transform to the pooled graph embeddings.
+//
+// A CTA owns a block of whole graphs (<= kFsgRows nodes, <= kFsgEntries CSR entries; fsg.cuh) for the whole
+// pass.  Its node features stay in shared memory from layer to layer, so message passing (gcn_conv.py:92-97)
+// never leaves the SM; the node transforms x W (gcn_conv.py:75) run on the tensor cores (tcgen05.mma, 3xTF32,
+// accumulators in TMEM) with the weight matrix as the M operand and the block's node rows on the N dimension
+// (cost proportional to the number of rows, granularity 8); the weight operand of the next layer arrives by
+// one cp.async.bulk of a pre-split image while the current layer's epilogue runs.  Training-mode BatchNorm is
+// the only coupling between CTAs: per BatchNorm boundary one deterministic in-kernel all-reduce of the
+// per-channel (sum, sum of squares) -- groups of 8 CTAs, fixed order, no float atomics -- whose latency is
+// overlapped with the RAW aggregation of the next layer:  sum_e norm_e bn(x)[src_e] = sc * (sum_e norm_e x[src_e])
+// + sh * (sum_e norm_e), so only an affine per row remains once the statistics arrive.
+//
+// The kernel writes the same workspace regions as the tiled kernels it replaces (conv.cu k_feat_fwd /
+// k_conv_fwd / k_masked_fwd_both, attn.cu k_edge_att, head.cu k_pool), so the backward pass and the tests
+// are agnostic of which forward ran.
+#include "fsg.cuh"
+#include "umma.cuh"
+
+namespace cal {
+namespace {
+
+constexpr int FT = 256;                               // threads per CTA
+constexpr int FH = 128;                               // hidden size this path is built for
+constexpr uint32_t kALbo = 2048, kASbo = 128;         // weight operand: chunk c of row m at c * 2048 + m * 16
+constexpr uint32_t kBLbo = 144, kBSbo = 32 * 144;     // node operand: chunk c of row i at (i / 8) * 4608 + c * 144 + (i % 8) * 16
+constexpr int kBPart = (kFsgRows / 8) * (int)kBSbo;   // 23040 bytes
+constexpr int kTmemCols = 256;                        // main accumulators at columns 0 / 64, correction terms at 128 / 192
+
+// per-category cycle counters of CTA 0 / thread 0 (-DCAL_PHASE_TIMING builds): status[48 + category]
+#ifdef CAL_PHASE_TIMING
+#define FSG_TDECL long long ft_last = clock64(); long long ft_acc[16] = {0};
+#define FSG_T(cat) do { const long long t_ = clock64(); ft_acc[cat] += t_ - ft_last; ft_last = t_; } while (0)
+#define FSG_TDUMP(c) do { if (blockIdx.x == 0 && threadIdx.x == 0) for (int q_ = 0; q_ < 16; ++q_) (c).status[48 + q_] = (int)ft_acc[q_]; } while (0)
+#else
+#define FSG_TDECL
+#define FSG_T(cat)
+#define FSG_TDUMP(c)
+#endif
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// ---- shared memory ----
+struct FsgSmem {
+  size_t a_hi, a_lo, b_hi, b_lo, x, in_ptr, out_ptr, in_src, in_nrm, out_dst, out_pos, w, wn, gptr, rowf, aff, part, tot, total;
+};
+__host__ __device__ inline FsgSmem fsg_smem() {
+  FsgSmem s;
+  size_t o = 0;
+  s.a_hi = o;    o += 65536;
+  s.a_lo = o;    o += 65536;
+  s.b_hi = o;    o += kBPart;
+  s.b_lo = o;    o += kBPart;
+  s.x = o;       o += (size_t)kFsgRows * FH * 4;
+  s.in_ptr = o;  o += 48 * 4;
+  s.out_ptr = o; o += 48 * 4;
+  s.in_src = o;  o += kFsgEntries * 4;
+  s.in_nrm = o;  o += kFsgEntries * 4;
+  s.out_dst = o; o += kFsgEntries * 4;
+  s.out_pos = o; o += kFsgEntries * 4;
+  s.w = o;       o += kFsgEntries * 8;                  // edge attention by in-CSR position (both branches)
+  s.wn = o;      o += kFsgEntries * 8;                  // dis_w[source] * edge attention
+  s.gptr = o;    o += 48 * 4;                           // first local row of every graph of the block
+  s.rowf = o;    o += (size_t)kFsgRows * 12 * 4;        // per row: s (1), s_c / s_o (2), node att (2), p / q (4), dis_w (2), pad
+  s.aff = o;     o += 4 * FH * 4;                       // BatchNorm scale / shift (two sets)
+  s.part = o;    o += 512 * 8;
+  s.tot = o;     o += 512 * 8;
+  s.total = o;
+  return s;
+}
+
+// ---- the in-kernel all-reduce of per-CTA fp64 vectors (deterministic: groups of 8 CTAs, fixed order) ----
+__device__ __forceinline__ void fsg_publish(const FsgWs& w, int phase, int G, const double* sPart, int n) {
+  __shared__ int s_lead;
+  const int t = threadIdx.x;
+  const int grp = blockIdx.x / kFsgGroup, gsize = imin(kFsgGroup, G - grp * kFsgGroup);
+  double* mine = w.l0 + (size_t)blockIdx.x * kFsgVec;
+  for (int i = t; i < n; i += FT) mine[i] = sPart[i];
+  __syncthreads();
+  if (t == 0) {
+    __threadfence();
+    const unsigned int old = atomicAdd(&w.cnt[phase * kFsgCntStride + 1 + grp], 1u);
+    s_lead = (old == (unsigned int)gsize - 1u);
+    if (s_lead) __threadfence();
+  }
+  __syncthreads();
+  if (!s_lead) return;
+  double* dst = w.l1 + ((size_t)(phase & 1) * kFsgMaxGroups + grp) * kFsgVec;
+  for (int i = t; i < n; i += FT) {
+    double v[kFsgGroup];
+#pragma unroll
+    for (int m = 0; m < kFsgGroup; ++m) v[m] = m < gsize ? __ldcg(&w.l0[(size_t)(grp * kFsgGroup + m) * kFsgVec + i]) : 0.0;
+    double sum = v[0];
+#pragma unroll
+    for (int m = 1; m < kFsgGroup; ++m) sum += v[m];
+    dst[i] = sum;
+  }
+  __syncthreads();
+  if (t == 0) {
+    __threadfence();
+    atomicAdd(&w.cnt[phase * kFsgCntStride], 1u);
+  }
+}
+__device__ __forceinline__ void fsg_wait_total(const FsgWs& w, int phase, int G, int n, double* sTot) {
+  const int t = threadIdx.x;
+  const int ngrp = (G + kFsgGroup - 1) / kFsgGroup;
+  if (t == 0) {
+    while (ld_acquire_gpu(&w.cnt[phase * kFsgCntStride]) < (unsigned int)ngrp) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  const double* src = w.l1 + (size_t)(phase & 1) * kFsgMaxGroups * kFsgVec;
+  for (int i = t; i < n; i += FT) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int g = 0;
+    for (; g + 4 <= ngrp; g += 4) {
+      s0 += __ldcg(src + (size_t)(g + 0) * kFsgVec + i);
+      s1 += __ldcg(src + (size_t)(g + 1) * kFsgVec + i);
+      s2 += __ldcg(src + (size_t)(g + 2) * kFsgVec + i);
+      s3 += __ldcg(src + (size_t)(g + 3) * kFsgVec + i);
+    }
+    for (; g < ngrp; ++g) s0 += __ldcg(src + (size_t)g * kFsgVec + i);
+    sTot[i] = (s0 + s1) + (s2 + s3);
+  }
+  __syncthreads();
+}
+
+// training-mode BatchNorm `id` from the grid totals tot[0..K) (sum) and tot[K..2K) (sum of squares): threads
+// [t0, t0 + K) write the affine into shared memory; CTA 0 publishes the record and the running statistics
+__device__ __forceinline__ void fsg_bn_finalize(const Ctx& c, int id, int count, const double* tot, float* s_sc, float* s_sh,
+                                                int t0) {
+  const int K = c.bn_K[id];
+  const int k = (int)threadIdx.x - t0;
+  if (k < 0 || k >= K) return;
+  const double s = tot[k], q = tot[K + k];
+  double mean = 0.0, var = 0.0;
+  if (count > 0) {
+    mean = s / count;
+    var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+  }
+  const float rstd = (float)(1.0 / sqrt(var + (double)c.eps));
+  const float sc = c.params[c.bn_gamma[id] + k] * rstd;
+  const float sh = c.params[c.bn_beta[id] + k] - (float)mean * sc;
+  s_sc[k] = sc;
+  s_sh[k] = sh;
+  if (blockIdx.x == 0) {
+    c.bnf(id, BN_SCALE)[k] = sc;
+    c.bnf(id, BN_SHIFT)[k] = sh;
+    c.bnf(id, BN_MEAN)[k] = (float)mean;
+    c.bnf(id, BN_RSTD)[k] = rstd;
+    if (c.bn_buffers != nullptr && c.bn_rm[id] >= 0) {
+      const double unb = count > 1 ? var * ((double)count / (double)(count - 1)) : var;
+      float* rm = c.bn_buffers + c.bn_rm[id];
+      float* rv = c.bn_buffers + c.bn_rv[id];
+      rm[k] = (1.f - c.momentum) * rm[k] + c.momentum * (float)mean;
+      rv[k] = (1.f - c.momentum) * rv[k] + c.momentum * (float)unb;
+    }
+    if (k == 0 && c.nbt != nullptr) c.nbt[id] += 1;
+  }
+}
+
+__device__ __forceinline__ uint32_t b_off(int i, int kc) { return (uint32_t)(i >> 3) * kBSbo + (uint32_t)kc * kBLbo + (uint32_t)(i & 7) * 16u; }
+
+// hi / lo split of one 16-byte chunk into the node operand
+__device__ __forceinline__ void put_b(unsigned char* b_hi, unsigned char* b_lo, int i, int kc, float4 v) {
+  float h0, h1, h2, h3, l0, l1, l2, l3;
+  umma::split_tf32(v.x, h0, l0);
+  umma::split_tf32(v.y, h1, l1);
+  umma::split_tf32(v.z, h2, l2);
+  umma::split_tf32(v.w, h3, l3);
+  const uint32_t off = b_off(i, kc);
+  *reinterpret_cast<float4*>(b_hi + off) = make_float4(h0, h1, h2, h3);
+  *reinterpret_cast<float4*>(b_lo + off) = make_float4(l0, l1, l2, l3);
+}
+
+// D_main (+)= A_hi B_hi ; D_corr (+)= A_lo B_hi + A_hi B_lo over `ksteps` steps of 8 k.  One thread.
+// (Two accumulators: every MMA re-rounds its accumulator, so the small correction terms are kept out of the
+// main sum's rounding chain: 16 instead of 48 roundings of the main accumulator at K = 128.)
+__device__ __forceinline__ void issue_3xtf32(const unsigned char* a_hi, const unsigned char* a_lo, const unsigned char* b_hi,
+                                             const unsigned char* b_lo, uint32_t d_main, uint32_t d_corr, int ksteps, int npad) {
+  const uint32_t idesc = umma::instr_desc(umma::kFmtTF32, 128, npad);
+  for (int s = 0; s < ksteps; ++s) {
+    const uint32_t aa = (uint32_t)s * 2u * kALbo, ba = (uint32_t)s * 2u * kBLbo;
+    const uint64_t ah = umma::smem_desc(umma::smem_addr(a_hi) + aa, kALbo, kASbo);
+    const uint64_t al = umma::smem_desc(umma::smem_addr(a_lo) + aa, kALbo, kASbo);
+    const uint64_t bh = umma::smem_desc(umma::smem_addr(b_hi) + ba, kBLbo, kBSbo);
+    const uint64_t bl = umma::smem_desc(umma::smem_addr(b_lo) + ba, kBLbo, kBSbo);
+    umma::mma_tf32(d_corr, al, bh, idesc, s > 0);
+    umma::mma_tf32(d_corr, ah, bl, idesc, 1u);
+    umma::mma_tf32(d_main, ah, bh, idesc, s > 0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The forward kernel.  grid = min(max_graphs, 148), 256 threads, 1 CTA per SM.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t bar_w, bar_mma;
+  __shared__ uint32_t tmem_slot;
+  const FsgSmem S = fsg_smem();
+  unsigned char* sAh = smem + S.a_hi;
+  unsigned char* sAl = smem + S.a_lo;
+  unsigned char* sBh = smem + S.b_hi;
+  unsigned char* sBl = smem + S.b_lo;
+  float* sX = reinterpret_cast<float*>(smem + S.x);                  // [rows][128] current node features
+  int* sInPtr = reinterpret_cast<int*>(smem + S.in_ptr);
+  int* sOutPtr = reinterpret_cast<int*>(smem + S.out_ptr);
+  int* sInSrc = reinterpret_cast<int*>(smem + S.in_src);
+  float* sInNrm = reinterpret_cast<float*>(smem + S.in_nrm);
+  int* sOutDst = reinterpret_cast<int*>(smem + S.out_dst);
+  int* sOutPos = reinterpret_cast<int*>(smem + S.out_pos);
+  float2* sW = reinterpret_cast<float2*>(smem + S.w);
+  float2* sWn = reinterpret_cast<float2*>(smem + S.wn);
+  int* sGptr = reinterpret_cast<int*>(smem + S.gptr);
+  float* sRow = reinterpret_cast<float*>(smem + S.rowf);             // [rows][12]
+  float* sAff = reinterpret_cast<float*>(smem + S.aff);              // sc0 | sh0 | sc1 | sh1
+  double* sPart = reinterpret_cast<double*>(smem + S.part);
+  double* sTot = reinterpret_cast<double*>(smem + S.tot);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const FsgWs ws = fsg_ws(c);
+  const int L = c.L, F = c.F;
+  const int Fp8 = (F + 7) & ~7;
+
+  // ---- before the dependency wait: TMEM, barriers, attention projection weights (parameters) ----
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, kTmemCols);
+  if (t == 0) {
+    umma::mbar_init(&bar_w, 1);
+    umma::mbar_init(&bar_mma, 1);
+    umma::mbar_fence_init();
+  }
+  float wn0[4], wn1[4], wp0[4], wp1[4], wq0[4], wq1[4];               // lane's 4 channels of node_att_mlp / edge_att_mlp
+  {
+    const float* Wn = c.params + c.po.node_att_w;                      // [2][H]
+    const float* We = c.params + c.po.edge_att_w;                      // [2][2H]
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = lane * 4 + i;
+      wn0[i] = Wn[k];
+      wn1[i] = Wn[FH + k];
+      wp0[i] = We[k];
+      wp1[i] = We[2 * FH + k];
+      wq0[i] = We[FH + k];
+      wq1[i] = We[3 * FH + k];
+    }
+  }
+  const float bnat0 = c.params[c.po.node_att_b], bnat1 = c.params[c.po.node_att_b + 1];
+  const float beat0 = c.params[c.po.edge_att_b], beat1 = c.params[c.po.edge_att_b + 1];
+  umma::fence_before_sync();
+  FSG_TDECL
+  pdl_sync();                                                         // everything below may read the predecessors' output
+  FSG_T(0);                                                           // 0: dependency wait
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const int nblk = ws.plan[0], plan_ok = ws.plan[1];
+  const int N = imin(imax(c.dims[0], 0), c.Nm);
+  bool active = plan_ok != 0 && (int)blockIdx.x < nblk;
+  if (!plan_ok && blockIdx.x == 0 && t == 0) atomicOr(c.status, kStCapacity);
+  int g0 = 0, g1 = 0, n0 = 0, n1 = 0, ie0 = 0, ie1 = 0, oe0 = 0;
+  if (active) {
+    const int4 a = *reinterpret_cast<const int4*>(ws.info + (size_t)blockIdx.x * 8);
+    const int4 b = *reinterpret_cast<const int4*>(ws.info + (size_t)blockIdx.x * 8 + 4);
+    g0 = a.x; g1 = a.y; n0 = a.z; n1 = a.w;
+    ie0 = b.x; ie1 = b.y; oe0 = b.z;
+  }
+  const int Nc = n1 - n0, Ec = ie1 - ie0;
+  const int npad = imax(8, (Nc + 7) & ~7);                             // MMA N
+  const int G = nblk;
+  uint32_t par_w = 0, par_m = 0;                                      // mbarrier phases
+  if (active) {
+    // weight operand of the input transform
+    if (t == 0) {
+      const uint32_t bytes = (uint32_t)(Fp8 / 4) * kALbo;
+      umma::mbar_expect_tx(&bar_w, 2 * bytes);
+      umma::bulk_g2s(sAh, fsg_img_feat(ws, L), bytes, &bar_w);
+      umma::bulk_g2s(sAl, fsg_img_feat(ws, L) + kFsgImgPart, bytes, &bar_w);
+    }
+    // the block's two CSR segments, local ids
+    for (int i = t; i <= Nc; i += FT) {
+      sInPtr[i] = c.in_ptr[n0 + i] - ie0;
+      sOutPtr[i] = c.out_ptr[n0 + i] - oe0;
+    }
+    for (int e = t; e < Ec; e += FT) {
+      sInSrc[e] = c.in_src[ie0 + e] - n0;
+      sInNrm[e] = c.in_norm[ie0 + e];
+      sOutDst[e] = c.out_dst[oe0 + e] - n0;
+      sOutPos[e] = c.out_pos[oe0 + e] - ie0;
+    }
+    for (int g = t; g <= g1 - g0; g += FT) sGptr[g] = c.graph_ptr[g0 + g] - n0;
+    // bn_feat (model.py:90): the column totals come from cal_prep (statp[0 .. 2F))
+    float* sc = sAff;
+    float* sh = sAff + FH;
+    if (c.train) {
+      for (int k = t; k < F; k += FT) {
+        const double s = c.statp[k], q = c.statp[F + k];
+        double mean = 0.0, var = 0.0;
+        if (N > 0) {
+          mean = s / N;
+          var = q / N - mean * mean;
+          if (var < 0.0) var = 0.0;
+        }
+        const float rstd = (float)(1.0 / sqrt(var + (double)c.eps));
+        const float scale = c.params[c.bn_gamma[0] + k] * rstd;
+        const float shift = c.params[c.bn_beta[0] + k] - (float)mean * scale;
+        sc[k] = scale;
+        sh[k] = shift;
+        if (blockIdx.x == 0) {
+          c.bnf(0, BN_SCALE)[k] = scale;
+          c.bnf(0, BN_SHIFT)[k] = shift;
+          c.bnf(0, BN_MEAN)[k] = (float)mean;
+          c.bnf(0, BN_RSTD)[k] = rstd;
+          if (c.bn_buffers != nullptr && c.bn_rm[0] >= 0) {
+            const double unb = N > 1 ? var * ((double)N / (double)(N - 1)) : var;
+            float* rm = c.bn_buffers + c.bn_rm[0];
+            float* rv = c.bn_buffers + c.bn_rv[0];
+            rm[k] = (1.f - c.momentum) * rm[k] + c.momentum * (float)mean;
+            rv[k] = (1.f - c.momentum) * rv[k] + c.momentum * (float)unb;
+          }
+        }
+      }
+      if (blockIdx.x == 0 && t == 0 && c.nbt != nullptr) c.nbt[0] += 1;
+    } else {
+      for (int k = t; k < F; k += FT) {
+        sc[k] = c.bnf(0, BN_SCALE)[k];
+        sh[k] = c.bnf(0, BN_SHIFT)[k];
+      }
+    }
+    __syncthreads();
+    FSG_T(1);                                                         // 1: plan, CSR segments, bn_feat
+
+    // ================= input transform: x_1 = relu(bn_feat(x) W_feat)  (gfn: no bias, no propagation) =================
+    {
+      const int nkc = Fp8 / 4;
+      for (int i = warp; i < npad; i += 8) {
+        if (lane < nkc) {
+          float v[4] = {0.f, 0.f, 0.f, 0.f};
+          if (i < Nc) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int k = lane * 4 + e;
+              if (k < F) v[e] = fmaf(c.feat[(size_t)(n0 + i) * F + k], sc[k], sh[k]);
+            }
+          }
+          put_b(sBh, sBl, i, lane, make_float4(v[0], v[1], v[2], v[3]));
+        }
+      }
+      umma::fence_async_smem();
+      __syncthreads();
+      umma::mbar_wait(&bar_w, par_w);
+      par_w ^= 1u;
+      if (t == 0) {
+        umma::fence_after_sync();
+        issue_3xtf32(sAh, sAl, sBh, sBl, tmem, tmem + 128u, Fp8 / 8, npad);
+        umma::commit(&bar_mma);
+      }
+      umma::mbar_wait(&bar_mma, par_m);
+      par_m ^= 1u;
+      umma::fence_after_sync();
+      FSG_T(2);                                                       // 2: input transform (operand + MMA)
+    }
+  }
+
+  // ================= layers + masked convs =================
+  // phase p = 0 .. L-1: statistics of bns_conv[p] (input of layer p); phase L: statistics of bnc / bno
+  for (int l = 0; l <= L; ++l) {
+    const bool masked = l == L;
+    if (active) {
+      // -- weight operand of this phase (the previous MMAs have completed: the buffer is free) --
+      if (t == 0) {
+        const float* img = fsg_img_fwd(ws, l);
+        umma::mbar_expect_tx(&bar_w, 2u * 65536u);
+        umma::bulk_g2s(sAh, img, 65536u, &bar_w);
+        umma::bulk_g2s(sAl, img + kFsgImgPart, 65536u, &bar_w);
+      }
+      // -- epilogue of the previous product: thread = output channel (warps 0-3) --
+      if (warp < 4) {
+        const int ch = t;
+        const float bias = l == 0 ? 0.f : c.params[c.po.convs_b[l - 1] + ch];
+        float* xg = c.Xl(l) + (size_t)n0 * FH;
+        double s = 0.0, q = 0.0;
+        for (int g8 = 0; g8 < npad; g8 += 8) {
+          float vm[8], vc[8];
+          umma::ld8(umma::tmem_addr(tmem, warp * 32, g8), vm);
+          umma::ld8(umma::tmem_addr(tmem, warp * 32, 128 + g8), vc);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int i = g8 + e;
+            if (i < Nc) {
+              const float x = fmaxf((vm[e] + vc[e]) + bias, 0.f);
+              sX[i * FH + ch] = x;
+              xg[(size_t)i * FH + ch] = x;
+              s += (double)x;
+              q += (double)x * (double)x;
+            }
+          }
+        }
+        sPart[ch] = s;
+        sPart[FH + ch] = q;
+      }
+      umma::fence_before_sync();
+      __syncthreads();
+      umma::fence_after_sync();
+      FSG_T(3);                                                       // 3: epilogues (TMEM -> x, statistics)
+    }
+    if (!masked) {
+      // ---------------- backbone layer l: x_{l+2} = relu(A bn_l(x_{l+1}) W_l + b_l)  (model.py:93-95) ----------------
+      if (active) {
+        if (c.train) fsg_publish(ws, l, G, sPart, 2 * FH);
+        FSG_T(4);                                                     // 4: publish
+        // raw aggregate while the statistics travel: warp per target row, lanes over 4 channels
+        for (int i = warp; i < Nc; i += 8) {
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          float sn = 0.f;
+          for (int e = sInPtr[i]; e < sInPtr[i + 1]; ++e) {
+            const float w = sInNrm[e];
+            const float4 v = *reinterpret_cast<const float4*>(sX + sInSrc[e] * FH + lane * 4);
+            acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+            sn += w;
+          }
+          *reinterpret_cast<float4*>(sBh + b_off(i, lane)) = acc;
+          if (lane == 0) sRow[i * 12] = sn;
+        }
+        FSG_T(5);                                                     // 5: raw aggregation
+        float* sc = sAff;
+        float* sh = sAff + FH;
+        if (c.train) {
+          fsg_wait_total(ws, l, G, 2 * FH, sTot);
+          fsg_bn_finalize(c, 1 + l, N, sTot, sc, sh, 0);
+        } else if (t < FH) {
+          sc[t] = c.bnf(1 + l, BN_SCALE)[t];
+          sh[t] = c.bnf(1 + l, BN_SHIFT)[t];
+        }
+        __syncthreads();
+        FSG_T(6);                                                     // 6: statistics wait + finalize
+        const float4 sc4 = *reinterpret_cast<const float4*>(sc + lane * 4), sh4 = *reinterpret_cast<const float4*>(sh + lane * 4);
+        for (int i = warp; i < npad; i += 8) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < Nc) {
+            const float4 r = *reinterpret_cast<const float4*>(sBh + b_off(i, lane));
+            const float sn = sRow[i * 12];
+            a = make_float4(fmaf(sc4.x, r.x, sh4.x * sn), fmaf(sc4.y, r.y, sh4.y * sn), fmaf(sc4.z, r.z, sh4.z * sn),
+                            fmaf(sc4.w, r.w, sh4.w * sn));
+          }
+          put_b(sBh, sBl, i, lane, a);
+        }
+        umma::fence_async_smem();
+        __syncthreads();
+        FSG_T(7);                                                     // 7: affine + split into the operand
+        umma::mbar_wait(&bar_w, par_w);
+        par_w ^= 1u;
+        FSG_T(8);                                                     // 8: weight image wait
+        if (t == 0) {
+          umma::fence_after_sync();
+          issue_3xtf32(sAh, sAl, sBh, sBl, tmem, tmem + 128u, FH / 8, npad);
+          umma::commit(&bar_mma);
+        }
+        umma::mbar_wait(&bar_mma, par_m);
+        par_m ^= 1u;
+        umma::fence_after_sync();
+        FSG_T(9);                                                     // 9: MMA
+      }
+      continue;
+    }
+    // ---------------- attention masks + the two masked convs + pooling (model.py:97-116) ----------------
+    if (!active) break;
+    // node attention softmax(node_att_mlp(x)), the per-node halves p, q of edge_att_mlp([x_row || x_col])
+    for (int i = warp; i < Nc; i += 8) {
+      const float4 v = *reinterpret_cast<const float4*>(sX + i * FH + lane * 4);
+      const float o[4] = {v.x, v.y, v.z, v.w};
+      float s0 = 0.f, s1 = 0.f, p0 = 0.f, p1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        s0 = fmaf(o[k], wn0[k], s0);
+        s1 = fmaf(o[k], wn1[k], s1);
+        p0 = fmaf(o[k], wp0[k], p0);
+        p1 = fmaf(o[k], wp1[k], p1);
+        q0 = fmaf(o[k], wq0[k], q0);
+        q1 = fmaf(o[k], wq1[k], q1);
+      }
+      s0 = warp_sum(s0) + bnat0;
+      s1 = warp_sum(s1) + bnat1;
+      p0 = warp_sum(p0);
+      p1 = warp_sum(p1);
+      q0 = warp_sum(q0);
+      q1 = warp_sum(q1);
+      float a0 = 0.5f, a1 = 0.5f;
+      if (!c.no_natt) {
+        const float mx = fmaxf(s0, s1);
+        const float e0 = expf(s0 - mx), e1 = expf(s1 - mx);
+        const float inv = 1.0f / (e0 + e1);
+        a0 = e0 * inv;
+        a1 = e1 * inv;
+      }
+      if (lane == 0) {
+        float* r = sRow + i * 12;
+        r[3] = a0; r[4] = a1; r[5] = p0; r[6] = p1; r[7] = q0; r[8] = q1;
+        *reinterpret_cast<float2*>(c.natt + (size_t)(n0 + i) * 2) = make_float2(a0, a1);
+        *reinterpret_cast<float4*>(c.pq + (size_t)(n0 + i) * 4) = make_float4(p0, p1, q0, q1);
+      }
+    }
+    __syncthreads();
+    // statistics of bnc / bno on att * x: thread = channel (warps 0-3)
+    if (warp < 4 && c.train) {
+      double a = 0.0, b = 0.0, d = 0.0, e = 0.0;
+      for (int i = 0; i < Nc; ++i) {
+        const float x = sX[i * FH + t];
+        const float vc = sRow[i * 12 + 3] * x, vo = sRow[i * 12 + 4] * x;
+        a += (double)vc; b += (double)vc * (double)vc;
+        d += (double)vo; e += (double)vo * (double)vo;
+      }
+      sPart[t] = a;
+      sPart[FH + t] = b;
+      sPart[2 * FH + t] = d;
+      sPart[3 * FH + t] = e;
+    }
+    __syncthreads();
+    FSG_T(10);                                                        // 10: node attention + bnc / bno statistics
+    if (c.train) fsg_publish(ws, L, G, sPart, 4 * FH);
+    FSG_T(4);
+    // edge attention softmax(p[row] + q[col] + b) per edge (never materialises [E, 2H]), the attention-weighted
+    // degree by source row and dis_w = deg^-1/2 (gcn_conv.py:59-70 with edge_weight): warp per source node
+    for (int n = warp; n < Nc; n += 8) {
+      const float* rn = sRow + n * 12;
+      const float pn0 = rn[5], pn1 = rn[6];
+      const int q0 = sOutPtr[n], q1 = sOutPtr[n + 1] - 1;             // last slot = the appended self loop
+      float deg0 = 0.f, deg1 = 0.f;
+      for (int qb = q0; qb <= q1; qb += 32) {
+        const int qq = qb + lane;
+        float w0 = 0.f, w1 = 0.f;
+        if (qq <= q1) {
+          w0 = w1 = qq == q1 ? 1.f : 0.5f;
+          if (qq != q1 && !c.no_eatt) {
+            const float* rd = sRow + sOutDst[qq] * 12;
+            const float t0 = pn0 + rd[7] + beat0, t1 = pn1 + rd[8] + beat1;
+            const float mx = fmaxf(t0, t1);
+            const float e0 = expf(t0 - mx), e1 = expf(t1 - mx);
+            const float inv = 1.0f / (e0 + e1);
+            w0 = e0 * inv;
+            w1 = e1 * inv;
+          }
+          sW[sOutPos[qq]] = make_float2(w0, w1);
+        }
+        deg0 += warp_sum(w0);
+        deg1 += warp_sum(w1);
+      }
+      const float2 dn = make_float2(1.0f / sqrtf(deg0), 1.0f / sqrtf(deg1));
+      if (lane == 0) {
+        sRow[n * 12 + 9] = dn.x;
+        sRow[n * 12 + 10] = dn.y;
+        *reinterpret_cast<float2*>(c.disw + (size_t)(n0 + n) * 2) = dn;
+      }
+      __syncwarp();
+      const float2 an = make_float2(rn[3], rn[4]);
+      for (int qq = q0 + lane; qq <= q1; qq += 32) {
+        const int pos = sOutPos[qq];
+        const float2 w = sW[pos];                                      // written by this lane above
+        const float2 wn = make_float2(dn.x * w.x, dn.y * w.y);
+        sWn[pos] = wn;
+        *reinterpret_cast<float2*>(c.watt + (size_t)(ie0 + pos) * 2) = w;
+        *reinterpret_cast<float2*>(c.edge_wn + (size_t)(ie0 + pos) * 2) = wn;
+        *reinterpret_cast<float2*>(c.edge_na + (size_t)(ie0 + pos) * 2) = an;
+      }
+    }
+    __syncthreads();
+    FSG_T(11);                                                        // 11: edge attention
+    float* sc0 = sAff;
+    float* sh0 = sAff + FH;
+    float* sc1 = sAff + 2 * FH;
+    float* sh1 = sAff + 3 * FH;
+    for (int br = 0; br < 2; ++br) {
+      // raw aggregate of branch br: sum_e (wn_e * dis_w[i]) * (att[src] * x[src]) and the weight sum
+      for (int i = warp; i < Nc; i += 8) {
+        const float di = sRow[i * 12 + 9 + br];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float sn = 0.f;
+        for (int e = sInPtr[i]; e < sInPtr[i + 1]; ++e) {
+          const int src = sInSrc[e];
+          const float2 wn = sWn[e];
+          const float w = (br ? wn.y : wn.x) * di;
+          const float am = sRow[src * 12 + 3 + br];
+          const float4 v = *reinterpret_cast<const float4*>(sX + src * FH + lane * 4);
+          acc.x = fmaf(w, am * v.x, acc.x); acc.y = fmaf(w, am * v.y, acc.y); acc.z = fmaf(w, am * v.z, acc.z); acc.w = fmaf(w, am * v.w, acc.w);
+          sn += w;
+        }
+        *reinterpret_cast<float4*>(sBh + b_off(i, lane)) = acc;
+        if (lane == 0) sRow[i * 12 + 1 + br] = sn;
+      }
+      FSG_T(5);
+      if (br == 0) {
+        if (c.train) {
+          fsg_wait_total(ws, L, G, 4 * FH, sTot);
+          fsg_bn_finalize(c, L + 1, N, sTot, sc0, sh0, 0);
+          fsg_bn_finalize(c, L + 2, N, sTot + 2 * FH, sc1, sh1, FH);
+        } else if (t < FH) {
+          sc0[t] = c.bnf(L + 1, BN_SCALE)[t];
+          sh0[t] = c.bnf(L + 1, BN_SHIFT)[t];
+          sc1[t] = c.bnf(L + 2, BN_SCALE)[t];
+          sh1[t] = c.bnf(L + 2, BN_SHIFT)[t];
+        }
+      }
+      __syncthreads();
+      FSG_T(6);
+      {
+        const float* sc = br ? sc1 : sc0;
+        const float* sh = br ? sh1 : sh0;
+        const float4 sc4 = *reinterpret_cast<const float4*>(sc + lane * 4), sh4 = *reinterpret_cast<const float4*>(sh + lane * 4);
+        float* aggg = c.agg + (size_t)br * c.Nm * FH + (size_t)n0 * FH;
+        for (int i = warp; i < npad; i += 8) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < Nc) {
+            const float4 r = *reinterpret_cast<const float4*>(sBh + b_off(i, lane));
+            const float sn = sRow[i * 12 + 1 + br];
+            a = make_float4(fmaf(sc4.x, r.x, sh4.x * sn), fmaf(sc4.y, r.y, sh4.y * sn), fmaf(sc4.z, r.z, sh4.z * sn),
+                            fmaf(sc4.w, r.w, sh4.w * sn));
+            *reinterpret_cast<float4*>(aggg + (size_t)i * FH + lane * 4) = a;    // saved for the weight gradient
+          }
+          put_b(sBh, sBl, i, lane, a);
+        }
+      }
+      umma::fence_async_smem();
+      __syncthreads();
+      FSG_T(7);
+      umma::mbar_wait(&bar_w, par_w);
+      par_w ^= 1u;
+      FSG_T(8);
+      if (t == 0) {
+        umma::fence_after_sync();
+        issue_3xtf32(sAh, sAl, sBh, sBl, tmem + (br ? 64u : 0u), tmem + 128u + (br ? 64u : 0u), FH / 8, npad);
+        umma::commit(&bar_mma);
+      }
+      umma::mbar_wait(&bar_mma, par_m);
+      par_m ^= 1u;
+      umma::fence_after_sync();
+      FSG_T(9);
+      if (br == 0 && t == 0) {                                         // objects_convs weights while branch 0 is finished
+        const float* img = fsg_img_fwd(ws, L + 1);
+        umma::mbar_expect_tx(&bar_w, 2u * 65536u);
+        umma::bulk_g2s(sAh, img, 65536u, &bar_w);
+        umma::bulk_g2s(sAl, img + kFsgImgPart, 65536u, &bar_w);
+      }
+      // epilogue of the branch: z = relu(. + b), saved; global_add_pool over the rows of every graph (model.py:115-116)
+      if (warp < 4) {
+        const int ch = t;
+        const float bias = c.params[(br ? c.po.objects_b : c.po.context_b) + ch];
+        float* zg = c.Z + (size_t)br * c.Nm * FH + (size_t)n0 * FH;
+        float* pg = c.pooled + (size_t)br * c.Bm * FH;
+        const uint32_t cm = br ? 64u : 0u;
+        int g = 0;
+        float pool = 0.f;
+        for (int g8 = 0; g8 < npad; g8 += 8) {
+          float vm[8], vc[8];
+          umma::ld8(umma::tmem_addr(tmem, warp * 32, cm + g8), vm);
+          umma::ld8(umma::tmem_addr(tmem, warp * 32, 128 + cm + g8), vc);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int i = g8 + e;
+            if (i < Nc) {
+              while (i >= sGptr[g + 1]) {                              // the row starts a new graph: flush the finished one
+                pg[(size_t)(g0 + g) * FH + ch] = pool;
+                pool = 0.f;
+                ++g;
+              }
+              const float z = fmaxf((vm[e] + vc[e]) + bias, 0.f);
+              zg[(size_t)i * FH + ch] = z;
+              pool += z;
+            }
+          }
+        }
+        for (; g < g1 - g0; ++g) {
+          pg[(size_t)(g0 + g) * FH + ch] = pool;
+          pool = 0.f;
+        }
+      }
+      umma::fence_before_sync();
+      __syncthreads();
+      umma::fence_after_sync();
+      FSG_T(12);                                                      // 12: masked epilogue + pooling
+    }
+  }
+  FSG_TDUMP(c);
+
+  // ---- teardown: TMEM, and the last CTA re-arms the all-reduce counters for the next launch ----
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
+  if (active && t == 0) {
+    __threadfence();
+    if (atomicAdd(&ws.cnt[kFsgPhases * kFsgCntStride], 1u) == (unsigned int)G - 1u) {
+      for (int i = 0; i <= kFsgPhases * kFsgCntStride; ++i) ws.cnt[i] = 0u;
+      __threadfence();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-step preparation of the path: the block plan (one block per graph) and the pre-split
+// (hi | lo) weight-operand images in the canonical K-major layout the MMA reads.
+//   blocks [0, n_img): 2048 elements of one operand image each;  block n_img: the plan.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fsg_prep(const Ctx c, const int n_img_blocks, const int fsg_grid) {
+  pdl_sync();
+  const FsgWs ws = fsg_ws(c);
+  const int t = threadIdx.x;
+  const int L = c.L;
+  if ((int)blockIdx.x < n_img_blocks) {
+    const int img = blockIdx.x >> 3, sub = blockIdx.x & 7;              // 8 blocks of 2048 elements per image
+    float* dst;
+    const float* W;
+    int mode;                                                           // 0: A[m][k] = W[k][m] (forward), 1: A[m][k] = W[m][k] (backward), 2: feat
+    int K = FH;
+    if (img < 2 * (L + 2)) {
+      const int j = img >> 1;
+      mode = img & 1;
+      W = c.params + (j < L ? c.po.convs_w[j] : (j == L ? c.po.context_w : c.po.objects_w));
+      dst = mode ? fsg_img_bwd(ws, j) : fsg_img_fwd(ws, j);
+    } else {
+      mode = 2;
+      W = c.params + c.po.conv_feat_w;                                  // [F][H]
+      dst = fsg_img_feat(ws, L);
+      K = (c.F + 7) & ~7;
+    }
+    for (int e = sub * 2048 + t; e < (sub + 1) * 2048; e += 256) {
+      const int kc = e >> 9, m = (e & 511) >> 2, kk = e & 3;            // float offset e = kc * 512 + m * 4 + kk
+      const int k = kc * 4 + kk;
+      if (k >= K) continue;
+      float v;
+      if (mode == 0) v = W[(size_t)k * FH + m];
+      else if (mode == 1) v = W[(size_t)m * FH + k];
+      else v = k < c.F ? W[(size_t)k * FH + m] : 0.f;
+      float hi, lo;
+      umma::split_tf32(v, hi, lo);
+      dst[e] = hi;
+      dst[kFsgImgPart + e] = lo;
+    }
+    return;
+  }
+  // ---- the plan: one block per graph (thread g describes block g); ok = every graph within the limits ----
+  const int B = imin(imax(c.dims[2], 0), c.Bm);
+  bool ok = B <= fsg_grid;
+  for (int g = t; g < B && g < fsg_grid; g += 256) {
+    const int na = c.graph_ptr[g], nb = c.graph_ptr[g + 1];
+    const int ea = c.in_ptr[na], eb = c.in_ptr[nb];
+    if (nb - na > kFsgRows || eb - ea > kFsgEntries || nb < na) ok = false;
+    int* info = ws.info + (size_t)g * 8;
+    info[0] = g; info[1] = g + 1; info[2] = na; info[3] = nb;
+    info[4] = ea; info[5] = eb; info[6] = c.out_ptr[na]; info[7] = 0;
+  }
+  const int all_ok = __syncthreads_and(ok ? 1 : 0);
+  if (t == 0) {
+    ws.plan[0] = all_ok ? B : 0;
+    ws.plan[1] = all_ok;
+  }
+}
+
+}  // namespace
+
+int fsg_grid(const Ctx& c) { return imax(1, imin(c.Bm, kSMs)); }
+size_t fsg_region_bytes(int Bm, int L) { return fsg_layout(Bm, L).total; }
+
+int launch_fsg_prep(const Ctx& c, cudaStream_t s) {
+  const int n_img = (2 * (c.L + 2) + 1) * 8;
+  launch_k(k_fsg_prep, dim3(n_img + 1), dim3(256), 0, s, c, n_img, fsg_grid(c));
+  note_launches(1);
+  CAL_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_fsg_forward(const Ctx& c, cudaStream_t s) {
+  const size_t smem = fsg_smem().total;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_fsg_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  launch_k(k_fsg_forward, dim3(fsg_grid(c)), dim3(FT), smem, s, c);
+  note_launches(1);
+  CAL_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace cal

@@ -801,26 +801,26 @@ size_t readout_smem_bytes(int Bm, int H, int cat, int C, int backward) {
   return readout_smem(Bp, H, (cat ? 2 : 1) * (H / kRC), C, backward != 0).total;
 }
 
-// Which readout kernels run: 2 = the resident-tile tensor-core kernels (head_tc2.cu: B <= 128, "add", C <= 8),
-// 1 = the streaming tensor-core kernels (head_tc.cu: B <= 512; slower, used when bf16 is requested outside
-// the envelope of 2), 0 = the fp32 FFMA cluster kernels below.  CAL_READOUT=legacy|tc1|tc2 (environment,
-// read once) forces a path for A/B measurements.
+// Which readout kernels run: 0 = the fp32 FFMA cluster kernels below, 1 = the streaming tensor-core kernels
+// (head_tc.cu, B <= 512), 2 = the resident-tile tensor-core kernels (head_tc2.cu: B <= 128, "add", C <= 8).
+// Default: the tensor cores when bf16 operands are requested (cal_model_desc.readout_bf16) or forced
+// (readout_tc, or CAL_READOUT=tc in the environment); otherwise the FFMA kernels -- at B = 128 the readout is
+// a latency chain on three SMs, not a FLOP problem, and the 24-CTA cluster kernels measure faster
+// (profiles/README.md).  CAL_READOUT=legacy forces them even for bf16 (A/B measurements).
 static int readout_path(const Ctx& c) {
   static const int forced = [] {
     const char* e = getenv("CAL_READOUT");
     if (e == nullptr) return -1;
     if (strcmp(e, "legacy") == 0) return 0;
-    if (strcmp(e, "tc1") == 0) return 1;
-    if (strcmp(e, "tc2") == 0) return 2;
+    if (strcmp(e, "tc") == 0) return 1;
     return -1;
   }();
   const bool legacy_fits = readout_smem_bytes(c.Bm, c.H, c.cat, c.C, 1) <= 225 * 1024 &&
                            readout_smem_bytes(c.Bm, c.H, c.cat, c.C, 0) <= 225 * 1024;
-  if (forced == 2 && readout_tc2_supported(c)) return 2;
-  if (forced == 1 && readout_tc_supported(c)) return 1;
-  if (forced == 0 && legacy_fits) return 0;
+  const bool want_tc = forced == 1 || (forced != 0 && (c.readout_bf16 || c.readout_tc)) || !legacy_fits;
+  if (!want_tc) return 0;
   if (readout_tc2_supported(c)) return 2;
-  if ((c.readout_bf16 || !legacy_fits) && readout_tc_supported(c)) return 1;
+  if (readout_tc_supported(c)) return 1;
   return 0;
 }
 
@@ -828,19 +828,21 @@ int launch_heads_forward(const Ctx& c, int with_loss, cudaStream_t s) {
   (void)with_loss;
   const int path = readout_path(c);
   if (path != 0) {
-    CAL_DISPATCH_VEC(c.H, { launch_k(k_pool<VEC>, dim3(c.Bm), dim3(256), 0, s, c); });
-    note_launches(1);
-    CAL_CUDA_CHECK_LAUNCH();
+    if (!c.fsg_on) {                                   // (the fused small-graph forward pools in its epilogue)
+      CAL_DISPATCH_VEC(c.H, { launch_k(k_pool<VEC>, dim3(c.Bm), dim3(256), 0, s, c); });
+      note_launches(1);
+      CAL_CUDA_CHECK_LAUNCH();
+    }
     return path == 2 ? launch_readout_tc2_forward(c, s) : launch_readout_tc_forward(c, s);
   }
   CAL_DISPATCH_VEC(c.H, {
-    launch_k(k_pool<VEC>, dim3(c.Bm), dim3(256), 0, s, c);
+    if (!c.fsg_on) launch_k(k_pool<VEC>, dim3(c.Bm), dim3(256), 0, s, c);
     const size_t smem = readout_smem_bytes(c.Bm, c.H, c.cat, c.C, 0);
     int rc = set_smem_h(k_readout_fwd<VEC>, smem);
     if (rc) return rc;
     launch_k(k_readout_fwd<VEC>, dim3(kRC, 3), dim3(256), smem, s, c);
   });
-  note_launches(2);
+  note_launches(c.fsg_on ? 1 : 2);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }

@@ -49,7 +49,7 @@ struct Layout {
 // Everything a kernel needs, passed by value.
 struct Ctx {
   // model
-  int model, F, H, C, L, heads, cat, no_natt, no_eatt, train, readout_bf16;
+  int model, F, H, C, L, heads, cat, no_natt, no_eatt, train, readout_bf16, readout_tc;
   float eps, momentum, w_c, w_o, w_co, gat_p;
   // capacities and plan
   int Nm, Em, Bm, EP, kmax, g_tile, g_row, t_head1, g_head2;
@@ -87,6 +87,8 @@ struct Ctx {
   size_t gp_conv[CAL_MAX_LAYERS + 2], gp_att, gp_feat, gp_fc1[3], gp_fc2[3], gp_gat[CAL_MAX_LAYERS];
   size_t gp_gin2[CAL_MAX_LAYERS];
   const float* grad_logp;   // external dL/dlogp (nullptr = fused loss)
+  unsigned char* fsg;       // CAL_WS_FSG region (fsg.cuh)
+  int fsg_on;               // the fused small-graph forward replaces feat .. masked_convs (and the pooling)
 
   __host__ __device__ float* bnf(int id, int field) const { return bn + ((size_t)id * BN_FIELDS + field) * kmax; }
   __host__ __device__ float* Xl(int l) const { return X + (size_t)l * Nm * H; }     // l = 0..L  (x_{l+1})
@@ -124,6 +126,9 @@ int launch_heads_backward(const Ctx& c, cudaStream_t s);
 bool readout_tc_supported(const Ctx& c);                                   // tensor-core readout (head_tc.cu)
 int launch_readout_tc_forward(const Ctx& c, cudaStream_t s);
 int launch_readout_tc_backward(const Ctx& c, cudaStream_t s);
+int launch_fsg_prep(const Ctx& c, cudaStream_t s);                         // fused small-graph path (fsg.cu)
+int launch_fsg_forward(const Ctx& c, cudaStream_t s);
+size_t fsg_region_bytes(int Bm, int L);
 bool readout_tc2_supported(const Ctx& c);                                  // resident-tile variant (head_tc2.cu)
 int launch_readout_tc2_forward(const Ctx& c, cudaStream_t s);
 int launch_readout_tc2_backward(const Ctx& c, cudaStream_t s);

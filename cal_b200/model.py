@@ -143,6 +143,7 @@ class Engine:
         d.w_co = float(getattr(m.args, "co", 0.5))
         # not a reference option: bf16 operands (fp32 accumulate) in the readout MLP GEMMs (BASELINE.json configs[4])
         d.readout_bf16 = int(bool(getattr(m.args, "readout_bf16", False)))
+        d.readout_tc = int(bool(getattr(m.args, "readout_tc", False)))      # force the tensor-core readout kernels
         self.desc = d
         self._flatten()
         self.caps = None
@@ -152,6 +153,7 @@ class Engine:
         self._ring_i = 0
         self.opt_state = None
         self._owner = None          # weakref to the Trainer whose captured CUDA graphs point into self.ws
+        self.fsg_mode = "auto"      # "off": never take the fused small-graph forward (A/B tests)
 
     # ---- flat parameter / buffer storage ----
     def _flatten(self):
@@ -243,10 +245,12 @@ class Engine:
                 "batches too (batch_caps(train_batches + eval_batches))" % (N, E, B, c.max_nodes, c.max_edges, c.max_graphs))
         grow = lambda need, cur, q: max(cur, _round_up(int(need * 1.25) + 1, q))
         return self.set_caps(grow(N, c.max_nodes if c else 0, 256), grow(E, c.max_edges if c else 0, 256),
-                             grow(B, c.max_graphs if c else 0, 32) if c else _round_up(max(B, 1), 32))
+                             grow(B, c.max_graphs if c else 0, 32) if c else _round_up(max(B, 1), 32),
+                             small_graphs=bool(c.small_graphs) if c else False)
 
-    def set_caps(self, max_nodes, max_edges, max_graphs):
-        """(Re)allocate the workspace for explicit capacities.  A Trainer that owned the previous
+    def set_caps(self, max_nodes, max_edges, max_graphs, small_graphs=False):
+        """(Re)allocate the workspace for explicit capacities.  ``small_graphs``: the caller guarantees
+        <= 40 nodes and <= 320 CSR entries per graph (cal_caps.small_graphs: the fused small-graph forward).  A Trainer that owned the previous
         workspace is invalidated (its captured CUDA graphs point into freed memory): its next step raises."""
         owner = self._owner() if self._owner is not None else None
         if owner is not None:
@@ -254,6 +258,7 @@ class Engine:
         self._owner = None
         caps = _lib.Caps()
         caps.max_nodes, caps.max_edges, caps.max_graphs = int(max_nodes), int(max_edges), int(max_graphs)
+        caps.small_graphs = int(bool(small_graphs))
         nbytes = self.lib.cal_workspace_bytes(C.byref(self.desc), C.byref(caps))
         if nbytes == 0:
             raise _lib.CalError("cal_b200: unsupported model configuration or capacities (hidden must be 32/64/128, "
@@ -300,6 +305,7 @@ class Engine:
         if x.size(1) != self.F:
             raise _lib.CalError("cal_b200: batch has %d features, model expects %d" % (x.size(1), self.F))
         self.ensure_caps(N, E, B)
+        self._auto_small_graphs(bvec, ei, N, B)
         slot = self._ring[self._ring_i]
         self._ring_i = (self._ring_i + 1) % self.RING
         slot[0], slot[1], slot[2], slot[3] = N, E, B, 0
@@ -319,6 +325,24 @@ class Engine:
         st.N, st.E, st.B, st.cbatch = N, E, B, cb
         st.keep = (x, ei, bvec, y, gat_keep)
         return st
+
+    FSG_ROWS, FSG_ENTRIES, FSG_GRAPHS = 40, 320, 148     # csrc/fsg.cuh
+
+    def _auto_small_graphs(self, bvec, ei, N, B):
+        """The module path (``model(data)``) decides per batch whether the fused small-graph forward applies
+        (one device reduction + sync); a Trainer declares it once for its whole dataset instead."""
+        owner = self._owner() if self._owner is not None else None
+        if owner is not None and not owner._dead:
+            return                                         # frozen by the Trainer's declaration
+        small = False
+        if (self.fsg_mode != "off" and not self.is_gat and not self.is_gin and self.H == 128 and self.F <= 128 and 0 < B <= self.FSG_GRAPHS
+                and self.caps.max_graphs <= self.FSG_GRAPHS and N > 0):
+            nodes = torch.bincount(bvec, minlength=B)
+            ents = nodes.clone()
+            if ei.numel() > 0:
+                ents += torch.bincount(bvec[ei[0]], minlength=B)
+            small = bool((nodes.max() <= self.FSG_ROWS) & (ents.max() <= self.FSG_ENTRIES))
+        self.caps.small_graphs = int(small)
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream

@@ -29,12 +29,24 @@ def _up(x, m):
     return (x + m - 1) // m * m
 
 
+FSG_ROWS, FSG_ENTRIES = 40, 320          # csrc/fsg.cuh: the fused small-graph path's per-graph limits
+
+
 def batch_caps(batches, slack=1.0):
-    """Capacities (max nodes, max edge_index columns, max graphs) covering ``batches``."""
+    """Capacities covering ``batches``: (max nodes, max edge_index columns, max graphs, small_graphs) --
+    ``small_graphs`` is True when every graph has <= 40 nodes and <= 320 CSR entries (edges + one self loop
+    per node), which lets CausalGCN run the fused small-graph forward (cal_caps.small_graphs)."""
     n = max(int(b.batch.numel()) for b in batches)
     e = max(int(b.edge_index.size(1)) for b in batches)
     g = max(int(b.num_graphs) for b in batches)
-    return _up(int(n * slack), 32), _up(max(int(e * slack), 1), 32), _up(g, 8)
+    small = True
+    for b in batches:
+        nodes = np.bincount(b.batch.numpy(), minlength=int(b.num_graphs))
+        ents = nodes + np.bincount(b.batch.numpy()[b.edge_index[0].numpy()], minlength=int(b.num_graphs))
+        if nodes.max(initial=0) > FSG_ROWS or ents.max(initial=0) > FSG_ENTRIES:
+            small = False
+            break
+    return _up(int(n * slack), 32), _up(max(int(e * slack), 1), 32), _up(g, 8), small
 
 
 def epoch_order(num_graphs, epoch, seed=0, rank=0, world_size=1, graphs_per_step=None):
@@ -110,7 +122,9 @@ class GraphStore:
             nn = np.concatenate([self.node_counts[o], np.zeros(pad, dtype=np.int64)]).reshape(-1, B).sum(1)
             ee = np.concatenate([self.edge_counts[o], np.zeros(pad, dtype=np.int64)]).reshape(-1, B).sum(1)
             n, e = int(nn.max()), int(ee.max())
-        return _up(n, 32), _up(max(e, 1), 32), _up(B, 8)
+        small = bool(self.node_counts.max(initial=0) <= FSG_ROWS and
+                     (self.node_counts + self.edge_counts).max(initial=0) <= FSG_ENTRIES)
+        return _up(n, 32), _up(max(e, 1), 32), _up(B, 8), small
 
 
 class PeerExchange:
@@ -264,6 +278,7 @@ class Trainer:
         self._dead = False
         eng.set_caps(*caps)              # invalidates a Trainer that owned the previous workspace
         eng._owner = weakref.ref(self)   # ... and freezes the capacities: Engine.ensure_caps raises instead of growing
+        self.fused_small_graphs = bool(eng.caps.small_graphs)
         self.layout = PackedLayout(eng.caps.max_nodes, eng.caps.max_edges, eng.caps.max_graphs, eng.F)
         self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=self.device)

@@ -69,6 +69,9 @@ typedef struct {
   float w_c, w_o, w_co;        /* loss weights args.c / args.o / args.co */
   int32_t readout_bf16;        /* 0: readout MLP GEMMs as 3xTF32 on the tensor cores (fp32 accuracy, the 1e-5 parity path);
                                   1: bf16 operands, fp32 accumulate (BASELINE.json configs[4] "bf16 MLP / fp32 aggregate") */
+  int32_t readout_tc;          /* 0: auto -- the fp32 readout runs on the FFMA cluster kernels (measured faster at B = 128, where the
+                                  readout is latency- not FLOP-bound: profiles/README.md), bf16 on the tensor cores;
+                                  1: always the tensor-core kernels (tcgen05.mma, accumulators in TMEM) */
 } cal_model_desc;
 
 /* Capacities a workspace is sized for. */
@@ -76,7 +79,11 @@ typedef struct {
   int32_t max_nodes;
   int32_t max_edges;           /* edge_index columns before self-loop surgery */
   int32_t max_graphs;
-  int32_t reserved;
+  int32_t small_graphs;        /* != 0: the caller guarantees that every graph of every batch has <= 40 nodes and <= 320 edges after
+                                  self-loop surgery (edge_index columns without self loops + one per node).  CausalGCN with
+                                  hidden 128, <= 128 features and <= 148 graphs per batch then runs the fused small-graph
+                                  forward (one persistent kernel, graph blocks resident in shared memory, tensor-core node
+                                  transforms; csrc/fsg.cu).  A batch that breaks the promise sets CAL_ST_CAPACITY. */
 } cal_caps;
 
 /* Offsets (in floats) of every parameter inside the flat parameter buffer;
@@ -171,6 +178,7 @@ enum cal_ws_region {
   CAL_WS_OUT_NORM,     /* f32[EP] unweighted norm by out-CSR position (= IN_NORM[OUT_POS]) */
   CAL_WS_EDGE_WN,      /* f32[EP][2] dis_w[source] * edge_att by in-CSR position (weighted norm without the target factor) */
   CAL_WS_EDGE_NA,      /* f32[EP][2] node_att[source] by in-CSR position */
+  CAL_WS_FSG,          /* fused small-graph path: block plan, all-reduce scratch and counters, pre-split weight images */
   CAL_WS_REGION_COUNT
 };
 

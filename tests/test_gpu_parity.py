@@ -560,3 +560,53 @@ def test_full_size_cfg5_shapes():
     ora, b, perm = random_case(seed=91, hidden=128, layers=3, batch_size=512, features=64, avg_nodes=200,
                                ba_m=2, noise=0.0)
     _step_and_compare(clone_to_cuda(ora, M), ora, b, perm, M, O, illcond=True)      # BatchNorm sums over 103 788 rows
+
+
+def test_fused_small_graph_forward_matches_tiled_forward():
+    """csrc/fsg.cu (one persistent kernel, graph blocks resident in shared memory, tensor-core node
+    transforms) against the tiled kernels it replaces: every workspace region the backward pass reads,
+    the BatchNorm records and running statistics, and the outputs -- then the oracle."""
+    M, O = _mods()
+    ora, b, perm = random_case(seed=501, hidden=128, layers=3, batch_size=128)
+    bd = b.to(DEV)
+    N, E, B = b.batch.numel(), b.edge_index.size(1), 128
+    res = {}
+    for mode in ("off", "auto"):
+        net = clone_to_cuda(ora, M)
+        eng = net.engine
+        eng.fsg_mode = mode
+        st = eng.stage(bd, perm=perm.tolist())
+        assert bool(eng.caps.small_graphs) == (mode == "auto")
+        eng.prep(st)
+        out = eng.forward(st, train=True, with_loss=True).clone()
+        torch.cuda.synchronize()
+        assert eng.status() == 0
+        H, L, Nm, Bm = eng.H, eng.L, eng.caps.max_nodes, eng.caps.max_graphs
+        EPn = int(eng.region("IN_PTR", torch.int32)[N])
+        r = {"out": out.cpu(), "X": eng.region("X").view(L + 1, Nm, H)[:, :N].cpu(),
+             "NODE_ATT": eng.region("NODE_ATT").view(Nm, 2)[:N].cpu(), "PQ": eng.region("PQ").view(Nm, 4)[:N].cpu(),
+             "EDGE_ATT": eng.region("EDGE_ATT").view(-1, 2)[:EPn].cpu(), "DISW": eng.region("DISW").view(Nm, 2)[:N].cpu(),
+             "EDGE_WN": eng.region("EDGE_WN").view(-1, 2)[:EPn].cpu(), "EDGE_NA": eng.region("EDGE_NA").view(-1, 2)[:EPn].cpu(),
+             "AGG": eng.region("AGG").view(2, Nm, H)[:, :N].cpu(), "Z": eng.region("Z").view(2, Nm, H)[:, :N].cpu(),
+             "POOLED": eng.region("POOLED").view(2, Bm, H)[:, :B].cpu(), "loss": eng.loss_parts().cpu(),
+             "bn": eng.bn_buf.cpu().clone(), "nbt": eng.nbt.cpu().clone()}
+        kmax = -(-max(-(-eng.F // 4) * 4, 2 * H) // 32) * 32
+        rec = eng.region("BN").view(-1, 6, kmax)
+        r["rec"] = rec[:L + 3, :4, :H].cpu().clone()
+        r["rec0"] = rec[0, :4, :eng.F].cpu().clone()
+        res[mode] = r
+        if mode == "auto":
+            eng.backward(st, None)                       # the tiled backward runs on what the fused forward saved
+            torch.cuda.synchronize()
+            masks = _gpu_relu_masks(eng, N, B)
+            _, _, g32, _, _ = _oracle_step(ora, b, perm, torch.float32, masks)
+            _, _, g64, _, _ = _oracle_step(ora, b, perm, torch.float64, masks)
+            gpu = {n: eng.flat_grad[eng.param_offs[n]:eng.param_offs[n] + p.numel()].view(p.shape) for n, p in net.named_parameters()}
+            _check_grads(gpu, g32, g64)
+    a, f = res["off"], res["auto"]
+    assert torch.equal(a["nbt"], f["nbt"])
+    for k in ("X", "NODE_ATT", "PQ", "EDGE_ATT", "DISW", "EDGE_WN", "EDGE_NA", "AGG", "Z", "POOLED", "out", "loss", "bn", "rec", "rec0"):
+        assert rel_err(f[k], a[k]) < TOL, "%s: fused vs tiled rel err %.3e" % (k, rel_err(f[k], a[k]))
+    o32, _, _, _, _ = _oracle_step(ora, b, perm)
+    o64, _, _, _, _ = _oracle_step(ora, b, perm, torch.float64)
+    _check_outputs([f["out"][h] for h in range(3)], o32, o64)

@@ -185,11 +185,11 @@ def test_graph_store_layout_and_caps():
         assert int(st.edge_dst[s0:s1].max()) < n[g]
     order = np.random.RandomState(0).permutation(23)
     B = 5
-    cn, ce, cb = st.caps(B, order)
+    cn, ce, cb, _small = st.caps(B, order)
     for s in range(0, 23, B):
         b = M.Batch.from_data_list([ds[i] for i in order[s:s + B]])
         assert b.batch.numel() <= cn and b.edge_index.size(1) <= ce
-    wn, we, wb = st.caps(B)                                  # worst case covers any order
+    wn, we, wb, _small = st.caps(B)                                  # worst case covers any order
     assert wn >= cn and we >= ce and wb == cb == 8
 
 

@@ -24,6 +24,10 @@ names_rb = ["dep wait", "d logits", "fc2/bn2 bwd + da1", "dW1 stage+issue", "dW1
             "dy1 mma tail", "bn1 bwd + du"]
 print("k_readout_tc_fwd (head 0) cycles:", list(zip(names_rf, st[64:72])), "sum", sum(st[64:72]))
 print("k_readout_tc_bwd (head 0) cycles:", list(zip(names_rb, st[80:89])), "sum", sum(st[80:89]))
+names_fsg = ["dep wait", "plan+CSR+bn_feat", "feat product", "epilogues", "publish", "raw aggregation", "stats wait+finalize",
+             "affine+split", "weight wait", "MMA", "node att+stats", "edge att", "masked epilogue+pool"]
+if tr.fused_small_graphs:
+    print("k_fsg_forward (CTA 0) cycles:", list(zip(names_fsg, st[48:61])), "sum", sum(st[48:61]))
 names_p = ["wait+zero", "edges+counts", "node pass", "scan", "fill", "sort", "write-out"]
 print("k_prep_small structure CTA (slice 0) cycles:", list(zip(names_p, st[96:103])), "sum", sum(st[96:103]))
 print("k_prep_small statistics CTA 0 [column sums, grid sum]:", st[112:114], " finishing CTA:", st[116:118])
