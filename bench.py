@@ -460,6 +460,22 @@ def run_gpu(a, rank, local_rank, world):
             ab = algorithmic_bytes(name, N, E1, bs, eng.H, eng.F, eng.C, eng.L, P)
             stage_tab.append({"stage": name, "launches": nl, "us": 1e3 * t_ms, "alg_bytes": ab,
                               "gbs": ab / (t_ms * 1e-3) / 1e9 if t_ms > 0 else None})
+        # fused small-graph path (csrc/fsg.cu, fsg_bwd.cu): ONE kernel runs the stages feat .. masked_convs
+        # (masked_gemm_bwd .. feat_bwd); the stages it absorbs launch nothing -- their algorithmic bytes
+        # belong to the kernel that does their work
+        merged, owner = [], None
+        for r in stage_tab:
+            if r["launches"] == 0 and owner is not None and owner["stage"] in ("feat", "masked_gemm_bwd", "fsg_forward", "fsg_backward"):
+                owner["alg_bytes"] += r["alg_bytes"]
+                owner["us"] += r["us"]
+                owner.setdefault("absorbs", []).append(r["stage"])
+                owner["stage"] = "fsg_forward" if owner["stage"] in ("feat", "fsg_forward") else "fsg_backward"
+                continue
+            owner = dict(r)
+            merged.append(owner)
+        for r in merged:
+            r["gbs"] = r["alg_bytes"] / (r["us"] * 1e-6) / 1e9 if r["us"] > 0 else None
+        stage_tab = merged
         # dominant KERNEL = the kernel family with the largest share of the step (the three backbone
         # layers run the same kernel); achieved = its algorithmic bytes / its time, per launch
         fam = {}

@@ -166,6 +166,7 @@ int build_ctx(const cal_model_desc* m, const cal_caps* caps, const cal_param_off
   c.fsg = REG(unsigned char, CAL_WS_FSG);
   c.fsg_on = m->model == CAL_MODEL_GCN && m->hidden == 128 && m->num_features <= 128 && caps->max_graphs <= kSMs &&
              caps->small_graphs != 0;
+  c.fsg_bwd_on = c.fsg_on && caps->small_graphs != 2;
 #undef REG
   for (int l = 0; l < CAL_MAX_LAYERS + 2; ++l) c.gp_conv[l] = lay.gp_conv[l];
   c.gp_att = lay.gp_att;
@@ -368,6 +369,10 @@ int cal_causal_backward(const cal_model_desc* m, const cal_caps* caps, const cal
   stage_range(flags, &lo, &hi);
   for (int st = lo; st <= hi; ++st) {
     if (st == 0) rc = launch_heads_backward(c, s);
+    else if (c.fsg_bwd_on && st >= 1 && st <= 5 + L) {
+      // fused small-graph path: stage "masked_gemm_bwd" runs the whole backward down to the input transform (fsg_bwd.cu)
+      if (st == 1) rc = launch_fsg_backward(c, s);
+    } else if (c.fsg_bwd_on && st == 6 + L) rc = launch_fsg_grad_reduce(c, s);
     else if (st == 1) rc = launch_masked_bwd_gemm(c, s);
     else if (st == 2) rc = launch_masked_bwd_gather(c, s);
     else if (st == 3) rc = launch_norm_backward(c, s);

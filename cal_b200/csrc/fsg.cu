@@ -15,35 +15,10 @@
 // The kernel writes the same workspace regions as the tiled kernels it replaces (conv.cu k_feat_fwd /
 // k_conv_fwd / k_masked_fwd_both, attn.cu k_edge_att, head.cu k_pool), so the backward pass and the tests
 // are agnostic of which forward ran.
-#include "fsg.cuh"
-#include "umma.cuh"
+#include "fsg_dev.cuh"
 
 namespace cal {
 namespace {
-
-constexpr int FT = 256;                               // threads per CTA
-constexpr int FH = 128;                               // hidden size this path is built for
-constexpr uint32_t kALbo = 2048, kASbo = 128;         // weight operand: chunk c of row m at c * 2048 + m * 16
-constexpr uint32_t kBLbo = 144, kBSbo = 32 * 144;     // node operand: chunk c of row i at (i / 8) * 4608 + c * 144 + (i % 8) * 16
-constexpr int kBPart = (kFsgRows / 8) * (int)kBSbo;   // 23040 bytes
-constexpr int kTmemCols = 256;                        // main accumulators at columns 0 / 64, correction terms at 128 / 192
-
-// per-category cycle counters of CTA 0 / thread 0 (-DCAL_PHASE_TIMING builds): status[48 + category]
-#ifdef CAL_PHASE_TIMING
-#define FSG_TDECL long long ft_last = clock64(); long long ft_acc[16] = {0};
-#define FSG_T(cat) do { const long long t_ = clock64(); ft_acc[cat] += t_ - ft_last; ft_last = t_; } while (0)
-#define FSG_TDUMP(c) do { if (blockIdx.x == 0 && threadIdx.x == 0) for (int q_ = 0; q_ < 16; ++q_) (c).status[48 + q_] = (int)ft_acc[q_]; } while (0)
-#else
-#define FSG_TDECL
-#define FSG_T(cat)
-#define FSG_TDUMP(c)
-#endif
-
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 
 // ---- shared memory ----
 struct FsgSmem {
@@ -72,63 +47,6 @@ __host__ __device__ inline FsgSmem fsg_smem() {
   s.tot = o;     o += 512 * 8;
   s.total = o;
   return s;
-}
-
-// ---- the in-kernel all-reduce of per-CTA fp64 vectors (deterministic: groups of 8 CTAs, fixed order) ----
-__device__ __forceinline__ void fsg_publish(const FsgWs& w, int phase, int G, const double* sPart, int n) {
-  __shared__ int s_lead;
-  const int t = threadIdx.x;
-  const int grp = blockIdx.x / kFsgGroup, gsize = imin(kFsgGroup, G - grp * kFsgGroup);
-  double* mine = w.l0 + (size_t)blockIdx.x * kFsgVec;
-  for (int i = t; i < n; i += FT) mine[i] = sPart[i];
-  __syncthreads();
-  if (t == 0) {
-    __threadfence();
-    const unsigned int old = atomicAdd(&w.cnt[phase * kFsgCntStride + 1 + grp], 1u);
-    s_lead = (old == (unsigned int)gsize - 1u);
-    if (s_lead) __threadfence();
-  }
-  __syncthreads();
-  if (!s_lead) return;
-  double* dst = w.l1 + ((size_t)(phase & 1) * kFsgMaxGroups + grp) * kFsgVec;
-  for (int i = t; i < n; i += FT) {
-    double v[kFsgGroup];
-#pragma unroll
-    for (int m = 0; m < kFsgGroup; ++m) v[m] = m < gsize ? __ldcg(&w.l0[(size_t)(grp * kFsgGroup + m) * kFsgVec + i]) : 0.0;
-    double sum = v[0];
-#pragma unroll
-    for (int m = 1; m < kFsgGroup; ++m) sum += v[m];
-    dst[i] = sum;
-  }
-  __syncthreads();
-  if (t == 0) {
-    __threadfence();
-    atomicAdd(&w.cnt[phase * kFsgCntStride], 1u);
-  }
-}
-__device__ __forceinline__ void fsg_wait_total(const FsgWs& w, int phase, int G, int n, double* sTot) {
-  const int t = threadIdx.x;
-  const int ngrp = (G + kFsgGroup - 1) / kFsgGroup;
-  if (t == 0) {
-    while (ld_acquire_gpu(&w.cnt[phase * kFsgCntStride]) < (unsigned int)ngrp) {
-    }
-    __threadfence();
-  }
-  __syncthreads();
-  const double* src = w.l1 + (size_t)(phase & 1) * kFsgMaxGroups * kFsgVec;
-  for (int i = t; i < n; i += FT) {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int g = 0;
-    for (; g + 4 <= ngrp; g += 4) {
-      s0 += __ldcg(src + (size_t)(g + 0) * kFsgVec + i);
-      s1 += __ldcg(src + (size_t)(g + 1) * kFsgVec + i);
-      s2 += __ldcg(src + (size_t)(g + 2) * kFsgVec + i);
-      s3 += __ldcg(src + (size_t)(g + 3) * kFsgVec + i);
-    }
-    for (; g < ngrp; ++g) s0 += __ldcg(src + (size_t)g * kFsgVec + i);
-    sTot[i] = (s0 + s1) + (s2 + s3);
-  }
-  __syncthreads();
 }
 
 // training-mode BatchNorm `id` from the grid totals tot[0..K) (sum) and tot[K..2K) (sum of squares): threads
@@ -163,38 +81,6 @@ __device__ __forceinline__ void fsg_bn_finalize(const Ctx& c, int id, int count,
       rv[k] = (1.f - c.momentum) * rv[k] + c.momentum * (float)unb;
     }
     if (k == 0 && c.nbt != nullptr) c.nbt[id] += 1;
-  }
-}
-
-__device__ __forceinline__ uint32_t b_off(int i, int kc) { return (uint32_t)(i >> 3) * kBSbo + (uint32_t)kc * kBLbo + (uint32_t)(i & 7) * 16u; }
-
-// hi / lo split of one 16-byte chunk into the node operand
-__device__ __forceinline__ void put_b(unsigned char* b_hi, unsigned char* b_lo, int i, int kc, float4 v) {
-  float h0, h1, h2, h3, l0, l1, l2, l3;
-  umma::split_tf32(v.x, h0, l0);
-  umma::split_tf32(v.y, h1, l1);
-  umma::split_tf32(v.z, h2, l2);
-  umma::split_tf32(v.w, h3, l3);
-  const uint32_t off = b_off(i, kc);
-  *reinterpret_cast<float4*>(b_hi + off) = make_float4(h0, h1, h2, h3);
-  *reinterpret_cast<float4*>(b_lo + off) = make_float4(l0, l1, l2, l3);
-}
-
-// D_main (+)= A_hi B_hi ; D_corr (+)= A_lo B_hi + A_hi B_lo over `ksteps` steps of 8 k.  One thread.
-// (Two accumulators: every MMA re-rounds its accumulator, so the small correction terms are kept out of the
-// main sum's rounding chain: 16 instead of 48 roundings of the main accumulator at K = 128.)
-__device__ __forceinline__ void issue_3xtf32(const unsigned char* a_hi, const unsigned char* a_lo, const unsigned char* b_hi,
-                                             const unsigned char* b_lo, uint32_t d_main, uint32_t d_corr, int ksteps, int npad) {
-  const uint32_t idesc = umma::instr_desc(umma::kFmtTF32, 128, npad);
-  for (int s = 0; s < ksteps; ++s) {
-    const uint32_t aa = (uint32_t)s * 2u * kALbo, ba = (uint32_t)s * 2u * kBLbo;
-    const uint64_t ah = umma::smem_desc(umma::smem_addr(a_hi) + aa, kALbo, kASbo);
-    const uint64_t al = umma::smem_desc(umma::smem_addr(a_lo) + aa, kALbo, kASbo);
-    const uint64_t bh = umma::smem_desc(umma::smem_addr(b_hi) + ba, kBLbo, kBSbo);
-    const uint64_t bl = umma::smem_desc(umma::smem_addr(b_lo) + ba, kBLbo, kBSbo);
-    umma::mma_tf32(d_corr, al, bh, idesc, s > 0);
-    umma::mma_tf32(d_corr, ah, bl, idesc, 1u);
-    umma::mma_tf32(d_main, ah, bh, idesc, s > 0);
   }
 }
 
@@ -685,7 +571,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
       FSG_T(12);                                                      // 12: masked epilogue + pooling
     }
   }
-  FSG_TDUMP(c);
+  FSG_TDUMP(c, 48);
 
   // ---- teardown: TMEM, and the last CTA re-arms the all-reduce counters for the next launch ----
   umma::fence_before_sync();
@@ -763,7 +649,7 @@ __global__ void __launch_bounds__(256) k_fsg_prep(const Ctx c, const int n_img_b
 }  // namespace
 
 int fsg_grid(const Ctx& c) { return imax(1, imin(c.Bm, kSMs)); }
-size_t fsg_region_bytes(int Bm, int L) { return fsg_layout(Bm, L).total; }
+size_t fsg_region_bytes(int Bm, int L, int F) { return fsg_layout(Bm, L, F).total; }
 
 int launch_fsg_prep(const Ctx& c, cudaStream_t s) {
   const int n_img = (2 * (c.L + 2) + 1) * 8;

@@ -22,10 +22,20 @@ constexpr int kFsgImg = 2 * kFsgImgPart;   // hi | lo
 
 // the CAL_WS_FSG region (byte offsets)
 struct FsgLayout {
-  size_t plan, info, cnt, l0, l1, img, total;
+  size_t plan, info, cnt, l0, l1, img, part, total;
 };
 __host__ __device__ inline size_t fsg_up(size_t x) { return (x + 255) & ~(size_t)255; }
-__host__ __device__ inline FsgLayout fsg_layout(int Bm, int L) {
+
+// Per-block partial parameter gradients of the fused backward (floats per block, H = 128):
+//   conv matrix j in [0, L+2): [H*H] d W | [H] d b;  attention: node_att_w [2][H] | edge_att_w as p0 | q0 | p1 | q1 |
+//   node_att_b [2] | edge_att_b [2] (padded to 8H + 4);  input transform: M [F][H] | column sums [H] (k_feat_bwd).
+constexpr int kFsgH = 128;
+__host__ __device__ inline size_t fsg_part_conv(int j) { return (size_t)j * (kFsgH * kFsgH + kFsgH); }
+__host__ __device__ inline size_t fsg_part_att(int L) { return fsg_part_conv(L + 2); }
+__host__ __device__ inline size_t fsg_part_feat(int L) { return fsg_part_att(L) + 8 * kFsgH + 4; }
+__host__ __device__ inline size_t fsg_part_floats(int L, int F) { return fsg_part_feat(L) + (size_t)F * kFsgH + kFsgH; }
+
+__host__ __device__ inline FsgLayout fsg_layout(int Bm, int L, int F) {
   FsgLayout f;
   size_t o = 0;
   f.plan = o;  o = fsg_up(o + 16);                                        // i32[4]: number of blocks, ok flag
@@ -34,6 +44,8 @@ __host__ __device__ inline FsgLayout fsg_layout(int Bm, int L) {
   f.l0 = o;    o = fsg_up(o + (size_t)kSMs * kFsgVec * 8);
   f.l1 = o;    o = fsg_up(o + (size_t)2 * kFsgMaxGroups * kFsgVec * 8);
   f.img = o;   o = fsg_up(o + (size_t)((L + 2) * 2 + 1) * kFsgImg * 4);   // forward / backward image per conv matrix + feat
+  f.part = o;                                                             // partial gradients, one slot per block
+  if (Bm <= kSMs && F <= 128) o = fsg_up(o + (size_t)(Bm > 0 ? Bm : 1) * fsg_part_floats(L, F) * 4);
   f.total = o;
   return f;
 }
@@ -45,9 +57,10 @@ struct FsgWs {
   double* l0;
   double* l1;
   float* img;
+  float* part;
 };
 __host__ __device__ inline FsgWs fsg_ws(const Ctx& c) {
-  const FsgLayout f = fsg_layout(c.Bm, c.L);
+  const FsgLayout f = fsg_layout(c.Bm, c.L, c.F);
   FsgWs w;
   w.plan = reinterpret_cast<int*>(c.fsg + f.plan);
   w.info = reinterpret_cast<int*>(c.fsg + f.info);
@@ -55,6 +68,7 @@ __host__ __device__ inline FsgWs fsg_ws(const Ctx& c) {
   w.l0 = reinterpret_cast<double*>(c.fsg + f.l0);
   w.l1 = reinterpret_cast<double*>(c.fsg + f.l1);
   w.img = reinterpret_cast<float*>(c.fsg + f.img);
+  w.part = reinterpret_cast<float*>(c.fsg + f.part);
   return w;
 }
 // weight-operand images: matrix j in [0, L+2) = convs[j] / context_convs / objects_convs

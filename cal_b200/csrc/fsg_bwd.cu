@@ -1,0 +1,912 @@
+// fsg_bwd.cu -- the fused small-graph BACKWARD pass of CausalGCN: ONE persistent kernel from the pooled-embedding
+// gradients (left by the readout backward) down to the input transform, the mirror of fsg.cu.
+//
+// A CTA owns one block of whole graphs (the plan of k_fsg_prep).  Everything that couples nodes -- the transpose
+// aggregates (gcn_conv.py:92-97 backward), the weighted-normalisation backward through both endpoints' degrees
+// (gcn_conv.py:59-70), the edge / node attention softmax backward (model.py:97-111) -- is local to the CTA's
+// shared memory; the gradient products  D = u W^T  (and  d agg = d z W^T  of the two masked convs) run on the
+// tensor cores (tcgen05.mma, 3xTF32, accumulators in TMEM, pre-split weight images by cp.async.bulk); the weight
+// gradients  d W = y^T u  are FFMA2 outer products that run while the BatchNorm all-reduce of the layer travels.
+// Training-mode BatchNorm backward is the only coupling between CTAs: one deterministic in-kernel all-reduce of
+// (sum dy, sum dy * xhat) per BatchNorm (bnc | bno together, then bns_conv[L-1 .. 0]): 1 + L per step.
+//
+// Replaces k_masked_bwd_gemm, k_masked_bwd_gather, k_norm_bwd, k_att_bwd, k_conv_bwd x L and k_feat_bwd
+// (conv.cu / attn.cu) when the fused small-graph path is on; the per-block partial parameter gradients go to
+// the CAL_WS_FSG region and are summed in block order by k_fsg_grad_reduce (deterministic).
+#include "fsg_dev.cuh"
+
+namespace cal {
+namespace {
+
+constexpr int kGBytes = kFsgRows * FH * 4;            // 20480: one row-major [rows][128] fp32 tile
+constexpr uint32_t kTailOff = 65536u - (uint32_t)kGBytes;   // the gradient rows alias the last 10 K-chunks of the lo image
+constexpr int kTailStep = (int)(kTailOff / (2u * kALbo));   // first K step (of 8) whose lo operand lies in the tail: 11
+static_assert(kTailOff % (2u * kALbo) == 0, "the tail starts on a K-step boundary");
+constexpr int kRowsPerWarp = kFsgRows / 8;            // 5
+
+struct FsgBSmem {
+  size_t a_hi, a_lo, g, b_hi, b_lo, x, in_ptr, out_ptr, in_src, out_dst, out_pos, out_nrm, w, dnrm, dt, rowf, vec, part, tot, pool, total;
+};
+__host__ __device__ inline FsgBSmem fsg_bsmem() {
+  FsgBSmem s;
+  size_t o = 0;
+  s.a_hi = o;    o += 65536;
+  s.a_lo = o;    o += 65536;
+  s.g = s.a_lo + kTailOff;                              // [rows][128] gradient rows (layer loop), inside a_lo
+  s.b_hi = o;    o += kBPart;
+  s.b_lo = o;    o += kBPart;
+  s.x = o;       o += (size_t)kGBytes;
+  s.in_ptr = o;  o += 48 * 4;
+  s.out_ptr = o; o += 48 * 4;
+  s.in_src = o;  o += kFsgEntries * 4;
+  s.out_dst = o; o += kFsgEntries * 4;
+  s.out_pos = o; o += kFsgEntries * 4;
+  s.out_nrm = o; o += kFsgEntries * 4;
+  s.w = o;       o += kFsgEntries * 8;                  // edge attention by in-CSR position (both branches)
+  s.dnrm = o;    o += kFsgEntries * 8;                  // d norm by in-CSR position
+  s.dt = o;      o += kFsgEntries * 8;                  // d (edge logits) by in-CSR position
+  s.rowf = o;    o += (size_t)kFsgRows * 8 * 4;         // per row: node att (2), dis_w (2), dp (2), pad (2)
+  s.vec = o;     o += 12 * FH * 4;                      // per-channel BatchNorm vectors (two sets of sc, sh, mean, rstd, c1, c2)
+  s.part = o;    o += 512 * 8;
+  s.tot = o;     o += 512 * 8;
+  s.pool = o;    o += 2 * FH * 4;                       // pooled-embedding gradient of the block's graph, both branches
+  s.total = o;
+  return s;
+}
+
+// BatchNorm-backward totals tot[0..K) = sum dy, tot[K..2K) = sum dy * xhat  ->  c1 = mean(dy), c2 = mean(dy * xhat) in
+// shared memory by threads [t0, t0 + K); CTA 0 publishes d gamma / d beta (and the record)
+__device__ __forceinline__ void fsg_bn_bwd_finalize(const Ctx& c, int id, int count, const double* tot, float* s_c1, float* s_c2,
+                                                    int t0) {
+  const int K = c.bn_K[id];
+  const int k = (int)threadIdx.x - t0;
+  if (k < 0 || k >= K) return;
+  const double inv = count > 0 ? 1.0 / count : 0.0;
+  const double a = tot[k], b = tot[K + k];
+  const float c1 = (float)(a * inv), c2 = (float)(b * inv);
+  s_c1[k] = c1;
+  s_c2[k] = c2;
+  if (blockIdx.x == 0) {
+    c.bnf(id, BN_C1)[k] = c1;
+    c.bnf(id, BN_C2)[k] = c2;
+    c.grads[c.bn_gamma[id] + k] = (float)b;
+    c.grads[c.bn_beta[id] + k] = (float)a;
+  }
+}
+
+// ---- the weight-gradient outer product  acc[ia][ib] += sum_r P[r][ia] * Q[r][ib]  over the block's rows ----
+// 256 threads cover the [128 x 128] result: thread (ty = tid / 16, tx = tid % 16) owns rows {ty*4 + i, 64 + ty*4 + i}
+// and columns {tx*4 + i, 64 + tx*4 + i} (i < 4), 32 FFMA2 per row of the block.  P comes from a row-major tile
+// (optionally through the BatchNorm affine: y = sc * x + sh), Q from the MMA node operand (hi + lo = the value).
+struct DwAcc {
+  f32x2 acc[8][4];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = pack2(0.f, 0.f);
+  }
+  __device__ __forceinline__ static void load_p(const float* sP, int r, int ty, float (&p)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(sP + r * FH + ty * 4);
+    const float4 b = *reinterpret_cast<const float4*>(sP + r * FH + 64 + ty * 4);
+    p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;
+  }
+  __device__ __forceinline__ static void load_q(const unsigned char* bh, const unsigned char* bl, int r, int tx, float (&q)[8]) {
+    const uint32_t o0 = b_off(r, tx), o1 = b_off(r, 16 + tx);
+    const float4 h0 = *reinterpret_cast<const float4*>(bh + o0), l0 = *reinterpret_cast<const float4*>(bl + o0);
+    const float4 h1 = *reinterpret_cast<const float4*>(bh + o1), l1 = *reinterpret_cast<const float4*>(bl + o1);
+    q[0] = h0.x + l0.x; q[1] = h0.y + l0.y; q[2] = h0.z + l0.z; q[3] = h0.w + l0.w;
+    q[4] = h1.x + l1.x; q[5] = h1.y + l1.y; q[6] = h1.z + l1.z; q[7] = h1.w + l1.w;
+  }
+  template <bool AFFINE>
+  __device__ __forceinline__ void accumulate(const float* sP, const float* s_sc, const float* s_sh, const unsigned char* bh,
+                                             const unsigned char* bl, int rows) {
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    float sc[8], sh[8];
+    if (AFFINE) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = (i >> 2) * 64 + ty * 4 + (i & 3);
+        sc[i] = s_sc[k];
+        sh[i] = s_sh[k];
+      }
+    }
+    if (rows <= 0) return;
+    float p[8], q[8], pn[8], qn[8];
+    load_p(sP, 0, ty, p);
+    load_q(bh, bl, 0, tx, q);
+    for (int r = 0; r < rows; ++r) {
+      const int rn = r + 1 < rows ? r + 1 : r;
+      load_p(sP, rn, ty, pn);
+      load_q(bh, bl, rn, tx, qn);
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        const float pv = AFFINE ? fmaf(p[a], sc[a], sh[a]) : p[a];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = ffma2_bcast(pv, pack2(q[2 * b], q[2 * b + 1]), acc[a][b]);
+      }
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        p[a] = pn[a];
+        q[a] = qn[a];
+      }
+    }
+  }
+  __device__ __forceinline__ void store(float* dst) const {        // dst [128][128]
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const int row = (a >> 2) * 64 + ty * 4 + (a & 3);
+      float v[8];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) unpack2(acc[a][b], v[2 * b], v[2 * b + 1]);
+      *reinterpret_cast<float4*>(dst + (size_t)row * FH + tx * 4) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(dst + (size_t)row * FH + 64 + tx * 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+};
+
+// sum over the 8 warps of a lane-owned [4-channel] accumulator, fixed order: dst[k] (k < 128) by threads 0..127
+__device__ __forceinline__ void colsum8(const float (&acc)[4], float* sRed /* [8][128] */, float* dst) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  *reinterpret_cast<float4*>(sRed + warp * FH + lane * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  __syncthreads();
+  if (threadIdx.x < FH) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += sRed[w * FH + threadIdx.x];
+    dst[threadIdx.x] = s;
+  }
+}
+
+// global rows [n0, n0 + rows) of a [*, 128] fp32 matrix -> row-major shared tile (16-byte asynchronous copies)
+__device__ __forceinline__ void rows_async(float* sdst, const float* gsrc, int rows) {
+  for (int i = threadIdx.x; i < rows * (FH / 4); i += FT) cp_async16(sdst + i * 4, gsrc + (size_t)i * 4);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The backward kernel.  grid = min(max_graphs, 148), 256 threads, 1 CTA per SM.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t bar_w, bar_w2, bar_mma;
+  __shared__ uint32_t tmem_slot;
+  const FsgBSmem S = fsg_bsmem();
+  unsigned char* sAh = smem + S.a_hi;
+  unsigned char* sAl = smem + S.a_lo;
+  float* sG = reinterpret_cast<float*>(smem + S.g);                  // [rows][128]
+  unsigned char* sBh = smem + S.b_hi;
+  unsigned char* sBl = smem + S.b_lo;
+  float* sX = reinterpret_cast<float*>(smem + S.x);                  // [rows][128]
+  int* sInPtr = reinterpret_cast<int*>(smem + S.in_ptr);
+  int* sOutPtr = reinterpret_cast<int*>(smem + S.out_ptr);
+  int* sInSrc = reinterpret_cast<int*>(smem + S.in_src);
+  int* sOutDst = reinterpret_cast<int*>(smem + S.out_dst);
+  int* sOutPos = reinterpret_cast<int*>(smem + S.out_pos);
+  float* sOutNrm = reinterpret_cast<float*>(smem + S.out_nrm);
+  float2* sW = reinterpret_cast<float2*>(smem + S.w);
+  float2* sDn = reinterpret_cast<float2*>(smem + S.dnrm);
+  float2* sDt = reinterpret_cast<float2*>(smem + S.dt);
+  float* sRow = reinterpret_cast<float*>(smem + S.rowf);             // [rows][8]
+  float* sVec = reinterpret_cast<float*>(smem + S.vec);
+  double* sPart = reinterpret_cast<double*>(smem + S.part);
+  double* sTot = reinterpret_cast<double*>(smem + S.tot);
+  float* sPool = reinterpret_cast<float*>(smem + S.pool);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const FsgWs ws = fsg_ws(c);
+  const int L = c.L, F = c.F;
+
+  // ---- before the dependency wait: TMEM, barriers, attention projection weights (parameters) ----
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, kTmemCols);
+  if (t == 0) {
+    umma::mbar_init(&bar_w, 1);
+    umma::mbar_init(&bar_w2, 1);
+    umma::mbar_init(&bar_mma, 1);
+    umma::mbar_fence_init();
+  }
+  float wn0[4], wn1[4], wp0[4], wp1[4], wq0[4], wq1[4];
+  {
+    const float* Wn = c.params + c.po.node_att_w;                      // [2][H]
+    const float* We = c.params + c.po.edge_att_w;                      // [2][2H]
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = lane * 4 + i;
+      wn0[i] = Wn[k];
+      wn1[i] = Wn[FH + k];
+      wp0[i] = We[k];
+      wp1[i] = We[2 * FH + k];
+      wq0[i] = We[FH + k];
+      wq1[i] = We[3 * FH + k];
+    }
+  }
+  umma::fence_before_sync();
+  FSG_TDECL
+  pdl_sync();
+  FSG_T(0);                                                           // 0: dependency wait
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const int nblk = ws.plan[0], plan_ok = ws.plan[1];
+  const int N = imin(imax(c.dims[0], 0), c.Nm);
+  const bool active = plan_ok != 0 && (int)blockIdx.x < nblk;
+  const int G = nblk;
+  uint32_t par_w = 0, par_w2 = 0, par_m = 0;
+
+  if (active) {
+    const int4 ia = *reinterpret_cast<const int4*>(ws.info + (size_t)blockIdx.x * 8);
+    const int4 ib = *reinterpret_cast<const int4*>(ws.info + (size_t)blockIdx.x * 8 + 4);
+    const int g0 = ia.x, n0 = ia.z, n1 = ia.w, ie0 = ib.x, ie1 = ib.y, oe0 = ib.z;
+    const int Nc = n1 - n0, Ec = ie1 - ie0;
+    const int npad = imax(8, (Nc + 7) & ~7);
+    float* part = ws.part + (size_t)blockIdx.x * fsg_part_floats(L, F);
+
+    // ================= stage 0: block-local structure, masks, BatchNorm records, pooled gradient =================
+    if (t == 0) {                                                      // context_convs backward image (whole)
+      umma::mbar_expect_tx(&bar_w, 2u * 65536u);
+      umma::bulk_g2s(sAh, fsg_img_bwd(ws, L), 65536u, &bar_w);
+      umma::bulk_g2s(sAl, fsg_img_bwd(ws, L) + kFsgImgPart, 65536u, &bar_w);
+    }
+    rows_async(sX, c.agg + (size_t)n0 * FH, Nc);                       // agg of the causal branch (weight gradient)
+    for (int i = t; i <= Nc; i += FT) {
+      sInPtr[i] = c.in_ptr[n0 + i] - ie0;
+      sOutPtr[i] = c.out_ptr[n0 + i] - oe0;
+    }
+    for (int e = t; e < Ec; e += FT) {
+      sInSrc[e] = c.in_src[ie0 + e] - n0;
+      sOutDst[e] = c.out_dst[oe0 + e] - n0;
+      sOutPos[e] = c.out_pos[oe0 + e] - ie0;
+      sOutNrm[e] = c.out_norm[oe0 + e];
+      sW[e] = *reinterpret_cast<const float2*>(c.watt + (size_t)(ie0 + e) * 2);
+    }
+    for (int i = t; i < Nc; i += FT) {
+      const float2 a = *reinterpret_cast<const float2*>(c.natt + (size_t)(n0 + i) * 2);
+      const float2 d = *reinterpret_cast<const float2*>(c.disw + (size_t)(n0 + i) * 2);
+      float* r = sRow + i * 8;
+      r[0] = a.x; r[1] = a.y; r[2] = d.x; r[3] = d.y; r[4] = 0.f; r[5] = 0.f;
+    }
+    {
+      // records of bnc (threads 0..127) / bno (128..255): sc | sh | mean | rstd  (set br at sVec + br * 6 * FH)
+      const int br = t >> 7, k = t & 127, id = L + 1 + br;
+      float* v = sVec + br * 6 * FH;
+      v[k] = c.bnf(id, BN_SCALE)[k];
+      v[FH + k] = c.bnf(id, BN_SHIFT)[k];
+      v[2 * FH + k] = c.bnf(id, BN_MEAN)[k];
+      v[3 * FH + k] = c.bnf(id, BN_RSTD)[k];
+      // global_add_pool backward = broadcast of the pooled gradient (model.py:115-116); the c <- co path goes
+      // through the inverse permutation (model.py:152-157)
+      const size_t H2 = 2 * FH;
+      float g;
+      if (br == 0) g = c.du[((size_t)0 * c.Bm + g0) * H2 + k] + c.du[((size_t)2 * c.Bm + c.invperm[g0]) * H2 + k];
+      else g = c.du[((size_t)1 * c.Bm + g0) * H2 + k] + c.du[((size_t)2 * c.Bm + g0) * H2 + (c.cat ? FH : 0) + k];
+      sPool[br * FH + k] = g;
+    }
+    __syncthreads();
+    FSG_T(1);                                                         // 1: structure + records
+
+    // ================= stage 1: the two masked convs, dense part (model.py:112-113 backward) =================
+    //   dz = dpool * relu'(z);  d agg = dz W^T (tensor cores);  dW += agg^T dz;  db += dz
+    for (int br = 0; br < 2; ++br) {
+      const float* Zg = c.Z + (size_t)br * c.Nm * FH + (size_t)n0 * FH;
+      const float4 gp = *reinterpret_cast<const float4*>(sPool + br * FH + lane * 4);
+      float dbias[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int i = warp; i < npad; i += 8) {
+        float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < Nc) {
+          const float4 z = __ldcg(reinterpret_cast<const float4*>(Zg + (size_t)i * FH + lane * 4));
+          u = make_float4(z.x > 0.f ? gp.x : 0.f, z.y > 0.f ? gp.y : 0.f, z.z > 0.f ? gp.z : 0.f, z.w > 0.f ? gp.w : 0.f);
+          dbias[0] += u.x; dbias[1] += u.y; dbias[2] += u.z; dbias[3] += u.w;
+        }
+        put_b(sBh, sBl, i, lane, u);
+      }
+      umma::fence_async_smem();
+      cp_async_wait_all();
+      __syncthreads();
+      if (t == 0) {
+        umma::mbar_wait(&bar_w, par_w);
+        umma::fence_after_sync();
+        issue_3xtf32(sAh, sAl, sBh, sBl, tmem + (br ? 64u : 0u), tmem + 128u + (br ? 64u : 0u), FH / 8, npad);
+        umma::commit(&bar_mma);
+      }
+      par_w ^= 1u;
+      FSG_T(2);                                                       // 2: dz operand + issue
+      {
+        DwAcc dw;
+        dw.zero();
+        dw.accumulate<false>(sX, nullptr, nullptr, sBh, sBl, Nc);
+        dw.store(part + fsg_part_conv(L + br));
+      }
+      colsum8(dbias, reinterpret_cast<float*>(sPart), part + fsg_part_conv(L + br) + FH * FH);
+      FSG_T(3);                                                       // 3: weight gradient (FFMA)
+      umma::mbar_wait(&bar_mma, par_m);
+      par_m ^= 1u;
+      umma::fence_after_sync();
+      __syncthreads();                                                // sX / the operand are free; so is the weight image
+      if (br == 0) {
+        rows_async(sX, c.agg + (size_t)c.Nm * FH + (size_t)n0 * FH, Nc);
+        if (t == 0) {
+          umma::mbar_expect_tx(&bar_w, 2u * 65536u);
+          umma::bulk_g2s(sAh, fsg_img_bwd(ws, L + 1), 65536u, &bar_w);
+          umma::bulk_g2s(sAl, fsg_img_bwd(ws, L + 1) + kFsgImgPart, 65536u, &bar_w);
+        }
+      }
+      FSG_T(4);                                                       // 4: MMA tail
+    }
+    // x_{L+1} rows for the sparse part; the image of the top backbone layer (all but the tail the gradient rows alias)
+    rows_async(sX, c.Xl(L) + (size_t)n0 * FH, Nc);
+    if (t == 0) {
+      umma::mbar_expect_tx(&bar_w, 65536u + kTailOff);
+      umma::bulk_g2s(sAh, fsg_img_bwd(ws, L - 1), 65536u, &bar_w);
+      umma::bulk_g2s(sAl, fsg_img_bwd(ws, L - 1) + kFsgImgPart, kTailOff, &bar_w);
+    }
+    // d agg of both branches, TMEM -> row-major tiles in the (free) operand buffers: thread = channel
+    float* sR0 = reinterpret_cast<float*>(sBh);
+    float* sR1 = reinterpret_cast<float*>(sBl);
+    {
+      const int ch = (warp & 3) * 32 + lane;
+      for (int g8 = (warp >> 2) * 8; g8 < npad; g8 += 16) {
+        float vm[8], vc[8], um[8], uc[8];
+        umma::ld8(umma::tmem_addr(tmem, (warp & 3) * 32, g8), vm);
+        umma::ld8(umma::tmem_addr(tmem, (warp & 3) * 32, 128 + g8), vc);
+        umma::ld8(umma::tmem_addr(tmem, (warp & 3) * 32, 64 + g8), um);
+        umma::ld8(umma::tmem_addr(tmem, (warp & 3) * 32, 192 + g8), uc);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int i = g8 + e;
+          if (i < Nc) {
+            sR0[i * FH + ch] = vm[e] + vc[e];
+            sR1[i * FH + ch] = um[e] + uc[e];
+          }
+        }
+      }
+    }
+    umma::fence_before_sync();
+    cp_async_wait_all();
+    __syncthreads();
+    umma::fence_after_sync();
+    FSG_T(5);                                                         // 5: d agg tiles
+
+    // ================= stage 2: masked convs, sparse part (warp per source row j) =================
+    //   dy_j = sum_{e: row_e = j} norm_e d agg[col_e];  d norm_e = <d agg[col_e], y_j>,  y_j = bn_k(att_k[j] x_j)
+    float4 dyk[kRowsPerWarp][2];                                      // dy of this warp's rows, kept across the all-reduce
+    {
+      double st[4][4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) st[v][i] = 0.0;
+#pragma unroll
+      for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+        const int j = warp + rr * 8;
+        dyk[rr][0] = dyk[rr][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j >= Nc) continue;
+        const float4 x = *reinterpret_cast<const float4*>(sX + j * FH + lane * 4);
+        const int q0 = sOutPtr[j], q1 = sOutPtr[j + 1];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const float* v = sVec + k * 6 * FH;
+          const float4 sc = *reinterpret_cast<const float4*>(v + lane * 4), sh = *reinterpret_cast<const float4*>(v + FH + lane * 4);
+          const float4 mu = *reinterpret_cast<const float4*>(v + 2 * FH + lane * 4), rs = *reinterpret_cast<const float4*>(v + 3 * FH + lane * 4);
+          const float aj = sRow[j * 8 + k], dj = sRow[j * 8 + 2 + k];
+          const float4 xm = make_float4(aj * x.x, aj * x.y, aj * x.z, aj * x.w);
+          const float4 y = make_float4(fmaf(xm.x, sc.x, sh.x), fmaf(xm.y, sc.y, sh.y), fmaf(xm.z, sc.z, sh.z), fmaf(xm.w, sc.w, sh.w));
+          const float4 xh = make_float4((xm.x - mu.x) * rs.x, (xm.y - mu.y) * rs.y, (xm.z - mu.z) * rs.z, (xm.w - mu.w) * rs.w);
+          const float* sR = k ? sR1 : sR0;
+          float4 dy = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int q = q0; q < q1; ++q) {
+            const int dd = sOutDst[q], pos = sOutPos[q];
+            const float2 wa = sW[pos];
+            const float w = (dj * (k ? wa.y : wa.x)) * sRow[dd * 8 + 2 + k];
+            const float4 g = *reinterpret_cast<const float4*>(sR + dd * FH + lane * 4);
+            dy.x = fmaf(w, g.x, dy.x); dy.y = fmaf(w, g.y, dy.y); dy.z = fmaf(w, g.z, dy.z); dy.w = fmaf(w, g.w, dy.w);
+            float dot = fmaf(g.x, y.x, fmaf(g.y, y.y, fmaf(g.z, y.z, g.w * y.w)));
+            dot = warp_sum(dot);
+            if (lane == 0) {
+              if (k) sDn[pos].y = dot;
+              else sDn[pos].x = dot;
+            }
+          }
+          dyk[rr][k] = dy;
+          st[2 * k][0] += (double)dy.x; st[2 * k][1] += (double)dy.y; st[2 * k][2] += (double)dy.z; st[2 * k][3] += (double)dy.w;
+          st[2 * k + 1][0] += (double)dy.x * (double)xh.x; st[2 * k + 1][1] += (double)dy.y * (double)xh.y;
+          st[2 * k + 1][2] += (double)dy.z * (double)xh.z; st[2 * k + 1][3] += (double)dy.w * (double)xh.w;
+        }
+      }
+      // block totals [bnc: sum dy | sum dy xhat | bno: sum dy | sum dy xhat]; the d agg tiles are dead: scratch
+      __syncthreads();
+      block_totals<4, 4>(st, reinterpret_cast<double*>(sBh), sPart, FH, 0, FH, 0);
+    }
+    FSG_T(6);                                                         // 6: masked gather
+    fsg_publish(ws, 12, G, sPart, 4 * FH);
+    FSG_T(7);                                                         // 7: publish
+
+    // ================= stage 3: weighted-norm backward (warp per node; overlaps the all-reduce) =================
+    for (int n = warp; n < Nc; n += 8) {
+      const int q0 = sOutPtr[n], q1 = sOutPtr[n + 1] - 1;              // q1 = the appended self loop
+      const int p0 = sInPtr[n], p1 = sInPtr[n + 1] - 1;                // p1 = the appended self loop
+      if (c.no_eatt) {
+        for (int q = q0 + lane; q <= q1; q += 32) sDt[sOutPos[q]] = make_float2(0.f, 0.f);
+        if (lane == 0) sRow[n * 8 + 4] = sRow[n * 8 + 5] = 0.f;
+        continue;
+      }
+      const float2 dn = make_float2(sRow[n * 8 + 2], sRow[n * 8 + 3]);
+      float dd0 = 0.f, dd1 = 0.f;                                     // d dis[n]
+      for (int q = q0 + lane; q < q1; q += 32) {
+        const int pos = sOutPos[q], d = sOutDst[q];
+        const float2 g = sDn[pos], w = sW[pos];
+        dd0 = fmaf(g.x * w.x, sRow[d * 8 + 2], dd0);
+        dd1 = fmaf(g.y * w.y, sRow[d * 8 + 3], dd1);
+      }
+      for (int p = p0 + lane; p < p1; p += 32) {
+        const int s = sInSrc[p];
+        const float2 g = sDn[p], w = sW[p];
+        dd0 = fmaf(g.x * w.x, sRow[s * 8 + 2], dd0);
+        dd1 = fmaf(g.y * w.y, sRow[s * 8 + 3], dd1);
+      }
+      if (lane == 0) {
+        const float2 g = sDn[p1];
+        dd0 = fmaf(2.f * dn.x, g.x, dd0);
+        dd1 = fmaf(2.f * dn.y, g.y, dd1);
+      }
+      dd0 = warp_sum(dd0);
+      dd1 = warp_sum(dd1);
+      const float ddeg0 = -0.5f * dn.x * dn.x * dn.x * dd0;           // d deg = -1/2 deg^-3/2 d dis
+      const float ddeg1 = -0.5f * dn.y * dn.y * dn.y * dd1;
+      float dp0 = 0.f, dp1 = 0.f;
+      for (int q = q0 + lane; q < q1; q += 32) {
+        const int pos = sOutPos[q], d = sOutDst[q];
+        const float2 g = sDn[pos], w = sW[pos];
+        const float dw0 = fmaf(g.x * dn.x, sRow[d * 8 + 2], ddeg0);
+        const float dw1 = fmaf(g.y * dn.y, sRow[d * 8 + 3], ddeg1);
+        const float dot = w.x * dw0 + w.y * dw1;
+        const float dt0 = w.x * (dw0 - dot), dt1 = w.y * (dw1 - dot);
+        sDt[pos] = make_float2(dt0, dt1);
+        dp0 += dt0;
+        dp1 += dt1;
+      }
+      dp0 = warp_sum(dp0);
+      dp1 = warp_sum(dp1);
+      if (lane == 0) {
+        sDt[sOutPos[q1]] = make_float2(0.f, 0.f);
+        sRow[n * 8 + 4] = dp0;
+        sRow[n * 8 + 5] = dp1;
+      }
+    }
+    __syncthreads();
+    FSG_T(8);                                                         // 8: norm backward
+
+    // ================= stage 4: attention backward -> gradient rows of the top backbone layer =================
+    fsg_wait_total(ws, 12, G, 4 * FH, sTot);
+    fsg_bn_bwd_finalize(c, L + 1, N, sTot, sVec + 4 * FH, sVec + 5 * FH, 0);
+    fsg_bn_bwd_finalize(c, L + 2, N, sTot + 2 * FH, sVec + 6 * FH + 4 * FH, sVec + 6 * FH + 5 * FH, FH);
+    __syncthreads();
+    FSG_T(9);                                                         // 9: all-reduce wait
+    {
+      float g_wn0[4], g_wn1[4], g_wp0[4], g_wp1[4], g_wq0[4], g_wq1[4], dbias[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) g_wn0[i] = g_wn1[i] = g_wp0[i] = g_wp1[i] = g_wq0[i] = g_wq1[i] = dbias[i] = 0.f;
+      float g_bn0 = 0.f, g_bn1 = 0.f, g_be0 = 0.f, g_be1 = 0.f;
+      float bsc[2][4], bmu[2][4], brs[2][4], bc1[2][4], bc2[2][4];
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float* v = sVec + k * 6 * FH + lane * 4 + i;
+          bsc[k][i] = v[0];
+          bmu[k][i] = v[2 * FH];
+          brs[k][i] = v[3 * FH];
+          bc1[k][i] = v[4 * FH];
+          bc2[k][i] = v[5 * FH];
+        }
+#pragma unroll
+      for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+        const int n = warp + rr * 8;
+        if (n >= Nc) continue;
+        float dq0 = 0.f, dq1 = 0.f;
+        for (int p = sInPtr[n] + lane; p < sInPtr[n + 1]; p += 32) {
+          const float2 d = sDt[p];
+          dq0 += d.x;
+          dq1 += d.y;
+        }
+        dq0 = warp_sum(dq0);
+        dq1 = warp_sum(dq1);
+        const float* r = sRow + n * 8;
+        const float a0 = r[0], a1 = r[1], dpx = r[4], dpy = r[5];
+        const float4 x4 = *reinterpret_cast<const float4*>(sX + n * FH + lane * 4);
+        const float x[4] = {x4.x, x4.y, x4.z, x4.w};
+        const float dc[4] = {dyk[rr][0].x, dyk[rr][0].y, dyk[rr][0].z, dyk[rr][0].w};
+        const float dO[4] = {dyk[rr][1].x, dyk[rr][1].y, dyk[rr][1].z, dyk[rr][1].w};
+        float gc[4], go[4];
+        float da0 = 0.f, da1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float xhc = (a0 * x[i] - bmu[0][i]) * brs[0][i];
+          const float xho = (a1 * x[i] - bmu[1][i]) * brs[1][i];
+          gc[i] = bsc[0][i] * (dc[i] - bc1[0][i] - xhc * bc2[0][i]);
+          go[i] = bsc[1][i] * (dO[i] - bc1[1][i] - xho * bc2[1][i]);
+          da0 = fmaf(gc[i], x[i], da0);
+          da1 = fmaf(go[i], x[i], da1);
+        }
+        da0 = warp_sum(da0);
+        da1 = warp_sum(da1);
+        float ds0 = 0.f, ds1 = 0.f;
+        if (!c.no_natt) {
+          const float dot = a0 * da0 + a1 * da1;
+          ds0 = a0 * (da0 - dot);
+          ds1 = a1 * (da1 - dot);
+        }
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v = a0 * gc[i] + a1 * go[i];
+          v = fmaf(ds0, wn0[i], v);
+          v = fmaf(ds1, wn1[i], v);
+          v = fmaf(dpx, wp0[i], v);
+          v = fmaf(dpy, wp1[i], v);
+          v = fmaf(dq0, wq0[i], v);
+          v = fmaf(dq1, wq1[i], v);
+          // the top layer has no BatchNorm above it: gradient w.r.t. its pre-activation = relu'(x_{L+1}) * dX
+          o[i] = x[i] > 0.f ? v : 0.f;
+          dbias[i] += o[i];
+          g_wn0[i] = fmaf(ds0, x[i], g_wn0[i]);
+          g_wn1[i] = fmaf(ds1, x[i], g_wn1[i]);
+          g_wp0[i] = fmaf(dpx, x[i], g_wp0[i]);
+          g_wp1[i] = fmaf(dpy, x[i], g_wp1[i]);
+          g_wq0[i] = fmaf(dq0, x[i], g_wq0[i]);
+          g_wq1[i] = fmaf(dq1, x[i], g_wq1[i]);
+        }
+        *reinterpret_cast<float4*>(sG + n * FH + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
+        g_bn0 += ds0;
+        g_bn1 += ds1;
+        g_be0 += dpx;
+        g_be1 += dpy;
+      }
+      // per-block partials of the attention parameters and of the top layer's bias
+      float* sRed = reinterpret_cast<float*>(sPart);                  // [8][128] floats (sPart | sTot are contiguous)
+      float* pa = part + fsg_part_att(L);
+      colsum8(g_wn0, sRed, pa);
+      colsum8(g_wn1, sRed, pa + FH);
+      colsum8(g_wp0, sRed, pa + 2 * FH);
+      colsum8(g_wq0, sRed, pa + 3 * FH);
+      colsum8(g_wp1, sRed, pa + 4 * FH);
+      colsum8(g_wq1, sRed, pa + 5 * FH);
+      colsum8(dbias, sRed, part + fsg_part_conv(L - 1) + FH * FH);
+      __syncthreads();
+      if (lane == 0) {
+        sRed[warp * 4 + 0] = g_bn0;
+        sRed[warp * 4 + 1] = g_bn1;
+        sRed[warp * 4 + 2] = g_be0;
+        sRed[warp * 4 + 3] = g_be1;
+      }
+      __syncthreads();
+      if (t < 4) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += sRed[w * 4 + t];
+        pa[6 * FH + t] = s;
+      }
+    }
+    __syncthreads();
+    FSG_T(10);                                                        // 10: attention backward
+
+    // ================= stage 5: backbone layers L-1 .. 0 =================
+    //   sG: g = gradient w.r.t. the layer's pre-activation;  u_j = sum_{e: row_e = j} norm_e g[col_e];
+    //   D = u W^T (gradient w.r.t. bn_l output, stays in TMEM);  dW += bn_l(x_in)^T u;  sums of bn_l backward.
+    // Vector sets alternate: set (l & 1) holds bn_l = bns_conv[l] (id 1 + l): sc | sh | mean | rstd | c1 | c2.
+    for (int l = L - 1; l >= 0; --l) {
+      float* vin = sVec + (l & 1) * 6 * FH;
+      rows_async(sX, c.Xl(l) + (size_t)n0 * FH, Nc);                   // x_in (x_up has been consumed)
+      if (t < FH) {
+        vin[t] = c.bnf(1 + l, BN_SCALE)[t];
+        vin[FH + t] = c.bnf(1 + l, BN_SHIFT)[t];
+        vin[2 * FH + t] = c.bnf(1 + l, BN_MEAN)[t];
+        vin[3 * FH + t] = c.bnf(1 + l, BN_RSTD)[t];
+      }
+      for (int j = warp; j < npad; j += 8) {
+        float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < Nc) {
+          for (int q = sOutPtr[j]; q < sOutPtr[j + 1]; ++q) {
+            const float w = sOutNrm[q];
+            const float4 g = *reinterpret_cast<const float4*>(sG + sOutDst[q] * FH + lane * 4);
+            u.x = fmaf(w, g.x, u.x); u.y = fmaf(w, g.y, u.y); u.z = fmaf(w, g.z, u.z); u.w = fmaf(w, g.w, u.w);
+          }
+        }
+        put_b(sBh, sBl, j, lane, u);
+      }
+      umma::fence_async_smem();
+      cp_async_wait_all();
+      __syncthreads();                                                // the gradient rows are dead: the image tail may land
+      FSG_T(11);                                                      // 11: transpose aggregate
+      if (t == 0) {
+        umma::mbar_expect_tx(&bar_w2, (uint32_t)kGBytes);
+        umma::bulk_g2s(sAl + kTailOff, fsg_img_bwd(ws, l) + kFsgImgPart + kTailOff / 4, (uint32_t)kGBytes, &bar_w2);
+        umma::mbar_wait(&bar_w, par_w);
+        umma::fence_after_sync();
+        const uint32_t idesc = umma::instr_desc(umma::kFmtTF32, 128, npad);
+        for (int s = 0; s < FH / 8; ++s) {
+          if (s == kTailStep) umma::mbar_wait(&bar_w2, par_w2);
+          const uint32_t aa = (uint32_t)s * 2u * kALbo, ba = (uint32_t)s * 2u * kBLbo;
+          const uint64_t ah = umma::smem_desc(umma::smem_addr(sAh) + aa, kALbo, kASbo);
+          const uint64_t al = umma::smem_desc(umma::smem_addr(sAl) + aa, kALbo, kASbo);
+          const uint64_t bh = umma::smem_desc(umma::smem_addr(sBh) + ba, kBLbo, kBSbo);
+          const uint64_t bl = umma::smem_desc(umma::smem_addr(sBl) + ba, kBLbo, kBSbo);
+          umma::mma_tf32(tmem + 128u, al, bh, idesc, s > 0);
+          umma::mma_tf32(tmem + 128u, ah, bl, idesc, 1u);
+          umma::mma_tf32(tmem, ah, bh, idesc, s > 0);
+        }
+        umma::commit(&bar_mma);
+      }
+      par_w ^= 1u;
+      par_w2 ^= 1u;
+      umma::mbar_wait(&bar_mma, par_m);
+      par_m ^= 1u;
+      umma::fence_after_sync();
+      FSG_T(12);                                                      // 12: MMA
+      if (t == 0 && l > 0) {                                          // next image (all but the tail) while the rest runs
+        umma::mbar_expect_tx(&bar_w, 65536u + kTailOff);
+        umma::bulk_g2s(sAh, fsg_img_bwd(ws, l - 1), 65536u, &bar_w);
+        umma::bulk_g2s(sAl, fsg_img_bwd(ws, l - 1) + kFsgImgPart, kTailOff, &bar_w);
+      }
+      // sums of bn_l backward: thread = channel, the two warp sets split the row groups
+      {
+        const int ch = (warp & 3) * 32 + lane;
+        const float mu = vin[2 * FH + ch], rs = vin[3 * FH + ch];
+        double s = 0.0, q = 0.0;
+        for (int g8 = (warp >> 2) * 8; g8 < npad; g8 += 16) {
+          float vm[8], vc[8];
+          umma::ld8(umma::tmem_addr(tmem, (warp & 3) * 32, g8), vm);
+          umma::ld8(umma::tmem_addr(tmem, (warp & 3) * 32, 128 + g8), vc);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int i = g8 + e;
+            if (i < Nc) {
+              const float d = vm[e] + vc[e];
+              const float xh = (sX[i * FH + ch] - mu) * rs;
+              s += (double)d;
+              q += (double)d * (double)xh;
+            }
+          }
+        }
+        if (warp >= 4) {
+          sTot[ch] = s;
+          sTot[FH + ch] = q;
+        }
+        __syncthreads();
+        if (warp < 4) {
+          sPart[ch] = s + sTot[ch];
+          sPart[FH + ch] = q + sTot[FH + ch];
+        }
+        __syncthreads();
+      }
+      FSG_T(13);                                                      // 13: statistics epilogue
+      fsg_publish(ws, 13 + (L - 1 - l), G, sPart, 2 * FH);
+      FSG_T(7);
+      {
+        DwAcc dw;
+        dw.zero();
+        dw.accumulate<true>(sX, vin, vin + FH, sBh, sBl, Nc);
+        dw.store(part + fsg_part_conv(l));
+      }
+      FSG_T(3);
+      fsg_wait_total(ws, 13 + (L - 1 - l), G, 2 * FH, sTot);
+      fsg_bn_bwd_finalize(c, 1 + l, N, sTot, vin + 4 * FH, vin + 5 * FH, 0);
+      __syncthreads();
+      FSG_T(9);
+      // gradient w.r.t. the pre-activation of the layer below (the input transform for l == 0):
+      //   g = relu'(x_in) * bn_l'(D)  -> sG (thread = channel), and its column sums = that layer's bias gradient
+      {
+        const int ch = (warp & 3) * 32 + lane;
+        const float sc = vin[ch], mu = vin[2 * FH + ch], rs = vin[3 * FH + ch], c1 = vin[4 * FH + ch], c2 = vin[5 * FH + ch];
+        float db = 0.f;
+        for (int g8 = (warp >> 2) * 8; g8 < npad; g8 += 16) {
+          float vm[8], vc[8];
+          umma::ld8(umma::tmem_addr(tmem, (warp & 3) * 32, g8), vm);
+          umma::ld8(umma::tmem_addr(tmem, (warp & 3) * 32, 128 + g8), vc);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int i = g8 + e;
+            if (i < Nc) {
+              const float x = sX[i * FH + ch];
+              const float xh = (x - mu) * rs;
+              const float g = x > 0.f ? sc * ((vm[e] + vc[e]) - c1 - xh * c2) : 0.f;
+              sG[i * FH + ch] = g;
+              db += g;
+            }
+          }
+        }
+        float* sRed = reinterpret_cast<float*>(sPart);
+        if (warp >= 4) sRed[ch] = db;
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+        if (warp < 4) {
+          const float tot = db + sRed[ch];
+          if (l > 0) part[fsg_part_conv(l - 1) + FH * FH + ch] = tot;
+          else part[fsg_part_feat(L) + (size_t)F * FH + ch] = tot;     // column sums of g_1 (k_feat_bwd's cs)
+        }
+      }
+      FSG_T(14);                                                      // 14: BatchNorm backward into the rows below
+    }
+
+    // ================= stage 6: input transform backward: M = xhat_0^T g_1  [F, H] =================
+    {
+      __syncthreads();
+      float* sF = sX;                                                  // [rows][F] xhat_0
+      const float* mean0 = c.bnf(0, BN_MEAN);
+      const float* rstd0 = c.bnf(0, BN_RSTD);
+      for (int i = t; i < Nc * F; i += FT) {
+        const int r = i / F, f = i - r * F;
+        sF[i] = (c.feat[(size_t)(n0 + r) * F + f] - mean0[f]) * rstd0[f];
+      }
+      __syncthreads();
+      const int m = t & 127;
+      for (int f = t >> 7; f < F; f += 2) {
+        float acc = 0.f;
+        for (int j = 0; j < Nc; ++j) acc = fmaf(sF[j * F + f], sG[j * FH + m], acc);
+        part[fsg_part_feat(L) + (size_t)f * FH + m] = acc;
+      }
+    }
+    FSG_T(15);                                                        // 15: input transform backward
+  }
+  FSG_TDUMP(c, 64);
+
+  // ---- teardown: TMEM, and the last CTA re-arms the all-reduce counters for the next launch ----
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
+  if (active && t == 0) {
+    __threadfence();
+    if (atomicAdd(&ws.cnt[kFsgPhases * kFsgCntStride], 1u) == (unsigned int)G - 1u) {
+      for (int i = 0; i <= kFsgPhases * kFsgCntStride; ++i) ws.cnt[i] = 0u;
+      __threadfence();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Block-order sum of the per-block partial gradients into the flat gradient buffer.
+//   blocks [0, n_generic): 256 consecutive elements of the partial vector x 4 block slices (1024 threads);
+//   blocks [n_generic, n_generic + F): the input transform, one feature row each:
+//     d W_feat = gamma_0 * M + beta_0 (x) cs,  d gamma_0[f] = sum_j W[f][j] M[f][j],  d beta_0[f] = sum_j W[f][j] cs[j]
+// ---------------------------------------------------------------------------------------------
+constexpr int kRedMax = 2 * (CAL_MAX_LAYERS + 2) + 4;
+struct FsgRedTable {
+  int count;
+  int V;                      // floats per block slot
+  int generic_end;            // elements [0, generic_end) of a slot belong to the generic entries
+  long long dst[kRedMax];
+  int src[kRedMax], n[kRedMax];
+};
+
+__global__ void __launch_bounds__(1024) k_fsg_grad_reduce(const Ctx c, const FsgRedTable tb, const int n_generic) {
+  pdl_sync();
+  __shared__ float s_a[4][256], s_b[4][256];
+  const FsgWs ws = fsg_ws(c);
+  const int np = ws.plan[1] != 0 ? ws.plan[0] : 0;
+  const int tx = threadIdx.x & 255, ty = threadIdx.x >> 8;
+  if ((int)blockIdx.x < n_generic) {
+    const int i = blockIdx.x * 256 + tx;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (i < tb.generic_end) {
+      const float* p = ws.part + i;
+      int g = ty;
+#pragma unroll 2
+      for (; g + 12 < np; g += 16) {
+        s0 += __ldcg(p + (size_t)g * tb.V);
+        s1 += __ldcg(p + (size_t)(g + 4) * tb.V);
+        s2 += __ldcg(p + (size_t)(g + 8) * tb.V);
+        s3 += __ldcg(p + (size_t)(g + 12) * tb.V);
+      }
+      for (; g < np; g += 4) s0 += __ldcg(p + (size_t)g * tb.V);
+    }
+    s_a[ty][tx] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (ty == 0 && i < tb.generic_end) {
+      const float sum = (s_a[0][tx] + s_a[1][tx]) + (s_a[2][tx] + s_a[3][tx]);
+      for (int e = 0; e < tb.count; ++e)
+        if (i >= tb.src[e] && i < tb.src[e] + tb.n[e]) {
+          c.grads[tb.dst[e] + (i - tb.src[e])] = sum;
+          break;
+        }
+    }
+    return;
+  }
+  const int F = c.F, L = c.L;
+  const int f = (int)blockIdx.x - n_generic;
+  if (f >= F) return;
+  const int j = tx & 127, sl = ty * 2 + (tx >> 7);                     // column, block slice (8 slices)
+  const float* pm = ws.part + fsg_part_feat(L) + (size_t)f * FH + j;
+  const float* pc = ws.part + fsg_part_feat(L) + (size_t)F * FH + j;
+  float m0 = 0.f, m1 = 0.f, c0 = 0.f, c1 = 0.f;
+  int g = sl;
+  for (; g + 8 < np; g += 16) {
+    m0 += __ldcg(pm + (size_t)g * tb.V);
+    m1 += __ldcg(pm + (size_t)(g + 8) * tb.V);
+    c0 += __ldcg(pc + (size_t)g * tb.V);
+    c1 += __ldcg(pc + (size_t)(g + 8) * tb.V);
+  }
+  for (; g < np; g += 8) {
+    m0 += __ldcg(pm + (size_t)g * tb.V);
+    c0 += __ldcg(pc + (size_t)g * tb.V);
+  }
+  s_a[ty][tx] = m0 + m1;
+  s_b[ty][tx] = c0 + c1;
+  __syncthreads();
+  __shared__ float s_g[4], s_d[4];
+  float dg = 0.f, db = 0.f;
+  if (threadIdx.x < FH) {
+    float m = 0.f, cs = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      m += s_a[q][j] + s_a[q][FH + j];
+      cs += s_b[q][j] + s_b[q][FH + j];
+    }
+    const float g0 = c.params[c.po.bn_feat_w + f], b0 = c.params[c.po.bn_feat_b + f];
+    c.grads[c.po.conv_feat_w + (size_t)f * FH + j] = g0 * m + b0 * cs;
+    const float w = c.params[c.po.conv_feat_w + (size_t)f * FH + j];
+    dg = w * m;
+    db = w * cs;
+    if (f == 0 && c.po.conv_feat_b >= 0) c.grads[c.po.conv_feat_b + j] = 0.f;   // gfn=True: the bias never gets a gradient
+    dg = warp_sum(dg);
+    db = warp_sum(db);
+    if ((threadIdx.x & 31) == 0) {
+      s_g[threadIdx.x >> 5] = dg;
+      s_d[threadIdx.x >> 5] = db;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    c.grads[c.po.bn_feat_w + f] = (s_g[0] + s_g[1]) + (s_g[2] + s_g[3]);
+    c.grads[c.po.bn_feat_b + f] = (s_d[0] + s_d[1]) + (s_d[2] + s_d[3]);
+  }
+}
+
+}  // namespace
+
+int launch_fsg_backward(const Ctx& c, cudaStream_t s) {
+  const size_t smem = fsg_bsmem().total;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_fsg_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  launch_k(k_fsg_backward, dim3(imax(1, imin(c.Bm, kSMs))), dim3(FT), smem, s, c);
+  note_launches(1);
+  CAL_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_fsg_grad_reduce(const Ctx& c, cudaStream_t s) {
+  FsgRedTable tb;
+  const int L = c.L;
+  tb.count = 0;
+  tb.V = (int)fsg_part_floats(L, c.F);
+  tb.generic_end = (int)fsg_part_feat(L);
+  auto add = [&](long long dst, size_t src, int n) {
+    if (dst < 0 || tb.count >= kRedMax) return;
+    tb.dst[tb.count] = dst;
+    tb.src[tb.count] = (int)src;
+    tb.n[tb.count] = n;
+    ++tb.count;
+  };
+  for (int l = 0; l < L; ++l) {
+    add(c.po.convs_w[l], fsg_part_conv(l), FH * FH);
+    add(c.po.convs_b[l], fsg_part_conv(l) + FH * FH, FH);
+  }
+  add(c.po.context_w, fsg_part_conv(L), FH * FH);
+  add(c.po.context_b, fsg_part_conv(L) + FH * FH, FH);
+  add(c.po.objects_w, fsg_part_conv(L + 1), FH * FH);
+  add(c.po.objects_b, fsg_part_conv(L + 1) + FH * FH, FH);
+  const size_t pa = fsg_part_att(L);
+  add(c.po.node_att_w, pa, 2 * FH);
+  add(c.po.edge_att_w, pa + 2 * FH, 4 * FH);
+  add(c.po.node_att_b, pa + 6 * FH, 2);
+  add(c.po.edge_att_b, pa + 6 * FH + 2, 2);
+  const int n_generic = ceil_div(tb.generic_end, 256);
+  launch_k(k_fsg_grad_reduce, dim3(n_generic + c.F), dim3(1024), 0, s, c, tb, n_generic);
+  note_launches(1);
+  CAL_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace cal

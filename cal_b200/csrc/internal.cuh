@@ -89,6 +89,7 @@ struct Ctx {
   const float* grad_logp;   // external dL/dlogp (nullptr = fused loss)
   unsigned char* fsg;       // CAL_WS_FSG region (fsg.cuh)
   int fsg_on;               // the fused small-graph forward replaces feat .. masked_convs (and the pooling)
+  int fsg_bwd_on;           // ... and the fused small-graph backward replaces masked_gemm_bwd .. feat_bwd
 
   __host__ __device__ float* bnf(int id, int field) const { return bn + ((size_t)id * BN_FIELDS + field) * kmax; }
   __host__ __device__ float* Xl(int l) const { return X + (size_t)l * Nm * H; }     // l = 0..L  (x_{l+1})
@@ -128,7 +129,9 @@ int launch_readout_tc_forward(const Ctx& c, cudaStream_t s);
 int launch_readout_tc_backward(const Ctx& c, cudaStream_t s);
 int launch_fsg_prep(const Ctx& c, cudaStream_t s);                         // fused small-graph path (fsg.cu)
 int launch_fsg_forward(const Ctx& c, cudaStream_t s);
-size_t fsg_region_bytes(int Bm, int L);
+size_t fsg_region_bytes(int Bm, int L, int F);
+int launch_fsg_backward(const Ctx& c, cudaStream_t s);                      // masked convs .. input transform, one kernel
+int launch_fsg_grad_reduce(const Ctx& c, cudaStream_t s);
 bool readout_tc2_supported(const Ctx& c);                                  // resident-tile variant (head_tc2.cu)
 int launch_readout_tc2_forward(const Ctx& c, cudaStream_t s);
 int launch_readout_tc2_backward(const Ctx& c, cudaStream_t s);

@@ -153,7 +153,7 @@ class Engine:
         self._ring_i = 0
         self.opt_state = None
         self._owner = None          # weakref to the Trainer whose captured CUDA graphs point into self.ws
-        self.fsg_mode = "auto"      # "off": never take the fused small-graph forward (A/B tests)
+        self.fsg_mode = "auto"      # "off": never take the fused small-graph kernels; "fwd": fused forward, tiled backward (A/B tests)
 
     # ---- flat parameter / buffer storage ----
     def _flatten(self):
@@ -258,7 +258,7 @@ class Engine:
         self._owner = None
         caps = _lib.Caps()
         caps.max_nodes, caps.max_edges, caps.max_graphs = int(max_nodes), int(max_edges), int(max_graphs)
-        caps.small_graphs = int(bool(small_graphs))
+        caps.small_graphs = self._fsg_level(small_graphs)
         nbytes = self.lib.cal_workspace_bytes(C.byref(self.desc), C.byref(caps))
         if nbytes == 0:
             raise _lib.CalError("cal_b200: unsupported model configuration or capacities (hidden must be 32/64/128, "
@@ -342,7 +342,13 @@ class Engine:
             if ei.numel() > 0:
                 ents += torch.bincount(bvec[ei[0]], minlength=B)
             small = bool((nodes.max() <= self.FSG_ROWS) & (ents.max() <= self.FSG_ENTRIES))
-        self.caps.small_graphs = int(small)
+        self.caps.small_graphs = self._fsg_level(small)
+
+    def _fsg_level(self, small):
+        """cal_caps.small_graphs: 0 = tiled kernels, 1 = fused small-graph forward and backward, 2 = fused forward only."""
+        if not small or self.fsg_mode == "off":
+            return 0
+        return 2 if self.fsg_mode == "fwd" else 1
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream

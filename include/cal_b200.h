@@ -83,7 +83,9 @@ typedef struct {
                                   self-loop surgery (edge_index columns without self loops + one per node).  CausalGCN with
                                   hidden 128, <= 128 features and <= 148 graphs per batch then runs the fused small-graph
                                   forward (one persistent kernel, graph blocks resident in shared memory, tensor-core node
-                                  transforms; csrc/fsg.cu).  A batch that breaks the promise sets CAL_ST_CAPACITY. */
+                                  transforms; csrc/fsg.cu) and the fused small-graph backward (csrc/fsg_bwd.cu).  2: the fused
+                                  forward only (the tiled backward kernels run on what it saved; A/B tests).  A batch that
+                                  breaks the promise sets CAL_ST_CAPACITY. */
 } cal_caps;
 
 /* Offsets (in floats) of every parameter inside the flat parameter buffer;

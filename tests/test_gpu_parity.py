@@ -562,21 +562,22 @@ def test_full_size_cfg5_shapes():
     _step_and_compare(clone_to_cuda(ora, M), ora, b, perm, M, O, illcond=True)      # BatchNorm sums over 103 788 rows
 
 
-def test_fused_small_graph_forward_matches_tiled_forward():
-    """csrc/fsg.cu (one persistent kernel, graph blocks resident in shared memory, tensor-core node
-    transforms) against the tiled kernels it replaces: every workspace region the backward pass reads,
-    the BatchNorm records and running statistics, and the outputs -- then the oracle."""
+def test_fused_small_graph_kernels_match_tiled_kernels():
+    """csrc/fsg.cu + csrc/fsg_bwd.cu (one persistent kernel per pass, graph blocks resident in shared memory,
+    tensor-core node transforms) against the tiled kernels they replace: every workspace region the backward
+    pass reads, the BatchNorm records and running statistics, the outputs and every parameter gradient (tiled
+    backward on the fused forward, then the fused backward) -- then the oracle."""
     M, O = _mods()
     ora, b, perm = random_case(seed=501, hidden=128, layers=3, batch_size=128)
     bd = b.to(DEV)
     N, E, B = b.batch.numel(), b.edge_index.size(1), 128
     res = {}
-    for mode in ("off", "auto"):
+    for mode in ("off", "fwd", "auto"):
         net = clone_to_cuda(ora, M)
         eng = net.engine
         eng.fsg_mode = mode
         st = eng.stage(bd, perm=perm.tolist())
-        assert bool(eng.caps.small_graphs) == (mode == "auto")
+        assert int(eng.caps.small_graphs) == {"off": 0, "fwd": 2, "auto": 1}[mode]
         eng.prep(st)
         out = eng.forward(st, train=True, with_loss=True).clone()
         torch.cuda.synchronize()
@@ -594,19 +595,46 @@ def test_fused_small_graph_forward_matches_tiled_forward():
         rec = eng.region("BN").view(-1, 6, kmax)
         r["rec"] = rec[:L + 3, :4, :H].cpu().clone()
         r["rec0"] = rec[0, :4, :eng.F].cpu().clone()
-        res[mode] = r
-        if mode == "auto":
-            eng.backward(st, None)                       # the tiled backward runs on what the fused forward saved
-            torch.cuda.synchronize()
+        eng.backward(st, None)
+        torch.cuda.synchronize()
+        assert eng.status() == 0
+        gpu = {n: eng.flat_grad[eng.param_offs[n]:eng.param_offs[n] + p.numel()].view(p.shape).clone() for n, p in net.named_parameters()}
+        r["grads"] = gpu
+        if mode != "off":
             masks = _gpu_relu_masks(eng, N, B)
             _, _, g32, _, _ = _oracle_step(ora, b, perm, torch.float32, masks)
             _, _, g64, _, _ = _oracle_step(ora, b, perm, torch.float64, masks)
-            gpu = {n: eng.flat_grad[eng.param_offs[n]:eng.param_offs[n] + p.numel()].view(p.shape) for n, p in net.named_parameters()}
             _check_grads(gpu, g32, g64)
-    a, f = res["off"], res["auto"]
-    assert torch.equal(a["nbt"], f["nbt"])
-    for k in ("X", "NODE_ATT", "PQ", "EDGE_ATT", "DISW", "EDGE_WN", "EDGE_NA", "AGG", "Z", "POOLED", "out", "loss", "bn", "rec", "rec0"):
-        assert rel_err(f[k], a[k]) < TOL, "%s: fused vs tiled rel err %.3e" % (k, rel_err(f[k], a[k]))
+        res[mode] = r
+    a = res["off"]
+    for mode in ("fwd", "auto"):
+        f = res[mode]
+        assert torch.equal(a["nbt"], f["nbt"])
+        for k in ("X", "NODE_ATT", "PQ", "EDGE_ATT", "DISW", "EDGE_WN", "EDGE_NA", "AGG", "Z", "POOLED", "out", "loss", "bn", "rec", "rec0"):
+            assert rel_err(f[k], a[k]) < TOL, "%s: fused (%s) vs tiled rel err %.3e" % (k, mode, rel_err(f[k], a[k]))
     o32, _, _, _, _ = _oracle_step(ora, b, perm)
     o64, _, _, _, _ = _oracle_step(ora, b, perm, torch.float64)
-    _check_outputs([f["out"][h] for h in range(3)], o32, o64)
+    _check_outputs([res["auto"]["out"][h] for h in range(3)], o32, o64)
+
+
+def test_fused_small_graph_backward_is_deterministic_and_handles_ablations():
+    """Bit-identical gradients across two runs of the fused backward (in-kernel all-reduce in fixed order, block-order
+    partial sums), and the ablation / concat variants against the oracle."""
+    M, O = _mods()
+    for kw in ({}, {"cat": "cat"}, {"without_node_attention": True}, {"without_edge_attention": True}, {"layers": 1}, {"layers": 4}):
+        ora, b, perm = random_case(seed=601, hidden=128, batch_size=64, **({"layers": 3} | kw))
+        net = clone_to_cuda(ora, M)
+        eng = net.engine
+        bd = b.to(DEV)
+        runs = []
+        for _ in range(2):
+            st = eng.stage(bd, perm=perm.tolist())
+            assert int(eng.caps.small_graphs) == 1
+            eng.prep(st)
+            eng.forward(st, train=True, with_loss=True)
+            eng.backward(st, None)
+            torch.cuda.synchronize()
+            assert eng.status() == 0
+            runs.append(eng.flat_grad.clone())
+        assert torch.equal(runs[0], runs[1]), "fused backward is not bit-identical across runs (%s)" % kw
+        _step_and_compare(clone_to_cuda(ora, M), ora, b, perm, M, O)

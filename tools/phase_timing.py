@@ -28,6 +28,10 @@ names_fsg = ["dep wait", "plan+CSR+bn_feat", "feat product", "epilogues", "publi
              "affine+split", "weight wait", "MMA", "node att+stats", "edge att", "masked epilogue+pool"]
 if tr.fused_small_graphs:
     print("k_fsg_forward (CTA 0) cycles:", list(zip(names_fsg, st[48:61])), "sum", sum(st[48:61]))
+names_fb = ["dep wait", "structure+records", "dz operand+issue", "dW (FFMA)", "MMA tail", "d agg tiles", "masked gather", "publish",
+            "norm bwd", "all-reduce wait", "att bwd", "transpose aggregate", "MMA", "stats epilogue", "bn bwd rows", "feat bwd"]
+if tr.fused_small_graphs:
+    print("k_fsg_backward (CTA 0) cycles:", list(zip(names_fb, st[64:80])), "sum", sum(st[64:80]))
 names_p = ["wait+zero", "edges+counts", "node pass", "scan", "fill", "sort", "write-out"]
 print("k_prep_small structure CTA (slice 0) cycles:", list(zip(names_p, st[96:103])), "sum", sum(st[96:103]))
 print("k_prep_small statistics CTA 0 [column sums, grid sum]:", st[112:114], " finishing CTA:", st[116:118])
