@@ -25,7 +25,7 @@ static_assert(kTailOff % (2u * kALbo) == 0, "the tail starts on a K-step boundar
 constexpr int kRowsPerWarp = kFsgRows / 8;            // 5
 
 struct FsgBSmem {
-  size_t a_hi, a_lo, g, b_hi, b_lo, x, in_ptr, out_ptr, in_src, out_dst, out_pos, out_nrm, w, dnrm, dt, rowf, vec, part, tot, pool, total;
+  size_t a_hi, a_lo, g, b_hi, b_lo, x, in_ptr, out_ptr, in_src, out_dst, out_pos, out_row, out_nrm, w, dnrm, dt, rowf, vec, part, tot, pool, total;
 };
 __host__ __device__ inline FsgBSmem fsg_bsmem() {
   FsgBSmem s;
@@ -41,6 +41,7 @@ __host__ __device__ inline FsgBSmem fsg_bsmem() {
   s.in_src = o;  o += kFsgEntries * 4;
   s.out_dst = o; o += kFsgEntries * 4;
   s.out_pos = o; o += kFsgEntries * 4;
+  s.out_row = o; o += kFsgEntries * 4;                  // source row of every out-CSR entry
   s.out_nrm = o; o += kFsgEntries * 4;
   s.w = o;       o += kFsgEntries * 8;                  // edge attention by in-CSR position (both branches)
   s.dnrm = o;    o += kFsgEntries * 8;                  // d norm by in-CSR position
@@ -74,77 +75,77 @@ __device__ __forceinline__ void fsg_bn_bwd_finalize(const Ctx& c, int id, int co
   }
 }
 
-// ---- the weight-gradient outer product  acc[ia][ib] += sum_r P[r][ia] * Q[r][ib]  over the block's rows ----
-// 256 threads cover the [128 x 128] result: thread (ty = tid / 16, tx = tid % 16) owns rows {ty*4 + i, 64 + ty*4 + i}
-// and columns {tx*4 + i, 64 + tx*4 + i} (i < 4), 32 FFMA2 per row of the block.  P comes from a row-major tile
-// (optionally through the BatchNorm affine: y = sc * x + sh), Q from the MMA node operand (hi + lo = the value).
-struct DwAcc {
-  f32x2 acc[8][4];
-  __device__ __forceinline__ void zero() {
+// ---- the weight gradient  dW[ka][kb] = sum_r P[r][ka] * Q[r][kb]  over the block's rows, on the tensor cores ----
+// Both operands are needed "rows = K": transposed, K-major, in the layout of the weight images (chunk c of channel m at
+// c * 2048 + m * 16, a chunk = 4 consecutive block rows).  They are built in the (idle) weight-image buffer:
+// P^T hi | P^T lo | Q^T hi | Q^T lo, kOpT bytes each.  P comes from a row-major tile (optionally through the BatchNorm
+// affine y = sc * x + sh), Q from the node operand of the gradient product (its hi / lo parts are copied as they are).
+// Threads 0..127 build P^T (thread = channel), threads 128..255 build Q^T.
+constexpr uint32_t kOpT = (uint32_t)(kFsgRows / 4) * kALbo;            // 20480
+template <bool AFFINE>
+__device__ __forceinline__ void build_dw_operands(unsigned char* wbuf, const float* sP, int ldp, const float* s_sc, const float* s_sh,
+                                                  const unsigned char* bh, const unsigned char* bl, int rows, int npad) {
+  const int t = threadIdx.x;
+  if (t < FH) {
+    const int ch = t;
+    const float sc = AFFINE ? s_sc[ch] : 1.f, sh = AFFINE ? s_sh[ch] : 0.f;
+    for (int kc = 0; kc < npad / 4; ++kc) {
+      float v[4], h[4], l[4];
 #pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = pack2(0.f, 0.f);
-  }
-  __device__ __forceinline__ static void load_p(const float* sP, int r, int ty, float (&p)[8]) {
-    const float4 a = *reinterpret_cast<const float4*>(sP + r * FH + ty * 4);
-    const float4 b = *reinterpret_cast<const float4*>(sP + r * FH + 64 + ty * 4);
-    p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;
-  }
-  __device__ __forceinline__ static void load_q(const unsigned char* bh, const unsigned char* bl, int r, int tx, float (&q)[8]) {
-    const uint32_t o0 = b_off(r, tx), o1 = b_off(r, 16 + tx);
-    const float4 h0 = *reinterpret_cast<const float4*>(bh + o0), l0 = *reinterpret_cast<const float4*>(bl + o0);
-    const float4 h1 = *reinterpret_cast<const float4*>(bh + o1), l1 = *reinterpret_cast<const float4*>(bl + o1);
-    q[0] = h0.x + l0.x; q[1] = h0.y + l0.y; q[2] = h0.z + l0.z; q[3] = h0.w + l0.w;
-    q[4] = h1.x + l1.x; q[5] = h1.y + l1.y; q[6] = h1.z + l1.z; q[7] = h1.w + l1.w;
-  }
-  template <bool AFFINE>
-  __device__ __forceinline__ void accumulate(const float* sP, const float* s_sc, const float* s_sh, const unsigned char* bh,
-                                             const unsigned char* bl, int rows) {
-    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-    float sc[8], sh[8];
-    if (AFFINE) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int k = (i >> 2) * 64 + ty * 4 + (i & 3);
-        sc[i] = s_sc[k];
-        sh[i] = s_sh[k];
+      for (int e = 0; e < 4; ++e) {
+        const int r = kc * 4 + e;
+        v[e] = r < rows ? (AFFINE ? fmaf(sP[r * ldp + ch], sc, sh) : sP[r * ldp + ch]) : 0.f;
+        umma::split_tf32(v[e], h[e], l[e]);
       }
+      const uint32_t off = (uint32_t)kc * kALbo + (uint32_t)ch * 16u;
+      *reinterpret_cast<float4*>(wbuf + off) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(wbuf + kOpT + off) = make_float4(l[0], l[1], l[2], l[3]);
     }
-    if (rows <= 0) return;
-    float p[8], q[8], pn[8], qn[8];
-    load_p(sP, 0, ty, p);
-    load_q(bh, bl, 0, tx, q);
-    for (int r = 0; r < rows; ++r) {
-      const int rn = r + 1 < rows ? r + 1 : r;
-      load_p(sP, rn, ty, pn);
-      load_q(bh, bl, rn, tx, qn);
+  } else {
+    const int ch = t - FH;
+    for (int kc = 0; kc < npad / 4; ++kc) {
+      float h[4], l[4];
 #pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        const float pv = AFFINE ? fmaf(p[a], sc[a], sh[a]) : p[a];
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = ffma2_bcast(pv, pack2(q[2 * b], q[2 * b + 1]), acc[a][b]);
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t o = b_off(kc * 4 + e, ch >> 2) + (uint32_t)(ch & 3) * 4u;     // rows >= `rows` hold zeros
+        h[e] = *reinterpret_cast<const float*>(bh + o);
+        l[e] = *reinterpret_cast<const float*>(bl + o);
       }
-#pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        p[a] = pn[a];
-        q[a] = qn[a];
-      }
+      const uint32_t off = (uint32_t)kc * kALbo + (uint32_t)ch * 16u;
+      *reinterpret_cast<float4*>(wbuf + 2 * kOpT + off) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(wbuf + 3 * kOpT + off) = make_float4(l[0], l[1], l[2], l[3]);
     }
   }
-  __device__ __forceinline__ void store(float* dst) const {        // dst [128][128]
-    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-#pragma unroll
-    for (int a = 0; a < 8; ++a) {
-      const int row = (a >> 2) * 64 + ty * 4 + (a & 3);
-      float v[8];
-#pragma unroll
-      for (int b = 0; b < 4; ++b) unpack2(acc[a][b], v[2 * b], v[2 * b + 1]);
-      *reinterpret_cast<float4*>(dst + (size_t)row * FH + tx * 4) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(dst + (size_t)row * FH + 64 + tx * 4) = make_float4(v[4], v[5], v[6], v[7]);
-    }
+}
+// one thread: dW (128 TMEM columns at d) = P^T Q over npad rows (3xTF32, one accumulator: K <= 40)
+__device__ __forceinline__ void issue_dw(const unsigned char* wbuf, uint32_t d, int npad) {
+  const uint32_t idesc = umma::instr_desc(umma::kFmtTF32, 128, 128);
+  const uint32_t base = umma::smem_addr(wbuf);
+  for (int s = 0; s < npad / 8; ++s) {
+    const uint32_t o = (uint32_t)s * 2u * kALbo;
+    const uint64_t ph = umma::smem_desc(base + o, kALbo, kASbo);
+    const uint64_t pl = umma::smem_desc(base + kOpT + o, kALbo, kASbo);
+    const uint64_t qh = umma::smem_desc(base + 2 * kOpT + o, kALbo, kASbo);
+    const uint64_t ql = umma::smem_desc(base + 3 * kOpT + o, kALbo, kASbo);
+    umma::mma_tf32(d, pl, qh, idesc, s > 0);
+    umma::mma_tf32(d, ph, ql, idesc, 1u);
+    umma::mma_tf32(d, ph, qh, idesc, 1u);
   }
-};
+}
+// all 8 warps: dW from TMEM -> dst [128][128] (thread = row of dW, the two warp sets split the columns)
+__device__ __forceinline__ void drain_dw(uint32_t tmem_dw, float* dst) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = (warp & 3) * 32 + lane;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int col = (warp >> 2) * 64 + h * 32;
+    float v[32];
+    umma::ld32(umma::tmem_addr(tmem_dw, (warp & 3) * 32, col), v);
+    float4* o = reinterpret_cast<float4*>(dst + (size_t)row * FH + col);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
+}
 
 // sum over the 8 warps of a lane-owned [4-channel] accumulator, fixed order: dst[k] (k < 128) by threads 0..127
 __device__ __forceinline__ void colsum8(const float (&acc)[4], float* sRed /* [8][128] */, float* dst) {
@@ -168,9 +169,13 @@ __device__ __forceinline__ void rows_async(float* sdst, const float* gsrc, int r
 // ---------------------------------------------------------------------------------------------
 // The backward kernel.  grid = min(max_graphs, 148), 256 threads, 1 CTA per SM.
 // ---------------------------------------------------------------------------------------------
+constexpr int kTmemColsB = 512;                       // D main 0 / 64, D correction 128 / 192, dW 256 .. 383
+constexpr uint32_t kTmemDw = 256;
+constexpr int kLdR = FH + 4;                          // row stride of the d agg / y tiles (conflict-free quarter-warp dots)
+
 __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t bar_w, bar_w2, bar_mma;
+  __shared__ uint64_t bar_w, bar_w2, bar_mma, bar_dw;
   __shared__ uint32_t tmem_slot;
   const FsgBSmem S = fsg_bsmem();
   unsigned char* sAh = smem + S.a_hi;
@@ -184,6 +189,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
   int* sInSrc = reinterpret_cast<int*>(smem + S.in_src);
   int* sOutDst = reinterpret_cast<int*>(smem + S.out_dst);
   int* sOutPos = reinterpret_cast<int*>(smem + S.out_pos);
+  int* sOutRow = reinterpret_cast<int*>(smem + S.out_row);
   float* sOutNrm = reinterpret_cast<float*>(smem + S.out_nrm);
   float2* sW = reinterpret_cast<float2*>(smem + S.w);
   float2* sDn = reinterpret_cast<float2*>(smem + S.dnrm);
@@ -197,12 +203,16 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
   const FsgWs ws = fsg_ws(c);
   const int L = c.L, F = c.F;
 
-  // ---- before the dependency wait: TMEM, barriers, attention projection weights (parameters) ----
-  if (warp == 0) umma::tmem_alloc(&tmem_slot, kTmemCols);
+  // ---- before the dependency wait.  The immediate predecessor (the readout backward) only writes the gradient of
+  // the pooled embeddings; everything else this kernel reads -- the plan, the CSRs, the forward pass's activations,
+  // masks and BatchNorm records, the weight images -- was complete before the predecessor could start, so the whole
+  // block-local set-up overlaps the predecessor's run. ----
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, kTmemColsB);
   if (t == 0) {
     umma::mbar_init(&bar_w, 1);
     umma::mbar_init(&bar_w2, 1);
     umma::mbar_init(&bar_mma, 1);
+    umma::mbar_init(&bar_dw, 1);
     umma::mbar_fence_init();
   }
   float wn0[4], wn1[4], wp0[4], wp1[4], wq0[4], wq1[4];
@@ -220,28 +230,18 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
       wq1[i] = We[3 * FH + k];
     }
   }
-  umma::fence_before_sync();
-  FSG_TDECL
-  pdl_sync();
-  FSG_T(0);                                                           // 0: dependency wait
-  __syncthreads();
-  umma::fence_after_sync();
-  const uint32_t tmem = tmem_slot;
   const int nblk = ws.plan[0], plan_ok = ws.plan[1];
   const int N = imin(imax(c.dims[0], 0), c.Nm);
   const bool active = plan_ok != 0 && (int)blockIdx.x < nblk;
   const int G = nblk;
-  uint32_t par_w = 0, par_w2 = 0, par_m = 0;
-
+  uint32_t par_w = 0, par_w2 = 0, par_m = 0, par_d = 0;
+  int g0 = 0, n0 = 0, Nc = 0, Ec = 0, ie0 = 0, oe0 = 0;
   if (active) {
     const int4 ia = *reinterpret_cast<const int4*>(ws.info + (size_t)blockIdx.x * 8);
     const int4 ib = *reinterpret_cast<const int4*>(ws.info + (size_t)blockIdx.x * 8 + 4);
-    const int g0 = ia.x, n0 = ia.z, n1 = ia.w, ie0 = ib.x, ie1 = ib.y, oe0 = ib.z;
-    const int Nc = n1 - n0, Ec = ie1 - ie0;
-    const int npad = imax(8, (Nc + 7) & ~7);
-    float* part = ws.part + (size_t)blockIdx.x * fsg_part_floats(L, F);
-
-    // ================= stage 0: block-local structure, masks, BatchNorm records, pooled gradient =================
+    g0 = ia.x; n0 = ia.z; Nc = ia.w - ia.z;
+    ie0 = ib.x; Ec = ib.y - ib.x; oe0 = ib.z;
+    // ================= stage 0: block-local structure, masks, BatchNorm records =================
     if (t == 0) {                                                      // context_convs backward image (whole)
       umma::mbar_expect_tx(&bar_w, 2u * 65536u);
       umma::bulk_g2s(sAh, fsg_img_bwd(ws, L), 65536u, &bar_w);
@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
       const float2 d = *reinterpret_cast<const float2*>(c.disw + (size_t)(n0 + i) * 2);
       float* r = sRow + i * 8;
       r[0] = a.x; r[1] = a.y; r[2] = d.x; r[3] = d.y; r[4] = 0.f; r[5] = 0.f;
+      for (int q = c.out_ptr[n0 + i] - oe0, q1 = c.out_ptr[n0 + i + 1] - oe0; q < q1; ++q) sOutRow[q] = i;
     }
     {
       // records of bnc (threads 0..127) / bno (128..255): sc | sh | mean | rstd  (set br at sVec + br * 6 * FH)
@@ -273,8 +274,23 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
       v[FH + k] = c.bnf(id, BN_SHIFT)[k];
       v[2 * FH + k] = c.bnf(id, BN_MEAN)[k];
       v[3 * FH + k] = c.bnf(id, BN_RSTD)[k];
+    }
+  }
+  umma::fence_before_sync();
+  FSG_TDECL
+  pdl_sync();
+  FSG_T(0);                                                           // 0: dependency wait (set-up overlapped)
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (active) {
+    const int npad = imax(8, (Nc + 7) & ~7);
+    float* part = ws.part + (size_t)blockIdx.x * fsg_part_floats(L, F);
+    {
       // global_add_pool backward = broadcast of the pooled gradient (model.py:115-116); the c <- co path goes
       // through the inverse permutation (model.py:152-157)
+      const int br = t >> 7, k = t & 127;
       const size_t H2 = 2 * FH;
       float g;
       if (br == 0) g = c.du[((size_t)0 * c.Bm + g0) * H2 + k] + c.du[((size_t)2 * c.Bm + c.invperm[g0]) * H2 + k];
@@ -282,10 +298,10 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
       sPool[br * FH + k] = g;
     }
     __syncthreads();
-    FSG_T(1);                                                         // 1: structure + records
+    FSG_T(1);                                                         // 1: pooled gradient
 
     // ================= stage 1: the two masked convs, dense part (model.py:112-113 backward) =================
-    //   dz = dpool * relu'(z);  d agg = dz W^T (tensor cores);  dW += agg^T dz;  db += dz
+    //   dz = dpool * relu'(z);  d agg = dz W^T (tensor cores);  dW += agg^T dz (tensor cores);  db += dz
     for (int br = 0; br < 2; ++br) {
       const float* Zg = c.Z + (size_t)br * c.Nm * FH + (size_t)n0 * FH;
       const float4 gp = *reinterpret_cast<const float4*>(sPool + br * FH + lane * 4);
@@ -309,19 +325,25 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
         umma::commit(&bar_mma);
       }
       par_w ^= 1u;
-      FSG_T(2);                                                       // 2: dz operand + issue
-      {
-        DwAcc dw;
-        dw.zero();
-        dw.accumulate<false>(sX, nullptr, nullptr, sBh, sBl, Nc);
-        dw.store(part + fsg_part_conv(L + br));
-      }
       colsum8(dbias, reinterpret_cast<float*>(sPart), part + fsg_part_conv(L + br) + FH * FH);
-      FSG_T(3);                                                       // 3: weight gradient (FFMA)
+      FSG_T(2);                                                       // 2: dz operand + issue
       umma::mbar_wait(&bar_mma, par_m);
       par_m ^= 1u;
       umma::fence_after_sync();
-      __syncthreads();                                                // sX / the operand are free; so is the weight image
+      FSG_T(4);                                                       // 4: MMA tail
+      // the weight image is dead: the transposed operands of dW = agg^T dz go there
+      build_dw_operands<false>(sAh, sX, FH, nullptr, nullptr, sBh, sBl, Nc, npad);
+      umma::fence_async_smem();
+      __syncthreads();
+      if (t == 0) {
+        umma::fence_after_sync();
+        issue_dw(sAh, tmem + kTmemDw, npad);
+        umma::commit(&bar_dw);
+      }
+      umma::mbar_wait(&bar_dw, par_d);
+      par_d ^= 1u;
+      umma::fence_after_sync();
+      __syncthreads();                                                // sX / the operands / the image buffer are free
       if (br == 0) {
         rows_async(sX, c.agg + (size_t)c.Nm * FH + (size_t)n0 * FH, Nc);
         if (t == 0) {
@@ -329,19 +351,18 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
           umma::bulk_g2s(sAh, fsg_img_bwd(ws, L + 1), 65536u, &bar_w);
           umma::bulk_g2s(sAl, fsg_img_bwd(ws, L + 1) + kFsgImgPart, 65536u, &bar_w);
         }
+      } else {
+        rows_async(sX, c.Xl(L) + (size_t)n0 * FH, Nc);                 // x_{L+1} rows for the sparse part
       }
-      FSG_T(4);                                                       // 4: MMA tail
-    }
-    // x_{L+1} rows for the sparse part; the image of the top backbone layer (all but the tail the gradient rows alias)
-    rows_async(sX, c.Xl(L) + (size_t)n0 * FH, Nc);
-    if (t == 0) {
-      umma::mbar_expect_tx(&bar_w, 65536u + kTailOff);
-      umma::bulk_g2s(sAh, fsg_img_bwd(ws, L - 1), 65536u, &bar_w);
-      umma::bulk_g2s(sAl, fsg_img_bwd(ws, L - 1) + kFsgImgPart, kTailOff, &bar_w);
+      drain_dw(tmem + kTmemDw, part + fsg_part_conv(L + br));
+      umma::fence_before_sync();
+      FSG_T(3);                                                       // 3: weight gradient
     }
     // d agg of both branches, TMEM -> row-major tiles in the (free) operand buffers: thread = channel
     float* sR0 = reinterpret_cast<float*>(sBh);
     float* sR1 = reinterpret_cast<float*>(sBl);
+    float* sY0 = reinterpret_cast<float*>(sAh);                        // y = bn_k(att_k x) tiles in the idle image buffer
+    float* sY1 = sY0 + kFsgRows * kLdR;
     {
       const int ch = (warp & 3) * 32 + lane;
       for (int g8 = (warp >> 2) * 8; g8 < npad; g8 += 16) {
@@ -354,8 +375,8 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
         for (int e = 0; e < 8; ++e) {
           const int i = g8 + e;
           if (i < Nc) {
-            sR0[i * FH + ch] = vm[e] + vc[e];
-            sR1[i * FH + ch] = um[e] + uc[e];
+            sR0[i * kLdR + ch] = vm[e] + vc[e];
+            sR1[i * kLdR + ch] = um[e] + uc[e];
           }
         }
       }
@@ -366,8 +387,9 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
     umma::fence_after_sync();
     FSG_T(5);                                                         // 5: d agg tiles
 
-    // ================= stage 2: masked convs, sparse part (warp per source row j) =================
-    //   dy_j = sum_{e: row_e = j} norm_e d agg[col_e];  d norm_e = <d agg[col_e], y_j>,  y_j = bn_k(att_k[j] x_j)
+    // ================= stage 2: masked convs, sparse part =================
+    //   dy_j = sum_{e: row_e = j} norm_e d agg[col_e]  (warp per source row j);
+    //   d norm_e = <d agg[col_e], y_j>,  y_j = bn_k(att_k[j] x_j)  (quarter warp per (entry, branch))
     float4 dyk[kRowsPerWarp][2];                                      // dy of this warp's rows, kept across the all-reduce
     {
       double st[4][4];
@@ -391,20 +413,15 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
           const float4 xm = make_float4(aj * x.x, aj * x.y, aj * x.z, aj * x.w);
           const float4 y = make_float4(fmaf(xm.x, sc.x, sh.x), fmaf(xm.y, sc.y, sh.y), fmaf(xm.z, sc.z, sh.z), fmaf(xm.w, sc.w, sh.w));
           const float4 xh = make_float4((xm.x - mu.x) * rs.x, (xm.y - mu.y) * rs.y, (xm.z - mu.z) * rs.z, (xm.w - mu.w) * rs.w);
+          *reinterpret_cast<float4*>((k ? sY1 : sY0) + j * kLdR + lane * 4) = y;
           const float* sR = k ? sR1 : sR0;
           float4 dy = make_float4(0.f, 0.f, 0.f, 0.f);
           for (int q = q0; q < q1; ++q) {
-            const int dd = sOutDst[q], pos = sOutPos[q];
-            const float2 wa = sW[pos];
+            const int dd = sOutDst[q];
+            const float2 wa = sW[sOutPos[q]];
             const float w = (dj * (k ? wa.y : wa.x)) * sRow[dd * 8 + 2 + k];
-            const float4 g = *reinterpret_cast<const float4*>(sR + dd * FH + lane * 4);
+            const float4 g = *reinterpret_cast<const float4*>(sR + dd * kLdR + lane * 4);
             dy.x = fmaf(w, g.x, dy.x); dy.y = fmaf(w, g.y, dy.y); dy.z = fmaf(w, g.z, dy.z); dy.w = fmaf(w, g.w, dy.w);
-            float dot = fmaf(g.x, y.x, fmaf(g.y, y.y, fmaf(g.z, y.z, g.w * y.w)));
-            dot = warp_sum(dot);
-            if (lane == 0) {
-              if (k) sDn[pos].y = dot;
-              else sDn[pos].x = dot;
-            }
           }
           dyk[rr][k] = dy;
           st[2 * k][0] += (double)dy.x; st[2 * k][1] += (double)dy.y; st[2 * k][2] += (double)dy.z; st[2 * k][3] += (double)dy.w;
@@ -412,12 +429,43 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
           st[2 * k + 1][2] += (double)dy.z * (double)xh.z; st[2 * k + 1][3] += (double)dy.w * (double)xh.w;
         }
       }
-      // block totals [bnc: sum dy | sum dy xhat | bno: sum dy | sum dy xhat]; the d agg tiles are dead: scratch
-      __syncthreads();
+      __syncthreads();                                                // the y tiles are complete
+      {
+        const int sub = lane & 7, grp = t >> 3;                        // 32 quarter warps; lane `sub` owns 16 channels
+        for (int it0 = 0; it0 < 2 * Ec; it0 += FT / 8) {               // warp-uniform trip count (full-mask shuffles)
+          const int it = it0 + grp;
+          const bool ok = it < 2 * Ec;
+          const int q = ok ? it >> 1 : 0, k = it & 1;
+          const float* g = (k ? sR1 : sR0) + sOutDst[q] * kLdR + sub * 16;
+          const float* y = (k ? sY1 : sY0) + sOutRow[q] * kLdR + sub * 16;
+          float dot = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 a = *reinterpret_cast<const float4*>(g + 4 * i), b = *reinterpret_cast<const float4*>(y + 4 * i);
+            dot = fmaf(a.x, b.x, dot); dot = fmaf(a.y, b.y, dot); dot = fmaf(a.z, b.z, dot); dot = fmaf(a.w, b.w, dot);
+          }
+          dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+          dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+          dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+          if (ok && sub == 0) {
+            if (k) sDn[sOutPos[q]].y = dot;
+            else sDn[sOutPos[q]].x = dot;
+          }
+        }
+      }
+      umma::fence_async_smem();                                       // (the y tiles sit where the next weight image lands)
+      // block totals [bnc: sum dy | sum dy xhat | bno: sum dy | sum dy xhat]
+      __syncthreads();                                                // the tiles are dead: the d agg buffer is scratch
       block_totals<4, 4>(st, reinterpret_cast<double*>(sBh), sPart, FH, 0, FH, 0);
     }
     FSG_T(6);                                                         // 6: masked gather
     fsg_publish(ws, 12, G, sPart, 4 * FH);
+    if (t == 0) {                                                      // image of the top backbone layer (all but the tail)
+      umma::fence_async_smem();
+      umma::mbar_expect_tx(&bar_w, 65536u + kTailOff);
+      umma::bulk_g2s(sAh, fsg_img_bwd(ws, L - 1), 65536u, &bar_w);
+      umma::bulk_g2s(sAl, fsg_img_bwd(ws, L - 1) + kFsgImgPart, kTailOff, &bar_w);
+    }
     FSG_T(7);                                                         // 7: publish
 
     // ================= stage 3: weighted-norm backward (warp per node; overlaps the all-reduce) =================
@@ -508,8 +556,6 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
           dq0 += d.x;
           dq1 += d.y;
         }
-        dq0 = warp_sum(dq0);
-        dq1 = warp_sum(dq1);
         const float* r = sRow + n * 8;
         const float a0 = r[0], a1 = r[1], dpx = r[4], dpy = r[5];
         const float4 x4 = *reinterpret_cast<const float4*>(sX + n * FH + lane * 4);
@@ -527,8 +573,14 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
           da0 = fmaf(gc[i], x[i], da0);
           da1 = fmaf(go[i], x[i], da1);
         }
-        da0 = warp_sum(da0);
-        da1 = warp_sum(da1);
+        // four warp sums at once: the butterfly's independent shuffles pipeline
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          dq0 += __shfl_xor_sync(0xffffffffu, dq0, o);
+          dq1 += __shfl_xor_sync(0xffffffffu, dq1, o);
+          da0 += __shfl_xor_sync(0xffffffffu, da0, o);
+          da1 += __shfl_xor_sync(0xffffffffu, da1, o);
+        }
         float ds0 = 0.f, ds1 = 0.f;
         if (!c.no_natt) {
           const float dot = a0 * da0 + a1 * da1;
@@ -561,27 +613,36 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
         g_be0 += dpx;
         g_be1 += dpy;
       }
-      // per-block partials of the attention parameters and of the top layer's bias
-      float* sRed = reinterpret_cast<float*>(sPart);                  // [8][128] floats (sPart | sTot are contiguous)
-      float* pa = part + fsg_part_att(L);
-      colsum8(g_wn0, sRed, pa);
-      colsum8(g_wn1, sRed, pa + FH);
-      colsum8(g_wp0, sRed, pa + 2 * FH);
-      colsum8(g_wq0, sRed, pa + 3 * FH);
-      colsum8(g_wp1, sRed, pa + 4 * FH);
-      colsum8(g_wq1, sRed, pa + 5 * FH);
-      colsum8(dbias, sRed, part + fsg_part_conv(L - 1) + FH * FH);
+      // per-block partials of the attention parameters and of the top layer's bias: one pass over [7][8 warps][128]
+      float* sRed = reinterpret_cast<float*>(sBh);                    // 28 KB of the (idle) node-operand buffers
       __syncthreads();
-      if (lane == 0) {
-        sRed[warp * 4 + 0] = g_bn0;
-        sRed[warp * 4 + 1] = g_bn1;
-        sRed[warp * 4 + 2] = g_be0;
-        sRed[warp * 4 + 3] = g_be1;
+      {
+        float* q = sRed + warp * FH + lane * 4;
+        *reinterpret_cast<float4*>(q + 0 * 8 * FH) = make_float4(g_wn0[0], g_wn0[1], g_wn0[2], g_wn0[3]);
+        *reinterpret_cast<float4*>(q + 1 * 8 * FH) = make_float4(g_wn1[0], g_wn1[1], g_wn1[2], g_wn1[3]);
+        *reinterpret_cast<float4*>(q + 2 * 8 * FH) = make_float4(g_wp0[0], g_wp0[1], g_wp0[2], g_wp0[3]);
+        *reinterpret_cast<float4*>(q + 3 * 8 * FH) = make_float4(g_wq0[0], g_wq0[1], g_wq0[2], g_wq0[3]);
+        *reinterpret_cast<float4*>(q + 4 * 8 * FH) = make_float4(g_wp1[0], g_wp1[1], g_wp1[2], g_wp1[3]);
+        *reinterpret_cast<float4*>(q + 5 * 8 * FH) = make_float4(g_wq1[0], g_wq1[1], g_wq1[2], g_wq1[3]);
+        *reinterpret_cast<float4*>(q + 6 * 8 * FH) = make_float4(dbias[0], dbias[1], dbias[2], dbias[3]);
+        if (lane == 0) {
+          float* sc4 = sRed + 7 * 8 * FH + warp * 4;
+          sc4[0] = g_bn0; sc4[1] = g_bn1; sc4[2] = g_be0; sc4[3] = g_be1;
+        }
       }
       __syncthreads();
+      float* pa = part + fsg_part_att(L);
+      for (int i = t; i < 7 * FH; i += FT) {
+        const int v = i >> 7, k = i & 127;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += sRed[(v * 8 + w) * FH + k];
+        if (v < 6) pa[v * FH + k] = s;
+        else part[fsg_part_conv(L - 1) + FH * FH + k] = s;
+      }
       if (t < 4) {
         float s = 0.f;
-        for (int w = 0; w < 8; ++w) s += sRed[w * 4 + t];
+        for (int w = 0; w < 8; ++w) s += sRed[7 * 8 * FH + w * 4 + t];
         pa[6 * FH + t] = s;
       }
     }
@@ -629,9 +690,10 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
           const uint64_t al = umma::smem_desc(umma::smem_addr(sAl) + aa, kALbo, kASbo);
           const uint64_t bh = umma::smem_desc(umma::smem_addr(sBh) + ba, kBLbo, kBSbo);
           const uint64_t bl = umma::smem_desc(umma::smem_addr(sBl) + ba, kBLbo, kBSbo);
-          umma::mma_tf32(tmem + 128u, al, bh, idesc, s > 0);
-          umma::mma_tf32(tmem + 128u, ah, bl, idesc, 1u);
+          // (the products that need the lo image last: its tail is still landing during the first steps)
           umma::mma_tf32(tmem, ah, bh, idesc, s > 0);
+          umma::mma_tf32(tmem + 128u, ah, bl, idesc, s > 0);
+          umma::mma_tf32(tmem + 128u, al, bh, idesc, 1u);
         }
         umma::commit(&bar_mma);
       }
@@ -641,11 +703,6 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
       par_m ^= 1u;
       umma::fence_after_sync();
       FSG_T(12);                                                      // 12: MMA
-      if (t == 0 && l > 0) {                                          // next image (all but the tail) while the rest runs
-        umma::mbar_expect_tx(&bar_w, 65536u + kTailOff);
-        umma::bulk_g2s(sAh, fsg_img_bwd(ws, l - 1), 65536u, &bar_w);
-        umma::bulk_g2s(sAl, fsg_img_bwd(ws, l - 1) + kFsgImgPart, kTailOff, &bar_w);
-      }
       // sums of bn_l backward: thread = channel, the two warp sets split the row groups
       {
         const int ch = (warp & 3) * 32 + lane;
@@ -680,15 +737,26 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
       FSG_T(13);                                                      // 13: statistics epilogue
       fsg_publish(ws, 13 + (L - 1 - l), G, sPart, 2 * FH);
       FSG_T(7);
-      {
-        DwAcc dw;
-        dw.zero();
-        dw.accumulate<true>(sX, vin, vin + FH, sBh, sBl, Nc);
-        dw.store(part + fsg_part_conv(l));
+      // dW = bn_l(x_in)^T u on the tensor cores while the all-reduce travels (operands in the idle image buffer)
+      build_dw_operands<true>(sAh, sX, FH, vin, vin + FH, sBh, sBl, Nc, npad);
+      umma::fence_async_smem();
+      __syncthreads();
+      if (t == 0) {
+        umma::fence_after_sync();
+        issue_dw(sAh, tmem + kTmemDw, npad);
+        umma::commit(&bar_dw);
       }
       FSG_T(3);
       fsg_wait_total(ws, 13 + (L - 1 - l), G, 2 * FH, sTot);
       fsg_bn_bwd_finalize(c, 1 + l, N, sTot, vin + 4 * FH, vin + 5 * FH, 0);
+      umma::mbar_wait(&bar_dw, par_d);
+      par_d ^= 1u;
+      umma::fence_after_sync();
+      if (t == 0 && l > 0) {                                          // next image (all but the tail) while the rest runs
+        umma::mbar_expect_tx(&bar_w, 65536u + kTailOff);
+        umma::bulk_g2s(sAh, fsg_img_bwd(ws, l - 1), 65536u, &bar_w);
+        umma::bulk_g2s(sAl, fsg_img_bwd(ws, l - 1) + kFsgImgPart, kTailOff, &bar_w);
+      }
       __syncthreads();
       FSG_T(9);
       // gradient w.r.t. the pre-activation of the layer below (the input transform for l == 0):
@@ -715,6 +783,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
         }
         float* sRed = reinterpret_cast<float*>(sPart);
         if (warp >= 4) sRed[ch] = db;
+        drain_dw(tmem + kTmemDw, part + fsg_part_conv(l));
         umma::fence_before_sync();
         __syncthreads();
         umma::fence_after_sync();
@@ -724,7 +793,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
           else part[fsg_part_feat(L) + (size_t)F * FH + ch] = tot;     // column sums of g_1 (k_feat_bwd's cs)
         }
       }
-      FSG_T(14);                                                      // 14: BatchNorm backward into the rows below
+      FSG_T(14);                                                      // 14: BatchNorm backward into the rows below + dW drain
     }
 
     // ================= stage 6: input transform backward: M = xhat_0^T g_1  [F, H] =================
@@ -752,7 +821,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
   // ---- teardown: TMEM, and the last CTA re-arms the all-reduce counters for the next launch ----
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
+  if (warp == 0) umma::tmem_dealloc(tmem, kTmemColsB);
   if (active && t == 0) {
     __threadfence();
     if (atomicAdd(&ws.cnt[kFsgPhases * kFsgCntStride], 1u) == (unsigned int)G - 1u) {
