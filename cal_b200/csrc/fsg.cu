@@ -139,36 +139,26 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
   }
   const float bnat0 = c.params[c.po.node_att_b], bnat1 = c.params[c.po.node_att_b + 1];
   const float beat0 = c.params[c.po.edge_att_b], beat1 = c.params[c.po.edge_att_b + 1];
-  umma::fence_before_sync();
-  FSG_TDECL
-  pdl_sync();                                                         // everything below may read the predecessors' output
-  FSG_T(0);                                                           // 0: dependency wait
-  __syncthreads();
-  umma::fence_after_sync();
-  const uint32_t tmem = tmem_slot;
-  const int nblk = ws.plan[0], plan_ok = ws.plan[1];
+  // ---- still before the dependency wait: the immediate predecessor (k_fsg_prep) only writes the weight images and the
+  // plan; the structure (cal_prep), the input features and their column totals were complete before it could start.
+  // A block is ONE graph (k_fsg_prep's plan, restated here from the structure so that it need not be waited for). ----
   const int N = imin(imax(c.dims[0], 0), c.Nm);
-  bool active = plan_ok != 0 && (int)blockIdx.x < nblk;
-  if (!plan_ok && blockIdx.x == 0 && t == 0) atomicOr(c.status, kStCapacity);
   int g0 = 0, g1 = 0, n0 = 0, n1 = 0, ie0 = 0, ie1 = 0, oe0 = 0;
-  if (active) {
-    const int4 a = *reinterpret_cast<const int4*>(ws.info + (size_t)blockIdx.x * 8);
-    const int4 b = *reinterpret_cast<const int4*>(ws.info + (size_t)blockIdx.x * 8 + 4);
-    g0 = a.x; g1 = a.y; n0 = a.z; n1 = a.w;
-    ie0 = b.x; ie1 = b.y; oe0 = b.z;
+  bool own = (int)blockIdx.x < imin(imax(c.dims[2], 0), c.Bm);
+  if (own) {
+    g0 = blockIdx.x; g1 = g0 + 1;
+    n0 = c.graph_ptr[g0]; n1 = c.graph_ptr[g1];
+    if (n1 < n0 || n1 - n0 > kFsgRows || n0 < 0 || n1 > c.Nm) own = false;
   }
+  if (own) {
+    ie0 = c.in_ptr[n0]; ie1 = c.in_ptr[n1]; oe0 = c.out_ptr[n0];
+    if (ie1 < ie0 || ie1 - ie0 > kFsgEntries) own = false;
+  }
+  if (!own) g0 = g1 = n0 = n1 = ie0 = ie1 = oe0 = 0;
   const int Nc = n1 - n0, Ec = ie1 - ie0;
   const int npad = imax(8, (Nc + 7) & ~7);                             // MMA N
-  const int G = nblk;
   uint32_t par_w = 0, par_m = 0;                                      // mbarrier phases
-  if (active) {
-    // weight operand of the input transform
-    if (t == 0) {
-      const uint32_t bytes = (uint32_t)(Fp8 / 4) * kALbo;
-      umma::mbar_expect_tx(&bar_w, 2 * bytes);
-      umma::bulk_g2s(sAh, fsg_img_feat(ws, L), bytes, &bar_w);
-      umma::bulk_g2s(sAl, fsg_img_feat(ws, L) + kFsgImgPart, bytes, &bar_w);
-    }
+  if (own) {
     // the block's two CSR segments, local ids
     for (int i = t; i <= Nc; i += FT) {
       sInPtr[i] = c.in_ptr[n0 + i] - ie0;
@@ -220,26 +210,46 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
       }
     }
     __syncthreads();
-    FSG_T(1);                                                         // 1: plan, CSR segments, bn_feat
+    // node operand of the input transform: bn_feat(x) rows, split
+    const int nkc = Fp8 / 4;
+    for (int i = warp; i < npad; i += 8) {
+      if (lane < nkc) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (i < Nc) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int k = lane * 4 + e;
+            if (k < F) v[e] = fmaf(c.feat[(size_t)(n0 + i) * F + k], sc[k], sh[k]);
+          }
+        }
+        put_b(sBh, sBl, i, lane, make_float4(v[0], v[1], v[2], v[3]));
+      }
+    }
+    umma::fence_async_smem();
+  }
+  umma::fence_before_sync();
+  FSG_TDECL
+  pdl_sync();                                                         // the weight images and the plan
+  FSG_T(0);                                                           // 0: dependency wait (set-up overlapped)
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const int nblk = ws.plan[0], plan_ok = ws.plan[1];
+  const bool active = own && plan_ok != 0 && (int)blockIdx.x < nblk;
+  if (!plan_ok && blockIdx.x == 0 && t == 0) atomicOr(c.status, kStCapacity);
+  const int G = nblk;
+  if (active) {
+    // weight operand of the input transform
+    if (t == 0) {
+      const uint32_t bytes = (uint32_t)(Fp8 / 4) * kALbo;
+      umma::mbar_expect_tx(&bar_w, 2 * bytes);
+      umma::bulk_g2s(sAh, fsg_img_feat(ws, L), bytes, &bar_w);
+      umma::bulk_g2s(sAl, fsg_img_feat(ws, L) + kFsgImgPart, bytes, &bar_w);
+    }
+    FSG_T(1);                                                         // 1: (set-up now happens before the wait)
 
     // ================= input transform: x_1 = relu(bn_feat(x) W_feat)  (gfn: no bias, no propagation) =================
     {
-      const int nkc = Fp8 / 4;
-      for (int i = warp; i < npad; i += 8) {
-        if (lane < nkc) {
-          float v[4] = {0.f, 0.f, 0.f, 0.f};
-          if (i < Nc) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int k = lane * 4 + e;
-              if (k < F) v[e] = fmaf(c.feat[(size_t)(n0 + i) * F + k], sc[k], sh[k]);
-            }
-          }
-          put_b(sBh, sBl, i, lane, make_float4(v[0], v[1], v[2], v[3]));
-        }
-      }
-      umma::fence_async_smem();
-      __syncthreads();
       umma::mbar_wait(&bar_w, par_w);
       par_w ^= 1u;
       if (t == 0) {
@@ -250,7 +260,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
       umma::mbar_wait(&bar_mma, par_m);
       par_m ^= 1u;
       umma::fence_after_sync();
-      FSG_T(2);                                                       // 2: input transform (operand + MMA)
+      FSG_T(2);                                                       // 2: input transform (MMA)
     }
   }
 
@@ -266,30 +276,36 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
         umma::bulk_g2s(sAh, img, 65536u, &bar_w);
         umma::bulk_g2s(sAl, img + kFsgImgPart, 65536u, &bar_w);
       }
-      // -- epilogue of the previous product: thread = output channel (warps 0-3) --
-      if (warp < 4) {
-        const int ch = t;
+      // -- epilogue of the previous product: thread = output channel, the two warp sets split the row groups --
+      {
+        const int ch = (warp & 3) * 32 + lane;
         const float bias = l == 0 ? 0.f : c.params[c.po.convs_b[l - 1] + ch];
-        float* xg = c.Xl(l) + (size_t)n0 * FH;
         double s = 0.0, q = 0.0;
-        for (int g8 = 0; g8 < npad; g8 += 8) {
+        for (int g8 = (warp >> 2) * 8; g8 < npad; g8 += 16) {
           float vm[8], vc[8];
-          umma::ld8(umma::tmem_addr(tmem, warp * 32, g8), vm);
-          umma::ld8(umma::tmem_addr(tmem, warp * 32, 128 + g8), vc);
+          umma::ld8(umma::tmem_addr(tmem, (warp & 3) * 32, g8), vm);
+          umma::ld8(umma::tmem_addr(tmem, (warp & 3) * 32, 128 + g8), vc);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int i = g8 + e;
             if (i < Nc) {
               const float x = fmaxf((vm[e] + vc[e]) + bias, 0.f);
               sX[i * FH + ch] = x;
-              xg[(size_t)i * FH + ch] = x;
               s += (double)x;
               q += (double)x * (double)x;
             }
           }
         }
-        sPart[ch] = s;
-        sPart[FH + ch] = q;
+        if (warp >= 4) {
+          sTot[ch] = s;
+          sTot[FH + ch] = q;
+        }
+        umma::fence_before_sync();
+        __syncthreads();
+        if (warp < 4) {
+          sPart[ch] = s + sTot[ch];
+          sPart[FH + ch] = q + sTot[FH + ch];
+        }
       }
       umma::fence_before_sync();
       __syncthreads();
@@ -299,8 +315,15 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
     if (!masked) {
       // ---------------- backbone layer l: x_{l+2} = relu(A bn_l(x_{l+1}) W_l + b_l)  (model.py:93-95) ----------------
       if (active) {
-        if (c.train) fsg_publish(ws, l, G, sPart, 2 * FH);
+        if (c.train) fsg_publish_fx(ws, l, sPart, 2 * FH);
         FSG_T(4);                                                     // 4: publish
+        // x_{l+1} rows to the workspace (the backward pass reads them): coalesced, after the publish so that the
+        // all-reduce's fence does not wait for these stores
+        {
+          float4* xg = reinterpret_cast<float4*>(c.Xl(l) + (size_t)n0 * FH);
+          const float4* xs = reinterpret_cast<const float4*>(sX);
+          for (int i = t; i < Nc * (FH / 4); i += FT) xg[i] = xs[i];
+        }
         // raw aggregate while the statistics travel: warp per target row, lanes over 4 channels
         for (int i = warp; i < Nc; i += 8) {
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -318,7 +341,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
         float* sc = sAff;
         float* sh = sAff + FH;
         if (c.train) {
-          fsg_wait_total(ws, l, G, 2 * FH, sTot);
+          fsg_wait_total_fx(ws, l, G, 2 * FH, sTot);
           fsg_bn_finalize(c, 1 + l, N, sTot, sc, sh, 0);
         } else if (t < FH) {
           sc[t] = c.bnf(1 + l, BN_SCALE)[t];
@@ -371,12 +394,17 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
         q0 = fmaf(o[k], wq0[k], q0);
         q1 = fmaf(o[k], wq1[k], q1);
       }
-      s0 = warp_sum(s0) + bnat0;
-      s1 = warp_sum(s1) + bnat1;
-      p0 = warp_sum(p0);
-      p1 = warp_sum(p1);
-      q0 = warp_sum(q0);
-      q1 = warp_sum(q1);
+#pragma unroll
+      for (int o_ = 16; o_ > 0; o_ >>= 1) {                            // six warp sums at once: independent shuffles pipeline
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o_);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o_);
+        p0 += __shfl_xor_sync(0xffffffffu, p0, o_);
+        p1 += __shfl_xor_sync(0xffffffffu, p1, o_);
+        q0 += __shfl_xor_sync(0xffffffffu, q0, o_);
+        q1 += __shfl_xor_sync(0xffffffffu, q1, o_);
+      }
+      s0 += bnat0;
+      s1 += bnat1;
       float a0 = 0.5f, a1 = 0.5f;
       if (!c.no_natt) {
         const float mx = fmaxf(s0, s1);
@@ -393,23 +421,35 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
       }
     }
     __syncthreads();
-    // statistics of bnc / bno on att * x: thread = channel (warps 0-3)
-    if (warp < 4 && c.train) {
+    // statistics of bnc / bno on att * x: thread = channel, the two warp sets split the rows
+    if (c.train) {
+      const int ch = t & 127, half = t >> 7;
       double a = 0.0, b = 0.0, d = 0.0, e = 0.0;
-      for (int i = 0; i < Nc; ++i) {
-        const float x = sX[i * FH + t];
+      for (int i = half; i < Nc; i += 2) {
+        const float x = sX[i * FH + ch];
         const float vc = sRow[i * 12 + 3] * x, vo = sRow[i * 12 + 4] * x;
         a += (double)vc; b += (double)vc * (double)vc;
         d += (double)vo; e += (double)vo * (double)vo;
       }
-      sPart[t] = a;
-      sPart[FH + t] = b;
-      sPart[2 * FH + t] = d;
-      sPart[3 * FH + t] = e;
+      if (half) {
+        sTot[ch] = a; sTot[FH + ch] = b; sTot[2 * FH + ch] = d; sTot[3 * FH + ch] = e;
+      }
+      __syncthreads();
+      if (!half) {
+        sPart[ch] = a + sTot[ch];
+        sPart[FH + ch] = b + sTot[FH + ch];
+        sPart[2 * FH + ch] = d + sTot[2 * FH + ch];
+        sPart[3 * FH + ch] = e + sTot[3 * FH + ch];
+      }
     }
     __syncthreads();
     FSG_T(10);                                                        // 10: node attention + bnc / bno statistics
-    if (c.train) fsg_publish(ws, L, G, sPart, 4 * FH);
+    if (c.train) fsg_publish_fx(ws, L, sPart, 4 * FH);
+    {
+      float4* xg = reinterpret_cast<float4*>(c.Xl(L) + (size_t)n0 * FH);      // x_{L+1} rows to the workspace
+      const float4* xs = reinterpret_cast<const float4*>(sX);
+      for (int i = t; i < Nc * (FH / 4); i += FT) xg[i] = xs[i];
+    }
     FSG_T(4);
     // edge attention softmax(p[row] + q[col] + b) per edge (never materialises [E, 2H]), the attention-weighted
     // degree by source row and dis_w = deg^-1/2 (gcn_conv.py:59-70 with edge_weight): warp per source node
@@ -482,7 +522,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
       FSG_T(5);
       if (br == 0) {
         if (c.train) {
-          fsg_wait_total(ws, L, G, 4 * FH, sTot);
+          fsg_wait_total_fx(ws, L, G, 4 * FH, sTot);
           fsg_bn_finalize(c, L + 1, N, sTot, sc0, sh0, 0);
           fsg_bn_finalize(c, L + 2, N, sTot + 2 * FH, sc1, sh1, FH);
         } else if (t < FH) {
@@ -532,38 +572,33 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
         umma::bulk_g2s(sAh, img, 65536u, &bar_w);
         umma::bulk_g2s(sAl, img + kFsgImgPart, 65536u, &bar_w);
       }
-      // epilogue of the branch: z = relu(. + b), saved; global_add_pool over the rows of every graph (model.py:115-116)
-      if (warp < 4) {
-        const int ch = t;
+      // epilogue of the branch: z = relu(. + b), saved; global_add_pool over the rows of the block's graph
+      // (model.py:115-116; a block is one graph).  thread = channel, the two warp sets split the row groups.
+      {
+        const int ch = (warp & 3) * 32 + lane;
         const float bias = c.params[(br ? c.po.objects_b : c.po.context_b) + ch];
         float* zg = c.Z + (size_t)br * c.Nm * FH + (size_t)n0 * FH;
-        float* pg = c.pooled + (size_t)br * c.Bm * FH;
         const uint32_t cm = br ? 64u : 0u;
-        int g = 0;
         float pool = 0.f;
-        for (int g8 = 0; g8 < npad; g8 += 8) {
+        for (int g8 = (warp >> 2) * 8; g8 < npad; g8 += 16) {
           float vm[8], vc[8];
-          umma::ld8(umma::tmem_addr(tmem, warp * 32, cm + g8), vm);
-          umma::ld8(umma::tmem_addr(tmem, warp * 32, 128 + cm + g8), vc);
+          umma::ld8(umma::tmem_addr(tmem, (warp & 3) * 32, cm + g8), vm);
+          umma::ld8(umma::tmem_addr(tmem, (warp & 3) * 32, 128 + cm + g8), vc);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int i = g8 + e;
             if (i < Nc) {
-              while (i >= sGptr[g + 1]) {                              // the row starts a new graph: flush the finished one
-                pg[(size_t)(g0 + g) * FH + ch] = pool;
-                pool = 0.f;
-                ++g;
-              }
               const float z = fmaxf((vm[e] + vc[e]) + bias, 0.f);
               zg[(size_t)i * FH + ch] = z;
               pool += z;
             }
           }
         }
-        for (; g < g1 - g0; ++g) {
-          pg[(size_t)(g0 + g) * FH + ch] = pool;
-          pool = 0.f;
-        }
+        float* sRed = reinterpret_cast<float*>(sPart);
+        if (warp >= 4) sRed[br * FH + ch] = pool;
+        umma::fence_before_sync();
+        __syncthreads();
+        if (warp < 4) c.pooled[((size_t)br * c.Bm + g0) * FH + ch] = pool + sRed[br * FH + ch];
       }
       umma::fence_before_sync();
       __syncthreads();
@@ -577,13 +612,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
-  if (active && t == 0) {
-    __threadfence();
-    if (atomicAdd(&ws.cnt[kFsgPhases * kFsgCntStride], 1u) == (unsigned int)G - 1u) {
-      for (int i = 0; i <= kFsgPhases * kFsgCntStride; ++i) ws.cnt[i] = 0u;
-      __threadfence();
-    }
-  }
+  if (active) fsg_rearm(ws, G, 0, L + 1);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -22,7 +22,7 @@ constexpr int kFsgImg = 2 * kFsgImgPart;   // hi | lo
 
 // the CAL_WS_FSG region (byte offsets)
 struct FsgLayout {
-  size_t plan, info, cnt, l0, l1, img, part, total;
+  size_t plan, info, cnt, l0, l1, acc, img, part, total;
 };
 __host__ __device__ inline size_t fsg_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -43,6 +43,7 @@ __host__ __device__ inline FsgLayout fsg_layout(int Bm, int L, int F) {
   f.cnt = o;   o = fsg_up(o + (size_t)(kFsgPhases * kFsgCntStride + 8) * 4);
   f.l0 = o;    o = fsg_up(o + (size_t)kSMs * kFsgVec * 8);
   f.l1 = o;    o = fsg_up(o + (size_t)2 * kFsgMaxGroups * kFsgVec * 8);
+  f.acc = o;   o = fsg_up(o + (size_t)kFsgPhases * 8 * 2 * kFsgVec * 8);           // fixed-point all-reduce accumulators (fsg_dev.cuh)
   f.img = o;   o = fsg_up(o + (size_t)((L + 2) * 2 + 1) * kFsgImg * 4);   // forward / backward image per conv matrix + feat
   f.part = o;                                                             // partial gradients, one slot per block
   if (Bm <= kSMs && F <= 128) o = fsg_up(o + (size_t)(Bm > 0 ? Bm : 1) * fsg_part_floats(L, F) * 4);
@@ -56,6 +57,7 @@ struct FsgWs {
   unsigned int* cnt;
   double* l0;
   double* l1;
+  long long* acc;
   float* img;
   float* part;
 };
@@ -67,6 +69,7 @@ __host__ __device__ inline FsgWs fsg_ws(const Ctx& c) {
   w.cnt = reinterpret_cast<unsigned int*>(c.fsg + f.cnt);
   w.l0 = reinterpret_cast<double*>(c.fsg + f.l0);
   w.l1 = reinterpret_cast<double*>(c.fsg + f.l1);
+  w.acc = reinterpret_cast<long long*>(c.fsg + f.acc);
   w.img = reinterpret_cast<float*>(c.fsg + f.img);
   w.part = reinterpret_cast<float*>(c.fsg + f.part);
   return w;

@@ -132,18 +132,29 @@ __device__ __forceinline__ void issue_dw(const unsigned char* wbuf, uint32_t d, 
     umma::mma_tf32(d, ph, qh, idesc, 1u);
   }
 }
-// all 8 warps: dW from TMEM -> dst [128][128] (thread = row of dW, the two warp sets split the columns)
-__device__ __forceinline__ void drain_dw(uint32_t tmem_dw, float* dst) {
+// all 8 warps: dW from TMEM -> dst [128][128].  A thread holds a ROW of the accumulator (lane = row), so a direct store
+// would touch 32 different 128-byte lines per instruction; every warp transposes its 32 x 32 blocks through a private
+// shared-memory scratch (stride 33: conflict-free both ways) and stores 4 rows x 128 contiguous bytes per instruction.
+constexpr int kDrainScratch = 8 * 32 * 33;            // floats
+__device__ __forceinline__ void drain_dw(uint32_t tmem_dw, float* dst, float* scratch) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = (warp & 3) * 32 + lane;
+  const int row0 = (warp & 3) * 32;
+  float* sw = scratch + warp * 32 * 33;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const int col = (warp >> 2) * 64 + h * 32;
+    const int col0 = (warp >> 2) * 64 + h * 32;
     float v[32];
-    umma::ld32(umma::tmem_addr(tmem_dw, (warp & 3) * 32, col), v);
-    float4* o = reinterpret_cast<float4*>(dst + (size_t)row * FH + col);
+    umma::ld32(umma::tmem_addr(tmem_dw, row0, col0), v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    for (int cc = 0; cc < 32; ++cc) sw[lane * 33 + cc] = v[cc];
+    __syncwarp();
+    const int rr = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float* q = sw + (rr + 4 * i) * 33 + c4;
+      *reinterpret_cast<float4*>(dst + (size_t)(row0 + rr + 4 * i) * FH + col0 + c4) = make_float4(q[0], q[1], q[2], q[3]);
+    }
+    __syncwarp();
   }
 }
 
@@ -354,8 +365,10 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
       } else {
         rows_async(sX, c.Xl(L) + (size_t)n0 * FH, Nc);                 // x_{L+1} rows for the sparse part
       }
-      drain_dw(tmem + kTmemDw, part + fsg_part_conv(L + br));
+      drain_dw(tmem + kTmemDw, part + fsg_part_conv(L + br), reinterpret_cast<float*>(sBh));
       umma::fence_before_sync();
+      __syncthreads();                                                // (the scratch is the node-operand buffer)
+      umma::fence_after_sync();
       FSG_T(3);                                                       // 3: weight gradient
     }
     // d agg of both branches, TMEM -> row-major tiles in the (free) operand buffers: thread = channel
@@ -404,26 +417,30 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
         if (j >= Nc) continue;
         const float4 x = *reinterpret_cast<const float4*>(sX + j * FH + lane * 4);
         const int q0 = sOutPtr[j], q1 = sOutPtr[j + 1];
+        const float dj0 = sRow[j * 8 + 2], dj1 = sRow[j * 8 + 3];
+        float4 dy0 = make_float4(0.f, 0.f, 0.f, 0.f), dy1 = dy0;
+        for (int q = q0; q < q1; ++q) {
+          const int dd = sOutDst[q];
+          const float2 wa = sW[sOutPos[q]];
+          const float w0 = (dj0 * wa.x) * sRow[dd * 8 + 2], w1 = (dj1 * wa.y) * sRow[dd * 8 + 3];
+          const float4 ga = *reinterpret_cast<const float4*>(sR0 + dd * kLdR + lane * 4);
+          const float4 gb = *reinterpret_cast<const float4*>(sR1 + dd * kLdR + lane * 4);
+          dy0.x = fmaf(w0, ga.x, dy0.x); dy0.y = fmaf(w0, ga.y, dy0.y); dy0.z = fmaf(w0, ga.z, dy0.z); dy0.w = fmaf(w0, ga.w, dy0.w);
+          dy1.x = fmaf(w1, gb.x, dy1.x); dy1.y = fmaf(w1, gb.y, dy1.y); dy1.z = fmaf(w1, gb.z, dy1.z); dy1.w = fmaf(w1, gb.w, dy1.w);
+        }
+        dyk[rr][0] = dy0;
+        dyk[rr][1] = dy1;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const float* v = sVec + k * 6 * FH;
           const float4 sc = *reinterpret_cast<const float4*>(v + lane * 4), sh = *reinterpret_cast<const float4*>(v + FH + lane * 4);
           const float4 mu = *reinterpret_cast<const float4*>(v + 2 * FH + lane * 4), rs = *reinterpret_cast<const float4*>(v + 3 * FH + lane * 4);
-          const float aj = sRow[j * 8 + k], dj = sRow[j * 8 + 2 + k];
+          const float aj = sRow[j * 8 + k];
           const float4 xm = make_float4(aj * x.x, aj * x.y, aj * x.z, aj * x.w);
           const float4 y = make_float4(fmaf(xm.x, sc.x, sh.x), fmaf(xm.y, sc.y, sh.y), fmaf(xm.z, sc.z, sh.z), fmaf(xm.w, sc.w, sh.w));
           const float4 xh = make_float4((xm.x - mu.x) * rs.x, (xm.y - mu.y) * rs.y, (xm.z - mu.z) * rs.z, (xm.w - mu.w) * rs.w);
           *reinterpret_cast<float4*>((k ? sY1 : sY0) + j * kLdR + lane * 4) = y;
-          const float* sR = k ? sR1 : sR0;
-          float4 dy = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int q = q0; q < q1; ++q) {
-            const int dd = sOutDst[q];
-            const float2 wa = sW[sOutPos[q]];
-            const float w = (dj * (k ? wa.y : wa.x)) * sRow[dd * 8 + 2 + k];
-            const float4 g = *reinterpret_cast<const float4*>(sR + dd * kLdR + lane * 4);
-            dy.x = fmaf(w, g.x, dy.x); dy.y = fmaf(w, g.y, dy.y); dy.z = fmaf(w, g.z, dy.z); dy.w = fmaf(w, g.w, dy.w);
-          }
-          dyk[rr][k] = dy;
+          const float4 dy = k ? dy1 : dy0;
           st[2 * k][0] += (double)dy.x; st[2 * k][1] += (double)dy.y; st[2 * k][2] += (double)dy.z; st[2 * k][3] += (double)dy.w;
           st[2 * k + 1][0] += (double)dy.x * (double)xh.x; st[2 * k + 1][1] += (double)dy.y * (double)xh.y;
           st[2 * k + 1][2] += (double)dy.z * (double)xh.z; st[2 * k + 1][3] += (double)dy.w * (double)xh.w;
@@ -459,7 +476,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
       block_totals<4, 4>(st, reinterpret_cast<double*>(sBh), sPart, FH, 0, FH, 0);
     }
     FSG_T(6);                                                         // 6: masked gather
-    fsg_publish(ws, 12, G, sPart, 4 * FH);
+    fsg_publish_fx(ws, 12, sPart, 4 * FH);
     if (t == 0) {                                                      // image of the top backbone layer (all but the tail)
       umma::fence_async_smem();
       umma::mbar_expect_tx(&bar_w, 65536u + kTailOff);
@@ -524,7 +541,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
     FSG_T(8);                                                         // 8: norm backward
 
     // ================= stage 4: attention backward -> gradient rows of the top backbone layer =================
-    fsg_wait_total(ws, 12, G, 4 * FH, sTot);
+    fsg_wait_total_fx(ws, 12, G, 4 * FH, sTot);
     fsg_bn_bwd_finalize(c, L + 1, N, sTot, sVec + 4 * FH, sVec + 5 * FH, 0);
     fsg_bn_bwd_finalize(c, L + 2, N, sTot + 2 * FH, sVec + 6 * FH + 4 * FH, sVec + 6 * FH + 5 * FH, FH);
     __syncthreads();
@@ -674,7 +691,6 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
         put_b(sBh, sBl, j, lane, u);
       }
       umma::fence_async_smem();
-      cp_async_wait_all();
       __syncthreads();                                                // the gradient rows are dead: the image tail may land
       FSG_T(11);                                                      // 11: transpose aggregate
       if (t == 0) {
@@ -683,25 +699,28 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
         umma::mbar_wait(&bar_w, par_w);
         umma::fence_after_sync();
         const uint32_t idesc = umma::instr_desc(umma::kFmtTF32, 128, npad);
+        const uint32_t aH = umma::smem_addr(sAh), aL = umma::smem_addr(sAl), bH = umma::smem_addr(sBh), bL = umma::smem_addr(sBl);
+        // the two products of the hi image first, the product of the lo image last: its tail is still landing
+        for (int s = 0; s < FH / 8; ++s) {
+          const uint32_t aa = (uint32_t)s * 2u * kALbo, ba = (uint32_t)s * 2u * kBLbo;
+          const uint64_t ah = umma::smem_desc(aH + aa, kALbo, kASbo);
+          umma::mma_tf32(tmem, ah, umma::smem_desc(bH + ba, kBLbo, kBSbo), idesc, s > 0);
+          umma::mma_tf32(tmem + 128u, ah, umma::smem_desc(bL + ba, kBLbo, kBSbo), idesc, s > 0);
+        }
         for (int s = 0; s < FH / 8; ++s) {
           if (s == kTailStep) umma::mbar_wait(&bar_w2, par_w2);
           const uint32_t aa = (uint32_t)s * 2u * kALbo, ba = (uint32_t)s * 2u * kBLbo;
-          const uint64_t ah = umma::smem_desc(umma::smem_addr(sAh) + aa, kALbo, kASbo);
-          const uint64_t al = umma::smem_desc(umma::smem_addr(sAl) + aa, kALbo, kASbo);
-          const uint64_t bh = umma::smem_desc(umma::smem_addr(sBh) + ba, kBLbo, kBSbo);
-          const uint64_t bl = umma::smem_desc(umma::smem_addr(sBl) + ba, kBLbo, kBSbo);
-          // (the products that need the lo image last: its tail is still landing during the first steps)
-          umma::mma_tf32(tmem, ah, bh, idesc, s > 0);
-          umma::mma_tf32(tmem + 128u, ah, bl, idesc, s > 0);
-          umma::mma_tf32(tmem + 128u, al, bh, idesc, 1u);
+          umma::mma_tf32(tmem + 128u, umma::smem_desc(aL + aa, kALbo, kASbo), umma::smem_desc(bH + ba, kBLbo, kBSbo), idesc, 1u);
         }
         umma::commit(&bar_mma);
       }
       par_w ^= 1u;
       par_w2 ^= 1u;
+      cp_async_wait_all();                                            // x_in rows (in flight since the top of the iteration)
       umma::mbar_wait(&bar_mma, par_m);
       par_m ^= 1u;
       umma::fence_after_sync();
+      __syncthreads();
       FSG_T(12);                                                      // 12: MMA
       // sums of bn_l backward: thread = channel, the two warp sets split the row groups
       {
@@ -735,7 +754,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
         __syncthreads();
       }
       FSG_T(13);                                                      // 13: statistics epilogue
-      fsg_publish(ws, 13 + (L - 1 - l), G, sPart, 2 * FH);
+      fsg_publish_fx(ws, 13 + (L - 1 - l), sPart, 2 * FH);
       FSG_T(7);
       // dW = bn_l(x_in)^T u on the tensor cores while the all-reduce travels (operands in the idle image buffer)
       build_dw_operands<true>(sAh, sX, FH, vin, vin + FH, sBh, sBl, Nc, npad);
@@ -745,18 +764,19 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
         umma::fence_after_sync();
         issue_dw(sAh, tmem + kTmemDw, npad);
         umma::commit(&bar_dw);
+        if (l > 0) {                                                  // next image (all but the tail) as soon as the operands are dead
+          umma::mbar_wait(&bar_dw, par_d);
+          umma::mbar_expect_tx(&bar_w, 65536u + kTailOff);
+          umma::bulk_g2s(sAh, fsg_img_bwd(ws, l - 1), 65536u, &bar_w);
+          umma::bulk_g2s(sAl, fsg_img_bwd(ws, l - 1) + kFsgImgPart, kTailOff, &bar_w);
+        }
       }
       FSG_T(3);
-      fsg_wait_total(ws, 13 + (L - 1 - l), G, 2 * FH, sTot);
+      fsg_wait_total_fx(ws, 13 + (L - 1 - l), G, 2 * FH, sTot);
       fsg_bn_bwd_finalize(c, 1 + l, N, sTot, vin + 4 * FH, vin + 5 * FH, 0);
       umma::mbar_wait(&bar_dw, par_d);
       par_d ^= 1u;
       umma::fence_after_sync();
-      if (t == 0 && l > 0) {                                          // next image (all but the tail) while the rest runs
-        umma::mbar_expect_tx(&bar_w, 65536u + kTailOff);
-        umma::bulk_g2s(sAh, fsg_img_bwd(ws, l - 1), 65536u, &bar_w);
-        umma::bulk_g2s(sAl, fsg_img_bwd(ws, l - 1) + kFsgImgPart, kTailOff, &bar_w);
-      }
       __syncthreads();
       FSG_T(9);
       // gradient w.r.t. the pre-activation of the layer below (the input transform for l == 0):
@@ -783,7 +803,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
         }
         float* sRed = reinterpret_cast<float*>(sPart);
         if (warp >= 4) sRed[ch] = db;
-        drain_dw(tmem + kTmemDw, part + fsg_part_conv(l));
+        drain_dw(tmem + kTmemDw, part + fsg_part_conv(l), reinterpret_cast<float*>(sBh));
         umma::fence_before_sync();
         __syncthreads();
         umma::fence_after_sync();
@@ -822,13 +842,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, kTmemColsB);
-  if (active && t == 0) {
-    __threadfence();
-    if (atomicAdd(&ws.cnt[kFsgPhases * kFsgCntStride], 1u) == (unsigned int)G - 1u) {
-      for (int i = 0; i <= kFsgPhases * kFsgCntStride; ++i) ws.cnt[i] = 0u;
-      __threadfence();
-    }
-  }
+  if (active) fsg_rearm(ws, G, 12, 13 + L);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -89,6 +89,77 @@ __device__ __forceinline__ void fsg_wait_total(const FsgWs& w, int phase, int G,
   __syncthreads();
 }
 
+// ---- the same all-reduce in ONE level: exact fixed-point accumulation with integer atomics ----
+// Integer addition is associative, so the totals do not depend on the arrival order (bit-identical runs) although
+// every CTA adds straight into shared accumulators -- no group leaders, no second counter phase.  A value v is scaled
+// to |v| * 2^40 (truncated; |v| < 2^55, resolution 2^-40 -- far below the fp32 results derived from the sums) and split
+// into two limbs of 48 bits, each added with the sign of v into its own 64-bit word (no carries between the words:
+// up to 2^15 addends).  kFxCopies accumulator copies (CTA b adds into copy b % kFxCopies) cut the same-address
+// serialisation of the L2 atomic unit; the reader adds the copies (integers: still exact) and recombines
+// hi * 2^48 + lo.  Latency: the atomics of a CTA are fire-and-forget (RED), then ONE fence + ONE counter atomic; a
+// waiting CTA polls that counter and reads 2 * kFxCopies words per value in one round trip.
+constexpr int kFxCopies = 8;
+constexpr int kFxWords = 2 * kFsgVec;                                 // 64-bit words per copy per phase
+__device__ __forceinline__ void fsg_fx_add(long long* acc2, double v) {
+  // limbs of the MAGNITUDE (every step below is exact in fp64: the operands are aligned), added with the value's sign
+  const double a = fabs(v) * 1099511627776.0;                         // 2^40 (exact scaling)
+  const double hi = floor(a * 3.552713678800501e-15);                 // 2^-48
+  const double lo = floor(a - hi * 281474976710656.0);                // in [0, 2^48): truncates below 2^-40
+  long long l0 = (long long)lo, l1 = (long long)hi;
+  if (v < 0.0) {
+    l0 = -l0; l1 = -l1;
+  }
+  atomicAdd(reinterpret_cast<unsigned long long*>(acc2), (unsigned long long)l0);
+  atomicAdd(reinterpret_cast<unsigned long long*>(acc2 + 1), (unsigned long long)l1);
+}
+__device__ __forceinline__ void fsg_publish_fx(const FsgWs& w, int phase, const double* sPart, int n) {
+  const int t = threadIdx.x;
+  long long* acc = w.acc + ((size_t)phase * kFxCopies + (blockIdx.x % kFxCopies)) * kFxWords;
+  for (int i = t; i < n; i += FT) fsg_fx_add(acc + 2 * i, sPart[i]);
+  __syncthreads();
+  if (t == 0) {
+    __threadfence();
+    atomicAdd(&w.cnt[phase * kFsgCntStride], 1u);
+  }
+}
+__device__ __forceinline__ void fsg_wait_total_fx(const FsgWs& w, int phase, int G, int n, double* sTot) {
+  const int t = threadIdx.x;
+  if (t == 0) {
+    while (ld_acquire_gpu(&w.cnt[phase * kFsgCntStride]) < (unsigned int)G) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  const longlong2* acc = reinterpret_cast<const longlong2*>(w.acc + (size_t)phase * kFxCopies * kFxWords);
+  for (int i = t; i < n; i += FT) {
+    longlong2 v[kFxCopies];
+#pragma unroll
+    for (int cp = 0; cp < kFxCopies; ++cp) v[cp] = __ldcg(acc + (size_t)cp * (kFxWords / 2) + i);
+    long long lo = 0, hi = 0;
+#pragma unroll
+    for (int cp = 0; cp < kFxCopies; ++cp) {
+      lo += v[cp].x;
+      hi += v[cp].y;
+    }
+    sTot[i] = ((double)hi * 281474976710656.0 + (double)lo) * 9.094947017729282e-13;   // 2^48, 2^-40
+  }
+  __syncthreads();
+}
+// teardown: the last CTA of the launch re-arms the counters and clears the accumulators of phases [p0, p1)
+__device__ __forceinline__ void fsg_rearm(const FsgWs& w, int G, int p0, int p1) {
+  __shared__ int s_last;
+  const int t = threadIdx.x;
+  if (t == 0) {
+    __threadfence();
+    s_last = atomicAdd(&w.cnt[kFsgPhases * kFsgCntStride], 1u) == (unsigned int)G - 1u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  for (int i = t; i < (p1 - p0) * kFxCopies * kFxWords; i += FT) w.acc[(size_t)p0 * kFxCopies * kFxWords + i] = 0;
+  for (int i = t; i <= kFsgPhases * kFsgCntStride; i += FT) w.cnt[i] = 0u;
+  __threadfence();
+}
+
 __device__ __forceinline__ uint32_t b_off(int i, int kc) { return (uint32_t)(i >> 3) * kBSbo + (uint32_t)kc * kBLbo + (uint32_t)(i & 7) * 16u; }
 
 // hi / lo split of one 16-byte chunk into the node operand
