@@ -636,11 +636,16 @@ __global__ void __launch_bounds__(256) k_fsg_prep(const Ctx c, const int n_img_b
       mode = img & 1;
       W = c.params + (j < L ? c.po.convs_w[j] : (j == L ? c.po.context_w : c.po.objects_w));
       dst = mode ? fsg_img_bwd(ws, j) : fsg_img_fwd(ws, j);
-    } else {
+    } else if (img == 2 * (L + 2)) {
       mode = 2;
       W = c.params + c.po.conv_feat_w;                                  // [F][H]
       dst = fsg_img_feat(ws, L);
       K = (c.F + 7) & ~7;
+    } else {                                                            // fc1 of readout h ("add": [H][H] as stored = [out][in])
+      const int q = img - 2 * (L + 2) - 1, h = q >> 1;
+      mode = (q & 1) ? 0 : 1;                                           // forward image: A[m][k] = W[m][k]; backward: A[m][k] = W[k][m]
+      W = c.params + c.po.fc1_w[h];
+      dst = (q & 1) ? fsg_img_fc1_bwd(ws, L, h) : fsg_img_fc1_fwd(ws, L, h);
     }
     for (int e = sub * 2048 + t; e < (sub + 1) * 2048; e += 256) {
       const int kc = e >> 9, m = (e & 511) >> 2, kk = e & 3;            // float offset e = kc * 512 + m * 4 + kk
@@ -681,7 +686,7 @@ int fsg_grid(const Ctx& c) { return imax(1, imin(c.Bm, kSMs)); }
 size_t fsg_region_bytes(int Bm, int L, int F) { return fsg_layout(Bm, L, F).total; }
 
 int launch_fsg_prep(const Ctx& c, cudaStream_t s) {
-  const int n_img = (2 * (c.L + 2) + 1) * 8;
+  const int n_img = (2 * (c.L + 2) + 1 + (c.cat ? 0 : 6)) * 8;       // (the fc1 images only exist for cat_or_add = "add")
   launch_k(k_fsg_prep, dim3(n_img + 1), dim3(256), 0, s, c, n_img, fsg_grid(c));
   note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();

@@ -44,7 +44,7 @@ __host__ __device__ inline FsgLayout fsg_layout(int Bm, int L, int F) {
   f.l0 = o;    o = fsg_up(o + (size_t)kSMs * kFsgVec * 8);
   f.l1 = o;    o = fsg_up(o + (size_t)2 * kFsgMaxGroups * kFsgVec * 8);
   f.acc = o;   o = fsg_up(o + (size_t)kFsgPhases * 8 * 2 * kFsgVec * 8);           // fixed-point all-reduce accumulators (fsg_dev.cuh)
-  f.img = o;   o = fsg_up(o + (size_t)((L + 2) * 2 + 1) * kFsgImg * 4);   // forward / backward image per conv matrix + feat
+  f.img = o;   o = fsg_up(o + (size_t)((L + 2) * 2 + 1 + 6) * kFsgImg * 4);   // forward / backward image per conv matrix + feat + fc1 of the 3 readouts
   f.part = o;                                                             // partial gradients, one slot per block
   if (Bm <= kSMs && F <= 128) o = fsg_up(o + (size_t)(Bm > 0 ? Bm : 1) * fsg_part_floats(L, F) * 4);
   f.total = o;
@@ -78,5 +78,8 @@ __host__ __device__ inline FsgWs fsg_ws(const Ctx& c) {
 __host__ __device__ inline float* fsg_img_fwd(const FsgWs& w, int j) { return w.img + (size_t)(2 * j) * kFsgImg; }
 __host__ __device__ inline float* fsg_img_bwd(const FsgWs& w, int j) { return w.img + (size_t)(2 * j + 1) * kFsgImg; }
 __host__ __device__ inline float* fsg_img_feat(const FsgWs& w, int L) { return w.img + (size_t)(2 * (L + 2)) * kFsgImg; }
+// readout fc1 (torch Linear [out, in], "add": in = H) of head h: forward image A[m = out][k = in], backward image A[m = in][k = out]
+__host__ __device__ inline float* fsg_img_fc1_fwd(const FsgWs& w, int L, int h) { return w.img + (size_t)(2 * (L + 2) + 1 + 2 * h) * kFsgImg; }
+__host__ __device__ inline float* fsg_img_fc1_bwd(const FsgWs& w, int L, int h) { return w.img + (size_t)(2 * (L + 2) + 2 + 2 * h) * kFsgImg; }
 
 }  // namespace cal

@@ -19,11 +19,13 @@ constexpr int kTmemCols = 256;                        // main accumulators at co
 #ifdef CAL_PHASE_TIMING
 #define FSG_TDECL long long ft_last = clock64(); long long ft_acc[16] = {0};
 #define FSG_T(cat) do { const long long t_ = clock64(); ft_acc[cat] += t_ - ft_last; ft_last = t_; } while (0)
-#define FSG_TDUMP(c, base) do { if (blockIdx.x == 0 && threadIdx.x == 0) for (int q_ = 0; q_ < 16; ++q_) (c).status[(base) + q_] = (int)ft_acc[q_]; } while (0)
+#define FSG_TDUMP(c, base) do { if (blockIdx.x == 0 && threadIdx.x == 0) for (int q_ = 0; q_ < 16 && (base) + q_ < 128; ++q_) (c).status[(base) + q_] = (int)ft_acc[q_]; } while (0)
+#define FSG_TVAL(q) ((int)ft_acc[q])
 #else
 #define FSG_TDECL
 #define FSG_T(cat)
 #define FSG_TDUMP(c, base)
+#define FSG_TVAL(q) 0
 #endif
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {

@@ -801,7 +801,8 @@ size_t readout_smem_bytes(int Bm, int H, int cat, int C, int backward) {
   return readout_smem(Bp, H, (cat ? 2 : 1) * (H / kRC), C, backward != 0).total;
 }
 
-// Which readout kernels run: 0 = the fp32 FFMA cluster kernels below, 1 = the streaming tensor-core kernels
+// Which readout kernels run: 3 = the short-chain kernels of the fused small-graph path (head_ro.cu: H = 128, B <= 128,
+// "add", C <= 8; the default there), 0 = the fp32 FFMA cluster kernels below, 1 = the streaming tensor-core kernels
 // (head_tc.cu, B <= 512), 2 = the resident-tile tensor-core kernels (head_tc2.cu: B <= 128, "add", C <= 8).
 // Default: the tensor cores when bf16 operands are requested (cal_model_desc.readout_bf16) or forced
 // (readout_tc, or CAL_READOUT=tc in the environment); otherwise the FFMA kernels -- at B = 128 the readout is
@@ -815,6 +816,7 @@ static int readout_path(const Ctx& c) {
     if (strcmp(e, "tc") == 0) return 1;
     return -1;
   }();
+  if (forced < 0 && readout_ro_supported(c)) return 3;  // fused small-graph path: the short-chain kernels of head_ro.cu
   const bool legacy_fits = readout_smem_bytes(c.Bm, c.H, c.cat, c.C, 1) <= 225 * 1024 &&
                            readout_smem_bytes(c.Bm, c.H, c.cat, c.C, 0) <= 225 * 1024;
   const bool want_tc = forced == 1 || (forced != 0 && (c.readout_bf16 || c.readout_tc)) || !legacy_fits;
@@ -827,6 +829,7 @@ static int readout_path(const Ctx& c) {
 int launch_heads_forward(const Ctx& c, int with_loss, cudaStream_t s) {
   (void)with_loss;
   const int path = readout_path(c);
+  if (path == 3) return launch_readout_ro_forward(c, s);
   if (path != 0) {
     if (!c.fsg_on) {                                   // (the fused small-graph forward pools in its epilogue)
       CAL_DISPATCH_VEC(c.H, { launch_k(k_pool<VEC>, dim3(c.Bm), dim3(256), 0, s, c); });
@@ -849,6 +852,7 @@ int launch_heads_forward(const Ctx& c, int with_loss, cudaStream_t s) {
 
 int launch_heads_backward(const Ctx& c, cudaStream_t s) {
   const int path = readout_path(c);
+  if (path == 3) return launch_readout_ro_backward(c, s);
   if (path != 0) return path == 2 ? launch_readout_tc2_backward(c, s) : launch_readout_tc_backward(c, s);
   CAL_DISPATCH_VEC(c.H, {
     const size_t smem = readout_smem_bytes(c.Bm, c.H, c.cat, c.C, 1);

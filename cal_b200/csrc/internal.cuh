@@ -127,6 +127,9 @@ int launch_heads_backward(const Ctx& c, cudaStream_t s);
 bool readout_tc_supported(const Ctx& c);                                   // tensor-core readout (head_tc.cu)
 int launch_readout_tc_forward(const Ctx& c, cudaStream_t s);
 int launch_readout_tc_backward(const Ctx& c, cudaStream_t s);
+bool readout_ro_supported(const Ctx& c);                                   // short-chain readout of the fused small-graph path (head_ro.cu)
+int launch_readout_ro_forward(const Ctx& c, cudaStream_t s);
+int launch_readout_ro_backward(const Ctx& c, cudaStream_t s);
 int launch_fsg_prep(const Ctx& c, cudaStream_t s);                         // fused small-graph path (fsg.cu)
 int launch_fsg_forward(const Ctx& c, cudaStream_t s);
 size_t fsg_region_bytes(int Bm, int L, int F);

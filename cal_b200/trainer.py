@@ -109,6 +109,32 @@ class GraphStore:
                                                self.edge_dst.data_ptr(), self.y.data_ptr())
         self.desc = d
 
+    @classmethod
+    def from_flat(cls, flat, device):
+        """From ``cal_b200.datasets.FlatGraphs`` (the vectorised generator / TU reader): the flat arrays go to the
+        device as they are -- no per-graph Python objects on the way."""
+        self = cls.__new__(cls)
+        self.device = torch.device(device)
+        self.num_graphs = len(flat)
+        n = (flat.node_ptr[1:] - flat.node_ptr[:-1]).cpu().numpy().astype(np.int64)
+        e = (flat.edge_ptr[1:] - flat.edge_ptr[:-1]).cpu().numpy().astype(np.int64)
+        if n.sum() >= 2 ** 31 or e.sum() >= 2 ** 31:
+            raise _lib.CalError("cal_b200: GraphStore is limited to 2^31 nodes / edge columns")
+        self.node_counts, self.edge_counts = n, e
+        self.F = int(flat.feat.size(1))
+        to = lambda t, dt: t.to(device=self.device, dtype=dt).contiguous()
+        self.node_ptr, self.edge_ptr = to(flat.node_ptr, torch.int32), to(flat.edge_ptr, torch.int32)
+        self.feat = to(flat.feat, torch.float32)
+        self.edge_src, self.edge_dst = to(flat.edge_index[0], torch.int32), to(flat.edge_index[1], torch.int32)
+        self.y = to(flat.y, torch.long)
+        d = _lib.GraphStoreDesc()
+        d.num_graphs, d.num_features = self.num_graphs, self.F
+        d.node_ptr, d.edge_ptr = self.node_ptr.data_ptr(), self.edge_ptr.data_ptr()
+        d.feat, d.edge_src, d.edge_dst, d.y = (self.feat.data_ptr(), self.edge_src.data_ptr(),
+                                               self.edge_dst.data_ptr(), self.y.data_ptr())
+        self.desc = d
+        return self
+
     def caps(self, graphs_per_step, order=None):
         """Capacities covering every step of ``order`` (default: the worst ``graphs_per_step``
         graphs of the dataset, which covers any order)."""

@@ -32,6 +32,9 @@ names_fb = ["dep wait", "structure+records", "dz operand+issue", "dW (FFMA)", "M
             "norm bwd", "all-reduce wait", "att bwd", "transpose aggregate", "MMA", "stats epilogue", "bn bwd rows", "feat bwd"]
 if tr.fused_small_graphs:
     print("k_fsg_backward (CTA 0) cycles:", list(zip(names_fb, st[64:80])), "sum", sum(st[64:80]))
+print("k_ro_fwd (head 0) cycles:", list(zip(["dep wait", "rows+bn1+operand", "fc1 product", "epilogue+bn2", "h1 store+fc2", "softmax+loss"], st[80:86])))
+print("k_ro_bwd (head 0, input-gradient CTA) cycles:", list(zip(["dep wait", "d logits", "fc2/bn2 sums", "d a1 operand", "product", "bn1 bwd + du"], st[112:118])))
+print("k_ro_bwd (head 0, weight-gradient CTA) cycles:", list(zip(["dep wait", "d logits", "fc2/bn2 sums", "slices+issue", "product tail", "dW1 drain"], st[120:126])))
 names_p = ["wait+zero", "edges+counts", "node pass", "scan", "fill", "sort", "write-out"]
 print("k_prep_small structure CTA (slice 0) cycles:", list(zip(names_p, st[96:103])), "sum", sum(st[96:103]))
 print("k_prep_small statistics CTA 0 [column sums, grid sum]:", st[112:114], " finishing CTA:", st[116:118])
