@@ -324,7 +324,9 @@ int cal_causal_forward(const cal_model_desc* m, const cal_caps* caps, const cal_
   stage_range(flags, &lo, &hi);
   for (int st = lo; st <= hi; ++st) {
     if (st == 0) {
-      rc = launch_param_prep(c, s);
+      // (the transposed weight copies of k_param_prep serve the tiled backward and the FFMA readouts; the fused
+      // small-graph path reads the operand images of k_fsg_prep instead -- in training mode it skips the launch)
+      if (!(c.train && c.fsg_bwd_on && readout_runs_ro(c))) rc = launch_param_prep(c, s);
       if (rc == 0 && c.fsg_on) rc = launch_fsg_prep(c, s);
     } else if (c.fsg_on && st >= 1 && st <= 3 + L) {
       // fused small-graph path: stage "feat" runs the whole forward up to the pooled embeddings (fsg.cu)

@@ -80,7 +80,7 @@ __device__ __forceinline__ void fsg_bn_finalize(const Ctx& c, int id, int count,
       rm[k] = (1.f - c.momentum) * rm[k] + c.momentum * (float)mean;
       rv[k] = (1.f - c.momentum) * rv[k] + c.momentum * (float)unb;
     }
-    if (k == 0 && c.nbt != nullptr) c.nbt[id] += 1;
+    if (k == 0 && c.nbt != nullptr) atomicAdd(reinterpret_cast<unsigned long long*>(c.nbt + id), 1ull);   // (RED: no load round trip in front of the barrier)
   }
 }
 
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
           }
         }
       }
-      if (blockIdx.x == 0 && t == 0 && c.nbt != nullptr) c.nbt[0] += 1;
+      if (blockIdx.x == 0 && t == 0 && c.nbt != nullptr) atomicAdd(reinterpret_cast<unsigned long long*>(c.nbt + 0), 1ull);   // (RED: no load round trip in front of the barrier)
     } else {
       for (int k = t; k < F; k += FT) {
         sc[k] = c.bnf(0, BN_SCALE)[k];
@@ -621,10 +621,15 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
 //   blocks [0, n_img): 2048 elements of one operand image each;  block n_img: the plan.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_fsg_prep(const Ctx c, const int n_img_blocks, const int fsg_grid) {
-  pdl_sync();
+  // The image blocks read only parameters: the optimizer step that wrote them is at least two launches back and
+  // complete by the time this kernel can be scheduled, so they do their work BEFORE the dependency wait -- the
+  // images are built while the predecessor (the structure kernel of cal_prep) still runs.  They still wait before
+  // they release the dependent launch: every kernel of the chain relies on "my predecessor has passed its wait,
+  // so everything before it is complete" (the fused forward reads the structure ahead of its own wait).
   const FsgWs ws = fsg_ws(c);
   const int t = threadIdx.x;
   const int L = c.L;
+  if ((int)blockIdx.x >= n_img_blocks) pdl_sync();                      // the plan block reads the structure
   if ((int)blockIdx.x < n_img_blocks) {
     const int img = blockIdx.x >> 3, sub = blockIdx.x & 7;              // 8 blocks of 2048 elements per image
     float* dst;
@@ -660,6 +665,7 @@ __global__ void __launch_bounds__(256) k_fsg_prep(const Ctx c, const int n_img_b
       dst[e] = hi;
       dst[kFsgImgPart + e] = lo;
     }
+    pdl_sync();
     return;
   }
   // ---- the plan: one block per graph (thread g describes block g); ok = every graph within the limits ----

@@ -121,15 +121,14 @@ __device__ __forceinline__ void build_dw_operands(unsigned char* wbuf, const flo
 __device__ __forceinline__ void issue_dw(const unsigned char* wbuf, uint32_t d, int npad) {
   const uint32_t idesc = umma::instr_desc(umma::kFmtTF32, 128, 128);
   const uint32_t base = umma::smem_addr(wbuf);
+  uint64_t ph = umma::smem_desc(base, kALbo, kASbo), pl = umma::smem_desc(base + kOpT, kALbo, kASbo);
+  uint64_t qh = umma::smem_desc(base + 2 * kOpT, kALbo, kASbo), ql = umma::smem_desc(base + 3 * kOpT, kALbo, kASbo);
+  constexpr uint64_t dd = (2u * kALbo) >> 4;
   for (int s = 0; s < npad / 8; ++s) {
-    const uint32_t o = (uint32_t)s * 2u * kALbo;
-    const uint64_t ph = umma::smem_desc(base + o, kALbo, kASbo);
-    const uint64_t pl = umma::smem_desc(base + kOpT + o, kALbo, kASbo);
-    const uint64_t qh = umma::smem_desc(base + 2 * kOpT + o, kALbo, kASbo);
-    const uint64_t ql = umma::smem_desc(base + 3 * kOpT + o, kALbo, kASbo);
     umma::mma_tf32(d, pl, qh, idesc, s > 0);
     umma::mma_tf32(d, ph, ql, idesc, 1u);
     umma::mma_tf32(d, ph, qh, idesc, 1u);
+    ph += dd; pl += dd; qh += dd; ql += dd;
   }
 }
 // all 8 warps: dW from TMEM -> dst [128][128].  A thread holds a ROW of the accumulator (lane = row), so a direct store
@@ -699,18 +698,23 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
         umma::mbar_wait(&bar_w, par_w);
         umma::fence_after_sync();
         const uint32_t idesc = umma::instr_desc(umma::kFmtTF32, 128, npad);
-        const uint32_t aH = umma::smem_addr(sAh), aL = umma::smem_addr(sAl), bH = umma::smem_addr(sBh), bL = umma::smem_addr(sBl);
+        constexpr uint64_t da = (2u * kALbo) >> 4, db = (2u * kBLbo) >> 4;      // descriptor step: start-address field only
+        uint64_t ah = umma::smem_desc(umma::smem_addr(sAh), kALbo, kASbo), al = umma::smem_desc(umma::smem_addr(sAl), kALbo, kASbo);
+        uint64_t bh = umma::smem_desc(umma::smem_addr(sBh), kBLbo, kBSbo), bl = umma::smem_desc(umma::smem_addr(sBl), kBLbo, kBSbo);
+        const uint64_t bh0 = bh;
         // the two products of the hi image first, the product of the lo image last: its tail is still landing
+#pragma unroll 4
         for (int s = 0; s < FH / 8; ++s) {
-          const uint32_t aa = (uint32_t)s * 2u * kALbo, ba = (uint32_t)s * 2u * kBLbo;
-          const uint64_t ah = umma::smem_desc(aH + aa, kALbo, kASbo);
-          umma::mma_tf32(tmem, ah, umma::smem_desc(bH + ba, kBLbo, kBSbo), idesc, s > 0);
-          umma::mma_tf32(tmem + 128u, ah, umma::smem_desc(bL + ba, kBLbo, kBSbo), idesc, s > 0);
+          umma::mma_tf32(tmem, ah, bh, idesc, s > 0);
+          umma::mma_tf32(tmem + 128u, ah, bl, idesc, s > 0);
+          ah += da; bh += db; bl += db;
         }
+        bh = bh0;
+#pragma unroll 4
         for (int s = 0; s < FH / 8; ++s) {
           if (s == kTailStep) umma::mbar_wait(&bar_w2, par_w2);
-          const uint32_t aa = (uint32_t)s * 2u * kALbo, ba = (uint32_t)s * 2u * kBLbo;
-          umma::mma_tf32(tmem + 128u, umma::smem_desc(aL + aa, kALbo, kASbo), umma::smem_desc(bH + ba, kBLbo, kBSbo), idesc, 1u);
+          umma::mma_tf32(tmem + 128u, al, bh, idesc, 1u);
+          al += da; bh += db;
         }
         umma::commit(&bar_mma);
       }

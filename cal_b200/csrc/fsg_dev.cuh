@@ -182,15 +182,18 @@ __device__ __forceinline__ void put_b(unsigned char* b_hi, unsigned char* b_lo, 
 __device__ __forceinline__ void issue_3xtf32(const unsigned char* a_hi, const unsigned char* a_lo, const unsigned char* b_hi,
                                              const unsigned char* b_lo, uint32_t d_main, uint32_t d_corr, int ksteps, int npad) {
   const uint32_t idesc = umma::instr_desc(umma::kFmtTF32, 128, npad);
+  // the descriptors of step s differ from those of step 0 only in the start-address field (bits [0, 14) = byte address
+  // >> 4; shared memory is < 256 KB, so the sum never carries out of the field): one 64-bit add per operand per step
+  // instead of rebuilding four descriptors -- the issue loop, not the tensor pipe, bounds these small products
+  uint64_t ah = umma::smem_desc(umma::smem_addr(a_hi), kALbo, kASbo), al = umma::smem_desc(umma::smem_addr(a_lo), kALbo, kASbo);
+  uint64_t bh = umma::smem_desc(umma::smem_addr(b_hi), kBLbo, kBSbo), bl = umma::smem_desc(umma::smem_addr(b_lo), kBLbo, kBSbo);
+  constexpr uint64_t da = (2u * kALbo) >> 4, db = (2u * kBLbo) >> 4;
+#pragma unroll 4
   for (int s = 0; s < ksteps; ++s) {
-    const uint32_t aa = (uint32_t)s * 2u * kALbo, ba = (uint32_t)s * 2u * kBLbo;
-    const uint64_t ah = umma::smem_desc(umma::smem_addr(a_hi) + aa, kALbo, kASbo);
-    const uint64_t al = umma::smem_desc(umma::smem_addr(a_lo) + aa, kALbo, kASbo);
-    const uint64_t bh = umma::smem_desc(umma::smem_addr(b_hi) + ba, kBLbo, kBSbo);
-    const uint64_t bl = umma::smem_desc(umma::smem_addr(b_lo) + ba, kBLbo, kBSbo);
     umma::mma_tf32(d_corr, al, bh, idesc, s > 0);
     umma::mma_tf32(d_corr, ah, bl, idesc, 1u);
     umma::mma_tf32(d_main, ah, bh, idesc, s > 0);
+    ah += da; al += da; bh += db; bl += db;
   }
 }
 

@@ -826,6 +826,8 @@ static int readout_path(const Ctx& c) {
   return 0;
 }
 
+bool readout_runs_ro(const Ctx& c) { return readout_path(c) == 3; }
+
 int launch_heads_forward(const Ctx& c, int with_loss, cudaStream_t s) {
   (void)with_loss;
   const int path = readout_path(c);

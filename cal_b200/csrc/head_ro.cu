@@ -40,18 +40,19 @@ __device__ __forceinline__ void ro_gemm_image(unsigned char* ring, const float* 
                                               int npad) {
   const uint32_t idesc = umma::instr_desc(umma::kFmtTF32, 128, npad);
   const uint32_t yh = umma::smem_addr(y_hi), yl = umma::smem_addr(y_lo);
+  constexpr uint64_t da = (2u * kALbo) >> 4, db = (2u * kYLbo) >> 4;       // descriptor step: start-address field only
   auto slice_mmas = [&](int s) {
     const uint32_t st = umma::smem_addr(ring + (s & 1) * kStage);
+    uint64_t ah = umma::smem_desc(st, kALbo, kASbo), al = umma::smem_desc(st + 16384u, kALbo, kASbo);
+    uint64_t bh = umma::smem_desc(yh + (uint32_t)(s * 4) * 2u * kYLbo, kYLbo, kYSbo);
+    uint64_t bl = umma::smem_desc(yl + (uint32_t)(s * 4) * 2u * kYLbo, kYLbo, kYSbo);
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      const int gk = s * 4 + ks;
-      const uint64_t ah = umma::smem_desc(st + (uint32_t)ks * 2u * kALbo, kALbo, kASbo);
-      const uint64_t al = umma::smem_desc(st + 16384u + (uint32_t)ks * 2u * kALbo, kALbo, kASbo);
-      const uint64_t bh = umma::smem_desc(yh + (uint32_t)gk * 2u * kYLbo, kYLbo, kYSbo);
-      const uint64_t bl = umma::smem_desc(yl + (uint32_t)gk * 2u * kYLbo, kYLbo, kYSbo);
-      umma::mma_tf32(d_main, ah, bh, idesc, gk > 0);
-      umma::mma_tf32(d_corr, ah, bl, idesc, gk > 0);
+      const uint32_t acc = (s * 4 + ks) > 0 ? 1u : 0u;
+      umma::mma_tf32(d_main, ah, bh, idesc, acc);
+      umma::mma_tf32(d_corr, ah, bl, idesc, acc);
       umma::mma_tf32(d_corr, al, bh, idesc, 1u);
+      ah += da; al += da; bh += db; bl += db;
     }
   };
   umma::mbar_wait(&bar_full[0], 0);
@@ -112,6 +113,8 @@ __host__ __device__ inline RoFSmem ro_fsmem() {
   return s;
 }
 
+// CC: number of classes when it is 2, 3 or 4 (loops over the classes unrolled without predicates), 8 = generic (C <= 8)
+template <int CC>
 __global__ void __launch_bounds__(RT, 1) k_ro_fwd(const Ctx c) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t bar_full[2], bar_empty[2], bar_mma;
@@ -161,6 +164,8 @@ __global__ void __launch_bounds__(RT, 1) k_ro_fwd(const Ctx c) {
     }
   }
   for (int i = t; i < C * FH; i += RT) sW2[(i >> 7) * kLdT + (i & 127)] = c.params[c.po.fc2_w[h] + i];
+  float* sB2raw = sRed + 48;                              // [C] fc2 bias
+  if (t < C) sB2raw[t] = c.params[c.po.fc2_b[h] + t];
   const int B = ro_clampB(c);
   if (t < kRoB) sPerm[t] = t < B ? c.perm[t] : 0;         // (cal_prep's output: complete before the predecessor started)
   umma::fence_before_sync();
@@ -186,49 +191,66 @@ __global__ void __launch_bounds__(RT, 1) k_ro_fwd(const Ctx c) {
   float* sh2 = sVec + 3 * FH;
   const float* b1 = sVec + 4 * FH;
   if (c.train) {
-    double s[4] = {0.0, 0.0, 0.0, 0.0}, qq[4] = {0.0, 0.0, 0.0, 0.0};
+    // per thread: mean and centred sum of squares of its <= 8 rows (fp32: 8 terms, no cancellation), combined over the
+    // 16 row groups in fp64 (Chan et al.): as accurate as fp64 accumulation at a fraction of the instructions
+    const int cnt = imin(imax(B - g * 8, 0), 8);
+    float* sMean = reinterpret_cast<float*>(sStat);       // [16][128]
+    float* sM2 = sMean + 16 * FH;
+    {
+      float m[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      s[0] += (double)u[i].x; s[1] += (double)u[i].y; s[2] += (double)u[i].z; s[3] += (double)u[i].w;
-      qq[0] += (double)u[i].x * (double)u[i].x; qq[1] += (double)u[i].y * (double)u[i].y;
-      qq[2] += (double)u[i].z * (double)u[i].z; qq[3] += (double)u[i].w * (double)u[i].w;
-    }
+      for (int i = 0; i < 8; ++i) {                        // rows >= B hold zeros
+        m[0] += u[i].x; m[1] += u[i].y; m[2] += u[i].z; m[3] += u[i].w;
+      }
+      const float inv = cnt > 0 ? 1.f / (float)cnt : 0.f;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      sStat[g * FH + q * 4 + e] = s[e];
-      sStat[16 * FH + g * FH + q * 4 + e] = qq[e];
+      for (int e = 0; e < 4; ++e) m[e] *= inv;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < cnt) {
+          const float d0 = u[i].x - m[0], d1 = u[i].y - m[1], d2 = u[i].z - m[2], d3 = u[i].w - m[3];
+          m2[0] = fmaf(d0, d0, m2[0]); m2[1] = fmaf(d1, d1, m2[1]); m2[2] = fmaf(d2, d2, m2[2]); m2[3] = fmaf(d3, d3, m2[3]);
+        }
+      *reinterpret_cast<float4*>(sMean + g * FH + q * 4) = make_float4(m[0], m[1], m[2], m[3]);
+      *reinterpret_cast<float4*>(sM2 + g * FH + q * 4) = make_float4(m2[0], m2[1], m2[2], m2[3]);
     }
     __syncthreads();
+    FSG_T(6);                                            // 6: input rows loaded + per-thread statistics
     if (t < FH) {
-      double a = 0.0, b = 0.0;
+      // Chan combination of the 16 groups, fp32: every term is a mean or a centred sum of squares (no cancellation)
+      float a = 0.f;
+#pragma unroll
+      for (int gg = 0; gg < 16; ++gg) a = fmaf((float)imin(imax(B - gg * 8, 0), 8), sMean[gg * FH + t], a);
+      const float invB = B > 0 ? 1.f / (float)B : 0.f;
+      const float mean = a * invB;
+      float b = 0.f;
 #pragma unroll
       for (int gg = 0; gg < 16; ++gg) {
-        a += sStat[gg * FH + t];
-        b += sStat[16 * FH + gg * FH + t];
+        const float dm = sMean[gg * FH + t] - mean;
+        b += sM2[gg * FH + t] + (float)imin(imax(B - gg * 8, 0), 8) * dm * dm;
       }
-      const double mean = B > 0 ? a / B : 0.0;
-      double var = B > 0 ? b / B - mean * mean : 0.0;
-      if (var < 0.0) var = 0.0;
-      const float rstd = (float)(1.0 / sqrt(var + (double)c.eps));
-      const float sc = g1 * rstd, sh = be1 - (float)mean * sc;
+      const float var = b * invB;
+      const float rstd = 1.0f / sqrtf(var + c.eps);
+      const float sc = g1 * rstd, sh = be1 - mean * sc;
       sc1[t] = sc;
       sh1[t] = sh;
       c.bnf(bn1, BN_SCALE)[t] = sc;
       c.bnf(bn1, BN_SHIFT)[t] = sh;
-      c.bnf(bn1, BN_MEAN)[t] = (float)mean;
+      c.bnf(bn1, BN_MEAN)[t] = mean;
       c.bnf(bn1, BN_RSTD)[t] = rstd;
       if (c.bn_buffers != nullptr && c.bn_rm[bn1] >= 0) {
-        const double unb = B > 1 ? var * ((double)B / (double)(B - 1)) : var;
-        c.bn_buffers[c.bn_rm[bn1] + t] = (1.f - c.momentum) * rm1 + c.momentum * (float)mean;
-        c.bn_buffers[c.bn_rv[bn1] + t] = (1.f - c.momentum) * rv1 + c.momentum * (float)unb;
+        const float unb = B > 1 ? b / (float)(B - 1) : var;
+        c.bn_buffers[c.bn_rm[bn1] + t] = (1.f - c.momentum) * rm1 + c.momentum * mean;
+        c.bn_buffers[c.bn_rv[bn1] + t] = (1.f - c.momentum) * rv1 + c.momentum * unb;
       }
-      if (t == 0 && c.nbt != nullptr) c.nbt[bn1] += 1;
+      if (t == 0 && c.nbt != nullptr) atomicAdd(reinterpret_cast<unsigned long long*>(c.nbt + bn1), 1ull);   // (RED: no load round trip in front of the barrier)
     }
   } else if (t < FH) {
     sc1[t] = c.bnf(bn1, BN_SCALE)[t];
     sh1[t] = c.bnf(bn1, BN_SHIFT)[t];
   }
   __syncthreads();
+  FSG_T(7);                                              // 7: bn1 finalisation
   {
     const float4 sc = *reinterpret_cast<const float4*>(sc1 + q * 4), sh = *reinterpret_cast<const float4*>(sh1 + q * 4);
 #pragma unroll
@@ -262,12 +284,15 @@ __global__ void __launch_bounds__(RT, 1) k_ro_fwd(const Ctx c) {
   FSG_T(2);                                              // 2: fc1 product
 
   // ---- C: epilogue: h1 = relu(a1 + b1) -> tile [graph][channel]; bn2 sums (thread = channel, 4 column groups) ----
-  double* sSt2 = reinterpret_cast<double*>(sRing);      // [2][4][128] (the ring is idle)
+  float* sSt2 = reinterpret_cast<float*>(sRing);        // [2][4][128]: mean | centred sum of squares per column group (the ring is idle)
   {
     const int j = (warp & 3) * 32 + lane, cg = warp >> 2, c0 = cg * 32;
-    double s = 0.0, qq = 0.0;
+    const int cnt = imin(imax(B - c0, 0), 32);
+    float v[32];
+    float m = 0.f, m2 = 0.f;
     if (c0 < npad) {
       const float bj = b1[j];
+      float* H1 = c.H1 + (size_t)h * c.Bm * FH;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         float vm[16], vc[16];
@@ -276,41 +301,54 @@ __global__ void __launch_bounds__(RT, 1) k_ro_fwd(const Ctx c) {
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const int b = c0 + hh * 16 + e;
+          const float x = b < B ? fmaxf((vm[e] + vc[e]) + bj, 0.f) : 0.f;
+          v[hh * 16 + e] = x;
           if (b < B) {
-            const float v = fmaxf((vm[e] + vc[e]) + bj, 0.f);
-            sT[b * kLdT + j] = v;
-            s += (double)v;
-            qq += (double)v * (double)v;
+            sT[b * kLdT + j] = x;
+            H1[(size_t)b * FH + j] = x;                    // the backward reads h1 from the workspace
+            m += x;
           }
         }
       }
+      m *= cnt > 0 ? 1.f / (float)cnt : 0.f;
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        if (e < cnt) m2 = fmaf(v[e] - m, v[e] - m, m2);
     }
-    sSt2[cg * FH + j] = s;
-    sSt2[4 * FH + cg * FH + j] = qq;
+    sSt2[cg * FH + j] = m;
+    sSt2[4 * FH + cg * FH + j] = m2;
   }
   umma::fence_before_sync();
   __syncthreads();
+  FSG_T(8);                                              // 8: TMEM epilogue (h1 tile, bn2 partial statistics)
   if (c.train) {
     if (t < FH) {
-      const double a = (sSt2[t] + sSt2[FH + t]) + (sSt2[2 * FH + t] + sSt2[3 * FH + t]);
-      const double b = (sSt2[4 * FH + t] + sSt2[5 * FH + t]) + (sSt2[6 * FH + t] + sSt2[7 * FH + t]);
-      const double mean = B > 0 ? a / B : 0.0;
-      double var = B > 0 ? b / B - mean * mean : 0.0;
-      if (var < 0.0) var = 0.0;
-      const float rstd = (float)(1.0 / sqrt(var + (double)c.eps));
-      const float sc = g2 * rstd, sh = be2 - (float)mean * sc;
+      float a = 0.f;
+#pragma unroll
+      for (int cg = 0; cg < 4; ++cg) a = fmaf((float)imin(imax(B - cg * 32, 0), 32), sSt2[cg * FH + t], a);
+      const float invB = B > 0 ? 1.f / (float)B : 0.f;
+      const float mean = a * invB;
+      float b = 0.f;
+#pragma unroll
+      for (int cg = 0; cg < 4; ++cg) {
+        const float dm = sSt2[cg * FH + t] - mean;
+        b += sSt2[4 * FH + cg * FH + t] + (float)imin(imax(B - cg * 32, 0), 32) * dm * dm;
+      }
+      const float var = b * invB;
+      const float rstd = 1.0f / sqrtf(var + c.eps);
+      const float sc = g2 * rstd, sh = be2 - mean * sc;
       sc2[t] = sc;
       sh2[t] = sh;
       c.bnf(bn2, BN_SCALE)[t] = sc;
       c.bnf(bn2, BN_SHIFT)[t] = sh;
-      c.bnf(bn2, BN_MEAN)[t] = (float)mean;
+      c.bnf(bn2, BN_MEAN)[t] = mean;
       c.bnf(bn2, BN_RSTD)[t] = rstd;
       if (c.bn_buffers != nullptr && c.bn_rm[bn2] >= 0) {
-        const double unb = B > 1 ? var * ((double)B / (double)(B - 1)) : var;
-        c.bn_buffers[c.bn_rm[bn2] + t] = (1.f - c.momentum) * rm2 + c.momentum * (float)mean;
-        c.bn_buffers[c.bn_rv[bn2] + t] = (1.f - c.momentum) * rv2 + c.momentum * (float)unb;
+        const float unb = B > 1 ? b / (float)(B - 1) : var;
+        c.bn_buffers[c.bn_rm[bn2] + t] = (1.f - c.momentum) * rm2 + c.momentum * mean;
+        c.bn_buffers[c.bn_rv[bn2] + t] = (1.f - c.momentum) * rv2 + c.momentum * unb;
       }
-      if (t == 0 && c.nbt != nullptr) c.nbt[bn2] += 1;
+      if (t == 0 && c.nbt != nullptr) atomicAdd(reinterpret_cast<unsigned long long*>(c.nbt + bn2), 1ull);   // (RED: no load round trip in front of the barrier)
     }
   } else if (t < FH) {
     sc2[t] = c.bnf(bn2, BN_SCALE)[t];
@@ -319,29 +357,40 @@ __global__ void __launch_bounds__(RT, 1) k_ro_fwd(const Ctx c) {
   __syncthreads();
   FSG_T(3);                                              // 3: epilogue + bn2
 
-  // ---- D: h1 to the workspace (the backward reads it); fc2: thread per (graph, class) ----
+  // ---- D: h1 to the workspace (the backward reads it); fc2 with bn2 folded into its weights:
+  //      logits[b][cls] = sum_k h1[b][k] (sc2[k] W2[cls][k]) + (b2[cls] + sum_k sh2[k] W2[cls][k]); thread per (graph, class) ----
   {
-    float4* H1 = reinterpret_cast<float4*>(c.H1 + (size_t)h * c.Bm * FH);
-    for (int i = t; i < B * (FH / 4); i += RT) {
-      const int b = i >> 5, qd = i & 31;
-      H1[(size_t)b * (FH / 4) + qd] = *reinterpret_cast<const float4*>(sT + b * kLdT + qd * 4);
+    float* sB2 = sRed + 32;                               // [C] folded bias
+    if (warp < C) {                                        // warp cls: the folded bias from the raw weights
+      float a = 0.f;
+#pragma unroll
+      for (int k = lane; k < FH; k += 32) a = fmaf(sh2[k], sW2[warp * kLdT + k], a);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) sB2[warp] = a + sB2raw[warp];
     }
-  }
-  for (int i = t; i < B * C; i += RT) {
-    const int b = i / C, cls = i - b * C;
-    const float* hr = sT + b * kLdT;
-    const float* wr = sW2 + cls * kLdT;
-    float s0 = 0.f, s1 = 0.f;
-#pragma unroll 4
-    for (int k = 0; k < FH; k += 4) {
-      const float4 hv = *reinterpret_cast<const float4*>(hr + k), wv = *reinterpret_cast<const float4*>(wr + k);
-      const float4 sc = *reinterpret_cast<const float4*>(sc2 + k), sh = *reinterpret_cast<const float4*>(sh2 + k);
-      s0 = fmaf(fmaf(hv.x, sc.x, sh.x), wv.x, s0);
-      s1 = fmaf(fmaf(hv.y, sc.y, sh.y), wv.y, s1);
-      s0 = fmaf(fmaf(hv.z, sc.z, sh.z), wv.z, s0);
-      s1 = fmaf(fmaf(hv.w, sc.w, sh.w), wv.w, s1);
+    __syncthreads();
+    for (int i = t; i < C * FH; i += RT) {
+      const int cls = i >> 7, k = i & 127;
+      sW2[cls * kLdT + k] *= sc2[k];
     }
-    sLg[i] = (s0 + s1) + c.params[c.po.fc2_b[h] + cls];
+    __syncthreads();
+    FSG_T(9);                                            // 9: weight fold + h1 store
+    for (int i = t; i < B * C; i += RT) {
+      const int b = i / C, cls = i - b * C;
+      const float* hr = sT + b * kLdT;
+      const float* wr = sW2 + cls * kLdT;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < FH; k += 4) {
+        const float4 hv = *reinterpret_cast<const float4*>(hr + k), wv = *reinterpret_cast<const float4*>(wr + k);
+        s0 = fmaf(hv.x, wv.x, s0);
+        s1 = fmaf(hv.y, wv.y, s1);
+        s2 = fmaf(hv.z, wv.z, s2);
+        s3 = fmaf(hv.w, wv.w, s3);
+      }
+      sLg[i] = ((s0 + s1) + (s2 + s3)) + sB2[cls];
+    }
   }
   __syncthreads();
   FSG_T(4);                                              // 4: h1 store + fc2
@@ -352,24 +401,30 @@ __global__ void __launch_bounds__(RT, 1) k_ro_fwd(const Ctx c) {
     const int b = t;
     float m = -INFINITY;
     int am = 0;
-    for (int cls = 0; cls < C; ++cls) {
-      const float v = sLg[b * C + cls];
-      if (v > m) {
-        m = v;
+    float lg[CC];
+#pragma unroll
+    for (int cls = 0; cls < CC; ++cls) {
+      lg[cls] = cls < C ? sLg[b * C + cls] : -INFINITY;
+      if (lg[cls] > m) {
+        m = lg[cls];
         am = cls;
       }
     }
     float se = 0.f;
-    for (int cls = 0; cls < C; ++cls) se += expf(sLg[b * C + cls] - m);
+#pragma unroll
+    for (int cls = 0; cls < CC; ++cls)
+      if (cls < C) se += expf(lg[cls] - m);
     const float lse = logf(se);
     const long long yb = (c.with_loss && c.y != nullptr) ? c.y[b] : -1;
     float slp = 0.f, picked = 0.f;
-    for (int cls = 0; cls < C; ++cls) {
-      const float lp = sLg[b * C + cls] - m - lse;
-      c.logp[((size_t)h * c.Bm + b) * C + cls] = lp;
-      slp += lp;
-      if ((long long)cls == yb) picked = lp;
-    }
+#pragma unroll
+    for (int cls = 0; cls < CC; ++cls)
+      if (cls < C) {
+        const float lp = lg[cls] - m - lse;
+        c.logp[((size_t)h * c.Bm + b) * C + cls] = lp;
+        slp += lp;
+        if ((long long)cls == yb) picked = lp;
+      }
     if (c.with_loss) {
       loss_part = h == 0 ? -logf((float)C) - slp / (float)C : -picked;   // KL(uniform || .) row / NLL row
       correct_part = (long long)am == yb ? 1.f : 0.f;
@@ -395,6 +450,7 @@ __global__ void __launch_bounds__(RT, 1) k_ro_fwd(const Ctx c) {
       c.loss[1 + h] = B > 0 ? ls / (float)B : 0.f;
       c.loss[4 + h] = cs;
     }
+    FSG_T(10);                                           // 10: log-softmax + loss parts
     if (grid_last_block(&c.counters[CNT_HEAD2], 3)) {
       if (t == 0) {
         const volatile float* lv = c.loss;
@@ -432,6 +488,7 @@ __host__ __device__ inline RoBSmem ro_bsmem() {
 }
 static_assert(2 * kYPart >= 131072 + 2 * 4 * FH * 8, "the fp64 partial sums fit behind the weight-gradient stages");
 
+template <int CC>
 __global__ void __launch_bounds__(RT, 1) k_ro_bwd(const Ctx c) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t bar_full[2], bar_empty[2], bar_mma;
@@ -484,9 +541,9 @@ __global__ void __launch_bounds__(RT, 1) k_ro_bwd(const Ctx c) {
   if (t < B) {
     const int b = t;
     const long long yb = c.y != nullptr ? c.y[b] : -1;
-    float dlp[kMaxC], sd = 0.f;
+    float dlp[CC], sd = 0.f;
 #pragma unroll
-    for (int cls = 0; cls < kMaxC; ++cls) {
+    for (int cls = 0; cls < CC; ++cls) {
       dlp[cls] = 0.f;
       if (cls < C) {
         if (c.grad_logp != nullptr) dlp[cls] = c.grad_logp[((size_t)h * B + b) * C + cls];
@@ -496,7 +553,7 @@ __global__ void __launch_bounds__(RT, 1) k_ro_bwd(const Ctx c) {
       }
     }
 #pragma unroll
-    for (int cls = 0; cls < kMaxC; ++cls)
+    for (int cls = 0; cls < CC; ++cls)
       if (cls < C) sDl[b * C + cls] = dlp[cls] - expf(c.logp[((size_t)h * c.Bm + b) * C + cls]) * sd;
   }
   if (t < FH) {
@@ -511,57 +568,58 @@ __global__ void __launch_bounds__(RT, 1) k_ro_bwd(const Ctx c) {
     v1[2 * FH + k] = c.bnf(bn1, BN_MEAN)[k];
     v1[3 * FH + k] = c.bnf(bn1, BN_RSTD)[k];
   }
-  __syncthreads();
-  FSG_T(1);                                              // 1: d logits, records
-
-  // ---- fc2 / bn2 backward sums: thread = (hidden channel j, row part): d y2 = dl W2, sum d y2, sum d y2 * hhat,
-  //      and d W2[cls][j] = sum_b dl[b][cls] * y2[b][j] ----
+  // thread = (hidden channel j, row part p): the 32 CONSECUTIVE graph rows 32 p .. 32 p + 31 of channel j stay in
+  // registers from here to the operand build (no second pass over memory, no recomputation)
   const int j = t & 127, part = t >> 7;
   const float* H1 = c.H1 + (size_t)h * c.Bm * FH;
-  float w2c[kMaxC];
+  float hv[32], dy[32];
 #pragma unroll
-  for (int cls = 0; cls < kMaxC; ++cls) w2c[cls] = cls < C ? sW2[cls * FH + j] : 0.f;
+  for (int i = 0; i < 32; ++i) {
+    const int b = 32 * part + i;
+    hv[i] = b < B ? __ldcg(H1 + (size_t)b * FH + j) : 0.f;
+  }
+  float w2c[CC];
+#pragma unroll
+  for (int cls = 0; cls < CC; ++cls) w2c[cls] = cls < C ? sW2[cls * FH + j] : 0.f;
+  __syncthreads();
+  FSG_T(1);                                              // 1: d logits, records, h1 rows
+
+  // ---- fc2 / bn2 backward sums: d y2 = dl W2, sum d y2, sum d y2 * hhat (fp32 over the thread's 32 rows, fp64 over the
+  //      4 parts), and d W2[cls][j] = sum_b dl[b][cls] * y2[b][j] ----
   const float sc2 = v2[j], sh2 = v2[FH + j], mu2 = v2[2 * FH + j], rs2 = v2[3 * FH + j];
+  float* sStF = reinterpret_cast<float*>(sSt);            // [2][4][128]
   {
-    double s = 0.0, qq = 0.0;
-    float dw[kMaxC];
+    float s = 0.f, qq = 0.f, dw[CC];
 #pragma unroll
-    for (int cls = 0; cls < kMaxC; ++cls) dw[cls] = 0.f;
-    for (int b0 = part; b0 < B; b0 += 32) {              // 8 rows per batch of loads
-      float hv[8];
+    for (int cls = 0; cls < CC; ++cls) dw[cls] = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int b = b0 + 4 * i;
-        hv[i] = b < B ? __ldcg(H1 + (size_t)b * FH + j) : 0.f;
+    for (int i = 0; i < 32; ++i) {
+      const int b = 32 * part + i;
+      float d = 0.f;
+      if (b < B) {
+        const float y2 = fmaf(hv[i], sc2, sh2);
+#pragma unroll
+        for (int cls = 0; cls < CC; ++cls)
+          if (cls < C) {
+            const float dl = sDl[b * C + cls];
+            d = fmaf(dl, w2c[cls], d);
+            dw[cls] = fmaf(dl, y2, dw[cls]);
+          }
+        s += d;
+        qq = fmaf(d, (hv[i] - mu2) * rs2, qq);
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int b = b0 + 4 * i;
-        if (b < B) {
-          const float y2 = fmaf(hv[i], sc2, sh2), hh = (hv[i] - mu2) * rs2;
-          float dy = 0.f;
-#pragma unroll
-          for (int cls = 0; cls < kMaxC; ++cls)
-            if (cls < C) {
-              const float d = sDl[b * C + cls];
-              dy = fmaf(d, w2c[cls], dy);
-              dw[cls] = fmaf(d, y2, dw[cls]);
-            }
-          s += (double)dy;
-          qq += (double)dy * (double)hh;
-        }
-      }
+      dy[i] = d;
     }
-    sSt[part * FH + j] = s;
-    sSt[4 * FH + part * FH + j] = qq;
+    sStF[part * FH + j] = s;
+    sStF[4 * FH + part * FH + j] = qq;
 #pragma unroll
-    for (int cls = 0; cls < kMaxC; ++cls)
+    for (int cls = 0; cls < CC; ++cls)
       if (cls < C) sDw2[(part * kMaxC + cls) * FH + j] = dw[cls];
   }
   __syncthreads();
   if (t < FH) {
-    const double a = (sSt[t] + sSt[FH + t]) + (sSt[2 * FH + t] + sSt[3 * FH + t]);
-    const double b = (sSt[4 * FH + t] + sSt[5 * FH + t]) + (sSt[6 * FH + t] + sSt[7 * FH + t]);
+    const double a = ((double)sStF[t] + (double)sStF[FH + t]) + ((double)sStF[2 * FH + t] + (double)sStF[3 * FH + t]);
+    const double b = ((double)sStF[4 * FH + t] + (double)sStF[5 * FH + t]) + ((double)sStF[6 * FH + t] + (double)sStF[7 * FH + t]);
     const double inv = B > 0 ? 1.0 / B : 0.0;
     v2[4 * FH + t] = (float)(a * inv);
     v2[5 * FH + t] = (float)(b * inv);
@@ -578,47 +636,39 @@ __global__ void __launch_bounds__(RT, 1) k_ro_bwd(const Ctx c) {
       c.grads[c.po.fc2_w[h] + i] = (sDw2[(0 * kMaxC + cls) * FH + k] + sDw2[(1 * kMaxC + cls) * FH + k]) +
                                    (sDw2[(2 * kMaxC + cls) * FH + k] + sDw2[(3 * kMaxC + cls) * FH + k]);
     }
-    if (t < C) {
-      float s = 0.f;
-      for (int b = 0; b < B; ++b) s += sDl[b * C + t];
-      c.grads[c.po.fc2_b[h] + t] = s;
+    if (warp < C) {                                      // warp cls: d b2[cls] = sum_b dl[b][cls]
+      float a = 0.f;
+      for (int b = lane; b < B; b += 32) a += sDl[b * C + warp];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) c.grads[c.po.fc2_b[h] + warp] = a;
     }
   }
   __syncthreads();
   FSG_T(2);                                              // 2: fc2 / bn2 backward sums
-  const float c1 = v2[4 * FH + j], c2 = v2[5 * FH + j];
-  // d a1[b][j] = relu'(h1) * bn2'(d y2)
-  auto da1 = [&](int b, float hval) -> float {
-    float dy = 0.f;
+  {
+    // d a1[b][j] = relu'(h1) * bn2'(d y2), in place of d y2
+    const float c1 = v2[4 * FH + j], c2 = v2[5 * FH + j];
 #pragma unroll
-    for (int cls = 0; cls < kMaxC; ++cls)
-      if (cls < C) dy = fmaf(sDl[b * C + cls], w2c[cls], dy);
-    const float hh = (hval - mu2) * rs2;
-    return hval > 0.f ? sc2 * (dy - c1 - hh * c2) : 0.f;
-  };
+    for (int i = 0; i < 32; ++i) {
+      const float hh = (hv[i] - mu2) * rs2;
+      dy[i] = (hv[i] > 0.f && 32 * part + i < B) ? sc2 * (dy[i] - c1 - hh * c2) : 0.f;
+    }
+  }
 
   if (role == 0) {
     // ================= input gradient: d y1^T [in channel][graph] = W1^T d a1^T =================
     unsigned char* sYh = sOp;
     unsigned char* sYl = sOp + kYPart;
-    for (int b0 = part; b0 < npad; b0 += 32) {
-      float hv[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int b = b0 + 4 * i;
-        hv[i] = b < B ? __ldcg(H1 + (size_t)b * FH + j) : 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int b = b0 + 4 * i;
-        if (b < npad) {
-          const float v = b < B ? da1(b, hv[i]) : 0.f;
-          float hi, lo;
-          umma::split_tf32(v, hi, lo);
-          const uint32_t off = y_off(b, j >> 2) + (uint32_t)(j & 3) * 4u;
-          *reinterpret_cast<float*>(sYh + off) = hi;
-          *reinterpret_cast<float*>(sYl + off) = lo;
-        }
+    for (int i = 0; i < 32; ++i) {
+      const int b = 32 * part + i;
+      if (b < npad) {
+        float hi, lo;
+        umma::split_tf32(dy[i], hi, lo);
+        const uint32_t off = y_off(b, j >> 2) + (uint32_t)(j & 3) * 4u;
+        *reinterpret_cast<float*>(sYh + off) = hi;
+        *reinterpret_cast<float*>(sYl + off) = lo;
       }
     }
     umma::fence_async_smem();
@@ -641,8 +691,7 @@ __global__ void __launch_bounds__(RT, 1) k_ro_bwd(const Ctx c) {
     umma::mbar_wait(&bar_mma, 0);
     umma::fence_after_sync();
     FSG_T(4);                                            // 4: product (+ input rows)
-    float d[32];
-    double s = 0.0, qq = 0.0;
+    float s = 0.f, qq = 0.f;
     if (c0 < npad) {
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
@@ -653,21 +702,21 @@ __global__ void __launch_bounds__(RT, 1) k_ro_bwd(const Ctx c) {
         for (int e = 0; e < 16; ++e) {
           const int b = c0 + hh * 16 + e;
           const float v = b < B ? vm[e] + vc[e] : 0.f;
-          d[hh * 16 + e] = v;
-          uu[hh * 16 + e] = (uu[hh * 16 + e] - mu1) * rs1;      // uhat
-          s += (double)v;
-          qq += (double)v * (double)uu[hh * 16 + e];
+          dy[hh * 16 + e] = v;                             // (d a1 is dead: the registers now hold d y1)
+          uu[hh * 16 + e] = (uu[hh * 16 + e] - mu1) * rs1;  // uhat
+          s += v;
+          qq = fmaf(v, uu[hh * 16 + e], qq);
         }
       }
     } else {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) d[e] = 0.f;
+      for (int e = 0; e < 32; ++e) dy[e] = 0.f;
     }
-    sSt[cg * FH + k] = s;
-    sSt[4 * FH + cg * FH + k] = qq;
+    sStF[cg * FH + k] = s;
+    sStF[4 * FH + cg * FH + k] = qq;
     __syncthreads();
-    const double a = (sSt[k] + sSt[FH + k]) + (sSt[2 * FH + k] + sSt[3 * FH + k]);
-    const double bsum = (sSt[4 * FH + k] + sSt[5 * FH + k]) + (sSt[6 * FH + k] + sSt[7 * FH + k]);
+    const double a = ((double)sStF[k] + (double)sStF[FH + k]) + ((double)sStF[2 * FH + k] + (double)sStF[3 * FH + k]);
+    const double bsum = ((double)sStF[4 * FH + k] + (double)sStF[5 * FH + k]) + ((double)sStF[6 * FH + k] + (double)sStF[7 * FH + k]);
     const double inv = B > 0 ? 1.0 / B : 0.0;
     const float e1 = (float)(a * inv), e2 = (float)(bsum * inv);
     if (cg == 0) {
@@ -679,103 +728,92 @@ __global__ void __launch_bounds__(RT, 1) k_ro_bwd(const Ctx c) {
 #pragma unroll
     for (int e = 0; e < 32; ++e) {
       const int b = c0 + e;
-      if (b < B) c.du[((size_t)h * c.Bm + b) * 2 * FH + k] = sc1 * (d[e] - e1 - uu[e] * e2);
+      if (b < B) c.du[((size_t)h * c.Bm + b) * 2 * FH + k] = sc1 * (dy[e] - e1 - uu[e] * e2);
     }
     FSG_T(5);                                            // 5: bn1 backward, d u
     if (blockIdx.x == 0 && threadIdx.x == 0)
       for (int q_ = 0; q_ < 8; ++q_) c.status[112 + q_] = FSG_TVAL(q_);
   } else {
     // ================= weight gradient: d W1 [out][in] = d a1^T y1 over the graph rows; d b1 =================
-    // thread groups: (t < 256: K slice 2p, t >= 256: K slice 2p + 1) x (first 128: d a1^T chunks, next 128: y1^T chunks)
-    const int grp = t >> 8, sub = (t >> 7) & 1, ch = t & 127;
-    const float sc1 = v1[ch], sh1 = v1[FH + ch];
+    // A operand d a1^T: all four 32-row K slices resident (slice p at sOp + p * 32 KB: hi 16 KB | lo 16 KB), built by
+    // thread (j, p) straight from its registers.  B operand y1^T: two slices at a time in the (otherwise unused) ring
+    // area; thread (k, p) builds 16 rows of a slice per pass.
     float db1 = 0.f;
+    {
+      unsigned char* st = sOp + part * 32768;
+#pragma unroll
+      for (int kc = 0; kc < 8; ++kc) {
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          db1 += dy[kc * 4 + e];
+          umma::split_tf32(dy[kc * 4 + e], hi[e], lo[e]);
+        }
+        const uint32_t off = (uint32_t)kc * kALbo + (uint32_t)j * 16u;
+        *reinterpret_cast<float4*>(st + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(st + 16384 + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+    const float sc1 = v1[j], sh1 = v1[FH + j];
     const uint32_t idesc = umma::instr_desc(umma::kFmtTF32, 128, 128);
     for (int p = 0; p < 2; ++p) {
-      if (p == 1) {                                      // the stages are reused: the first pass's products must be done
+      if (32 * 2 * p >= npad) break;
+      if (p == 1) {                                        // the y1^T stages are reused: the first pass's products must be done
         umma::mbar_wait(&bar_empty[0], 0);
         umma::fence_after_sync();
       }
-      const int s = 2 * p + grp;                         // K slice: rows 32 s .. 32 s + 31
-      unsigned char* st = sOp + grp * 65536 + sub * 32768;     // stage: d a1^T hi | lo | y1^T hi | lo (16 KB each)
-      if (32 * s < npad) {
-        if (sub == 0) {
-          float hv[32];
+      const int sl = 2 * p + (part >> 1), r0 = 32 * sl + 16 * (part & 1);      // this thread: rows r0 .. r0 + 15 of slice sl
+      unsigned char* st = sRing + (part >> 1) * kStage;
+      float uv[16];
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int b = 32 * s + e;
-            hv[e] = b < B ? __ldcg(H1 + (size_t)b * FH + ch) : 0.f;
-          }
+      for (int e = 0; e < 16; ++e) uv[e] = r0 + e < B ? ro_input1(c, h, r0 + e, j, sPerm) : 0.f;
 #pragma unroll
-          for (int kc = 0; kc < 8; ++kc) {
-            float hi[4], lo[4];
+      for (int kc = 0; kc < 4; ++kc) {
+        float hi[4], lo[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int b = 32 * s + kc * 4 + e;
-              const float v = b < B ? da1(b, hv[kc * 4 + e]) : 0.f;
-              db1 += v;
-              umma::split_tf32(v, hi[e], lo[e]);
-            }
-            const uint32_t off = (uint32_t)kc * kALbo + (uint32_t)ch * 16u;
-            *reinterpret_cast<float4*>(st + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4*>(st + 16384 + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-          }
-        } else {
-          float uv[32];
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int b = 32 * s + e;
-            uv[e] = b < B ? ro_input1(c, h, b, ch, sPerm) : 0.f;
-          }
-#pragma unroll
-          for (int kc = 0; kc < 8; ++kc) {
-            float hi[4], lo[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int b = 32 * s + kc * 4 + e;
-              const float v = b < B ? fmaf(uv[kc * 4 + e], sc1, sh1) : 0.f;
-              umma::split_tf32(v, hi[e], lo[e]);
-            }
-            const uint32_t off = (uint32_t)kc * kALbo + (uint32_t)ch * 16u;
-            *reinterpret_cast<float4*>(st + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4*>(st + 16384 + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-          }
+        for (int e = 0; e < 4; ++e) {
+          const float v = r0 + kc * 4 + e < B ? fmaf(uv[kc * 4 + e], sc1, sh1) : 0.f;
+          umma::split_tf32(v, hi[e], lo[e]);
         }
+        const uint32_t off = (uint32_t)((part & 1) * 4 + kc) * kALbo + (uint32_t)j * 16u;
+        *reinterpret_cast<float4*>(st + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(st + 16384 + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
       }
       umma::fence_async_smem();
       __syncthreads();
       if (t == 0) {
         umma::fence_after_sync();
         for (int g2 = 0; g2 < 2; ++g2) {
-          const int sl = 2 * p + g2;
-          if (32 * sl >= npad) break;
-          const uint32_t base = umma::smem_addr(sOp + g2 * 65536);
-          const int ksteps = imin(4, (npad - 32 * sl) / 8);
+          const int s2 = 2 * p + g2;
+          if (32 * s2 >= npad) break;
+          const uint32_t abase = umma::smem_addr(sOp + s2 * 32768), bbase = umma::smem_addr(sRing + g2 * kStage);
+          const int ksteps = imin(4, (npad - 32 * s2) / 8);
           for (int ks = 0; ks < ksteps; ++ks) {
             const uint32_t o = (uint32_t)ks * 2u * kALbo;
-            const uint64_t ah = umma::smem_desc(base + o, kALbo, kASbo), al = umma::smem_desc(base + 16384u + o, kALbo, kASbo);
-            const uint64_t bh = umma::smem_desc(base + 32768u + o, kALbo, kASbo), bl = umma::smem_desc(base + 49152u + o, kALbo, kASbo);
-            const uint32_t first = (sl == 0 && ks == 0) ? 0u : 1u;
+            const uint64_t ah = umma::smem_desc(abase + o, kALbo, kASbo), al = umma::smem_desc(abase + 16384u + o, kALbo, kASbo);
+            const uint64_t bh = umma::smem_desc(bbase + o, kALbo, kASbo), bl = umma::smem_desc(bbase + 16384u + o, kALbo, kASbo);
+            const uint32_t first = (s2 == 0 && ks == 0) ? 0u : 1u;
             umma::mma_tf32(tmem, al, bh, idesc, first);
             umma::mma_tf32(tmem, ah, bl, idesc, 1u);
             umma::mma_tf32(tmem, ah, bh, idesc, 1u);
           }
         }
-        umma::commit(p == 0 ? &bar_empty[0] : &bar_mma);
+        if (p == 0 && 64 < npad) umma::commit(&bar_empty[0]);
       }
     }
-    // d b1: the two slice groups of a channel, fixed order
-    float* sDb = reinterpret_cast<float*>(sSt);
-    if (sub == 0) sDb[grp * FH + ch] = db1;
+    if (t == 0) umma::commit(&bar_mma);
+    // d b1: the four row parts of a channel, fixed order
+    float* sDb = sStF;
+    sDb[part * FH + j] = db1;
     FSG_T(3);                                            // 3: operand slices + issue (both passes)
     umma::mbar_wait(&bar_mma, 0);
     umma::fence_after_sync();
     __syncthreads();
     FSG_T(4);                                            // 4: product tail
-    if (t < FH) c.grads[c.po.fc1_b[h] + t] = sDb[t] + sDb[FH + t];
+    if (t < FH) c.grads[c.po.fc1_b[h] + t] = (sDb[t] + sDb[FH + t]) + (sDb[2 * FH + t] + sDb[3 * FH + t]);
     // d W1 from TMEM: 16 warps = 4 lane quarters x 4 column groups, transposed through a private scratch
     {
-      float* sw = reinterpret_cast<float*>(sOp) + warp * 32 * 33;     // (the operand stages are idle)
+      float* sw = reinterpret_cast<float*>(sOp) + warp * 32 * 33;     // (the operand slices are idle)
       const int row0 = (warp & 3) * 32, col0 = (warp >> 2) * 32;
       float v[32];
       umma::ld32(umma::tmem_addr(tmem, row0, col0), v);
@@ -807,13 +845,14 @@ bool readout_ro_supported(const Ctx& c) {
 
 int launch_readout_ro_forward(const Ctx& c, cudaStream_t s) {
   const size_t smem = ro_fsmem().total;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_ro_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto go = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
-  launch_k(k_ro_fwd, dim3(3), dim3(RT), smem, s, c);
+    launch_k(kern, dim3(3), dim3(RT), smem, s, c);
+    return 0;
+  };
+  const int rc = c.C == 2 ? go(k_ro_fwd<2>) : c.C == 3 ? go(k_ro_fwd<3>) : c.C == 4 ? go(k_ro_fwd<4>) : go(k_ro_fwd<8>);
+  if (rc) return rc;
   note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
@@ -821,13 +860,14 @@ int launch_readout_ro_forward(const Ctx& c, cudaStream_t s) {
 
 int launch_readout_ro_backward(const Ctx& c, cudaStream_t s) {
   const size_t smem = ro_bsmem().total;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_ro_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto go = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
-  launch_k(k_ro_bwd, dim3(6), dim3(RT), smem, s, c);
+    launch_k(kern, dim3(6), dim3(RT), smem, s, c);
+    return 0;
+  };
+  const int rc = c.C == 2 ? go(k_ro_bwd<2>) : c.C == 3 ? go(k_ro_bwd<3>) : c.C == 4 ? go(k_ro_bwd<4>) : go(k_ro_bwd<8>);
+  if (rc) return rc;
   note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;

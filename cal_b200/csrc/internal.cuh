@@ -128,6 +128,7 @@ bool readout_tc_supported(const Ctx& c);                                   // te
 int launch_readout_tc_forward(const Ctx& c, cudaStream_t s);
 int launch_readout_tc_backward(const Ctx& c, cudaStream_t s);
 bool readout_ro_supported(const Ctx& c);                                   // short-chain readout of the fused small-graph path (head_ro.cu)
+bool readout_runs_ro(const Ctx& c);                                        // ... and they are the ones that will run (no override)
 int launch_readout_ro_forward(const Ctx& c, cudaStream_t s);
 int launch_readout_ro_backward(const Ctx& c, cudaStream_t s);
 int launch_fsg_prep(const Ctx& c, cudaStream_t s);                         // fused small-graph path (fsg.cu)

@@ -177,6 +177,13 @@ def spmotif_graph(rng, base, motif, n_base, noise=0.1, ba_m=2, max_degree=10,
     if feature_dim is None:                              # one-hot degree; featgen.py:19-28
         deg = np.bincount(ei[0], minlength=n)
         feat = np.eye(max_degree, dtype=np.float32)[np.minimum(deg, max_degree - 1)]
+    elif feature_dim == "mutag":
+        # main_real.py's MUTAG features: 7-way node-label one-hot | degree | one-hot(min(degree,
+        # 100)) = 109 columns (feature_expansion.py:56-59,101-106); the node labels are synthetic (uniform)
+        deg = np.bincount(ei[0], minlength=n)
+        lab = np.eye(7, dtype=np.float32)[rng.randint(7, size=n)]
+        feat = np.concatenate([lab, deg[:, None].astype(np.float32),
+                               np.eye(101, dtype=np.float32)[np.minimum(deg, 100)]], axis=1)
     else:
         feat = rng.standard_normal((n, feature_dim)).astype(np.float32)
     return Data(feat=torch.from_numpy(feat), edge_index=torch.from_numpy(ei),
@@ -192,16 +199,17 @@ CONFIGS = {
     "spmotif_refsize": dict(avg_nodes=240, ba_m=2, noise=0.1, feature_dim=None, max_degree=10,
                             num_classes=4, batch_size=128),
     # cfg 3: MUTAG-shaped (17.93 nodes, 39.6 directed edges), F=109, 2 classes.
-    "mutag": dict(avg_nodes=18, ba_m=1, noise=0.1, feature_dim=109, max_degree=10,
+    "mutag": dict(avg_nodes=18, ba_m=1, noise=0.1, feature_dim="mutag", max_degree=10,
                   num_classes=2, batch_size=128),
     # cfg 5: large synthetic, ~200 nodes / ~800 edge columns, 64-d features, batch 512.
+    # (BA(m=2)-based graphs only -> 4 edge_index columns per node)
     "large": dict(avg_nodes=200, ba_m=2, noise=0.0, feature_dim=64, max_degree=10,
-                  num_classes=4, batch_size=512),
+                  num_classes=4, batch_size=512, base="ba"),
 }
 
 
 def make_dataset(num_graphs, seed=666, bias=0.9, avg_nodes=25, ba_m=1, noise=0.1,
-                 feature_dim=None, max_degree=10, num_classes=4, **_):
+                 feature_dim=None, max_degree=10, num_classes=4, base=None, **_):
     """``num_graphs`` graphs with balanced labels; P(tree base | house) = bias,
     P(tree base | other motif) = 1 - bias (utils.py:126,142-150)."""
     rng = np.random.RandomState(seed)
@@ -210,11 +218,13 @@ def make_dataset(num_graphs, seed=666, bias=0.9, avg_nodes=25, ba_m=1, noise=0.1
         label = i % num_classes
         motif = MOTIFS[label % len(MOTIFS)]
         p_tree = bias if motif == "house" else 1.0 - bias
-        base = "tree" if rng.rand() < p_tree else "ba"
+        base_kind = "tree" if rng.rand() < p_tree else "ba"
+        if base is not None:                                 # a workload made of one base type only
+            base_kind = base
         nm = _motif_edges(motif)[0]
         lo = max(3, int(round(0.6 * (avg_nodes - nm))))
         hi = max(lo + 1, int(round(1.4 * (avg_nodes - nm))) + 1)
-        g = spmotif_graph(rng, base, motif, int(rng.randint(lo, hi)), noise, ba_m,
+        g = spmotif_graph(rng, base_kind, motif, int(rng.randint(lo, hi)), noise, ba_m,
                           max_degree, feature_dim)
         g.y = torch.tensor([label], dtype=torch.long)
         out.append(g)

@@ -24,22 +24,23 @@ def _free_port():
     return p
 
 
-def _rank_batches(rank):
-    return [random_case(seed=300 + 10 * rank + i, hidden=64, batch_size=24)[1] for i in range(2)]
+def _rank_batches(rank, hidden=64):
+    return [random_case(seed=300 + 10 * rank + i, hidden=hidden, batch_size=24)[1] for i in range(2)]
 
 
-def _worker(rank, world, port, out_dir, use_graph, collective="nccl"):
+def _worker(rank, world, port, out_dir, use_graph, collective="nccl", hidden=64):
     import torch.distributed as dist
     import cal_b200
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    ora, _, _ = random_case(seed=299, hidden=64, batch_size=24)          # identical replica on every rank
+    ora, _, _ = random_case(seed=299, hidden=hidden, batch_size=24)      # identical replica on every rank
     net = clone_to_cuda(ora, cal_b200, device="cuda:%d" % rank)
-    batches = _rank_batches(rank)
-    caps = cal_b200.batch_caps([b for r in range(world) for b in _rank_batches(r)])
+    batches = _rank_batches(rank, hidden)
+    caps = cal_b200.batch_caps([b for r in range(world) for b in _rank_batches(r, hidden)])
     tr = cal_b200.Trainer(net, caps, lr=1e-3, process_group=True, use_graph=use_graph, collective=collective)
     assert tr.collective == collective
+    assert tr.fused_small_graphs == (hidden == 128)      # hidden 128: the fused small-graph kernels (csrc/fsg*.cu, head_ro.cu)
     for s in range(STEPS):
         b = batches[s % 2]
         tr.step_host(tr.pack(b, perm=list(range(b.num_graphs))))
@@ -89,24 +90,25 @@ def test_dp_adam_back_to_back_world1_matches_adam():
     lib.cal_dp_free(mine)
 
 
+@pytest.mark.parametrize("hidden", [64, 128], ids=["tiled_h64", "fused_h128"])
 @pytest.mark.parametrize("collective", ["nccl", "peer"])
 @pytest.mark.parametrize("use_graph", [True, False], ids=["graph", "eager"])
-def test_dp_world2_matches_oracle_average(tmp_path, use_graph, collective):
+def test_dp_world2_matches_oracle_average(tmp_path, use_graph, collective, hidden):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     import copy
     import torch.multiprocessing as mp
     from oracle import cal_oracle as O
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), use_graph, collective), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), use_graph, collective, hidden), nprocs=world, join=True)
     got = [torch.load(os.path.join(tmp_path, "p%d.pt" % r)) for r in range(world)]
     for n in got[0]:
         assert torch.equal(got[0][n], got[1][n]), "rank parameters diverged: " + n
     # oracle emulation: one replica per rank (own BatchNorm statistics), shared averaged gradients
-    ora, _, _ = random_case(seed=299, hidden=64, batch_size=24)
+    ora, _, _ = random_case(seed=299, hidden=hidden, batch_size=24)
     reps = [copy.deepcopy(ora) for _ in range(world)]
     opts = [torch.optim.Adam(r.parameters(), lr=1e-3) for r in reps]
-    data = [_rank_batches(r) for r in range(world)]
+    data = [_rank_batches(r, hidden) for r in range(world)]
     for s in range(STEPS):
         for r in range(world):
             b = data[r][s % 2]

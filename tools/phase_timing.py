@@ -32,7 +32,7 @@ names_fb = ["dep wait", "structure+records", "dz operand+issue", "dW (FFMA)", "M
             "norm bwd", "all-reduce wait", "att bwd", "transpose aggregate", "MMA", "stats epilogue", "bn bwd rows", "feat bwd"]
 if tr.fused_small_graphs:
     print("k_fsg_backward (CTA 0) cycles:", list(zip(names_fb, st[64:80])), "sum", sum(st[64:80]))
-print("k_ro_fwd (head 0) cycles:", list(zip(["dep wait", "rows+bn1+operand", "fc1 product", "epilogue+bn2", "h1 store+fc2", "softmax+loss"], st[80:86])))
+print("k_ro_fwd (head 0) cycles:", list(zip(["dep wait", "operand write", "fc1 product", "bn2 finalise", "fc2 loop", "last-block tail", "rows+thread stats", "bn1 finalise", "TMEM epilogue", "fold+h1 store", "softmax+loss"], st[80:91])))
 print("k_ro_bwd (head 0, input-gradient CTA) cycles:", list(zip(["dep wait", "d logits", "fc2/bn2 sums", "d a1 operand", "product", "bn1 bwd + du"], st[112:118])))
 print("k_ro_bwd (head 0, weight-gradient CTA) cycles:", list(zip(["dep wait", "d logits", "fc2/bn2 sums", "slices+issue", "product tail", "dW1 drain"], st[120:126])))
 names_p = ["wait+zero", "edges+counts", "node pass", "scan", "fill", "sort", "write-out"]
