@@ -52,13 +52,16 @@ def parse():
     ap.add_argument("--collective", default="auto", choices=["auto", "peer", "nccl"],
                     help="N>1 gradient exchange: NVLink peer push fused with Adam, or ncclAllReduce")
     ap.add_argument("--no-stage-timing", action="store_true", help="skip the live per-stage timing / roofline")
+    ap.add_argument("--readout-bf16", action="store_true",
+                    help="readout MLP products with bf16 operands / fp32 accumulate (BASELINE.json configs[4]: "
+                         "'bf16 MLP / fp32 aggregate'); everything else stays fp32")
     return ap.parse_args()
 
 
-def model_args(hidden=128, layers=3):
+def model_args(hidden=128, layers=3, readout_bf16=False):
     return argparse.Namespace(layers=layers, hidden=hidden, with_random=True, without_node_attention=False,
                               without_edge_attention=False, fc_num="222", cat_or_add="add", c=0.5, o=1.0, co=0.5,
-                              eval_random=False)
+                              eval_random=False, readout_bf16=readout_bf16)
 
 
 def build_batches(workload, batch_size, n_batches, pool, seed):
@@ -367,11 +370,11 @@ def run_gpu(a, rank, local_rank, world):
     import random
     random.seed(666 + rank)
     if a.model == "CausalGCN":
-        net = cal_b200.CausalGCN(F, C, model_args()).to(dev)
+        net = cal_b200.CausalGCN(F, C, model_args(readout_bf16=a.readout_bf16)).to(dev)
     elif a.model == "CausalGIN":
-        net = cal_b200.CausalGIN(F, C, model_args()).to(dev)
+        net = cal_b200.CausalGIN(F, C, model_args(readout_bf16=a.readout_bf16)).to(dev)
     else:
-        net = cal_b200.CausalGAT(F, C, model_args()).to(dev)
+        net = cal_b200.CausalGAT(F, C, model_args(readout_bf16=a.readout_bf16)).to(dev)
     net.train()
     tr = cal_b200.Trainer(net, cal_b200.batch_caps(batches), lr=1e-3, process_group=True if world > 1 else None,
                           use_graph=not a.no_graph, collective=a.collective)
@@ -583,7 +586,7 @@ def run_gpu(a, rank, local_rank, world):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f32 (readout MLP products: bf16 operands, fp32 accumulate)" if a.readout_bf16 else "f32", "data": "synthetic",
             "config": workload_config(a, bs, batches),
             "sample": sample_stats(batches, "inputs larger than L2: %d distinct resident batches (%.0f MB) cycled; "
                                             "workspace reused" % (n_res, resident_bytes / 2 ** 20)),

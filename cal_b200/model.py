@@ -258,7 +258,7 @@ class Engine:
         self._owner = None
         caps = _lib.Caps()
         caps.max_nodes, caps.max_edges, caps.max_graphs = int(max_nodes), int(max_edges), int(max_graphs)
-        caps.small_graphs = self._fsg_level(small_graphs)
+        caps.small_graphs = self._fsg_level(small_graphs) if int(max_graphs) <= self.FSG_GRAPHS else 0
         nbytes = self.lib.cal_workspace_bytes(C.byref(self.desc), C.byref(caps))
         if nbytes == 0:
             raise _lib.CalError("cal_b200: unsupported model configuration or capacities (hidden must be 32/64/128, "
@@ -348,6 +348,8 @@ class Engine:
         """cal_caps.small_graphs: 0 = tiled kernels, 1 = fused small-graph forward and backward, 2 = fused forward only."""
         if not small or self.fsg_mode == "off":
             return 0
+        if self.is_gat or self.is_gin or self.H != 128 or self.F > 128:
+            return 0                                       # (the C side would ignore the promise: keep the flag truthful)
         return 2 if self.fsg_mode == "fwd" else 1
 
     def _stream(self):

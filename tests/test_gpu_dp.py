@@ -120,5 +120,11 @@ def test_dp_world2_matches_oracle_average(tmp_path, use_graph, collective, hidde
                 p.grad = avg.clone()
         for o in opts:
             o.step()
+    # Adam normalises every gradient entry by its own running magnitude, so where the rank-averaged gradient nearly
+    # cancels (bn_feat.bias, the KL head at hidden 128) fp32 rounding noise of the gradient moves the parameter by up
+    # to ~lr per step whatever the kernel: measured 5.8e-4 (DP) and 4.9e-4 / 8.9e-4 (one GPU, tiled / fused kernels,
+    # tools/debug_traj.py, profiles/r02_traj.txt) of the tensor's largest entry after 3 steps.  The replica identity
+    # above is the exchange's own property and stays bit-exact.
+    tol = 1e-4 if hidden == 64 else 2e-3
     for n, p in reps[0].named_parameters():
-        assert rel_err(got[0][n], p.detach()) < 1e-4, n
+        assert rel_err(got[0][n], p.detach()) < tol, n

@@ -477,16 +477,18 @@ def test_abi_argument_errors_on_device():
     assert eng.status() & L.CAL_ST_CAPACITY
 
 
-def test_trainer_graph_replay_matches_oracle_trajectory():
+@pytest.mark.parametrize("hidden", [64, 128], ids=["tiled_h64", "fused_h128"])
+def test_trainer_graph_replay_matches_oracle_trajectory(hidden):
     """5 optimizer steps: Trainer (captured CUDA graph, fused loss, fused Adam) vs oracle + torch Adam."""
     M, O = _mods()
-    ora, b0, _ = random_case(seed=71, hidden=64, batch_size=32)
-    batches = [b0] + [random_case(seed=72 + i, hidden=64, batch_size=32)[1] for i in range(2)]
+    ora, b0, _ = random_case(seed=71, hidden=hidden, batch_size=32)
+    batches = [b0] + [random_case(seed=72 + i, hidden=hidden, batch_size=32)[1] for i in range(2)]
     g = torch.Generator().manual_seed(5)
     perms = [torch.randperm(32, generator=g) for _ in range(5)]
     net = clone_to_cuda(ora, M)
     tr = M.Trainer(net, M.batch_caps(batches), lr=1e-3)
     tr_e = M.Trainer(clone_to_cuda(ora, M), M.batch_caps(batches), lr=1e-3, use_graph=False)
+    assert tr.fused_small_graphs == (hidden == 128)
     opt = torch.optim.Adam(ora.parameters(), lr=1e-3)
     dev_batches = {}
     for step in range(5):
@@ -500,7 +502,10 @@ def test_trainer_graph_replay_matches_oracle_trajectory():
         assert abs(float(res[0]) - float(losses[0])) < 1e-4 * max(1.0, abs(float(losses[0])))
     torch.cuda.synchronize()
     for (n, p), (_, q) in zip(net.named_parameters(), ora.named_parameters()):
-        assert rel_err(p.detach().cpu(), q.detach()) < 1e-4, n
+        # (hidden 128: the KL head's gradients are ~1e-3 of the model's largest; Adam turns their fp32 rounding noise
+        # into up to ~lr of parameter movement per step whatever the kernels -- tiled 4.9e-4, fused 8.9e-4 after 3
+        # steps, profiles/r02_traj.txt)
+        assert rel_err(p.detach().cpu(), q.detach()) < (1e-4 if hidden == 64 else 3e-3), n
     assert tr.launches_per_step == tr_e.launches_per_step and tr.launches_per_step > 0
     assert len(tr._graphs) == 1               # one captured graph served all host batches
 
