@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--collective", default="auto", choices=["auto", "peer", "nccl"],
                     help="N>1 gradient exchange: NVLink peer push fused with Adam, or ncclAllReduce")
     ap.add_argument("--no-stage-timing", action="store_true", help="skip the live per-stage timing / roofline")
+    ap.add_argument("--same-batches", action="store_true",
+                    help="N > 1: every rank steps the SAME batches (rank 0's): the step time then shows the pure cost of the "
+                         "gradient exchange, without the max-over-ranks of data-dependent step times (an experiment, not the metric)")
     ap.add_argument("--readout-bf16", action="store_true",
                     help="readout MLP products with bf16 operands / fp32 accumulate (BASELINE.json configs[4]: "
                          "'bf16 MLP / fp32 aggregate'); everything else stays fp32")
@@ -265,7 +268,7 @@ def workload_config(a, bs, batches):
             "graphs_per_batch": bs, "features": int(batches[0].feat.size(1)), "hidden": 128, "layers": 3,
             "generator": "cal_b200.data.make_dataset(pool=%d, seed=666 + rank, bias=0.9); batches drawn without "
                          "replacement from the pool by RandomState(667 + rank)" % pool_size(a, bs),
-            "parallelism": "dp%d" % a.gpus}
+            "parallelism": "dp%d" % a.gpus + (" (experiment: every rank steps rank 0's batches)" if getattr(a, "same_batches", False) else "")}
 
 
 def pool_size(a, bs):
@@ -355,7 +358,8 @@ def run_gpu(a, rank, local_rank, world):
     bs = a.batch or CONFIGS[a.workload]["batch_size"]
     # enough distinct resident batches that the inputs of the timed region exceed L2 (no batch is
     # reused within ~L2 worth of input bytes) -- the "inputs larger than L2" timing rule
-    probe, cfg = build_batches(a.workload, bs, 2, 4 * bs, 666 + rank)
+    drank = 0 if a.same_batches else rank
+    probe, cfg = build_batches(a.workload, bs, 2, 4 * bs, 666 + drank)
     caps_probe = cal_b200.batch_caps(probe, slack=1.15)
     lay_probe = cal_b200.PackedLayout(*caps_probe[:3], probe[0].feat.size(1))
     n_res = a.resident or int(min(max(L2_BYTES // lay_probe.nbytes + 8, 16), 1024))
@@ -364,7 +368,7 @@ def run_gpu(a, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         n_res = int(t.item())
     pool = pool_size(a, bs)
-    batches, cfg = build_batches(a.workload, bs, n_res, pool, 666 + rank)
+    batches, cfg = build_batches(a.workload, bs, n_res, pool, 666 + drank)
     F, C = int(batches[0].feat.size(1)), cfg["num_classes"]
     torch.manual_seed(666)
     import random

@@ -49,23 +49,45 @@ __host__ __device__ inline FsgSmem fsg_smem() {
   return s;
 }
 
-// training-mode BatchNorm `id` from the grid totals tot[0..K) (sum) and tot[K..2K) (sum of squares): threads
-// [t0, t0 + K) write the affine into shared memory; CTA 0 publishes the record and the running statistics
-__device__ __forceinline__ void fsg_bn_finalize(const Ctx& c, int id, int count, const double* tot, float* s_sc, float* s_sh,
-                                                int t0) {
-  const int K = c.bn_K[id];
+// What a thread needs to finalise channel k of BatchNorm `id`, fetched BEFORE the all-reduce wait: the indexed
+// constant-bank loads (c.bn_*[id]) and the global loads of gamma / beta / the running statistics otherwise sit on
+// the critical path right behind the wait (ncu: 6 % of the backward kernel's samples on one indexed LDC).
+struct FsgBnPre {
+  float g, b, rm, rv;
+  long long rm_off, rv_off;
+};
+__device__ __forceinline__ FsgBnPre fsg_bn_prefetch(const Ctx& c, int id, int t0) {
+  FsgBnPre p = {1.f, 0.f, 0.f, 1.f, -1, -1};
   const int k = (int)threadIdx.x - t0;
-  if (k < 0 || k >= K) return;
-  const double s = tot[k], q = tot[K + k];
+  if (k >= 0 && k < FH) {
+    p.g = c.params[c.bn_gamma[id] + k];
+    p.b = c.params[c.bn_beta[id] + k];
+    if (blockIdx.x == 0 && c.bn_buffers != nullptr && c.bn_rm[id] >= 0) {
+      p.rm_off = c.bn_rm[id] + k;
+      p.rv_off = c.bn_rv[id] + k;
+      p.rm = c.bn_buffers[p.rm_off];
+      p.rv = c.bn_buffers[p.rv_off];
+    }
+  }
+  return p;
+}
+// training-mode BatchNorm `id` (H channels) from the grid totals tot[0..H) (sum) and tot[H..2H) (sum of squares):
+// threads [t0, t0 + H) write the affine into shared memory; CTA 0 publishes the record and the running statistics
+__device__ __forceinline__ void fsg_bn_finalize(const Ctx& c, int id, int count, const FsgBnPre& pre, const double* tot, float* s_sc,
+                                                float* s_sh, int t0) {
+  const int k = (int)threadIdx.x - t0;
+  if (k < 0 || k >= FH) return;
+  const double s = tot[k], q = tot[FH + k];
   double mean = 0.0, var = 0.0;
   if (count > 0) {
-    mean = s / count;
-    var = q / count - mean * mean;
+    const double inv = 1.0 / (double)count;
+    mean = s * inv;
+    var = q * inv - mean * mean;
     if (var < 0.0) var = 0.0;
   }
   const float rstd = (float)(1.0 / sqrt(var + (double)c.eps));
-  const float sc = c.params[c.bn_gamma[id] + k] * rstd;
-  const float sh = c.params[c.bn_beta[id] + k] - (float)mean * sc;
+  const float sc = pre.g * rstd;
+  const float sh = pre.b - (float)mean * sc;
   s_sc[k] = sc;
   s_sh[k] = sh;
   if (blockIdx.x == 0) {
@@ -73,14 +95,12 @@ __device__ __forceinline__ void fsg_bn_finalize(const Ctx& c, int id, int count,
     c.bnf(id, BN_SHIFT)[k] = sh;
     c.bnf(id, BN_MEAN)[k] = (float)mean;
     c.bnf(id, BN_RSTD)[k] = rstd;
-    if (c.bn_buffers != nullptr && c.bn_rm[id] >= 0) {
+    if (pre.rm_off >= 0) {
       const double unb = count > 1 ? var * ((double)count / (double)(count - 1)) : var;
-      float* rm = c.bn_buffers + c.bn_rm[id];
-      float* rv = c.bn_buffers + c.bn_rv[id];
-      rm[k] = (1.f - c.momentum) * rm[k] + c.momentum * (float)mean;
-      rv[k] = (1.f - c.momentum) * rv[k] + c.momentum * (float)unb;
+      c.bn_buffers[pre.rm_off] = (1.f - c.momentum) * pre.rm + c.momentum * (float)mean;
+      c.bn_buffers[pre.rv_off] = (1.f - c.momentum) * pre.rv + c.momentum * (float)unb;
     }
-    if (k == 0 && c.nbt != nullptr) atomicAdd(reinterpret_cast<unsigned long long*>(c.nbt + id), 1ull);   // (RED: no load round trip in front of the barrier)
+    if (k == 0 && c.nbt != nullptr) atomicAdd(reinterpret_cast<unsigned long long*>(c.nbt + id), 1ull);   // (RED: no load round trip)
   }
 }
 
@@ -266,6 +286,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
 
   // ================= layers + masked convs =================
   // phase p = 0 .. L-1: statistics of bns_conv[p] (input of layer p); phase L: statistics of bnc / bno
+  float bias_next = 0.f;                                              // bias of the product whose epilogue comes next (fetched ahead of its MMA wait)
   for (int l = 0; l <= L; ++l) {
     const bool masked = l == L;
     if (active) {
@@ -279,7 +300,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
       // -- epilogue of the previous product: thread = output channel, the two warp sets split the row groups --
       {
         const int ch = (warp & 3) * 32 + lane;
-        const float bias = l == 0 ? 0.f : c.params[c.po.convs_b[l - 1] + ch];
+        const float bias = bias_next;
         double s = 0.0, q = 0.0;
         for (int g8 = (warp >> 2) * 8; g8 < npad; g8 += 16) {
           float vm[8], vc[8];
@@ -316,6 +337,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
       // ---------------- backbone layer l: x_{l+2} = relu(A bn_l(x_{l+1}) W_l + b_l)  (model.py:93-95) ----------------
       if (active) {
         if (c.train) fsg_publish_fx(ws, l, sPart, 2 * FH);
+        const FsgBnPre pre = c.train ? fsg_bn_prefetch(c, 1 + l, 0) : FsgBnPre();
         FSG_T(4);                                                     // 4: publish
         // x_{l+1} rows to the workspace (the backward pass reads them): coalesced, after the publish so that the
         // all-reduce's fence does not wait for these stores
@@ -342,7 +364,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
         float* sh = sAff + FH;
         if (c.train) {
           fsg_wait_total_fx(ws, l, G, 2 * FH, sTot);
-          fsg_bn_finalize(c, 1 + l, N, sTot, sc, sh, 0);
+          fsg_bn_finalize(c, 1 + l, N, pre, sTot, sc, sh, 0);
         } else if (t < FH) {
           sc[t] = c.bnf(1 + l, BN_SCALE)[t];
           sh[t] = c.bnf(1 + l, BN_SHIFT)[t];
@@ -371,6 +393,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
           issue_3xtf32(sAh, sAl, sBh, sBl, tmem, tmem + 128u, FH / 8, npad);
           umma::commit(&bar_mma);
         }
+        bias_next = c.params[c.po.convs_b[l] + (warp & 3) * 32 + lane];
         umma::mbar_wait(&bar_mma, par_m);
         par_m ^= 1u;
         umma::fence_after_sync();
@@ -445,6 +468,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
     __syncthreads();
     FSG_T(10);                                                        // 10: node attention + bnc / bno statistics
     if (c.train) fsg_publish_fx(ws, L, sPart, 4 * FH);
+    const FsgBnPre pre_m = c.train ? fsg_bn_prefetch(c, t < FH ? L + 1 : L + 2, t < FH ? 0 : FH) : FsgBnPre();
     {
       float4* xg = reinterpret_cast<float4*>(c.Xl(L) + (size_t)n0 * FH);      // x_{L+1} rows to the workspace
       const float4* xs = reinterpret_cast<const float4*>(sX);
@@ -523,8 +547,8 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
       if (br == 0) {
         if (c.train) {
           fsg_wait_total_fx(ws, L, G, 4 * FH, sTot);
-          fsg_bn_finalize(c, L + 1, N, sTot, sc0, sh0, 0);
-          fsg_bn_finalize(c, L + 2, N, sTot + 2 * FH, sc1, sh1, FH);
+          fsg_bn_finalize(c, L + 1, N, pre_m, sTot, sc0, sh0, 0);
+          fsg_bn_finalize(c, L + 2, N, pre_m, sTot + 2 * FH, sc1, sh1, FH);
         } else if (t < FH) {
           sc0[t] = c.bnf(L + 1, BN_SCALE)[t];
           sh0[t] = c.bnf(L + 1, BN_SHIFT)[t];
@@ -562,6 +586,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
         issue_3xtf32(sAh, sAl, sBh, sBl, tmem + (br ? 64u : 0u), tmem + 128u + (br ? 64u : 0u), FH / 8, npad);
         umma::commit(&bar_mma);
       }
+      const float bias_br = c.params[(br ? c.po.objects_b : c.po.context_b) + (warp & 3) * 32 + lane];
       umma::mbar_wait(&bar_mma, par_m);
       par_m ^= 1u;
       umma::fence_after_sync();
@@ -576,7 +601,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
       // (model.py:115-116; a block is one graph).  thread = channel, the two warp sets split the row groups.
       {
         const int ch = (warp & 3) * 32 + lane;
-        const float bias = c.params[(br ? c.po.objects_b : c.po.context_b) + ch];
+        const float bias = bias_br;
         float* zg = c.Z + (size_t)br * c.Nm * FH + (size_t)n0 * FH;
         const uint32_t cm = br ? 64u : 0u;
         float pool = 0.f;

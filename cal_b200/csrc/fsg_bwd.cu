@@ -57,21 +57,22 @@ __host__ __device__ inline FsgBSmem fsg_bsmem() {
 
 // BatchNorm-backward totals tot[0..K) = sum dy, tot[K..2K) = sum dy * xhat  ->  c1 = mean(dy), c2 = mean(dy * xhat) in
 // shared memory by threads [t0, t0 + K); CTA 0 publishes d gamma / d beta (and the record)
-__device__ __forceinline__ void fsg_bn_bwd_finalize(const Ctx& c, int id, int count, const double* tot, float* s_c1, float* s_c2,
-                                                    int t0) {
-  const int K = c.bn_K[id];
+__device__ __forceinline__ void fsg_bn_bwd_finalize(const Ctx& c, int id, int count, long long gamma_off, long long beta_off,
+                                                    const double* tot, float* s_c1, float* s_c2, int t0) {
+  // (gamma_off / beta_off = c.bn_gamma[id] / c.bn_beta[id], read by the caller BEFORE the all-reduce wait: an indexed
+  // constant-bank load right behind the wait was 6 % of this kernel's stall samples)
   const int k = (int)threadIdx.x - t0;
-  if (k < 0 || k >= K) return;
+  if (k < 0 || k >= FH) return;
   const double inv = count > 0 ? 1.0 / count : 0.0;
-  const double a = tot[k], b = tot[K + k];
+  const double a = tot[k], b = tot[FH + k];
   const float c1 = (float)(a * inv), c2 = (float)(b * inv);
   s_c1[k] = c1;
   s_c2[k] = c2;
   if (blockIdx.x == 0) {
     c.bnf(id, BN_C1)[k] = c1;
     c.bnf(id, BN_C2)[k] = c2;
-    c.grads[c.bn_gamma[id] + k] = (float)b;
-    c.grads[c.bn_beta[id] + k] = (float)a;
+    c.grads[gamma_off + k] = (float)b;
+    c.grads[beta_off + k] = (float)a;
   }
 }
 
@@ -540,9 +541,10 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
     FSG_T(8);                                                         // 8: norm backward
 
     // ================= stage 4: attention backward -> gradient rows of the top backbone layer =================
+    const long long go_c = c.bn_gamma[L + 1], bo_c = c.bn_beta[L + 1], go_o = c.bn_gamma[L + 2], bo_o = c.bn_beta[L + 2];
     fsg_wait_total_fx(ws, 12, G, 4 * FH, sTot);
-    fsg_bn_bwd_finalize(c, L + 1, N, sTot, sVec + 4 * FH, sVec + 5 * FH, 0);
-    fsg_bn_bwd_finalize(c, L + 2, N, sTot + 2 * FH, sVec + 6 * FH + 4 * FH, sVec + 6 * FH + 5 * FH, FH);
+    fsg_bn_bwd_finalize(c, L + 1, N, go_c, bo_c, sTot, sVec + 4 * FH, sVec + 5 * FH, 0);
+    fsg_bn_bwd_finalize(c, L + 2, N, go_o, bo_o, sTot + 2 * FH, sVec + 6 * FH + 4 * FH, sVec + 6 * FH + 5 * FH, FH);
     __syncthreads();
     FSG_T(9);                                                         // 9: all-reduce wait
     {
@@ -776,8 +778,9 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
         }
       }
       FSG_T(3);
+      const long long go_l = c.bn_gamma[1 + l], bo_l = c.bn_beta[1 + l];
       fsg_wait_total_fx(ws, 13 + (L - 1 - l), G, 2 * FH, sTot);
-      fsg_bn_bwd_finalize(c, 1 + l, N, sTot, vin + 4 * FH, vin + 5 * FH, 0);
+      fsg_bn_bwd_finalize(c, 1 + l, N, go_l, bo_l, sTot, vin + 4 * FH, vin + 5 * FH, 0);
       umma::mbar_wait(&bar_dw, par_d);
       par_d ^= 1u;
       umma::fence_after_sync();
