@@ -287,6 +287,14 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
       v[3 * FH + k] = c.bnf(id, BN_RSTD)[k];
     }
   }
+  // the masked convs' outputs of this warp's rows (ReLU masks of stage 1): branch 0 now, branch 1 while branch 0 runs
+  float4 zpre[kRowsPerWarp];
+#pragma unroll
+  for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+    const int i = warp + rr * 8;
+    zpre[rr] = (active && i < Nc) ? __ldcg(reinterpret_cast<const float4*>(c.Z + (size_t)(n0 + i) * FH + lane * 4))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   umma::fence_before_sync();
   FSG_TDECL
   pdl_sync();
@@ -314,17 +322,26 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
     // ================= stage 1: the two masked convs, dense part (model.py:112-113 backward) =================
     //   dz = dpool * relu'(z);  d agg = dz W^T (tensor cores);  dW += agg^T dz (tensor cores);  db += dz
     for (int br = 0; br < 2; ++br) {
-      const float* Zg = c.Z + (size_t)br * c.Nm * FH + (size_t)n0 * FH;
       const float4 gp = *reinterpret_cast<const float4*>(sPool + br * FH + lane * 4);
       float dbias[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int i = warp; i < npad; i += 8) {
+#pragma unroll
+      for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+        const int i = warp + rr * 8;
+        if (i >= npad) break;
         float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < Nc) {
-          const float4 z = __ldcg(reinterpret_cast<const float4*>(Zg + (size_t)i * FH + lane * 4));
+          const float4 z = zpre[rr];
           u = make_float4(z.x > 0.f ? gp.x : 0.f, z.y > 0.f ? gp.y : 0.f, z.z > 0.f ? gp.z : 0.f, z.w > 0.f ? gp.w : 0.f);
           dbias[0] += u.x; dbias[1] += u.y; dbias[2] += u.z; dbias[3] += u.w;
         }
         put_b(sBh, sBl, i, lane, u);
+      }
+      if (br == 0) {                                                   // branch 1's masks: in flight under branch 0's products
+#pragma unroll
+        for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+          const int i = warp + rr * 8;
+          if (i < Nc) zpre[rr] = __ldcg(reinterpret_cast<const float4*>(c.Z + (size_t)c.Nm * FH + (size_t)(n0 + i) * FH + lane * 4));
+        }
       }
       umma::fence_async_smem();
       cp_async_wait_all();
@@ -473,7 +490,22 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
       umma::fence_async_smem();                                       // (the y tiles sit where the next weight image lands)
       // block totals [bnc: sum dy | sum dy xhat | bno: sum dy | sum dy xhat]
       __syncthreads();                                                // the tiles are dead: the d agg buffer is scratch
-      block_totals<4, 4>(st, reinterpret_cast<double*>(sBh), sPart, FH, 0, FH, 0);
+      {
+        double* sc8 = reinterpret_cast<double*>(sBh);                  // [4][8][128] doubles = 32 KB of the 45 KB operand area
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) sc8[(v * 8 + warp) * FH + lane * 4 + i] = st[v][i];
+        __syncthreads();
+        for (int i = t; i < 4 * FH; i += FT) {
+          const int v = i >> 7, k = i & 127;
+          double a = 0.0;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) a += sc8[(v * 8 + w) * FH + k];
+          sPart[i] = a;
+        }
+        __syncthreads();
+      }
     }
     FSG_T(6);                                                         // 6: masked gather
     fsg_publish_fx(ws, 12, sPart, 4 * FH);
