@@ -464,6 +464,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
         }
       }
       __syncthreads();                                                // the y tiles are complete
+      FSG_T(6);                                                       // 6: masked gather, rows (dy, y tiles)
       {
         const int sub = lane & 7, grp = t >> 3;                        // 32 quarter warps; lane `sub` owns 16 channels
         for (int it0 = 0; it0 < 2 * Ec; it0 += FT / 8) {               // warp-uniform trip count (full-mask shuffles)
@@ -507,7 +508,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
         __syncthreads();
       }
     }
-    FSG_T(6);                                                         // 6: masked gather
+    FSG_T(4);                                                         // 4 (+ MMA tail): masked gather, d-norm dots + block totals
     fsg_publish_fx(ws, 12, sPart, 4 * FH);
     if (t == 0) {                                                      // image of the top backbone layer (all but the tail)
       umma::fence_async_smem();
@@ -666,6 +667,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
       // per-block partials of the attention parameters and of the top layer's bias: one pass over [7][8 warps][128]
       float* sRed = reinterpret_cast<float*>(sBh);                    // 28 KB of the (idle) node-operand buffers
       __syncthreads();
+      FSG_T(10);                                                      // 10: attention backward, rows
       {
         float* q = sRed + warp * FH + lane * 4;
         *reinterpret_cast<float4*>(q + 0 * 8 * FH) = make_float4(g_wn0[0], g_wn0[1], g_wn0[2], g_wn0[3]);
@@ -697,7 +699,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
       }
     }
     __syncthreads();
-    FSG_T(10);                                                        // 10: attention backward
+    FSG_T(1);                                                         // 1 (+ pooled gradient): attention backward, partial sums
 
     // ================= stage 5: backbone layers L-1 .. 0 =================
     //   sG: g = gradient w.r.t. the layer's pre-activation;  u_j = sum_{e: row_e = j} norm_e g[col_e];

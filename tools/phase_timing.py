@@ -28,8 +28,8 @@ names_fsg = ["dep wait", "plan+CSR+bn_feat", "feat product", "epilogues", "publi
              "affine+split", "weight wait", "MMA", "node att+stats", "edge att", "masked epilogue+pool"]
 if tr.fused_small_graphs:
     print("k_fsg_forward (CTA 0) cycles:", list(zip(names_fsg, st[48:61])), "sum", sum(st[48:61]))
-names_fb = ["dep wait", "structure+records", "dz operand+issue", "dW (FFMA)", "MMA tail", "d agg tiles", "masked gather", "publish",
-            "norm bwd", "all-reduce wait", "att bwd", "transpose aggregate", "MMA", "stats epilogue", "bn bwd rows", "feat bwd"]
+names_fb = ["dep wait", "pooled grad + att-bwd partial sums", "dz operand+issue", "dW (build, MMA, drain)", "MMA tail + gather dots/totals", "d agg tiles", "masked gather rows", "publish",
+            "norm bwd", "all-reduce wait", "att bwd rows", "transpose aggregate", "MMA", "stats epilogue", "bn bwd rows + dW drain", "feat bwd"]
 if tr.fused_small_graphs:
     print("k_fsg_backward (CTA 0) cycles:", list(zip(names_fb, st[64:80])), "sum", sum(st[64:80]))
 print("k_ro_fwd (head 0) cycles:", list(zip(["dep wait", "operand write", "fc1 product", "bn2 finalise", "fc2 loop", "last-block tail", "rows+thread stats", "bn1 finalise", "TMEM epilogue", "fold+h1 store", "softmax+loss"], st[80:91])))
