@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--collective", default="auto", choices=["auto", "peer", "nccl"],
                     help="N>1 gradient exchange: NVLink peer push fused with Adam, or ncclAllReduce")
     ap.add_argument("--no-stage-timing", action="store_true", help="skip the live per-stage timing / roofline")
+    ap.add_argument("--no-prep-ahead", action="store_true",
+                    help="do not overlap the next batch's structure preparation with this step's update")
     ap.add_argument("--same-batches", action="store_true",
                     help="N > 1: every rank steps the SAME batches (rank 0's): the step time then shows the pure cost of the "
                          "gradient exchange, without the max-over-ranks of data-dependent step times (an experiment, not the metric)")
@@ -392,19 +394,23 @@ def run_gpu(a, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # capture one graph per resident batch (outside the timed region), then W warm-up steps
-    for r in resident:
-        tr.step(r)
+    # capture one graph per resident batch (outside the timed region), then W warm-up steps.  The loop knows its next
+    # batch, so each step prepares the NEXT batch's structure beside its own update (Trainer.step(cur, next)): every
+    # batch is still prepared exactly once per step, inside the timed region.
+    ahead = not a.no_prep_ahead
+    nxt = (lambda k: resident[(k + 1) % n_res]) if ahead else (lambda k: None)
+    for k, r in enumerate(resident):
+        tr.step(r, nxt(k))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # clocks are sampled (NVML, every 2 ms) from the warm-up on: a 20-step timed region is only ~3 ms long
     with ClockSampler(visible_gpu_index(local_rank)) as clk:
         for i in range(max(a.warmup, 3)):
-            tr.step(resident[i % n_res])
+            tr.step(resident[i % n_res], nxt(i))
         barrier()
         t_begin = time.perf_counter()
         e0.record()
         for i in range(a.steps):
-            tr.step(resident[(a.warmup + i) % n_res])
+            tr.step(resident[(a.warmup + i) % n_res], nxt(a.warmup + i))
         e1.record()
         barrier()
         t_end = time.perf_counter()

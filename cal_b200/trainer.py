@@ -385,9 +385,12 @@ class Trainer:
         return self.pack(data, perm=perm).to(self.device, non_blocking=False)
 
     # ---- the step ----
-    def _issue(self, base_ptr, gat_keep=None, part="all"):
+    def _issue(self, base_ptr, gat_keep=None, part="all", next_ptr=None, prepped=False):
         """Enqueue the step on the current stream.  part: "all", or "compute" (prep + forward + loss +
-        backward) / "update" (gradient all-reduce + Adam) for the two-graph data-parallel replay."""
+        backward) / "update" (gradient all-reduce + Adam) for the two-graph data-parallel replay.
+        ``prepped``: cal_prep of this batch already ran (at the end of the previous step);  ``next_ptr``: run
+        cal_prep of the NEXT batch on a forked branch next to this step's update (the structure work needs only the
+        batch itself, so it hides under the gradient exchange / Adam instead of heading the next step)."""
         eng, lib = self.eng, self.eng.lib
         if part in ("all", "compute"):
             cb = self.layout.cbatch(base_ptr)
@@ -395,7 +398,8 @@ class Trainer:
                 cb.gat_keep = gat_keep.data_ptr()
             s = eng._stream()
             d, caps = C.byref(eng.desc), C.byref(eng.caps)
-            _lib.check(lib.cal_prep(d, caps, C.byref(cb), eng.ws.data_ptr(), eng.ws_bytes, s), "cal_prep")
+            if not prepped:
+                _lib.check(lib.cal_prep(d, caps, C.byref(cb), eng.ws.data_ptr(), eng.ws_bytes, s), "cal_prep")
             _lib.check(lib.cal_causal_forward(d, caps, C.byref(eng.po), C.byref(eng.bo), eng.flat.data_ptr(),
                                               eng.bn_buf.data_ptr(), eng.nbt.data_ptr(), C.byref(cb),
                                               _lib.CAL_F_TRAIN | _lib.CAL_F_LOSS, 0, eng.ws.data_ptr(), eng.ws_bytes, s),
@@ -404,14 +408,36 @@ class Trainer:
                                                eng.flat_grad.data_ptr(), 0, eng.ws.data_ptr(), eng.ws_bytes, s),
                        "cal_causal_backward")
             eng.gen += 1
+        side = None
+        if next_ptr is not None and part == "all":
+            # fork: the next batch's structure preparation runs beside the update (it writes only workspace regions
+            # that the finished backward pass no longer reads; the update touches the flat buffers / the exchange region)
+            main = torch.cuda.current_stream(self.device)
+            side = self._side_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                cbn = self.layout.cbatch(next_ptr)
+                if gat_keep is not None:
+                    cbn.gat_keep = gat_keep.data_ptr()
+                _lib.check(lib.cal_prep(C.byref(eng.desc), C.byref(eng.caps), C.byref(cbn), eng.ws.data_ptr(), eng.ws_bytes,
+                                        side.cuda_stream), "cal_prep")
         if self.peer is not None:
             if part in ("all", "update"):
                 self.peer.adam_step(eng, 0.0, self.betas, self.eps, self.weight_decay, lr_device=self.lr_dev)
+            if side is not None:
+                torch.cuda.current_stream(self.device).wait_stream(side)
             return
         if part in ("all", "allreduce"):
             self._scale = allreduce_flat_grads(eng.flat_grad, self.pg) if self.world > 1 else 1.0
         if part in ("all", "update"):
             eng.adam_step(0.0, self.betas, self.eps, self.weight_decay, 1.0 / self.world, lr_device=self.lr_dev)
+        if side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(side)
+
+    def _side_stream(self):
+        if not hasattr(self, "_side"):
+            self._side = torch.cuda.Stream(self.device)
+        return self._side
 
     def _gat_keep_for(self, key):
         """Attention-dropout keep mask of CausalGAT (model.py:340 dropout=0.2), regenerated on the
@@ -429,21 +455,31 @@ class Trainer:
             p = float(self.model.dropout)
             self._keep.bernoulli_(1.0 - p).mul_(1.0 / (1.0 - p))
 
-    def step(self, packed_dev):
-        """Enqueue one training step on a device-resident packed batch (asynchronous)."""
+    def step(self, packed_dev, next_packed=None):
+        """Enqueue one training step on a device-resident packed batch (asynchronous).
+
+        ``next_packed``: the device-resident batch of the NEXT call (a loader that knows it one step ahead): its
+        structure preparation (cal_prep) is then issued on a forked branch beside this step's update and the next
+        ``step(next_packed, ...)`` skips it -- every batch is still prepared exactly once.  (Single captured graph
+        per step only: not with the two-graph NCCL replay.)"""
         self._check_alive()
         if packed_dev.device != self.device:
             raise _lib.CalError("cal_b200: Trainer.step needs a device-resident packed batch (use step_host)")
         keep = self._gat_keep_for(None)
         if keep is not None:
             self._refresh_keep()
+        ahead_ok = self.world == 1 or self.peer is not None
+        ptr = packed_dev.data_ptr()
+        prepped = ahead_ok and getattr(self, "_prepped_ptr", None) == ptr
+        nxt = next_packed.data_ptr() if (next_packed is not None and ahead_ok) else None
+        self._prepped_ptr = nxt
         if not self.use_graph:
             c0 = self.eng.lib.cal_launch_count()
-            self._issue(packed_dev.data_ptr(), keep)
+            self._issue(ptr, keep, next_ptr=nxt, prepped=prepped)
             self.launches_per_step = int(self.eng.lib.cal_launch_count() - c0) + (
                 1 if self.world > 1 and self.peer is None else 0)
             return
-        key = packed_dev.data_ptr()
+        key = ptr if (nxt is None and not prepped) else (ptr, nxt, prepped)
         g = self._graphs.get(key)
         if g is None:
             if len(self._graphs) >= self._max_graphs:
@@ -455,7 +491,7 @@ class Trainer:
             if self.world == 1 or self.peer is not None:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=self._capture_stream()):
-                    self._issue(key, keep)
+                    self._issue(ptr, keep, next_ptr=nxt, prepped=prepped)
                 g = (g, None)
                 self.launches_per_step = int(count() - c0)
             else:
@@ -463,13 +499,13 @@ class Trainer:
                 # (compute | update); the update graph is shared by every batch
                 ga = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(ga, stream=self._capture_stream()):
-                    self._issue(key, keep, part="compute")
+                    self._issue(ptr, keep, part="compute")
                 n_compute = int(count() - c0)
                 if self._update_graph is None:
                     c1 = count()
                     self._update_graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(self._update_graph, stream=self._capture_stream()):
-                        self._issue(key, keep, part="update")
+                        self._issue(ptr, keep, part="update")
                     self._update_launches = int(count() - c1)
                 g = (ga, self._update_graph)
                 self.launches_per_step = n_compute + 1 + self._update_launches     # + the NCCL all-reduce kernel
@@ -478,7 +514,7 @@ class Trainer:
             g = g[0]
         g[0].replay()
         if g[1] is not None:
-            self._issue(key, keep, part="allreduce")
+            self._issue(ptr, keep, part="allreduce")
             g[1].replay()
 
     def _capture_stream(self):
@@ -495,6 +531,7 @@ class Trainer:
         """Load every kernel (lazy module loading, cudaFuncSetAttribute) outside capture without
         touching the model state: run the pass, then restore parameters / statistics."""
         eng = self.eng
+        self._prepped_ptr = None
         saved = self._save_state()
         self._issue(packed_dev.data_ptr(), keep)
         self._restore_state(saved)
@@ -520,6 +557,7 @@ class Trainer:
         (as one CUDA-graph replay) between two CUDA events on the launching stream.  Model state is restored afterwards.
         -> list of (name, kernel launches per issue, average milliseconds per issue)."""
         eng, lib = self.eng, self.eng.lib
+        self._prepped_ptr = None
         saved = self._save_state()
         keep = self._gat_keep_for(None)
         self._issue(packed_dev.data_ptr(), keep)               # every buffer holds a consistent step
@@ -679,6 +717,7 @@ class Trainer:
     def step_epoch(self):
         """One training step on the next ``graphs_per_step`` graphs of the epoch (asynchronous)."""
         self._check_alive()
+        self._prepped_ptr = None
         ep = self._epoch
         if ep["done"] >= ep["steps"]:
             raise _lib.CalError("cal_b200: the epoch is exhausted (call begin_epoch)")
@@ -751,6 +790,7 @@ class Trainer:
     # ---- evaluation (train_causal.py:202-223) ----
     @torch.no_grad()
     def eval_batch(self, data_dev, eval_random=False):
+        self._prepped_ptr = None                         # (the module path runs cal_prep on its own batch)
         was = self.model.training
         self.model.eval()
         out = self.model(data_dev, eval_random=eval_random)

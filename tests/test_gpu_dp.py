@@ -28,6 +28,15 @@ def _rank_batches(rank, hidden=64):
     return [random_case(seed=300 + 10 * rank + i, hidden=hidden, batch_size=24)[1] for i in range(2)]
 
 
+def _adam_eps(hidden):
+    # hidden 128: Adam with eps = 1 (update ~ lr * m / (sqrt(v) + 1): LINEAR in the gradient).  With the default eps every
+    # entry is normalised by its own magnitude, so where the rank-averaged gradient nearly cancels, fp32 rounding noise
+    # of ANY correct kernel flips the sign of the update and moves the parameter by up to lr per step (measured: 5.8e-4 ..
+    # 3.9e-3 of the tensor's largest entry after 3 steps, profiles/r02_traj.txt, r02_dp_tests_2gpu_before_tolerance_rule.log):
+    # the comparison would test the noise, not the exchange.
+    return 1e-8 if hidden == 64 else 1.0
+
+
 def _worker(rank, world, port, out_dir, use_graph, collective="nccl", hidden=64):
     import torch.distributed as dist
     import cal_b200
@@ -38,7 +47,8 @@ def _worker(rank, world, port, out_dir, use_graph, collective="nccl", hidden=64)
     net = clone_to_cuda(ora, cal_b200, device="cuda:%d" % rank)
     batches = _rank_batches(rank, hidden)
     caps = cal_b200.batch_caps([b for r in range(world) for b in _rank_batches(r, hidden)])
-    tr = cal_b200.Trainer(net, caps, lr=1e-3, process_group=True, use_graph=use_graph, collective=collective)
+    tr = cal_b200.Trainer(net, caps, lr=1e-3, eps=_adam_eps(hidden), process_group=True, use_graph=use_graph,
+                          collective=collective)
     assert tr.collective == collective
     assert tr.fused_small_graphs == (hidden == 128)      # hidden 128: the fused small-graph kernels (csrc/fsg*.cu, head_ro.cu)
     for s in range(STEPS):
@@ -107,7 +117,8 @@ def test_dp_world2_matches_oracle_average(tmp_path, use_graph, collective, hidde
     # oracle emulation: one replica per rank (own BatchNorm statistics), shared averaged gradients
     ora, _, _ = random_case(seed=299, hidden=hidden, batch_size=24)
     reps = [copy.deepcopy(ora) for _ in range(world)]
-    opts = [torch.optim.Adam(r.parameters(), lr=1e-3) for r in reps]
+    opts = [torch.optim.Adam(r.parameters(), lr=1e-3, eps=_adam_eps(hidden)) for r in reps]
+    init = {n: p.detach().clone() for n, p in ora.named_parameters()}
     data = [_rank_batches(r, hidden) for r in range(world)]
     for s in range(STEPS):
         for r in range(world):
@@ -120,11 +131,13 @@ def test_dp_world2_matches_oracle_average(tmp_path, use_graph, collective, hidde
                 p.grad = avg.clone()
         for o in opts:
             o.step()
-    # Adam normalises every gradient entry by its own running magnitude, so where the rank-averaged gradient nearly
-    # cancels (bn_feat.bias, the KL head at hidden 128) fp32 rounding noise of the gradient moves the parameter by up
-    # to ~lr per step whatever the kernel: measured 5.8e-4 (DP) and 4.9e-4 / 8.9e-4 (one GPU, tiled / fused kernels,
-    # tools/debug_traj.py, profiles/r02_traj.txt) of the tensor's largest entry after 3 steps.  The replica identity
-    # above is the exchange's own property and stays bit-exact.
-    tol = 1e-4 if hidden == 64 else 2e-3
     for n, p in reps[0].named_parameters():
-        assert rel_err(got[0][n], p.detach()) < tol, n
+        if hidden == 64:                                  # default Adam: the parameters themselves
+            assert rel_err(got[0][n], p.detach()) < 1e-4, n
+            continue
+        # linear regime: the parameter UPDATES (value - initial value), relative to the tensor's largest update
+        du_got, du_ref = got[0][n] - init[n], p.detach() - init[n]
+        if float(du_ref.abs().max()) == 0.0:
+            assert float(du_got.abs().max()) == 0.0, n
+        else:
+            assert rel_err(du_got, du_ref) < 1e-3, n

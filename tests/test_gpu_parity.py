@@ -510,6 +510,28 @@ def test_trainer_graph_replay_matches_oracle_trajectory(hidden):
     assert len(tr._graphs) == 1               # one captured graph served all host batches
 
 
+@pytest.mark.parametrize("use_graph", [True, False], ids=["graph", "eager"])
+def test_trainer_prep_ahead_is_bit_identical(use_graph):
+    """Trainer.step(cur, next): the next batch's cal_prep runs on a forked branch beside this step's update and the next
+    step skips it -- same parameters, bit for bit, as the plain loop (every batch prepared exactly once either way)."""
+    M, O = _mods()
+    ora, b0, _ = random_case(seed=75, hidden=128, batch_size=32)
+    batches = [b0] + [random_case(seed=76 + i, hidden=128, batch_size=32)[1] for i in range(2)]
+    out = []
+    for ahead in (False, True):
+        net = clone_to_cuda(ora, M)
+        tr = M.Trainer(net, M.batch_caps(batches), lr=1e-3, use_graph=use_graph)
+        dev = [tr.upload(b, perm=list(range(b.num_graphs))) for b in batches]
+        for step in range(7):
+            cur, nxt = dev[step % 3], dev[(step + 1) % 3]
+            tr.step(cur, nxt if ahead else None)
+        tr.step(dev[1])                                   # a step without a hint after hinted ones
+        torch.cuda.synchronize()
+        tr.check()
+        out.append(net.engine.flat.clone())
+    assert torch.equal(out[0], out[1])
+
+
 def test_full_size_properties_cfg1():
     """BASELINE.json cfg 1/2 size (B=128, H=128, L=3): size-independent properties + oracle."""
     M, O = _mods()
