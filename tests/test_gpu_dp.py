@@ -131,13 +131,22 @@ def test_dp_world2_matches_oracle_average(tmp_path, use_graph, collective, hidde
                 p.grad = avg.clone()
         for o in opts:
             o.step()
+    bad = []
     for n, p in reps[0].named_parameters():
         if hidden == 64:                                  # default Adam: the parameters themselves
             assert rel_err(got[0][n], p.detach()) < 1e-4, n
             continue
         # linear regime: the parameter UPDATES (value - initial value), relative to the tensor's largest update
+        # (+ 4 ulp of the parameter: a weight near 1 moves by ~1e-4 in three steps, so one fp32 ulp of the parameter is
+        # already 1e-3 of its update -- profiles/r02_traj_eps1_rank1.txt: "param err 9.2e-08, update err 1.0e-03")
         du_got, du_ref = got[0][n] - init[n], p.detach() - init[n]
-        if float(du_ref.abs().max()) == 0.0:
-            assert float(du_got.abs().max()) == 0.0, n
-        else:
-            assert rel_err(du_got, du_ref) < 1e-3, n
+        # 2e-2: with 24 graphs (~600 nodes) per rank ONE ReLU whose pre-activation sits within an ulp of zero and flips
+        # between two correct fp32 evaluations moves a backbone weight gradient by ~1/600 of its largest entry (measured:
+        # 0.2 - 0.7 % on conv_feat / convs.*.weight, none on the heads; the parity tests pin the pattern instead,
+        # cal_oracle.RELU_OVERRIDE).  A wrong average (x2), a missing rank or a rank-order mix-up is >= 10 %.
+        bound = 2e-2 * float(du_ref.abs().max()) + 4 * 1.1920929e-07 * float(p.detach().abs().max())
+        err = float((du_got - du_ref).abs().max())
+        if err > bound:
+            bad.append("%s: update err %.3e > %.3e (max update %.3e, max param %.3e)"
+                       % (n, err, bound, float(du_ref.abs().max()), float(p.detach().abs().max())))
+    assert not bad, "\n".join(bad)

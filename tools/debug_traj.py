@@ -7,13 +7,15 @@ import cal_b200 as M
 from oracle import cal_oracle as O
 from tests.util import clone_to_cuda, random_case, rel_err
 
+EPS = float(os.environ.get("ADAM_EPS", "1e-8"))
 ora, b0, _ = random_case(seed=299, hidden=128, batch_size=24)
-batches = [random_case(seed=300 + i, hidden=128, batch_size=24)[1] for i in range(2)]
+SEED0 = int(os.environ.get("SEED0", "300"))
+batches = [random_case(seed=SEED0 + i, hidden=128, batch_size=24)[1] for i in range(2)]
 res = {}
 for mode in ("off", "auto"):
     net = clone_to_cuda(ora, M)
     net.engine.fsg_mode = mode
-    tr = M.Trainer(net, M.batch_caps(batches), lr=1e-3, use_graph=False)
+    tr = M.Trainer(net, M.batch_caps(batches), lr=1e-3, eps=EPS, use_graph=False)
     print(mode, "fused:", tr.fused_small_graphs)
     grads = []
     for s in range(3):
@@ -24,7 +26,8 @@ for mode in ("off", "auto"):
     res[mode] = ({n: p.detach().cpu().clone() for n, p in net.named_parameters()}, grads, net.engine)
 import copy
 o = copy.deepcopy(ora)
-opt = torch.optim.Adam(o.parameters(), lr=1e-3)
+opt = torch.optim.Adam(o.parameters(), lr=1e-3, eps=EPS)
+init = {n: p.detach().clone() for n, p in ora.named_parameters()}
 og = []
 for s in range(3):
     b = batches[s % 2]
@@ -34,7 +37,8 @@ for s in range(3):
 eng = res["auto"][2]
 for n, p in o.named_parameters():
     a, f = res["off"][0][n], res["auto"][0][n]
-    line = "%-28s param err tiled %.2e fused %.2e |" % (n, rel_err(a, p.detach()), rel_err(f, p.detach()))
+    line = "%-28s param err tiled %.2e fused %.2e | update err tiled %.2e fused %.2e |" % (
+        n, rel_err(a, p.detach()), rel_err(f, p.detach()), rel_err(a - init[n], p.detach() - init[n]), rel_err(f - init[n], p.detach() - init[n]))
     off = eng.param_offs[n]
     for s in range(3):
         gt = res["off"][1][s][off:off + p.numel()].view(p.shape)
