@@ -433,6 +433,7 @@ def run_gpu(a, rank, local_rank, world):
             last = None
             for i in range(a.steps):
                 last = fn(hosts[i % len(hosts)])
+            tr.pipe_flush()                              # (the pipelined path issues a batch's step one call late)
             e1.record()
             barrier()
             tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -441,7 +442,10 @@ def run_gpu(a, rank, local_rank, world):
             return float(tt.item()), last
         for i in range(max(3, a.warmup // 2)):
             tr.step_host(hosts[i % len(hosts)])
-            tr.step_host_async(hosts[i % len(hosts)])
+        for rnd in range(3):                             # every (staging buffer, follower, prepared?) graph gets captured:
+            for i in range(4):                           # 4 calls + flush start the next round one buffer later
+                tr.step_host_async(hosts[i % len(hosts)])
+            tr.pipe_flush()
         # (a) pipelined: H2D of batch i+1 on a copy stream overlaps step i; loss parts of every step
         #     land in a pinned ring; the host only waits when the ring (16 steps) is full
         ms_p, slot = timed(tr.step_host_async)
@@ -452,7 +456,8 @@ def run_gpu(a, rank, local_rank, world):
                "h2d_bytes_per_step": int(tr.layout.nbytes), "d2h_bytes_per_step": 32,
                "ms_per_step": ms_p / a.steps,
                "api": "Trainer.step_host_async(pinned packed batch): cudaMemcpyAsync H2D on a copy stream into a "
-                      "double-buffered staging area + captured step + loss parts D2H into a pinned ring, every step",
+                      "triple-buffered staging area + captured step (the follower's structure preparation rides beside the "
+                      "update) + loss parts D2H into a pinned ring, every step; all K steps issued and flushed inside the timed region",
                "sync_every_step": {"value": a.steps * graphs_per_step * world / (ms_s * 1e-3),
                                    "ms_per_step": ms_s / a.steps,
                                    "api": "Trainer.step_host(..., sync=True): same copies, host waits for every step's loss"},

@@ -117,6 +117,31 @@ __device__ __forceinline__ void pdl_sync() {
   pdl_trigger();
 }
 
+// -DCAL_TIMELINE builds: block 0 / thread 0 of the step's kernels stamp %globaltimer (ns, low 30 bits) into
+// status[96 + id] -- the live schedule of one graph-replayed step (tools/timeline.py); compiled out otherwise.
+#ifdef CAL_TIMELINE
+#define CAL_TL(statusp, id)                                                          \
+  do {                                                                               \
+    if (threadIdx.x == 0) {                                                          \
+      unsigned long long tl_;                                                        \
+      asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(tl_));                      \
+      (statusp)[96 + (id)] = (int)(tl_ & 0x3fffffffull);                             \
+    }                                                                                \
+  } while (0)
+// per-CTA stamps of the two fused kernels: int[(kern * 160 + block) * 8 + slot] in the (idle) CAL_WS_D region
+#define CAL_TLC(c, kern, slot)                                                       \
+  do {                                                                               \
+    if (threadIdx.x == 0) {                                                          \
+      unsigned long long tl_;                                                        \
+      asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(tl_));                      \
+      reinterpret_cast<int*>((c).D)[((kern) * 160 + blockIdx.x) * 8 + (slot)] = (int)(tl_ & 0x3fffffffull); \
+    }                                                                                \
+  } while (0)
+#else
+#define CAL_TL(statusp, id) do { } while (0)
+#define CAL_TLC(c, kern, slot) do { } while (0)
+#endif
+
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

@@ -250,6 +250,8 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
   umma::fence_before_sync();
   FSG_TDECL
   pdl_sync();                                                         // the weight images and the plan
+  if (blockIdx.x == 0) CAL_TL(c.status, 2);
+  CAL_TLC(c, 0, 0);
   FSG_T(0);                                                           // 0: dependency wait (set-up overlapped)
   __syncthreads();
   umma::fence_after_sync();
@@ -547,6 +549,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
       if (br == 0) {
         if (c.train) {
           fsg_wait_total_fx(ws, L, G, 4 * FH, sTot);
+          CAL_TLC(c, 0, 1);
           fsg_bn_finalize(c, L + 1, N, pre_m, sTot, sc0, sh0, 0);
           fsg_bn_finalize(c, L + 2, N, pre_m, sTot + 2 * FH, sc1, sh1, FH);
         } else if (t < FH) {
@@ -632,12 +635,15 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
     }
   }
   FSG_TDUMP(c, 48);
+  if (blockIdx.x == 0) CAL_TL(c.status, 3);
+  CAL_TLC(c, 0, 2);
 
   // ---- teardown: TMEM, and the last CTA re-arms the all-reduce counters for the next launch ----
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
   if (active) fsg_rearm(ws, G, 0, L + 1);
+  CAL_TLC(c, 0, 3);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -654,7 +660,10 @@ __global__ void __launch_bounds__(256) k_fsg_prep(const Ctx c, const int n_img_b
   const FsgWs ws = fsg_ws(c);
   const int t = threadIdx.x;
   const int L = c.L;
-  if ((int)blockIdx.x >= n_img_blocks) pdl_sync();                      // the plan block reads the structure
+  if ((int)blockIdx.x >= n_img_blocks) {
+    pdl_sync();                                                         // the plan block reads the structure
+    CAL_TL(c.status, 1);
+  }
   if ((int)blockIdx.x < n_img_blocks) {
     const int img = blockIdx.x >> 3, sub = blockIdx.x & 7;              // 8 blocks of 2048 elements per image
     float* dst;

@@ -298,6 +298,8 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
   umma::fence_before_sync();
   FSG_TDECL
   pdl_sync();
+  if (blockIdx.x == 0) CAL_TL(c.status, 8);
+  CAL_TLC(c, 1, 0);
   FSG_T(0);                                                           // 0: dependency wait (set-up overlapped)
   __syncthreads();
   umma::fence_after_sync();
@@ -576,6 +578,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
     // ================= stage 4: attention backward -> gradient rows of the top backbone layer =================
     const long long go_c = c.bn_gamma[L + 1], bo_c = c.bn_beta[L + 1], go_o = c.bn_gamma[L + 2], bo_o = c.bn_beta[L + 2];
     fsg_wait_total_fx(ws, 12, G, 4 * FH, sTot);
+    CAL_TLC(c, 1, 4);
     fsg_bn_bwd_finalize(c, L + 1, N, go_c, bo_c, sTot, sVec + 4 * FH, sVec + 5 * FH, 0);
     fsg_bn_bwd_finalize(c, L + 2, N, go_o, bo_o, sTot + 2 * FH, sVec + 6 * FH + 4 * FH, sVec + 6 * FH + 5 * FH, FH);
     __syncthreads();
@@ -814,6 +817,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
       FSG_T(3);
       const long long go_l = c.bn_gamma[1 + l], bo_l = c.bn_beta[1 + l];
       fsg_wait_total_fx(ws, 13 + (L - 1 - l), G, 2 * FH, sTot);
+      if (l == 0) CAL_TLC(c, 1, 1);
       fsg_bn_bwd_finalize(c, 1 + l, N, go_l, bo_l, sTot, vin + 4 * FH, vin + 5 * FH, 0);
       umma::mbar_wait(&bar_dw, par_d);
       par_d ^= 1u;
@@ -878,12 +882,15 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
     FSG_T(15);                                                        // 15: input transform backward
   }
   FSG_TDUMP(c, 64);
+  if (blockIdx.x == 0) CAL_TL(c.status, 9);
+  CAL_TLC(c, 1, 2);
 
   // ---- teardown: TMEM, and the last CTA re-arms the all-reduce counters for the next launch ----
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, kTmemColsB);
   if (active) fsg_rearm(ws, G, 12, 13 + L);
+  CAL_TLC(c, 1, 3);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -903,6 +910,7 @@ struct FsgRedTable {
 
 __global__ void __launch_bounds__(1024) k_fsg_grad_reduce(const Ctx c, const FsgRedTable tb, const int n_generic) {
   pdl_sync();
+  if (blockIdx.x == 0) CAL_TL(c.status, 10);
   __shared__ float s_a[4][256], s_b[4][256];
   const FsgWs ws = fsg_ws(c);
   const int np = ws.plan[1] != 0 ? ws.plan[0] : 0;

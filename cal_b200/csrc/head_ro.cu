@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(RT, 1) k_ro_fwd(const Ctx c) {
   umma::fence_before_sync();
   FSG_TDECL
   pdl_sync();
+  if (blockIdx.x == 0) CAL_TL(c.status, 4);
   FSG_T(0);                                              // 0: dependency wait
   __syncthreads();
   umma::fence_after_sync();
@@ -461,6 +462,7 @@ __global__ void __launch_bounds__(RT, 1) k_ro_fwd(const Ctx c) {
   }
   FSG_T(5);                                              // 5: log-softmax, loss
   FSG_TDUMP(c, 80);
+  if (blockIdx.x == 0) CAL_TL(c.status, 5);
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, 256);
@@ -531,6 +533,7 @@ __global__ void __launch_bounds__(RT, 1) k_ro_bwd(const Ctx c) {
   umma::fence_before_sync();
   FSG_TDECL
   pdl_sync();
+  if (blockIdx.x == 0) CAL_TL(c.status, 6);
   FSG_T(0);                                              // 0: dependency wait
   __syncthreads();
   umma::fence_after_sync();
@@ -832,6 +835,7 @@ __global__ void __launch_bounds__(RT, 1) k_ro_bwd(const Ctx c) {
     if (blockIdx.x == 1 && threadIdx.x == 0)
       for (int q_ = 0; q_ < 8; ++q_) c.status[120 + q_] = FSG_TVAL(q_);
   }
+  if (blockIdx.x == 0) CAL_TL(c.status, 7);
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, 256);

@@ -352,6 +352,7 @@ __global__ void __launch_bounds__(kPrepT) k_prep_small(const Ctx c) {
   const int lane = t & 31, warp = t >> 5;
   PT_DECL
   if (t == 0) s_status = 0;
+  if (sj == 0) CAL_TL(c.status, 0);
   for (int n = t; n < N; n += T) s_cin[n] = s_cout[n] = 0;
   __syncthreads();
   PT_MARK();                                           // 0: dependency wait + zero
@@ -550,6 +551,7 @@ __global__ void __launch_bounds__(kPrepT) k_prep_small(const Ctx c) {
       c.status[0] = s_status;
       c.status[1] = c.status[2] = c.status[3] = 0;
     }
+    CAL_TL(c.status, 12);
 #ifdef CAL_PHASE_TIMING
     if (t == 0) for (int q_ = 0; q_ < pt_i; ++q_) c.status[96 + q_] = (int)pt_v[q_];
 #endif

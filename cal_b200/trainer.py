@@ -404,14 +404,21 @@ class Trainer:
                                               eng.bn_buf.data_ptr(), eng.nbt.data_ptr(), C.byref(cb),
                                               _lib.CAL_F_TRAIN | _lib.CAL_F_LOSS, 0, eng.ws.data_ptr(), eng.ws_bytes, s),
                        "cal_causal_forward")
-            _lib.check(lib.cal_causal_backward(d, caps, C.byref(eng.po), eng.flat.data_ptr(), C.byref(cb), 0,
-                                               eng.flat_grad.data_ptr(), 0, eng.ws.data_ptr(), eng.ws_bytes, s),
-                       "cal_causal_backward")
+            fork = next_ptr is not None and part == "all"
+            last = eng.L + 6                                   # backward stage "grad_reduce"
+
+            def bwd(flags):
+                _lib.check(lib.cal_causal_backward(d, caps, C.byref(eng.po), eng.flat.data_ptr(), C.byref(cb), 0,
+                                                   eng.flat_grad.data_ptr(), flags, eng.ws.data_ptr(), eng.ws_bytes, s),
+                           "cal_causal_backward")
+            bwd(_lib.stages_flag(0, last - 1) if fork else 0)
             eng.gen += 1
         side = None
         if next_ptr is not None and part == "all":
-            # fork: the next batch's structure preparation runs beside the update (it writes only workspace regions
-            # that the finished backward pass no longer reads; the update touches the flat buffers / the exchange region)
+            # fork: the next batch's structure preparation runs beside the block-order gradient reduction and the
+            # update.  It writes only workspace regions (CSR, norms, graph_ptr, input-feature statistics, status) that
+            # nothing after the last backward kernel reads: the reduction reads the partial gradients and the batch
+            # dims, the update touches the flat buffers / the exchange region.
             main = torch.cuda.current_stream(self.device)
             side = self._side_stream()
             side.wait_stream(main)
@@ -421,6 +428,7 @@ class Trainer:
                     cbn.gat_keep = gat_keep.data_ptr()
                 _lib.check(lib.cal_prep(C.byref(eng.desc), C.byref(eng.caps), C.byref(cbn), eng.ws.data_ptr(), eng.ws_bytes,
                                         side.cuda_stream), "cal_prep")
+            bwd(_lib.stages_flag(last, last))
         if self.peer is not None:
             if part in ("all", "update"):
                 self.peer.adam_step(eng, 0.0, self.betas, self.eps, self.weight_decay, lr_device=self.lr_dev)
@@ -463,6 +471,7 @@ class Trainer:
         ``step(next_packed, ...)`` skips it -- every batch is still prepared exactly once.  (Single captured graph
         per step only: not with the two-graph NCCL replay.)"""
         self._check_alive()
+        self.pipe_flush()                                # (no-op unless a step_host_async batch is pending)
         if packed_dev.device != self.device:
             raise _lib.CalError("cal_b200: Trainer.step needs a device-resident packed batch (use step_host)")
         keep = self._gat_keep_for(None)
@@ -557,6 +566,7 @@ class Trainer:
         (as one CUDA-graph replay) between two CUDA events on the launching stream.  Model state is restored afterwards.
         -> list of (name, kernel launches per issue, average milliseconds per issue)."""
         eng, lib = self.eng, self.eng.lib
+        self.pipe_flush()
         self._prepped_ptr = None
         saved = self._save_state()
         keep = self._gat_keep_for(None)
@@ -618,49 +628,77 @@ class Trainer:
 
     # ---- pipelined end-to-end path: H2D of batch i+1 overlaps the step of batch i ----
     PIPE_RING = 16
+    PIPE_STAGES = 3
 
     def _pipe_init(self):
         dev = self.device
+        n = self.PIPE_STAGES
         self._pipe = {
             "i": 0,
-            "stage": [torch.zeros(self.layout.nbytes, dtype=torch.uint8, device=dev) for _ in range(2)],
+            "stage": [torch.zeros(self.layout.nbytes, dtype=torch.uint8, device=dev) for _ in range(n)],
             "copy": torch.cuda.Stream(dev),
-            "ready": [torch.cuda.Event() for _ in range(2)],
-            "done": [torch.cuda.Event() for _ in range(2)],
+            "ready": [torch.cuda.Event() for _ in range(n)],
+            "done": [torch.cuda.Event() for _ in range(n)],
             "ring": torch.zeros(self.PIPE_RING, 8, dtype=torch.float32).pin_memory(),
             "ring_ev": [torch.cuda.Event() for _ in range(self.PIPE_RING)],
+            "pending": None,
         }
 
     def step_host_async(self, packed_host):
-        """Enqueue one end-to-end step without synchronising the host: the packed batch is uploaded
-        on a copy stream into one of two staging buffers (overlapping the previous step), the step
-        runs on the current stream, and its loss parts / correct counts are copied into a pinned
-        ring slot.  Returns the ring slot index; ``pipe_result(slot)`` waits for it."""
+        """Enqueue one end-to-end step without synchronising the host.  The packed batch is uploaded on a copy
+        stream into one of three staging buffers (overlapping earlier steps) and its loss parts / correct counts
+        are copied into a pinned ring slot after its step.  Returns the ring slot index; ``pipe_result(slot)``
+        waits for it.
+
+        The step of a batch is ISSUED one call late -- together with the upload of the batch that follows it -- so
+        that the follower's structure preparation can ride beside this step's gradient reduction and update
+        (``step(cur, next)``); ``pipe_result`` / ``pipe_flush`` (and every other entry point of the trainer) issue
+        the step that is still pending.  Every batch is prepared and stepped exactly once, in call order."""
         if not hasattr(self, "_pipe"):
             self._pipe_init()
         p = self._pipe
         i = p["i"]
-        b, r = i % 2, i % self.PIPE_RING
+        b, r = i % self.PIPE_STAGES, i % self.PIPE_RING
         main = torch.cuda.current_stream(self.device)
         if i >= self.PIPE_RING:
             p["ring_ev"][r].synchronize()                # bound the host run-ahead to the ring depth
         cs = p["copy"]
-        if i >= 2:
+        if i >= self.PIPE_STAGES:
             cs.wait_event(p["done"][b])                  # the step that last read this staging buffer
         with torch.cuda.stream(cs):
             p["stage"][b].copy_(packed_host, non_blocking=True)
             p["ready"][b].record(cs)
         main.wait_event(p["ready"][b])
-        self.step(p["stage"][b])
-        p["done"][b].record(main)
-        p["ring"][r].copy_(self.eng.loss_parts_full(), non_blocking=True)
-        p["ring_ev"][r].record(main)
+        pend = p["pending"]
+        p["pending"] = None
+        if pend is not None:
+            self._pipe_issue(pend, b)
+        p["pending"] = (b, r)
         p["i"] = i + 1
         return r
 
+    def _pipe_issue(self, pend, nxt):
+        p = self._pipe
+        b, r = pend
+        main = torch.cuda.current_stream(self.device)
+        self.step(p["stage"][b], p["stage"][nxt] if nxt is not None else None)
+        p["done"][b].record(main)
+        p["ring"][r].copy_(self.eng.loss_parts_full(), non_blocking=True)
+        p["ring_ev"][r].record(main)
+
+    def pipe_flush(self):
+        """Issue the step of the most recent ``step_host_async`` batch if it is still pending."""
+        p = getattr(self, "_pipe", None)
+        if p is not None and p["pending"] is not None:
+            pend, p["pending"] = p["pending"], None
+            self._pipe_issue(pend, None)
+
     def pipe_result(self, slot):
-        self._pipe["ring_ev"][slot].synchronize()
-        return self._pipe["ring"][slot]
+        p = self._pipe
+        if p["pending"] is not None and p["pending"][1] == slot:
+            self.pipe_flush()
+        p["ring_ev"][slot].synchronize()
+        return p["ring"][slot]
 
     # ---- device-resident epochs: collate on the GPU, one captured graph for every step ----
     def begin_epoch(self, store, order, graphs_per_step, perms="draw"):
@@ -717,6 +755,7 @@ class Trainer:
     def step_epoch(self):
         """One training step on the next ``graphs_per_step`` graphs of the epoch (asynchronous)."""
         self._check_alive()
+        self.pipe_flush()
         self._prepped_ptr = None
         ep = self._epoch
         if ep["done"] >= ep["steps"]:
@@ -775,6 +814,7 @@ class Trainer:
     def check(self):
         """Raise on a data-dependent violation of the last step (status word: node id out of range, unsorted
         ``batch``, capacity overflow) or a failed peer exchange.  Synchronises; called by ``end_epoch``."""
+        self.pipe_flush()
         st = self.eng.status()
         if st != 0:
             raise _lib.CalError("cal_b200: the last step reported status bits 0x%x (1 = edge endpoint out of range, "
@@ -785,11 +825,13 @@ class Trainer:
     def metrics(self):
         """f32[7] device view: loss, c_loss, o_loss, co_loss, correct_c, correct_o, correct_co of
         the most recent step."""
+        self.pipe_flush()
         return self.eng.loss_parts()
 
     # ---- evaluation (train_causal.py:202-223) ----
     @torch.no_grad()
     def eval_batch(self, data_dev, eval_random=False):
+        self.pipe_flush()
         self._prepped_ptr = None                         # (the module path runs cal_prep on its own batch)
         was = self.model.training
         self.model.eval()

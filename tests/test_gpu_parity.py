@@ -532,6 +532,43 @@ def test_trainer_prep_ahead_is_bit_identical(use_graph):
     assert torch.equal(out[0], out[1])
 
 
+def test_pipelined_host_path_matches_the_synchronous_loop():
+    """Trainer.step_host_async (upload on a copy stream into three staging buffers, a batch's step issued one call
+    late so that its follower's cal_prep rides beside the update, loss parts into a pinned ring) against
+    Trainer.step_host(sync=True) on the same pinned batches: same loss parts every step and the same parameters,
+    bit for bit; pipe_result of the newest slot issues the pending step; a plain step() after async calls flushes first."""
+    M, O = _mods()
+    ora, b0, _ = random_case(seed=85, hidden=128, batch_size=32)
+    batches = [b0] + [random_case(seed=86 + i, hidden=128, batch_size=32)[1] for i in range(4)]
+    order = [0, 1, 2, 3, 4, 0, 2, 4, 1, 3, 0, 1, 2, 3, 4, 0, 1, 2, 3, 4, 4, 3]       # 22 steps > ring depth 16
+    res, flat = [], []
+    for mode in ("sync", "async"):
+        net = clone_to_cuda(ora, M)
+        tr = M.Trainer(net, M.batch_caps(batches), lr=1e-3)
+        hosts = [tr.pack(b, perm=list(range(b.num_graphs))) for b in batches]
+        losses = []
+        if mode == "sync":
+            for k in order:
+                losses.append(tr.step_host(hosts[k], sync=True).clone())
+        else:
+            slots = []
+            for n, k in enumerate(order):
+                slots.append(tr.step_host_async(hosts[k]))
+                if n >= 3:                                # read results three steps late (keeps the pipeline full)
+                    losses.append(tr.pipe_result(slots[n - 3]).clone())
+            for n in range(len(order) - 3, len(order)):
+                losses.append(tr.pipe_result(slots[n]).clone())       # the last one issues the pending step
+        dev0 = tr.upload(batches[1], perm=list(range(batches[1].num_graphs)))
+        tr.step_host_async(hosts[2])                      # left pending ...
+        tr.step(dev0)                                     # ... and flushed by the next entry point, in call order
+        torch.cuda.synchronize()
+        tr.check()
+        res.append(torch.stack(losses))
+        flat.append(net.engine.flat.clone())
+    assert torch.equal(res[0], res[1])
+    assert torch.equal(flat[0], flat[1])
+
+
 def test_full_size_properties_cfg1():
     """BASELINE.json cfg 1/2 size (B=128, H=128, L=3): size-independent properties + oracle."""
     M, O = _mods()
