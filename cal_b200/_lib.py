@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("CAL_B200_LIB") or os.path.join(HERE, "libcal_b200.so"
 CAL_MAX_LAYERS = 8
 CAL_MAX_BN = 1 + CAL_MAX_LAYERS + 2 + 6
 CAL_MODEL_GCN, CAL_MODEL_GAT, CAL_MODEL_GIN = 0, 1, 2
-CAL_F_TRAIN, CAL_F_LOSS = 1, 2
+CAL_F_TRAIN, CAL_F_LOSS, CAL_F_FSG_READY, CAL_F_NO_OVERLAP = 1, 2, 4, 8
 CAL_ST_BAD_NODE, CAL_ST_BAD_BATCH, CAL_ST_CAPACITY = 1, 2, 4
 
 # enum cal_ws_region, in header order
@@ -33,6 +33,7 @@ EXPORTS = [
     "cal_launch_count", "cal_stage_count", "cal_stage_name",
     "cal_dp_region_bytes", "cal_dp_alloc", "cal_dp_free", "cal_dp_export", "cal_dp_import", "cal_dp_unmap",
     "cal_dp_adam_step", "cal_dp_read_error", "cal_collate", "cal_collate_flush", "cal_selftest_umma",
+    "cal_image_sink_init", "cal_adam_step_images", "cal_dp_adam_step_images",
 ]
 CAL_MAX_WORLD, CAL_DP_HANDLE_BYTES = 16, 64
 CAL_PASS_FORWARD, CAL_PASS_BACKWARD = 0, 1
@@ -96,6 +97,16 @@ class DpComm(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("region", C.c_void_p * CAL_MAX_WORLD)]
 
 
+class ImageEntry(C.Structure):
+    _fields_ = [("offset", C.c_int64), ("dst_t", C.c_void_p), ("dst_n", C.c_void_p), ("rows", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class ImageSink(C.Structure):
+    """cal_image_sink: where an optimizer step writes the fused small-graph path's operand images."""
+    _fields_ = [("count", C.c_int32), ("reserved", C.c_int32), ("entry", ImageEntry * 16)]
+
+
 class CalError(RuntimeError):
     pass
 
@@ -134,6 +145,10 @@ def load():
     lib.cal_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                   C.c_float, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                   C.c_void_p]
+    lib.cal_adam_step_images.restype = C.c_int
+    lib.cal_adam_step_images.argtypes = lib.cal_adam_step.argtypes[:-1] + [P(ImageSink), C.c_void_p]
+    lib.cal_image_sink_init.restype = C.c_int
+    lib.cal_image_sink_init.argtypes = [P(ModelDesc), P(Caps), P(ParamOffsets), C.c_void_p, C.c_size_t, P(ImageSink)]
     lib.cal_launch_count.restype = C.c_uint64
     lib.cal_stage_count.restype = C.c_int
     lib.cal_stage_count.argtypes = [P(ModelDesc), C.c_int]
@@ -164,12 +179,14 @@ def load():
     lib.cal_dp_adam_step.argtypes = [P(DpComm), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_float, C.c_float,
                                      C.c_float, C.c_void_p]
+    lib.cal_dp_adam_step_images.restype = C.c_int
+    lib.cal_dp_adam_step_images.argtypes = lib.cal_dp_adam_step.argtypes[:-1] + [P(ImageSink), C.c_void_p]
     lib.cal_dp_read_error.restype = C.c_int
     lib.cal_dp_read_error.argtypes = [P(DpComm), C.c_void_p]
     lib.cal_selftest_umma.restype = C.c_int
     lib.cal_selftest_umma.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                       C.c_void_p]
-    if lib.cal_abi_version() != 2:
+    if lib.cal_abi_version() != 3:
         raise CalError("cal_b200: ABI version mismatch")
     _lib = lib
     return lib

@@ -276,6 +276,30 @@ int cal_workspace_region(const cal_model_desc* m, const cal_caps* caps, int regi
   return CAL_OK;
 }
 
+int cal_image_sink_init(const cal_model_desc* m, const cal_caps* caps, const cal_param_offsets* po, void* workspace,
+                        size_t ws_bytes, cal_image_sink* sink) {
+  if (sink == nullptr) return CAL_ENULL;
+  memset(sink, 0, sizeof(*sink));
+  int rc = validate_model(m);
+  if (rc != CAL_OK) return rc;
+  rc = check_offsets(m, po);
+  if (rc != CAL_OK) return rc;
+  alignas(16) static const int64_t no_data[2] = {0, 0};             // (the batch pointers are only validated here, never read)
+  cal_batch nb;
+  memset(&nb, 0, sizeof(nb));
+  nb.dims = reinterpret_cast<const int32_t*>(no_data);
+  nb.feat = reinterpret_cast<const float*>(no_data);
+  nb.edge_index = no_data;
+  nb.batch = no_data;
+  Ctx c;
+  rc = build_ctx(m, caps, po, nullptr, &nb, workspace, ws_bytes, &c);
+  if (rc != CAL_OK) return rc;
+  c.train = 1;
+  if (!(c.fsg_bwd_on && readout_runs_ro(c))) return CAL_OK;          // count = 0: the fused path is not taken
+  fsg_fill_image_sink(c, sink);
+  return CAL_OK;
+}
+
 int cal_prep(const cal_model_desc* m, const cal_caps* caps, const cal_batch* b, void* workspace, size_t ws_bytes,
              void* stream) {
   Ctx c;
@@ -284,17 +308,19 @@ int cal_prep(const cal_model_desc* m, const cal_caps* caps, const cal_batch* b, 
   return launch_prep(c, (cudaStream_t)stream);
 }
 
-int cal_read_status(const cal_model_desc* m, const cal_caps* caps, const void* workspace, void* stream) {
+int cal_read_status(const cal_model_desc* m, const cal_caps* caps, void* workspace, void* stream) {
   Layout lay;
   int rc = compute_layout(m, caps, &lay);
   if (rc != CAL_OK) return rc;
   if (workspace == nullptr) return CAL_ENULL;
-  int st = 0;
-  cudaError_t e = cudaMemcpyAsync(&st, static_cast<const unsigned char*>(workspace) + lay.off[CAL_WS_STATUS], 4,
-                                  cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  // status[0]: the batch prepared last; status[kStSticky]: everything raised since the previous read (cleared here)
+  int st[kStSticky + 1] = {0};
+  unsigned char* base = static_cast<unsigned char*>(workspace) + lay.off[CAL_WS_STATUS];
+  cudaError_t e = cudaMemcpyAsync(st, base, sizeof(st), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (e == cudaSuccess && st[kStSticky] != 0) e = cudaMemsetAsync(base + 4 * kStSticky, 0, 4, (cudaStream_t)stream);
   if (e != cudaSuccess) return (int)e;
-  return st;
+  return st[0] | st[kStSticky];
 }
 
 int cal_causal_forward(const cal_model_desc* m, const cal_caps* caps, const cal_param_offsets* po,
@@ -322,15 +348,18 @@ int cal_causal_forward(const cal_model_desc* m, const cal_caps* caps, const cal_
   const int L = c.L;
   int lo = 0, hi = L + 5;
   stage_range(flags, &lo, &hi);
+  // CAL_F_FSG_READY (include/cal_b200.h): honoured only where stage 0 is k_fsg_prep alone
+  const bool ready = (flags & CAL_F_FSG_READY) != 0 && c.train && c.fsg_bwd_on && readout_runs_ro(c);
   for (int st = lo; st <= hi; ++st) {
     if (st == 0) {
       // (the transposed weight copies of k_param_prep serve the tiled backward and the FFMA readouts; the fused
       // small-graph path reads the operand images of k_fsg_prep instead -- in training mode it skips the launch)
+      if (ready) continue;                               // CAL_F_FSG_READY: the operand images are in place
       if (!(c.train && c.fsg_bwd_on && readout_runs_ro(c))) rc = launch_param_prep(c, s);
-      if (rc == 0 && c.fsg_on) rc = launch_fsg_prep(c, s);
+      if (rc == 0 && c.fsg_on) rc = launch_fsg_prep(c, s, (flags & CAL_F_NO_OVERLAP) != 0);
     } else if (c.fsg_on && st >= 1 && st <= 3 + L) {
       // fused small-graph path: stage "feat" runs the whole forward up to the pooled embeddings (fsg.cu)
-      if (st == 1) rc = launch_fsg_forward(c, s);
+      if (st == 1) rc = launch_fsg_forward(c, s, ready);
     } else if (st == 1) rc = launch_feat_forward(c, s);
     else if (st < 2 + L)
       rc = c.model == CAL_MODEL_GAT ? launch_gat_forward(c, st - 2, s)

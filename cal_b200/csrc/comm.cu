@@ -24,6 +24,7 @@
 #include <string.h>
 
 #include "internal.cuh"
+#include "fsg.cuh"
 
 namespace cal {
 
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(256) k_dp_adam(const DpPeers peers, const int 
                                                  float* __restrict__ v, const long long n, int* __restrict__ step,
                                                  float lr, const float* __restrict__ lr_dev, const float b1,
                                                  const float b2, const float eps, const float wd,
-                                                 const unsigned long long timeout_ns) {
+                                                 const unsigned long long timeout_ns, const cal_image_sink sink) {
   __shared__ float s_c[2];
   __shared__ int s_t;
   __shared__ unsigned int s_seq;
@@ -158,6 +159,10 @@ __global__ void __launch_bounds__(256) k_dp_adam(const DpPeers peers, const int 
     *reinterpret_cast<float4*>(m + i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
     *reinterpret_cast<float4*>(v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
     *reinterpret_cast<float4*>(p + i) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    if (sink.count > 0) {                                            // operand images of the fused small-graph path
+#pragma unroll
+      for (int k = 0; k < 4; ++k) fsg_sink_emit(sink, i + k, pp[k]);
+    }
   }
   // every CTA has read hdr->seq and *step before it arrives here, so the last one may advance them
   __syncthreads();
@@ -240,9 +245,13 @@ extern "C" int cal_dp_read_error(const cal_dp_comm* comm, void* stream) {
   return h.error ? CAL_ETIMEOUT : 0;
 }
 
-extern "C" int cal_dp_adam_step(const cal_dp_comm* comm, float* params, const float* grads, float* exp_avg,
-                                float* exp_avg_sq, int64_t n, int32_t* step, float lr, const float* lr_device,
-                                float beta1, float beta2, float eps, float weight_decay, void* stream) {
+extern "C" int cal_dp_adam_step_images(const cal_dp_comm* comm, float* params, const float* grads, float* exp_avg,
+                                       float* exp_avg_sq, int64_t n, int32_t* step, float lr, const float* lr_device,
+                                       float beta1, float beta2, float eps, float weight_decay,
+                                       const cal_image_sink* sink, void* stream) {
+  cal_image_sink sk = {};
+  if (sink != nullptr) sk = *sink;
+  if (sk.count < 0 || sk.count > 16) return CAL_EINVAL;
   if (!comm || !params || !grads || !exp_avg || !exp_avg_sq || !step) return CAL_ENULL;
   if (comm->world < 1 || comm->world > CAL_MAX_WORLD || comm->rank < 0 || comm->rank >= comm->world) return CAL_EINVAL;
   if (n <= 0 || (n & 3) != 0) return CAL_EINVAL;
@@ -259,8 +268,15 @@ extern "C" int cal_dp_adam_step(const cal_dp_comm* comm, float* params, const fl
   }();
   cal::launch_k(cal::k_dp_adam, dim3(cal::kDpCtas), dim3(256), 0, (cudaStream_t)stream, peers, (int)comm->world,
                 (int)comm->rank, params, grads, exp_avg, exp_avg_sq, (long long)n, step, lr, lr_device, beta1, beta2,
-                eps, weight_decay, timeout_ns);
+                eps, weight_decay, timeout_ns, sk);
   cal::note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int cal_dp_adam_step(const cal_dp_comm* comm, float* params, const float* grads, float* exp_avg,
+                                float* exp_avg_sq, int64_t n, int32_t* step, float lr, const float* lr_device,
+                                float beta1, float beta2, float eps, float weight_decay, void* stream) {
+  return cal_dp_adam_step_images(comm, params, grads, exp_avg, exp_avg_sq, n, step, lr, lr_device, beta1, beta2, eps,
+                                 weight_decay, nullptr, stream);
 }

@@ -18,6 +18,9 @@ constexpr int kMaxStatBlocks = 2 * kSMs;       // cap on CTAs that emit BN parti
 constexpr int kStBadNode = 1;                  // edge endpoint outside [0, N)
 constexpr int kStBadBatch = 2;                 // batch not sorted / outside [0, B)
 constexpr int kStCapacity = 4;                 // N/E/B exceeds the workspace capacity
+// status[0]: the bits of the batch prepared last (cal_prep rewrites it);  status[kStSticky]: every bit raised since the
+// last cal_read_status (which clears it) -- a batch prepared ahead of its step must not hide the bits of the step before
+constexpr int kStSticky = 4;
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -142,6 +145,11 @@ __device__ __forceinline__ void pdl_sync() {
 #define CAL_TLC(c, kern, slot) do { } while (0)
 #endif
 
+__device__ __forceinline__ void raise_status(int* status, int bits) {
+  atomicOr(status, bits);
+  atomicOr(status + kStSticky, bits);
+}
+
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -155,6 +163,18 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface in cudaGetLastError()
+}
+
+// ... without the programmatic edge: the kernel starts after everything before it in the stream has completed (its
+// own griddepcontrol.wait is then a no-op)
+template <typename... KArgs, typename... Args>
+inline void launch_k_plain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -159,9 +159,9 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
   }
   const float bnat0 = c.params[c.po.node_att_b], bnat1 = c.params[c.po.node_att_b + 1];
   const float beat0 = c.params[c.po.edge_att_b], beat1 = c.params[c.po.edge_att_b + 1];
-  // ---- still before the dependency wait: the immediate predecessor (k_fsg_prep) only writes the weight images and the
-  // plan; the structure (cal_prep), the input features and their column totals were complete before it could start.
-  // A block is ONE graph (k_fsg_prep's plan, restated here from the structure so that it need not be waited for). ----
+  // ---- still before the dependency wait: the immediate predecessor (k_fsg_prep) only writes the weight images; the
+  // structure (cal_prep), the input features and their column totals were complete before it could start.
+  // A block is ONE graph. ----
   const int N = imin(imax(c.dims[0], 0), c.Nm);
   int g0 = 0, g1 = 0, n0 = 0, n1 = 0, ie0 = 0, ie1 = 0, oe0 = 0;
   bool own = (int)blockIdx.x < imin(imax(c.dims[2], 0), c.Bm);
@@ -249,17 +249,28 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
   }
   umma::fence_before_sync();
   FSG_TDECL
-  pdl_sync();                                                         // the weight images and the plan
+  pdl_sync();                                                         // the weight images
   if (blockIdx.x == 0) CAL_TL(c.status, 2);
   CAL_TLC(c, 0, 0);
   FSG_T(0);                                                           // 0: dependency wait (set-up overlapped)
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = tmem_slot;
-  const int nblk = ws.plan[0], plan_ok = ws.plan[1];
-  const bool active = own && plan_ok != 0 && (int)blockIdx.x < nblk;
-  if (!plan_ok && blockIdx.x == 0 && t == 0) atomicOr(c.status, kStCapacity);
-  const int G = nblk;
+  const int fx_set = fsg_epoch_begin(ws, 0, 0, L + 1);               // (every CTA of the grid, active or not)
+  // One block per graph: G live blocks.  A live block whose graph does not fit the limits (the caller promised
+  // cal_caps.small_graphs) reports it through the status word and only keeps the all-reduces of the others complete.
+  const int G = imin(imax(c.dims[2], 0), c.Bm);
+  // (opaque to the compiler on purpose: with `active` known before the wait it merges the set-up above into the body
+  // below and the kernel runs 8 % slower -- 47.6 against 43.9 us, measured)
+  int act_ = own ? 1 : 0;
+  asm volatile("" : "+r"(act_));
+  const bool active = act_ != 0;
+  const bool unfit = !own && (int)blockIdx.x < G;
+  if (t == 0 && (int)blockIdx.x < G) {                                // this block's record for the backward kernel
+    int4* info = reinterpret_cast<int4*>(ws.info + (size_t)blockIdx.x * 8);
+    info[0] = make_int4(g0, g1, n0, n1);
+    info[1] = make_int4(ie0, ie1, oe0, own ? 1 : 0);
+  }
   if (active) {
     // weight operand of the input transform
     if (t == 0) {
@@ -338,7 +349,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
     if (!masked) {
       // ---------------- backbone layer l: x_{l+2} = relu(A bn_l(x_{l+1}) W_l + b_l)  (model.py:93-95) ----------------
       if (active) {
-        if (c.train) fsg_publish_fx(ws, l, sPart, 2 * FH);
+        if (c.train) fsg_publish_fx(ws, fx_set, l, G, sPart, 2 * FH);
         const FsgBnPre pre = c.train ? fsg_bn_prefetch(c, 1 + l, 0) : FsgBnPre();
         FSG_T(4);                                                     // 4: publish
         // x_{l+1} rows to the workspace (the backward pass reads them): coalesced, after the publish so that the
@@ -365,7 +376,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
         float* sc = sAff;
         float* sh = sAff + FH;
         if (c.train) {
-          fsg_wait_total_fx(ws, l, G, 2 * FH, sTot);
+          fsg_wait_total_fx(ws, fx_set, l, G, 2 * FH, sTot);
           fsg_bn_finalize(c, 1 + l, N, pre, sTot, sc, sh, 0);
         } else if (t < FH) {
           sc[t] = c.bnf(1 + l, BN_SCALE)[t];
@@ -469,7 +480,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
     }
     __syncthreads();
     FSG_T(10);                                                        // 10: node attention + bnc / bno statistics
-    if (c.train) fsg_publish_fx(ws, L, sPart, 4 * FH);
+    if (c.train) fsg_publish_fx(ws, fx_set, L, G, sPart, 4 * FH, 0);   // (the launch's final site)
     const FsgBnPre pre_m = c.train ? fsg_bn_prefetch(c, t < FH ? L + 1 : L + 2, t < FH ? 0 : FH) : FsgBnPre();
     {
       float4* xg = reinterpret_cast<float4*>(c.Xl(L) + (size_t)n0 * FH);      // x_{L+1} rows to the workspace
@@ -548,7 +559,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
       FSG_T(5);
       if (br == 0) {
         if (c.train) {
-          fsg_wait_total_fx(ws, L, G, 4 * FH, sTot);
+          fsg_wait_total_fx(ws, fx_set, L, G, 4 * FH, sTot);
           CAL_TLC(c, 0, 1);
           fsg_bn_finalize(c, L + 1, N, pre_m, sTot, sc0, sh0, 0);
           fsg_bn_finalize(c, L + 2, N, pre_m, sTot + 2 * FH, sc1, sh1, FH);
@@ -634,37 +645,37 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
       FSG_T(12);                                                      // 12: masked epilogue + pooling
     }
   }
+  if (unfit && t == 0) {                                              // (skipped everything above)
+    raise_status(c.status, kStCapacity);
+    if (c.train) fsg_unfit_arrive(ws, fx_set, G, 0, L, 0);
+  }
   FSG_TDUMP(c, 48);
   if (blockIdx.x == 0) CAL_TL(c.status, 3);
   CAL_TLC(c, 0, 2);
 
-  // ---- teardown: TMEM, and the last CTA re-arms the all-reduce counters for the next launch ----
+  // ---- teardown: TMEM (the all-reduce state needs none: fsg_epoch_begin) ----
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
-  if (active) fsg_rearm(ws, G, 0, L + 1);
   CAL_TLC(c, 0, 3);
 }
 
 // ---------------------------------------------------------------------------------------------
-// Per-step preparation of the path: the block plan (one block per graph) and the pre-split
-// (hi | lo) weight-operand images in the canonical K-major layout the MMA reads.
-//   blocks [0, n_img): 2048 elements of one operand image each;  block n_img: the plan.
+// Per-step preparation of the path: the pre-split (hi | lo) weight-operand images in the canonical K-major layout
+// the MMA reads; every block builds 2048 elements of one image.  (A training loop can have the optimizer kernel
+// write the image words instead: cal_image_sink / CAL_F_FSG_READY.)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_fsg_prep(const Ctx c, const int n_img_blocks, const int fsg_grid) {
-  // The image blocks read only parameters: the optimizer step that wrote them is at least two launches back and
-  // complete by the time this kernel can be scheduled, so they do their work BEFORE the dependency wait -- the
-  // images are built while the predecessor (the structure kernel of cal_prep) still runs.  They still wait before
-  // they release the dependent launch: every kernel of the chain relies on "my predecessor has passed its wait,
-  // so everything before it is complete" (the fused forward reads the structure ahead of its own wait).
+__global__ void __launch_bounds__(256) k_fsg_prep(const Ctx c) {
+  // The blocks read only parameters: the optimizer step that wrote them is at least two launches back and complete by
+  // the time this kernel can be scheduled (cal_prep sits between them; a caller whose cal_prep ran elsewhere passes
+  // CAL_F_NO_OVERLAP), so they do their work BEFORE the dependency wait -- the images are built while the
+  // predecessor (the structure kernel of cal_prep) still runs.  They still wait before they release the dependent
+  // launch: every kernel of the chain relies on "my predecessor has passed its wait, so everything before it is
+  // complete" (the fused forward reads the structure ahead of its own wait).
   const FsgWs ws = fsg_ws(c);
   const int t = threadIdx.x;
   const int L = c.L;
-  if ((int)blockIdx.x >= n_img_blocks) {
-    pdl_sync();                                                         // the plan block reads the structure
-    CAL_TL(c.status, 1);
-  }
-  if ((int)blockIdx.x < n_img_blocks) {
+  {
     const int img = blockIdx.x >> 3, sub = blockIdx.x & 7;              // 8 blocks of 2048 elements per image
     float* dst;
     const float* W;
@@ -699,25 +710,9 @@ __global__ void __launch_bounds__(256) k_fsg_prep(const Ctx c, const int n_img_b
       dst[e] = hi;
       dst[kFsgImgPart + e] = lo;
     }
-    pdl_sync();
-    return;
   }
-  // ---- the plan: one block per graph (thread g describes block g); ok = every graph within the limits ----
-  const int B = imin(imax(c.dims[2], 0), c.Bm);
-  bool ok = B <= fsg_grid;
-  for (int g = t; g < B && g < fsg_grid; g += 256) {
-    const int na = c.graph_ptr[g], nb = c.graph_ptr[g + 1];
-    const int ea = c.in_ptr[na], eb = c.in_ptr[nb];
-    if (nb - na > kFsgRows || eb - ea > kFsgEntries || nb < na) ok = false;
-    int* info = ws.info + (size_t)g * 8;
-    info[0] = g; info[1] = g + 1; info[2] = na; info[3] = nb;
-    info[4] = ea; info[5] = eb; info[6] = c.out_ptr[na]; info[7] = 0;
-  }
-  const int all_ok = __syncthreads_and(ok ? 1 : 0);
-  if (t == 0) {
-    ws.plan[0] = all_ok ? B : 0;
-    ws.plan[1] = all_ok;
-  }
+  if (blockIdx.x == 0) CAL_TL(c.status, 1);
+  pdl_sync();
 }
 
 }  // namespace
@@ -725,15 +720,39 @@ __global__ void __launch_bounds__(256) k_fsg_prep(const Ctx c, const int n_img_b
 int fsg_grid(const Ctx& c) { return imax(1, imin(c.Bm, kSMs)); }
 size_t fsg_region_bytes(int Bm, int L, int F) { return fsg_layout(Bm, L, F).total; }
 
-int launch_fsg_prep(const Ctx& c, cudaStream_t s) {
+// where the optimizer kernels write the image words of the parameters they update (cal_image_sink)
+int fsg_fill_image_sink(const Ctx& c, cal_image_sink* sink) {
+  const FsgWs ws = fsg_ws(c);
+  const int L = c.L;
+  int n = 0;
+  auto add = [&](long long off, int rows, float* dst_t, float* dst_n) {
+    sink->entry[n].offset = off;
+    sink->entry[n].rows = rows;
+    sink->entry[n].reserved = 0;
+    sink->entry[n].dst_t = dst_t;
+    sink->entry[n].dst_n = dst_n;
+    ++n;
+  };
+  for (int j = 0; j < L + 2; ++j)                                     // forward image A[m][k] = W[k][m], backward A[m][k] = W[m][k]
+    add(j < L ? c.po.convs_w[j] : (j == L ? c.po.context_w : c.po.objects_w), FH, fsg_img_fwd(ws, j), fsg_img_bwd(ws, j));
+  add(c.po.conv_feat_w, c.F, fsg_img_feat(ws, L), nullptr);           // [F][H]; rows F .. of the image stay zero
+  if (!c.cat)
+    for (int h = 0; h < 3; ++h)                                       // fc1 [out][in]: forward A[m][k] = W[m][k], backward A[m][k] = W[k][m]
+      add(c.po.fc1_w[h], FH, fsg_img_fc1_bwd(ws, L, h), fsg_img_fc1_fwd(ws, L, h));
+  sink->count = n;
+  return 0;
+}
+
+int launch_fsg_prep(const Ctx& c, cudaStream_t s, bool no_overlap) {
   const int n_img = (2 * (c.L + 2) + 1 + (c.cat ? 0 : 6)) * 8;       // (the fc1 images only exist for cat_or_add = "add")
-  launch_k(k_fsg_prep, dim3(n_img + 1), dim3(256), 0, s, c, n_img, fsg_grid(c));
+  if (no_overlap) launch_k_plain(k_fsg_prep, dim3(n_img), dim3(256), 0, s, c);
+  else launch_k(k_fsg_prep, dim3(n_img), dim3(256), 0, s, c);
   note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
 }
 
-int launch_fsg_forward(const Ctx& c, cudaStream_t s) {
+int launch_fsg_forward(const Ctx& c, cudaStream_t s, bool after_full_dependency) {
   const size_t smem = fsg_smem().total;
   static bool attr_set = false;
   if (!attr_set) {
@@ -741,7 +760,10 @@ int launch_fsg_forward(const Ctx& c, cudaStream_t s) {
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  launch_k(k_fsg_forward, dim3(fsg_grid(c)), dim3(FT), smem, s, c);
+  // CAL_F_FSG_READY: no k_fsg_prep ahead of this kernel -- its predecessor is then the optimizer kernel, whose output
+  // (the attention projections) the set-up before the dependency wait reads: no programmatic overlap with it
+  if (after_full_dependency) launch_k_plain(k_fsg_forward, dim3(fsg_grid(c)), dim3(FT), smem, s, c);
+  else launch_k(k_fsg_forward, dim3(fsg_grid(c)), dim3(FT), smem, s, c);
   note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;

@@ -14,15 +14,13 @@ constexpr int kFsgRows = 40;            // rows (nodes) per block: 5 groups of 8
 constexpr int kFsgEntries = 320;        // CSR entries per block
 constexpr int kFsgPhases = 24;          // all-reduce sites per launch
 constexpr int kFsgVec = 512;            // doubles per all-reduce vector slot
-constexpr int kFsgGroup = 8;            // CTAs per first-level group
-constexpr int kFsgMaxGroups = 20;
-constexpr int kFsgCntStride = 40;       // counters per phase: [0] second level, [1 + g] first level
+constexpr int kFsgCntStride = 40;       // u32 words between the arrival counters of two sites (own 128-byte line each)
 constexpr int kFsgImgPart = 16384;      // floats of one operand part (128 x 128)
 constexpr int kFsgImg = 2 * kFsgImgPart;   // hi | lo
 
 // the CAL_WS_FSG region (byte offsets)
 struct FsgLayout {
-  size_t plan, info, cnt, l0, l1, acc, img, part, total;
+  size_t plan, info, cnt, acc, img, part, total;
 };
 __host__ __device__ inline size_t fsg_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -38,12 +36,10 @@ __host__ __device__ inline size_t fsg_part_floats(int L, int F) { return fsg_par
 __host__ __device__ inline FsgLayout fsg_layout(int Bm, int L, int F) {
   FsgLayout f;
   size_t o = 0;
-  f.plan = o;  o = fsg_up(o + 16);                                        // i32[4]: number of blocks, ok flag
-  f.info = o;  o = fsg_up(o + (size_t)(Bm > 0 ? Bm : 1) * 32);            // i32[8] per block
-  f.cnt = o;   o = fsg_up(o + (size_t)(kFsgPhases * kFsgCntStride + 8) * 4);
-  f.l0 = o;    o = fsg_up(o + (size_t)kSMs * kFsgVec * 8);
-  f.l1 = o;    o = fsg_up(o + (size_t)2 * kFsgMaxGroups * kFsgVec * 8);
-  f.acc = o;   o = fsg_up(o + (size_t)kFsgPhases * 8 * 2 * kFsgVec * 8);           // fixed-point all-reduce accumulators (fsg_dev.cuh)
+  f.plan = o;  o = fsg_up(o + 16);                                        // (reserved)
+  f.info = o;  o = fsg_up(o + (size_t)(Bm > 0 ? Bm : 1) * 32);            // i32[8] per block, written by the forward kernel: graphs [g0, g1), nodes [n0, n1), in-CSR entries [e0, e1), first out-CSR entry, fits-the-limits flag
+  f.cnt = o;   o = fsg_up(o + (size_t)(2 * kFsgPhases * kFsgCntStride + 8) * 4);     // site counters of both sets + the epoch words
+  f.acc = o;   o = fsg_up(o + (size_t)2 * kFsgPhases * 8 * 2 * kFsgVec * 8);       // fixed-point all-reduce accumulators, two sets (fsg_dev.cuh)
   f.img = o;   o = fsg_up(o + (size_t)((L + 2) * 2 + 1 + 6) * kFsgImg * 4);   // forward / backward image per conv matrix + feat + fc1 of the 3 readouts
   f.part = o;                                                             // partial gradients, one slot per block
   if (Bm <= kSMs && F <= 128) o = fsg_up(o + (size_t)(Bm > 0 ? Bm : 1) * fsg_part_floats(L, F) * 4);
@@ -55,8 +51,6 @@ struct FsgWs {
   int* plan;
   int* info;
   unsigned int* cnt;
-  double* l0;
-  double* l1;
   long long* acc;
   float* img;
   float* part;
@@ -67,8 +61,6 @@ __host__ __device__ inline FsgWs fsg_ws(const Ctx& c) {
   w.plan = reinterpret_cast<int*>(c.fsg + f.plan);
   w.info = reinterpret_cast<int*>(c.fsg + f.info);
   w.cnt = reinterpret_cast<unsigned int*>(c.fsg + f.cnt);
-  w.l0 = reinterpret_cast<double*>(c.fsg + f.l0);
-  w.l1 = reinterpret_cast<double*>(c.fsg + f.l1);
   w.acc = reinterpret_cast<long long*>(c.fsg + f.acc);
   w.img = reinterpret_cast<float*>(c.fsg + f.img);
   w.part = reinterpret_cast<float*>(c.fsg + f.part);
@@ -81,5 +73,30 @@ __host__ __device__ inline float* fsg_img_feat(const FsgWs& w, int L) { return w
 // readout fc1 (torch Linear [out, in], "add": in = H) of head h: forward image A[m = out][k = in], backward image A[m = in][k = out]
 __host__ __device__ inline float* fsg_img_fc1_fwd(const FsgWs& w, int L, int h) { return w.img + (size_t)(2 * (L + 2) + 1 + 2 * h) * kFsgImg; }
 __host__ __device__ inline float* fsg_img_fc1_bwd(const FsgWs& w, int L, int h) { return w.img + (size_t)(2 * (L + 2) + 2 + 2 * h) * kFsgImg; }
+
+
+// The image words of parameter i (value v) -- what k_fsg_prep derives from the whole matrix, written by the optimizer
+// kernel that just produced v (cal_image_sink, include/cal_b200.h).  Image element (m, k) lives at float offset
+// (k / 4) * 512 + m * 4 + k % 4 of the hi part, the lo part kFsgImgPart floats behind it.
+__device__ __forceinline__ void fsg_sink_emit(const cal_image_sink& sk, long long i, float v) {
+  for (int q = 0; q < sk.count; ++q) {
+    const long long d = i - sk.entry[q].offset;
+    if (d < 0 || d >= (long long)sk.entry[q].rows * kFsgH) continue;
+    const int r = (int)(d >> 7), cc = (int)(d & 127);
+    const unsigned int u = __float_as_uint(v);
+    const float hi = __uint_as_float((u + 0x1000u) & 0xffffe000u), lo = v - hi;      // umma::split_tf32
+    if (sk.entry[q].dst_t != nullptr) {
+      float* p = sk.entry[q].dst_t + (r >> 2) * 512 + cc * 4 + (r & 3);
+      p[0] = hi;
+      p[kFsgImgPart] = lo;
+    }
+    if (sk.entry[q].dst_n != nullptr) {
+      float* p = sk.entry[q].dst_n + (cc >> 2) * 512 + r * 4 + (cc & 3);
+      p[0] = hi;
+      p[kFsgImgPart] = lo;
+    }
+    return;
+  }
+}
 
 }  // namespace cal

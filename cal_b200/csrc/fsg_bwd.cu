@@ -1,7 +1,7 @@
 // fsg_bwd.cu -- the fused small-graph BACKWARD pass of CausalGCN: ONE persistent kernel from the pooled-embedding
 // gradients (left by the readout backward) down to the input transform, the mirror of fsg.cu.
 //
-// A CTA owns one block of whole graphs (the plan of k_fsg_prep).  Everything that couples nodes -- the transpose
+// A CTA owns one graph (the block record its forward CTA left in the workspace).  Everything that couples nodes -- the transpose
 // aggregates (gcn_conv.py:92-97 backward), the weighted-normalisation backward through both endpoints' degrees
 // (gcn_conv.py:59-70), the edge / node attention softmax backward (model.py:97-111) -- is local to the CTA's
 // shared memory; the gradient products  D = u W^T  (and  d agg = d z W^T  of the two masked convs) run on the
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
   const int L = c.L, F = c.F;
 
   // ---- before the dependency wait.  The immediate predecessor (the readout backward) only writes the gradient of
-  // the pooled embeddings; everything else this kernel reads -- the plan, the CSRs, the forward pass's activations,
+  // the pooled embeddings; everything else this kernel reads -- the block records, the CSRs, the forward pass's activations,
   // masks and BatchNorm records, the weight images -- was complete before the predecessor could start, so the whole
   // block-local set-up overlaps the predecessor's run. ----
   if (warp == 0) umma::tmem_alloc(&tmem_slot, kTmemColsB);
@@ -241,15 +241,19 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
       wq1[i] = We[3 * FH + k];
     }
   }
-  const int nblk = ws.plan[0], plan_ok = ws.plan[1];
+  // one block per graph: G live blocks, each with the record its forward block left (fitting the limits or not)
   const int N = imin(imax(c.dims[0], 0), c.Nm);
-  const bool active = plan_ok != 0 && (int)blockIdx.x < nblk;
-  const int G = nblk;
+  const int G = imin(imax(c.dims[2], 0), c.Bm);
+  int4 ia = make_int4(0, 0, 0, 0), ib = make_int4(0, 0, 0, 0);
+  if ((int)blockIdx.x < G) {
+    ia = *reinterpret_cast<const int4*>(ws.info + (size_t)blockIdx.x * 8);
+    ib = *reinterpret_cast<const int4*>(ws.info + (size_t)blockIdx.x * 8 + 4);
+  }
+  const bool active = ib.w != 0;
+  const bool unfit = (int)blockIdx.x < G && !active;
   uint32_t par_w = 0, par_w2 = 0, par_m = 0, par_d = 0;
   int g0 = 0, n0 = 0, Nc = 0, Ec = 0, ie0 = 0, oe0 = 0;
   if (active) {
-    const int4 ia = *reinterpret_cast<const int4*>(ws.info + (size_t)blockIdx.x * 8);
-    const int4 ib = *reinterpret_cast<const int4*>(ws.info + (size_t)blockIdx.x * 8 + 4);
     g0 = ia.x; n0 = ia.z; Nc = ia.w - ia.z;
     ie0 = ib.x; Ec = ib.y - ib.x; oe0 = ib.z;
     // ================= stage 0: block-local structure, masks, BatchNorm records =================
@@ -298,6 +302,9 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
   umma::fence_before_sync();
   FSG_TDECL
   pdl_sync();
+  // (after the wait: when this kernel is issued back to back its predecessor is its own previous launch, whose final
+  // all-reduce site moves the epoch)
+  const int fx_set = fsg_epoch_begin(ws, 1, 12, 13 + L);             // every CTA of the grid, active or not
   if (blockIdx.x == 0) CAL_TL(c.status, 8);
   CAL_TLC(c, 1, 0);
   FSG_T(0);                                                           // 0: dependency wait (set-up overlapped)
@@ -511,7 +518,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
       }
     }
     FSG_T(4);                                                         // 4 (+ MMA tail): masked gather, d-norm dots + block totals
-    fsg_publish_fx(ws, 12, sPart, 4 * FH);
+    fsg_publish_fx(ws, fx_set, 12, G, sPart, 4 * FH);
     if (t == 0) {                                                      // image of the top backbone layer (all but the tail)
       umma::fence_async_smem();
       umma::mbar_expect_tx(&bar_w, 65536u + kTailOff);
@@ -577,7 +584,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
 
     // ================= stage 4: attention backward -> gradient rows of the top backbone layer =================
     const long long go_c = c.bn_gamma[L + 1], bo_c = c.bn_beta[L + 1], go_o = c.bn_gamma[L + 2], bo_o = c.bn_beta[L + 2];
-    fsg_wait_total_fx(ws, 12, G, 4 * FH, sTot);
+    fsg_wait_total_fx(ws, fx_set, 12, G, 4 * FH, sTot);
     CAL_TLC(c, 1, 4);
     fsg_bn_bwd_finalize(c, L + 1, N, go_c, bo_c, sTot, sVec + 4 * FH, sVec + 5 * FH, 0);
     fsg_bn_bwd_finalize(c, L + 2, N, go_o, bo_o, sTot + 2 * FH, sVec + 6 * FH + 4 * FH, sVec + 6 * FH + 5 * FH, FH);
@@ -797,7 +804,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
         __syncthreads();
       }
       FSG_T(13);                                                      // 13: statistics epilogue
-      fsg_publish_fx(ws, 13 + (L - 1 - l), sPart, 2 * FH);
+      fsg_publish_fx(ws, fx_set, 13 + (L - 1 - l), G, sPart, 2 * FH, l == 0 ? 1 : -1);   // (layer 0: the launch's final site)
       FSG_T(7);
       // dW = bn_l(x_in)^T u on the tensor cores while the all-reduce travels (operands in the idle image buffer)
       build_dw_operands<true>(sAh, sX, FH, vin, vin + FH, sBh, sBl, Nc, npad);
@@ -816,7 +823,7 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
       }
       FSG_T(3);
       const long long go_l = c.bn_gamma[1 + l], bo_l = c.bn_beta[1 + l];
-      fsg_wait_total_fx(ws, 13 + (L - 1 - l), G, 2 * FH, sTot);
+      fsg_wait_total_fx(ws, fx_set, 13 + (L - 1 - l), G, 2 * FH, sTot);
       if (l == 0) CAL_TLC(c, 1, 1);
       fsg_bn_bwd_finalize(c, 1 + l, N, go_l, bo_l, sTot, vin + 4 * FH, vin + 5 * FH, 0);
       umma::mbar_wait(&bar_dw, par_d);
@@ -881,15 +888,15 @@ __global__ void __launch_bounds__(FT, 1) k_fsg_backward(const Ctx c) {
     }
     FSG_T(15);                                                        // 15: input transform backward
   }
+  if (unfit && t == 0) fsg_unfit_arrive(ws, fx_set, G, 12, 12 + L, 1);   // (reported by the forward kernel)
   FSG_TDUMP(c, 64);
   if (blockIdx.x == 0) CAL_TL(c.status, 9);
   CAL_TLC(c, 1, 2);
 
-  // ---- teardown: TMEM, and the last CTA re-arms the all-reduce counters for the next launch ----
+  // ---- teardown: TMEM (the all-reduce state needs none: fsg_epoch_begin) ----
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, kTmemColsB);
-  if (active) fsg_rearm(ws, G, 12, 13 + L);
   CAL_TLC(c, 1, 3);
 }
 
@@ -913,7 +920,7 @@ __global__ void __launch_bounds__(1024) k_fsg_grad_reduce(const Ctx c, const Fsg
   if (blockIdx.x == 0) CAL_TL(c.status, 10);
   __shared__ float s_a[4][256], s_b[4][256];
   const FsgWs ws = fsg_ws(c);
-  const int np = ws.plan[1] != 0 ? ws.plan[0] : 0;
+  const int np = imin(imax(c.dims[2], 0), c.Bm);                    // one partial per live block
   const int tx = threadIdx.x & 255, ty = threadIdx.x >> 8;
   if ((int)blockIdx.x < n_generic) {
     const int i = blockIdx.x * 256 + tx;

@@ -34,64 +34,7 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   return v;
 }
 
-// ---- the in-kernel all-reduce of per-CTA fp64 vectors (deterministic: groups of 8 CTAs, fixed order) ----
-__device__ __forceinline__ void fsg_publish(const FsgWs& w, int phase, int G, const double* sPart, int n) {
-  __shared__ int s_lead;
-  const int t = threadIdx.x;
-  const int grp = blockIdx.x / kFsgGroup, gsize = imin(kFsgGroup, G - grp * kFsgGroup);
-  double* mine = w.l0 + (size_t)blockIdx.x * kFsgVec;
-  for (int i = t; i < n; i += FT) mine[i] = sPart[i];
-  __syncthreads();
-  if (t == 0) {
-    __threadfence();
-    const unsigned int old = atomicAdd(&w.cnt[phase * kFsgCntStride + 1 + grp], 1u);
-    s_lead = (old == (unsigned int)gsize - 1u);
-    if (s_lead) __threadfence();
-  }
-  __syncthreads();
-  if (!s_lead) return;
-  double* dst = w.l1 + ((size_t)(phase & 1) * kFsgMaxGroups + grp) * kFsgVec;
-  for (int i = t; i < n; i += FT) {
-    double v[kFsgGroup];
-#pragma unroll
-    for (int m = 0; m < kFsgGroup; ++m) v[m] = m < gsize ? __ldcg(&w.l0[(size_t)(grp * kFsgGroup + m) * kFsgVec + i]) : 0.0;
-    double sum = v[0];
-#pragma unroll
-    for (int m = 1; m < kFsgGroup; ++m) sum += v[m];
-    dst[i] = sum;
-  }
-  __syncthreads();
-  if (t == 0) {
-    __threadfence();
-    atomicAdd(&w.cnt[phase * kFsgCntStride], 1u);
-  }
-}
-__device__ __forceinline__ void fsg_wait_total(const FsgWs& w, int phase, int G, int n, double* sTot) {
-  const int t = threadIdx.x;
-  const int ngrp = (G + kFsgGroup - 1) / kFsgGroup;
-  if (t == 0) {
-    while (ld_acquire_gpu(&w.cnt[phase * kFsgCntStride]) < (unsigned int)ngrp) {
-    }
-    __threadfence();
-  }
-  __syncthreads();
-  const double* src = w.l1 + (size_t)(phase & 1) * kFsgMaxGroups * kFsgVec;
-  for (int i = t; i < n; i += FT) {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int g = 0;
-    for (; g + 4 <= ngrp; g += 4) {
-      s0 += __ldcg(src + (size_t)(g + 0) * kFsgVec + i);
-      s1 += __ldcg(src + (size_t)(g + 1) * kFsgVec + i);
-      s2 += __ldcg(src + (size_t)(g + 2) * kFsgVec + i);
-      s3 += __ldcg(src + (size_t)(g + 3) * kFsgVec + i);
-    }
-    for (; g < ngrp; ++g) s0 += __ldcg(src + (size_t)g * kFsgVec + i);
-    sTot[i] = (s0 + s1) + (s2 + s3);
-  }
-  __syncthreads();
-}
-
-// ---- the same all-reduce in ONE level: exact fixed-point accumulation with integer atomics ----
+// ---- the in-kernel all-reduce of per-CTA fp64 vectors: exact fixed-point accumulation with integer atomics ----
 // Integer addition is associative, so the totals do not depend on the arrival order (bit-identical runs) although
 // every CTA adds straight into shared accumulators -- no group leaders, no second counter phase.  A value v is scaled
 // to |v| * 2^40 (truncated; |v| < 2^55, resolution 2^-40 -- far below the fp32 results derived from the sums) and split
@@ -102,6 +45,7 @@ __device__ __forceinline__ void fsg_wait_total(const FsgWs& w, int phase, int G,
 // waiting CTA polls that counter and reads 2 * kFxCopies words per value in one round trip.
 constexpr int kFxCopies = 8;
 constexpr int kFxWords = 2 * kFsgVec;                                 // 64-bit words per copy per phase
+constexpr int kFsgCtl = 2 * kFsgPhases * kFsgCntStride;               // control words behind the site counters: epoch of kernel 0 / 1
 __device__ __forceinline__ void fsg_fx_add(long long* acc2, double v) {
   // limbs of the MAGNITUDE (every step below is exact in fp64: the operands are aligned), added with the value's sign
   const double a = fabs(v) * 1099511627776.0;                         // 2^40 (exact scaling)
@@ -114,25 +58,58 @@ __device__ __forceinline__ void fsg_fx_add(long long* acc2, double v) {
   atomicAdd(reinterpret_cast<unsigned long long*>(acc2), (unsigned long long)l0);
   atomicAdd(reinterpret_cast<unsigned long long*>(acc2 + 1), (unsigned long long)l1);
 }
-__device__ __forceinline__ void fsg_publish_fx(const FsgWs& w, int phase, const double* sPart, int n) {
+// Two accumulator SETS alternate between the launches of a kernel (its epoch word, bumped by the last CTA to arrive at
+// the launch's final all-reduce site): a launch adds into set epoch & 1 and, right after its dependency wait, every CTA
+// clears its slice of the OTHER set -- the one the previous launch dirtied and the next launch will use.  Nothing is
+// left to do at teardown (a single CTA re-arming 256 KB of accumulators there cost 6 us per kernel on the critical path).
+__device__ __forceinline__ unsigned int* fsg_cnt(const FsgWs& w, int set, int phase) {
+  return w.cnt + (size_t)(set * kFsgPhases + phase) * kFsgCntStride;
+}
+__device__ __forceinline__ long long* fsg_acc(const FsgWs& w, int set, int phase) {
+  return w.acc + ((size_t)set * kFsgPhases + phase) * kFxCopies * kFxWords;
+}
+// kern: 0 = forward (sites [0, L]), 1 = backward (sites [12, 12 + L]).  Call after the dependency wait, all CTAs.
+__device__ __forceinline__ int fsg_epoch_begin(const FsgWs& w, int kern, int p0, int p1) {
+  const int set = (int)(ld_acquire_gpu(&w.cnt[kFsgCtl + kern]) & 1u), other = set ^ 1;
+  longlong2* z = reinterpret_cast<longlong2*>(fsg_acc(w, other, p0));
+  const int items = (p1 - p0) * kFxCopies * kFxWords / 2;
+  for (int i = blockIdx.x * FT + threadIdx.x; i < items; i += gridDim.x * FT) z[i] = make_longlong2(0, 0);
+  if (blockIdx.x == 0 && (int)threadIdx.x < p1 - p0) *fsg_cnt(w, other, p0 + threadIdx.x) = 0u;
+  return set;
+}
+// `last_site`: this is the launch's final site -- the CTA that completes it moves the kernel's epoch on
+__device__ __forceinline__ void fsg_publish_fx(const FsgWs& w, int set, int phase, int G, const double* sPart, int n,
+                                               int kern = -1) {
   const int t = threadIdx.x;
-  long long* acc = w.acc + ((size_t)phase * kFxCopies + (blockIdx.x % kFxCopies)) * kFxWords;
+  long long* acc = fsg_acc(w, set, phase) + (size_t)(blockIdx.x % kFxCopies) * kFxWords;
   for (int i = t; i < n; i += FT) fsg_fx_add(acc + 2 * i, sPart[i]);
   __syncthreads();
   if (t == 0) {
     __threadfence();
-    atomicAdd(&w.cnt[phase * kFsgCntStride], 1u);
+    const unsigned int old = atomicAdd(fsg_cnt(w, set, phase), 1u);
+    if (kern >= 0 && old == (unsigned int)G - 1u) atomicAdd(&w.cnt[kFsgCtl + kern], 1u);
   }
 }
-__device__ __forceinline__ void fsg_wait_total_fx(const FsgWs& w, int phase, int G, int n, double* sTot) {
+// A live block whose graph does not fit the path's limits (fsg.cuh) arrives at every all-reduce site [first, last]
+// of its launch without adding anything, so that the other blocks' waits complete.  `last` is the launch's final
+// site (fsg_publish_fx: moves the epoch on).  One thread.  (Inline on purpose: a call in the kernel body puts the
+// whole kernel under the function-call ABI -- 204 instead of 182 registers and an 8 % slower forward, measured.)
+__device__ __forceinline__ void fsg_unfit_arrive(const FsgWs& w, int set, int G, int first, int last, int kern) {
+  for (int p = first; p <= last; ++p) {
+    const unsigned int old = atomicAdd(fsg_cnt(w, set, p), 1u);
+    if (p == last && old == (unsigned int)G - 1u) atomicAdd(&w.cnt[kFsgCtl + kern], 1u);
+  }
+}
+
+__device__ __forceinline__ void fsg_wait_total_fx(const FsgWs& w, int set, int phase, int G, int n, double* sTot) {
   const int t = threadIdx.x;
   if (t == 0) {
-    while (ld_acquire_gpu(&w.cnt[phase * kFsgCntStride]) < (unsigned int)G) {
+    while (ld_acquire_gpu(fsg_cnt(w, set, phase)) < (unsigned int)G) {
     }
     __threadfence();
   }
   __syncthreads();
-  const longlong2* acc = reinterpret_cast<const longlong2*>(w.acc + (size_t)phase * kFxCopies * kFxWords);
+  const longlong2* acc = reinterpret_cast<const longlong2*>(fsg_acc(w, set, phase));
   for (int i = t; i < n; i += FT) {
     longlong2 v[kFxCopies];
 #pragma unroll
@@ -146,20 +123,6 @@ __device__ __forceinline__ void fsg_wait_total_fx(const FsgWs& w, int phase, int
     sTot[i] = ((double)hi * 281474976710656.0 + (double)lo) * 9.094947017729282e-13;   // 2^48, 2^-40
   }
   __syncthreads();
-}
-// teardown: the last CTA of the launch re-arms the counters and clears the accumulators of phases [p0, p1)
-__device__ __forceinline__ void fsg_rearm(const FsgWs& w, int G, int p0, int p1) {
-  __shared__ int s_last;
-  const int t = threadIdx.x;
-  if (t == 0) {
-    __threadfence();
-    s_last = atomicAdd(&w.cnt[kFsgPhases * kFsgCntStride], 1u) == (unsigned int)G - 1u;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  for (int i = t; i < (p1 - p0) * kFxCopies * kFxWords; i += FT) w.acc[(size_t)p0 * kFxCopies * kFxWords + i] = 0;
-  for (int i = t; i <= kFsgPhases * kFsgCntStride; i += FT) w.cnt[i] = 0u;
-  __threadfence();
 }
 
 __device__ __forceinline__ uint32_t b_off(int i, int kc) { return (uint32_t)(i >> 3) * kBSbo + (uint32_t)kc * kBLbo + (uint32_t)(i & 7) * 16u; }

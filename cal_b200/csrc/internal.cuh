@@ -131,8 +131,9 @@ bool readout_ro_supported(const Ctx& c);                                   // sh
 bool readout_runs_ro(const Ctx& c);                                        // ... and they are the ones that will run (no override)
 int launch_readout_ro_forward(const Ctx& c, cudaStream_t s);
 int launch_readout_ro_backward(const Ctx& c, cudaStream_t s);
-int launch_fsg_prep(const Ctx& c, cudaStream_t s);                         // fused small-graph path (fsg.cu)
-int launch_fsg_forward(const Ctx& c, cudaStream_t s);
+int launch_fsg_prep(const Ctx& c, cudaStream_t s, bool no_overlap = false);                         // fused small-graph path (fsg.cu)
+int launch_fsg_forward(const Ctx& c, cudaStream_t s, bool after_full_dependency = false);
+int fsg_fill_image_sink(const Ctx& c, cal_image_sink* sink);
 size_t fsg_region_bytes(int Bm, int L, int F);
 int launch_fsg_backward(const Ctx& c, cudaStream_t s);                      // masked convs .. input transform, one kernel
 int launch_fsg_grad_reduce(const Ctx& c, cudaStream_t s);

@@ -1,6 +1,7 @@
 // optim.cu -- fixed-order reduction of the per-CTA partial parameter gradients into the flat
 // gradient buffer, and the fused Adam step on flat buffers (train_causal.py:21,192).
 #include "internal.cuh"
+#include "fsg.cuh"
 
 namespace cal {
 
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(256) k_grad_reduce(const Ctx c, const RedTable
 __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                        float* __restrict__ v, long long n, int* __restrict__ step, unsigned int* __restrict__ done,
                        float lr, const float* __restrict__ lr_dev, float b1, float b2, float eps, float wd,
-                       float gscale) {
+                       float gscale, const cal_image_sink sink) {
   pdl_sync();
   __shared__ float s_c[2];
   __shared__ int s_t;
@@ -170,7 +171,9 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
     m[i] = mi;
     v[i] = vi;
     float denom = sqrtf(vi) / bc2s + eps;
-    p[i] = pi - step_size * (mi / denom);
+    const float pn = pi - step_size * (mi / denom);
+    p[i] = pn;
+    if (sink.count > 0) fsg_sink_emit(sink, i, pn);       // operand images of the fused small-graph path
   }
   // fused tick: every CTA has read *step before it arrives here, so the last one may advance it
   if (done != nullptr) {
@@ -247,20 +250,31 @@ int launch_grad_reduce(const Ctx& c, cudaStream_t s) {
 
 }  // namespace cal
 
-extern "C" int cal_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
-                             int32_t* step, float lr, const float* lr_device, float beta1, float beta2,
-                             float eps, float weight_decay, float grad_scale, void* stream) {
+extern "C" int cal_adam_step_images(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                    int32_t* step, float lr, const float* lr_device, float beta1, float beta2,
+                                    float eps, float weight_decay, float grad_scale, const cal_image_sink* sink,
+                                    void* stream) {
   if (!params || !grads || !exp_avg || !exp_avg_sq || !step) return CAL_ENULL;
   if (n <= 0) return CAL_EINVAL;
+  cal_image_sink sk = {};
+  if (sink != nullptr) sk = *sink;
+  if (sk.count < 0 || sk.count > 16) return CAL_EINVAL;
   int g = (int)((n + 255) / 256);
   if (g > 4 * cal::kSMs) g = 4 * cal::kSMs;
   // step[0] = number of updates applied so far (advanced by this call); step[1] = arrival counter
   cal::launch_k(cal::k_adam, dim3(g), dim3(256), 0, (cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, (long long)n, step,
                                                   reinterpret_cast<unsigned int*>(step + 1), lr, lr_device, beta1,
-                                                  beta2, eps, weight_decay, grad_scale);
+                                                  beta2, eps, weight_decay, grad_scale, sk);
   cal::note_launches(1);
   CAL_CUDA_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int cal_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                             int32_t* step, float lr, const float* lr_device, float beta1, float beta2,
+                             float eps, float weight_decay, float grad_scale, void* stream) {
+  return cal_adam_step_images(params, grads, exp_avg, exp_avg_sq, n, step, lr, lr_device, beta1, beta2, eps,
+                              weight_decay, grad_scale, nullptr, stream);
 }
 
 extern "C" int cal_adam_tick(int32_t* step, void* stream) {

@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(256) k_prep_init(const Ctx c) {
   if (tid == 0) {
     c.status[0] = bad_caps ? kStCapacity : 0;
     c.status[1] = c.status[2] = c.status[3] = 0;
+    if (bad_caps) atomicOr(&c.status[kStSticky], kStCapacity);
   }
   if (tid < 64 + kGsSites * kGsCounters) c.counters[tid] = 0u;
   if (bad_caps) return;
@@ -41,7 +42,7 @@ __global__ void __launch_bounds__(256) k_prep_init(const Ctx c) {
     long long g = c.batch[n];
     long long gp = n > 0 ? c.batch[n - 1] : -1;
     if (g < 0 || g >= B || g < gp) {
-      atomicOr(c.status, kStBadBatch);
+      raise_status(c.status, kStBadBatch);
       g = g < 0 ? 0 : (g >= B ? B - 1 : g);
     }
     c.node_graph[n] = (int)g;
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(256) k_prep_init(const Ctx c) {
   for (int b = tid; b < B; b += nth) {
     int p = c.perm_in != nullptr ? c.perm_in[b] : b;
     if (p < 0 || p >= B) {
-      atomicOr(c.status, kStBadBatch);
+      raise_status(c.status, kStBadBatch);
       p = b;
     }
     c.perm[b] = p;
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(256) k_prep_init(const Ctx c) {
   for (int e = tid; e < E; e += nth) {
     long long r = c.ei_row[e], d = c.ei_col[e];
     if (r < 0 || r >= N || d < 0 || d >= N) {
-      atomicOr(c.status, kStBadNode);
+      raise_status(c.status, kStBadNode);
       continue;
     }
     if (r != d) {
@@ -337,6 +338,7 @@ __global__ void __launch_bounds__(kPrepT) k_prep_small(const Ctx c) {
     if (sj == 0 && t == 0) {
       c.status[0] = kStCapacity;
       c.status[1] = c.status[2] = c.status[3] = 0;
+      atomicOr(&c.status[kStSticky], kStCapacity);
     }
     return;
   }
@@ -550,6 +552,7 @@ __global__ void __launch_bounds__(kPrepT) k_prep_small(const Ctx c) {
     if (t == 0) {
       c.status[0] = s_status;
       c.status[1] = c.status[2] = c.status[3] = 0;
+      if (s_status != 0) atomicOr(&c.status[kStSticky], s_status);
     }
     CAL_TL(c.status, 12);
 #ifdef CAL_PHASE_TIMING

@@ -402,17 +402,50 @@ class Engine:
         return self.region("LOSS")[:8]
 
     # ---- fused Adam on the flat buffers (train_causal.py:21,192) ----
-    def adam_step(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0, lr_device=None):
-        """``lr_device`` (f32[1] device tensor) overrides ``lr`` so captured graphs follow a schedule."""
+    # ``images_version``: the parameter version signature at the last optimizer step that also wrote the fused path's
+    # operand images (None: the images in the workspace may be stale).  Our kernels do not move torch's version
+    # counters, any torch-side in-place modification of a parameter (optimizers, load_state_dict, p.mul_()) or of the
+    # flat buffer does -- so "unchanged" means the images still match the parameters.  The one hole is the one autograd
+    # has too: writes through ``p.data`` / ``p.detach()`` aliases are invisible; after such a write call
+    # ``images_stale()`` (or Trainer.params_changed()).
+    images_version = None
+
+    def param_version(self):
+        v = self.flat._version
+        for p in self.params:
+            v += p._version
+        return v
+
+    def images_fresh(self):
+        return self.images_version is not None and self.images_version == self.param_version()
+
+    def images_stale(self):
+        self.images_version = None
+
+    def image_sink(self):
+        """cal_image_sink of the current workspace (count == 0 unless the fused small-graph path is taken)."""
+        key = (self.ws.data_ptr(), int(self.caps.small_graphs))
+        if getattr(self, "_sink_key", None) != key:
+            sk = _lib.ImageSink()
+            _lib.check(self.lib.cal_image_sink_init(C.byref(self.desc), C.byref(self.caps), C.byref(self.po), self.ws.data_ptr(),
+                                                    self.ws_bytes, C.byref(sk)), "cal_image_sink_init")
+            self._sink, self._sink_key = sk, key
+        return self._sink
+
+    def adam_step(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0, lr_device=None, sink=None):
+        """``lr_device`` (f32[1] device tensor) overrides ``lr`` so captured graphs follow a schedule.
+        ``sink``: cal_image_sink -- also write the fused path's operand images of the updated parameters."""
         if self.opt_state is None:
             self.opt_state = (torch.zeros_like(self.flat), torch.zeros_like(self.flat),
                               torch.zeros(2, dtype=torch.int32, device=self.device))
         m, v, step = self.opt_state
         s = self._stream()
-        _lib.check(self.lib.cal_adam_step(self.flat.data_ptr(), self.flat_grad.data_ptr(), m.data_ptr(),
-                                          v.data_ptr(), self.total, step.data_ptr(), float(lr),
-                                          lr_device.data_ptr() if lr_device is not None else 0,
-                                          betas[0], betas[1], eps, weight_decay, grad_scale, s), "cal_adam_step")
+        _lib.check(self.lib.cal_adam_step_images(self.flat.data_ptr(), self.flat_grad.data_ptr(), m.data_ptr(),
+                                                 v.data_ptr(), self.total, step.data_ptr(), float(lr),
+                                                 lr_device.data_ptr() if lr_device is not None else 0,
+                                                 betas[0], betas[1], eps, weight_decay, grad_scale,
+                                                 C.byref(sink) if sink is not None else None, s), "cal_adam_step")
+        self.images_version = self.param_version() if sink is not None else None
 
     def stage_names(self, backward=False):
         p = _lib.CAL_PASS_BACKWARD if backward else _lib.CAL_PASS_FORWARD

@@ -207,15 +207,18 @@ class PeerExchange:
         self.comm = comm
         self.nbytes = nbytes
 
-    def adam_step(self, eng, lr, betas, eps, weight_decay, lr_device=None):
+    def adam_step(self, eng, lr, betas, eps, weight_decay, lr_device=None, sink=None):
         if eng.opt_state is None:
             eng.opt_state = (torch.zeros_like(eng.flat), torch.zeros_like(eng.flat),
                              torch.zeros(2, dtype=torch.int32, device=eng.device))
         m, v, step = eng.opt_state
-        _lib.check(self.lib.cal_dp_adam_step(C.byref(self.comm), eng.flat.data_ptr(), eng.flat_grad.data_ptr(),
-                                             m.data_ptr(), v.data_ptr(), eng.total, step.data_ptr(), float(lr),
-                                             lr_device.data_ptr() if lr_device is not None else 0,
-                                             betas[0], betas[1], eps, weight_decay, eng._stream()), "cal_dp_adam_step")
+        _lib.check(self.lib.cal_dp_adam_step_images(C.byref(self.comm), eng.flat.data_ptr(), eng.flat_grad.data_ptr(),
+                                                    m.data_ptr(), v.data_ptr(), eng.total, step.data_ptr(), float(lr),
+                                                    lr_device.data_ptr() if lr_device is not None else 0,
+                                                    betas[0], betas[1], eps, weight_decay,
+                                                    C.byref(sink) if sink is not None else None, eng._stream()),
+                   "cal_dp_adam_step")
+        eng.images_version = eng.param_version() if sink is not None else None
 
     def check(self, eng):
         """Raise if an exchange timed out waiting for a peer (synchronises)."""
@@ -385,13 +388,25 @@ class Trainer:
         return self.pack(data, perm=perm).to(self.device, non_blocking=False)
 
     # ---- the step ----
-    def _issue(self, base_ptr, gat_keep=None, part="all", next_ptr=None, prepped=False):
+    def params_changed(self):
+        """Tell the trainer that parameters were written behind torch's version counters (through ``p.data`` or a
+        detached alias): the next step rebuilds the fused path's operand images from the parameters."""
+        self.eng.images_stale()
+
+    def _sink(self):
+        sk = self.eng.image_sink()
+        return sk if sk.count > 0 else None
+
+    def _issue(self, base_ptr, gat_keep=None, part="all", next_ptr=None, prepped=False, ready=False):
         """Enqueue the step on the current stream.  part: "all", or "compute" (prep + forward + loss +
         backward) / "update" (gradient all-reduce + Adam) for the two-graph data-parallel replay.
         ``prepped``: cal_prep of this batch already ran (at the end of the previous step);  ``next_ptr``: run
         cal_prep of the NEXT batch on a forked branch next to this step's update (the structure work needs only the
-        batch itself, so it hides under the gradient exchange / Adam instead of heading the next step)."""
+        batch itself, so it hides under the gradient exchange / Adam instead of heading the next step);
+        ``ready``: prepped AND the operand images of the fused small-graph path are current (the optimizer steps issued
+        here write them, cal_image_sink) -- the forward pass then starts with the fused kernel itself."""
         eng, lib = self.eng, self.eng.lib
+        sink = self._sink()
         if part in ("all", "compute"):
             cb = self.layout.cbatch(base_ptr)
             if gat_keep is not None:
@@ -400,9 +415,12 @@ class Trainer:
             d, caps = C.byref(eng.desc), C.byref(eng.caps)
             if not prepped:
                 _lib.check(lib.cal_prep(d, caps, C.byref(cb), eng.ws.data_ptr(), eng.ws_bytes, s), "cal_prep")
+            fflags = _lib.CAL_F_TRAIN | _lib.CAL_F_LOSS
+            if prepped:                                        # the kernel ahead of this call is the optimizer's, not cal_prep's
+                fflags |= _lib.CAL_F_NO_OVERLAP | (_lib.CAL_F_FSG_READY if ready else 0)
             _lib.check(lib.cal_causal_forward(d, caps, C.byref(eng.po), C.byref(eng.bo), eng.flat.data_ptr(),
                                               eng.bn_buf.data_ptr(), eng.nbt.data_ptr(), C.byref(cb),
-                                              _lib.CAL_F_TRAIN | _lib.CAL_F_LOSS, 0, eng.ws.data_ptr(), eng.ws_bytes, s),
+                                              fflags, 0, eng.ws.data_ptr(), eng.ws_bytes, s),
                        "cal_causal_forward")
             fork = next_ptr is not None and part == "all"
             last = eng.L + 6                                   # backward stage "grad_reduce"
@@ -431,14 +449,14 @@ class Trainer:
             bwd(_lib.stages_flag(last, last))
         if self.peer is not None:
             if part in ("all", "update"):
-                self.peer.adam_step(eng, 0.0, self.betas, self.eps, self.weight_decay, lr_device=self.lr_dev)
+                self.peer.adam_step(eng, 0.0, self.betas, self.eps, self.weight_decay, lr_device=self.lr_dev, sink=sink)
             if side is not None:
                 torch.cuda.current_stream(self.device).wait_stream(side)
             return
         if part in ("all", "allreduce"):
             self._scale = allreduce_flat_grads(eng.flat_grad, self.pg) if self.world > 1 else 1.0
         if part in ("all", "update"):
-            eng.adam_step(0.0, self.betas, self.eps, self.weight_decay, 1.0 / self.world, lr_device=self.lr_dev)
+            eng.adam_step(0.0, self.betas, self.eps, self.weight_decay, 1.0 / self.world, lr_device=self.lr_dev, sink=sink)
         if side is not None:
             torch.cuda.current_stream(self.device).wait_stream(side)
 
@@ -482,13 +500,14 @@ class Trainer:
         prepped = ahead_ok and getattr(self, "_prepped_ptr", None) == ptr
         nxt = next_packed.data_ptr() if (next_packed is not None and ahead_ok) else None
         self._prepped_ptr = nxt
+        ready = prepped and self._sink() is not None and self.eng.images_fresh()
         if not self.use_graph:
             c0 = self.eng.lib.cal_launch_count()
-            self._issue(ptr, keep, next_ptr=nxt, prepped=prepped)
+            self._issue(ptr, keep, next_ptr=nxt, prepped=prepped, ready=ready)
             self.launches_per_step = int(self.eng.lib.cal_launch_count() - c0) + (
                 1 if self.world > 1 and self.peer is None else 0)
             return
-        key = ptr if (nxt is None and not prepped) else (ptr, nxt, prepped)
+        key = ptr if (nxt is None and not prepped) else (ptr, nxt, prepped, ready)
         g = self._graphs.get(key)
         if g is None:
             if len(self._graphs) >= self._max_graphs:
@@ -500,7 +519,7 @@ class Trainer:
             if self.world == 1 or self.peer is not None:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=self._capture_stream()):
-                    self._issue(ptr, keep, next_ptr=nxt, prepped=prepped)
+                    self._issue(ptr, keep, next_ptr=nxt, prepped=prepped, ready=ready)
                 g = (g, None)
                 self.launches_per_step = int(count() - c0)
             else:
@@ -525,6 +544,8 @@ class Trainer:
         if g[1] is not None:
             self._issue(ptr, keep, part="allreduce")
             g[1].replay()
+        # (the replayed optimizer kernel wrote the operand images of the parameters it produced)
+        self.eng.images_version = self.eng.param_version() if self._sink() is not None else None
 
     def _capture_stream(self):
         if not hasattr(self, "_cap_stream"):

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CAL_ABI_VERSION 2
+#define CAL_ABI_VERSION 3
 #define CAL_MAX_LAYERS 8
 #define CAL_MAX_BN (1 + CAL_MAX_LAYERS + 2 + 6)
 
@@ -192,6 +192,9 @@ enum cal_ws_region {
 /* flags for cal_causal_forward */
 #define CAL_F_TRAIN 1        /* BatchNorm batch statistics + running-stat update; GAT dropout */
 #define CAL_F_LOSS 2         /* also evaluate train_causal.py:178-186 (needs batch.y) */
+#define CAL_F_NO_OVERLAP 8   /* cal_causal_forward: the kernel that precedes this call in the stream is not cal_prep's (e.g. the optimizer's:
+                                cal_prep ran ahead, elsewhere) -- the first kernel must not overlap its tail */
+#define CAL_F_FSG_READY 4    /* cal_causal_forward, training: structure and operand images are complete (see cal_image_sink) */
 /* Run only stages [lo, hi] of the pass (see cal_stage_count / cal_stage_name); flags without a
  * range run the whole pass.  Used for per-operator tests and live per-kernel timing. */
 #define CAL_F_STAGES(lo, hi) ((((lo) + 1) << 8) | (((hi) + 1) << 16))
@@ -255,6 +258,34 @@ int cal_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                   float beta2, float eps, float weight_decay, float grad_scale, void* stream);
 int cal_adam_tick(int32_t* step, void* stream);   /* ++step[0] on the device (manual stepping) */
 
+/* ---- fused small-graph path: operand images as a side product of the optimizer step ------------
+ * The fused kernels (cal_caps.small_graphs, csrc/fsg.cu) multiply by hi / lo split, K-major IMAGES of the conv /
+ * fc1 weights that a small kernel (k_fsg_prep) rebuilds from the parameters at the head of every forward pass.  A
+ * training loop can take that kernel off the critical path: cal_image_sink_init describes where the images of
+ * this model live in `workspace`, cal_adam_step_images / cal_dp_adam_step_images (= cal_adam_step /
+ * cal_dp_adam_step + `sink`) write the image words of every parameter they update, and the NEXT
+ * cal_causal_forward on that workspace may then be called with CAL_F_FSG_READY, which asserts
+ *   (1) cal_prep of its batch completed on this workspace before any kernel of the call can start, and
+ *   (2) the parameters were last modified by an optimizer step that carried this workspace's sink
+ * and starts with the fused forward kernel itself (no k_fsg_prep, no k_param_prep).  sink->count == 0 when the
+ * model / capacities do not take the fused path -- CAL_F_FSG_READY is then ignored. */
+typedef struct {
+  int64_t offset;              /* first float of a [rows][128] row-major matrix in the flat parameter buffer */
+  float* dst_t;                /* image with A[m][k] = W[k][m] (or NULL) */
+  float* dst_n;                /* image with A[m][k] = W[m][k] (or NULL) */
+  int32_t rows, reserved;
+} cal_image_entry;
+typedef struct {
+  int32_t count, reserved;
+  cal_image_entry entry[16];
+} cal_image_sink;
+int cal_image_sink_init(const cal_model_desc* m, const cal_caps* caps, const cal_param_offsets* po,
+                        void* workspace, size_t ws_bytes, cal_image_sink* sink);
+int cal_adam_step_images(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                         int64_t n, int32_t* step, float lr, const float* lr_device, float beta1,
+                         float beta2, float eps, float weight_decay, float grad_scale,
+                         const cal_image_sink* sink, void* stream);
+
 /* ---- mini-batch collation on the device ---------------------------------------------------------
  * Replaces the host-side collate of the reference's loader (torch_geometric DataLoader ->
  * Batch.from_data_list, train_causal.py:13-15,171-176): node features concatenated, edge_index
@@ -315,6 +346,11 @@ int cal_dp_unmap(void* mapped);
 int cal_dp_adam_step(const cal_dp_comm* comm, float* params, const float* grads, float* exp_avg,
                      float* exp_avg_sq, int64_t n, int32_t* step, float lr, const float* lr_device,
                      float beta1, float beta2, float eps, float weight_decay, void* stream);
+/* ... + the operand images of the fused small-graph path (cal_image_sink above; NULL = none) */
+int cal_dp_adam_step_images(const cal_dp_comm* comm, float* params, const float* grads, float* exp_avg,
+                            float* exp_avg_sq, int64_t n, int32_t* step, float lr, const float* lr_device,
+                            float beta1, float beta2, float eps, float weight_decay,
+                            const cal_image_sink* sink, void* stream);
 /* A peer that does not deliver within CAL_DP_TIMEOUT_S seconds (environment, default 600; 0 = wait for ever)
  * makes the kernel record an error word and trap: the rank fails with a launch error instead of
  * applying an update from stale data.  Consecutive calls on one stream are safe (the exchange number is
@@ -330,9 +366,10 @@ int cal_dp_read_error(const cal_dp_comm* comm, void* stream);
 int cal_selftest_umma(int kind, int M, int N, int K, const float* A, const float* B, float* D, int variant,
                       void* stream);
 
-/* Poll the status word written by cal_prep (synchronises the stream): returns the CAL_ST_* bits,
- * or a negative CAL_E* / positive cudaError_t. */
-int cal_read_status(const cal_model_desc* m, const cal_caps* caps, const void* workspace, void* stream);
+/* Poll the status words (synchronises the stream): returns the CAL_ST_* bits of the batch prepared last OR-ed with
+ * every bit raised since the previous call (a second word that only this call clears: a batch prepared ahead of its
+ * step does not hide what the step before it reported), or a negative CAL_E* / positive cudaError_t. */
+int cal_read_status(const cal_model_desc* m, const cal_caps* caps, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libcal_b200.so does not export %s" % n
     assert sorted(L.EXPORTS) == names, "cal_b200/_lib.py EXPORTS out of sync with the header"
-    assert lib.cal_abi_version() == 2
+    assert lib.cal_abi_version() == 3
 
 
 def test_header_cites_reference_interfaces():

@@ -513,7 +513,10 @@ def test_trainer_graph_replay_matches_oracle_trajectory(hidden):
 @pytest.mark.parametrize("use_graph", [True, False], ids=["graph", "eager"])
 def test_trainer_prep_ahead_is_bit_identical(use_graph):
     """Trainer.step(cur, next): the next batch's cal_prep runs on a forked branch beside this step's update and the next
-    step skips it -- same parameters, bit for bit, as the plain loop (every batch prepared exactly once either way)."""
+    step skips it -- same parameters, bit for bit, as the plain loop (every batch prepared exactly once either way).
+    With the hint the optimizer kernel also writes the fused path's operand images and the next forward starts with
+    the fused kernel itself (CAL_F_FSG_READY); a torch-side change of a parameter in between (here: after step 3) is
+    noticed through the version counter and that step rebuilds the images from the parameters."""
     M, O = _mods()
     ora, b0, _ = random_case(seed=75, hidden=128, batch_size=32)
     batches = [b0] + [random_case(seed=76 + i, hidden=128, batch_size=32)[1] for i in range(2)]
@@ -525,11 +528,45 @@ def test_trainer_prep_ahead_is_bit_identical(use_graph):
         for step in range(7):
             cur, nxt = dev[step % 3], dev[(step + 1) % 3]
             tr.step(cur, nxt if ahead else None)
+            if step == 3:
+                assert net.engine.images_fresh() == tr.fused_small_graphs
+                with torch.no_grad():
+                    dict(net.named_parameters())["convs.1.weight"].mul_(0.75)
+                assert not net.engine.images_fresh()
         tr.step(dev[1])                                   # a step without a hint after hinted ones
         torch.cuda.synchronize()
         tr.check()
         out.append(net.engine.flat.clone())
     assert torch.equal(out[0], out[1])
+
+
+def test_fused_path_reports_a_graph_beyond_its_limits_and_recovers():
+    """cal_caps.small_graphs is a promise of the caller (<= 40 nodes, <= 320 CSR entries per graph).  A batch that breaks
+    it must not hang the in-kernel all-reduces: the block of an unfit graph only keeps them complete, the status word
+    gets the capacity bit (Trainer.check raises), and the next well-formed batch steps normally."""
+    M, O = _mods()
+    ora, b0, _ = random_case(seed=95, hidden=128, batch_size=16)
+    big = random_case(seed=96, hidden=128, batch_size=16, avg_nodes=48)[1]
+    assert M.batch_caps([b0])[3] and not M.batch_caps([big])[3]
+    c = M.batch_caps([b0, big])
+    net = clone_to_cuda(ora, M)
+    tr = M.Trainer(net, (c[0], c[1], c[2], True), lr=1e-3)
+    assert tr.fused_small_graphs
+    d0 = tr.upload(b0, perm=list(range(16)))
+    d1 = tr.upload(big, perm=list(range(16)))
+    tr.step(d0)
+    torch.cuda.synchronize()
+    tr.check()
+    tr.step(d1, d0)                                       # (with the look-ahead: d0 is prepared beside this step's update)
+    torch.cuda.synchronize()
+    assert net.engine.region("STATUS", torch.int32)[0].item() == 0     # the per-batch word now belongs to d0's preparation ...
+    with pytest.raises(M._lib.CalError):
+        tr.check()                                        # ... the bits raised since the last read are kept beside it
+    tr.step(d0, d0)
+    tr.step(d0)
+    tr.step(d0)
+    torch.cuda.synchronize()
+    tr.check()
 
 
 def test_pipelined_host_path_matches_the_synchronous_loop():

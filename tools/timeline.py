@@ -14,7 +14,7 @@ torch.manual_seed(666)
 net = cal_b200.CausalGCN(10, 4, model_args()).cuda().train()
 tr = cal_b200.Trainer(net, cal_b200.batch_caps(batches), use_graph=True)
 dev = [tr.upload(b) for b in batches]
-names = ["prep start", "fsg_prep plan start", "fsg_forward start", "fsg_forward end", "ro_fwd start", "ro_fwd end",
+names = ["prep start", "fsg_prep block 0 images built", "fsg_forward start", "fsg_forward end", "ro_fwd start", "ro_fwd end",
          "ro_bwd start", "ro_bwd end", "fsg_backward start", "fsg_backward end", "grad_reduce start", "-", "prep end"]
 for rep in range(3):
     n = 40 + rep
