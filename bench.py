@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--collective", default="auto", choices=["auto", "peer", "nccl"],
                     help="N>1 gradient exchange: NVLink peer push fused with Adam, or ncclAllReduce")
     ap.add_argument("--no-stage-timing", action="store_true", help="skip the live per-stage timing / roofline")
+    ap.add_argument("--steps-per-graph", type=int, default=1,
+                    help="resident loop: consecutive steps captured as one CUDA graph (Trainer.step_many); 1 = one graph per step")
     ap.add_argument("--no-prep-ahead", action="store_true",
                     help="do not overlap the next batch's structure preparation with this step's update")
     ap.add_argument("--same-batches", action="store_true",
@@ -394,23 +396,36 @@ def run_gpu(a, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # capture one graph per resident batch (outside the timed region), then W warm-up steps.  The loop knows its next
-    # batch, so each step prepares the NEXT batch's structure beside its own update (Trainer.step(cur, next)): every
-    # batch is still prepared exactly once per step, inside the timed region.
+    # The loop knows its next batch, so each step prepares the NEXT batch's structure beside its own update
+    # (Trainer.step(cur, next)): every batch is still prepared exactly once per step, inside the timed region; and it
+    # issues `--steps-per-graph` consecutive steps per graph launch (Trainer.step_many: same kernels, same order).
+    # The warm-up + timed sequence runs once untimed first, which captures exactly the graphs the timed run replays.
     ahead = not a.no_prep_ahead
-    nxt = (lambda k: resident[(k + 1) % n_res]) if ahead else (lambda k: None)
-    for k, r in enumerate(resident):
-        tr.step(r, nxt(k))
+    spg = max(1, a.steps_per_graph) if (ahead and not a.no_graph) else 1
+    W = max(a.warmup, 3)
+
+    def run(start, count):
+        i = 0
+        while i < count:
+            k = min(spg, count - i)
+            group = [resident[(start + i + j) % n_res] for j in range(k)]
+            follower = resident[(start + i + k) % n_res] if ahead else None
+            if k > 1:
+                tr.step_many(group, follower)
+            else:
+                tr.step(group[0], follower)
+            i += k
+
+    run(0, W)
+    run(W, a.steps)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # clocks are sampled (NVML, every 2 ms) from the warm-up on: a 20-step timed region is only ~3 ms long
     with ClockSampler(visible_gpu_index(local_rank)) as clk:
-        for i in range(max(a.warmup, 3)):
-            tr.step(resident[i % n_res], nxt(i))
+        run(0, W)
         barrier()
         t_begin = time.perf_counter()
         e0.record()
-        for i in range(a.steps):
-            tr.step(resident[(a.warmup + i) % n_res], nxt(a.warmup + i))
+        run(W, a.steps)
         e1.record()
         barrier()
         t_end = time.perf_counter()
@@ -442,10 +457,9 @@ def run_gpu(a, rank, local_rank, world):
             return float(tt.item()), last
         for i in range(max(3, a.warmup // 2)):
             tr.step_host(hosts[i % len(hosts)])
-        for rnd in range(3):                             # every (staging buffer, follower, prepared?) graph gets captured:
-            for i in range(4):                           # 4 calls + flush start the next round one buffer later
-                tr.step_host_async(hosts[i % len(hosts)])
-            tr.pipe_flush()
+        for i in range(a.steps):                         # the timed sequence once untimed: its graphs (one per staging
+            tr.step_host_async(hosts[i % len(hosts)])    # buffer pair, + the first and the flushed step) get captured
+        tr.pipe_reset()
         # (a) pipelined: H2D of batch i+1 on a copy stream overlaps step i; loss parts of every step
         #     land in a pinned ring; the host only waits when the ring (16 steps) is full
         ms_p, slot = timed(tr.step_host_async)
@@ -456,8 +470,9 @@ def run_gpu(a, rank, local_rank, world):
                "h2d_bytes_per_step": int(tr.layout.nbytes), "d2h_bytes_per_step": 32,
                "ms_per_step": ms_p / a.steps,
                "api": "Trainer.step_host_async(pinned packed batch): cudaMemcpyAsync H2D on a copy stream into a "
-                      "triple-buffered staging area + captured step (the follower's structure preparation rides beside the "
-                      "update) + loss parts D2H into a pinned ring, every step; all K steps issued and flushed inside the timed region",
+                      "ring of 16 staging buffers + captured step (the follower's structure preparation rides beside the "
+                      "update, the loss parts' D2H copy into the buffer's pinned result slot beside the backward pass), every step; "
+                      "all K steps issued and flushed inside the timed region",
                "sync_every_step": {"value": a.steps * graphs_per_step * world / (ms_s * 1e-3),
                                    "ms_per_step": ms_s / a.steps,
                                    "api": "Trainer.step_host(..., sync=True): same copies, host waits for every step's loss"},
@@ -606,7 +621,7 @@ def run_gpu(a, rank, local_rank, world):
             "sample": sample_stats(batches, "inputs larger than L2: %d distinct resident batches (%.0f MB) cycled; "
                                             "workspace reused" % (n_res, resident_bytes / 2 ** 20)),
             "clocks": clk.summary(t_begin, t_end), "e2e": e2e, "gpu_launches": launches,
-            "launches_per_step": int(tr.launches_per_step), "cuda_graph": not a.no_graph,
+            "launches_per_step": int(tr.launches_per_step), "cuda_graph": not a.no_graph, "steps_per_graph_launch": spg,
             "collective": {"none": "none (1 GPU)", "nccl": "ncclAllReduce of the flat gradient buffer between a compute and an update graph",
                            "peer": "NVLink peer-memory push of the gradient chunks fused with Adam (cal_dp_adam_step), one captured graph per step"}[tr.collective],
             "dp_check": dp_check, "roofline": roofline, "cpu_baseline": cpu, "stages": stage_tab,

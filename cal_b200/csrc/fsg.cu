@@ -108,6 +108,7 @@ __device__ __forceinline__ void fsg_bn_finalize(const Ctx& c, int id, int count,
 // The forward kernel.  grid = min(max_graphs, 148), 256 threads, 1 CTA per SM.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FT, 1) k_fsg_forward(const Ctx c) {
+  if (blockIdx.x == 0) CAL_TL(c.status, 11);                         // (timeline builds: kernel entry)
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t bar_w, bar_mma;
   __shared__ uint32_t tmem_slot;

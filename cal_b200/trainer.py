@@ -397,16 +397,19 @@ class Trainer:
         sk = self.eng.image_sink()
         return sk if sk.count > 0 else None
 
-    def _issue(self, base_ptr, gat_keep=None, part="all", next_ptr=None, prepped=False, ready=False):
+    def _issue(self, base_ptr, gat_keep=None, part="all", next_ptr=None, prepped=False, ready=False, loss_out=None):
         """Enqueue the step on the current stream.  part: "all", or "compute" (prep + forward + loss +
         backward) / "update" (gradient all-reduce + Adam) for the two-graph data-parallel replay.
         ``prepped``: cal_prep of this batch already ran (at the end of the previous step);  ``next_ptr``: run
         cal_prep of the NEXT batch on a forked branch next to this step's update (the structure work needs only the
         batch itself, so it hides under the gradient exchange / Adam instead of heading the next step);
         ``ready``: prepped AND the operand images of the fused small-graph path are current (the optimizer steps issued
-        here write them, cal_image_sink) -- the forward pass then starts with the fused kernel itself."""
+        here write them, cal_image_sink) -- the forward pass then starts with the fused kernel itself;
+        ``loss_out``: pinned f32[8] host tensor -- the loss parts / correct counts are copied into it on a branch forked
+        right behind the forward pass (the copy engine works beside the backward pass)."""
         eng, lib = self.eng, self.eng.lib
         sink = self._sink()
+        side2 = None
         if part in ("all", "compute"):
             cb = self.layout.cbatch(base_ptr)
             if gat_keep is not None:
@@ -422,6 +425,12 @@ class Trainer:
                                               eng.bn_buf.data_ptr(), eng.nbt.data_ptr(), C.byref(cb),
                                               fflags, 0, eng.ws.data_ptr(), eng.ws_bytes, s),
                        "cal_causal_forward")
+            if loss_out is not None:
+                main = torch.cuda.current_stream(self.device)
+                side2 = self._side_stream(1)
+                side2.wait_stream(main)
+                with torch.cuda.stream(side2):
+                    loss_out.copy_(eng.loss_parts_full(), non_blocking=True)
             fork = next_ptr is not None and part == "all"
             last = eng.L + 6                                   # backward stage "grad_reduce"
 
@@ -450,20 +459,22 @@ class Trainer:
         if self.peer is not None:
             if part in ("all", "update"):
                 self.peer.adam_step(eng, 0.0, self.betas, self.eps, self.weight_decay, lr_device=self.lr_dev, sink=sink)
-            if side is not None:
-                torch.cuda.current_stream(self.device).wait_stream(side)
+            for sd in (side, side2):
+                if sd is not None:
+                    torch.cuda.current_stream(self.device).wait_stream(sd)
             return
         if part in ("all", "allreduce"):
             self._scale = allreduce_flat_grads(eng.flat_grad, self.pg) if self.world > 1 else 1.0
         if part in ("all", "update"):
             eng.adam_step(0.0, self.betas, self.eps, self.weight_decay, 1.0 / self.world, lr_device=self.lr_dev, sink=sink)
-        if side is not None:
-            torch.cuda.current_stream(self.device).wait_stream(side)
+        for sd in (side, side2):
+            if sd is not None:
+                torch.cuda.current_stream(self.device).wait_stream(sd)
 
-    def _side_stream(self):
+    def _side_stream(self, i=0):
         if not hasattr(self, "_side"):
-            self._side = torch.cuda.Stream(self.device)
-        return self._side
+            self._side = [torch.cuda.Stream(self.device) for _ in range(2)]
+        return self._side[i]
 
     def _gat_keep_for(self, key):
         """Attention-dropout keep mask of CausalGAT (model.py:340 dropout=0.2), regenerated on the
@@ -481,13 +492,15 @@ class Trainer:
             p = float(self.model.dropout)
             self._keep.bernoulli_(1.0 - p).mul_(1.0 / (1.0 - p))
 
-    def step(self, packed_dev, next_packed=None):
+    def step(self, packed_dev, next_packed=None, loss_out=None):
         """Enqueue one training step on a device-resident packed batch (asynchronous).
 
         ``next_packed``: the device-resident batch of the NEXT call (a loader that knows it one step ahead): its
         structure preparation (cal_prep) is then issued on a forked branch beside this step's update and the next
         ``step(next_packed, ...)`` skips it -- every batch is still prepared exactly once.  (Single captured graph
-        per step only: not with the two-graph NCCL replay.)"""
+        per step only: not with the two-graph NCCL replay.)
+        ``loss_out``: pinned f32[8] host tensor that receives this step's loss parts / correct counts (copied beside the
+        backward pass; valid once the step has completed)."""
         self._check_alive()
         self.pipe_flush()                                # (no-op unless a step_host_async batch is pending)
         if packed_dev.device != self.device:
@@ -503,11 +516,12 @@ class Trainer:
         ready = prepped and self._sink() is not None and self.eng.images_fresh()
         if not self.use_graph:
             c0 = self.eng.lib.cal_launch_count()
-            self._issue(ptr, keep, next_ptr=nxt, prepped=prepped, ready=ready)
+            self._issue(ptr, keep, next_ptr=nxt, prepped=prepped, ready=ready, loss_out=loss_out)
             self.launches_per_step = int(self.eng.lib.cal_launch_count() - c0) + (
                 1 if self.world > 1 and self.peer is None else 0)
             return
-        key = ptr if (nxt is None and not prepped) else (ptr, nxt, prepped, ready)
+        key = ptr if (nxt is None and not prepped and loss_out is None) else (
+            ptr, nxt, prepped, ready, loss_out.data_ptr() if loss_out is not None else None)
         g = self._graphs.get(key)
         if g is None:
             if len(self._graphs) >= self._max_graphs:
@@ -519,7 +533,7 @@ class Trainer:
             if self.world == 1 or self.peer is not None:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=self._capture_stream()):
-                    self._issue(ptr, keep, next_ptr=nxt, prepped=prepped, ready=ready)
+                    self._issue(ptr, keep, next_ptr=nxt, prepped=prepped, ready=ready, loss_out=loss_out)
                 g = (g, None)
                 self.launches_per_step = int(count() - c0)
             else:
@@ -537,15 +551,66 @@ class Trainer:
                     self._update_launches = int(count() - c1)
                 g = (ga, self._update_graph)
                 self.launches_per_step = n_compute + 1 + self._update_launches     # + the NCCL all-reduce kernel
-            self._graphs[key] = (g, packed_dev)
+            self._graphs[key] = (g, packed_dev, loss_out)
         else:
             g = g[0]
         g[0].replay()
         if g[1] is not None:
             self._issue(ptr, keep, part="allreduce")
             g[1].replay()
+        if loss_out is not None and g[1] is not None:      # (two-graph NCCL replay: the copy is not part of a graph)
+            loss_out.copy_(self.eng.loss_parts_full(), non_blocking=True)
         # (the replayed optimizer kernel wrote the operand images of the parameters it produced)
         self.eng.images_version = self.eng.param_version() if self._sink() is not None else None
+
+    def step_many(self, batches, next_packed=None, loss_out=None):
+        """``len(batches)`` consecutive training steps as ONE captured graph (asynchronous) -- the same kernels in the
+        same order as ``step(b0, b1); step(b1, b2); ...; step(b_last, next_packed)`` (bit-identical parameters), but the
+        steps inside the group are separated by a kernel-to-kernel dependency instead of the gap between two graph
+        launches (measured: 7.7 us).  ``loss_out``: one pinned f32[8] tensor per step, or None.  Falls back to single
+        steps where a step needs host work of its own (CausalGAT's per-step dropout mask, the two-graph NCCL replay,
+        eager mode)."""
+        batches = list(batches)
+        K = len(batches)
+        outs = list(loss_out) if loss_out is not None else [None] * K
+        ahead_ok = self.world == 1 or self.peer is not None
+        if K == 1 or not self.use_graph or not ahead_ok or self._gat_keep_for(None) is not None:
+            for k, b in enumerate(batches):
+                self.step(b, batches[k + 1] if k + 1 < K else next_packed, outs[k])
+            return
+        self._check_alive()
+        self.pipe_flush()
+        for b in batches:
+            if b.device != self.device:
+                raise _lib.CalError("cal_b200: Trainer.step_many needs device-resident packed batches")
+        ptrs = tuple(b.data_ptr() for b in batches)
+        prepped = getattr(self, "_prepped_ptr", None) == ptrs[0]
+        nxt = next_packed.data_ptr() if next_packed is not None else None
+        self._prepped_ptr = nxt
+        sink = self._sink()
+        ready = prepped and sink is not None and self.eng.images_fresh()
+        key = (ptrs, nxt, prepped, ready, tuple(o.data_ptr() if o is not None else None for o in outs))
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) >= self._max_graphs:
+                self._graphs.pop(next(iter(self._graphs)))
+            if not self._warm:
+                self._warmup(batches[0], None)
+            count = self.eng.lib.cal_launch_count
+            c0 = count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self._capture_stream()):
+                for k, p in enumerate(ptrs):
+                    # inside the group every step finds its batch prepared and the images written by the step before it
+                    self._issue(p, None, next_ptr=ptrs[k + 1] if k + 1 < K else nxt,
+                                prepped=prepped if k == 0 else True, ready=ready if k == 0 else sink is not None,
+                                loss_out=outs[k])
+            self.launches_per_step = int(round((count() - c0) / K))
+            self._graphs[key] = ((g, None), batches, outs)
+        else:
+            g = g[0][0]
+        g.replay()
+        self.eng.images_version = self.eng.param_version() if sink is not None else None
 
     def _capture_stream(self):
         if not hasattr(self, "_cap_stream"):
@@ -640,26 +705,23 @@ class Trainer:
         """End-to-end step: H2D copy of a (pinned) packed host batch, the step, and the loss parts /
         correct counts back on the host.  Returns the pinned f32[8] result when ``sync``."""
         self.staging.copy_(packed_host, non_blocking=True)
-        self.step(self.staging)
-        self._host_loss.copy_(self.eng.loss_parts_full(), non_blocking=True)
+        self.step(self.staging, loss_out=self._host_loss)
         if sync:
             torch.cuda.current_stream(self.device).synchronize()
             return self._host_loss
         return None
 
     # ---- pipelined end-to-end path: H2D of batch i+1 overlaps the step of batch i ----
-    PIPE_RING = 16
-    PIPE_STAGES = 3
+    PIPE_RING = 16              # staging buffers = result slots: batch i uses buffer / slot i % PIPE_RING
 
     def _pipe_init(self):
         dev = self.device
-        n = self.PIPE_STAGES
+        n = self.PIPE_RING
         self._pipe = {
             "i": 0,
             "stage": [torch.zeros(self.layout.nbytes, dtype=torch.uint8, device=dev) for _ in range(n)],
             "copy": torch.cuda.Stream(dev),
             "ready": [torch.cuda.Event() for _ in range(n)],
-            "done": [torch.cuda.Event() for _ in range(n)],
             "ring": torch.zeros(self.PIPE_RING, 8, dtype=torch.float32).pin_memory(),
             "ring_ev": [torch.cuda.Event() for _ in range(self.PIPE_RING)],
             "pending": None,
@@ -667,9 +729,9 @@ class Trainer:
 
     def step_host_async(self, packed_host):
         """Enqueue one end-to-end step without synchronising the host.  The packed batch is uploaded on a copy
-        stream into one of three staging buffers (overlapping earlier steps) and its loss parts / correct counts
-        are copied into a pinned ring slot after its step.  Returns the ring slot index; ``pipe_result(slot)``
-        waits for it.
+        stream into one of PIPE_RING staging buffers (overlapping earlier steps) and its loss parts / correct counts
+        are copied into the buffer's pinned result slot beside its backward pass (a copy node of the step's captured
+        graph).  Returns the slot index; ``pipe_result(slot)`` waits for it.
 
         The step of a batch is ISSUED one call late -- together with the upload of the batch that follows it -- so
         that the follower's structure preparation can ride beside this step's gradient reduction and update
@@ -679,13 +741,12 @@ class Trainer:
             self._pipe_init()
         p = self._pipe
         i = p["i"]
-        b, r = i % self.PIPE_STAGES, i % self.PIPE_RING
+        b = r = i % self.PIPE_RING
         main = torch.cuda.current_stream(self.device)
         if i >= self.PIPE_RING:
-            p["ring_ev"][r].synchronize()                # bound the host run-ahead to the ring depth
+            p["ring_ev"][r].synchronize()                # bound the host run-ahead to the ring depth (and: the
+            #                                              step that last read this staging buffer / wrote this slot is done)
         cs = p["copy"]
-        if i >= self.PIPE_STAGES:
-            cs.wait_event(p["done"][b])                  # the step that last read this staging buffer
         with torch.cuda.stream(cs):
             p["stage"][b].copy_(packed_host, non_blocking=True)
             p["ready"][b].record(cs)
@@ -702,9 +763,7 @@ class Trainer:
         p = self._pipe
         b, r = pend
         main = torch.cuda.current_stream(self.device)
-        self.step(p["stage"][b], p["stage"][nxt] if nxt is not None else None)
-        p["done"][b].record(main)
-        p["ring"][r].copy_(self.eng.loss_parts_full(), non_blocking=True)
+        self.step(p["stage"][b], p["stage"][nxt] if nxt is not None else None, loss_out=p["ring"][r])
         p["ring_ev"][r].record(main)
 
     def pipe_flush(self):
@@ -713,6 +772,14 @@ class Trainer:
         if p is not None and p["pending"] is not None:
             pend, p["pending"] = p["pending"], None
             self._pipe_issue(pend, None)
+
+    def pipe_reset(self):
+        """Issue the pending step, wait for everything and rewind the buffer cursor (the next ``step_host_async`` uses
+        buffer / slot 0 again -- a repeated sequence of calls then replays the same captured graphs)."""
+        self.pipe_flush()
+        torch.cuda.current_stream(self.device).synchronize()
+        if hasattr(self, "_pipe"):
+            self._pipe["i"] = 0
 
     def pipe_result(self, slot):
         p = self._pipe

@@ -540,6 +540,36 @@ def test_trainer_prep_ahead_is_bit_identical(use_graph):
     assert torch.equal(out[0], out[1])
 
 
+@pytest.mark.parametrize("hidden", [64, 128], ids=["tiled_h64", "fused_h128"])
+def test_step_many_is_bit_identical_to_single_steps(hidden):
+    """Trainer.step_many: K consecutive steps captured as one graph (look-ahead and image hand-over inside the group) --
+    same parameters and the same per-step loss parts, bit for bit, as K single steps."""
+    M, O = _mods()
+    ora, b0, _ = random_case(seed=77, hidden=hidden, batch_size=32)
+    batches = [b0] + [random_case(seed=78 + i, hidden=hidden, batch_size=32)[1] for i in range(3)]
+    seq = [0, 1, 2, 3, 1, 0, 2, 3, 3, 0, 1, 2]
+    flat, losses = [], []
+    for mode in ("single", "many"):
+        net = clone_to_cuda(ora, M)
+        tr = M.Trainer(net, M.batch_caps(batches), lr=1e-3)
+        dev = [tr.upload(b, perm=list(range(b.num_graphs))) for b in batches]
+        outs = [torch.zeros(8).pin_memory() for _ in seq]
+        if mode == "single":
+            for n, k in enumerate(seq):
+                tr.step(dev[k], dev[seq[n + 1]] if n + 1 < len(seq) else None, loss_out=outs[n])
+        else:
+            for g in range(0, len(seq), 3):               # groups of 3; the follower of a group is the next group's head
+                grp = [dev[k] for k in seq[g:g + 3]]
+                fol = dev[seq[g + 3]] if g + 3 < len(seq) else None
+                tr.step_many(grp, fol, loss_out=outs[g:g + 3])
+        torch.cuda.synchronize()
+        tr.check()
+        flat.append(net.engine.flat.clone())
+        losses.append(torch.stack(outs).clone())
+    assert torch.equal(losses[0], losses[1])
+    assert torch.equal(flat[0], flat[1])
+
+
 def test_fused_path_reports_a_graph_beyond_its_limits_and_recovers():
     """cal_caps.small_graphs is a promise of the caller (<= 40 nodes, <= 320 CSR entries per graph).  A batch that breaks
     it must not hang the in-kernel all-reduces: the block of an unfit graph only keeps them complete, the status word

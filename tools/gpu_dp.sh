@@ -4,10 +4,10 @@ set -u
 TAG=${1:-r01}
 NG=${2:-2}
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_dp.py -m gpu -q -x > gpurun_out/${TAG}_dp_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_dp_tests.log
+timeout -k 10 300 python -m pytest tests/test_gpu_dp.py -m gpu -q -x > gpurun_out/${TAG}_dp_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_dp_tests.log
 tail -15 gpurun_out/${TAG}_dp_tests.log
 for COLL in nccl peer; do
-  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533 \
-    bench.py --gpus $NG --steps 400 --warmup 20 --collective $COLL --no-stage-timing > gpurun_out/${TAG}_bench_${NG}gpu_${COLL}.json 2> gpurun_out/${TAG}_bench_${NG}gpu_${COLL}.err
+  timeout -k 10 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533 \
+    bench.py --gpus $NG --steps 400 --warmup 20 --collective $COLL --no-stage-timing --no-cpu-baseline > gpurun_out/${TAG}_bench_${NG}gpu_${COLL}.json 2> gpurun_out/${TAG}_bench_${NG}gpu_${COLL}.err
   echo "bench $COLL rc=$?"; tail -3 gpurun_out/${TAG}_bench_${NG}gpu_${COLL}.err; head -c 700 gpurun_out/${TAG}_bench_${NG}gpu_${COLL}.json; echo
 done
