@@ -23,7 +23,7 @@ WS_REGIONS = [
     "OUT_KEY", "CNT_IN", "CNT_OUT", "GRAPH_PTR", "NODE_GRAPH", "PERM", "INVPERM", "DIS", "X",
     "NODE_ATT", "PQ", "EDGE_ATT", "DISW", "AGG", "Z", "POOLED", "H1", "LOGP", "LOSS", "BN", "STATP",
     "WT", "GAT", "DLOGIT", "DH", "DU", "DAGG", "DYM", "DNRM", "DT", "DP", "D", "GPART",
-    "OUT_NORM", "EDGE_WN", "EDGE_NA", "FSG",
+    "OUT_NORM", "EDGE_WN", "EDGE_NA", "FSG", "EDGE_GPTR",
 ]
 WS = {n: i for i, n in enumerate(WS_REGIONS)}
 
@@ -55,7 +55,7 @@ class ModelDesc(C.Structure):
 
 class Caps(C.Structure):
     _fields_ = [("max_nodes", C.c_int32), ("max_edges", C.c_int32), ("max_graphs", C.c_int32),
-                ("small_graphs", C.c_int32)]
+                ("small_graphs", C.c_int32), ("grouped_edges", C.c_int32)]
 
 
 class ParamOffsets(C.Structure):

@@ -164,6 +164,8 @@ int build_ctx(const cal_model_desc* m, const cal_caps* caps, const cal_param_off
   c.edge_wn = REG(float, CAL_WS_EDGE_WN);
   c.edge_na = REG(float, CAL_WS_EDGE_NA);
   c.fsg = REG(unsigned char, CAL_WS_FSG);
+  c.egp = REG(int, CAL_WS_EDGE_GPTR);
+  c.grouped = caps->grouped_edges != 0;
   c.fsg_on = m->model == CAL_MODEL_GCN && m->hidden == 128 && m->num_features <= 128 && caps->max_graphs <= kSMs &&
              caps->small_graphs != 0;
   c.fsg_bwd_on = c.fsg_on && caps->small_graphs != 2;

@@ -88,6 +88,8 @@ struct Ctx {
   size_t gp_gin2[CAL_MAX_LAYERS];
   const float* grad_logp;   // external dL/dlogp (nullptr = fused loss)
   unsigned char* fsg;       // CAL_WS_FSG region (fsg.cuh)
+  int* egp;                 // [Bm+1] first edge column per graph | [Bm] self loops per graph | arrival counter (grouped_edges)
+  int grouped;              // cal_caps.grouped_edges
   int fsg_on;               // the fused small-graph forward replaces feat .. masked_convs (and the pooling)
   int fsg_bwd_on;           // ... and the fused small-graph backward replaces masked_gemm_bwd .. feat_bwd
 

@@ -94,6 +94,7 @@ int compute_layout(const cal_model_desc* m, const cal_caps* caps, Layout* lay) {
   sz[CAL_WS_EDGE_WN] = EP * 2 * 4;
   sz[CAL_WS_EDGE_NA] = EP * 2 * 4;
   if (m->model == CAL_MODEL_GCN && m->hidden == 128) sz[CAL_WS_FSG] = fsg_region_bytes((int)Bm, (int)L, (int)F);
+  sz[CAL_WS_EDGE_GPTR] = (2 * Bm + 8) * 4;
 
   size_t gp = 0;
   for (size_t l = 0; l < L + 2; ++l) {

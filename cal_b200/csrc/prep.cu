@@ -63,16 +63,38 @@ __global__ void __launch_bounds__(256) k_prep_init(const Ctx c) {
     c.perm[b] = p;
     c.invperm[p] = b;
   }
-  // ---- degree counts (gcn_conv.py:56: self loops are dropped) ----
-  for (int e = tid; e < E; e += nth) {
-    long long r = c.ei_row[e], d = c.ei_col[e];
-    if (r < 0 || r >= N || d < 0 || d >= N) {
-      raise_status(c.status, kStBadNode);
-      continue;
+  if (c.grouped) {
+    // ---- cal_caps.grouped_edges: the first edge_index column of every graph (k_prep_graph builds the CSRs graph by
+    // graph) and the number of self loops per graph (they are dropped, so they shift the rows of all later graphs) ----
+    int* egp = c.egp;
+    int* nself = c.egp + c.Bm + 1;
+    if (E == 0)
+      for (int b = tid; b <= B; b += nth) egp[b] = 0;
+    for (int e = tid; e < E; e += nth) {
+      const long long r = c.ei_row[e], rp = e > 0 ? c.ei_row[e - 1] : -1;
+      const bool ok = r >= 0 && r < N;
+      long long g = ok ? c.batch[r] : 0, gp = (rp >= 0 && rp < N) ? c.batch[rp] : (e > 0 ? 0 : -1);
+      if (!ok) raise_status(c.status, kStBadNode);
+      g = g < 0 ? 0 : (g >= B ? B - 1 : g);                 // (an invalid `batch` is reported by the node pass above)
+      gp = gp < -1 ? -1 : (gp >= B ? B - 1 : gp);
+      if (g < gp) raise_status(c.status, kStBadBatch);       // the promise is broken: columns not grouped by graph
+      for (long long b = gp + 1; b <= g; ++b) egp[b] = e;    // graphs whose columns start at e (edgeless ones too)
+      if (e == E - 1)
+        for (long long b = g + 1; b <= B; ++b) egp[b] = E;
+      if (ok && r == c.ei_col[e]) atomicAdd(&nself[(int)g], 1);
     }
-    if (r != d) {
-      atomicAdd(&c.cnt_in[(int)d], 1);
-      atomicAdd(&c.cnt_out[(int)r], 1);
+  } else {
+    // ---- degree counts (gcn_conv.py:56: self loops are dropped) ----
+    for (int e = tid; e < E; e += nth) {
+      long long r = c.ei_row[e], d = c.ei_col[e];
+      if (r < 0 || r >= N || d < 0 || d >= N) {
+        raise_status(c.status, kStBadNode);
+        continue;
+      }
+      if (r != d) {
+        atomicAdd(&c.cnt_in[(int)d], 1);
+        atomicAdd(&c.cnt_out[(int)r], 1);
+      }
     }
   }
   // ---- input-feature column statistics (fp64), this CTA's slice of the rows ----
@@ -229,6 +251,206 @@ __global__ void k_prep_link(const Ctx c) {
       c.out_pos[lo] = p;
       c.out_norm[lo] = nrm;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// cal_caps.grouped_edges: one CTA per graph builds that graph's rows of both CSRs in shared memory (edges packed to
+// 2 x u16 local ids, shared-memory atomics for the degree counts and fill cursors, a shuffle scan, rank-by-counting
+// inside the short rows) and writes them at the graph's place in the global arrays: rows of graph g start at
+//   (edge_index columns before g) - (self loops before g) + (nodes before g).
+// Same results as the other two paths (the row order is fixed by the ranks, not by the atomics).  Replaces the five
+// global passes for batches the single-kernel path cannot hold (cfg 5: 512 graphs x 200 nodes: 625 us -> see profiles/).
+// A graph beyond kPgNodes / kPgCols or with an endpoint outside itself raises the status word and gets empty rows.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPgT = 256;
+constexpr int kPgNodes = 512;
+constexpr int kPgCols = 4096;
+
+__global__ void __launch_bounds__(kPgT) k_prep_graph(const Ctx c) {
+  pdl_sync();
+  __shared__ int s_cin[kPgNodes], s_cout[kPgNodes], s_iptr[kPgNodes + 1], s_optr[kPgNodes + 1];
+  __shared__ float s_dis[kPgNodes];
+  __shared__ unsigned int s_edge[kPgCols];                             // (row << 16) | col, local ids; 0xffffffff = dropped
+  __shared__ unsigned short s_ikey[kPgCols + kPgNodes], s_okey[kPgCols + kPgNodes];
+  __shared__ int s_wi[kPgT / 32], s_wo[kPgT / 32], s_red[kPgT / 32], s_bad, s_last;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, T = kPgT;
+  const int N = c.dims[0], E = c.dims[1], B = c.dims[2];
+  if (N < 0 || E < 0 || B < 0 || N > c.Nm || E > c.Em || B > c.Bm) return;     // (k_prep_init reported it and stopped too)
+  const int* egp = c.egp;
+  int* nself = c.egp + c.Bm + 1;
+  int* done = c.egp + 2 * c.Bm + 1;
+  if (blockIdx.x == 0 && t == 0 && B == 0) c.in_ptr[0] = c.out_ptr[0] = 0;
+  for (int g = blockIdx.x; g < B; g += gridDim.x) {
+    const int n0 = c.graph_ptr[g], n1 = c.graph_ptr[g + 1], e0 = egp[g], e1 = egp[g + 1];
+    const int Nc = n1 - n0, Ec = e1 - e0;
+    // self loops of the graphs before this one
+    int sl = 0;
+    for (int b = t; b < g; b += T) sl += nself[b];
+    for (int o = 16; o > 0; o >>= 1) sl += __shfl_xor_sync(0xffffffffu, sl, o);
+    if (t == 0) s_bad = 0;
+    if (lane == 0) s_red[warp] = sl;
+    __syncthreads();
+    sl = 0;
+    for (int w = 0; w < T / 32; ++w) sl += s_red[w];
+    const int base = e0 - sl + n0;
+    bool fits = Nc >= 0 && Nc <= kPgNodes && Ec >= 0 && Ec <= kPgCols && n0 >= 0 && n1 <= N && e0 >= 0 && e1 <= E;
+    if (!fits) {
+      if (t == 0) raise_status(c.status, kStCapacity);
+      if (Nc < 0 || n0 < 0 || n1 > N) {                               // (an invalid `batch`: nothing sane to write)
+        __syncthreads();
+        continue;
+      }
+    }
+    for (int i = t; i < imin(Nc, kPgNodes); i += T) s_cin[i] = s_cout[i] = 0;
+    __syncthreads();
+    // 0. this graph's edge_index columns -> shared memory + degree counts (gcn_conv.py:56: self loops are dropped)
+    if (fits)
+      for (int el = t; el < Ec; el += T) {
+        const long long r = c.ei_row[e0 + el] - n0, d = c.ei_col[e0 + el] - n0;
+        unsigned int pk = 0xffffffffu;
+        if (r < 0 || r >= Nc || d < 0 || d >= Nc) {
+          s_bad = 1;                                                  // an endpoint outside the graph
+        } else if (r != d) {
+          pk = ((unsigned int)r << 16) | (unsigned int)d;
+          atomicAdd(&s_cin[(int)d], 1);
+          atomicAdd(&s_cout[(int)r], 1);
+        }
+        s_edge[el] = pk;
+      }
+    __syncthreads();
+    const bool empty_rows = !fits || s_bad != 0;                      // reported; the graph keeps only its place
+    if (s_bad != 0 && t == 0) raise_status(c.status, kStBadNode);
+    if (empty_rows) {
+      // rows without entries at the graph's place (the arrays stay consistent: later graphs do not move)
+      for (int i = t; i < Nc; i += T) {
+        c.in_ptr[n0 + i] = base;
+        c.out_ptr[n0 + i] = base;
+        c.dis[n0 + i] = 1.f;
+      }
+      if (g == B - 1 && t == 0) c.in_ptr[N] = c.out_ptr[N] = base;
+      __syncthreads();
+      continue;
+    }
+    // 1. exclusive scan of (count + 1) in chunks of T nodes; in- and out-counts packed in one word (both < 2^16)
+    {
+      unsigned int carry = 0u;
+      for (int c0 = 0; c0 < Nc; c0 += T) {
+        const int i = c0 + t;
+        const unsigned int v = i < Nc ? (unsigned int)(s_cin[i] + 1) | ((unsigned int)(s_cout[i] + 1) << 16) : 0u;
+        unsigned int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned int a = __shfl_up_sync(0xffffffffu, x, o);
+          if (lane >= o) x += a;
+        }
+        if (lane == 31) s_wi[warp] = (int)x;
+        __syncthreads();
+        if (warp == 0) {
+          unsigned int a = lane < T / 32 ? (unsigned int)s_wi[lane] : 0u;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int a2 = __shfl_up_sync(0xffffffffu, a, o);
+            if (lane >= o) a += a2;
+          }
+          if (lane < T / 32) s_wo[lane] = (int)a;
+        }
+        __syncthreads();
+        if (i < Nc) {
+          const unsigned int ex = carry + (warp > 0 ? (unsigned int)s_wo[warp - 1] : 0u) + x - v;
+          s_iptr[i] = (int)(ex & 0xffffu);
+          s_optr[i] = (int)(ex >> 16);
+          s_dis[i] = 1.0f / sqrtf((float)(v >> 16));                  // deg^-1/2, degree by source row incl. the loop (gcn_conv.py:66)
+          s_cin[i] = 0;                                               // becomes the fill cursor
+          s_cout[i] = 0;
+        }
+        carry += (unsigned int)s_wo[T / 32 - 1];
+        __syncthreads();
+      }
+      if (t == 0) {
+        s_iptr[Nc] = (int)(carry & 0xffffu);
+        s_optr[Nc] = (int)(carry >> 16);
+      }
+    }
+    __syncthreads();
+    // 2. fill in arrival order (arbitrary); key = local column index, the appended self loop (key Ec + node) takes
+    //    the last slot of its row
+    for (int el = t; el < Ec; el += T) {
+      const unsigned int pk = s_edge[el];
+      if (pk == 0xffffffffu) continue;
+      const int r = (int)(pk >> 16), d = (int)(pk & 0xffffu);
+      s_ikey[s_iptr[d] + atomicAdd(&s_cin[d], 1)] = (unsigned short)el;
+      s_okey[s_optr[r] + atomicAdd(&s_cout[r], 1)] = (unsigned short)el;
+    }
+    for (int i = t; i < Nc; i += T) {
+      s_ikey[s_iptr[i + 1] - 1] = (unsigned short)(Ec + i);
+      s_okey[s_optr[i + 1] - 1] = (unsigned short)(Ec + i);
+    }
+    __syncthreads();
+    // 3. write-out.  Rows are ordered by edge_index column WITHOUT sorting: the final slot of an entry is its row
+    //    start + the number of smaller keys in its (short) row, counted entry-parallel.
+    for (int i = t; i < Nc; i += T) {
+      c.in_ptr[n0 + i] = base + s_iptr[i];
+      c.out_ptr[n0 + i] = base + s_optr[i];
+      c.dis[n0 + i] = s_dis[i];
+    }
+    if (g == B - 1 && t == 0) {
+      c.in_ptr[N] = base + s_iptr[Nc];
+      c.out_ptr[N] = base + s_optr[Nc];
+    }
+    const int tot = s_iptr[Nc];
+    for (int u = t; u < tot; u += T) {
+      const int key = (int)s_ikey[u];
+      int n, src;
+      if (key < Ec) {
+        const unsigned int pk = s_edge[key];
+        src = (int)(pk >> 16);
+        n = (int)(pk & 0xffffu);
+      } else {
+        n = src = key - Ec;
+      }
+      const int a = s_iptr[n], b = s_iptr[n + 1];
+      int rank = 0;
+      for (int v = a; v < b; ++v) rank += (int)s_ikey[v] < key;
+      const int p = base + a + rank;
+      c.in_key[p] = key < Ec ? e0 + key : E + n0 + n;
+      c.in_src[p] = n0 + src;
+      c.in_norm[p] = s_dis[src] * s_dis[n];                           // dis[row] * 1 * dis[col]
+    }
+    for (int u = t; u < tot; u += T) {
+      const int key = (int)s_okey[u];
+      int n, dst;
+      if (key < Ec) {
+        const unsigned int pk = s_edge[key];
+        n = (int)(pk >> 16);
+        dst = (int)(pk & 0xffffu);
+      } else {
+        n = dst = key - Ec;
+      }
+      const int a = s_optr[n], b = s_optr[n + 1];
+      int rank = 0;
+      for (int v = a; v < b; ++v) rank += (int)s_okey[v] < key;
+      const int a2 = s_iptr[dst], b2 = s_iptr[dst + 1];
+      int rank2 = 0;
+      for (int v = a2; v < b2; ++v) rank2 += (int)s_ikey[v] < key;
+      const int q = base + a + rank;
+      c.out_key[q] = key < Ec ? e0 + key : E + n0 + n;
+      c.out_dst[q] = n0 + dst;
+      c.out_pos[q] = base + a2 + rank2;                               // in-CSR position of the same edge
+      c.out_norm[q] = s_dis[n] * s_dis[dst];
+    }
+    __syncthreads();
+  }
+  // the last CTA to finish clears the self-loop counters for the next batch (every CTA has read its prefixes by now)
+  __syncthreads();
+  if (t == 0) {
+    __threadfence();
+    s_last = atomicAdd(done, 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {
+    for (int b = t; b < c.Bm; b += T) nself[b] = 0;
+    if (t == 0) *done = 0;
   }
 }
 
@@ -577,6 +799,14 @@ int launch_prep(const Ctx& c, cudaStream_t s) {
     return 0;
   }
   const int T = 256;
+  if (c.grouped) {                                  // cal_caps.grouped_edges: two launches, one CTA per graph
+    const int gi2 = imax(1, imin(ceil_div(imax(imax(c.Nm, c.Bm + 1), c.Em), T), kMaxStatBlocks));
+    launch_k(k_prep_init, dim3(gi2), dim3(T), 0, s, c);
+    launch_k(k_prep_graph, dim3(imax(1, imin(c.Bm, 4 * kSMs))), dim3(kPgT), 0, s, c);
+    note_launches(2);
+    CAL_CUDA_CHECK_LAUNCH();
+    return 0;
+  }
   int gi = imax(1, imin(ceil_div(imax(imax(c.Nm, c.Bm + 1), c.Em), T), kMaxStatBlocks));
   int ge = imax(1, imin(ceil_div(imax(c.Em, c.Nm), T), 4 * kSMs));
   launch_k(k_prep_init, dim3(gi), dim3(T), 0, s, c);

@@ -246,11 +246,14 @@ class Engine:
         grow = lambda need, cur, q: max(cur, _round_up(int(need * 1.25) + 1, q))
         return self.set_caps(grow(N, c.max_nodes if c else 0, 256), grow(E, c.max_edges if c else 0, 256),
                              grow(B, c.max_graphs if c else 0, 32) if c else _round_up(max(B, 1), 32),
-                             small_graphs=bool(c.small_graphs) if c else False)
+                             small_graphs=bool(c.small_graphs) if c else False,
+                             grouped_edges=bool(c.grouped_edges) if c else False)
 
-    def set_caps(self, max_nodes, max_edges, max_graphs, small_graphs=False):
+    def set_caps(self, max_nodes, max_edges, max_graphs, small_graphs=False, grouped_edges=False):
         """(Re)allocate the workspace for explicit capacities.  ``small_graphs``: the caller guarantees
-        <= 40 nodes and <= 320 CSR entries per graph (cal_caps.small_graphs: the fused small-graph forward).  A Trainer that owned the previous
+        <= 40 nodes and <= 320 CSR entries per graph (cal_caps.small_graphs: the fused small-graph forward);
+        ``grouped_edges``: the caller guarantees edge_index columns grouped by graph, <= 512 nodes and <= 4096 columns
+        per graph (cal_caps.grouped_edges: per-graph structure preparation).  A Trainer that owned the previous
         workspace is invalidated (its captured CUDA graphs point into freed memory): its next step raises."""
         owner = self._owner() if self._owner is not None else None
         if owner is not None:
@@ -259,6 +262,7 @@ class Engine:
         caps = _lib.Caps()
         caps.max_nodes, caps.max_edges, caps.max_graphs = int(max_nodes), int(max_edges), int(max_graphs)
         caps.small_graphs = self._fsg_level(small_graphs) if int(max_graphs) <= self.FSG_GRAPHS else 0
+        caps.grouped_edges = 1 if grouped_edges else 0
         nbytes = self.lib.cal_workspace_bytes(C.byref(self.desc), C.byref(caps))
         if nbytes == 0:
             raise _lib.CalError("cal_b200: unsupported model configuration or capacities (hidden must be 32/64/128, "
@@ -343,6 +347,20 @@ class Engine:
                 ents += torch.bincount(bvec[ei[0]], minlength=B)
             small = bool((nodes.max() <= self.FSG_ROWS) & (ents.max() <= self.FSG_ENTRIES))
         self.caps.small_graphs = self._fsg_level(small)
+        # batches beyond the single-kernel structure path (csrc/prep.cu launch_prep): per-graph preparation when the
+        # edge_index columns are grouped by graph (PyG collate) and every graph fits a CTA's shared memory
+        c = self.caps
+        beyond = (4 * (5 * c.max_nodes + (c.max_edges + c.max_nodes) + c.max_edges + 8) > 225 * 1024
+                  or c.max_edges + c.max_nodes >= 65535)
+        grouped = False
+        if beyond and N > 0 and B > 0 and ei.numel() > 0:
+            gs = bvec[ei[0]]
+            grouped = bool((gs[1:] >= gs[:-1]).all() & (gs == bvec[ei[1]]).all()
+                           & (torch.bincount(bvec, minlength=B).max() <= self.PG_NODES)
+                           & (torch.bincount(gs, minlength=B).max() <= self.PG_COLS))
+        c.grouped_edges = 1 if grouped else 0
+
+    PG_NODES, PG_COLS = 512, 4096                        # csrc/prep.cu k_prep_graph
 
     def _fsg_level(self, small):
         """cal_caps.small_graphs: 0 = tiled kernels, 1 = fused small-graph forward and backward, 2 = fused forward only."""

@@ -30,23 +30,31 @@ def _up(x, m):
 
 
 FSG_ROWS, FSG_ENTRIES = 40, 320          # csrc/fsg.cuh: the fused small-graph path's per-graph limits
+PG_NODES, PG_COLS = 512, 4096            # csrc/prep.cu k_prep_graph: per-graph limits of cal_caps.grouped_edges
 
 
 def batch_caps(batches, slack=1.0):
-    """Capacities covering ``batches``: (max nodes, max edge_index columns, max graphs, small_graphs) --
+    """Capacities covering ``batches``: (max nodes, max edge_index columns, max graphs, small_graphs, grouped_edges) --
     ``small_graphs`` is True when every graph has <= 40 nodes and <= 320 CSR entries (edges + one self loop
-    per node), which lets CausalGCN run the fused small-graph forward (cal_caps.small_graphs)."""
+    per node), which lets CausalGCN run the fused small-graph forward (cal_caps.small_graphs);
+    ``grouped_edges`` is True when the edge_index columns of every batch are grouped by graph in graph order with both
+    endpoints inside the graph (what PyG's collate produces) and no graph exceeds 512 nodes / 4096 columns
+    (cal_caps.grouped_edges: per-graph structure preparation for batches beyond the single-kernel path)."""
     n = max(int(b.batch.numel()) for b in batches)
     e = max(int(b.edge_index.size(1)) for b in batches)
     g = max(int(b.num_graphs) for b in batches)
-    small = True
+    small, grouped = True, True
     for b in batches:
-        nodes = np.bincount(b.batch.numpy(), minlength=int(b.num_graphs))
-        ents = nodes + np.bincount(b.batch.numpy()[b.edge_index[0].numpy()], minlength=int(b.num_graphs))
-        if nodes.max(initial=0) > FSG_ROWS or ents.max(initial=0) > FSG_ENTRIES:
+        bv, ei = b.batch.numpy(), b.edge_index.numpy()
+        nodes = np.bincount(bv, minlength=int(b.num_graphs))
+        gsrc = bv[ei[0]]
+        cols = np.bincount(gsrc, minlength=int(b.num_graphs))
+        if nodes.max(initial=0) > FSG_ROWS or (nodes + cols).max(initial=0) > FSG_ENTRIES:
             small = False
-            break
-    return _up(int(n * slack), 32), _up(max(int(e * slack), 1), 32), _up(g, 8), small
+        if (nodes.max(initial=0) > PG_NODES or cols.max(initial=0) > PG_COLS or np.any(np.diff(gsrc) < 0)
+                or np.any(gsrc != bv[ei[1]])):
+            grouped = False
+    return _up(int(n * slack), 32), _up(max(int(e * slack), 1), 32), _up(g, 8), small, grouped
 
 
 def epoch_order(num_graphs, epoch, seed=0, rank=0, world_size=1, graphs_per_step=None):

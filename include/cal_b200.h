@@ -86,6 +86,12 @@ typedef struct {
                                   transforms; csrc/fsg.cu) and the fused small-graph backward (csrc/fsg_bwd.cu).  2: the fused
                                   forward only (the tiled backward kernels run on what it saved; A/B tests).  A batch that
                                   breaks the promise sets CAL_ST_CAPACITY. */
+  int32_t grouped_edges;       /* != 0: the caller guarantees that the edge_index columns of every batch are grouped by graph, in
+                                  graph order, with both endpoints inside the graph (what Batch.from_data_list / PyG collate
+                                  and cal_collate produce), and that no graph has more than 512 nodes or 4096 edge_index
+                                  columns.  Batches too large for the single-kernel structure path are then prepared by
+                                  one CTA per graph in shared memory (k_prep_graph) instead of the global counting sort.
+                                  A batch that breaks the promise sets CAL_ST_BAD_BATCH / CAL_ST_CAPACITY. */
 } cal_caps;
 
 /* Offsets (in floats) of every parameter inside the flat parameter buffer;
@@ -181,6 +187,7 @@ enum cal_ws_region {
   CAL_WS_EDGE_WN,      /* f32[EP][2] dis_w[source] * edge_att by in-CSR position (weighted norm without the target factor) */
   CAL_WS_EDGE_NA,      /* f32[EP][2] node_att[source] by in-CSR position */
   CAL_WS_FSG,          /* fused small-graph path: block plan, all-reduce scratch and counters, pre-split weight images */
+  CAL_WS_EDGE_GPTR,    /* i32[B+1] first edge_index column of every graph | i32[B] self loops per graph | arrival counter (grouped_edges) */
   CAL_WS_REGION_COUNT
 };
 

@@ -198,6 +198,87 @@ def test_prep_structure_bit_exact(name):
     assert np.array_equal(eng.region("IN_NORM")[:EPn].cpu().numpy(), rp["in_norm"])
 
 
+def _big_batch(seed):
+    """A batch beyond the single-kernel structure path (N ~ 10 k nodes), with self loops inside some graphs, an
+    edgeless graph and a one-node neighbourhood -- the cases that move the rows of all later graphs."""
+    ora, b, _ = random_case(seed=seed, hidden=32, batch_size=96, avg_nodes=110)
+    ei, bv = b.edge_index.clone(), b.batch
+    g_of = bv[ei[0]]
+    keep = g_of != 7                                           # graph 7 loses all its edges
+    ei = ei[:, keep]
+    g_of = g_of[keep]
+    for g in (0, 3, 40, 95):                                    # self loops: replace the 2nd column of these graphs by (r, r)
+        idx = torch.nonzero(g_of == g)[1, 0]
+        ei[1, idx] = ei[0, idx]
+    b.edge_index = ei
+    return ora, b
+
+
+@pytest.mark.parametrize("grouped", [False, True], ids=["global_sort", "per_graph"])
+def test_prep_structure_bit_exact_beyond_the_single_kernel_path(grouped):
+    """Batches too large for k_prep_small: the five-pass global path and the per-graph path (cal_caps.grouped_edges,
+    k_prep_graph) both reproduce the reference structure bit for bit."""
+    M, _ = _mods()
+    ora, b = _big_batch(301)
+    N, E, B = b.batch.numel(), b.edge_index.size(1), b.y.numel()
+    assert N > 8000
+    net = clone_to_cuda(ora, M)
+    eng = net.engine
+    eng.set_caps(N + 7, E + 5, B, grouped_edges=grouped)
+    st = eng.stage(b.to(DEV))
+    eng.caps.grouped_edges = int(grouped)                       # (stage() auto-detects the layout on the module path)
+    for rep in range(2):                                        # twice: the self-loop counters re-arm themselves
+        eng.prep(st)
+        torch.cuda.synchronize()
+        assert eng.status() == 0
+        assert int(eng.caps.grouped_edges) == int(grouped)
+        rp = ref_prep(b.edge_index.numpy(), b.batch.numpy(), B)
+        EPn = int(rp["in_ptr"][-1])
+        for k, n in (("IN_PTR", N + 1), ("IN_SRC", EPn), ("IN_KEY", EPn), ("OUT_PTR", N + 1), ("OUT_DST", EPn),
+                     ("OUT_KEY", EPn), ("OUT_POS", EPn), ("GRAPH_PTR", B + 1)):
+            got = eng.region(k, torch.int32)[:n].cpu().numpy()
+            assert np.array_equal(got, rp[k.lower()]), (k, rep)
+        assert np.array_equal(eng.region("DIS")[:N].cpu().numpy(), rp["dis"])
+        assert np.array_equal(eng.region("IN_NORM")[:EPn].cpu().numpy(), rp["in_norm"])
+        pos = eng.region("OUT_POS", torch.int32)[:EPn].long()
+        assert torch.equal(eng.region("OUT_NORM")[:EPn], eng.region("IN_NORM")[:EPn][pos])
+
+
+def test_grouped_edges_promise_is_checked_and_auto_detected():
+    """cal_caps.grouped_edges with edge_index columns that are NOT grouped by graph: the status word says so; the module
+    path (no Trainer) detects the layout per batch and falls back to the global path with correct results."""
+    M, _ = _mods()
+    L = M._lib
+    ora, b = _big_batch(302)
+    N, E, B = b.batch.numel(), b.edge_index.size(1), b.y.numel()
+    perm = torch.randperm(E, generator=torch.Generator().manual_seed(5))
+    bs = copy.copy(b)
+    bs.edge_index = b.edge_index[:, perm]                        # same graph, columns shuffled
+    net = clone_to_cuda(ora, M)
+    eng = net.engine
+    st = eng.stage(bs.to(DEV))                                   # module path: auto-detection
+    assert int(eng.caps.grouped_edges) == 0
+    eng.prep(st)
+    torch.cuda.synchronize()
+    assert eng.status() == 0
+    rp = ref_prep(bs.edge_index.numpy(), bs.batch.numpy(), B)
+    assert np.array_equal(eng.region("IN_KEY", torch.int32)[:int(rp["in_ptr"][-1])].cpu().numpy(), rp["in_key"])
+    st = eng.stage(b.to(DEV))                                    # grouped columns: detected
+    assert int(eng.caps.grouped_edges) == 1
+    eng.prep(st)
+    torch.cuda.synchronize()
+    assert eng.status() == 0
+    rp = ref_prep(b.edge_index.numpy(), b.batch.numpy(), B)
+    assert np.array_equal(eng.region("IN_KEY", torch.int32)[:int(rp["in_ptr"][-1])].cpu().numpy(), rp["in_key"])
+    # a false promise
+    eng.caps.grouped_edges = 1
+    st2 = eng.stage(bs.to(DEV))
+    eng.caps.grouped_edges = 1                                   # (stage() re-detected it)
+    eng.prep(st2)
+    torch.cuda.synchronize()
+    assert eng.status() & (L.CAL_ST_BAD_BATCH | L.CAL_ST_BAD_NODE)
+
+
 @pytest.mark.parametrize("name", ALL_GOLDEN)
 def test_module_matches_reference_golden(name):
     """The nn.Module drop-in against vectors frozen from the reference's own model.py."""

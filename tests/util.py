@@ -145,7 +145,9 @@ def ref_prep(edge_index, batch, num_graphs):
     b = np.asarray(batch)
     graph_ptr = np.searchsorted(b, np.arange(num_graphs + 1), side="left").astype(np.int32)
     deg = np.bincount(rows, minlength=N).astype(np.float32)
-    dis = (deg ** np.float32(-0.5)).astype(np.float32)
+    # gcn_conv.py:67 deg.pow(-0.5): torch evaluates the exponent -0.5 as 1 / sqrt(x), correctly rounded twice (checked
+    # for every degree below 2000); numpy's float32 power differs from it in the last bit from degree 17 on
+    dis = (np.float32(1.0) / np.sqrt(deg)).astype(np.float32)
     return dict(in_ptr=in_ptr, in_src=rows[o_in].astype(np.int32), in_key=keys[o_in].astype(np.int32),
                 out_ptr=out_ptr, out_dst=cols[o_out].astype(np.int32), out_key=keys[o_out].astype(np.int32),
                 out_pos=out_pos, graph_ptr=graph_ptr, dis=dis,
