@@ -299,6 +299,11 @@ int cal_image_sink_init(const cal_model_desc* m, const cal_caps* caps, const cal
   c.train = 1;
   if (!(c.fsg_bwd_on && readout_runs_ro(c))) return CAL_OK;          // count = 0: the fused path is not taken
   fsg_fill_image_sink(c, sink);
+  for (int q = 0; q < sink->count; ++q)
+    if (sink->entry[q].offset % 4 != 0) {                             // (the optimizer kernels write four image words at a time)
+      memset(sink, 0, sizeof(*sink));
+      return CAL_OK;
+    }
   return CAL_OK;
 }
 

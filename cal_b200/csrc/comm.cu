@@ -90,6 +90,13 @@ __global__ void __launch_bounds__(256) k_dp_adam(const DpPeers peers, const int 
   const long long c0 = (long long)blockIdx.x * chunk;
   const long long c1 = c0 + chunk < n ? c0 + chunk : n;            // n % 4 == 0 is checked on the host
   pdl_sync();                                                      // the gradients are complete
+#ifdef CAL_TIMELINE
+  int* dp_stamps = reinterpret_cast<int*>(hdr) + 16;                     // (timeline builds: CTA 0's stamps in the header's spare words)
+#define DP_TL(id) do { if (blockIdx.x == 0) CAL_TL(dp_stamps - 96, id); } while (0)
+#else
+#define DP_TL(id) do { } while (0)
+#endif
+  DP_TL(0);
   // (hdr->seq is read AFTER the dependency wait: a directly preceding cal_dp_adam_step has then published it)
   if (threadIdx.x == 0) s_seq = *reinterpret_cast<volatile unsigned int*>(&hdr->seq) + 1u;
   if (threadIdx.x == 0) {       // bias corrections in fp64 like the Python scalars of torch.optim.Adam
@@ -100,6 +107,19 @@ __global__ void __launch_bounds__(256) k_dp_adam(const DpPeers peers, const int 
     s_c[0] = (float)((double)lr / bc1);
     s_c[1] = (float)sqrt(bc2);
   }
+  // This thread's piece of the chunk, fetched before anything waits: the gradient goes to the peers from registers,
+  // the parameter and its moments are only needed after the peers' flags have arrived.  (A chunk is n_pad / 148 floats:
+  // at most one float4 per thread up to 151 552 parameters; larger models take the strided loops.)
+  const bool one = chunk <= 4ll * blockDim.x;                       // uniform
+  const long long i0 = c0 + 4ll * threadIdx.x;
+  const bool have = one && i0 < c1;
+  float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), p4 = g4, m4 = g4, v4 = g4;
+  if (have) {
+    g4 = *reinterpret_cast<const float4*>(g + i0);
+    p4 = *reinterpret_cast<const float4*>(p + i0);
+    m4 = *reinterpret_cast<const float4*>(m + i0);
+    v4 = *reinterpret_cast<const float4*>(v + i0);
+  }
   __syncthreads();
   const unsigned int seq = s_seq;
   const int par = (int)(seq & 1u);
@@ -107,13 +127,22 @@ __global__ void __launch_bounds__(256) k_dp_adam(const DpPeers peers, const int 
   for (int d = 1; d < world; ++d) {
     const int q = (rank + d) % world;                              // staggered: ranks do not all hit peer 0 first
     float* dst = dp_slot(peers.region[q], world, n_pad, par, rank);
-    for (long long i = c0 + 4ll * threadIdx.x; i < c1; i += 4ll * blockDim.x)
-      *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(g + i);
+    if (one) {
+      if (have) *reinterpret_cast<float4*>(dst + i0) = g4;
+    } else {
+      for (long long i = i0; i < c1; i += 4ll * blockDim.x)
+        *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(g + i);
+    }
   }
-  __threadfence_system();
+  DP_TL(1);
+  // One release per flag: the barrier orders every thread's pushes before the flag writers' st.release.sys, whose
+  // fence is cumulative over them (the pattern of a grid barrier: bar.sync, then one thread fences and signals).  An
+  // extra __threadfence_system() by all 256 threads in front of the barrier cost 6.6 us here (timeline build).
   __syncthreads();
+  DP_TL(2);
   if ((int)threadIdx.x < world && (int)threadIdx.x != rank)
     st_release_sys(dp_flag(peers.region[threadIdx.x], world, par, rank, blockIdx.x), seq);
+  DP_TL(3);
   // ---- 2. wait for every peer's chunk ----
   if ((int)threadIdx.x < world && (int)threadIdx.x != rank) {
     const unsigned int* f = dp_flag(peers.region[rank], world, par, threadIdx.x, blockIdx.x);
@@ -132,20 +161,24 @@ __global__ void __launch_bounds__(256) k_dp_adam(const DpPeers peers, const int 
     }
   }
   __syncthreads();
+  DP_TL(4);
   // ---- 3. rank-ordered sum + Adam on the chunk ----
   const float step_size = s_c[0], bc2s = s_c[1];
   const float gscale = 1.0f / (float)world;
   const float* mine = dp_slot(peers.region[rank], world, n_pad, par, 0);
-  for (long long i = c0 + 4ll * threadIdx.x; i < c1; i += 4ll * blockDim.x) {
+  for (long long i = i0; i < c1; i += 4ll * blockDim.x) {
+    if (!one) {
+      g4 = *reinterpret_cast<const float4*>(g + i);
+      p4 = *reinterpret_cast<const float4*>(p + i);
+      m4 = *reinterpret_cast<const float4*>(m + i);
+      v4 = *reinterpret_cast<const float4*>(v + i);
+    }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int q = 0; q < world; ++q) {
-      const float4 t = q == rank ? *reinterpret_cast<const float4*>(g + i)
-                                 : __ldcg(reinterpret_cast<const float4*>(mine + (size_t)q * n_pad + i));
+      const float4 t = q == rank ? g4 : __ldcg(reinterpret_cast<const float4*>(mine + (size_t)q * n_pad + i));
       acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
     }
     float gi[4] = {acc.x * gscale, acc.y * gscale, acc.z * gscale, acc.w * gscale};
-    float4 p4 = *reinterpret_cast<float4*>(p + i), m4 = *reinterpret_cast<float4*>(m + i),
-           v4 = *reinterpret_cast<float4*>(v + i);
     float pp[4] = {p4.x, p4.y, p4.z, p4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -159,11 +192,10 @@ __global__ void __launch_bounds__(256) k_dp_adam(const DpPeers peers, const int 
     *reinterpret_cast<float4*>(m + i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
     *reinterpret_cast<float4*>(v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
     *reinterpret_cast<float4*>(p + i) = make_float4(pp[0], pp[1], pp[2], pp[3]);
-    if (sink.count > 0) {                                            // operand images of the fused small-graph path
-#pragma unroll
-      for (int k = 0; k < 4; ++k) fsg_sink_emit(sink, i + k, pp[k]);
-    }
+    DP_TL(6);
+    if (sink.count > 0) fsg_sink_emit4(sink, i, make_float4(pp[0], pp[1], pp[2], pp[3]));   // operand images of the fused small-graph path
   }
+  DP_TL(5);
   // every CTA has read hdr->seq and *step before it arrives here, so the last one may advance them
   __syncthreads();
   if (threadIdx.x == 0) {

@@ -99,4 +99,36 @@ __device__ __forceinline__ void fsg_sink_emit(const cal_image_sink& sk, long lon
   }
 }
 
+// ... of four consecutive parameters i .. i + 3 (i % 4 == 0: they share a matrix row, every sink offset is a multiple
+// of 4).  The four words of the "n" image are contiguous (one 16-byte store per part), those of the "t" image are
+// 16 bytes apart.
+__device__ __forceinline__ void fsg_sink_emit4(const cal_image_sink& sk, long long i, float4 v) {
+  for (int q = 0; q < sk.count; ++q) {
+    const long long d = i - sk.entry[q].offset;
+    if (d < 0 || d >= (long long)sk.entry[q].rows * kFsgH) continue;
+    const int r = (int)(d >> 7), cc = (int)(d & 127);
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    float hi[4], lo[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      hi[k] = __uint_as_float((__float_as_uint(x[k]) + 0x1000u) & 0xffffe000u);      // umma::split_tf32
+      lo[k] = x[k] - hi[k];
+    }
+    if (sk.entry[q].dst_n != nullptr) {
+      float* p = sk.entry[q].dst_n + (cc >> 2) * 512 + r * 4;
+      *reinterpret_cast<float4*>(p) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(p + kFsgImgPart) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    if (sk.entry[q].dst_t != nullptr) {
+      float* p = sk.entry[q].dst_t + (r >> 2) * 512 + cc * 4 + (r & 3);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        p[4 * k] = hi[k];
+        p[4 * k + kFsgImgPart] = lo[k];
+      }
+    }
+    return;
+  }
+}
+
 }  // namespace cal
