@@ -436,7 +436,8 @@ def run_gpu(a, rank, local_rank, world):
     ms = float(t.item())
     value = a.steps * graphs_per_step * world / (ms * 1e-3)
     loss_after = tr.metrics().cpu().tolist()
-    launches = int(tr.launches_per_step) * a.steps
+    lps = int(tr.launches_per_step)                  # kernels per step of the timed loop (with the look-ahead: the next batch's structure kernel included)
+    launches = lps * a.steps
     dp_check = dp_verify(tr, resident[0], dist, dev, world) if dist is not None else None
 
     # ---- end to end: pinned host batch -> H2D -> step -> loss parts D2H, every step ----
@@ -621,7 +622,7 @@ def run_gpu(a, rank, local_rank, world):
             "sample": sample_stats(batches, "inputs larger than L2: %d distinct resident batches (%.0f MB) cycled; "
                                             "workspace reused" % (n_res, resident_bytes / 2 ** 20)),
             "clocks": clk.summary(t_begin, t_end), "e2e": e2e, "gpu_launches": launches,
-            "launches_per_step": int(tr.launches_per_step), "cuda_graph": not a.no_graph, "steps_per_graph_launch": spg,
+            "launches_per_step": lps, "cuda_graph": not a.no_graph, "steps_per_graph_launch": spg,
             "collective": {"none": "none (1 GPU)", "nccl": "ncclAllReduce of the flat gradient buffer between a compute and an update graph",
                            "peer": "NVLink peer-memory push of the gradient chunks fused with Adam (cal_dp_adam_step), one captured graph per step"}[tr.collective],
             "dp_check": dp_check, "roofline": roofline, "cpu_baseline": cpu, "stages": stage_tab,
