@@ -664,7 +664,10 @@ class Trainer:
         self._prepped_ptr = None
         saved = self._save_state()
         keep = self._gat_keep_for(None)
-        self._issue(packed_dev.data_ptr(), keep)               # every buffer holds a consistent step
+        # every buffer holds a consistent step.  LOCAL update: this is a single-rank measurement -- a gradient exchange
+        # here would wait for peers that are not taking part (bench.py times the stages on rank 0 only)
+        self._issue(packed_dev.data_ptr(), keep, part="compute")
+        eng.adam_step(0.0, self.betas, self.eps, self.weight_decay, 1.0, lr_device=self.lr_dev)
         cb = self.layout.cbatch(packed_dev.data_ptr())
         if keep is not None:
             cb.gat_keep = keep.data_ptr()
