@@ -1,4 +1,4 @@
-// fsg.cuh -- shared definitions of the fused small-graph path (fsg.cu, fsg_prep in prep.cu).
+// fsg.cuh -- shared definitions of the fused small-graph path (fsg.cu, fsg_bwd.cu, head_ro.cu; the image sink of optim.cu / comm.cu).
 //
 // "Small graphs": every graph of the batch has at most kFsgRows nodes and kFsgEntries CSR entries (edges
 // after self-loop surgery), and the batch has at most kSMs row blocks.  Then a CTA owns a BLOCK of whole
@@ -20,7 +20,7 @@ constexpr int kFsgImg = 2 * kFsgImgPart;   // hi | lo
 
 // the CAL_WS_FSG region (byte offsets)
 struct FsgLayout {
-  size_t plan, info, cnt, acc, img, part, total;
+  size_t info, cnt, acc, img, part, total;
 };
 __host__ __device__ inline size_t fsg_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -36,7 +36,6 @@ __host__ __device__ inline size_t fsg_part_floats(int L, int F) { return fsg_par
 __host__ __device__ inline FsgLayout fsg_layout(int Bm, int L, int F) {
   FsgLayout f;
   size_t o = 0;
-  f.plan = o;  o = fsg_up(o + 16);                                        // (reserved)
   f.info = o;  o = fsg_up(o + (size_t)(Bm > 0 ? Bm : 1) * 32);            // i32[8] per block, written by the forward kernel: graphs [g0, g1), nodes [n0, n1), in-CSR entries [e0, e1), first out-CSR entry, fits-the-limits flag
   f.cnt = o;   o = fsg_up(o + (size_t)(2 * kFsgPhases * kFsgCntStride + 8) * 4);     // site counters of both sets + the epoch words
   f.acc = o;   o = fsg_up(o + (size_t)2 * kFsgPhases * 8 * 2 * kFsgVec * 8);       // fixed-point all-reduce accumulators, two sets (fsg_dev.cuh)
@@ -48,7 +47,6 @@ __host__ __device__ inline FsgLayout fsg_layout(int Bm, int L, int F) {
 }
 
 struct FsgWs {
-  int* plan;
   int* info;
   unsigned int* cnt;
   long long* acc;
@@ -58,7 +56,6 @@ struct FsgWs {
 __host__ __device__ inline FsgWs fsg_ws(const Ctx& c) {
   const FsgLayout f = fsg_layout(c.Bm, c.L, c.F);
   FsgWs w;
-  w.plan = reinterpret_cast<int*>(c.fsg + f.plan);
   w.info = reinterpret_cast<int*>(c.fsg + f.info);
   w.cnt = reinterpret_cast<unsigned int*>(c.fsg + f.cnt);
   w.acc = reinterpret_cast<long long*>(c.fsg + f.acc);

@@ -186,7 +186,7 @@ enum cal_ws_region {
   CAL_WS_OUT_NORM,     /* f32[EP] unweighted norm by out-CSR position (= IN_NORM[OUT_POS]) */
   CAL_WS_EDGE_WN,      /* f32[EP][2] dis_w[source] * edge_att by in-CSR position (weighted norm without the target factor) */
   CAL_WS_EDGE_NA,      /* f32[EP][2] node_att[source] by in-CSR position */
-  CAL_WS_FSG,          /* fused small-graph path: block plan, all-reduce scratch and counters, pre-split weight images */
+  CAL_WS_FSG,          /* fused small-graph path: block records, all-reduce accumulators and counters, pre-split weight images, per-block partial gradients */
   CAL_WS_EDGE_GPTR,    /* i32[B+1] first edge_index column of every graph | i32[B] self loops per graph | arrival counter (grouped_edges) */
   CAL_WS_REGION_COUNT
 };
