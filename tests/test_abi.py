@@ -110,6 +110,70 @@ def test_host_side_argument_validation_no_launch():
     assert lib.cal_launch_count() == n0
 
 
+def _offsets(L, layers=3):
+    """Synthetic parameter offsets: every tensor 16 384 floats apart (aligned; only the host-side checks read them)."""
+    po = L.ParamOffsets()
+    k = 0
+    for f, _t in po._fields_:
+        if f == "total":
+            continue
+        v = getattr(po, f)
+        if isinstance(v, int):
+            setattr(po, f, k * 16384)
+            k += 1
+        else:
+            for i in range(len(v)):
+                v[i] = k * 16384 if i < layers or len(v) == 3 else -1
+                k += 1
+    po.total = k * 16384
+    return po
+
+
+def test_image_sink_describes_the_fused_path_images_host_only():
+    """cal_image_sink_init (host only): one entry per conv matrix (forward + backward image), the input transform and the
+    three fc1 matrices when the fused small-graph path is taken, none otherwise; argument errors; no launch."""
+    L, lib = _lib()
+    n0 = lib.cal_launch_count()
+    d, po = _desc(L), _offsets(L)
+    c = _caps(L)
+    c.small_graphs = 1
+    nbytes = lib.cal_workspace_bytes(C.byref(d), C.byref(c))
+    ws = 1 << 20                                          # (never dereferenced on the host)
+    sk = L.ImageSink()
+    assert lib.cal_image_sink_init(C.byref(d), C.byref(c), C.byref(po), ws, nbytes, None) == -2
+    assert lib.cal_image_sink_init(C.byref(d), C.byref(c), C.byref(po), 0, nbytes, C.byref(sk)) == -2
+    assert lib.cal_image_sink_init(C.byref(d), C.byref(c), C.byref(po), ws, nbytes, C.byref(sk)) == 0
+    assert sk.count == 3 + 2 + 1 + 3
+    offs = [po.convs_w[0], po.convs_w[1], po.convs_w[2], po.context_w, po.objects_w, po.conv_feat_w,
+            po.fc1_w[0], po.fc1_w[1], po.fc1_w[2]]
+    img = 2 * 16384 * 4                                   # bytes of one image (hi | lo)
+    seen = set()
+    for q in range(sk.count):
+        e = sk.entry[q]
+        assert e.offset == offs[q] and e.rows == (10 if q == 5 else 128)
+        for p in (e.dst_t, e.dst_n):
+            if p:
+                assert ws <= p and p + img <= ws + nbytes and (p - ws) % 16 == 0 and p not in seen
+                seen.add(p)
+        assert (e.dst_n is None) == (q == 5)               # the input transform has one image only
+    assert len(seen) == 2 * 8 + 1
+    c.small_graphs = 0                                    # tiled kernels: nothing to write
+    nbytes0 = lib.cal_workspace_bytes(C.byref(d), C.byref(c))
+    assert lib.cal_image_sink_init(C.byref(d), C.byref(c), C.byref(po), ws, nbytes0, C.byref(sk)) == 0 and sk.count == 0
+    d64 = _desc(L, hidden=64)                             # the fused path is built for hidden 128
+    c.small_graphs = 1
+    nb64 = lib.cal_workspace_bytes(C.byref(d64), C.byref(c))
+    assert lib.cal_image_sink_init(C.byref(d64), C.byref(c), C.byref(po), ws, nb64, C.byref(sk)) == 0 and sk.count == 0
+    po.conv_feat_w += 2                                   # unaligned matrix: the optimizer writes four image words at a time
+    c128 = _caps(L)
+    c128.small_graphs = 1
+    assert lib.cal_image_sink_init(C.byref(d), C.byref(c128), C.byref(po), ws, nbytes, C.byref(sk)) == 0 and sk.count == 0
+    bad = L.ImageSink()
+    bad.count = 17
+    assert lib.cal_adam_step_images(16, 16, 16, 16, 8, 16, 1e-3, 0, 0.9, 0.999, 1e-8, 0.0, 1.0, C.byref(bad), 0) == -1
+    assert lib.cal_launch_count() == n0
+
+
 def test_collate_and_peer_exchange_argument_validation_no_launch():
     """cal_collate / cal_dp_*: sizes and argument errors are decided on the host before any CUDA call."""
     L, lib = _lib()
