@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("CAL_B200_LIB") or os.path.join(HERE, "libcal_b200.so"
 CAL_MAX_LAYERS = 8
 CAL_MAX_BN = 1 + CAL_MAX_LAYERS + 2 + 6
 CAL_MODEL_GCN, CAL_MODEL_GAT, CAL_MODEL_GIN = 0, 1, 2
-CAL_F_TRAIN, CAL_F_LOSS, CAL_F_FSG_READY, CAL_F_NO_OVERLAP = 1, 2, 4, 8
+CAL_F_TRAIN, CAL_F_LOSS, CAL_F_FSG_READY, CAL_F_NO_OVERLAP, CAL_F_RAW_LOGITS_O = 1, 2, 4, 8, 16
 CAL_ST_BAD_NODE, CAL_ST_BAD_BATCH, CAL_ST_CAPACITY = 1, 2, 4
 
 # enum cal_ws_region, in header order

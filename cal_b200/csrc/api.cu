@@ -351,6 +351,8 @@ int cal_causal_forward(const cal_model_desc* m, const cal_caps* caps, const cal_
   c.nbt = reinterpret_cast<long long*>(bn_num_batches_tracked);
   c.train = train;
   c.with_loss = (flags & CAL_F_LOSS) != 0;
+  c.raw_o = (flags & CAL_F_RAW_LOGITS_O) != 0;
+  if (c.raw_o && (readout_path_id(c) != 0 || c.with_loss)) return CAL_EUNSUPPORTED;   // FFMA readout kernels, loss by the caller
   cudaStream_t s = (cudaStream_t)stream;
   const int L = c.L;
   int lo = 0, hi = L + 5;
@@ -401,6 +403,8 @@ int cal_causal_backward(const cal_model_desc* m, const cal_caps* caps, const cal
   c.grads = grads;
   c.train = 1;
   c.grad_logp = grad_logp;
+  c.raw_o = (flags & CAL_F_RAW_LOGITS_O) != 0;
+  if (c.raw_o && (readout_path_id(c) != 0 || grad_logp == nullptr)) return CAL_EUNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   const int L = c.L;
   int lo = 0, hi = L + 6;

@@ -430,7 +430,7 @@ __global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_fwd
       const long long yb = b == t ? y0 : (b == t + 256 ? y1 : ((c.with_loss && c.y != nullptr) ? c.y[b] : -1));
       for (int cls = 0; cls < C; ++cls) {
         const float lp = sLg[b * C + cls] - m - lse;
-        c.logp[((size_t)h * c.Bm + b) * C + cls] = lp;
+        c.logp[((size_t)h * c.Bm + b) * C + cls] = (c.raw_o && h == 1) ? sLg[b * C + cls] : lp;   // (model.py:288-289: raw logits)
         slp += lp;
         if ((long long)cls == yb) picked = lp;
       }
@@ -514,10 +514,11 @@ __global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(256) k_readout_bwd
       sDl[b * C + cls] = dlp;
       sd += dlp;
     }
-    for (int cls = 0; cls < C; ++cls) {
-      const float lp = c.logp[((size_t)h * c.Bm + b) * C + cls];
-      sDl[b * C + cls] -= expf(lp) * sd;
-    }
+    if (!(c.raw_o && h == 1))                          // (raw logits: the caller's gradient already is d logits)
+      for (int cls = 0; cls < C; ++cls) {
+        const float lp = c.logp[((size_t)h * c.Bm + b) * C + cls];
+        sDl[b * C + cls] -= expf(lp) * sd;
+      }
   }
   // ---- hidden slice, input slice, their BatchNorm records ----
   const float* H1 = c.H1 + (size_t)h * c.Bm * H;
@@ -827,6 +828,7 @@ static int readout_path(const Ctx& c) {
 }
 
 bool readout_runs_ro(const Ctx& c) { return readout_path(c) == 3; }
+int readout_path_id(const Ctx& c) { return readout_path(c); }         // 0 = FFMA cluster kernels
 
 int launch_heads_forward(const Ctx& c, int with_loss, cudaStream_t s) {
   (void)with_loss;

@@ -90,6 +90,7 @@ struct Ctx {
   unsigned char* fsg;       // CAL_WS_FSG region (fsg.cuh)
   int* egp;                 // [Bm+1] first edge column per graph | [Bm] self loops per graph | arrival counter (grouped_edges)
   int grouped;              // cal_caps.grouped_edges
+  int raw_o;                // CAL_F_RAW_LOGITS_O: head 1 exchanges raw logits with the caller
   int fsg_on;               // the fused small-graph forward replaces feat .. masked_convs (and the pooling)
   int fsg_bwd_on;           // ... and the fused small-graph backward replaces masked_gemm_bwd .. feat_bwd
 
@@ -130,6 +131,7 @@ bool readout_tc_supported(const Ctx& c);                                   // te
 int launch_readout_tc_forward(const Ctx& c, cudaStream_t s);
 int launch_readout_tc_backward(const Ctx& c, cudaStream_t s);
 bool readout_ro_supported(const Ctx& c);                                   // short-chain readout of the fused small-graph path (head_ro.cu)
+int readout_path_id(const Ctx& c);                                          // 0 = the FFMA cluster kernels of head.cu
 bool readout_runs_ro(const Ctx& c);                                        // ... and they are the ones that will run (no override)
 int launch_readout_ro_forward(const Ctx& c, cudaStream_t s);
 int launch_readout_ro_backward(const Ctx& c, cudaStream_t s);

@@ -109,7 +109,7 @@ def flat_offsets(module):
 
 class _Staged:
     """Device-side view of one mini-batch handed to the C ABI."""
-    __slots__ = ("N", "E", "B", "cbatch", "keep", "gen")
+    __slots__ = ("N", "E", "B", "cbatch", "keep", "gen", "raw_o")
 
 
 class Engine:
@@ -326,6 +326,7 @@ class Engine:
         cb.perm = self._meta_dev.data_ptr() + 16 if perm is not None else 0
         cb.gat_keep = gat_keep.data_ptr() if gat_keep is not None else 0
         st = _Staged()
+        st.raw_o = False
         st.N, st.E, st.B, st.cbatch = N, E, B, cb
         st.keep = (x, ei, bvec, y, gat_keep)
         return st
@@ -377,8 +378,10 @@ class Engine:
         _lib.check(self.lib.cal_prep(C.byref(self.desc), C.byref(self.caps), C.byref(st.cbatch),
                                      self.ws.data_ptr(), self.ws_bytes, self._stream()), "cal_prep")
 
-    def forward(self, st, train, with_loss=False, copy_out=True, stages=None):
+    def forward(self, st, train, with_loss=False, copy_out=True, stages=None, raw_o=False):
         flags = (_lib.CAL_F_TRAIN if train else 0) | (_lib.CAL_F_LOSS if with_loss else 0)
+        if raw_o:                                          # objects head: raw logits instead of log-probabilities
+            flags |= _lib.CAL_F_RAW_LOGITS_O
         if stages is not None:
             flags |= _lib.stages_flag(*stages)
         self.gen += 1
@@ -392,7 +395,7 @@ class Engine:
             return self.out_logp[:3 * st.B * self.C].view(3, st.B, self.C)
         return None
 
-    def backward(self, st, grad_logp=None, stages=None):
+    def backward(self, st, grad_logp=None, stages=None, raw_o=False):
         if st.gen != self.gen:
             raise _lib.CalError("cal_b200: backward through a stale forward (the workspace holds the "
                                 "activations of the most recent forward only)")
@@ -402,7 +405,8 @@ class Engine:
             gp = grad_logp.data_ptr()
         _lib.check(self.lib.cal_causal_backward(
             C.byref(self.desc), C.byref(self.caps), C.byref(self.po), self.flat.data_ptr(), C.byref(st.cbatch),
-            gp, self.flat_grad.data_ptr(), _lib.stages_flag(*stages) if stages is not None else 0,
+            gp, self.flat_grad.data_ptr(),
+            (_lib.stages_flag(*stages) if stages is not None else 0) | (_lib.CAL_F_RAW_LOGITS_O if raw_o else 0),
             self.ws.data_ptr(), self.ws_bytes, self._stream()),
             "cal_causal_backward")
 
@@ -477,14 +481,15 @@ class _CausalFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, eng, st, *params):
-        out = eng.forward(st, train=True)
-        ctx.eng, ctx.st = eng, st
+        raw_o = bool(getattr(st, "raw_o", False))           # objects head returns raw logits (CausalGIN "irm")
+        out = eng.forward(st, train=True, raw_o=raw_o)
+        ctx.eng, ctx.st, ctx.raw_o = eng, st, raw_o
         return out.clone()
 
     @staticmethod
     def backward(ctx, gout):
         eng = ctx.eng
-        eng.backward(ctx.st, gout)
+        eng.backward(ctx.st, gout, raw_o=ctx.raw_o)
         g = eng.flat_grad.clone()
         outs = []
         for n, p in zip(eng.param_names, eng.params):
@@ -565,9 +570,9 @@ class _CausalBase(nn.Module):
     def _gat_keep(self, st_N, st_E):
         return None
 
-    def forward(self, data, eval_random=True, perm=None):
+    def forward(self, data, eval_random=True, perm=None, raw_o=False):
         """-> (xc_logis, xo_logis, xco_logis), three [B, C] log-probability tensors
-        (model.py:85-122 / 380-409)."""
+        (model.py:85-122 / 380-409).  ``raw_o``: the objects head's RAW logits in place of xo_logis."""
         eng = self.engine
         x = data.x if getattr(data, "x", None) is not None else data.feat
         B = int(getattr(data, "num_graphs", 0) or 0) or int(data.y.numel())
@@ -575,11 +580,12 @@ class _CausalBase(nn.Module):
             perm = self._perm(B, eval_random)
         keep = self._gat_keep(int(x.size(0)), int(data.edge_index.size(1))) if self.training else None
         st = eng.stage(data, perm=perm, gat_keep=keep)
+        st.raw_o = bool(raw_o)
         eng.prep(st)
         if self.training and torch.is_grad_enabled():
             out = _CausalFn.apply(eng, st, *eng.params)
         else:
-            out = eng.forward(st, train=self.training).clone()
+            out = eng.forward(st, train=self.training, raw_o=bool(raw_o)).clone()
         return out[0], out[1], out[2]
 
 
@@ -645,9 +651,13 @@ class CausalGIN(_CausalBase):
         return bool(eval_random)
 
     def forward(self, data, eval_random=True, train_type="base", perm=None):
-        if train_type != "base":
-            raise NotImplementedError("cal_b200.CausalGIN: train_type='irm' (raw logits, model.py:288-289) is not built")
-        return super().forward(data, eval_random=eval_random, perm=perm)
+        """model.py:234-270.  ``train_type="irm"``: the objects head also returns its raw logits -- the tuple
+        ``(xc_logis, (xo, xo_logis), xco_logis)`` of model.py:281-292.  The kernels hand back the raw logits of that head;
+        its log_softmax (and, in the backward pass, the sum of both gradients) is a [B, C] torch op."""
+        if train_type != "irm":
+            return super().forward(data, eval_random=eval_random, perm=perm)
+        xc_logis, xo, xco_logis = super().forward(data, eval_random=eval_random, perm=perm, raw_o=True)
+        return xc_logis, (xo, torch.log_softmax(xo, dim=-1)), xco_logis
 
 
 class CausalGAT(_CausalBase):

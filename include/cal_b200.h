@@ -199,6 +199,10 @@ enum cal_ws_region {
 /* flags for cal_causal_forward */
 #define CAL_F_TRAIN 1        /* BatchNorm batch statistics + running-stat update; GAT dropout */
 #define CAL_F_LOSS 2         /* also evaluate train_causal.py:178-186 (needs batch.y) */
+#define CAL_F_RAW_LOGITS_O 16 /* cal_causal_forward: the objects head returns its RAW logits (before log_softmax) in place of the
+                                log-probabilities -- CausalGIN's train_type="irm", model.py:288-289; cal_causal_backward: grad_logp of
+                                that head is the gradient with respect to those raw logits (grad_logp must be given).  FFMA readout
+                                kernels only (CAL_EUNSUPPORTED otherwise) */
 #define CAL_F_NO_OVERLAP 8   /* cal_causal_forward: the kernel that precedes this call in the stream is not cal_prep's (e.g. the optimizer's:
                                 cal_prep ran ahead, elsewhere) -- the first kernel must not overlap its tail */
 #define CAL_F_FSG_READY 4    /* cal_causal_forward, training: structure and operand images are complete (see cal_image_sink) */

@@ -265,7 +265,7 @@ class _CausalBase(nn.Module):
                 nn.init.constant_(m.bias, 0.0001)
 
     # model.py:85-122 / 380-409
-    def forward(self, data, eval_random=True, perm=None):
+    def forward(self, data, eval_random=True, perm=None, train_type="base"):
         x = data.x if getattr(data, "x", None) is not None else data.feat
         edge_index, batch = data.edge_index, data.batch
         row, col = edge_index
@@ -288,7 +288,7 @@ class _CausalBase(nn.Module):
         xc = global_add_pool(xc, batch, num_graphs)
         xo = global_add_pool(xo, batch, num_graphs)
         xc_logis = self._readout(xc, "c")
-        xo_logis = self._readout(xo, "o")
+        xo_logis = self._readout(xo, "o", raw=train_type == "irm")     # CausalGIN, model.py:288-290: (x, x_logis)
         xco_logis = self.random_readout_layer(xc, xo, eval_random, perm)
         return xc_logis, xo_logis, xco_logis
 
@@ -300,12 +300,12 @@ class _CausalBase(nn.Module):
             x = _relu(conv(x, edge_index), "x%d" % (i + 2))
         return x
 
-    def _readout(self, x, tag):                   # model.py:125-143
+    def _readout(self, x, tag, raw=False):        # model.py:125-143; raw: CausalGIN's train_type "irm", model.py:281-292
         x = getattr(self, "fc1_bn_" + tag)(x)
         x = _relu(getattr(self, "fc1_" + tag)(x), "h1_" + tag)
         x = getattr(self, "fc2_bn_" + tag)(x)
         x = getattr(self, "fc2_" + tag)(x)
-        return F.log_softmax(x, dim=-1)
+        return (x, F.log_softmax(x, dim=-1)) if raw else F.log_softmax(x, dim=-1)
 
     def _shuffles(self, eval_random):
         raise NotImplementedError

@@ -651,6 +651,47 @@ def test_step_many_is_bit_identical_to_single_steps(hidden):
     assert torch.equal(flat[0], flat[1])
 
 
+def test_causal_gin_irm_returns_raw_logits_and_backpropagates_through_them():
+    """CausalGIN ``train_type="irm"`` (model.py:281-292): the objects head returns ``(x, log_softmax(x))``.  Outputs and the
+    gradients of a loss that uses BOTH (the usual causal loss on the log-probabilities + a penalty on the raw logits)
+    against the oracle; the default ``train_type`` is untouched by the flag."""
+    M, O = _mods()
+    ora, b, perm = random_case(seed=131, kind="CausalGIN", hidden=64, batch_size=16)
+    C_ = ora.num_classes
+    net = clone_to_cuda(ora, M)
+    bd = b.to(DEV)
+    xc, (xo, xo_l), xco = net(bd, eval_random=True, train_type="irm", perm=perm.tolist())
+    loss = O.causal_loss(xc, xo_l, xco, bd.y, C_)[0] + 0.05 * (xo ** 2).mean()
+    loss.backward()
+    torch.cuda.synchronize()
+    eng = net.engine
+    assert eng.status() == 0
+    masks = _gpu_relu_masks(eng, b.batch.numel(), b.y.numel())
+
+    def oracle(dtype):
+        n2 = copy.deepcopy(ora).to(dtype)
+        bb = copy.copy(b)
+        bb.feat = b.feat.to(dtype)
+        O.RELU_OVERRIDE = masks
+        try:
+            oc, (oo, ool), oco = n2(bb, eval_random=True, perm=perm, train_type="irm")
+            l = O.causal_loss(oc, ool, oco, bb.y, C_)[0] + 0.05 * (oo ** 2).mean()
+            l.backward()
+        finally:
+            O.RELU_OVERRIDE = None
+        return [t.detach() for t in (oc, oo, ool, oco)], float(l), {n: grad_or_zero(p).detach() for n, p in n2.named_parameters()}
+
+    o32, l32, g32 = oracle(torch.float32)
+    o64, _, g64 = oracle(torch.float64)
+    _check_outputs([xc, xo, xo_l, xco], o32, o64)
+    assert abs(float(loss) - l32) < 3 * TOL * max(1.0, abs(l32))
+    _check_grads({n: grad_or_zero(p) for n, p in net.named_parameters()}, g32, g64)
+    # the default forward of the same module still returns log-probabilities for the objects head
+    net.zero_grad()
+    base = net(bd, eval_random=True, perm=perm.tolist())
+    assert rel_err(base[1].detach().cpu(), o32[2]) < TOL
+
+
 def test_fused_path_reports_a_graph_beyond_its_limits_and_recovers():
     """cal_caps.small_graphs is a promise of the caller (<= 40 nodes, <= 320 CSR entries per graph).  A batch that breaks
     it must not hang the in-kernel all-reduces: the block of an unfit graph only keeps them complete, the status word
