@@ -537,6 +537,10 @@ def run_gpu(a, rank, local_rank, world):
             if tj.get("workload") == a.workload and a.model == "CausalGCN" and top["stage"] in tj["kernels"]:
                 k = tj["kernels"][top["stage"]]
                 traffic = int(k["dram_read"]) + int(k["dram_write"])
+            else:                                        # the other workloads: "others": {"<workload>/<model>": {family: ...}}
+                k = tj.get("others", {}).get("%s/%s" % (a.workload, a.model), {}).get(top["stage"])
+                if k is not None:
+                    traffic = int(k["dram_read"]) + int(k["dram_write"])
         except Exception:
             traffic = None
         roofline = {"bound": "hbm", "kernel": top["stage"], "achieved": top["gbs"], "peak": peak, "unit": "GB/s",

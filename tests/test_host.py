@@ -65,6 +65,28 @@ def test_packed_layout_round_trip():
     assert cal_b200.batch_caps([b])[0] >= N
 
 
+def test_batch_caps_declares_what_the_batches_guarantee():
+    """batch_caps: capacities + the two promises the kernels may rely on -- small graphs (<= 40 nodes, <= 320 CSR
+    entries: the fused path) and edge_index columns grouped by graph (what the collate produces: per-graph structure
+    preparation); a batch that breaks a promise withdraws it."""
+    import copy
+    small = make_batches("spmotif", num_batches=2, seed=6, batch_size=12, avg_nodes=20)
+    n, e, g, is_small, grouped = cal_b200.batch_caps(small)
+    assert n >= max(b.batch.numel() for b in small) and n % 32 == 0
+    assert e >= max(b.edge_index.size(1) for b in small) and g >= 12 and g % 8 == 0
+    assert is_small and grouped
+    big = make_batches("spmotif", num_batches=1, seed=7, batch_size=6, avg_nodes=90)[0]
+    assert cal_b200.batch_caps([small[0], big])[3:] == (False, True)          # a 90-node graph: not "small", still grouped
+    shuffled = copy.copy(small[0])
+    shuffled.edge_index = small[0].edge_index[:, torch.randperm(small[0].edge_index.size(1), generator=torch.Generator().manual_seed(1))]
+    assert cal_b200.batch_caps([shuffled])[3:] == (True, False)               # same graphs, columns out of graph order
+    crossing = copy.copy(small[0])
+    ei = small[0].edge_index.clone()
+    ei[1, 0] = small[0].batch.numel() - 1                                      # an edge from graph 0 into the last graph
+    crossing.edge_index = ei
+    assert cal_b200.batch_caps([crossing])[4] is False
+
+
 def test_dataloader_rank_sharding_is_a_partition():
     ds = make_dataset(50, seed=1)
     for g in ds:
