@@ -577,7 +577,8 @@ def run_gpu(a, rank, local_rank, world):
                     tr2.step_epoch()
                 done += k
             return tr2.end_epoch()
-        run_epochs(max(3, a.warmup))
+        run_epochs(max(3, a.warmup, per_epoch + 2))     # a whole epoch and the start of the next: every graph of the
+        #                                                  epoch path (first / steady per buffer / last step) is captured untimed
         barrier()
         e0.record()
         m_ep = run_epochs(a.steps)
@@ -605,7 +606,7 @@ def run_gpu(a, rank, local_rank, world):
             "h2d_bytes_per_step": int((4 * per_epoch * bs + (4 * per_epoch * bs if tr2.with_random else 0)) / per_epoch),
             "d2h_bytes_per_epoch": 32, "graphs_in_store": len(ds), "steps_per_epoch": per_epoch,
             "api": "Trainer.begin_epoch(store, order) + step_epoch(): cal_collate on the GPU + the step in one captured "
-                   "graph; per epoch the shuffled order and the random-intervention permutations are uploaded, epoch "
+                   "graph (the next batch is collated and prepared on forked branches of the current step); per epoch the shuffled order and the random-intervention permutations are uploaded, epoch "
                    "metrics are accumulated on the device and read once (end_epoch)",
             "last_epoch_metrics": m_ep}
 

@@ -23,7 +23,7 @@ struct ColArgs {
   cal_graph_store st;
   const int* order;       // i32[n_order] graph ids of the epoch, device
   int n_order;
-  int* pos;               // device i32[4]: [0] offset of this step's first id, [1] arrival counter, [2] metrics pending
+  int* pos;               // device i32[4]: [0] offset of this step's first id, [1] arrival counter, [2] metrics pending, [3] graphs of the last collated batch
   int B;                  // graphs per step
   const int* perm_pool;   // i32[steps][B] random_idx per step (model.py:147-152), or NULL
   int Nm, Em, Bm;
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kColT) k_collate(const ColArgs a) {
   if (blockIdx.x == 0 && t == 0) {
     // metrics of the PREVIOUS step (its kernels precede this one in stream order) -> epoch sums
     if (a.acc != nullptr && a.prev_loss != nullptr && a.pos != nullptr && a.pos[2] != 0) {
-      const float pb = (float)a.out_dims[2];
+      const float pb = (float)a.pos[3];                                 // graphs of the batch collated before this one
       for (int k = 0; k < 4; ++k) a.acc[k] += a.prev_loss[k] * pb;      // batchmean losses -> sums over graphs
       for (int k = 4; k < 7; ++k) a.acc[k] += a.prev_loss[k];           // correct counts
       a.acc[7] += pb;
@@ -149,6 +149,8 @@ __global__ void __launch_bounds__(kColT) k_collate(const ColArgs a) {
       if (atomicAdd(reinterpret_cast<unsigned int*>(a.pos + 1), 1u) == gridDim.x - 1u) {
         a.pos[1] = 0;
         a.pos[2] = Bn > 0 ? 1 : 0;
+        a.pos[3] = Bn;                                     // (the next collate / the flush weigh this step's losses with it:
+        //                                                    with two staging buffers out_dims of THIS call's buffer is older)
         if (a.advance) a.pos[0] = base + Bn;
       }
     }
@@ -157,8 +159,9 @@ __global__ void __launch_bounds__(kColT) k_collate(const ColArgs a) {
 
 __global__ void k_collate_flush(const float* prev_loss, const int* dims, int* pos, float* acc) {
   pdl_sync();
+  (void)dims;
   if (threadIdx.x == 0 && blockIdx.x == 0 && pos[2] != 0) {
-    const float pb = (float)dims[2];
+    const float pb = (float)pos[3];
     for (int k = 0; k < 4; ++k) acc[k] += prev_loss[k] * pb;
     for (int k = 4; k < 7; ++k) acc[k] += prev_loss[k];
     acc[7] += pb;

@@ -405,7 +405,8 @@ class Trainer:
         sk = self.eng.image_sink()
         return sk if sk.count > 0 else None
 
-    def _issue(self, base_ptr, gat_keep=None, part="all", next_ptr=None, prepped=False, ready=False, loss_out=None):
+    def _issue(self, base_ptr, gat_keep=None, part="all", next_ptr=None, prepped=False, ready=False, loss_out=None,
+               side_first=None):
         """Enqueue the step on the current stream.  part: "all", or "compute" (prep + forward + loss +
         backward) / "update" (gradient all-reduce + Adam) for the two-graph data-parallel replay.
         ``prepped``: cal_prep of this batch already ran (at the end of the previous step);  ``next_ptr``: run
@@ -414,7 +415,10 @@ class Trainer:
         ``ready``: prepped AND the operand images of the fused small-graph path are current (the optimizer steps issued
         here write them, cal_image_sink) -- the forward pass then starts with the fused kernel itself;
         ``loss_out``: pinned f32[8] host tensor -- the loss parts / correct counts are copied into it on a branch forked
-        right behind the forward pass (the copy engine works beside the backward pass)."""
+        right behind the forward pass (the copy engine works beside the backward pass);
+        ``side_first``: callable issued on a branch forked right behind the forward pass; cal_prep(next) waits for it
+        (the device-resident epoch collates the next batch there: it touches only the other staging buffer and the
+        loss parts the forward pass has just written, so it runs beside the readout backward kernel)."""
         eng, lib = self.eng, self.eng.lib
         sink = self._sink()
         side2 = None
@@ -439,6 +443,13 @@ class Trainer:
                 side2.wait_stream(main)
                 with torch.cuda.stream(side2):
                     loss_out.copy_(eng.loss_parts_full(), non_blocking=True)
+            if side_first is not None and next_ptr is not None and part == "all":
+                # (the same branch that later prepares the batch: one chain  collate(next) -> [backward done] -> prep(next))
+                main = torch.cuda.current_stream(self.device)
+                early = self._side_stream()
+                early.wait_stream(main)
+                with torch.cuda.stream(early):
+                    side_first()
             fork = next_ptr is not None and part == "all"
             last = eng.L + 6                                   # backward stage "grad_reduce"
 
@@ -841,11 +852,12 @@ class Trainer:
             ep["with_perm"] = True
         ep["pos"].zero_()
         ep["acc"].zero_()
+        ep["next_collated"], ep["slot"] = False, 0         # (look-ahead state of _step_epoch_ahead)
         return n_steps
 
-    def _issue_collate(self, ep):
+    def _issue_collate(self, ep, staging=None):
         eng = self.eng
-        cb = self.layout.cbatch(self.staging.data_ptr())
+        cb = self.layout.cbatch((staging if staging is not None else self.staging).data_ptr())
         _lib.check(eng.lib.cal_collate(C.byref(ep["store"].desc), ep["order"].data_ptr(), ep["n"], ep["pos"].data_ptr(),
                                        ep["B"], ep["perm"].data_ptr() if ep["with_perm"] else 0, C.byref(eng.caps),
                                        C.byref(cb), 1, eng.loss_parts_full().data_ptr(), ep["acc"].data_ptr(),
@@ -855,7 +867,6 @@ class Trainer:
         """One training step on the next ``graphs_per_step`` graphs of the epoch (asynchronous)."""
         self._check_alive()
         self.pipe_flush()
-        self._prepped_ptr = None
         ep = self._epoch
         if ep["done"] >= ep["steps"]:
             raise _lib.CalError("cal_b200: the epoch is exhausted (call begin_epoch)")
@@ -863,6 +874,9 @@ class Trainer:
         keep = self._gat_keep_for(None)
         if keep is not None:
             self._refresh_keep()
+        if self.world == 1 or self.peer is not None:
+            return self._step_epoch_ahead(ep, keep)
+        self._prepped_ptr = None
         if not self.use_graph:
             self._issue_collate(ep)
             self._issue(self.staging.data_ptr(), keep)
@@ -896,6 +910,55 @@ class Trainer:
         if gb is not None:
             self._issue(self.staging.data_ptr(), keep, part="allreduce")
             gb.replay()
+
+    def _step_epoch_ahead(self, ep, keep):
+        """The epoch step with the look-ahead of ``step(cur, next)``: two staging buffers alternate; the NEXT batch is
+        collated and prepared on the forked branch beside this step's gradient reduction and update, so the step of a
+        batch that was prepared ahead starts with the forward pass.  (``cal_collate`` weighs the previous step's
+        losses with the graph count it left in the cursor block, not with the dims of the buffer it is about to
+        overwrite, so alternating buffers keep the epoch sums exact.)  A handful of captured graphs serve an epoch:
+        first / steady (one per buffer) / last."""
+        if not hasattr(self, "_staging2"):
+            self._staging2 = torch.zeros_like(self.staging)
+        stages = (self.staging, self._staging2)
+        slot = ep.get("slot", 0)
+        cur = stages[slot]
+        has_next = ep["done"] < ep["steps"]                 # (ep["done"] already counts this step)
+        need_collate = not ep.get("next_collated", False)
+        prepped = (not need_collate) and getattr(self, "_prepped_ptr", None) == cur.data_ptr()
+        nxt = stages[1 - slot] if has_next else None
+        sink = self._sink()
+        ready = prepped and sink is not None and self.eng.images_fresh()
+        ep["next_collated"] = has_next
+        ep["slot"] = 1 - slot if has_next else slot
+        self._prepped_ptr = nxt.data_ptr() if nxt is not None else None
+
+        def issue():
+            if need_collate:
+                self._issue_collate(ep, cur)
+            self._issue(cur.data_ptr(), keep, next_ptr=nxt.data_ptr() if nxt is not None else None, prepped=prepped,
+                        ready=ready, side_first=(lambda: self._issue_collate(ep, nxt)) if nxt is not None else None)
+
+        if not self.use_graph:
+            issue()
+            return
+        key = (ep["n"], ep["with_perm"], slot, need_collate, prepped, ready, has_next)
+        graphs = ep.setdefault("graphs", {})
+        g = graphs.get(key)
+        if g is None:
+            if not self._warm:
+                pos = ep["pos"].clone()
+                self._issue_collate(ep, cur)
+                self._warmup(cur, keep)
+                ep["pos"].copy_(pos)
+                ep["acc"].zero_()
+                self._prepped_ptr = nxt.data_ptr() if nxt is not None else None
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self._capture_stream()):
+                issue()
+            graphs[key] = g
+        g.replay()
+        self.eng.images_version = self.eng.param_version() if sink is not None else None
 
     def end_epoch(self):
         """Epoch metrics like train_causal.py:186-196 (synchronises): dict of mean losses and accuracies."""

@@ -321,7 +321,9 @@ typedef struct {
  * every step of the epoch, drawn on the host like the reference does.  `acc` f32[8] (or NULL, then
  * `prev_loss` is NULL too): epoch sums -- before the new batch is written, the previous step's
  * CAL_WS_LOSS (`prev_loss`) is added as sum over graphs of loss / c / o / co, the three correct
- * counts and the number of graphs (train_causal.py:186-191); cal_collate_flush adds the last step. */
+ * counts and the number of graphs (train_causal.py:186-191); cal_collate_flush adds the last step.
+ * pos[3] carries the graph count of the batch collated last (the weight of `prev_loss`), so consecutive calls may
+ * write to different `out` buffers -- the next batch can be collated while the current one is still in use. */
 int cal_collate(const cal_graph_store* store, const int32_t* order, int32_t n_order, int32_t* pos,
                 int32_t graphs_per_step, const int32_t* perm_pool, const cal_caps* caps,
                 const cal_batch* out, int advance, const float* prev_loss, float* acc, void* stream);

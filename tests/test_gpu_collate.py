@@ -139,7 +139,7 @@ def test_epoch_on_device_equals_host_collated_steps():
     assert m["graphs"] == len(order) == int(tot[7])
     assert abs(m["loss"] - tot[0] / tot[7]) < 1e-5 * max(1.0, abs(tot[0] / tot[7]))
     assert abs(m["acc_o"] - tot[5] / tot[7]) < 1e-6 and abs(m["acc_co"] - tot[6] / tot[7]) < 1e-6
-    assert tr_d._epoch["graph"] is not None                   # one captured graph served both epochs
+    assert 1 <= len(tr_d._epoch["graphs"]) <= 6               # a handful of captured graphs served both epochs (first / steady per buffer / last)
 
 
 def test_trainer_freezes_capacities_eval_cannot_reallocate():

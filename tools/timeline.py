@@ -50,3 +50,33 @@ for rep in range(3):
             print("   after re-arm          :", q(x[:, 3]))
             tail = x[:, 2] - x[:, 1]
             print("   tail (last all-reduce -> end):", q(tail))
+
+# ---- the device-resident epoch path (cal_collate + look-ahead): the same stamps over step_epoch() ----
+if len(sys.argv) > 2 and sys.argv[2] == "epoch":
+    from cal_b200.data import make_dataset
+    ds = make_dataset(2048, seed=666, bias=0.9)
+    store = cal_b200.GraphStore(ds, torch.device("cuda:0"))
+    torch.manual_seed(666)
+    net2 = cal_b200.CausalGCN(10, 4, model_args()).cuda().train()
+    tr2 = cal_b200.Trainer(net2, store.caps(128), use_graph=True)
+    import numpy as np
+    rng = np.random.RandomState(1)
+    for rep in range(3):
+        order = rng.permutation(len(ds))[:16 * 128]
+        tr2.begin_epoch(store, order, 128)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(4):
+            tr2.step_epoch()
+        e0.record()
+        for i in range(11):
+            tr2.step_epoch()
+        e1.record()
+        torch.cuda.synchronize()
+        st = tr2.eng.region("STATUS", torch.int32).cpu().tolist()[96:109]
+        print("epoch path  step %.2f us  (fused path: %s)" % (e0.elapsed_time(e1) * 1e3 / 11, tr2.fused_small_graphs))
+        t0 = st[11]
+        for k in sorted(range(13), key=lambda k: st[k]):
+            if k != 1:
+                print("   %8.2f us  %s" % ((st[k] - t0) / 1e3, names[k]))
+        tr2.step_epoch()
+        tr2.end_epoch()
