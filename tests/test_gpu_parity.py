@@ -117,7 +117,7 @@ def _step_and_compare(net, ora, b, perm, M, O, check_running=True, illcond=False
 
 
 # Per-tensor error scale.  A gradient tensor is judged relative to ITS OWN largest entry (of the exact,
-# fp64 value), with three named exceptions -- measured in profiles/grad_errors_r02.txt:
+# fp64 value), with three named exceptions -- measured in profiles/r02_a_grad_errors_before_rule_fix.txt:
 #  * GRAD_FLOOR: a tensor whose largest entry is below 1e-3 of the model's largest gradient entry is judged
 #    against that absolute level (fp32 cancellation level of sums of O(gmax) terms);
 #  * ATT_BIAS_FLOOR: the two-element attention biases (node_att_mlp.bias, edge_att_mlp.bias) are the sum
@@ -314,7 +314,7 @@ def test_module_matches_reference_golden(name):
 
 def _illcond(case):
     """The named ill-conditioned cases: readout BatchNorm statistics over <= 10 graph rows (the fp32
-    reference's own gradients are then up to ~2e-5 from the exact value: profiles/grad_errors_r02.txt,
+    reference's own gradients are then up to ~2e-5 from the exact value: profiles/r02_a_grad_errors_before_rule_fix.txt,
     seeds 5, 6, 11, 204, 205)."""
     return case["batch_size"] <= 10
 
