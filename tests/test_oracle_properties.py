@@ -84,6 +84,42 @@ def test_gcn_norm_self_loops_are_replaced_not_kept():
     assert torch.allclose(norm, want, atol=1e-15)
 
 
+def test_gcn_norm_isolated_node_parallel_edges_and_one_way_edges_by_hand():
+    """Node 2 is isolated (degree 1 from its appended loop: it keeps exactly its own transformed row); the column
+    0 -> 1 appears twice (both count in node 0's ROW degree); 1 -> 0 is absent (a one-way edge: node 1's degree is
+    its loop only, yet it RECEIVES from node 0 -- degree by source, aggregation at target, gcn_conv.py:66,92-97)."""
+    ei = torch.tensor([[0, 0], [1, 1]])
+    _, norm = O.gcn_norm(ei, 3, None, False, torch.float64)
+    d0, d1, d2 = 3.0, 1.0, 1.0
+    want = torch.tensor([1 / math.sqrt(d0 * d1)] * 2 + [1 / d0, 1 / d1, 1 / d2], dtype=torch.float64)
+    assert torch.allclose(norm, want, atol=1e-15)
+    conv = O.GCNConv(2, 2).double()
+    with torch.no_grad():
+        conv.weight.copy_(torch.eye(2))
+    x = torch.tensor([[1.0, 2.0], [10.0, 20.0], [100.0, 200.0]], dtype=torch.float64)
+    out = conv(x, ei)
+    assert torch.allclose(out[2], x[2])                                            # isolated: itself / 1
+    assert torch.allclose(out[0], x[0] / 3.0)                                      # nothing arrives at node 0
+    assert torch.allclose(out[1], x[1] + 2.0 * x[0] / math.sqrt(3.0))              # two parallel messages
+
+
+def test_oracle_ops_pass_torch_gradcheck():
+    """torch.autograd.gradcheck (fp64) of the oracle's GCNConv w.r.t. features, EDGE WEIGHTS and parameters, of the
+    per-target softmax and of GATConv w.r.t. features."""
+    gen = torch.Generator().manual_seed(11)
+    n, e = 5, 9
+    ei = torch.randint(0, n, (2, e), generator=gen)
+    x = torch.randn(n, 3, generator=gen, dtype=torch.float64, requires_grad=True)
+    w = (0.3 + torch.rand(e, generator=gen, dtype=torch.float64)).requires_grad_(True)
+    conv = O.GCNConv(3, 2).double()
+    # (W and b are the module's own tensors: gradcheck perturbs them in place)
+    assert torch.autograd.gradcheck(lambda xx, ww, W, b: conv(xx, ei, ww), (x, w, conv.weight, conv.bias))
+    sc = torch.randn(e, 2, generator=gen, dtype=torch.float64, requires_grad=True)
+    assert torch.autograd.gradcheck(lambda s_: O.segment_softmax(s_, ei[1], n), (sc,))
+    gat = O.GATConv(3, 2, heads=2, dropout=0.0).double()
+    assert torch.autograd.gradcheck(lambda xx: gat(xx, ei), (x,))
+
+
 @settings(**SET)
 @given(graphs(), st.booleans())
 def test_gcnconv_equals_dense_normalised_adjacency(g, weighted):
