@@ -124,6 +124,30 @@ def test_flat_offsets_cover_reference_state_dict_order():
     assert list(ours.state_dict().keys()) == list(net.state_dict().keys())
 
 
+def test_module_signatures_extend_the_reference_signatures():
+    """SURVEY.md 8(b) "Python signature to keep": constructor and forward of the three modules take the
+    reference's parameters, in the reference's order, with the reference's defaults (model.py:14-22,85,168,234,
+    316-320,380; frozen by tests/golden/make_signatures.py); ours may only APPEND keyword parameters."""
+    import inspect
+    import json
+    here = os.path.dirname(os.path.abspath(__file__))
+    frozen = json.load(open(os.path.join(here, "golden", "signatures.json")))
+    if os.path.isfile("/root/reference/model.py"):                       # the fixture is what the reference says
+        from tests.golden.make_signatures import reference_signatures
+        assert reference_signatures("/root/reference") == frozen
+    assert sorted(frozen) == sorted("%s.%s" % (k, f) for k in ("CausalGCN", "CausalGAT", "CausalGIN")
+                                    for f in ("__init__", "forward"))
+    for key, ref in frozen.items():
+        kind, fn = key.split(".")
+        sig = inspect.signature(getattr(getattr(cal_b200, kind), fn))
+        ours = list(sig.parameters.values())
+        n, nd = len(ref["args"]), len(ref["defaults"])
+        assert [p.name for p in ours[:n]] == ref["args"], key
+        assert [p.default for p in ours[n - nd:n]] == ref["defaults"], key
+        assert all(p.default is inspect.Parameter.empty for p in ours[1:n - nd]), key
+        assert all(p.default is not inspect.Parameter.empty for p in ours[n:]), key   # extras are optional
+
+
 @pytest.mark.parametrize("kind", ["CausalGCN", "CausalGAT", "CausalGIN"])
 def test_seeded_construction_reproduces_reference_init(kind):
     """gcn_conv.py:37-42 / model.py:80-83: the same seed draws the same initial parameters in the same
