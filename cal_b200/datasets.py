@@ -37,7 +37,8 @@ __all__ = ["FlatGraphs", "generate_spmotif", "dataset_bias_split", "read_tu_data
 class FlatGraphs:
     """A set of graphs as flat arrays (CPU or GPU tensors):
     ``node_ptr`` i64[G+1], ``edge_ptr`` i64[G+1], ``edge_index`` i64[2, E] (graph-local node ids, both
-    directions, sorted by (source, target) inside a graph like ``from_networkx`` emits them),
+    directions, sorted by (source, target) inside a graph; ``from_networkx`` emits the same columns grouped by
+    source in node order, the targets of a source in edge-insertion order -- only the summation order differs),
     ``feat`` f32[N, F], ``y`` i64[G], ``context`` i64[G] (0 = tree base, 1 = BA base; -1 unknown)."""
 
     def __init__(self, node_ptr, edge_ptr, edge_index, feat, y, context=None):
@@ -129,13 +130,17 @@ def _ba_edges_batched(n_nodes, m, gen, device):
 
 
 def generate_spmotif(num_per_class, node_num=15, tree_height=2, ba_m=2, noise=0.1, max_degree=10, feature_dim=-1,
-                     contexts=("tree", "ba"), base_nodes=None, seed=666, device="cpu"):
+                     contexts=("tree", "ba"), base_nodes=None, seed=666, device="cpu", random_plugin=True,
+                     gaussian_features=False):
     """All graphs of ``graph_dataset_generate`` (utils.py:59-89) at once: for every motif class and every context
     ``num_per_class`` graphs.  Reference sizes: tree = balanced ``node_num``-ary tree of height ``tree_height``
     (settings_dict, utils.py:62-63), BA = ``node_num ** 2`` nodes with ``m = 2``.  ``base_nodes=(lo, hi)`` instead
     draws every base size uniformly from [lo, hi) (a tree then is the first n nodes of the balanced binary tree):
-    the small-graph workloads of BASELINE.json.  ``feature_dim == -1``: one-hot(min(degree, max_degree - 1))
-    (featgen.py:19-28), else N(0, 1) features.  Returns :class:`FlatGraphs` on ``device``, ordered
+    the small-graph workloads of BASELINE.json.  The motif's first node is joined to ONE base node drawn uniformly
+    (``generate_graph`` passes ``rdm_basis_plugins=True``, gengraph.py:70-75, synthetic_structsim.py:247-249;
+    ``random_plugin=False``: base node 0).  ``feature_dim == -1``: one-hot(min(degree, max_degree - 1))
+    (featgen.py:19-28), else one U(0, 1) vector per graph repeated on every node (utils.py:46-47,
+    ``ConstFeatureGen``; ``gaussian_features=True``: N(0, 1) per node, the cfg 5 recipe of SURVEY.md 8d).  Returns :class:`FlatGraphs` on ``device``, ordered
     (class-major, then context, then index) like the reference's dict of lists."""
     device = torch.device(device)
     gen = torch.Generator(device=device).manual_seed(int(seed))
@@ -171,13 +176,17 @@ def generate_spmotif(num_per_class, node_num=15, tree_height=2, ba_m=2, noise=0.
         gb = gid_all[~is_tree]
         s, d, g_loc = _ba_edges_batched(nb[~is_tree], ba_m, gen, device)
         parts.append((gb[g_loc], s, d))
-    # motif edges, shifted behind the base; the attach edge (motif node 0 -- base node 0: plugins = [0] for one shape,
-    # synthetic_structsim.py:247-264 with rdm_basis_plugins=False)
+    # motif edges, shifted behind the base; the attach edge (motif node 0 -- the plugin, a base node drawn uniformly:
+    # np.random.choice(n_basis, 1), synthetic_structsim.py:247-264 with rdm_basis_plugins=True)
     me = m_edges[label]                                      # [G, 8, 2]
     ok = me[:, :, 0] >= 0
     g_rep = gid_all.unsqueeze(1).expand(-1, 8)[ok]
     parts.append((g_rep, me[:, :, 0][ok] + nb[g_rep], me[:, :, 1][ok] + nb[g_rep]))
-    parts.append((gid_all, torch.zeros(G, dtype=torch.long, device=device), nb.clone()))
+    if random_plugin:
+        plugin = (torch.rand(G, generator=gen, device=device, dtype=torch.float64) * nb).long().clamp(max=nb - 1)
+    else:
+        plugin = torch.zeros(G, dtype=torch.long, device=device)
+    parts.append((gid_all, plugin, nb.clone()))
     g_e = torch.cat([p[0] for p in parts])
     a_e = torch.cat([p[1] for p in parts])
     b_e = torch.cat([p[2] for p in parts])
@@ -225,8 +234,10 @@ def generate_spmotif(num_per_class, node_num=15, tree_height=2, ba_m=2, noise=0.
     if feature_dim == -1:
         deg = torch.bincount(node_ptr[g2] + s2, minlength=N)
         feat = torch.nn.functional.one_hot(deg.clamp(max=max_degree - 1), max_degree).to(torch.float32)
-    else:
+    elif gaussian_features:
         feat = torch.randn(N, int(feature_dim), generator=gen, device=device)
+    else:
+        feat = torch.rand(G, int(feature_dim), generator=gen, device=device).repeat_interleave(n, dim=0)
     return FlatGraphs(node_ptr, edge_ptr, edge_index, feat, label.clone(), ctx.clone())
 
 

@@ -106,3 +106,101 @@ def test_tu_reader_and_feature_expansion(tmp_path):
     assert torch.equal(fg.feat[:, 4:].argmax(1), deg) and torch.equal(fg.feat[:, :3].argmax(1), torch.tensor([0, 1, 2, 0, 0, 1, 2]))
     dl = fg.to_data_list()
     assert dl[1].feat.shape == (4, 105) and dl[1].edge_index.shape == (2, 6)
+
+
+# ---- against the reference's own generator code (synthetic_structsim.py needs only networkx + numpy) ----
+REF_SS = "/root/reference/synthetic_structsim.py"
+
+
+def _ref_structsim():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_synthetic_structsim", REF_SS)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _nx_graph(n, ei, lo=0, hi=None):
+    import networkx as nx
+    hi = n if hi is None else hi
+    G = nx.Graph()
+    G.add_nodes_from(range(lo, hi))
+    G.add_edges_from((a, b) for a, b in ei.t().tolist() if lo <= a < hi and lo <= b < hi)
+    return G
+
+
+@pytest.mark.skipif(not os.path.isfile(REF_SS), reason="needs /root/reference (build container only)")
+def test_generated_graphs_match_the_reference_build_graph():
+    """Every graph against ``synthetic_structsim.build_graph`` run with the arguments of gengraph.py:60-75 /
+    utils.py:62-63: same node and edge counts; the motif (its first node marked: that is where the attach edge
+    ends) is isomorphic to the reference's shape as a ROOTED graph; the tree base is the reference's balanced tree;
+    exactly one edge joins base and motif; the plugin node is spread over the base like np.random.choice."""
+    import networkx as nx
+    ss = _ref_structsim()
+    np.random.seed(0)
+    node_num = 4
+    fg = generate_spmotif(30, node_num=node_num, noise=0.0, seed=5)
+    shapes = {"house": [["house"]], "cycle": [["cycle", 6]], "grid": [["grid"]], "diamond": [["diamond"]]}
+    plug = {0: [], 1: []}
+    for g in range(len(fg)):
+        n, ei, _ = _graph(fg, g)
+        ctx, motif = int(fg.context[g]), MOTIFS[int(fg.y[g])]
+        width, m = (2, node_num) if ctx == 0 else (node_num ** 2, 2)               # settings_dict, utils.py:62-63
+        R, _, ref_plugins = ss.build_graph(width, "tree" if ctx == 0 else "ba", shapes[motif], rdm_basis_plugins=True,
+                                           start=0, m=m)
+        assert n == R.number_of_nodes() and ei.size(1) == 2 * R.number_of_edges(), (g, motif, ctx)
+        nb = n - {"house": 5, "cycle": 6, "grid": 6, "diamond": 6}[motif]
+        ours_m, ref_m = _nx_graph(n, ei, nb, n), R.subgraph(range(nb, n)).copy()
+        for G_, in ((ours_m,), (ref_m,)):
+            nx.set_node_attributes(G_, {v: int(v == nb) for v in G_.nodes}, "root")
+        assert nx.is_isomorphic(ours_m, ref_m, node_match=lambda a, b: a["root"] == b["root"]), (g, motif)
+        ours_b, ref_b = _nx_graph(n, ei, 0, nb), R.subgraph(range(nb)).copy()
+        if ctx == 0:
+            assert sorted(ours_b.edges) == sorted(tuple(sorted(e)) for e in ref_b.edges)   # the same labelled tree
+        else:
+            assert ours_b.number_of_edges() == ref_b.number_of_edges() and nx.is_connected(ours_b)
+        cross = [(a, b) for a, b in ei.t().tolist() if a < nb <= b]
+        assert len(cross) == 1 and cross[0][1] == nb                                       # base node -- motif node 0
+        plug[ctx].append(cross[0][0] / (nb - 1))
+        assert 0 <= int(ref_plugins[0]) < nb
+    for ctx in (0, 1):                                                                     # uniform over the base nodes
+        p = np.array(plug[ctx])
+        assert abs(p.mean() - 0.5) < 0.1 and p.min() < 0.15 and p.max() > 0.85 and len(set(p.tolist())) > 10
+
+
+@pytest.mark.skipif(not os.path.isfile(REF_SS), reason="needs /root/reference (build container only)")
+def test_batched_barabasi_albert_has_the_degree_statistics_of_the_reference_base():
+    """The BA base grown for all graphs at once (one multinomial draw without replacement per new node) against
+    ``synthetic_structsim.ba`` = ``nx.barabasi_albert_graph``: same edge count, and the same degree statistics
+    (second moment, hub degree, leaf fraction) within sampling error over 200 graphs of 100 nodes."""
+    from cal_b200.datasets import _ba_edges_batched
+    ss = _ref_structsim()
+    n, m, G = 100, 2, 200
+    s, d, gid = _ba_edges_batched(torch.full((G,), n), m, torch.Generator().manual_seed(3), torch.device("cpu"))
+    deg = torch.zeros(G, n)
+    deg.index_put_((gid, s), torch.ones(s.numel()), accumulate=True)
+    deg.index_put_((gid, d), torch.ones(s.numel()), accumulate=True)
+    assert s.numel() == G * m * (n - m) and bool((s != d).all())
+    key = (gid * n + torch.minimum(s, d)) * n + torch.maximum(s, d)
+    assert torch.unique(key).numel() == key.numel()                                        # simple graphs
+    import random
+    random.seed(1)
+    np.random.seed(1)
+    ref = np.array([[dg for _, dg in ss.ba(0, n, m=m)[0].degree()] for _ in range(G)], dtype=np.float64)
+    assert ref.sum() == float(deg.sum())
+    ours = deg.numpy().astype(np.float64)
+    for stat in (lambda a: (a ** 2).mean(1), lambda a: a.max(1), lambda a: (a == m).mean(1)):
+        a, b = stat(ours), stat(ref)
+        se = np.sqrt(a.var() / G + b.var() / G)
+        assert abs(a.mean() - b.mean()) < 4 * se + 1e-9, (a.mean(), b.mean(), se)
+
+
+def test_constant_and_gaussian_feature_modes():
+    """utils.py:46-47: with feature_dim > 0 every node of a graph carries the same U(0, 1) vector."""
+    fg = generate_spmotif(3, base_nodes=(6, 9), ba_m=1, noise=0.0, feature_dim=7, seed=2)
+    for g in range(len(fg)):
+        _, _, feat = _graph(fg, g)
+        assert feat.shape[1] == 7 and bool((feat == feat[0]).all()) and 0.0 <= float(feat.min()) and float(feat.max()) < 1.0
+    assert not torch.equal(_graph(fg, 0)[2][0], _graph(fg, 1)[2][0])
+    fgn = generate_spmotif(3, base_nodes=(6, 9), ba_m=1, noise=0.0, feature_dim=7, seed=2, gaussian_features=True)
+    assert float(fgn.feat.std()) > 0.8 and not bool((_graph(fgn, 0)[2] == _graph(fgn, 0)[2][0]).all())
