@@ -21,3 +21,10 @@ def softmax(src, index, num_nodes=None):
     out = src - scatter_max(src, index, dim=0, dim_size=num_nodes)[0][index]
     out = out.exp()
     return out / (scatter_add(out, index, dim=0, dim_size=num_nodes)[index] + 1e-16)
+
+
+def degree(index, num_nodes=None, dtype=None):
+    """torch_geometric.utils.degree (call site feature_expansion.py:102): occurrences of every node id, float."""
+    num_nodes = int(index.max()) + 1 if num_nodes is None else num_nodes
+    out = torch.zeros((num_nodes,), dtype=dtype if dtype is not None else torch.float, device=index.device)
+    return out.scatter_add_(0, index, out.new_ones((index.size(0),)))

@@ -204,3 +204,94 @@ def test_constant_and_gaussian_feature_modes():
     assert not torch.equal(_graph(fg, 0)[2][0], _graph(fg, 1)[2][0])
     fgn = generate_spmotif(3, base_nodes=(6, 9), ba_m=1, noise=0.0, feature_dim=7, seed=2, gaussian_features=True)
     assert float(fgn.feat.std()) > 0.8 and not bool((_graph(fgn, 0)[2] == _graph(fgn, 0)[2][0]).all())
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/utils.py"), reason="needs /root/reference (build container only)")
+def test_bias_split_selects_the_graphs_the_reference_function_selects(capsys):
+    """The UNMODIFIED body of ``dataset_bias_split`` (utils.py:121-159; extracted with ast -- the module itself
+    imports matplotlib / PyG) on the same graphs in the reference's dict-of-lists layout: identical train / val /
+    test membership and identical ``the``."""
+    import argparse
+    import ast
+    import random
+    src = open("/root/reference/utils.py").read()
+    lines = src.splitlines()
+    code = "\n\n".join("\n".join(lines[n.lineno - 1:n.end_lineno]) for n in ast.parse(src).body
+                       if isinstance(n, ast.FunctionDef) and n.name in ("dataset_bias_split", "print_graph_info"))
+    ns = {"random": random}
+    exec(compile(code, "reference_utils_excerpt", "exec"), ns)
+
+    class G:
+        def __init__(self, idx, nodes, edges):
+            self.idx, self.num_nodes, self.num_edges = idx, nodes, edges
+
+    fg = generate_spmotif(150, base_nodes=(8, 12), ba_m=1, noise=0.1, seed=4)
+    nodes, edges = fg.node_ptr[1:] - fg.node_ptr[:-1], fg.edge_ptr[1:] - fg.edge_ptr[:-1]
+    ds = {"tree": {}, "ba": {}}
+    for k, shape in enumerate(MOTIFS):
+        for c, name in enumerate(("tree", "ba")):
+            idx = torch.nonzero((fg.y == k) & (fg.context == c)).view(-1).tolist()
+            ds[name][shape] = [G(i, int(nodes[i]), int(edges[i])) for i in idx]
+    for bias, total in ((0.9, 400), (0.5, 240), (0.7, 520)):
+        random.seed(0)
+        r_tr, r_va, r_te, r_the = ns["dataset_bias_split"](ds, argparse.Namespace(num_classes=4), bias=bias,
+                                                           split=[7, 1, 2], total=total)
+        tr, va, te, the = dataset_bias_split(fg, bias=bias, split=(7, 1, 2), total=total)
+        assert sorted(g.idx for g in r_tr) == sorted(tr.tolist())
+        assert sorted(g.idx for g in r_va) == sorted(va.tolist())
+        assert sorted(g.idx for g in r_te) == sorted(te.tolist())
+        assert the == pytest.approx(r_the)
+    capsys.readouterr()                                          # (the reference prints a table per class)
+
+
+_FE_CHECK = r"""
+import os, sys
+root, ref = sys.argv[1], sys.argv[2]
+sys.path[:0] = [os.path.join(root, "oracle", "pyg_shim"), ref, root]
+import torch
+import feature_expansion                                          # the reference's file, unmodified
+from cal_b200.datasets import FlatGraphs, expand_features
+
+class D:                                                          # what FeatureExpander.transform touches of a PyG Data
+    def __init__(self, x, edge_index):
+        self.x, self.edge_index = x, edge_index
+    num_nodes = property(lambda s: s.x.size(0))
+    num_edges = property(lambda s: s.edge_index.size(1))
+
+gen = torch.Generator().manual_seed(7)
+G, L = 12, 7
+n = torch.randint(2, 30, (G,), generator=gen)
+node_ptr = torch.zeros(G + 1, dtype=torch.long); node_ptr[1:] = torch.cumsum(n, 0)
+eis, labels = [], torch.randint(0, L, (int(n.sum()),), generator=gen)
+for g in range(G):
+    e = int(torch.randint(1, 120, (1,), generator=gen)) if g != 3 else 300      # graph 3: degrees beyond the cap
+    a = torch.randint(0, int(n[g]), (2, e), generator=gen)
+    a = a[:, a[0] != a[1]]
+    a = torch.unique(torch.cat([a, a.flip(0)], 1), dim=1)                       # symmetric, coalesced (TU / PyG)
+    eis.append(a)
+edge_ptr = torch.zeros(G + 1, dtype=torch.long); edge_ptr[1:] = torch.cumsum(torch.tensor([a.size(1) for a in eis]), 0)
+for maxdeg in (100, 10, 3):                                                      # opts.py:122,133: odeg100 / odeg10
+    fg = FlatGraphs(node_ptr, edge_ptr, torch.cat(eis, 1), torch.zeros(int(n.sum()), 0), torch.zeros(G, dtype=torch.long))
+    fg = expand_features(fg, num_node_labels=L, node_labels=labels, degree=True, onehot_maxdeg=maxdeg)
+    fe = feature_expansion.FeatureExpander(degree=True, onehot_maxdeg=maxdeg, AK=0)
+    for g in range(G):
+        x0 = torch.nn.functional.one_hot(labels[node_ptr[g]:node_ptr[g + 1]], L).float()
+        want = fe.transform(D(x0, eis[g])).x
+        got = fg.feat[node_ptr[g]:node_ptr[g + 1]]
+        assert got.shape == want.shape == (int(n[g]), L + 1 + maxdeg + 1), (got.shape, want.shape)
+        assert torch.equal(got, want), (g, maxdeg)
+print("feature expansion identical")
+"""
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/feature_expansion.py"), reason="needs /root/reference (build container only)")
+def test_feature_expansion_equals_the_reference_feature_expander():
+    """The reference's unmodified ``FeatureExpander(degree=True, onehot_maxdeg=100 | 10, AK=0).transform``
+    (feature_expansion.py:42-59,100-113; the 'deg+odeg100' recipe of opts.py:122 that gives MUTAG its 109 columns)
+    over the stand-in PyG, graph by graph, against ``expand_features`` on the flat arrays: bit-identical."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _FE_CHECK, root, "/root/reference"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "feature expansion identical" in r.stdout
