@@ -10,4 +10,4 @@ __version__ = "0.1.0"
 from .data import Batch, Data, DataLoader, make_batches, make_dataset  # noqa: F401
 from .model import CausalGAT, CausalGCN, CausalGIN, Engine, GATConv, GCNConv, GINConv, flat_offsets  # noqa: F401
 from .trainer import (GraphStore, PackedLayout, PeerExchange, Trainer, allreduce_flat_grads, batch_caps,  # noqa: F401
-                      epoch_order)
+                      cosine_lr, epoch_order)

@@ -74,6 +74,14 @@ def epoch_order(num_graphs, epoch, seed=0, rank=0, world_size=1, graphs_per_step
     return shard.astype(np.int32)
 
 
+def cosine_lr(epoch, base_lr, min_lr=0.0, epochs=100):
+    """Learning rate of ``CosineAnnealingLR(optimizer, T_max=epochs, eta_min=min_lr)`` after ``epoch`` calls of
+    ``lr_scheduler.step()`` (train_causal.py:22,29: one call per epoch, so epoch e of 1..epochs trains with
+    ``cosine_lr(e - 1, ...)``) -- what a loop built on ``Trainer`` hands to ``Trainer.set_lr``."""
+    import math
+    return float(min_lr) + (float(base_lr) - float(min_lr)) * (1.0 + math.cos(math.pi * int(epoch) / int(epochs))) / 2.0
+
+
 def allreduce_flat_grads(flat_grad, group=None):
     """The ONE collective of the data-parallel step: sum the flat gradient
     buffer over the ranks in place and return the scale (1 / world_size) the optimizer applies.

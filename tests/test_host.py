@@ -270,3 +270,15 @@ def test_epoch_order_shards_like_a_distributed_sampler_gloo_world2(tmp_path):
     assert not np.array_equal(r[0][0][0], r[0][1][0])               # reshuffled between epochs
     solo = cal_b200.epoch_order(50, 3, seed=1)
     assert sorted(solo.tolist()) == list(range(50))                 # one rank, no step cut: a plain permutation
+
+
+def test_cosine_lr_is_the_reference_schedule():
+    """train_causal.py:22,29: CosineAnnealingLR(T_max=epochs, eta_min=min_lr), stepped once per epoch."""
+    for lr0, lr_min, T in ((1e-3, 1e-6, 100), (1e-2, 0.0, 7)):
+        w = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.Adam([w], lr=lr0)
+        sch = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=T, eta_min=lr_min, last_epoch=-1)
+        for epoch in range(T + 1):
+            assert cal_b200.cosine_lr(epoch, lr0, lr_min, T) == pytest.approx(opt.param_groups[0]["lr"], rel=1e-9, abs=1e-15)
+            opt.step()
+            sch.step()
