@@ -1,5 +1,7 @@
 """The oracle (oracle/cal_oracle.py) against the golden vectors frozen from the
 unmodified reference model.py / gcn_conv.py (tests/golden/make_golden.py)."""
+import os
+
 import pytest
 import torch
 
@@ -58,3 +60,18 @@ def test_init_matches_reference_rng_order():
         for n, p in net.named_parameters():
             if p.dim() >= 2:
                 assert torch.equal(p.detach(), gc.params[n]), n
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/model.py"), reason="needs /root/reference (build container only)")
+def test_committed_fixtures_replay_through_the_unmodified_reference():
+    """Every committed fixture, fed back through the reference's own model.py (stored parameters, stored batch,
+    stored permutation; tests/golden/replay_golden.py): outputs, loss parts, every parameter gradient and the
+    running statistics are what the file holds.  The fixtures stay pinned to the reference even when the input
+    generators of make_golden.py move on."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "golden", "replay_golden.py")], capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count(" ok") == len(golden_names()) and "MISMATCH" not in r.stdout
