@@ -282,3 +282,21 @@ def test_cosine_lr_is_the_reference_schedule():
             assert cal_b200.cosine_lr(epoch, lr0, lr_min, T) == pytest.approx(opt.param_groups[0]["lr"], rel=1e-9, abs=1e-15)
             opt.step()
             sch.step()
+
+
+def test_bench_algorithmic_bytes_follow_the_survey_formula():
+    """A = 100.75 MB per step at cfg 1 (N = 3 200, E = 6 400, F = 10, H = 128, L = 3, B = 128,
+    P = 138 660) -- the figure `roofline.achieved` is computed from; the per-stage split that credits the
+    kernels must not exceed the step figure by more than its documented extras (parameter re-reads, CSR words)."""
+    import bench
+    N, E, B, H, F, C, L, P = 3200, 6400, 128, 128, 10, 4, 3, 138660
+    A = bench.step_algorithmic_bytes(N, E + N, B, H, F, L, P)
+    assert A == 16 * 6 * N * H + 8 * H * 5 * (E + N) + 8 * H * (E + N) + (4 * N * F + 16 * E + 8 * N + 8 * B) + 12 * P + 32 * B * H
+    assert abs(A / 1e6 - 100.75) < 0.05
+    stages = (["prep", "feat"] + ["layer_%d" % l for l in range(L)] + ["edge_att", "masked_convs", "readout", "readout_bwd",
+              "masked_gemm_bwd", "masked_gather_bwd", "norm_bwd", "att_bwd"] + ["layer_%d_bwd" % l for l in range(L)] +
+              ["feat_bwd", "grad_reduce", "adam"])
+    per = {s: bench.algorithmic_bytes(s, N, E + N, B, H, F, C, L, P) for s in stages}
+    assert all(v > 0 for v in per.values())
+    total = sum(per.values())
+    assert 0.95 * A < total < 1.35 * A, (total, A)
