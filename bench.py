@@ -617,6 +617,13 @@ def run_gpu(a, rank, local_rank, world):
                                              model=a.model)
         cpu = {"value": gps, "unit": UNIT, "cores": thr, "kind": "port",
                "sample": "%d oracle train steps of %d graphs in %.1f s (same workload, %d torch threads)" % (done, bs, el, thr)}
+        if cores > 1:                                    # the CPU arm at one thread as well
+            try:
+                g1, d1, e1_, _ = cpu_train_steps(batches[:16], F, C, 128, 3, None, 1, seconds=min(4.0, a.cpu_seconds),
+                                                 threads=1, model=a.model)
+                cpu["single_thread"] = {"value": g1, "cores": 1, "sample": "%d steps in %.1f s" % (d1, e1_)}
+            finally:
+                torch.set_num_threads(cores)
 
     if rank == 0:
         line = {
