@@ -15,7 +15,8 @@ import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
-from hypothesis import given, settings, strategies as st
+pytest.importorskip("hypothesis")                     # (a missing package must skip this file, not abort a collection)
+from hypothesis import given, settings, strategies as st  # noqa: E402
 
 from oracle import cal_oracle as O
 from tests.util import random_case
